@@ -1,0 +1,430 @@
+// ref_gpu_dvr.cu — O-gpu: the reference's OWN device code for the DVR path, compiled for sm_100a.
+// TEST INFRASTRUCTURE (oracle).  Built by oracle/Makefile into oracle/_ref/libref_gpu_dvr.so from the
+// reference headers where they lie under /root/reference (nothing is copied into this repository).
+//
+// What runs unmodified from the reference (devices/rtx/gpu/*.h): createScreenSample, makePrimaryRay,
+// cameraCreateRay, rayMarchAllVolumes, detail::rayMarchVolume, _rayMarchVolume,
+// SpatialFieldSampler<cudaTextureObject_t>, classifySample, getBackground, accumulateValue,
+// accumResults (tonemap / inverseTonemap / writeOutputColor) — with hardware tex3D / tex1D and
+// cuRAND Philox, exactly as the OptiX raygen programs call them.
+// What is restated here because it lives in OptiX programs or host classes that cannot be built
+// without OptiX / ANARI-SDK:
+//   - the raygen "no surface hit" branch            renderer/Raycast_ptx.cu:60-179, DirectLight_ptx.cu:294-418
+//   - the volume AABB search (RT traversal + IS/CH) scene/Intersectors_ptx.cu:248-274, gpu/populateHit.h:370-390
+//   - host texture set-up                           StructuredRegularField.cpp:98-194, TransferFunction1D.cpp:152-186
+//   - frame reset fills                             frame/Frame.cu:590-660
+#include <cuda_runtime.h>
+#include <cstdio>
+#include <cstring>
+#include <vector>
+
+#include "gpu/gpu_util.h"
+#include "gpu/intersectRay.h"
+#include "gpu/createScreenSample.h"
+#include "gpu/volumeIntegration.h"
+
+#include "dvr_b200.h" // POD parameter structs only (DvrFrameParams, DvrCamera, DvrFrameBuffers)
+
+using namespace visrtx;
+
+struct RefInstanceXfm
+{
+  float m[12]; // world -> object
+  int identity;
+};
+
+__constant__ FrameGPUData frameData; // same launch-parameter symbol name as the reference (Renderer.cpp:733)
+__device__ const RefInstanceXfm *g_xfms;
+
+// Volume-BVH trace replacement: closest clamped AABB entry among the volume instances, skipping the
+// one hit last (Intersectors_ptx.cu:250-252), filling VolumeHit like populateVolumeHit.
+__device__ void refgpu_shim_trace(unsigned long long, float3 org, float3 dir, float tmin, float tmax, unsigned ssHi,
+    unsigned ssLo, unsigned dataHi, unsigned dataLo, unsigned bvhSelection)
+{
+  if (bvhSelection != 0u)
+    return; // surfaces: a volume-only world has none => miss
+  ScreenSample &ss = *(ScreenSample *)detail::unpackPointer(ssHi, ssLo);
+  VolumeHit &hit = *(VolumeHit *)detail::unpackPointer(dataHi, dataLo);
+  const FrameGPUData &fd = *ss.frameData;
+  int best = -1;
+  box1 bt;
+  vec3 bo, bd;
+  for (int i = 0; i < (int)fd.world.numVolumeInstances; ++i) {
+    const uint32_t objID = 0u, instID = (uint32_t)i;
+    if (hit.lastVolID == objID && hit.lastInstID == instID)
+      continue;
+    const auto &inst = fd.world.volumeInstances[i];
+    const VolumeGPUData &vd = fd.registry.volumes[inst.volumes[0]];
+    vec3 lo(org.x, org.y, org.z), ld(dir.x, dir.y, dir.z);
+    const RefInstanceXfm &x = g_xfms[i];
+    if (!x.identity) {
+      const float *m = x.m;
+      const vec3 o = lo, d = ld;
+      lo = vec3(m[0] * o.x + m[1] * o.y + m[2] * o.z + m[3], m[4] * o.x + m[5] * o.y + m[6] * o.z + m[7],
+          m[8] * o.x + m[9] * o.y + m[10] * o.z + m[11]);
+      ld = vec3(m[0] * d.x + m[1] * d.y + m[2] * d.z, m[4] * d.x + m[5] * d.y + m[6] * d.z,
+          m[8] * d.x + m[9] * d.y + m[10] * d.z);
+    }
+    const auto &bounds = vd.bounds;
+    const vec3 mins = (bounds.lower - lo) * (1.f / ld);
+    const vec3 maxs = (bounds.upper - lo) * (1.f / ld);
+    const vec3 nears = glm::min(mins, maxs);
+    const vec3 fars = glm::max(mins, maxs);
+    box1 t(glm::compMax(nears), glm::compMin(fars));
+    if (!(t.lower < t.upper))
+      continue;
+    if (t.upper < tmin || t.lower > tmax)
+      continue; // the traversal never visits an AABB outside the ray interval
+    const box1 rayt{tmin, tmax};
+    t.lower = clamp(t.lower, rayt);
+    t.upper = clamp(t.upper, rayt);
+    if (best < 0 || t.lower < bt.lower) {
+      best = i;
+      bt = t;
+      bo = lo;
+      bd = ld;
+    }
+  }
+  if (best < 0)
+    return;
+  const auto &inst = fd.world.volumeInstances[best];
+  hit.foundHit = true;
+  hit.volume = &fd.registry.volumes[inst.volumes[0]];
+  hit.instance = &inst;
+  hit.lastVolID = 0u;
+  hit.lastInstID = (uint32_t)best;
+  hit.localRay.org = bo;
+  hit.localRay.dir = bd;
+  hit.localRay.t.lower = bt.lower;
+  hit.localRay.t.upper = bt.upper;
+}
+
+// raygen, volume-only world.  centerPixel=true/1 iteration == raycast; otherwise default/directLight.
+__global__ void refgpu_raygen(int centerPixel)
+{
+  auto &rendererParams = frameData.renderer;
+  auto ss = createScreenSample(frameData);
+  if (pixelOutOfFrame(ss.pixel, frameData.fb))
+    return;
+  const int iters = centerPixel ? 1 : frameData.renderer.numIterations;
+  for (int i = 0; i < iters; i++) {
+    auto ray = makePrimaryRay(ss, centerPixel != 0);
+    vec3 outputColor(0.f);
+    vec3 outputNormal = ray.dir;
+    float outputOpacity = 0.f;
+    float depth = 1e30f;
+    uint32_t primID = ~0u, objID = ~0u, instID = ~0u;
+
+    vec3 color(0.f);
+    float opacity = 0.f;
+    uint32_t vObjID = ~0u, vInstID = ~0u;
+    const float volumeDepth = rayMarchAllVolumes(ss, ray, 0 /*RayType::PRIMARY*/, ray.t.upper,
+        rendererParams.inverseVolumeSamplingRate, color, opacity, vObjID, vInstID);
+    depth = min(depth, volumeDepth);
+    primID = 0;
+    objID = vObjID;
+    instID = vInstID;
+    color *= opacity;
+    const auto bg = getBackground(frameData, ss.screen, ray.dir);
+    accumulateValue(color, vec3(bg), opacity);
+    accumulateValue(opacity, bg.w, opacity);
+    accumulateValue(outputColor, color, outputOpacity);
+    accumulateValue(outputOpacity, opacity, outputOpacity);
+
+    accumResults(frameData.fb, ss.pixel, vec4(outputColor, outputOpacity), depth, outputColor, outputNormal, primID,
+        objID, instID, i);
+  }
+}
+
+template <typename T>
+__global__ void refgpu_fill(T *p, size_t n, T v)
+{
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+    p[i] = v;
+}
+template <typename T>
+static void fill(T *p, size_t n, T v, cudaStream_t s)
+{
+  if (p && n)
+    refgpu_fill<T><<<1184, 256, 0, s>>>(p, n, v);
+}
+
+struct RefField
+{
+  cudaArray_t arr = nullptr;
+  cudaTextureObject_t tex = 0;
+  SpatialFieldGPUData gpu{};
+  box3 bounds;
+  float stepSize = 0.f;
+};
+struct RefVolume
+{
+  RefField *field = nullptr;
+  cudaArray_t arr = nullptr;
+  cudaTextureObject_t tex = 0;
+  VolumeGPUData gpu{};
+};
+
+static thread_local char g_err[512];
+#define RCK(x)                                                                                      \
+  do {                                                                                              \
+    cudaError_t e_ = (x);                                                                           \
+    if (e_ != cudaSuccess) {                                                                        \
+      snprintf(g_err, sizeof(g_err), "%s: %s", #x, cudaGetErrorString(e_));                         \
+      return -3;                                                                                    \
+    }                                                                                               \
+  } while (0)
+
+extern "C" {
+
+const char *refgpu_last_error() { return g_err; }
+
+// StructuredRegularField::finalize + gpuData (f32 / u8 / u16 host data)
+int refgpu_field_create(const void *hostVoxels, int dataType, const uint32_t dims[3], const float origin[3],
+    const float spacing[3], int nearest, RefField **out)
+{
+  auto *f = new RefField();
+  int bits = 32;
+  cudaChannelFormatKind kind = cudaChannelFormatKindFloat;
+  if (dataType == DVR_UFIXED8) { bits = 8; kind = cudaChannelFormatKindUnsigned; }
+  else if (dataType == DVR_FIXED8) { bits = 8; kind = cudaChannelFormatKindSigned; }
+  else if (dataType == DVR_UFIXED16) { bits = 16; kind = cudaChannelFormatKindUnsigned; }
+  else if (dataType == DVR_FIXED16) { bits = 16; kind = cudaChannelFormatKindSigned; }
+  else if (dataType != DVR_FLOAT32) { snprintf(g_err, sizeof(g_err), "unsupported type"); return -1; }
+  auto desc = cudaCreateChannelDesc(bits, 0, 0, 0, kind);
+  RCK(cudaMalloc3DArray(&f->arr, &desc, make_cudaExtent(dims[0], dims[1], dims[2])));
+  cudaMemcpy3DParms cp;
+  std::memset(&cp, 0, sizeof(cp));
+  cp.srcPtr = make_cudaPitchedPtr(const_cast<void *>(hostVoxels), dims[0] * (bits / 8), dims[0], dims[1]);
+  cp.dstArray = f->arr;
+  cp.extent = make_cudaExtent(dims[0], dims[1], dims[2]);
+  cp.kind = cudaMemcpyDefault;
+  RCK(cudaMemcpy3D(&cp));
+  cudaResourceDesc rd;
+  std::memset(&rd, 0, sizeof(rd));
+  rd.resType = cudaResourceTypeArray;
+  rd.res.array.array = f->arr;
+  cudaTextureDesc td;
+  std::memset(&td, 0, sizeof(td));
+  td.addressMode[0] = td.addressMode[1] = td.addressMode[2] = cudaAddressModeClamp;
+  td.filterMode = nearest ? cudaFilterModePoint : cudaFilterModeLinear;
+  td.readMode = kind == cudaChannelFormatKindFloat ? cudaReadModeElementType : cudaReadModeNormalizedFloat;
+  td.normalizedCoords = 1;
+  RCK(cudaCreateTextureObject(&f->tex, &rd, &td, nullptr));
+  const vec3 o(origin[0], origin[1], origin[2]), sp(spacing[0], spacing[1], spacing[2]);
+  f->gpu.type = SpatialFieldType::STRUCTURED_REGULAR;
+  f->gpu.data.structuredRegular.texObj = f->tex;
+  f->gpu.data.structuredRegular.origin = o;
+  f->gpu.data.structuredRegular.spacing = sp;
+  f->gpu.data.structuredRegular.invSpacing = vec3(1.f) / (sp * vec3(dims[0], dims[1], dims[2]));
+  f->gpu.grid = UniformGridData{};
+  f->bounds = box3(o, o + ((vec3(dims[0], dims[1], dims[2]) - 1.f) * sp));
+  f->stepSize = glm::compMin(sp / 2.f);
+  *out = f;
+  return 0;
+}
+
+int refgpu_field_destroy(RefField *f)
+{
+  if (!f) return 0;
+  if (f->tex) cudaDestroyTextureObject(f->tex);
+  if (f->arr) cudaFreeArray(f->arr);
+  delete f;
+  return 0;
+}
+
+// TransferFunction1D::createTFTexture + gpuData
+int refgpu_volume_create(RefField *field, const float *tfRgba, const float valueRange[2], float unitDistance,
+    uint32_t id, RefVolume **out)
+{
+  auto *v = new RefVolume();
+  v->field = field;
+  auto desc = cudaCreateChannelDesc(32, 32, 32, 32, cudaChannelFormatKindFloat);
+  RCK(cudaMallocArray(&v->arr, &desc, DVR_TF_SIZE));
+  RCK(cudaMemcpy2DToArray(v->arr, 0, 0, tfRgba, DVR_TF_SIZE * 16, DVR_TF_SIZE * 16, 1, cudaMemcpyHostToDevice));
+  cudaResourceDesc rd;
+  std::memset(&rd, 0, sizeof(rd));
+  rd.resType = cudaResourceTypeArray;
+  rd.res.array.array = v->arr;
+  cudaTextureDesc td;
+  std::memset(&td, 0, sizeof(td));
+  td.addressMode[0] = cudaAddressModeClamp;
+  td.filterMode = cudaFilterModeLinear;
+  td.readMode = cudaReadModeElementType;
+  td.normalizedCoords = 1;
+  RCK(cudaCreateTextureObject(&v->tex, &rd, &td, nullptr));
+  v->gpu = VolumeGPUData{};
+  v->gpu.id = id;
+  v->gpu.type = VolumeType::TF1D;
+  v->gpu.bounds = field->bounds;
+  v->gpu.stepSize = field->stepSize;
+  v->gpu.data.tf1d.tfTex = v->tex;
+  v->gpu.data.tf1d.valueRange = box1(valueRange[0], valueRange[1]);
+  v->gpu.data.tf1d.oneOverUnitDistance = 1.0f / unitDistance;
+  v->gpu.data.tf1d.field = 0; // patched per launch
+  v->gpu.data.tf1d.uniformColor = vec3(1.f);
+  v->gpu.data.tf1d.uniformOpacity = 1.f;
+  *out = v;
+  return 0;
+}
+
+int refgpu_volume_destroy(RefVolume *v)
+{
+  if (!v) return 0;
+  if (v->tex) cudaDestroyTextureObject(v->tex);
+  if (v->arr) cudaFreeArray(v->arr);
+  delete v;
+  return 0;
+}
+
+struct RefInstance
+{
+  RefVolume *volume;
+  float worldToObject[12];
+  uint32_t instanceId;
+  uint32_t _pad;
+};
+
+// persistent per-scene device tables so that repeated launches (bench) cost one constant upload,
+// like Frame::upload() of the reference (Frame.cu:278)
+struct RefScene
+{
+  SpatialFieldGPUData *fields = nullptr;
+  VolumeGPUData *volumes = nullptr;
+  InstanceVolumeGPUData *instances = nullptr;
+  DeviceObjectIndex *volIdx = nullptr;
+  RefInstanceXfm *xfms = nullptr;
+  CameraGPUData *camera = nullptr;
+  int n = 0;
+};
+
+int refgpu_scene_create(const RefInstance *inst, int n, RefScene **out)
+{
+  auto *s = new RefScene();
+  s->n = n;
+  std::vector<SpatialFieldGPUData> fields(n);
+  std::vector<VolumeGPUData> vols(n);
+  std::vector<InstanceVolumeGPUData> insts(n);
+  std::vector<DeviceObjectIndex> idx(n);
+  std::vector<RefInstanceXfm> xf(n);
+  RCK(cudaMalloc(&s->volIdx, sizeof(DeviceObjectIndex) * (n ? n : 1)));
+  static const float ident[12] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0};
+  for (int i = 0; i < n; ++i) {
+    fields[i] = inst[i].volume->field->gpu;
+    vols[i] = inst[i].volume->gpu;
+    vols[i].data.tf1d.field = i;
+    idx[i] = i;
+    insts[i].volumes = s->volIdx + i;
+    insts[i].id = inst[i].instanceId;
+    std::memcpy(xf[i].m, inst[i].worldToObject, sizeof(ident));
+    xf[i].identity = std::memcmp(xf[i].m, ident, sizeof(ident)) == 0;
+  }
+  const int m = n ? n : 1;
+  RCK(cudaMalloc(&s->fields, sizeof(SpatialFieldGPUData) * m));
+  RCK(cudaMalloc(&s->volumes, sizeof(VolumeGPUData) * m));
+  RCK(cudaMalloc(&s->instances, sizeof(InstanceVolumeGPUData) * m));
+  RCK(cudaMalloc(&s->xfms, sizeof(RefInstanceXfm) * m));
+  RCK(cudaMalloc(&s->camera, sizeof(CameraGPUData)));
+  if (n) {
+    RCK(cudaMemcpy(s->fields, fields.data(), sizeof(SpatialFieldGPUData) * n, cudaMemcpyHostToDevice));
+    RCK(cudaMemcpy(s->volumes, vols.data(), sizeof(VolumeGPUData) * n, cudaMemcpyHostToDevice));
+    RCK(cudaMemcpy(s->instances, insts.data(), sizeof(InstanceVolumeGPUData) * n, cudaMemcpyHostToDevice));
+    RCK(cudaMemcpy(s->volIdx, idx.data(), sizeof(DeviceObjectIndex) * n, cudaMemcpyHostToDevice));
+    RCK(cudaMemcpy(s->xfms, xf.data(), sizeof(RefInstanceXfm) * n, cudaMemcpyHostToDevice));
+  }
+  *out = s;
+  return 0;
+}
+
+int refgpu_scene_destroy(RefScene *s)
+{
+  if (!s) return 0;
+  cudaFree(s->fields); cudaFree(s->volumes); cudaFree(s->instances); cudaFree(s->volIdx); cudaFree(s->xfms);
+  cudaFree(s->camera);
+  delete s;
+  return 0;
+}
+
+// Frame::renderFrame: newFrame() resets + upload() + launch (Frame.cu:272-289)
+int refgpu_render(const DvrFrameParams *p, const DvrCamera *c, RefScene *scene, const DvrFrameBuffers *b,
+    void *stream)
+{
+  cudaStream_t s = (cudaStream_t)stream;
+  CameraGPUData cam{};
+  cam.type = c->type == DVR_CAMERA_PERSPECTIVE ? CameraType::PERSPECTIVE : CameraType::ORTHOGRAPHIC;
+  cam.region = vec4(c->region[0], c->region[1], c->region[2], c->region[3]);
+  cam.pos = vec3(c->pos[0], c->pos[1], c->pos[2]);
+  cam.dir = vec3(c->dir[0], c->dir[1], c->dir[2]);
+  cam.up = vec3(c->up[0], c->up[1], c->up[2]);
+  if (c->type == DVR_CAMERA_PERSPECTIVE) {
+    cam.perspective.dir_du = vec3(c->du[0], c->du[1], c->du[2]);
+    cam.perspective.dir_dv = vec3(c->dv[0], c->dv[1], c->dv[2]);
+    cam.perspective.dir_00 = vec3(c->p00[0], c->p00[1], c->p00[2]);
+    cam.perspective.scaledAperture = c->scaledAperture;
+    cam.perspective.aspect = c->aspect;
+  } else {
+    cam.orthographic.pos_du = vec3(c->du[0], c->du[1], c->du[2]);
+    cam.orthographic.pos_dv = vec3(c->dv[0], c->dv[1], c->dv[2]);
+    cam.orthographic.pos_00 = vec3(c->p00[0], c->p00[1], c->p00[2]);
+  }
+  RCK(cudaMemcpyAsync(scene->camera, &cam, sizeof(cam), cudaMemcpyHostToDevice, s));
+
+  FrameGPUData fd;
+  std::memset(&fd, 0, sizeof(fd));
+  fd.fb.buffers.colorAccumulation = (vec4 *)b->colorAccumulation;
+  if (p->format == DVR_FORMAT_FLOAT32_VEC4)
+    fd.fb.buffers.outColorVec4 = (vec4 *)b->outColor;
+  else
+    fd.fb.buffers.outColorUint = (uint32_t *)b->outColor;
+  fd.fb.buffers.depth = b->depth;
+  fd.fb.buffers.primID = b->primId;
+  fd.fb.buffers.objID = b->objId;
+  fd.fb.buffers.instID = b->instId;
+  fd.fb.buffers.albedo = (vec3 *)b->albedo;
+  fd.fb.buffers.normal = (vec3 *)b->normal;
+  fd.fb.frameID = p->frameID;
+  fd.fb.checkerboardID = p->checkerboardID;
+  fd.fb.invFrameID = 1.f / (p->frameID + 1);
+  fd.fb.format = p->format == DVR_FORMAT_FLOAT32_VEC4
+      ? FrameFormat::FLOAT
+      : (p->format == DVR_FORMAT_UFIXED8_RGBA_SRGB ? FrameFormat::SRGB : FrameFormat::UINT);
+  fd.fb.size = uvec2(p->width, p->height);
+  fd.fb.invSize = 1.f / vec2(fd.fb.size);
+  fd.renderer.backgroundMode = BackgroundMode::COLOR;
+  fd.renderer.background.color = vec4(p->background[0], p->background[1], p->background[2], p->background[3]);
+  fd.renderer.ambientColor = vec3(1.f);
+  fd.renderer.ambientIntensity = 1.f;
+  fd.renderer.occlusionDistance = 1e20f;
+  fd.renderer.cullTriangleBF = false;
+  fd.renderer.inverseVolumeSamplingRate = p->inverseVolumeSamplingRate;
+  fd.renderer.numIterations = p->checkerboardID >= 0 ? 1 : (p->numIterations > 1 ? p->numIterations : 1);
+  fd.renderer.maxRayDepth = 5;
+  fd.world.volumeInstances = scene->instances;
+  fd.world.numVolumeInstances = scene->n;
+  fd.world.hdri = -1;
+  fd.camera = scene->camera;
+  fd.registry.fields = scene->fields;
+  fd.registry.volumes = scene->volumes;
+
+  const size_t npx = (size_t)p->width * p->height;
+  if (p->frameID == 0 && p->checkerboardID <= 0) { // Frame::newFrame reset, Frame.cu:594-647
+    fill((vec4 *)b->colorAccumulation, npx, vec4(0.f), s);
+    fill(b->depth, npx, std::numeric_limits<float>::max(), s);
+    fill(b->primId, npx, uint32_t(0), s);
+    fill(b->objId, npx, uint32_t(0), s);
+    fill(b->instId, npx, uint32_t(0), s);
+    fill((vec3 *)b->albedo, npx, vec3(0.f), s);
+    fill((vec3 *)b->normal, npx, vec3(0.f), s);
+  }
+  RCK(cudaMemcpyToSymbolAsync(frameData, &fd, sizeof(fd), 0, cudaMemcpyHostToDevice, s));
+  const RefInstanceXfm *xf = scene->xfms;
+  RCK(cudaMemcpyToSymbolAsync(g_xfms, &xf, sizeof(xf), 0, cudaMemcpyHostToDevice, s));
+  const uint32_t lw = p->checkerboardID >= 0 ? (p->width + 1) / 2 : p->width;
+  const uint32_t lh = p->checkerboardID >= 0 ? (p->height + 1) / 2 : p->height;
+  dim3 block(16, 8), grid((lw + 15) / 16, (lh + 7) / 8);
+  refgpu_raygen<<<grid, block, 0, s>>>(p->integrator == DVR_INTEGRATOR_RAYCAST ? 1 : 0);
+  RCK(cudaGetLastError());
+  return 0;
+}
+
+} // extern "C"

@@ -1,0 +1,322 @@
+"""Shared scene harness for the parity tests: one scene description, three renderers.
+
+  render_cuda()   the product: libdvr_b200.so through the C-ABI (visrtx_b200.capi), buffers in HBM (torch)
+  render_oracle() O-cpu  (oracle/liboracle_dvr.so)
+  render_refgpu() O-gpu  (oracle/_ref/libref_gpu_dvr.so, the reference's own device headers)
+
+Every renderer returns a dict of numpy arrays: color, accum, depth, primId, objId, instId (+albedo,
+normal when requested).
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass, field
+from typing import List, Optional
+
+import numpy as np
+
+import oracle_binding as ob
+from visrtx_b200 import capi, scenes
+
+_NP_TYPES = {
+    capi.DVR_FLOAT32: np.float32, capi.DVR_UFIXED8: np.uint8, capi.DVR_FIXED8: np.int8,
+    capi.DVR_UFIXED16: np.uint16, capi.DVR_FIXED16: np.int16, capi.DVR_FLOAT64: np.float64,
+    capi.DVR_FLOAT16: np.float16,
+}
+
+
+def normalized_float(vox: np.ndarray, data_type: int) -> np.ndarray:
+    """What cudaReadModeNormalizedFloat hands to the filter (CUDA programming guide, texture read modes)."""
+    if data_type == capi.DVR_UFIXED8:
+        return (vox.astype(np.float32) / np.float32(255.0)).astype(np.float32)
+    if data_type == capi.DVR_FIXED8:
+        return np.maximum(vox.astype(np.float32) / np.float32(127.0), np.float32(-1.0)).astype(np.float32)
+    if data_type == capi.DVR_UFIXED16:
+        return (vox.astype(np.float32) / np.float32(65535.0)).astype(np.float32)
+    if data_type == capi.DVR_FIXED16:
+        return np.maximum(vox.astype(np.float32) / np.float32(32767.0), np.float32(-1.0)).astype(np.float32)
+    return vox.astype(np.float32)
+
+
+@dataclass
+class VolumeDesc:
+    voxels: np.ndarray  # (z,y,x)
+    data_type: int = capi.DVR_FLOAT32
+    origin: tuple = (0.0, 0.0, 0.0)
+    spacing: tuple = (1.0, 1.0, 1.0)
+    nearest: bool = False
+    tf: Optional[np.ndarray] = None  # (256,4)
+    value_range: tuple = (0.0, 1.0)
+    unit_distance: float = 1.0
+    vol_id: int = 0xFFFFFFFF
+    inst_id: int = 0xFFFFFFFF
+    world_to_object: Optional[tuple] = None
+
+    @property
+    def dims(self):
+        nz, ny, nx = self.voxels.shape
+        return (nx, ny, nz)
+
+    def bounds(self):
+        lo = np.asarray(self.origin, dtype=np.float32)
+        hi = lo + (np.asarray(self.dims, dtype=np.float32) - np.float32(1.0)) * np.asarray(self.spacing, np.float32)
+        return lo, hi
+
+
+@dataclass
+class SceneDesc:
+    volumes: List[VolumeDesc]
+    width: int
+    height: int
+    camera: capi.DvrCamera
+    fmt: int = capi.DVR_FORMAT_UFIXED8_RGBA_SRGB
+    integrator: int = capi.DVR_INTEGRATOR_RAYCAST
+    volume_sampling_rate: float = 0.125
+    background: tuple = (0.1, 0.1, 0.1, 1.0)
+    num_iterations: int = 1
+    channels: tuple = ("depth", "primId", "objId", "instId")
+
+
+def default_scene(n=64, width=256, height=256, rate=0.5, field="ml", **kw) -> SceneDesc:
+    """BASELINE config C1 (scaled): Marschner-Lobb on [-1,1]^3, TSD default map, orbit camera."""
+    vox = scenes.marschner_lobb_np(n) if field == "ml" else scenes.blobs_np(n)
+    sp = 2.0 / (n - 1)
+    tf = capi.tf_discretize(color=scenes.tsd_default_colormap(256))
+    v = VolumeDesc(vox, origin=(-1.0, -1.0, -1.0), spacing=(sp, sp, sp), tf=tf, unit_distance=sp, vol_id=7,
+                   inst_id=3)
+    lo, hi = v.bounds()
+    pose = scenes.orbit_camera(lo, hi, width, height)
+    cam = capi.camera_perspective(pose.position, pose.direction, pose.up, pose.fovy, pose.aspect)
+    return SceneDesc([v], width, height, cam, volume_sampling_rate=rate, **kw)
+
+
+def _alloc_np(scene: SceneDesc):
+    n = scene.width * scene.height
+    out = {"accum": np.zeros((n, 4), np.float32)}
+    out["color"] = np.zeros((n, 4), np.float32) if scene.fmt == capi.DVR_FORMAT_FLOAT32_VEC4 else np.zeros(n, np.uint32)
+    if "depth" in scene.channels: out["depth"] = np.zeros(n, np.float32)
+    if "primId" in scene.channels: out["primId"] = np.zeros(n, np.uint32)
+    if "objId" in scene.channels: out["objId"] = np.zeros(n, np.uint32)
+    if "instId" in scene.channels: out["instId"] = np.zeros(n, np.uint32)
+    if "albedo" in scene.channels: out["albedo"] = np.zeros((n, 3), np.float32)
+    if "normal" in scene.channels: out["normal"] = np.zeros((n, 3), np.float32)
+    return out
+
+
+def _params(scene, frame_id, cb, **kw):
+    return capi.frame_params(scene.width, scene.height, scene.fmt, scene.integrator, frame_id, cb,
+                             scene.num_iterations, scene.volume_sampling_rate, scene.background, **kw)
+
+
+# ------------------------------------------------------------------------------------------------------------
+def render_oracle(scene: SceneDesc, frames=1, checkerboard=False, slab=None, state=None, return_samples=False):
+    """O-cpu; `frames` successive renderFrame calls with accumulation (Frame::newFrame bookkeeping)."""
+    out = state or _alloc_np(scene)
+    vols = (ob.OracleVolume * max(len(scene.volumes), 1))()
+    keep = []
+    for i, v in enumerate(scene.volumes):
+        f32 = np.ascontiguousarray(normalized_float(v.voxels, v.data_type))
+        tf = np.ascontiguousarray(v.tf, np.float32)
+        keep += [f32, tf]
+        o = vols[i]
+        o.voxels = f32.ctypes.data_as(C.c_void_p)
+        o.dims = (C.c_int32 * 3)(*v.dims)
+        o.origin = (C.c_float * 3)(*v.origin)
+        o.spacing = (C.c_float * 3)(*v.spacing)
+        o.filterNearest = 1 if v.nearest else 0
+        o.tf = tf.ctypes.data_as(C.c_void_p)
+        o.valueRange = (C.c_float * 2)(*v.value_range)
+        o.unitDistance = v.unit_distance
+        o.id = v.vol_id
+        o.worldToObject = (C.c_float * 12)(*(v.world_to_object or capi.IDENTITY_3X4))
+        o.instanceId = v.inst_id
+        if slab is not None:
+            o.zOwnBegin, o.zOwnEnd = slab
+    b = ob.OracleBuffers()
+    b.colorAccumulation = out["accum"].ctypes.data_as(C.c_void_p)
+    b.outColor = out["color"].ctypes.data_as(C.c_void_p)
+    for name, key in (("depth", "depth"), ("primId", "primId"), ("objId", "objId"), ("instId", "instId"),
+                      ("albedo", "albedo"), ("normal", "normal")):
+        if key in out:
+            setattr(b, name, out[key].ctypes.data_as(C.c_void_p))
+    total = 0
+    for frame_id, cb in frame_sequence(scene, frames, checkerboard):
+        p = _params(scene, frame_id, cb)
+        s = C.c_uint64()
+        rc = ob.cpu().oracle_render(C.byref(p), C.byref(scene.camera), vols, len(scene.volumes), C.byref(b),
+                                    C.byref(s), 0, 0)
+        assert rc == 0
+        total += s.value
+    if return_samples:
+        return out, total
+    return out
+
+
+def frame_sequence(scene, frames, checkerboard):
+    """(frameID, checkerboardID) per renderFrame call: Frame::newFrame, frame/Frame.cu:590-660."""
+    seq = []
+    frame_id, cb = 0, (0 if checkerboard else -1)
+    for i in range(frames):
+        if i > 0:
+            if checkerboard:
+                frame_id += 1 if cb == 3 else 0
+                cb = (cb + 1) & 3
+            else:
+                frame_id += scene.num_iterations
+        seq.append((frame_id, cb))
+    return seq
+
+
+# ------------------------------------------------------------------------------------------------------------
+class CudaScene:
+    """Device-side objects of a SceneDesc created through the C-ABI."""
+
+    def __init__(self, scene: SceneDesc, slab=None, device="cuda:0"):
+        import torch
+        self.torch = torch
+        self.scene = scene
+        self.device = torch.device(device)
+        torch.cuda.set_device(self.device)
+        self.fields, self.volumes = [], []
+        for v in scene.volumes:
+            vox = np.ascontiguousarray(v.voxels.astype(_NP_TYPES[v.data_type], copy=False))
+            filt = capi.DVR_FILTER_NEAREST if v.nearest else capi.DVR_FILTER_LINEAR
+            if slab is None:
+                f = capi.Field.create_structured(vox.ctypes.data, False, v.data_type, v.dims, v.origin, v.spacing, filt)
+            else:
+                zb, ze = slab
+                z0 = max(zb - 1, 0)
+                z1 = min(ze + 1, v.dims[2])
+                sub = np.ascontiguousarray(vox[z0:z1])
+                f = capi.Field.create_slab(sub.ctypes.data, False, v.data_type, v.dims, zb, ze, v.origin, v.spacing, filt)
+            self.fields.append(f)
+            self.volumes.append(capi.Volume.create(f, v.tf, v.value_range, v.unit_distance, v.vol_id))
+        self.instances, self.n = capi.make_instances(
+            self.volumes, [v.world_to_object for v in scene.volumes], [v.inst_id for v in scene.volumes])
+        n = scene.width * scene.height
+        t = torch
+        self.buf = {"accum": t.zeros((n, 4), dtype=t.float32, device=self.device)}
+        if scene.fmt == capi.DVR_FORMAT_FLOAT32_VEC4:
+            self.buf["color"] = t.zeros((n, 4), dtype=t.float32, device=self.device)
+        else:
+            self.buf["color"] = t.zeros(n, dtype=t.int32, device=self.device)
+        for key, shape, dt in (("depth", (n,), t.float32), ("primId", (n,), t.int32), ("objId", (n,), t.int32),
+                               ("instId", (n,), t.int32), ("albedo", (n, 3), t.float32), ("normal", (n, 3), t.float32)):
+            if key in scene.channels:
+                # poison so that "initialised by the launch" is really tested
+                self.buf[key] = t.full(shape, -12345, dtype=dt, device=self.device)
+        self.buf["accum"].fill_(777.0)
+        g = lambda k: self.buf[k].data_ptr() if k in self.buf else 0
+        self.fb = capi.frame_buffers(g("accum"), g("color"), g("depth"), g("primId"), g("objId"), g("instId"),
+                                     g("albedo"), g("normal"))
+
+    def render(self, frame_id=0, cb=-1, skip=False, tile_rank=0, tile_ranks=1, stats=False):
+        p = _params(self.scene, frame_id, cb, skip=skip, tile_rank=tile_rank, tile_ranks=tile_ranks)
+        if stats:
+            st = self.torch.zeros(4, dtype=self.torch.int64, device=self.device)
+            capi.render_instrumented(p, self.scene.camera, self.instances, self.n, self.fb, st.data_ptr())
+            self.torch.cuda.synchronize()
+            return dict(zip(("samplesTaken", "samplesSkipped", "raysHit", "macrocellsTouched"), st.tolist()))
+        capi.render(p, self.scene.camera, self.instances, self.n, self.fb)
+        return None
+
+    def download(self):
+        self.torch.cuda.synchronize()
+        out = {}
+        for k, v in self.buf.items():
+            a = v.cpu().numpy()
+            if a.dtype == np.int32:
+                a = a.view(np.uint32)
+            out[k] = a
+        return out
+
+    def destroy(self):
+        for v in self.volumes:
+            v.destroy()
+        for f in self.fields:
+            f.destroy()
+
+
+def render_cuda(scene: SceneDesc, frames=1, checkerboard=False, skip=False):
+    cs = CudaScene(scene)
+    try:
+        for frame_id, cb in frame_sequence(scene, frames, checkerboard):
+            cs.render(frame_id, cb, skip=skip)
+        return cs.download()
+    finally:
+        cs.destroy()
+
+
+# ------------------------------------------------------------------------------------------------------------
+def render_refgpu(scene: SceneDesc, frames=1, checkerboard=False):
+    """O-gpu: the reference's device headers (tex3D / tex1D / cuRAND) on the same GPU."""
+    import torch
+    lib = ob.refgpu()
+    fields, vols = [], []
+    inst = (ob.RefInstance * max(len(scene.volumes), 1))()
+    keep = []
+    for i, v in enumerate(scene.volumes):
+        vox = np.ascontiguousarray(v.voxels.astype(_NP_TYPES[v.data_type], copy=False))
+        keep.append(vox)
+        f = C.c_void_p()
+        rc = lib.refgpu_field_create(vox.ctypes.data_as(C.c_void_p), C.c_int(v.data_type), (C.c_uint32 * 3)(*v.dims),
+                                     (C.c_float * 3)(*v.origin), (C.c_float * 3)(*v.spacing),
+                                     C.c_int(1 if v.nearest else 0), C.byref(f))
+        assert rc == 0, lib.refgpu_last_error()
+        tf = np.ascontiguousarray(v.tf, np.float32)
+        h = C.c_void_p()
+        rc = lib.refgpu_volume_create(f, tf.ctypes.data_as(C.c_void_p), (C.c_float * 2)(*v.value_range),
+                                      C.c_float(v.unit_distance), C.c_uint32(v.vol_id), C.byref(h))
+        assert rc == 0, lib.refgpu_last_error()
+        fields.append(f)
+        vols.append(h)
+        inst[i].volume = h
+        inst[i].worldToObject = (C.c_float * 12)(*(v.world_to_object or capi.IDENTITY_3X4))
+        inst[i].instanceId = v.inst_id
+    sc = C.c_void_p()
+    rc = lib.refgpu_scene_create(inst, C.c_int(len(scene.volumes)), C.byref(sc))
+    assert rc == 0, lib.refgpu_last_error()
+    n = scene.width * scene.height
+    dev = torch.device("cuda:0")
+    buf = {"accum": torch.full((n, 4), 777.0, dtype=torch.float32, device=dev)}
+    buf["color"] = (torch.zeros((n, 4), dtype=torch.float32, device=dev)
+                    if scene.fmt == capi.DVR_FORMAT_FLOAT32_VEC4 else torch.zeros(n, dtype=torch.int32, device=dev))
+    for key, shape, dt in (("depth", (n,), torch.float32), ("primId", (n,), torch.int32), ("objId", (n,), torch.int32),
+                           ("instId", (n,), torch.int32), ("albedo", (n, 3), torch.float32),
+                           ("normal", (n, 3), torch.float32)):
+        if key in scene.channels:
+            buf[key] = torch.full(shape, -12345, dtype=dt, device=dev)
+    g = lambda k: buf[k].data_ptr() if k in buf else 0
+    fb = capi.frame_buffers(g("accum"), g("color"), g("depth"), g("primId"), g("objId"), g("instId"), g("albedo"),
+                            g("normal"))
+    for frame_id, cb in frame_sequence(scene, frames, checkerboard):
+        p = _params(scene, frame_id, cb)
+        rc = lib.refgpu_render(C.byref(p), C.byref(scene.camera), sc, C.byref(fb), C.c_void_p(0))
+        assert rc == 0, lib.refgpu_last_error()
+    torch.cuda.synchronize()
+    out = {}
+    for k, v in buf.items():
+        a = v.cpu().numpy()
+        out[k] = a.view(np.uint32) if a.dtype == np.int32 else a
+    lib.refgpu_scene_destroy(sc)
+    for h in vols:
+        lib.refgpu_volume_destroy(h)
+    for f in fields:
+        lib.refgpu_field_destroy(f)
+    return out
+
+
+# ------------------------------------------------------------------------------------------------------------
+def unpack_rgba8(u32: np.ndarray) -> np.ndarray:
+    return np.stack([(u32 >> s) & 0xFF for s in (0, 8, 16, 24)], axis=-1).astype(np.int32)
+
+
+def compare_color(a: np.ndarray, b: np.ndarray, fmt: int):
+    """max abs per-channel difference (in 1/255 units) and PSNR in dB."""
+    if fmt == capi.DVR_FORMAT_FLOAT32_VEC4:
+        d = np.abs(a.astype(np.float64) - b.astype(np.float64)) * 255.0
+    else:
+        d = np.abs(unpack_rgba8(a) - unpack_rgba8(b)).astype(np.float64)
+    mse = float(np.mean((d / 255.0) ** 2))
+    psnr = 99.0 if mse == 0 else 10.0 * np.log10(1.0 / mse)
+    return float(d.max()), psnr

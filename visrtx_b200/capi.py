@@ -1,0 +1,331 @@
+"""ctypes binding of the C-ABI launch layer (include/dvr_b200.h).
+
+One Python function per exported symbol, same names and argument meaning.  Errors are raised as
+:class:`DvrError` carrying ``dvr_last_error()``; nothing here computes anything on the CPU.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import Optional, Sequence
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libdvr_b200.so")
+
+DVR_TF_SIZE = 256
+DVR_MACROCELL_WIDTH = 16
+
+# enums (include/dvr_b200.h)
+DVR_OK, DVR_ERR_INVALID_ARGUMENT, DVR_ERR_NO_DEVICE, DVR_ERR_CUDA, DVR_ERR_UNSUPPORTED, DVR_ERR_OUT_OF_MEMORY = (
+    0, -1, -2, -3, -4, -5)
+DVR_FLOAT32, DVR_UFIXED8, DVR_FIXED8, DVR_UFIXED16, DVR_FIXED16, DVR_FLOAT64, DVR_FLOAT16 = range(7)
+DVR_FILTER_LINEAR, DVR_FILTER_NEAREST = 0, 1
+DVR_FORMAT_FLOAT32_VEC4, DVR_FORMAT_UFIXED8_VEC4, DVR_FORMAT_UFIXED8_RGBA_SRGB = 0, 1, 2
+DVR_CAMERA_PERSPECTIVE, DVR_CAMERA_ORTHOGRAPHIC = 0, 1
+DVR_INTEGRATOR_RAYCAST, DVR_INTEGRATOR_DEFAULT = 0, 1
+
+# every symbol include/dvr_b200.h declares (tests check the library exports all of them)
+EXPORTED_SYMBOLS = [
+    "dvr_last_error", "dvr_version", "dvr_device_count", "dvr_set_device", "dvr_device_info",
+    "dvr_camera_perspective", "dvr_camera_orthographic", "dvr_tf_discretize",
+    "dvr_field_create_structured", "dvr_field_create_structured_slab", "dvr_field_destroy",
+    "dvr_field_bounds", "dvr_field_step_size", "dvr_field_device_bytes", "dvr_field_build_macrocells",
+    "dvr_field_macrocells", "dvr_field_value_range",
+    "dvr_volume_create", "dvr_volume_update", "dvr_volume_destroy", "dvr_volume_majorants",
+    "dvr_render", "dvr_render_instrumented", "dvr_launch_count",
+    "dvr_render_partial", "dvr_composite_over", "dvr_resolve", "dvr_scale_vec3",
+]
+
+
+class DvrError(RuntimeError):
+    def __init__(self, code: int, msg: str):
+        super().__init__(f"dvr error {code}: {msg}")
+        self.code = code
+
+
+class DvrCamera(C.Structure):
+    _fields_ = [("type", C.c_int32), ("region", C.c_float * 4), ("pos", C.c_float * 3), ("dir", C.c_float * 3),
+                ("up", C.c_float * 3), ("du", C.c_float * 3), ("dv", C.c_float * 3), ("p00", C.c_float * 3),
+                ("scaledAperture", C.c_float), ("aspect", C.c_float)]
+
+
+class DvrVolumeInstance(C.Structure):
+    _fields_ = [("volume", C.c_void_p), ("worldToObject", C.c_float * 12), ("instanceId", C.c_uint32),
+                ("_pad", C.c_uint32)]
+
+
+class DvrFrameBuffers(C.Structure):
+    _fields_ = [("colorAccumulation", C.c_void_p), ("outColor", C.c_void_p), ("depth", C.c_void_p),
+                ("primId", C.c_void_p), ("objId", C.c_void_p), ("instId", C.c_void_p), ("albedo", C.c_void_p),
+                ("normal", C.c_void_p)]
+
+
+class DvrFrameParams(C.Structure):
+    _fields_ = [("width", C.c_uint32), ("height", C.c_uint32), ("format", C.c_int32), ("integrator", C.c_int32),
+                ("frameID", C.c_int32), ("checkerboardID", C.c_int32), ("numIterations", C.c_int32),
+                ("inverseVolumeSamplingRate", C.c_float), ("background", C.c_float * 4),
+                ("tileRank", C.c_uint32), ("tileRanks", C.c_uint32), ("useMacrocellSkipping", C.c_int32),
+                ("_reserved", C.c_int32 * 3)]
+
+
+class DvrRenderStats(C.Structure):
+    _fields_ = [("samplesTaken", C.c_ulonglong), ("samplesSkipped", C.c_ulonglong), ("raysHit", C.c_ulonglong),
+                ("macrocellsTouched", C.c_ulonglong)]
+
+
+IDENTITY_3X4 = (1.0, 0.0, 0.0, 0.0, 0.0, 1.0, 0.0, 0.0, 0.0, 0.0, 1.0, 0.0)
+
+
+def _load() -> C.CDLL:
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(
+            f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+            "(or `make -C visrtx_b200/csrc`).  There is no CPU fallback.")
+    return C.CDLL(LIB_PATH)
+
+
+lib = _load()
+lib.dvr_last_error.restype = C.c_char_p
+lib.dvr_launch_count.restype = C.c_ulonglong
+for _name in EXPORTED_SYMBOLS:
+    if _name not in ("dvr_last_error", "dvr_launch_count"):
+        getattr(lib, _name).restype = C.c_int
+
+_f3 = C.c_float * 3
+_f4 = C.c_float * 4
+_f2 = C.c_float * 2
+_u3 = C.c_uint32 * 3
+
+
+def _check(rc: int) -> None:
+    if rc != DVR_OK:
+        raise DvrError(rc, lib.dvr_last_error().decode())
+
+
+def last_error() -> str:
+    return lib.dvr_last_error().decode()
+
+
+def version():
+    a, b = C.c_int(), C.c_int()
+    _check(lib.dvr_version(C.byref(a), C.byref(b)))
+    return a.value, b.value
+
+
+def device_count() -> int:
+    return int(lib.dvr_device_count())
+
+
+def set_device(i: int) -> None:
+    _check(lib.dvr_set_device(C.c_int(i)))
+
+
+def device_info():
+    name = C.create_string_buffer(256)
+    sms, mem = C.c_int(), C.c_size_t()
+    _check(lib.dvr_device_info(name, C.c_size_t(256), C.byref(sms), C.byref(mem)))
+    return name.value.decode(), sms.value, mem.value
+
+
+def launch_count() -> int:
+    return int(lib.dvr_launch_count())
+
+
+def camera_perspective(pos, direction, up, fovy, aspect, focus_distance=1.0, aperture_radius=0.0,
+                       region=None) -> DvrCamera:
+    cam = DvrCamera()
+    reg = _f4(*region) if region is not None else None
+    _check(lib.dvr_camera_perspective(_f3(*pos), _f3(*direction), _f3(*up), C.c_float(fovy), C.c_float(aspect),
+                                      C.c_float(focus_distance), C.c_float(aperture_radius), reg, C.byref(cam)))
+    return cam
+
+
+def camera_orthographic(pos, direction, up, height, aspect, region=None) -> DvrCamera:
+    cam = DvrCamera()
+    reg = _f4(*region) if region is not None else None
+    _check(lib.dvr_camera_orthographic(_f3(*pos), _f3(*direction), _f3(*up), C.c_float(height), C.c_float(aspect),
+                                       reg, C.byref(cam)))
+    return cam
+
+
+def tf_discretize(color=None, opacity=None, uniform_color=(1.0, 1.0, 1.0, 1.0), uniform_opacity=1.0,
+                  value_range=(0.0, 1.0)):
+    """TransferFunction1D::discritizeTFData; color is an (N,3|4) float32 numpy array or None."""
+    import numpy as np
+    out = np.empty((DVR_TF_SIZE, 4), dtype=np.float32)
+    cptr, ncol, nch = None, 0, 4
+    if color is not None:
+        color = np.ascontiguousarray(color, dtype=np.float32)
+        ncol, nch = color.shape
+        cptr = color.ctypes.data_as(C.c_void_p)
+    optr, nop = None, 0
+    if opacity is not None:
+        opacity = np.ascontiguousarray(opacity, dtype=np.float32)
+        nop = opacity.shape[0]
+        optr = opacity.ctypes.data_as(C.c_void_p)
+    _check(lib.dvr_tf_discretize(cptr, C.c_size_t(ncol), C.c_int(nch), optr, C.c_size_t(nop), _f4(*uniform_color),
+                                 C.c_float(uniform_opacity), _f2(*value_range), out.ctypes.data_as(C.c_void_p)))
+    return out
+
+
+class Field:
+    """DvrField handle (StructuredRegularField GPU state)."""
+
+    def __init__(self, handle: C.c_void_p):
+        self.handle = handle
+
+    @staticmethod
+    def create_structured(data_ptr: int, is_device: bool, data_type: int, dims: Sequence[int], origin, spacing,
+                          filter_mode: int = DVR_FILTER_LINEAR, stream: int = 0) -> "Field":
+        h = C.c_void_p()
+        _check(lib.dvr_field_create_structured(C.c_void_p(data_ptr), C.c_int(1 if is_device else 0),
+                                               C.c_int(data_type), _u3(*dims), _f3(*origin), _f3(*spacing),
+                                               C.c_int(filter_mode), C.c_void_p(stream), C.byref(h)))
+        return Field(h)
+
+    @staticmethod
+    def create_slab(data_ptr: int, is_device: bool, data_type: int, global_dims, z_begin: int, z_end: int, origin,
+                    spacing, filter_mode: int = DVR_FILTER_LINEAR, stream: int = 0) -> "Field":
+        h = C.c_void_p()
+        _check(lib.dvr_field_create_structured_slab(C.c_void_p(data_ptr), C.c_int(1 if is_device else 0),
+                                                    C.c_int(data_type), _u3(*global_dims), C.c_uint32(z_begin),
+                                                    C.c_uint32(z_end), _f3(*origin), _f3(*spacing),
+                                                    C.c_int(filter_mode), C.c_void_p(stream), C.byref(h)))
+        return Field(h)
+
+    def destroy(self) -> None:
+        if self.handle:
+            lib.dvr_field_destroy(self.handle)
+            self.handle = None
+
+    def bounds(self):
+        lo, hi = _f3(), _f3()
+        _check(lib.dvr_field_bounds(self.handle, lo, hi))
+        return tuple(lo), tuple(hi)
+
+    def step_size(self) -> float:
+        s = C.c_float()
+        _check(lib.dvr_field_step_size(self.handle, C.byref(s)))
+        return s.value
+
+    def device_bytes(self) -> int:
+        b = C.c_size_t()
+        _check(lib.dvr_field_device_bytes(self.handle, C.byref(b)))
+        return b.value
+
+    def build_macrocells(self, stream: int = 0) -> None:
+        _check(lib.dvr_field_build_macrocells(self.handle, C.c_void_p(stream)))
+
+    def macrocells(self):
+        dims = _u3()
+        ptr = C.c_void_p()
+        _check(lib.dvr_field_macrocells(self.handle, dims, C.byref(ptr)))
+        return tuple(dims), ptr.value
+
+    def value_range(self, stream: int = 0):
+        r = _f2()
+        _check(lib.dvr_field_value_range(self.handle, C.c_void_p(stream), r))
+        return r[0], r[1]
+
+
+class Volume:
+    """DvrVolume handle (TransferFunction1D GPU state)."""
+
+    def __init__(self, handle: C.c_void_p, field: Field):
+        self.handle = handle
+        self.field = field
+
+    @staticmethod
+    def create(field: Field, tf_rgba, value_range=(0.0, 1.0), unit_distance=1.0, vol_id=0xFFFFFFFF,
+               stream: int = 0) -> "Volume":
+        import numpy as np
+        tf = np.ascontiguousarray(tf_rgba, dtype=np.float32).reshape(DVR_TF_SIZE, 4)
+        h = C.c_void_p()
+        _check(lib.dvr_volume_create(field.handle, tf.ctypes.data_as(C.c_void_p), _f2(*value_range),
+                                     C.c_float(unit_distance), C.c_uint32(vol_id), C.c_void_p(stream), C.byref(h)))
+        return Volume(h, field)
+
+    def update(self, tf_rgba, value_range=(0.0, 1.0), unit_distance=1.0, vol_id=0xFFFFFFFF, stream: int = 0):
+        import numpy as np
+        tf = np.ascontiguousarray(tf_rgba, dtype=np.float32).reshape(DVR_TF_SIZE, 4)
+        _check(lib.dvr_volume_update(self.handle, tf.ctypes.data_as(C.c_void_p), _f2(*value_range),
+                                     C.c_float(unit_distance), C.c_uint32(vol_id), C.c_void_p(stream)))
+
+    def majorants_ptr(self) -> int:
+        p = C.c_void_p()
+        _check(lib.dvr_volume_majorants(self.handle, C.byref(p)))
+        return p.value
+
+    def destroy(self) -> None:
+        if self.handle:
+            lib.dvr_volume_destroy(self.handle)
+            self.handle = None
+
+
+def make_instances(volumes: Sequence[Volume], xfms=None, inst_ids=None):
+    n = len(volumes)
+    arr = (DvrVolumeInstance * max(n, 1))()
+    for i, v in enumerate(volumes):
+        arr[i].volume = v.handle
+        m = IDENTITY_3X4 if xfms is None or xfms[i] is None else tuple(float(x) for x in xfms[i])
+        arr[i].worldToObject = (C.c_float * 12)(*m)
+        arr[i].instanceId = 0xFFFFFFFF if inst_ids is None else int(inst_ids[i])
+    return arr, n
+
+
+def frame_params(width, height, fmt=DVR_FORMAT_UFIXED8_RGBA_SRGB, integrator=DVR_INTEGRATOR_RAYCAST, frame_id=0,
+                 checkerboard_id=-1, num_iterations=1, volume_sampling_rate=0.125, background=(0.0, 0.0, 0.0, 1.0),
+                 tile_rank=0, tile_ranks=1, skip=False) -> DvrFrameParams:
+    p = DvrFrameParams()
+    p.width, p.height, p.format, p.integrator = int(width), int(height), int(fmt), int(integrator)
+    p.frameID, p.checkerboardID, p.numIterations = int(frame_id), int(checkerboard_id), int(num_iterations)
+    import numpy as np
+    p.inverseVolumeSamplingRate = float(np.float32(1.0) / np.float32(volume_sampling_rate))
+    p.background = _f4(*background)
+    p.tileRank, p.tileRanks = int(tile_rank), int(tile_ranks)
+    p.useMacrocellSkipping = 1 if skip else 0
+    return p
+
+
+def frame_buffers(accum: int, out_color: int, depth: int = 0, prim: int = 0, obj: int = 0, inst: int = 0,
+                  albedo: int = 0, normal: int = 0) -> DvrFrameBuffers:
+    b = DvrFrameBuffers()
+    b.colorAccumulation, b.outColor = accum or None, out_color or None
+    b.depth, b.primId, b.objId, b.instId = depth or None, prim or None, obj or None, inst or None
+    b.albedo, b.normal = albedo or None, normal or None
+    return b
+
+
+def render(params: DvrFrameParams, camera: DvrCamera, instances, n_instances: int, buffers: DvrFrameBuffers,
+           stream: int = 0) -> None:
+    _check(lib.dvr_render(C.byref(params), C.byref(camera), instances, C.c_uint32(n_instances), C.byref(buffers),
+                          C.c_void_p(stream)))
+
+
+def render_instrumented(params, camera, instances, n_instances, buffers, stats_dev_ptr: int, stream: int = 0):
+    _check(lib.dvr_render_instrumented(C.byref(params), C.byref(camera), instances, C.c_uint32(n_instances),
+                                       C.byref(buffers), C.c_void_p(stats_dev_ptr), C.c_void_p(stream)))
+
+
+def render_partial(params, camera, instance, partial_rgba: int, partial_depth: int, stream: int = 0):
+    _check(lib.dvr_render_partial(C.byref(params), C.byref(camera), instance, C.c_void_p(partial_rgba),
+                                  C.c_void_p(partial_depth), C.c_void_p(stream)))
+
+
+def composite_over(front_rgba: int, front_depth: int, back_rgba: int, back_depth: int, begin: int, end: int,
+                   back_is_in_front: bool, stream: int = 0):
+    _check(lib.dvr_composite_over(C.c_void_p(front_rgba), C.c_void_p(front_depth or None), C.c_void_p(back_rgba),
+                                  C.c_void_p(back_depth or None), C.c_size_t(begin), C.c_size_t(end),
+                                  C.c_int(1 if back_is_in_front else 0), C.c_void_p(stream)))
+
+
+def resolve(params, partial_rgba: int, partial_depth: int, obj_id: int, inst_id: int, buffers, begin: int, end: int,
+            stream: int = 0):
+    _check(lib.dvr_resolve(C.byref(params), C.c_void_p(partial_rgba), C.c_void_p(partial_depth or None),
+                           C.c_uint32(obj_id), C.c_uint32(inst_id), C.byref(buffers), C.c_size_t(begin),
+                           C.c_size_t(end), C.c_void_p(stream)))
+
+
+def scale_vec3(src: int, dst: int, n_pixels: int, scale: float, stream: int = 0):
+    _check(lib.dvr_scale_vec3(C.c_void_p(src), C.c_void_p(dst), C.c_size_t(n_pixels), C.c_float(scale),
+                              C.c_void_p(stream)))

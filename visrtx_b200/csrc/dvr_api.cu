@@ -1,0 +1,908 @@
+// dvr_api.cu — the extern "C" launch layer declared in include/dvr_b200.h.
+// Host-side object state (3-D array + texture objects, macrocell buffers, TF tables) and the
+// parameter translation from the POD structs of the C-ABI to the kernel parameter blocks.
+#include <cmath>
+#include <cstring>
+#include <atomic>
+#include <mutex>
+#include <vector>
+
+#include "dvr_internal.h"
+
+namespace dvr {
+
+static thread_local std::string g_lastError;
+static std::atomic<unsigned long long> g_launches{0};
+
+void setError(const std::string &msg) { g_lastError = msg; }
+
+int cudaFail(cudaError_t e, const char *what)
+{
+  g_lastError = std::string(what) + ": " + cudaGetErrorString(e);
+  if (e == cudaErrorNoDevice || e == cudaErrorInsufficientDriver)
+    return DVR_ERR_NO_DEVICE;
+  if (e == cudaErrorMemoryAllocation)
+    return DVR_ERR_OUT_OF_MEMORY;
+  return DVR_ERR_CUDA;
+}
+
+void countLaunch(unsigned n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+
+// per-device scheduler counters: a ring of {nextTile, warpsDone} pairs, always zero between launches
+struct DeviceScratch
+{
+  unsigned int *sched = nullptr;
+  unsigned next = 0;
+  int sms = 0;
+  InstanceDev *extInstances = nullptr;
+  size_t extCapacity = 0;
+};
+static std::mutex g_scratchMutex;
+static DeviceScratch g_scratch[64];
+constexpr unsigned kSchedSlots = 256;
+
+static DeviceScratch *scratch()
+{
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64)
+    return nullptr;
+  std::lock_guard<std::mutex> lock(g_scratchMutex);
+  DeviceScratch &s = g_scratch[dev];
+  if (!s.sched) {
+    if (cudaMalloc(&s.sched, kSchedSlots * 2 * sizeof(unsigned int)) != cudaSuccess)
+      return nullptr;
+    cudaMemset(s.sched, 0, kSchedSlots * 2 * sizeof(unsigned int));
+    cudaDeviceGetAttribute(&s.sms, cudaDevAttrMultiProcessorCount, dev);
+  }
+  return &s;
+}
+
+unsigned int *acquireSchedSlot()
+{
+  DeviceScratch *s = scratch();
+  if (!s)
+    return nullptr;
+  std::lock_guard<std::mutex> lock(g_scratchMutex);
+  unsigned int *p = s->sched + 2 * (s->next % kSchedSlots);
+  s->next++;
+  return p;
+}
+
+int smCount()
+{
+  DeviceScratch *s = scratch();
+  return s && s->sms > 0 ? s->sms : 148;
+}
+
+} // namespace dvr
+
+using namespace dvr;
+
+// ------------------------------------------------------------------------------------------------
+// opaque objects
+// ------------------------------------------------------------------------------------------------
+struct DvrField
+{
+  cudaArray_t array = nullptr;
+  cudaTextureObject_t tex = 0;      // filtering view (clamp, normalised)
+  cudaTextureObject_t pointTex = 0; // point view, unnormalised (macrocell build)
+  FieldDev dev{};
+  float2 *ranges = nullptr;
+  size_t nCells = 0;
+  size_t voxelBytes = 0;
+  int device = 0;
+};
+
+struct DvrVolume
+{
+  const DvrField *field = nullptr;
+  float4 *tf = nullptr;
+  float *maxOpacities = nullptr;
+  float vrLo = 0.f, vrHi = 1.f, oneOverUnitDistance = 1.f;
+  uint32_t id = ~0u;
+};
+
+static inline float3 v3(const float *p) { return make_float3(p[0], p[1], p[2]); }
+static float3 hnormalize(float3 v)
+{
+  const float d = v.x * v.x + v.y * v.y + v.z * v.z;
+  const float inv = 1.0f / std::sqrt(d);
+  return make_float3(v.x * inv, v.y * inv, v.z * inv);
+}
+static float3 hcross(float3 a, float3 b)
+{
+  return make_float3(a.y * b.z - b.y * a.z, a.z * b.x - b.z * a.x, a.x * b.y - b.x * a.y);
+}
+static float3 hscale(float3 a, float s) { return make_float3(a.x * s, a.y * s, a.z * s); }
+static float3 hsub(float3 a, float3 b) { return make_float3(a.x - b.x, a.y - b.y, a.z - b.z); }
+static void st3(float *d, float3 v) { d[0] = v.x; d[1] = v.y; d[2] = v.z; }
+
+extern "C" {
+
+const char *dvr_last_error(void) { return g_lastError.c_str(); }
+
+int dvr_version(int *major, int *minor)
+{
+  if (major) *major = DVR_B200_VERSION_MAJOR;
+  if (minor) *minor = DVR_B200_VERSION_MINOR;
+  return DVR_OK;
+}
+
+int dvr_device_count(void)
+{
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) {
+    cudaGetLastError();
+    return 0;
+  }
+  return n;
+}
+
+int dvr_set_device(int cudaDevice)
+{
+  DVR_CUDA(cudaSetDevice(cudaDevice));
+  return DVR_OK;
+}
+
+int dvr_device_info(char *name, size_t nameLen, int *sms, size_t *totalMem)
+{
+  int dev = 0;
+  DVR_CUDA(cudaGetDevice(&dev));
+  cudaDeviceProp prop;
+  DVR_CUDA(cudaGetDeviceProperties(&prop, dev));
+  if (name && nameLen) {
+    std::strncpy(name, prop.name, nameLen - 1);
+    name[nameLen - 1] = 0;
+  }
+  if (sms) *sms = prop.multiProcessorCount;
+  if (totalMem) *totalMem = prop.totalGlobalMem;
+  return DVR_OK;
+}
+
+unsigned long long dvr_launch_count(void) { return g_launches.load(); }
+
+// ---- cameras -------------------------------------------------------------------------------------
+
+static void cameraBase(const float pos[3], const float dir[3], const float up[3], const float region[4],
+    DvrCamera *out)
+{
+  std::memset(out, 0, sizeof(*out));
+  out->region[0] = region ? region[0] : 0.f;
+  out->region[1] = region ? region[1] : 0.f;
+  out->region[2] = region ? region[2] : 1.f;
+  out->region[3] = region ? region[3] : 1.f;
+  st3(out->pos, v3(pos));
+  st3(out->dir, hnormalize(v3(dir)));
+  st3(out->up, hnormalize(v3(up)));
+}
+
+int dvr_camera_perspective(const float pos[3], const float dir[3], const float up[3], float fovy, float aspect,
+    float focusDistance, float apertureRadius, const float region[4], DvrCamera *out)
+{
+  if (!pos || !dir || !up || !out) {
+    setError("dvr_camera_perspective: null argument");
+    return DVR_ERR_INVALID_ARGUMENT;
+  }
+  cameraBase(pos, dir, up, region, out);
+  out->type = DVR_CAMERA_PERSPECTIVE;
+  const float3 d = v3(out->dir), u = v3(out->up);
+  const float planeY = 2.f * tanf(0.5f * fovy);
+  const float planeX = planeY * aspect;
+  float3 du = hscale(hnormalize(hcross(d, u)), planeX);
+  float3 dv = hscale(hnormalize(hcross(du, d)), planeY);
+  float3 d00 = hsub(hsub(d, hscale(du, .5f)), hscale(dv, .5f));
+  const float scaledAperture = apertureRadius / (planeX * focusDistance);
+  if (scaledAperture > 0.f) {
+    du = hscale(du, focusDistance);
+    dv = hscale(dv, focusDistance);
+    d00 = hscale(d00, focusDistance);
+  }
+  st3(out->du, du);
+  st3(out->dv, dv);
+  st3(out->p00, d00);
+  out->scaledAperture = scaledAperture;
+  out->aspect = aspect;
+  return DVR_OK;
+}
+
+int dvr_camera_orthographic(const float pos[3], const float dir[3], const float up[3], float height, float aspect,
+    const float region[4], DvrCamera *out)
+{
+  if (!pos || !dir || !up || !out) {
+    setError("dvr_camera_orthographic: null argument");
+    return DVR_ERR_INVALID_ARGUMENT;
+  }
+  cameraBase(pos, dir, up, region, out);
+  out->type = DVR_CAMERA_ORTHOGRAPHIC;
+  const float3 d = v3(out->dir), u = v3(out->up), p = v3(out->pos);
+  const float3 du = hscale(hnormalize(hcross(d, u)), height * aspect);
+  const float3 dv = hscale(hnormalize(hcross(du, d)), height);
+  const float3 p00 = hsub(hsub(p, hscale(du, .5f)), hscale(dv, .5f));
+  st3(out->du, du);
+  st3(out->dv, dv);
+  st3(out->p00, p00);
+  out->aspect = aspect;
+  return DVR_OK;
+}
+
+// ---- transfer function discretisation ---------------------------------------------------------------
+
+namespace {
+struct Range1
+{
+  float lo, hi;
+};
+inline float rsize(Range1 r) { return r.hi - r.lo; }
+inline float rposition(float v, Range1 r)
+{
+  v = std::fmax(r.lo, std::fmin(v, r.hi));
+  return (v - r.lo) * (1.f / rsize(r));
+}
+inline bool rcontains(float v, Range1 r) { return v >= r.lo && v <= r.hi; }
+
+// colorMapHelpers.h:43-59: positions by repeated addition, first/last pinned, mapped into the range
+std::vector<float> linearPositions(size_t n, Range1 range)
+{
+  std::vector<float> p(n);
+  p.front() = 0.f;
+  p.back() = 1.f;
+  const float w = 1.f / (n - 1);
+  for (int i = 1; i < (int)p.size() - 1; i++)
+    p[i] = p[i - 1] + w;
+  for (auto &v : p)
+    v = v * rsize(range) + range.lo;
+  return p;
+}
+
+// colorMapHelpers.h:61-72 for `nch` interleaved channels
+void interpolated(const float *values, int nch, const std::vector<float> &positions, Range1 range, float pos,
+    float *out)
+{
+  const size_t n = positions.size();
+  for (size_t i = 0; i + 1 < n; i++) {
+    const Range1 r{rposition(positions[i], range), rposition(positions[i + 1], range)};
+    if (rcontains(pos, r)) {
+      const float a = rposition(pos, r);
+      for (int c = 0; c < nch; ++c)
+        out[c] = values[i * nch + c] * (1.f - a) + values[(i + 1) * nch + c] * a;
+      return;
+    }
+  }
+  const float *src = pos <= rposition(positions[0], range) ? values : values + (n - 1) * nch;
+  for (int c = 0; c < nch; ++c)
+    out[c] = src[c];
+}
+} // namespace
+
+int dvr_tf_discretize(const float *color, size_t nColor, int colorChannels, const float *opacity, size_t nOpacity,
+    const float uniformColor[4], float uniformOpacity, const float valueRange[2], float *outRgba)
+{
+  if (!outRgba || !valueRange || !uniformColor) {
+    setError("dvr_tf_discretize: null argument");
+    return DVR_ERR_INVALID_ARGUMENT;
+  }
+  if (color && (colorChannels != 3 && colorChannels != 4)) {
+    setError("dvr_tf_discretize: colorChannels must be 3 or 4");
+    return DVR_ERR_INVALID_ARGUMENT;
+  }
+  if ((color && nColor < 2) || (opacity && nOpacity < 2)) {
+    setError("dvr_tf_discretize: arrays need at least two entries");
+    return DVR_ERR_INVALID_ARGUMENT;
+  }
+  const Range1 range{valueRange[0], valueRange[1]};
+  std::vector<float> cpos, opos;
+  if (color)
+    cpos = linearPositions(nColor, range);
+  if (opacity)
+    opos = linearPositions(nOpacity, range);
+  for (size_t i = 0; i < DVR_TF_SIZE; i++) {
+    const float p = float(i) / (DVR_TF_SIZE - 1);
+    float c[4] = {uniformColor[0], uniformColor[1], uniformColor[2], uniformColor[3]};
+    if (color) {
+      if (colorChannels == 3) {
+        interpolated(color, 3, cpos, range, p, c);
+        c[3] = 1.f;
+      } else
+        interpolated(color, 4, cpos, range, p, c);
+    }
+    float o = uniformOpacity;
+    if (opacity)
+      interpolated(opacity, 1, opos, range, p, &o);
+    outRgba[4 * i + 0] = c[0];
+    outRgba[4 * i + 1] = c[1];
+    outRgba[4 * i + 2] = c[2];
+    outRgba[4 * i + 3] = c[3] * o;
+  }
+  return DVR_OK;
+}
+
+// ---- fields ------------------------------------------------------------------------------------------
+
+static size_t elementSize(int t)
+{
+  switch (t) {
+  case DVR_FLOAT32: return 4;
+  case DVR_UFIXED8:
+  case DVR_FIXED8: return 1;
+  case DVR_UFIXED16:
+  case DVR_FIXED16:
+  case DVR_FLOAT16: return 2;
+  case DVR_FLOAT64: return 8;
+  default: return 0;
+  }
+}
+
+static int createFieldImpl(const void *data, int dataIsDevice, int dataType, const uint32_t gdims[3],
+    uint32_t zBegin, uint32_t zEnd, const float origin[3], const float spacing[3], int filter, void *stream,
+    DvrField **out)
+{
+  if (!data || !gdims || !origin || !spacing || !out) {
+    setError("dvr_field_create: null argument");
+    return DVR_ERR_INVALID_ARGUMENT;
+  }
+  const size_t esz = elementSize(dataType);
+  if (esz == 0) {
+    setError("dvr_field_create: invalid data type (StructuredRegularField.cpp:45-60)");
+    return DVR_ERR_INVALID_ARGUMENT;
+  }
+  if (gdims[0] == 0 || gdims[1] == 0 || gdims[2] == 0 || zEnd > gdims[2] || zBegin >= zEnd) {
+    setError("dvr_field_create: bad dimensions / slab range");
+    return DVR_ERR_INVALID_ARGUMENT;
+  }
+  if (dvr_device_count() <= 0) {
+    setError("dvr_field_create: no CUDA device (this library has no CPU fallback)");
+    return DVR_ERR_NO_DEVICE;
+  }
+  cudaStream_t s = (cudaStream_t)stream;
+  const bool whole = zBegin == 0 && zEnd == gdims[2];
+  const uint32_t zTexBegin = zBegin > 0 ? zBegin - 1 : 0;
+  const uint32_t zTexEnd = zEnd < gdims[2] ? zEnd + 1 : gdims[2]; // exclusive; one ghost slice each side
+  const uint32_t texDepth = zTexEnd - zTexBegin;
+  const size_t nvox = (size_t)gdims[0] * gdims[1] * texDepth;
+
+  auto *f = new DvrField();
+  cudaGetDevice(&f->device);
+
+  // FLOAT64 is not a texturable format: convert to f32 first (the reference would fail here)
+  const void *src = data;
+  float *converted = nullptr;
+  int texType = dataType;
+  size_t texEsz = esz;
+  if (dataType == DVR_FLOAT64) {
+    double *staged = nullptr;
+    const double *dsrc = (const double *)data;
+    if (!dataIsDevice) {
+      if (cudaMalloc(&staged, nvox * 8) != cudaSuccess) {
+        delete f;
+        return cudaFail(cudaGetLastError(), "cudaMalloc(f64 staging)");
+      }
+      cudaMemcpyAsync(staged, data, nvox * 8, cudaMemcpyHostToDevice, s);
+      dsrc = staged;
+    }
+    if (cudaMalloc(&converted, nvox * 4) != cudaSuccess) {
+      cudaFree(staged);
+      delete f;
+      return cudaFail(cudaGetLastError(), "cudaMalloc(f64->f32)");
+    }
+    launchConvertToFloat(dsrc, DVR_FLOAT64, converted, nvox, s);
+    cudaStreamSynchronize(s);
+    cudaFree(staged);
+    src = converted;
+    dataIsDevice = 1;
+    texType = DVR_FLOAT32;
+    texEsz = 4;
+  }
+
+  cudaChannelFormatKind kind = cudaChannelFormatKindFloat;
+  if (texType == DVR_UFIXED8 || texType == DVR_UFIXED16)
+    kind = cudaChannelFormatKindUnsigned;
+  else if (texType == DVR_FIXED8 || texType == DVR_FIXED16)
+    kind = cudaChannelFormatKindSigned;
+  const cudaChannelFormatDesc desc = cudaCreateChannelDesc((int)texEsz * 8, 0, 0, 0, kind);
+  cudaError_t e = cudaMalloc3DArray(&f->array, &desc, make_cudaExtent(gdims[0], gdims[1], texDepth));
+  if (e != cudaSuccess) {
+    cudaFree(converted);
+    delete f;
+    return cudaFail(e, "cudaMalloc3DArray");
+  }
+  cudaMemcpy3DParms cp;
+  std::memset(&cp, 0, sizeof(cp));
+  cp.srcPtr = make_cudaPitchedPtr(const_cast<void *>(src), gdims[0] * texEsz, gdims[0], gdims[1]);
+  cp.dstArray = f->array;
+  cp.extent = make_cudaExtent(gdims[0], gdims[1], texDepth);
+  cp.kind = dataIsDevice ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
+  e = cudaMemcpy3DAsync(&cp, s);
+  if (e == cudaSuccess && (!dataIsDevice || converted))
+    e = cudaStreamSynchronize(s); // the caller's host buffer / our temporary may go away
+  cudaFree(converted);
+  if (e != cudaSuccess) {
+    cudaFreeArray(f->array);
+    delete f;
+    return cudaFail(e, "cudaMemcpy3D");
+  }
+  f->voxelBytes = nvox * texEsz;
+
+  cudaResourceDesc rd;
+  std::memset(&rd, 0, sizeof(rd));
+  rd.resType = cudaResourceTypeArray;
+  rd.res.array.array = f->array;
+  const bool isFloat = kind == cudaChannelFormatKindFloat;
+  cudaTextureDesc td;
+  std::memset(&td, 0, sizeof(td));
+  td.addressMode[0] = td.addressMode[1] = td.addressMode[2] = cudaAddressModeClamp;
+  td.filterMode = filter == DVR_FILTER_NEAREST ? cudaFilterModePoint : cudaFilterModeLinear;
+  td.readMode = isFloat ? cudaReadModeElementType : cudaReadModeNormalizedFloat;
+  td.normalizedCoords = 1;
+  e = cudaCreateTextureObject(&f->tex, &rd, &td, nullptr);
+  if (e == cudaSuccess) {
+    td.filterMode = cudaFilterModePoint;
+    td.normalizedCoords = 0;
+    e = cudaCreateTextureObject(&f->pointTex, &rd, &td, nullptr);
+  }
+  if (e != cudaSuccess) {
+    dvr_field_destroy(f);
+    return cudaFail(e, "cudaCreateTextureObject");
+  }
+
+  FieldDev &d = f->dev;
+  d.tex = f->tex;
+  d.origin = v3(origin);
+  d.spacing = v3(spacing);
+  d.dims = make_int3((int)gdims[0], (int)gdims[1], (int)gdims[2]);
+  // 1 / (spacing * dims), StructuredRegularField.cpp:188-189
+  d.invSpacing = make_float3(1.f / (spacing[0] * (float)gdims[0]), 1.f / (spacing[1] * (float)gdims[1]),
+      1.f / (spacing[2] * (float)gdims[2]));
+  d.boundsLo = d.origin;
+  d.boundsHi = make_float3(origin[0] + ((float)gdims[0] - 1.f) * spacing[0],
+      origin[1] + ((float)gdims[1] - 1.f) * spacing[1], origin[2] + ((float)gdims[2] - 1.f) * spacing[2]);
+  d.stepSize = std::fmin(std::fmin(spacing[0] / 2.f, spacing[1] / 2.f), spacing[2] / 2.f);
+  d.zOwnBegin = whole ? 0 : (int)zBegin;
+  d.zOwnEnd = whole ? (int)gdims[2] : (int)zEnd;
+  d.zTexBegin = (int)zTexBegin;
+  d.texDepth = (int)texDepth;
+  d.gridDims = make_int3((int)((gdims[0] + 15) / 16), (int)((gdims[1] + 15) / 16), (int)((gdims[2] + 15) / 16));
+  f->nCells = (size_t)d.gridDims.x * d.gridDims.y * d.gridDims.z;
+  e = cudaMalloc(&f->ranges, f->nCells * sizeof(float2));
+  if (e != cudaSuccess) {
+    dvr_field_destroy(f);
+    return cudaFail(e, "cudaMalloc(macrocell ranges)");
+  }
+  d.valueRanges = f->ranges;
+  const int rc = dvr_field_build_macrocells(f, stream);
+  if (rc != DVR_OK) {
+    dvr_field_destroy(f);
+    return rc;
+  }
+  *out = f;
+  return DVR_OK;
+}
+
+int dvr_field_create_structured(const void *data, int dataIsDevice, int dataType, const uint32_t dims[3],
+    const float origin[3], const float spacing[3], int filter, void *stream, DvrField **out)
+{
+  if (!dims) {
+    setError("dvr_field_create_structured: null dims");
+    return DVR_ERR_INVALID_ARGUMENT;
+  }
+  return createFieldImpl(data, dataIsDevice, dataType, dims, 0, dims[2], origin, spacing, filter, stream, out);
+}
+
+int dvr_field_create_structured_slab(const void *data, int dataIsDevice, int dataType, const uint32_t globalDims[3],
+    uint32_t zBegin, uint32_t zEnd, const float origin[3], const float spacing[3], int filter, void *stream,
+    DvrField **out)
+{
+  if (!globalDims) {
+    setError("dvr_field_create_structured_slab: null dims");
+    return DVR_ERR_INVALID_ARGUMENT;
+  }
+  return createFieldImpl(data, dataIsDevice, dataType, globalDims, zBegin, zEnd, origin, spacing, filter, stream, out);
+}
+
+int dvr_field_destroy(DvrField *f)
+{
+  if (!f)
+    return DVR_OK;
+  if (f->tex) cudaDestroyTextureObject(f->tex);
+  if (f->pointTex) cudaDestroyTextureObject(f->pointTex);
+  if (f->array) cudaFreeArray(f->array);
+  if (f->ranges) cudaFree(f->ranges);
+  delete f;
+  return DVR_OK;
+}
+
+int dvr_field_bounds(const DvrField *f, float lower[3], float upper[3])
+{
+  if (!f || !lower || !upper) {
+    setError("dvr_field_bounds: null argument");
+    return DVR_ERR_INVALID_ARGUMENT;
+  }
+  st3(lower, f->dev.boundsLo);
+  st3(upper, f->dev.boundsHi);
+  return DVR_OK;
+}
+
+int dvr_field_step_size(const DvrField *f, float *stepSize)
+{
+  if (!f || !stepSize) {
+    setError("dvr_field_step_size: null argument");
+    return DVR_ERR_INVALID_ARGUMENT;
+  }
+  *stepSize = f->dev.stepSize;
+  return DVR_OK;
+}
+
+int dvr_field_device_bytes(const DvrField *f, size_t *bytes)
+{
+  if (!f || !bytes) {
+    setError("dvr_field_device_bytes: null argument");
+    return DVR_ERR_INVALID_ARGUMENT;
+  }
+  *bytes = f->voxelBytes + f->nCells * sizeof(float2);
+  return DVR_OK;
+}
+
+int dvr_field_build_macrocells(DvrField *f, void *stream)
+{
+  if (!f) {
+    setError("dvr_field_build_macrocells: null field");
+    return DVR_ERR_INVALID_ARGUMENT;
+  }
+  return launchMacrocellBuild(
+      f->pointTex, f->dev.dims, f->dev.zTexBegin, f->dev.texDepth, f->dev.gridDims, f->ranges, (cudaStream_t)stream);
+}
+
+int dvr_field_macrocells(const DvrField *f, uint32_t gridDims[3], const float **valueRangesDev)
+{
+  if (!f) {
+    setError("dvr_field_macrocells: null field");
+    return DVR_ERR_INVALID_ARGUMENT;
+  }
+  if (gridDims) {
+    gridDims[0] = f->dev.gridDims.x;
+    gridDims[1] = f->dev.gridDims.y;
+    gridDims[2] = f->dev.gridDims.z;
+  }
+  if (valueRangesDev)
+    *valueRangesDev = (const float *)f->ranges;
+  return DVR_OK;
+}
+
+int dvr_field_value_range(const DvrField *f, void *stream, float range[2])
+{
+  if (!f || !range) {
+    setError("dvr_field_value_range: null argument");
+    return DVR_ERR_INVALID_ARGUMENT;
+  }
+  float2 *d = nullptr;
+  DVR_CUDA(cudaMalloc(&d, sizeof(float2)));
+  int rc = launchRangeReduce(f->ranges, f->nCells, d, (cudaStream_t)stream);
+  float2 h = make_float2(0.f, 1.f);
+  if (rc == DVR_OK) {
+    cudaError_t e = cudaMemcpyAsync(&h, d, sizeof(h), cudaMemcpyDeviceToHost, (cudaStream_t)stream);
+    if (e == cudaSuccess)
+      e = cudaStreamSynchronize((cudaStream_t)stream);
+    if (e != cudaSuccess)
+      rc = cudaFail(e, "dvr_field_value_range copy");
+  }
+  cudaFree(d);
+  range[0] = h.x;
+  range[1] = h.y;
+  return rc;
+}
+
+// ---- volumes -----------------------------------------------------------------------------------------
+
+int dvr_volume_update(DvrVolume *v, const float *tfRgba, const float valueRange[2], float unitDistance, uint32_t id,
+    void *stream)
+{
+  if (!v || !tfRgba || !valueRange) {
+    setError("dvr_volume_update: null argument");
+    return DVR_ERR_INVALID_ARGUMENT;
+  }
+  cudaStream_t s = (cudaStream_t)stream;
+  DVR_CUDA(cudaMemcpyAsync(v->tf, tfRgba, DVR_TF_SIZE * sizeof(float4), cudaMemcpyHostToDevice, s));
+  DVR_CUDA(cudaStreamSynchronize(s)); // tfRgba is caller-owned pageable memory
+  v->vrLo = valueRange[0];
+  v->vrHi = valueRange[1];
+  v->oneOverUnitDistance = 1.0f / unitDistance;
+  v->id = id;
+  return launchMajorants(v->field->ranges, v->field->nCells, v->tf, v->vrLo, v->vrHi, v->maxOpacities, s);
+}
+
+int dvr_volume_create(const DvrField *field, const float *tfRgba, const float valueRange[2], float unitDistance,
+    uint32_t id, void *stream, DvrVolume **out)
+{
+  if (!field || !tfRgba || !valueRange || !out) {
+    setError("dvr_volume_create: null argument (missing parameter 'value' on transferFunction1D?)");
+    return DVR_ERR_INVALID_ARGUMENT;
+  }
+  auto *v = new DvrVolume();
+  v->field = field;
+  cudaError_t e = cudaMalloc(&v->tf, DVR_TF_SIZE * sizeof(float4));
+  if (e == cudaSuccess)
+    e = cudaMalloc(&v->maxOpacities, field->nCells * sizeof(float));
+  if (e != cudaSuccess) {
+    dvr_volume_destroy(v);
+    return cudaFail(e, "cudaMalloc(volume)");
+  }
+  const int rc = dvr_volume_update(v, tfRgba, valueRange, unitDistance, id, stream);
+  if (rc != DVR_OK) {
+    dvr_volume_destroy(v);
+    return rc;
+  }
+  *out = v;
+  return DVR_OK;
+}
+
+int dvr_volume_destroy(DvrVolume *v)
+{
+  if (!v)
+    return DVR_OK;
+  if (v->tf) cudaFree(v->tf);
+  if (v->maxOpacities) cudaFree(v->maxOpacities);
+  delete v;
+  return DVR_OK;
+}
+
+int dvr_volume_majorants(const DvrVolume *v, const float **maxOpacitiesDev)
+{
+  if (!v || !maxOpacitiesDev) {
+    setError("dvr_volume_majorants: null argument");
+    return DVR_ERR_INVALID_ARGUMENT;
+  }
+  *maxOpacitiesDev = v->maxOpacities;
+  return DVR_OK;
+}
+
+// ---- render ------------------------------------------------------------------------------------------
+
+static void fillCamera(const DvrCamera *c, CameraDev &d)
+{
+  d.type = c->type;
+  d.region = make_float4(c->region[0], c->region[1], c->region[2], c->region[3]);
+  d.pos = v3(c->pos);
+  d.dir = v3(c->dir);
+  d.du = v3(c->du);
+  d.dv = v3(c->dv);
+  d.p00 = v3(c->p00);
+  d.scaledAperture = c->scaledAperture;
+  d.aspect = c->aspect;
+}
+
+static void fillInstance(const DvrVolumeInstance &in, InstanceDev &d)
+{
+  const DvrVolume *v = in.volume;
+  d.v.f = v->field->dev;
+  d.v.tf = v->tf;
+  d.v.vrLower = v->vrLo;
+  d.v.vrUpper = v->vrHi;
+  d.v.oneOverUnitDistance = v->oneOverUnitDistance;
+  d.v.id = v->id;
+  d.v.maxOpacities = v->maxOpacities;
+  static const float ident[12] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0};
+  std::memcpy(d.xfm, in.worldToObject, sizeof(d.xfm));
+  d.instId = in.instanceId;
+  d.identity = std::memcmp(in.worldToObject, ident, sizeof(ident)) == 0 ? 1u : 0u;
+}
+
+static int renderImpl(const DvrFrameParams *p, const DvrCamera *camera, const DvrVolumeInstance *instances,
+    uint32_t nInstances, const DvrFrameBuffers *b, DvrRenderStats *statsDev, bool stats, void *stream)
+{
+  if (!p || !camera || !b || (nInstances && !instances)) {
+    setError("dvr_render: null argument");
+    return DVR_ERR_INVALID_ARGUMENT;
+  }
+  if (!b->colorAccumulation || !b->outColor) {
+    setError("dvr_render: colorAccumulation and outColor buffers are required");
+    return DVR_ERR_INVALID_ARGUMENT;
+  }
+  if (p->width == 0 || p->height == 0 || p->numIterations < 1 || p->format < 0 || p->format > 2
+      || p->checkerboardID > 3) {
+    setError("dvr_render: invalid frame parameters");
+    return DVR_ERR_INVALID_ARGUMENT;
+  }
+  for (uint32_t i = 0; i < nInstances; ++i)
+    if (!instances[i].volume || !instances[i].volume->field) {
+      setError("dvr_render: instance without a valid volume");
+      return DVR_ERR_INVALID_ARGUMENT;
+    }
+  if (dvr_device_count() <= 0) {
+    setError("dvr_render: no CUDA device (this library has no CPU fallback)");
+    return DVR_ERR_NO_DEVICE;
+  }
+  cudaStream_t s = (cudaStream_t)stream;
+
+  FrameLaunch L;
+  std::memset(&L, 0, sizeof(L));
+  L.width = p->width;
+  L.height = p->height;
+  L.invW = 1.f / (float)p->width; // Frame.cu:112
+  L.invH = 1.f / (float)p->height;
+  L.format = p->format;
+  L.integrator = p->integrator;
+  L.frameID = p->frameID;
+  L.checkerboardID = p->checkerboardID;
+  L.numIterations = p->checkerboardID >= 0 ? 1 : p->numIterations; // Renderer.cpp:168-169
+  L.invSamplingRate = p->inverseVolumeSamplingRate;
+  L.background = make_float4(p->background[0], p->background[1], p->background[2], p->background[3]);
+  L.tileRank = p->tileRanks > 1 ? p->tileRank : 0;
+  L.tileRanks = p->tileRanks > 1 ? p->tileRanks : 1;
+  L.launchW = p->checkerboardID >= 0 ? (p->width + 1) / 2 : p->width; // Frame.cu:287-288
+  L.launchH = p->checkerboardID >= 0 ? (p->height + 1) / 2 : p->height;
+  L.tilesX = (L.launchW + kTileW - 1) / kTileW;
+  L.tilesY = (L.launchH + kTileH - 1) / kTileH;
+  fillCamera(camera, L.cam);
+  L.fb.accum = (float4 *)b->colorAccumulation;
+  L.fb.outU32 = (uint32_t *)b->outColor;
+  L.fb.outF32 = (float4 *)b->outColor;
+  L.fb.depth = b->depth;
+  L.fb.primId = b->primId;
+  L.fb.objId = b->objId;
+  L.fb.instId = b->instId;
+  L.fb.albedo = b->albedo;
+  L.fb.normal = b->normal;
+  L.nInst = (int)nInstances;
+
+  bool skip = p->useMacrocellSkipping != 0;
+  if (nInstances <= (uint32_t)kMaxInlineInstances) {
+    for (uint32_t i = 0; i < nInstances; ++i)
+      fillInstance(instances[i], L.inl[i]);
+  } else {
+    std::vector<InstanceDev> tmp(nInstances);
+    for (uint32_t i = 0; i < nInstances; ++i)
+      fillInstance(instances[i], tmp[i]);
+    InstanceDev *ext = nullptr;
+    DVR_CUDA(cudaMallocAsync(&ext, nInstances * sizeof(InstanceDev), s));
+    DVR_CUDA(cudaMemcpyAsync(ext, tmp.data(), nInstances * sizeof(InstanceDev), cudaMemcpyHostToDevice, s));
+    DVR_CUDA(cudaStreamSynchronize(s));
+    L.ext = ext;
+  }
+  L.sched = acquireSchedSlot();
+  if (!L.sched) {
+    setError("dvr_render: could not allocate scheduler scratch");
+    return DVR_ERR_CUDA;
+  }
+
+  unsigned int *bitmap = nullptr;
+  size_t nWords = 0;
+  if (stats) {
+    if (!statsDev) {
+      setError("dvr_render_instrumented: statsDev is null");
+      return DVR_ERR_INVALID_ARGUMENT;
+    }
+    DVR_CUDA(cudaMemsetAsync(statsDev, 0, sizeof(DvrRenderStats), s));
+    if (nInstances >= 1) {
+      const size_t nCells = instances[0].volume->field->nCells;
+      nWords = (nCells + 31) / 32;
+      DVR_CUDA(cudaMallocAsync(&bitmap, nWords * 4, s));
+      DVR_CUDA(cudaMemsetAsync(bitmap, 0, nWords * 4, s));
+    }
+    L.stats = statsDev;
+    L.cellBitmap = bitmap;
+  }
+
+  int rc = DVR_OK;
+  if (nInstances == 0) {
+    // a world without volumes still clears to the background (Raycast_ptx.cu:139-166 with no hit)
+    L.nInst = 0;
+    rc = launchFrame(L, false, stats, s);
+  } else
+    rc = launchFrame(L, skip, stats, s);
+
+  if (stats && bitmap) {
+    if (rc == DVR_OK)
+      rc = launchPopcount(bitmap, nWords, &statsDev->macrocellsTouched, s);
+    cudaFreeAsync(bitmap, s);
+  }
+  if (L.ext)
+    cudaFreeAsync((void *)L.ext, s);
+  return rc;
+}
+
+int dvr_render(const DvrFrameParams *params, const DvrCamera *camera, const DvrVolumeInstance *instances,
+    uint32_t nInstances, const DvrFrameBuffers *buffers, void *stream)
+{
+  return renderImpl(params, camera, instances, nInstances, buffers, nullptr, false, stream);
+}
+
+int dvr_render_instrumented(const DvrFrameParams *params, const DvrCamera *camera,
+    const DvrVolumeInstance *instances, uint32_t nInstances, const DvrFrameBuffers *buffers,
+    DvrRenderStats *statsDev, void *stream)
+{
+  return renderImpl(params, camera, instances, nInstances, buffers, statsDev, true, stream);
+}
+
+// ---- sort-last -------------------------------------------------------------------------------------------
+
+int dvr_render_partial(const DvrFrameParams *p, const DvrCamera *camera, const DvrVolumeInstance *instance,
+    float *partialRgba, float *partialDepth, void *stream)
+{
+  if (!p || !camera || !instance || !instance->volume || !partialRgba || !partialDepth) {
+    setError("dvr_render_partial: null argument");
+    return DVR_ERR_INVALID_ARGUMENT;
+  }
+  if (p->numIterations != 1 || p->checkerboardID >= 0) {
+    setError("dvr_render_partial: needs numIterations == 1 and no checkerboarding");
+    return DVR_ERR_UNSUPPORTED;
+  }
+  if (dvr_device_count() <= 0) {
+    setError("dvr_render_partial: no CUDA device (this library has no CPU fallback)");
+    return DVR_ERR_NO_DEVICE;
+  }
+  PartialLaunch L;
+  std::memset(&L, 0, sizeof(L));
+  L.width = p->width;
+  L.height = p->height;
+  L.invW = 1.f / (float)p->width;
+  L.invH = 1.f / (float)p->height;
+  L.integrator = p->integrator;
+  L.frameID = p->frameID;
+  L.invSamplingRate = p->inverseVolumeSamplingRate;
+  L.tilesX = (p->width + kTileW - 1) / kTileW;
+  L.tilesY = (p->height + kTileH - 1) / kTileH;
+  fillCamera(camera, L.cam);
+  fillInstance(*instance, L.inst);
+  L.partialRgba = (float4 *)partialRgba;
+  L.partialDepth = partialDepth;
+  L.skip = p->useMacrocellSkipping;
+  L.sched = acquireSchedSlot();
+  if (!L.sched) {
+    setError("dvr_render_partial: could not allocate scheduler scratch");
+    return DVR_ERR_CUDA;
+  }
+  return launchPartial(L, (cudaStream_t)stream);
+}
+
+int dvr_composite_over(float *frontRgba, float *frontDepth, const float *backRgba, const float *backDepth,
+    size_t pixelBegin, size_t pixelEnd, int backIsInFront, void *stream)
+{
+  if (!frontRgba || !backRgba) {
+    setError("dvr_composite_over: null argument");
+    return DVR_ERR_INVALID_ARGUMENT;
+  }
+  return launchCompositeOver((float4 *)frontRgba, frontDepth, (const float4 *)backRgba, backDepth, pixelBegin,
+      pixelEnd, backIsInFront != 0, (cudaStream_t)stream);
+}
+
+int dvr_resolve(const DvrFrameParams *p, const float *partialRgba, const float *partialDepth, uint32_t objId,
+    uint32_t instId, const DvrFrameBuffers *b, size_t pixelBegin, size_t pixelEnd, void *stream)
+{
+  if (!p || !partialRgba || !b || !b->colorAccumulation || !b->outColor) {
+    setError("dvr_resolve: null argument");
+    return DVR_ERR_INVALID_ARGUMENT;
+  }
+  ResolveLaunch R;
+  std::memset(&R, 0, sizeof(R));
+  R.width = p->width;
+  R.height = p->height;
+  R.format = p->format;
+  R.frameID = p->frameID;
+  R.background = make_float4(p->background[0], p->background[1], p->background[2], p->background[3]);
+  R.fb.accum = (float4 *)b->colorAccumulation;
+  R.fb.outU32 = (uint32_t *)b->outColor;
+  R.fb.outF32 = (float4 *)b->outColor;
+  R.fb.depth = b->depth;
+  R.fb.primId = b->primId;
+  R.fb.objId = b->objId;
+  R.fb.instId = b->instId;
+  R.fb.albedo = b->albedo;
+  R.fb.normal = b->normal;
+  R.partialRgba = (const float4 *)partialRgba;
+  R.partialDepth = partialDepth;
+  R.objId = objId;
+  R.instId = instId;
+  R.pixelBegin = pixelBegin;
+  R.pixelEnd = pixelEnd > (size_t)p->width * p->height ? (size_t)p->width * p->height : pixelEnd;
+  return launchResolve(R, (cudaStream_t)stream);
+}
+
+int dvr_scale_vec3(const float *accumVec3, float *outVec3, size_t nPixels, float scale, void *stream)
+{
+  if (!accumVec3 || !outVec3) {
+    setError("dvr_scale_vec3: null argument");
+    return DVR_ERR_INVALID_ARGUMENT;
+  }
+  return launchScaleVec3(accumVec3, outVec3, nPixels, scale, (cudaStream_t)stream);
+}
+
+} // extern "C"

@@ -1,0 +1,95 @@
+// dvr_internal.h — host-side declarations shared by the translation units of libdvr_b200.so
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <string>
+
+#include "../../include/dvr_b200.h"
+#include "dvr_device.cuh"
+
+namespace dvr {
+
+constexpr int kMaxInlineInstances = 4;
+constexpr int kTileW = 8; // one warp renders an 8x4 pixel tile
+constexpr int kTileH = 4;
+constexpr int kBlockThreads = 256;
+
+// kernel parameter block of the frame kernel (passed by value as __grid_constant__)
+struct FrameLaunch
+{
+  uint32_t width, height;
+  float invW, invH;
+  int format, integrator, frameID, checkerboardID, numIterations;
+  float invSamplingRate;
+  float4 background;
+  uint32_t tileRank, tileRanks;
+  uint32_t launchW, launchH; // pixel-sample grid actually launched (half size when checkerboarding)
+  uint32_t tilesX, tilesY;
+  CameraDev cam;
+  BuffersDev fb;
+  int nInst;
+  InstanceDev inl[kMaxInlineInstances];
+  const InstanceDev *ext; // used when nInst > kMaxInlineInstances
+  unsigned int *sched;    // [0] next tile, [1] warps finished
+  DvrRenderStats *stats;
+  unsigned int *cellBitmap;
+};
+
+struct PartialLaunch
+{
+  uint32_t width, height;
+  float invW, invH;
+  int integrator, frameID;
+  float invSamplingRate;
+  uint32_t tilesX, tilesY;
+  CameraDev cam;
+  InstanceDev inst;
+  float4 *partialRgba;
+  float *partialDepth;
+  unsigned int *sched;
+  int skip;
+};
+
+struct ResolveLaunch
+{
+  uint32_t width, height;
+  int format, frameID;
+  float4 background;
+  BuffersDev fb;
+  const float4 *partialRgba;
+  const float *partialDepth;
+  uint32_t objId, instId;
+  size_t pixelBegin, pixelEnd;
+};
+
+// error plumbing -----------------------------------------------------------------------------
+void setError(const std::string &msg);
+int cudaFail(cudaError_t e, const char *what);
+#define DVR_CUDA(call)                                                                                    \
+  do {                                                                                                    \
+    cudaError_t _e = (call);                                                                              \
+    if (_e != cudaSuccess)                                                                                \
+      return ::dvr::cudaFail(_e, #call);                                                                  \
+  } while (0)
+
+void countLaunch(unsigned n = 1);
+unsigned int *acquireSchedSlot(); // device pair of counters, zero on entry to every launch
+int smCount();
+
+// launchers (defined in the .cu files) --------------------------------------------------------
+int launchFrame(const FrameLaunch &p, bool skip, bool stats, cudaStream_t s);
+int launchPartial(const PartialLaunch &p, cudaStream_t s);
+int launchResolve(const ResolveLaunch &p, cudaStream_t s);
+int launchCompositeOver(float4 *front, float *frontDepth, const float4 *back, const float *backDepth,
+    size_t begin, size_t end, bool backIsInFront, cudaStream_t s);
+int launchScaleVec3(const float *in, float *out, size_t n, float scale, cudaStream_t s);
+int launchMacrocellBuild(cudaTextureObject_t pointTex, int3 dims, int zTexBegin, int texDepth, int3 gridDims,
+    float2 *ranges, cudaStream_t s);
+int launchMajorants(const float2 *ranges, size_t nCells, const float4 *tf, float vrLo, float vrHi,
+    float *maxOpacities, cudaStream_t s);
+int launchRangeReduce(const float2 *ranges, size_t nCells, float2 *out, cudaStream_t s);
+int launchPopcount(const unsigned int *bitmap, size_t nWords, unsigned long long *out, cudaStream_t s);
+int launchConvertToFloat(const void *src, int dataType, float *dst, size_t n, cudaStream_t s);
+
+} // namespace dvr

@@ -1,0 +1,439 @@
+// dvr_kernels.cu — frame kernel K1 (ray generation + march + background + accumulate/tonemap/encode),
+// the sort-last partial kernel, the resolve kernel K3 and the `over` compositing kernel.
+// Target: sm_100a only.  See DESIGN.md for the layout / scheduling rationale.
+#include "dvr_internal.h"
+#include "dvr_march.cuh"
+
+namespace dvr {
+
+// ----------------------------------------------------------------------------------------------
+// warp-granular dynamic tile scheduler.  sched[0] = next tile, sched[1] = warps finished.  The last
+// warp to leave re-arms both counters, so no memset is needed between frames.
+// ----------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t nextTile(unsigned int *sched, int lane)
+{
+  uint32_t t = 0;
+  if (lane == 0)
+    t = atomicAdd(&sched[0], 1u);
+  return __shfl_sync(0xffffffffu, t, 0);
+}
+
+__device__ __forceinline__ void retireWarp(unsigned int *sched, int lane)
+{
+  if (lane == 0) {
+    const unsigned int totalWarps = gridDim.x * (blockDim.x >> 5);
+    __threadfence();
+    const unsigned int done = atomicAdd(&sched[1], 1u);
+    if (done == totalWarps - 1u) {
+      sched[0] = 0u;
+      sched[1] = 0u;
+      __threadfence();
+    }
+  }
+}
+
+__device__ __forceinline__ unsigned long long warpSum(unsigned long long v)
+{
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1)
+    v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// accumResults, gpu/gpu_util.h:393-443, for one pixel-sample.  `init` replaces the cleared
+// buffers of Frame::newFrame (Frame.cu:609-647): 0 + x and min(FLT_MAX, x) are written directly.
+__device__ __forceinline__ void accumResults(const FrameLaunch &P, uint32_t px, uint32_t py, float4 color,
+    float depth, float3 albedo, float3 normal, uint32_t primID, uint32_t objID, uint32_t instID,
+    int frameIDOffset, bool init)
+{
+  const BuffersDev &fb = P.fb;
+  const uint32_t idx = px + py * P.width;
+  const int frameID = P.frameID + frameIDOffset;
+
+  // tonemap: v / (1 + max(0, compMax(v)))
+  const float m = 1.0f + fmaxf(0.0f, fmaxf(fmaxf(color.x, color.y), color.z));
+  const float4 tm = make_float4(color.x / m, color.y / m, color.z / m, color.w);
+
+  float4 acc;
+  if (init) {
+    acc = tm;
+  } else {
+    acc = fb.accum[idx];
+    acc.x += tm.x;
+    acc.y += tm.y;
+    acc.z += tm.z;
+    acc.w += tm.w;
+  }
+  fb.accum[idx] = acc;
+
+  if (fb.albedo) {
+    float *a = fb.albedo + 3 * (size_t)idx;
+    if (init) {
+      a[0] = albedo.x; a[1] = albedo.y; a[2] = albedo.z;
+    } else {
+      a[0] += albedo.x; a[1] += albedo.y; a[2] += albedo.z;
+    }
+  }
+  if (fb.normal) {
+    float *n = fb.normal + 3 * (size_t)idx;
+    if (init) {
+      n[0] = normal.x; n[1] = normal.y; n[2] = normal.z;
+    } else {
+      n[0] += normal.x; n[1] += normal.y; n[2] += normal.z;
+    }
+  }
+
+  bool closer = true;
+  if (fb.depth) {
+    const float prev = init ? FLT_MAX : fb.depth[idx];
+    closer = depth < prev;
+    if (closer)
+      fb.depth[idx] = depth;
+    else if (init)
+      fb.depth[idx] = prev;
+  }
+  if (closer) {
+    if (fb.primId) fb.primId[idx] = primID;
+    if (fb.objId) fb.objId[idx] = objID;
+    if (fb.instId) fb.instId[idx] = instID;
+  } else if (init) {
+    if (fb.primId) fb.primId[idx] = 0u;
+    if (fb.objId) fb.objId[idx] = 0u;
+    if (fb.instId) fb.instId[idx] = 0u;
+  }
+
+  writeOutputColor(fb, P.format, acc, idx, frameID);
+
+  // first checkerboard pass: replicate the colour into the three not-yet-rendered neighbours
+  // (gpu_util.h:424-442) and initialise their accumulation state for the passes that follow
+  if (P.checkerboardID == 0 && frameID == 0) {
+#pragma unroll
+    for (int n = 1; n < 4; ++n) {
+      const uint32_t ax = px + (n & 1), ay = py + (n >> 1);
+      if (ax >= P.width || ay >= P.height)
+        continue;
+      const uint32_t aidx = ax + ay * P.width;
+      writeOutputColor(fb, P.format, acc, aidx, frameID);
+      if (init) {
+        fb.accum[aidx] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (fb.depth) fb.depth[aidx] = FLT_MAX;
+        if (fb.primId) fb.primId[aidx] = 0u;
+        if (fb.objId) fb.objId[aidx] = 0u;
+        if (fb.instId) fb.instId[aidx] = 0u;
+        if (fb.albedo) { float *a = fb.albedo + 3 * (size_t)aidx; a[0] = a[1] = a[2] = 0.f; }
+        if (fb.normal) { float *a = fb.normal + 3 * (size_t)aidx; a[0] = a[1] = a[2] = 0.f; }
+      }
+    }
+  }
+}
+
+struct TfSelectShared
+{
+  const float4 *smem;
+  const InstanceDev *inst;
+  __device__ __forceinline__ const float4 *operator()(int i) const
+  {
+    return i < kMaxInlineInstances ? smem + i * DVR_TF_SIZE : inst[i].v.tf;
+  }
+};
+struct TfSelectSingle
+{
+  const float4 *smem;
+  __device__ __forceinline__ const float4 *operator()(int) const { return smem; }
+};
+
+// ----------------------------------------------------------------------------------------------
+// K1: one frame.  Persistent CTAs; every warp pulls 8x4-pixel tiles from a global counter.
+// ----------------------------------------------------------------------------------------------
+template <bool SKIP, bool STATS, bool SINGLE>
+__global__ void __launch_bounds__(kBlockThreads, 2) dvrFrameKernel(const __grid_constant__ FrameLaunch P)
+{
+  __shared__ float4 s_tf[(SINGLE ? 1 : kMaxInlineInstances) * DVR_TF_SIZE];
+
+  const int lane = threadIdx.x & 31;
+  const InstanceDev *inst = (P.nInst <= kMaxInlineInstances) ? P.inl : P.ext;
+  const int nInst = SINGLE ? 1 : P.nInst;
+
+  // stage the transfer-function tables (4 KiB each) once per CTA
+  {
+    const int nTab = SINGLE ? 1 : min(P.nInst, kMaxInlineInstances);
+    for (int i = threadIdx.x; i < nTab * DVR_TF_SIZE; i += blockDim.x)
+      s_tf[i] = __ldg(&inst[i / DVR_TF_SIZE].v.tf[i % DVR_TF_SIZE]);
+    __syncthreads();
+  }
+
+  MarchStats st{0ull, 0ull};
+  unsigned long long raysHit = 0ull;
+  const uint32_t nTiles = P.tilesX * P.tilesY;
+  const bool centered = P.integrator == DVR_INTEGRATOR_RAYCAST;
+  const bool initFrame = P.frameID == 0 && P.checkerboardID <= 0;
+
+  for (uint32_t tile = nextTile(P.sched, lane); tile < nTiles; tile = nextTile(P.sched, lane)) {
+    const uint32_t tyIdx = tile / P.tilesX, txIdx = tile - tyIdx * P.tilesX;
+    if (P.tileRanks > 1u && (tyIdx % P.tileRanks) != P.tileRank)
+      continue;
+    const uint32_t lx = txIdx * kTileW + (lane & 7), ly = tyIdx * kTileH + (lane >> 3);
+    if (lx >= P.launchW || ly >= P.launchH)
+      continue;
+    uint32_t px = lx, py = ly;
+    if (P.checkerboardID >= 0) { // createScreenSample.h:38-46
+      px = lx * 2u + (uint32_t)(P.checkerboardID & 1);
+      py = ly * 2u + (uint32_t)((P.checkerboardID >> 1) & 1);
+    }
+    if (px >= P.width || py >= P.height)
+      continue;
+
+    Philox rng;
+    rng.init((unsigned long long)(int)(py * P.width + px), (unsigned long long)P.frameID * 512ull);
+
+    for (int it = 0; it < P.numIterations; ++it) {
+      // makePrimaryRay, cameraCreateRay.h:74-81
+      const float4 r = rng.uniform4();
+      const float sx = (centered ? (float)px : (float)px + r.x) * P.invW;
+      const float sy = (centered ? (float)py : (float)py + r.y) * P.invH;
+      float3 org, dir;
+      cameraCreateRay(P.cam, sx, sy, r.z, r.w, org, dir);
+
+      float3 color = f3(0.f, 0.f, 0.f);
+      float opacity = 0.f;
+      uint32_t objID = ~0u, instID = ~0u;
+      bool anyHit = false;
+      float volumeDepth;
+      if (SINGLE)
+        volumeDepth = rayMarchAllVolumes<SKIP, false, STATS>(inst, 1, TfSelectSingle{s_tf}, org, dir, FLT_MAX,
+            P.invSamplingRate, rng, color, opacity, objID, instID, st, P.cellBitmap, anyHit);
+      else
+        volumeDepth = rayMarchAllVolumes<SKIP, false, STATS>(inst, nInst, TfSelectShared{s_tf, inst}, org, dir,
+            FLT_MAX, P.invSamplingRate, rng, color, opacity, objID, instID, st, P.cellBitmap, anyHit);
+      if (STATS && anyHit)
+        raysHit++;
+
+      // Raycast_ptx.cu:139-166 (no-surface branch)
+      const float depth = fminf(1e30f, volumeDepth);
+      color = color * opacity;
+      const float4 bg = P.background;
+      const float oneMinus = 1.f - opacity;
+      color.x += bg.x * oneMinus;
+      color.y += bg.y * oneMinus;
+      color.z += bg.z * oneMinus;
+      opacity += bg.w * oneMinus;
+      // outputColor/outputOpacity start at 0: accumulateValue(out, c, 0) == c
+      accumResults(P, px, py, make_float4(color.x, color.y, color.z, opacity), depth, color, dir, 0u, objID,
+          instID, it, initFrame && it == 0);
+    }
+  }
+
+  if (STATS) {
+    const unsigned long long a = warpSum(st.taken), b = warpSum(st.skipped), c = warpSum(raysHit);
+    if (lane == 0 && P.stats) {
+      atomicAdd(&P.stats->samplesTaken, a);
+      atomicAdd(&P.stats->samplesSkipped, b);
+      atomicAdd(&P.stats->raysHit, c);
+    }
+  }
+  retireWarp(P.sched, lane);
+}
+
+template <bool SKIP, bool STATS, bool SINGLE>
+static int launchFrameT(const FrameLaunch &p, cudaStream_t s)
+{
+  static int blocksPerSm = 0;
+  if (blocksPerSm == 0) {
+    DVR_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(
+        &blocksPerSm, dvrFrameKernel<SKIP, STATS, SINGLE>, kBlockThreads, 0));
+    if (blocksPerSm < 1)
+      blocksPerSm = 1;
+  }
+  const uint32_t nTiles = p.tilesX * p.tilesY;
+  const uint32_t warpsPerBlock = kBlockThreads / 32;
+  uint32_t grid = (uint32_t)(smCount() * blocksPerSm);
+  const uint32_t need = (nTiles + warpsPerBlock - 1) / warpsPerBlock;
+  if (grid > need)
+    grid = need;
+  if (grid == 0)
+    grid = 1;
+  dvrFrameKernel<SKIP, STATS, SINGLE><<<grid, kBlockThreads, 0, s>>>(p);
+  DVR_CUDA(cudaGetLastError());
+  countLaunch();
+  return DVR_OK;
+}
+
+int launchFrame(const FrameLaunch &p, bool skip, bool stats, cudaStream_t s)
+{
+  const bool single = p.nInst == 1;
+  if (stats) {
+    if (skip)
+      return single ? launchFrameT<true, true, true>(p, s) : launchFrameT<true, true, false>(p, s);
+    return single ? launchFrameT<false, true, true>(p, s) : launchFrameT<false, true, false>(p, s);
+  }
+  if (skip)
+    return single ? launchFrameT<true, false, true>(p, s) : launchFrameT<true, false, false>(p, s);
+  return single ? launchFrameT<false, false, true>(p, s) : launchFrameT<false, false, false>(p, s);
+}
+
+// ----------------------------------------------------------------------------------------------
+// sort-last partial render: premultiplied (C,A) + entry depth of ONE slab on the global lattice
+// ----------------------------------------------------------------------------------------------
+template <bool SKIP>
+__global__ void __launch_bounds__(kBlockThreads, 2) dvrPartialKernel(const __grid_constant__ PartialLaunch P)
+{
+  __shared__ float4 s_tf[DVR_TF_SIZE];
+  const int lane = threadIdx.x & 31;
+  for (int i = threadIdx.x; i < DVR_TF_SIZE; i += blockDim.x)
+    s_tf[i] = __ldg(&P.inst.v.tf[i]);
+  __syncthreads();
+
+  MarchStats st{0ull, 0ull};
+  const uint32_t nTiles = P.tilesX * P.tilesY;
+  const bool centered = P.integrator == DVR_INTEGRATOR_RAYCAST;
+  for (uint32_t tile = nextTile(P.sched, lane); tile < nTiles; tile = nextTile(P.sched, lane)) {
+    const uint32_t tyIdx = tile / P.tilesX, txIdx = tile - tyIdx * P.tilesX;
+    const uint32_t px = txIdx * kTileW + (lane & 7), py = tyIdx * kTileH + (lane >> 3);
+    if (px >= P.width || py >= P.height)
+      continue;
+    Philox rng;
+    rng.init((unsigned long long)(int)(py * P.width + px), (unsigned long long)P.frameID * 512ull);
+    const float4 r = rng.uniform4();
+    const float sx = (centered ? (float)px : (float)px + r.x) * P.invW;
+    const float sy = (centered ? (float)py : (float)py + r.y) * P.invH;
+    float3 org, dir;
+    cameraCreateRay(P.cam, sx, sy, r.z, r.w, org, dir);
+    float3 color = f3(0.f, 0.f, 0.f);
+    float opacity = 0.f;
+    uint32_t objID = ~0u, instID = ~0u;
+    bool anyHit = false;
+    const float depth = rayMarchAllVolumes<SKIP, true, false>(&P.inst, 1, TfSelectSingle{s_tf}, org, dir, FLT_MAX,
+        P.invSamplingRate, rng, color, opacity, objID, instID, st, nullptr, anyHit);
+    const uint32_t idx = px + py * P.width;
+    P.partialRgba[idx] = make_float4(color.x, color.y, color.z, opacity);
+    P.partialDepth[idx] = fminf(1e30f, depth);
+  }
+  retireWarp(P.sched, lane);
+}
+
+int launchPartial(const PartialLaunch &p, cudaStream_t s)
+{
+  static int bps[2] = {0, 0};
+  const int k = p.skip ? 1 : 0;
+  if (bps[k] == 0) {
+    if (k)
+      DVR_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps[k], dvrPartialKernel<true>, kBlockThreads, 0));
+    else
+      DVR_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps[k], dvrPartialKernel<false>, kBlockThreads, 0));
+    if (bps[k] < 1)
+      bps[k] = 1;
+  }
+  const uint32_t nTiles = p.tilesX * p.tilesY;
+  uint32_t grid = (uint32_t)(smCount() * bps[k]);
+  const uint32_t need = (nTiles + 7) / 8;
+  if (grid > need)
+    grid = need;
+  if (grid == 0)
+    grid = 1;
+  if (k)
+    dvrPartialKernel<true><<<grid, kBlockThreads, 0, s>>>(p);
+  else
+    dvrPartialKernel<false><<<grid, kBlockThreads, 0, s>>>(p);
+  DVR_CUDA(cudaGetLastError());
+  countLaunch();
+  return DVR_OK;
+}
+
+// ----------------------------------------------------------------------------------------------
+// `over` compositing of two partial images (front-to-back, premultiplied)
+// ----------------------------------------------------------------------------------------------
+__global__ void dvrCompositeOverKernel(float4 *__restrict__ front, float *__restrict__ frontDepth,
+    const float4 *__restrict__ back, const float *__restrict__ backDepth, size_t begin, size_t end,
+    bool backIsInFront)
+{
+  const size_t i = begin + blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  if (i >= end)
+    return;
+  float4 a = front[i];
+  float4 b = back[i];
+  if (backIsInFront) {
+    const float4 t = a;
+    a = b;
+    b = t;
+  }
+  const float k = 1.f - a.w;
+  front[i] = make_float4(a.x + k * b.x, a.y + k * b.y, a.z + k * b.z, a.w + k * b.w);
+  if (frontDepth && backDepth)
+    frontDepth[i] = fminf(frontDepth[i], backDepth[i]);
+}
+
+int launchCompositeOver(float4 *front, float *frontDepth, const float4 *back, const float *backDepth,
+    size_t begin, size_t end, bool backIsInFront, cudaStream_t s)
+{
+  if (end <= begin)
+    return DVR_OK;
+  const size_t n = end - begin;
+  dvrCompositeOverKernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(
+      front, frontDepth, back, backDepth, begin, end, backIsInFront);
+  DVR_CUDA(cudaGetLastError());
+  countLaunch();
+  return DVR_OK;
+}
+
+// ----------------------------------------------------------------------------------------------
+// K3: resolve a composited partial image (quirk Q2 + background + accumulate/tonemap/encode)
+// ----------------------------------------------------------------------------------------------
+__global__ void dvrResolveKernel(const __grid_constant__ ResolveLaunch R)
+{
+  const size_t i = R.pixelBegin + blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  if (i >= R.pixelEnd)
+    return;
+  const float4 pc = R.partialRgba[i];
+  const float pd = R.partialDepth ? R.partialDepth[i] : 1e30f;
+  float3 color = f3(pc.x, pc.y, pc.z);
+  float opacity = pc.w;
+  color = color * opacity;
+  const float oneMinus = 1.f - opacity;
+  color.x += R.background.x * oneMinus;
+  color.y += R.background.y * oneMinus;
+  color.z += R.background.z * oneMinus;
+  opacity += R.background.w * oneMinus;
+
+  FrameLaunch P{};
+  P.width = R.width;
+  P.height = R.height;
+  P.format = R.format;
+  P.frameID = R.frameID;
+  P.checkerboardID = -1;
+  P.fb = R.fb;
+  const bool hit = pd < 1e30f;
+  const uint32_t px = (uint32_t)(i % R.width), py = (uint32_t)(i / R.width);
+  accumResults(P, px, py, make_float4(color.x, color.y, color.z, opacity), pd, color, f3(0.f, 0.f, 0.f), 0u,
+      hit ? R.objId : ~0u, hit ? R.instId : ~0u, 0, R.frameID == 0);
+}
+
+int launchResolve(const ResolveLaunch &r, cudaStream_t s)
+{
+  if (r.pixelEnd <= r.pixelBegin)
+    return DVR_OK;
+  const size_t n = r.pixelEnd - r.pixelBegin;
+  dvrResolveKernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(r);
+  DVR_CUDA(cudaGetLastError());
+  countLaunch();
+  return DVR_OK;
+}
+
+__global__ void dvrScaleVec3Kernel(const float *__restrict__ in, float *__restrict__ out, size_t n, float scale)
+{
+  const size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  if (i < n)
+    out[i] = in[i] * scale;
+}
+
+int launchScaleVec3(const float *in, float *out, size_t nPixels, float scale, cudaStream_t s)
+{
+  const size_t n = nPixels * 3;
+  if (n == 0)
+    return DVR_OK;
+  dvrScaleVec3Kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(in, out, n, scale);
+  DVR_CUDA(cudaGetLastError());
+  countLaunch();
+  return DVR_OK;
+}
+
+} // namespace dvr

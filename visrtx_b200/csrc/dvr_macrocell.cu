@@ -1,0 +1,185 @@
+// dvr_macrocell.cu — K4 (macrocell value ranges), K5 (per-macrocell majorants from the transfer
+// function) and small reductions.  Replaces space_skipping/UniformGrid.cu:44-258 of the reference.
+//
+// K4 is one pass over the voxels (read through a point-sampled view of the same 3-D array the
+// marcher filters, so fixed-point formats are seen exactly as the filter sees them).  Cell c
+// covers voxel indices [16c-1, 16c+16] per axis (clamped): every trilinear fetch whose lower tap
+// index falls in [16c, 16c+15] reads only those voxels, and the one-voxel apron on the low side
+// absorbs texture-unit coordinate rounding.  The reference's build samples the wrong coordinates
+//  and is deliberately not reproduced.
+#include "dvr_internal.h"
+
+namespace dvr {
+
+__global__ void __launch_bounds__(256) dvrMacrocellRangeKernel(cudaTextureObject_t pointTex, int3 dims,
+    int zTexBegin, int texDepth, int3 gridDims, float2 *__restrict__ ranges)
+{
+  const int cx = blockIdx.x, cy = blockIdx.y, cz = blockIdx.z;
+  const int x0 = max(cx * 16 - 1, 0), x1 = min(cx * 16 + 16, dims.x - 1);
+  const int y0 = max(cy * 16 - 1, 0), y1 = min(cy * 16 + 16, dims.y - 1);
+  const int z0 = max(cz * 16 - 1, 0), z1 = min(cz * 16 + 16, dims.z - 1);
+  const int nx = x1 - x0 + 1, ny = y1 - y0 + 1, nz = z1 - z0 + 1;
+  const int n = nx * ny * nz;
+  float lo = FLT_MAX, hi = -FLT_MAX;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    const int x = x0 + i % nx, y = y0 + (i / nx) % ny, z = z0 + i / (nx * ny);
+    // slices outside the resident slab are clamped by the texture: conservative only for the
+    // slices this rank samples, which is all it is used for
+    const int zl = min(max(z - zTexBegin, 0), texDepth - 1);
+    const float v = tex3D<float>(pointTex, (float)x + 0.5f, (float)y + 0.5f, (float)zl + 0.5f);
+    lo = fminf(lo, v); // fminf/fmaxf drop NaNs
+    hi = fmaxf(hi, v);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    lo = fminf(lo, __shfl_xor_sync(0xffffffffu, lo, o));
+    hi = fmaxf(hi, __shfl_xor_sync(0xffffffffu, hi, o));
+  }
+  __shared__ float slo[8], shi[8];
+  const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+  if (l == 0) {
+    slo[w] = lo;
+    shi[w] = hi;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int i = 1; i < 8; ++i) {
+      lo = fminf(lo, slo[i]);
+      hi = fmaxf(hi, shi[i]);
+    }
+    ranges[((size_t)cz * gridDims.y + cy) * gridDims.x + cx] = make_float2(lo, hi);
+  }
+}
+
+int launchMacrocellBuild(cudaTextureObject_t pointTex, int3 dims, int zTexBegin, int texDepth, int3 gridDims,
+    float2 *ranges, cudaStream_t s)
+{
+  dim3 grid(gridDims.x, gridDims.y, gridDims.z);
+  dvrMacrocellRangeKernel<<<grid, 256, 0, s>>>(pointTex, dims, zTexBegin, texDepth, gridDims, ranges);
+  DVR_CUDA(cudaGetLastError());
+  countLaunch();
+  return DVR_OK;
+}
+
+// K5: majorant = max TF alpha the marcher's lookup can return for any value in the cell's range.
+// UniformGrid.cu:55-90 restated with (a) the volume's own valueRange (quirk Q8) and (b) the
+// texel interval derived from the same coordinate mapping tfLookup() uses, widened by one texel.
+__global__ void dvrMajorantKernel(const float2 *__restrict__ ranges, size_t nCells, const float4 *__restrict__ tf,
+    float vrLo, float vrHi, float *__restrict__ maxOpacities)
+{
+  __shared__ float s_alpha[DVR_TF_SIZE];
+  for (int i = threadIdx.x; i < DVR_TF_SIZE; i += blockDim.x)
+    s_alpha[i] = tf[i].w;
+  __syncthreads();
+  const size_t c = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  if (c >= nCells)
+    return;
+  const float2 r = ranges[c];
+  if (!(r.x <= r.y)) { // empty / all-NaN cell
+    maxOpacities[c] = 0.f;
+    return;
+  }
+  const float c0 = rangePosition(r.x, vrLo, vrHi), c1 = rangePosition(r.y, vrLo, vrHi);
+  int i0 = (int)floorf(c0 * 256.0f - 0.5f) - 1;
+  int i1 = (int)floorf(c1 * 256.0f - 0.5f) + 2;
+  i0 = max(0, min(i0, DVR_TF_SIZE - 1));
+  i1 = max(0, min(i1, DVR_TF_SIZE - 1));
+  float m = 0.f;
+  for (int i = i0; i <= i1; ++i)
+    m = fmaxf(m, s_alpha[i]);
+  maxOpacities[c] = m;
+}
+
+int launchMajorants(const float2 *ranges, size_t nCells, const float4 *tf, float vrLo, float vrHi,
+    float *maxOpacities, cudaStream_t s)
+{
+  if (nCells == 0)
+    return DVR_OK;
+  dvrMajorantKernel<<<(unsigned)((nCells + 255) / 256), 256, 0, s>>>(ranges, nCells, tf, vrLo, vrHi, maxOpacities);
+  DVR_CUDA(cudaGetLastError());
+  countLaunch();
+  return DVR_OK;
+}
+
+// global (min,max) over the macrocell ranges: one CTA, strided
+__global__ void dvrRangeReduceKernel(const float2 *__restrict__ ranges, size_t nCells, float2 *out)
+{
+  float lo = FLT_MAX, hi = -FLT_MAX;
+  for (size_t i = threadIdx.x; i < nCells; i += blockDim.x) {
+    const float2 r = ranges[i];
+    if (r.x <= r.y) {
+      lo = fminf(lo, r.x);
+      hi = fmaxf(hi, r.y);
+    }
+  }
+  __shared__ float slo[1024], shi[1024];
+  slo[threadIdx.x] = lo;
+  shi[threadIdx.x] = hi;
+  __syncthreads();
+  for (int o = blockDim.x / 2; o > 0; o >>= 1) {
+    if (threadIdx.x < o) {
+      slo[threadIdx.x] = fminf(slo[threadIdx.x], slo[threadIdx.x + o]);
+      shi[threadIdx.x] = fmaxf(shi[threadIdx.x], shi[threadIdx.x + o]);
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0)
+    *out = make_float2(slo[0], shi[0]);
+}
+
+int launchRangeReduce(const float2 *ranges, size_t nCells, float2 *out, cudaStream_t s)
+{
+  dvrRangeReduceKernel<<<1, 1024, 0, s>>>(ranges, nCells, out);
+  DVR_CUDA(cudaGetLastError());
+  countLaunch();
+  return DVR_OK;
+}
+
+__global__ void dvrPopcountKernel(const unsigned int *__restrict__ bitmap, size_t nWords, unsigned long long *out)
+{
+  unsigned long long c = 0;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < nWords; i += (size_t)gridDim.x * blockDim.x)
+    c += __popc(bitmap[i]);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1)
+    c += __shfl_xor_sync(0xffffffffu, c, o);
+  if ((threadIdx.x & 31) == 0 && c)
+    atomicAdd(out, c);
+}
+
+int launchPopcount(const unsigned int *bitmap, size_t nWords, unsigned long long *out, cudaStream_t s)
+{
+  if (nWords == 0)
+    return DVR_OK;
+  unsigned blocks = (unsigned)((nWords + 255) / 256);
+  if (blocks > 1024)
+    blocks = 1024;
+  dvrPopcountKernel<<<blocks, 256, 0, s>>>(bitmap, nWords, out);
+  DVR_CUDA(cudaGetLastError());
+  countLaunch();
+  return DVR_OK;
+}
+
+// element conversion for formats the 3-D array cannot hold natively (FLOAT64 -> f32)
+__global__ void dvrF64ToF32Kernel(const double *__restrict__ src, float *__restrict__ dst, size_t n)
+{
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+    dst[i] = (float)src[i];
+}
+
+int launchConvertToFloat(const void *src, int dataType, float *dst, size_t n, cudaStream_t s)
+{
+  if (dataType != DVR_FLOAT64) {
+    setError("launchConvertToFloat: only FLOAT64 needs conversion");
+    return DVR_ERR_INVALID_ARGUMENT;
+  }
+  unsigned blocks = (unsigned)((n + 255) / 256);
+  if (blocks > 148 * 16)
+    blocks = 148 * 16;
+  dvrF64ToF32Kernel<<<blocks, 256, 0, s>>>((const double *)src, dst, n);
+  DVR_CUDA(cudaGetLastError());
+  countLaunch();
+  return DVR_OK;
+}
+
+} // namespace dvr

@@ -1,0 +1,273 @@
+// dvr_march.cuh — the ray-march hot loop (K1) as device functions shared by the frame kernel and
+// the sort-last partial kernel.
+//
+// Reproduces, per pixel-sample, gpu/volumeIntegration.h:64-165,317-350 (fixed-step
+// emission-absorption with the reference's double jitter and early termination at 0.99),
+// scene/Intersectors_ptx.cu:248-274 (slab test, clamped to the ray interval) and
+// gpu/sampleSpatialField.h:54-78 (normalised-coordinate hardware trilinear fetch).
+#pragma once
+
+#include "dvr_device.cuh"
+
+namespace dvr {
+
+#ifndef DVR_BATCH
+#define DVR_BATCH 4 // field fetches issued back-to-back before compositing (memory-level parallelism)
+#endif
+
+struct MarchStats
+{
+  unsigned long long taken;
+  unsigned long long skipped;
+};
+
+// object-space ray/box slab test; returns false when the box is missed or outside [tmin,tmax]
+__device__ __forceinline__ bool intersectVolumeBox(
+    const float3 lo, const float3 hi, const float3 org, const float3 dir, float tmin, float tmax,
+    float &t0, float &t1)
+{
+  const float3 inv = f3(1.f / dir.x, 1.f / dir.y, 1.f / dir.z);
+  const float3 mins = (lo - org) * inv;
+  const float3 maxs = (hi - org) * inv;
+  const float3 nears = f3(fminf(mins.x, maxs.x), fminf(mins.y, maxs.y), fminf(mins.z, maxs.z));
+  const float3 fars = f3(fmaxf(mins.x, maxs.x), fmaxf(mins.y, maxs.y), fmaxf(mins.z, maxs.z));
+  const float tn = max3(nears);
+  const float tf = min3(fars);
+  if (!(tn < tf))
+    return false;
+  // OptiX only runs the intersection program for boxes that overlap the ray interval
+  if (tf < tmin || tn > tmax)
+    return false;
+  t0 = fmaxf(tmin, fminf(tn, tmax));
+  t1 = fmaxf(tmin, fminf(tf, tmax));
+  return true;
+}
+
+__device__ __forceinline__ float3 xfmPoint(const float *m, float3 p)
+{
+  return f3(m[0] * p.x + m[1] * p.y + m[2] * p.z + m[3], m[4] * p.x + m[5] * p.y + m[6] * p.z + m[7],
+      m[8] * p.x + m[9] * p.y + m[10] * p.z + m[11]);
+}
+__device__ __forceinline__ float3 xfmVector(const float *m, float3 v)
+{
+  return f3(m[0] * v.x + m[1] * v.y + m[2] * v.z, m[4] * v.x + m[5] * v.y + m[6] * v.z,
+      m[8] * v.x + m[9] * v.y + m[10] * v.z);
+}
+
+// texture coordinates of an object-space position: sampleSpatialField.h:66-70
+__device__ __forceinline__ float3 fieldTexCoord(const FieldDev &f, const float3 halfSpacing, float3 p)
+{
+  return ((p - f.origin) + halfSpacing) * f.invSpacing;
+}
+
+template <bool SLAB>
+__device__ __forceinline__ float fieldFetch(const FieldDev &f, float3 tc)
+{
+  if (SLAB) {
+    // remap the global normalised z onto the resident slices (see DESIGN.md "sort-last slabs")
+    const float zb = tc.z * (float)f.dims.z - (float)f.zTexBegin;
+    tc.z = zb / (float)f.texDepth;
+  }
+  return tex3D<float>(f.tex, tc.x, tc.y, tc.z);
+}
+
+// One volume segment [tLower(after jitter #1), tUpper] of one ray.
+//   SKIP : consult the per-macrocell majorants and step over fully transparent cells on the
+//          SAME sample lattice (t advances by repeated `t += step`, so the taken samples are
+//          bit-identical to the unskipped march)
+//   SLAB : only samples whose cell slice lies in [zOwnBegin,zOwnEnd) are taken (sort-last)
+//   STATS: count samples
+template <bool SKIP, bool SLAB, bool STATS>
+__device__ __forceinline__ void marchSegment(const VolumeDev &v, const float4 *__restrict__ tf,
+    const float3 org, const float3 dir, float t, const float tUpper, const float invSamplingRate,
+    Philox &rng, float3 &color, float &opacity, MarchStats &stats, unsigned int *cellBitmap)
+{
+  const FieldDev &f = v.f;
+  const float stepSize = f.stepSize * invSamplingRate;
+  const float exponent = stepSize * v.oneOverUnitDistance;
+  t += stepSize * rng.uniform(); // jitter #2, volumeIntegration.h:83
+
+  const float3 halfSpacing = 0.5f * f.spacing;
+  const float vrLo = v.vrLower, vrHi = v.vrUpper;
+  float transmittance = 1.f;
+
+  // d(voxel coordinate)/dt, used by SKIP/SLAB bookkeeping only (never for the sample position)
+  const float3 dvox = f3(dir.x * f.invSpacing.x * (float)f.dims.x, dir.y * f.invSpacing.y * (float)f.dims.y,
+      dir.z * f.invSpacing.z * (float)f.dims.z);
+
+  if (SLAB) {
+    // fast-forward to just before the ray enters the owned z range (sequential adds keep the
+    // lattice identical to the single-GPU march)
+    const float3 tc0 = fieldTexCoord(f, halfSpacing, org + dir * t);
+    const float z0 = tc0.z * (float)f.dims.z - 0.5f;
+    float tEnter = t;
+    if (dvox.z > 0.f)
+      tEnter = t + ((float)f.zOwnBegin - z0) / dvox.z;
+    else if (dvox.z < 0.f)
+      tEnter = t + ((float)f.zOwnEnd - z0) / dvox.z;
+    tEnter -= 2.f * stepSize;
+    while (t < tEnter && t <= tUpper) {
+      t += stepSize;
+      if (STATS)
+        stats.skipped++;
+    }
+  }
+
+  while (opacity < 0.99f && t <= tUpper) {
+    if (SKIP) {
+      const float3 tc = fieldTexCoord(f, halfSpacing, org + dir * t);
+      const float3 xb = f3(tc.x * (float)f.dims.x - 0.5f, tc.y * (float)f.dims.y - 0.5f,
+          tc.z * (float)f.dims.z - 0.5f);
+      const int cx = min(max((int)floorf(xb.x), 0), f.dims.x - 1) >> 4;
+      const int cy = min(max((int)floorf(xb.y), 0), f.dims.y - 1) >> 4;
+      const int cz = min(max((int)floorf(xb.z), 0), f.dims.z - 1) >> 4;
+      const float majorant = __ldg(&v.maxOpacities[(size_t)cz * f.gridDims.x * f.gridDims.y
+          + (size_t)cy * f.gridDims.x + cx]);
+      if (majorant <= 0.f) {
+        // distance (in t) to the nearest face of this macrocell along the ray
+        const float bx = dvox.x > 0.f ? (float)((cx + 1) << 4) : (float)(cx << 4);
+        const float by = dvox.y > 0.f ? (float)((cy + 1) << 4) : (float)(cy << 4);
+        const float bz = dvox.z > 0.f ? (float)((cz + 1) << 4) : (float)(cz << 4);
+        const float ex = dvox.x != 0.f ? (bx - xb.x) / dvox.x : FLT_MAX;
+        const float ey = dvox.y != 0.f ? (by - xb.y) / dvox.y : FLT_MAX;
+        const float ez = dvox.z != 0.f ? (bz - xb.z) / dvox.z : FLT_MAX;
+        const float dt = fminf(fminf(ex, ey), ez);
+        // whole steps that stay strictly inside the cell, one step of safety margin
+        int n = (int)floorf(fminf(dt / stepSize, 1.0e6f)) - 1;
+        if (n >= 1) {
+          while (n > 0 && t <= tUpper) {
+            t += stepSize;
+            --n;
+            if (STATS)
+              stats.skipped++;
+          }
+          continue;
+        }
+      }
+    }
+
+    float ts[DVR_BATCH];
+    float s[DVR_BATCH];
+    float tt = t;
+#pragma unroll
+    for (int k = 0; k < DVR_BATCH; ++k) {
+      ts[k] = tt;
+      tt += stepSize;
+    }
+#pragma unroll
+    for (int k = 0; k < DVR_BATCH; ++k) {
+      s[k] = __int_as_float(0x7fc00000);
+      if (ts[k] <= tUpper) {
+        const float3 p = org + dir * ts[k];
+        const float3 tc = fieldTexCoord(f, halfSpacing, p);
+        bool own = true;
+        if (SLAB) {
+          const int zc = min(max((int)floorf(tc.z * (float)f.dims.z - 0.5f), 0), f.dims.z - 1);
+          own = zc >= f.zOwnBegin && zc < f.zOwnEnd;
+        }
+        if (own) {
+          s[k] = fieldFetch<SLAB>(f, tc);
+          if (STATS) {
+            stats.taken++;
+            if (cellBitmap) {
+              const int cx = min(max((int)floorf(tc.x * (float)f.dims.x - 0.5f), 0), f.dims.x - 1) >> 4;
+              const int cy = min(max((int)floorf(tc.y * (float)f.dims.y - 0.5f), 0), f.dims.y - 1) >> 4;
+              const int cz = min(max((int)floorf(tc.z * (float)f.dims.z - 0.5f), 0), f.dims.z - 1) >> 4;
+              const size_t c = (size_t)cz * f.gridDims.x * f.gridDims.y + (size_t)cy * f.gridDims.x + cx;
+              atomicOr(&cellBitmap[c >> 5], 1u << (c & 31));
+            }
+          }
+        }
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < DVR_BATCH; ++k) {
+      if (opacity < 0.99f && ts[k] <= tUpper) {
+        const float sv = s[k];
+        if (!isnan(sv)) {
+          const float4 co = tfLookup(tf, rangePosition(sv, vrLo, vrHi));
+          const float stepTransmittance = powf(1.f - co.w, exponent);
+          const float w = transmittance * (1.f - stepTransmittance);
+          color.x += w * co.x;
+          color.y += w * co.y;
+          color.z += w * co.z;
+          opacity += w;
+          transmittance *= stepTransmittance;
+        }
+      }
+    }
+    t = tt;
+
+    if (SLAB) {
+      // past the owned range for good?
+      const float3 tc = fieldTexCoord(f, halfSpacing, org + dir * t);
+      const float z = tc.z * (float)f.dims.z - 0.5f;
+      if ((dvox.z > 0.f && z > (float)f.zOwnEnd + 2.f) || (dvox.z < 0.f && z < (float)f.zOwnBegin - 2.f))
+        break;
+    }
+  }
+}
+
+// rayMarchAllVolumes, volumeIntegration.h:317-350, with the OptiX volume-BVH trace replaced by a
+// loop over the flattened instance list (closest clamped entry first, the volume marched last
+// is excluded from the next search exactly like the lastVolID/lastInstID test of
+// Intersectors_ptx.cu:250-252).
+template <bool SKIP, bool SLAB, bool STATS, typename TfSelect>
+__device__ __forceinline__ float rayMarchAllVolumes(const InstanceDev *__restrict__ inst, const int nInst,
+    TfSelect tfOf, const float3 org, const float3 dir, const float tfar, const float invSamplingRate,
+    Philox &rng, float3 &color, float &opacity, uint32_t &objID, uint32_t &instID, MarchStats &stats,
+    unsigned int *cellBitmap, bool &anyHit)
+{
+  float rayLower = 0.f;
+  const float rayUpper = tfar;
+  float depth = tfar;
+  bool firstHit = true;
+  int last = -1;
+
+  do {
+    int best = -1;
+    float bt0 = 0.f, bt1 = 0.f;
+    float3 bo = org, bd = dir;
+    for (int i = 0; i < nInst; ++i) {
+      if (i == last)
+        continue;
+      const InstanceDev &in = inst[i];
+      float3 lo = org, ld = dir;
+      if (!in.identity) {
+        lo = xfmPoint(in.xfm, org);
+        ld = xfmVector(in.xfm, dir);
+      }
+      float t0, t1;
+      if (!intersectVolumeBox(in.v.f.boundsLo, in.v.f.boundsHi, lo, ld, rayLower, rayUpper, t0, t1))
+        continue;
+      if (best < 0 || t0 < bt0) {
+        best = i;
+        bt0 = t0;
+        bt1 = t1;
+        bo = lo;
+        bd = ld;
+      }
+    }
+    if (best < 0)
+      break;
+    const InstanceDev &in = inst[best];
+    if (firstHit) {
+      objID = in.v.id;
+      instID = in.instId;
+      firstHit = false;
+      anyHit = true;
+    }
+    depth = fminf(depth, bt0);
+    bt1 = fminf(tfar, bt1);
+    // detail::rayMarchVolume: jitter #1 uses the UNSCALED step (volumeIntegration.h:117-120)
+    const float tStart = bt0 + in.v.f.stepSize * rng.uniform();
+    marchSegment<SKIP, SLAB, STATS>(
+        in.v, tfOf(best), bo, bd, tStart, bt1, invSamplingRate, rng, color, opacity, stats, cellBitmap);
+    rayLower = bt1 + 1e-3f;
+    last = best;
+  } while (opacity < 0.99f);
+
+  return depth;
+}
+
+} // namespace dvr
