@@ -1,0 +1,596 @@
+#!/usr/bin/env python
+"""bench.py — DVR frames/s on BASELINE config C2 (1024^3 f32 volume, 1920x1080), B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+A "step" is one frame: one pass of the DVR hot path (ray generation, march, background,
+accumulate/tonemap/encode) over all W*H pixels of a synthetic analytic volume that is already
+resident in HBM.  Prints ONE JSON line (rank 0).  See DESIGN.md "Measurement" for the byte model.
+
+  value     frames/s, device-timed (CUDA events on the launching stream), progressive accumulation
+  e2e       frames/s through the public API with HOST buffers: every step re-commits a moved camera
+            (host -> device parameter upload), renders, and maps the colour channel to pinned host
+            memory (device -> host copy) inside the timed region
+  roofline  HBM: algorithmic bytes per frame (voxels of every macrocell the rays sample, measured
+            by an untimed instrumented launch, + 44 B/pixel + the 4 KiB TF) / average kernel time
+  cpu_baseline  O-cpu (oracle/liboracle_dvr.so) on a bounded band of image rows, all host cores
+
+--impl reference times O-gpu: the reference's OWN device headers (volumeIntegration.h etc.) compiled
+for sm_100a with an OptiX shim (oracle/_ref/libref_gpu_dvr.so) — VisRTX itself cannot be built
+without OptiX/ANARI-SDK — falling back to the O-cpu port when that library is absent.
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import json
+import math
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+
+# ---------------------------------------------------------------------------------------------------------
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=100)
+    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--size", type=int, default=1024, help="volume edge length (C2: 1024)")
+    ap.add_argument("--width", type=int, default=1920)
+    ap.add_argument("--height", type=int, default=1080)
+    ap.add_argument("--rate", type=float, default=0.5, help="volumeSamplingRate (0.5 => 1 voxel per step)")
+    ap.add_argument("--unit-distance", type=float, default=256.0,
+                    help="TF unitDistance in voxels; 256 = semi-transparent, every ray crosses the volume")
+    ap.add_argument("--field", default="ml", choices=["ml"])
+    ap.add_argument("--skip", type=int, default=0, help="macrocell skipping (no effect on the dense field)")
+    ap.add_argument("--mode", default="auto", choices=["auto", "sort-first", "sort-last"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-rows", type=int, default=0, help="rows of the CPU-baseline band (0 = auto)")
+    ap.add_argument("--extra", type=int, default=1, help="also measure the secondary variants (N=1 only)")
+    return ap.parse_args()
+
+
+# ---------------------------------------------------------------------------------------------------------
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms during the timed region."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.gpu = gpu_index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200", "-i",
+                 str(self.gpu)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.25)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[1]))
+                mx.append(float(r[2]))
+                for n, v in zip(names, r[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(n)
+            except Exception:
+                pass
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ---------------------------------------------------------------------------------------------------------
+def make_scene(args, torch, device, z_begin=0, z_end=None):
+    """C2: Marschner-Lobb evaluated on a size^3 lattice, origin 0, spacing 1, generated in HBM."""
+    from visrtx_b200 import scenes
+    n = args.size
+    vol = scenes.marschner_lobb_torch(n, device, z_begin=z_begin, z_end=z_end, nz_total=n)
+    return vol
+
+
+def orbit(args, az_deg=30.0):
+    from visrtx_b200 import capi, scenes
+    n = args.size
+    pose = scenes.orbit_camera((0, 0, 0), (n - 1, n - 1, n - 1), args.width, args.height, az_deg=az_deg)
+    return capi.camera_perspective(pose.position, pose.direction, pose.up, pose.fovy, pose.aspect), pose
+
+
+def bytes_per_frame(args, cells_touched: int, fmt_bytes: int = 4) -> int:
+    # N_vox_touched * sizeof(voxel) + N_px * (32 accum RW + colour + 8 depth RW) + 4 KiB TF
+    return cells_touched * 16 ** 3 * 4 + args.width * args.height * (32 + fmt_bytes + 8) + 4096
+
+
+def measured_peak():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+# ---------------------------------------------------------------------------------------------------------
+def cpu_baseline(args, torch, vol_dev, samples_per_frame: int):
+    """O-cpu on a bounded band of rows around the image centre (all host cores via OpenMP)."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import oracle_binding as ob
+    from visrtx_b200 import capi, scenes
+    n = args.size
+    host = vol_dev.cpu().numpy()  # (z,y,x) f32
+    tf = capi.tf_discretize(color=scenes.tsd_default_colormap(256))
+    cam, _ = orbit(args)
+    vols = (ob.OracleVolume * 1)()
+    o = vols[0]
+    o.voxels = host.ctypes.data_as(C.c_void_p)
+    o.dims = (C.c_int32 * 3)(n, n, n)
+    o.origin = (C.c_float * 3)(0, 0, 0)
+    o.spacing = (C.c_float * 3)(1, 1, 1)
+    o.tf = tf.ctypes.data_as(C.c_void_p)
+    o.valueRange = (C.c_float * 2)(0, 1)
+    o.unitDistance = args.unit_distance
+    o.id = 0
+    o.worldToObject = (C.c_float * 12)(*capi.IDENTITY_3X4)
+    o.instanceId = 0
+    npx = args.width * args.height
+    accum = np.zeros((npx, 4), np.float32)
+    color = np.zeros(npx, np.uint32)
+    depth = np.zeros(npx, np.float32)
+    b = ob.OracleBuffers()
+    b.colorAccumulation = accum.ctypes.data_as(C.c_void_p)
+    b.outColor = color.ctypes.data_as(C.c_void_p)
+    b.depth = depth.ctypes.data_as(C.c_void_p)
+    p = capi.frame_params(args.width, args.height, capi.DVR_FORMAT_UFIXED8_RGBA_SRGB, capi.DVR_INTEGRATOR_DEFAULT, 0,
+                          -1, 1, args.rate, (0.1, 0.1, 0.1, 1.0))
+    cores = os.cpu_count() or 1
+    rows = args.cpu_rows
+    mid = args.height // 2
+    lib = ob.cpu()
+
+    def run(nrows):
+        s = C.c_uint64()
+        t0 = time.perf_counter()
+        lib.oracle_render(C.byref(p), C.byref(cam), vols, 1, C.byref(b), C.byref(s), mid - nrows // 2,
+                          mid - nrows // 2 + nrows)
+        return time.perf_counter() - t0, s.value
+
+    if rows <= 0:  # calibrate on 2 rows, then size the band for ~15 s
+        dt, _ = run(2)
+        rows = int(max(2, min(args.height, 2 * 15.0 / max(dt, 1e-3))))
+    dt, nsamp = run(rows)
+    sps = nsamp / dt
+    return {"value": sps / max(samples_per_frame, 1), "unit": "frames/s", "cores": cores, "kind": "port",
+            "gsamples_per_s": sps / 1e9,
+            "sample": f"{rows} image rows around the centre of the same {args.width}x{args.height} frame "
+                      f"({nsamp} samples, {dt:.1f} s); frames/s = CPU samples/s / samples per frame"}
+
+
+# ---------------------------------------------------------------------------------------------------------
+def run_ours(args, torch, dist, rank, world):
+    from visrtx_b200 import capi, scenes
+    device = torch.device("cuda", int(os.environ.get("LOCAL_RANK", 0)))
+    torch.cuda.set_device(device)
+    capi.set_device(device.index)
+    stream = torch.cuda.current_stream().cuda_stream
+    n, W, H = args.size, args.width, args.height
+    npx = W * H
+
+    mode = args.mode
+    if mode == "auto":
+        mode = "sort-first" if n ** 3 * 4 <= 64e9 else "sort-last"
+    if world == 1:
+        mode = "single"
+
+    t_setup = time.perf_counter()
+    vol = make_scene(args, torch, device)
+    field = capi.Field.create_structured(vol.data_ptr(), True, capi.DVR_FLOAT32, (n, n, n), (0, 0, 0), (1, 1, 1),
+                                         capi.DVR_FILTER_LINEAR, stream)
+    torch.cuda.synchronize()
+    tf = capi.tf_discretize(color=scenes.tsd_default_colormap(256))
+    volume = capi.Volume.create(field, tf, (0.0, 1.0), args.unit_distance, 0, stream)
+    inst, ninst = capi.make_instances([volume], None, [0])
+    cam, _ = orbit(args)
+    setup_s = time.perf_counter() - t_setup
+
+    accum = torch.zeros((npx, 4), dtype=torch.float32, device=device)
+    color = torch.zeros(npx, dtype=torch.int32, device=device)
+    depth = torch.zeros(npx, dtype=torch.float32, device=device)
+    fb = capi.frame_buffers(accum.data_ptr(), color.data_ptr(), depth.data_ptr())
+    host_color = torch.empty(npx, dtype=torch.int32, pin_memory=True)
+
+    def params(frame_id):
+        return capi.frame_params(W, H, capi.DVR_FORMAT_UFIXED8_RGBA_SRGB, capi.DVR_INTEGRATOR_DEFAULT, frame_id, -1, 1,
+                                 args.rate, (0.1, 0.1, 0.1, 1.0), tile_rank=rank if mode == "sort-first" else 0,
+                                 tile_ranks=world if mode == "sort-first" else 1, skip=bool(args.skip))
+
+    gather_bufs = None
+    if mode == "sort-first":
+        gather_bufs = [torch.empty_like(color) for _ in range(world)] if rank == 0 else None
+
+    def exchange():
+        # sort-first: every rank rendered tile rows (ty % world == rank) into its own full-size buffer;
+        # rank 0 assembles the frame (one gather of the sRGB8 colour channel)
+        if mode != "sort-first":
+            return
+        dist.gather(color, gather_bufs, dst=0)
+        if rank == 0:
+            rows = color.view(H // 4 if H % 4 == 0 else -1, 4, W) if H % 4 == 0 else None
+            if rows is not None:
+                for r in range(1, world):
+                    src = gather_bufs[r].view(H // 4, 4, W)
+                    rows[r::world] = src[r::world]
+
+    def step(frame_id):
+        capi.render(params(frame_id), cam, inst, ninst, fb, stream)
+        exchange()
+
+    # ---- untimed instrumented launch: samples / touched macrocells of this workload
+    stats_t = torch.zeros(4, dtype=torch.int64, device=device)
+    p_stats = params(0)
+    p_stats.tileRank, p_stats.tileRanks = 0, 1
+    capi.render_instrumented(p_stats, cam, inst, ninst, fb, stats_t.data_ptr(), stream)
+    torch.cuda.synchronize()
+    samples, skipped, rays_hit, cells = stats_t.tolist()
+
+    # ---- device-timed region (clocks are sampled from here to the end of the e2e loop: the timed
+    # region alone is ~0.1 s, shorter than nvidia-smi's sampling period)
+    sampler = ClockSampler(device.index)
+    if rank == 0:
+        sampler.start()
+    for i in range(args.warmup):
+        step(i)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    l0 = capi.launch_count()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    ev0.record()
+    for i in range(args.steps):
+        step(args.warmup + i)
+    ev1.record()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    launches = capi.launch_count() - l0
+    ms = ev0.elapsed_time(ev1)
+    if world > 1:
+        t = torch.tensor([ms], dtype=torch.float64, device=device)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    ms_per_step = ms / args.steps
+    fps = 1000.0 / ms_per_step
+
+    # ---- kernel-only duration for the roofline (render launches only, no exchange)
+    for i in range(3):
+        capi.render(params(1 + i), cam, inst, ninst, fb, stream)
+    torch.cuda.synchronize()
+    k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    kn = max(10, min(args.steps, 50))
+    k0.record()
+    for i in range(kn):
+        capi.render(params(10 + i), cam, inst, ninst, fb, stream)
+    k1.record()
+    torch.cuda.synchronize()
+    kernel_ms = k0.elapsed_time(k1) / kn
+    if world > 1:
+        t = torch.tensor([kernel_ms], dtype=torch.float64, device=device)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        kernel_ms = float(t.item())
+
+    # ---- end-to-end through the public API with host buffers
+    def e2e_step(i):
+        cam_i, _ = orbit(args, az_deg=30.0 + 0.05 * i)  # moved camera => parameter re-commit => accumulation reset
+        capi.render(params(0), cam_i, inst, ninst, fb, stream)
+        exchange()
+        if rank == 0:
+            host_color.copy_(color, non_blocking=True)
+        torch.cuda.synchronize()
+
+    for i in range(3):
+        e2e_step(i)
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    ne2e = args.steps
+    for i in range(ne2e):
+        e2e_step(i)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    e2e_s = time.perf_counter() - t0
+    if world > 1:
+        t = torch.tensor([e2e_s], dtype=torch.float64, device=device)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_s = float(t.item())
+    e2e_fps = ne2e / e2e_s
+    clocks = sampler.stop() if rank == 0 else None
+
+    peak, peak_src = measured_peak()
+    bframe = bytes_per_frame(args, cells)
+    share = 1.0 / world if mode == "sort-first" else 1.0
+    achieved = bframe / (kernel_ms * 1e-3) / 1e9  # GB/s (whole volume is swept by every rank in sort-first)
+    out = {
+        "metric": "DVR frames/s, 1080p, 1024^3 f32 volume (Gsamples/s in extra)",
+        "value": fps, "unit": "frames/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic (analytic Marschner-Lobb field generated in HBM)",
+        "config": {
+            "workload": f"C2: {n}^3 f32 structuredRegular + transferFunction1D (TSD default map, unitDistance "
+                        f"{args.unit_distance:g} voxels), {W}x{H}, default renderer 1 spp progressive, "
+                        f"volumeSamplingRate {args.rate:g} (step {0.5 / args.rate:g} voxel), orbit camera az30/el20 "
+                        f"at 2|diag|, fovy 60",
+            "parallelism": mode + (f"x{world}" if world > 1 else ""),
+            "l2": f"input volume {n ** 3 * 4 / 2 ** 30:.1f} GiB >> 126 MB L2; no flush needed",
+            "macrocell_skipping": bool(args.skip),
+        },
+        "gpu_launches": int(launches),
+        "e2e": {"value": e2e_fps, "unit": "frames/s", "h2d_bytes_per_step": 4 * 1024,
+                "d2h_bytes_per_step": npx * 4,
+                "what": "C-ABI dvr_render with a re-committed camera (kernel parameter block upload) + colour "
+                        "channel mapped to pinned host memory every frame, wall clock incl. sync"},
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                     "traffic": None, "peak_source": peak_src, "kernel": "dvrFrameKernel",
+                     "kernel_ms": kernel_ms, "algorithmic_bytes": bframe,
+                     "macrocells_touched": int(cells), "macrocells_total": int(math.ceil(n / 16) ** 3)},
+        "extra": {"samples_per_frame": int(samples), "gsamples_per_s": samples * fps / 1e9 * (1 if world == 1 else 1),
+                  "rays_hit": int(rays_hit), "bytes_per_sample": bframe / max(samples, 1), "setup_s": setup_s,
+                  "share_per_rank": share},
+    }
+    if clocks is not None:
+        out["clocks"] = clocks
+
+    if rank == 0 and world == 1 and args.extra:
+        out["extra"]["variants"] = measure_variants(args, torch, capi, scenes, field, cam, inst, ninst, fb, stream, stats_t)
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        try:
+            out["cpu_baseline"] = cpu_baseline(args, torch, vol, samples)
+        except Exception as e:  # the oracle is optional at bench time
+            out["cpu_baseline"] = {"value": None, "unit": "frames/s", "cores": os.cpu_count(), "kind": "port",
+                                   "sample": f"unavailable: {e}"}
+    if rank == 0 and world == 1 and args.extra:
+        try:
+            out["extra"]["ref_gpu_fps"] = ref_gpu_fps(args, torch, vol, min(args.steps, 30))
+        except Exception as e:
+            out["extra"]["ref_gpu_fps"] = f"unavailable: {e}"
+    return out
+
+
+def measure_variants(args, torch, capi, scenes, field, cam, inst, ninst, fb, stream, stats_t):
+    """Secondary numbers (same scene): other sampling rates and the opaque BASELINE.md-literal TF."""
+    res = {}
+    tf = capi.tf_discretize(color=scenes.tsd_default_colormap(256))
+    for name, rate, ud in (("rate0.125_ud256", 0.125, args.unit_distance), ("rate1.0_ud256", 1.0, args.unit_distance),
+                           ("rate0.5_ud1_opaque", 0.5, 1.0)):
+        v = capi.Volume.create(field, tf, (0.0, 1.0), ud, 0, stream)
+        ins, nn = capi.make_instances([v], None, [0])
+        mk = lambda fid: capi.frame_params(args.width, args.height, capi.DVR_FORMAT_UFIXED8_RGBA_SRGB,
+                                           capi.DVR_INTEGRATOR_DEFAULT, fid, -1, 1, rate, (0.1, 0.1, 0.1, 1.0))
+        capi.render_instrumented(mk(0), cam, ins, nn, fb, stats_t.data_ptr(), stream)
+        torch.cuda.synchronize()
+        samples, _, _, cells = stats_t.tolist()
+        for i in range(3):
+            capi.render(mk(i), cam, ins, nn, fb, stream)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(20):
+            capi.render(mk(3 + i), cam, ins, nn, fb, stream)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / 20
+        bf = bytes_per_frame(args, cells)
+        res[name] = {"fps": 1000.0 / ms, "ms": ms, "samples_per_frame": samples, "gsamples_per_s": samples / ms / 1e6,
+                     "macrocells_touched": cells, "algorithmic_GBps": bf / ms / 1e6}
+        v.destroy()
+    return res
+
+
+# ---------------------------------------------------------------------------------------------------------
+def _refgpu_objects(args, torch, vol_dev):
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import oracle_binding as ob
+    from visrtx_b200 import capi, scenes
+    lib = ob.refgpu()
+    n = args.size
+    f = C.c_void_p()
+    rc = lib.refgpu_field_create(C.c_void_p(vol_dev.data_ptr()), C.c_int(capi.DVR_FLOAT32), (C.c_uint32 * 3)(n, n, n),
+                                 (C.c_float * 3)(0, 0, 0), (C.c_float * 3)(1, 1, 1), C.c_int(0), C.byref(f))
+    assert rc == 0, lib.refgpu_last_error()
+    tf = capi.tf_discretize(color=scenes.tsd_default_colormap(256))
+    v = C.c_void_p()
+    rc = lib.refgpu_volume_create(f, tf.ctypes.data_as(C.c_void_p), (C.c_float * 2)(0, 1), C.c_float(args.unit_distance),
+                                  C.c_uint32(0), C.byref(v))
+    assert rc == 0, lib.refgpu_last_error()
+    inst = (ob.RefInstance * 1)()
+    inst[0].volume = v
+    inst[0].worldToObject = (C.c_float * 12)(*capi.IDENTITY_3X4)
+    inst[0].instanceId = 0
+    sc = C.c_void_p()
+    rc = lib.refgpu_scene_create(inst, C.c_int(1), C.byref(sc))
+    assert rc == 0, lib.refgpu_last_error()
+    return lib, sc, (f, v)
+
+
+def ref_gpu_fps(args, torch, vol_dev, steps):
+    """O-gpu frames/s on the same scene (device-timed), reported next to our own number."""
+    from visrtx_b200 import capi
+    lib, sc, _ = _refgpu_objects(args, torch, vol_dev)
+    npx = args.width * args.height
+    dev = vol_dev.device
+    accum = torch.zeros((npx, 4), dtype=torch.float32, device=dev)
+    color = torch.zeros(npx, dtype=torch.int32, device=dev)
+    depth = torch.zeros(npx, dtype=torch.float32, device=dev)
+    fb = capi.frame_buffers(accum.data_ptr(), color.data_ptr(), depth.data_ptr())
+    cam, _ = orbit(args)
+    stream = torch.cuda.current_stream().cuda_stream
+    mk = lambda fid: capi.frame_params(args.width, args.height, capi.DVR_FORMAT_UFIXED8_RGBA_SRGB,
+                                       capi.DVR_INTEGRATOR_DEFAULT, fid, -1, 1, args.rate, (0.1, 0.1, 0.1, 1.0))
+    for i in range(3):
+        lib.refgpu_render(C.byref(mk(i)), C.byref(cam), sc, C.byref(fb), C.c_void_p(stream))
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    e0.record()
+    for i in range(steps):
+        lib.refgpu_render(C.byref(mk(3 + i)), C.byref(cam), sc, C.byref(fb), C.c_void_p(stream))
+    e1.record()
+    torch.cuda.synchronize()
+    return steps * 1000.0 / e0.elapsed_time(e1)
+
+
+def run_reference(args, torch, dist, rank, world):
+    """Reference arm: O-gpu (reference device headers) on ONE GPU; rank 0 only."""
+    from visrtx_b200 import capi
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import oracle_binding as ob
+    device = torch.device("cuda", int(os.environ.get("LOCAL_RANK", 0)))
+    torch.cuda.set_device(device)
+    n, W, H = args.size, args.width, args.height
+    npx = W * H
+    vol = make_scene(args, torch, device)
+    base = {"impl": "reference", "metric": "DVR frames/s, 1080p, 1024^3 f32 volume (Gsamples/s in extra)",
+            "unit": "frames/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic (analytic Marschner-Lobb field generated in HBM)"}
+    workload = (f"C2: {n}^3 f32 structuredRegular + transferFunction1D (TSD default map, unitDistance "
+                f"{args.unit_distance:g} voxels), {W}x{H}, default renderer 1 spp progressive, volumeSamplingRate "
+                f"{args.rate:g}, orbit camera az30/el20 at 2|diag|, fovy 60")
+    if not ob.have_ref_gpu():
+        # fall back to the CPU port
+        cb = cpu_baseline(args, torch, vol, 1)
+        sps = cb["gsamples_per_s"] * 1e9
+        # samples per frame of this workload from the oracle itself is unknown here: report samples/s based fps
+        # with the GPU-measured samples per frame when libdvr is present
+        from visrtx_b200 import scenes
+        stream = torch.cuda.current_stream().cuda_stream
+        field = capi.Field.create_structured(vol.data_ptr(), True, capi.DVR_FLOAT32, (n, n, n), (0, 0, 0), (1, 1, 1),
+                                             capi.DVR_FILTER_LINEAR, stream)
+        tf = capi.tf_discretize(color=scenes.tsd_default_colormap(256))
+        v = capi.Volume.create(field, tf, (0.0, 1.0), args.unit_distance, 0, stream)
+        inst, ninst = capi.make_instances([v], None, [0])
+        accum = torch.zeros((npx, 4), dtype=torch.float32, device=device)
+        color = torch.zeros(npx, dtype=torch.int32, device=device)
+        fb = capi.frame_buffers(accum.data_ptr(), color.data_ptr())
+        st = torch.zeros(4, dtype=torch.int64, device=device)
+        cam, _ = orbit(args)
+        capi.render_instrumented(capi.frame_params(W, H, 2, 1, 0, -1, 1, args.rate, (0.1, 0.1, 0.1, 1.0)), cam, inst,
+                                 ninst, fb, st.data_ptr(), stream)
+        torch.cuda.synchronize()
+        fps = sps / max(st[0].item(), 1)
+        cb["value"] = fps
+        base.update({"value": fps, "ms_per_step": 1000.0 / fps, "config": {"workload": workload, "parallelism": "cpu"},
+                     "cpu_baseline": cb, "gpu_launches": 0,
+                     "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}})
+        return base
+
+    lib, sc, _ = _refgpu_objects(args, torch, vol)
+    accum = torch.zeros((npx, 4), dtype=torch.float32, device=device)
+    color = torch.zeros(npx, dtype=torch.int32, device=device)
+    depth = torch.zeros(npx, dtype=torch.float32, device=device)
+    fb = capi.frame_buffers(accum.data_ptr(), color.data_ptr(), depth.data_ptr())
+    host_color = torch.empty(npx, dtype=torch.int32, pin_memory=True)
+    stream = torch.cuda.current_stream().cuda_stream
+    mk = lambda fid: capi.frame_params(W, H, capi.DVR_FORMAT_UFIXED8_RGBA_SRGB, capi.DVR_INTEGRATOR_DEFAULT, fid, -1, 1,
+                                       args.rate, (0.1, 0.1, 0.1, 1.0))
+    cam, _ = orbit(args)
+    for i in range(args.warmup):
+        lib.refgpu_render(C.byref(mk(i)), C.byref(cam), sc, C.byref(fb), C.c_void_p(stream))
+    torch.cuda.synchronize()
+    sampler = ClockSampler(device.index)
+    sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(args.steps):
+        lib.refgpu_render(C.byref(mk(args.warmup + i)), C.byref(cam), sc, C.byref(fb), C.c_void_p(stream))
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / args.steps
+    clocks = sampler.stop()
+
+    def e2e_step(i):
+        cam_i, _ = orbit(args, az_deg=30.0 + 0.05 * i)
+        lib.refgpu_render(C.byref(mk(0)), C.byref(cam_i), sc, C.byref(fb), C.c_void_p(stream))
+        host_color.copy_(color, non_blocking=True)
+        torch.cuda.synchronize()
+
+    for i in range(3):
+        e2e_step(i)
+    t0 = time.perf_counter()
+    for i in range(args.steps):
+        e2e_step(i)
+    e2e_fps = args.steps / (time.perf_counter() - t0)
+    base.update({
+        "value": 1000.0 / ms, "ms_per_step": ms,
+        "config": {"workload": workload, "parallelism": "single (the reference has no multi-GPU path)",
+                   "reference_kind": "O-gpu: VisRTX device headers (gpu/volumeIntegration.h, sampleSpatialField.h, "
+                                     "gpu_util.h ...) compiled for sm_100a, one thread per pixel, OptiX volume-BVH "
+                                     "trace replaced by the slab test; VisRTX proper cannot be built here"},
+        "gpu_launches": args.steps * 4,
+        "cpu_baseline": {"value": 1000.0 / ms, "unit": "frames/s", "cores": 0, "kind": "reference",
+                         "sample": "full frames on the B200 (the reference is GPU code; see config.reference_kind)"},
+        "e2e": {"value": e2e_fps, "unit": "frames/s", "h2d_bytes_per_step": 4 * 1024, "d2h_bytes_per_step": npx * 4},
+        "clocks": clocks,
+    })
+    return base
+
+
+# ---------------------------------------------------------------------------------------------------------
+def main():
+    args = parse_args()
+    import torch
+    if not torch.cuda.is_available():
+        print(json.dumps({"error": "no CUDA device: the DVR path has no CPU fallback"}))
+        sys.exit(1)
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    if args.impl == "reference":
+        # the reference has no multi-GPU path: rank 0 alone runs it, the other ranks leave without work
+        if rank == 0:
+            print(json.dumps(run_reference(args, torch, None, 0, world)), flush=True)
+        return
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", 0)))
+        dist.init_process_group("nccl")
+    try:
+        out = run_ours(args, torch, dist, rank, world)
+        if rank == 0:
+            print(json.dumps(out), flush=True)
+    finally:
+        if dist is not None and dist.is_initialized():
+            dist.barrier()
+            dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -44,6 +44,7 @@ int oracle_tf_discretize(const float *color, size_t nColor, int colorChannels, c
     size_t nOpacity, const float uniformColor[4], float uniformOpacity, const float valueRange[2], float *outRgba);
 float oracle_tex3d(const float *voxels, const int dims[3], float u, float v, float w);
 void oracle_tex1d_tf(const float *tf, float coord, float out[4]);
+void oracle_philox_block(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]);
 void oracle_philox_uniforms(uint64_t seed, uint64_t offset, int n, float *out);
 /* renders launch rows [rowBegin,rowEnd) (0,0 = all); samplesOut = field fetches */
 int oracle_render(const DvrFrameParams *params, const DvrCamera *camera, const OracleVolume *volumes, int nVolumes,

@@ -320,3 +320,88 @@ def compare_color(a: np.ndarray, b: np.ndarray, fmt: int):
     mse = float(np.mean((d / 255.0) ** 2))
     psnr = 99.0 if mse == 0 else 10.0 * np.log10(1.0 / mse)
     return float(d.max()), psnr
+
+
+# ------------------------------------------------------------------------------------------------------------
+# The scene zoo shared by the golden-fixture generator (tests/golden/make_golden.py, run on a B200 with
+# O-gpu) and the parity tests.  name -> (SceneDesc, frames, checkerboard)
+# ------------------------------------------------------------------------------------------------------------
+def _rot_y(deg, tx=0.0, ty=0.0, tz=0.0):
+    """world->object 3x4 for an object rotated by `deg` about y and translated by t (inverse = R^T (p - t))."""
+    import math
+    c, s = math.cos(math.radians(deg)), math.sin(math.radians(deg))
+    # object->world R = [[c,0,s],[0,1,0],[-s,0,c]], world->object = R^T, translation -R^T t
+    r = [[c, 0.0, -s], [0.0, 1.0, 0.0], [s, 0.0, c]]
+    t = [-(r[i][0] * tx + r[i][1] * ty + r[i][2] * tz) for i in range(3)]
+    return tuple(float(np.float32(v)) for i in range(3) for v in (r[i][0], r[i][1], r[i][2], t[i]))
+
+
+def scene_zoo():
+    zoo = {}
+    W = H = 96
+    # C1-style: ML 48^3, raycast at three sampling rates
+    for rate in (0.125, 0.5, 1.0):
+        zoo[f"ml48_raycast_r{rate}"] = (default_scene(48, W, H, rate=rate), 1, False)
+    # default renderer: jittered pixels, 2 spp, 3 accumulated frames, float colour + aux channels
+    s = default_scene(40, W, H, rate=0.5, integrator=capi.DVR_INTEGRATOR_DEFAULT, num_iterations=2,
+                      fmt=capi.DVR_FORMAT_FLOAT32_VEC4, channels=("depth", "primId", "objId", "instId", "albedo", "normal"))
+    zoo["ml40_default_spp2_f3_float"] = (s, 3, False)
+    # UFIXED8_VEC4 (linear) colour, no depth channel
+    s = default_scene(32, W, H, rate=0.5, fmt=capi.DVR_FORMAT_UFIXED8_VEC4, channels=())
+    zoo["ml32_unorm8_nodepth"] = (s, 1, False)
+    # checkerboard: 6 passes (crosses the frameID increment), odd image size
+    s = default_scene(32, 75, 53, rate=0.5, integrator=capi.DVR_INTEGRATOR_DEFAULT)
+    zoo["ml32_checkerboard_p6"] = (s, 6, True)
+    # semi-transparent blobs, large unit distance (long marches, no early termination)
+    s = default_scene(48, W, H, rate=1.0, field="blobs")
+    s.volumes[0].unit_distance = 1.5
+    zoo["blobs48_translucent"] = (s, 1, False)
+    # orthographic camera, non-cubic dims, anisotropic spacing, value range outside [0,1], nearest filter variant
+    rng = np.random.default_rng(7)
+    vox = (rng.random((20, 28, 36), dtype=np.float32) * 3.0 - 1.0).astype(np.float32)
+    tf = capi.tf_discretize(color=scenes.tsd_default_colormap(16), opacity=np.array([0.0, 0.2, 0.9, 0.1, 1.0], np.float32),
+                            value_range=(-1.0, 2.0))
+    for nearest in (False, True):
+        v = VolumeDesc(vox, origin=(0.5, -1.0, 2.0), spacing=(0.1, 0.15, 0.2), nearest=nearest, tf=tf,
+                       value_range=(-1.0, 2.0), unit_distance=0.4, vol_id=11, inst_id=5)
+        lo, hi = v.bounds()
+        c = 0.5 * (lo + hi)
+        cam = capi.camera_orthographic((float(c[0]) + 3.0, float(c[1]) + 2.0, float(c[2]) + 6.0), (-3.0, -2.0, -6.0),
+                                       (0.0, 1.0, 0.0), 6.0, 1.25)
+        zoo["noise_ortho_" + ("nearest" if nearest else "linear")] = (
+            SceneDesc([v], 100, 80, cam, volume_sampling_rate=0.5, background=(0.0, 0.2, 0.4, 0.5)), 1, False)
+    # fixed-point fields
+    base = scenes.blobs_np(32)
+    for name, dt, arr in (("u8", capi.DVR_UFIXED8, np.round(base * 255).astype(np.uint8)),
+                          ("u16", capi.DVR_UFIXED16, np.round(base * 65535).astype(np.uint16)),
+                          ("i16", capi.DVR_FIXED16, np.round((base * 2 - 1) * 32767).astype(np.int16)),
+                          ("i8", capi.DVR_FIXED8, np.round((base * 2 - 1) * 127).astype(np.int8))):
+        s = default_scene(32, W, H, rate=0.5)
+        s.volumes[0].voxels = arr
+        s.volumes[0].data_type = dt
+        s.volumes[0].unit_distance = 0.5
+        if name.startswith("i"):
+            s.volumes[0].value_range = (-1.0, 1.0)
+            s.volumes[0].tf = capi.tf_discretize(color=scenes.tsd_default_colormap(256), value_range=(-1.0, 1.0))
+        zoo[f"blobs32_{name}"] = (s, 1, False)
+    # two volumes: one rotated+translated instance overlapping the other; thin-lens perspective camera
+    a = default_scene(32, W, H, rate=0.5)
+    v0 = a.volumes[0]
+    v1 = VolumeDesc(scenes.blobs_np(24), origin=(-0.5, -0.5, -0.5), spacing=(1.0 / 23,) * 3,
+                    tf=capi.tf_discretize(uniform_color=(0.9, 0.8, 0.1, 0.7), uniform_opacity=0.6),
+                    unit_distance=0.2, vol_id=21, inst_id=9, world_to_object=_rot_y(25.0, 0.9, 0.2, 0.4))
+    pose = scenes.orbit_camera((-1, -1, -1), (1.5, 1, 1), W, H, az_deg=35.0, el_deg=15.0, dist_scale=1.2)
+    cam = capi.camera_perspective(pose.position, pose.direction, pose.up, pose.fovy, pose.aspect, 4.0, 0.05)
+    zoo["two_volumes_lens"] = (SceneDesc([v0, v1], W, H, cam, volume_sampling_rate=0.5,
+                                         integrator=capi.DVR_INTEGRATOR_DEFAULT), 2, False)
+    # camera inside the volume + image region crop
+    s = default_scene(32, W, H, rate=0.5)
+    s.camera = capi.camera_perspective((0.1, 0.0, 0.2), (0.3, -0.2, -1.0), (0.0, 1.0, 0.0), 1.2, 1.0,
+                                       region=(0.1, 0.2, 0.8, 0.9))
+    s.volumes[0].unit_distance = 1.0
+    zoo["camera_inside_region"] = (s, 1, False)
+    # empty world (no volume instance): background only
+    s = default_scene(8, 40, 24, rate=0.5)
+    s.volumes = []
+    zoo["empty_world"] = (s, 1, False)
+    return zoo

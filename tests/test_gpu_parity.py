@@ -1,0 +1,299 @@
+"""GPU suite: the CUDA path, called through the C-ABI, against
+  * the committed O-gpu golden renders (reference device code on a B200),
+  * O-gpu run live on this GPU (when oracle/_ref/libref_gpu_dvr.so travelled with the snapshot),
+  * O-cpu on the same seeded inputs,
+and the size-independent properties of the path at BASELINE sizes.
+Tolerances: north_star — per pixel <= 2/255 after tonemap, PSNR >= 45 dB (ERT-threshold outliers as in
+test_oracle_golden.py); the macrocell-skipping and sort-first variants must be BIT-identical."""
+import os
+
+import numpy as np
+import pytest
+
+import dvr_harness as H
+import oracle_binding as ob
+from visrtx_b200 import capi, scenes
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+ZOO = H.scene_zoo()
+
+
+def _pix_diff(a, b, fmt):
+    if fmt == capi.DVR_FORMAT_FLOAT32_VEC4:
+        return np.abs(a - b).max(axis=-1) * 255.0
+    return np.abs(H.unpack_rgba8(a) - H.unpack_rgba8(b)).max(axis=-1)
+
+
+def _check(got, want, scene, frames=1, strict=False, name=""):
+    max_d, psnr = H.compare_color(got["color"], want["color"], scene.fmt)
+    d = _pix_diff(got["color"], want["color"], scene.fmt)
+    assert psnr >= 45.0, (name, psnr)
+    assert (d <= 2).mean() >= 0.999, (name, float((d <= 2).mean()))
+    assert max_d <= (2.0 if strict else 6.0), (name, max_d)
+    if "depth" in got and "depth" in want:
+        np.testing.assert_allclose(got["depth"], want["depth"], rtol=2e-5, atol=1e-5)
+    for key in ("primId", "objId", "instId"):
+        if key in got and key in want:
+            assert (got[key] == want[key]).mean() >= 0.999, (name, key)
+    for key in ("albedo", "normal"):
+        if key in got and key in want:
+            assert np.percentile(np.abs(got[key] - want[key]), 99.9) <= 0.02 * frames * scene.num_iterations
+
+
+@pytest.mark.parametrize("name", sorted(ZOO))
+def test_cuda_matches_golden_reference_renders(name):
+    scene, frames, cb = ZOO[name]
+    g = np.load(os.path.join(GOLD, "refgpu_scenes.npz"))
+    want = {k.split("/", 1)[1]: g[k] for k in g.files if k.startswith(name + "/")}
+    got = H.render_cuda(scene, frames=frames, checkerboard=cb)
+    _check(got, want, scene, frames, name=name)
+
+
+@pytest.mark.parametrize("name", sorted(ZOO))
+def test_cuda_matches_oracle_cpu(name):
+    scene, frames, cb = ZOO[name]
+    got = H.render_cuda(scene, frames=frames, checkerboard=cb)
+    want = H.render_oracle(scene, frames=frames, checkerboard=cb)
+    _check(got, want, scene, frames, name=name)
+
+
+@pytest.mark.parametrize("name", ["ml48_raycast_r0.5", "two_volumes_lens", "ml32_checkerboard_p6", "blobs32_u16"])
+def test_cuda_matches_reference_device_code_live(name):
+    if not ob.have_ref_gpu():
+        pytest.skip("oracle/_ref/libref_gpu_dvr.so not present")
+    scene, frames, cb = ZOO[name]
+    got = H.render_cuda(scene, frames=frames, checkerboard=cb)
+    want = H.render_refgpu(scene, frames=frames, checkerboard=cb)
+    _check(got, want, scene, frames, strict=True, name=name)
+    # most pixels agree to the last bit of the float accumulation buffer
+    assert (got["accum"] == want["accum"]).all(axis=-1).mean() > 0.9
+
+
+def test_config_c1_full_size():
+    """BASELINE config 1: 64^3 Marschner-Lobb, 512x512, 1 spp, raycast."""
+    scene = H.default_scene(64, 512, 512, rate=0.5)
+    got = H.render_cuda(scene)
+    want = H.render_oracle(scene)
+    _check(got, want, scene, name="C1")
+    if ob.have_ref_gpu():
+        _check(got, H.render_refgpu(scene), scene, strict=True, name="C1/O-gpu")
+
+
+@pytest.mark.parametrize("name", ["ml48_raycast_r1.0", "blobs48_translucent", "two_volumes_lens", "blobs32_u8"])
+def test_macrocell_skipping_is_bit_identical(name):
+    scene, frames, cb = ZOO[name]
+    if name.startswith("blobs"):
+        for v in scene.volumes:  # make most of the volume fully transparent
+            v.tf = capi.tf_discretize(color=scenes.sparse_colormap(256, 0.4))
+    a = H.render_cuda(scene, frames=frames, checkerboard=cb, skip=False)
+    b = H.render_cuda(scene, frames=frames, checkerboard=cb, skip=True)
+    for k in a:
+        assert np.array_equal(a[k], b[k]), (name, k)
+
+
+def test_macrocell_skipping_actually_skips_and_majorants_are_conservative():
+    import torch
+    n = 96
+    vox = scenes.shells_np(n, n_shells=4, radius_frac=0.12, width_frac=0.01)
+    sp = 2.0 / (n - 1)
+    tf = capi.tf_discretize(color=scenes.sparse_colormap(256, 0.3))
+    v = H.VolumeDesc(vox, origin=(-1, -1, -1), spacing=(sp,) * 3, tf=tf, unit_distance=4 * sp)
+    pose = scenes.orbit_camera((-1, -1, -1), (1, 1, 1), 256, 256, dist_scale=1.0)
+    cam = capi.camera_perspective(pose.position, pose.direction, pose.up, pose.fovy, pose.aspect)
+    scene = H.SceneDesc([v], 256, 256, cam, volume_sampling_rate=1.0)
+    cs = H.CudaScene(scene)
+    try:
+        s0 = cs.render(stats=True, skip=False)
+        a = cs.download()
+        s1 = cs.render(stats=True, skip=True)
+        b = cs.download()
+        # fetches are issued in batches, so up to DVR_BATCH-1 prefetched samples past early termination
+        # are counted per ray; apart from that the lattice is identical
+        assert abs(s1["samplesTaken"] + s1["samplesSkipped"] - s0["samplesTaken"]) <= 4 * s0["raysHit"]
+        assert s1["samplesSkipped"] > 0.5 * s0["samplesTaken"]
+        for k in a:
+            assert np.array_equal(a[k], b[k]), k
+        # macrocell ranges: conservative w.r.t. a numpy min/max over the cell + apron
+        (gx, gy, gz), ptr = cs.fields[0].macrocells()
+        assert (gx, gy, gz) == (6, 6, 6)
+        rng = torch.empty((gz, gy, gx, 2), dtype=torch.float32, device="cuda")
+        import ctypes
+        torch.cuda.synchronize()
+        ctypes.CDLL("libcudart.so").cudaMemcpy(ctypes.c_void_p(rng.data_ptr()), ctypes.c_void_p(ptr),
+                                               ctypes.c_size_t(rng.numel() * 4), ctypes.c_int(3))
+        r = rng.cpu().numpy()
+        for cz in range(gz):
+            for cy in range(gy):
+                for cx in range(gx):
+                    blk = vox[max(cz * 16 - 1, 0):cz * 16 + 17, max(cy * 16 - 1, 0):cy * 16 + 17,
+                              max(cx * 16 - 1, 0):cx * 16 + 17]
+                    assert r[cz, cy, cx, 0] == blk.min() and r[cz, cy, cx, 1] == blk.max()
+        lo, hi = cs.fields[0].value_range()
+        assert lo == vox.min() and hi == vox.max()
+    finally:
+        cs.destroy()
+
+
+def test_sort_first_tiles_reassemble_bit_identically():
+    """Rendering tile rows rank-by-rank into one buffer gives exactly the single-GPU frame."""
+    scene, _, _ = ZOO["ml48_raycast_r0.5"]
+    full = H.render_cuda(scene)
+    for ranks in (2, 3, 8):
+        cs = H.CudaScene(scene)
+        try:
+            for r in range(ranks):
+                cs.render(tile_rank=r, tile_ranks=ranks)
+            part = cs.download()
+        finally:
+            cs.destroy()
+        for k in full:
+            assert np.array_equal(full[k], part[k]), (ranks, k)
+
+
+@pytest.mark.parametrize("nslabs", [2, 4])
+def test_sort_last_slabs_composite_to_the_single_gpu_image(nslabs):
+    """z-slabs rendered on the global lattice + `over` compositing + resolve == the one-pass frame."""
+    import torch
+    scene = H.default_scene(64, 160, 120, rate=0.5, field="blobs")
+    scene.volumes[0].unit_distance = 0.5
+    want = H.render_cuda(scene)
+    n = scene.width * scene.height
+    nz = 64
+    bounds = [round(i * nz / nslabs) for i in range(nslabs + 1)]
+    parts = []
+    p = H._params(scene, 0, -1)
+    for i in range(nslabs):
+        cs = H.CudaScene(scene, slab=(bounds[i], bounds[i + 1]))
+        rgba = torch.zeros((n, 4), dtype=torch.float32, device="cuda")
+        depth = torch.zeros(n, dtype=torch.float32, device="cuda")
+        capi.render_partial(p, scene.camera, cs.instances, rgba.data_ptr(), depth.data_ptr())
+        torch.cuda.synchronize()
+        parts.append((rgba, depth, cs))
+    # view order along z: the camera of default_scene looks from +z towards -z => slab nslabs-1 is in front
+    cam_z_positive = scene.camera.pos[2] > 0
+    order = list(range(nslabs))[::-1] if cam_z_positive else list(range(nslabs))
+    front_rgba, front_depth, _ = parts[order[0]]
+    for j in order[1:]:
+        capi.composite_over(front_rgba.data_ptr(), front_depth.data_ptr(), parts[j][0].data_ptr(),
+                            parts[j][1].data_ptr(), 0, n, False)
+    out = H.CudaScene(scene)
+    try:
+        capi.resolve(p, front_rgba.data_ptr(), front_depth.data_ptr(), scene.volumes[0].vol_id,
+                     scene.volumes[0].inst_id, out.fb, 0, n)
+        got = out.download()
+    finally:
+        out.destroy()
+        for _, _, cs in parts:
+            cs.destroy()
+    d = _pix_diff(got["color"], want["color"], scene.fmt)
+    assert (d <= 1).mean() >= 0.999 and d.max() <= 3
+    np.testing.assert_allclose(got["depth"], want["depth"], rtol=1e-6)
+    assert np.array_equal(got["objId"], want["objId"])
+
+
+def test_progressive_accumulation_converges_and_counts():
+    """64 accumulated frames (KHR_FRAME_ACCUMULATION semantics): matches O-cpu's accumulated image (MAE)."""
+    scene = H.default_scene(32, 64, 64, rate=0.5, integrator=capi.DVR_INTEGRATOR_DEFAULT,
+                            fmt=capi.DVR_FORMAT_FLOAT32_VEC4)
+    got = H.render_cuda(scene, frames=64)
+    want = H.render_oracle(scene, frames=64)
+    mae = float(np.abs(got["color"] - want["color"]).mean())
+    assert mae < 0.5 / 255, mae
+    one = H.render_cuda(scene, frames=1)
+    # accumulation reduces the jitter noise: the 64-frame image is smoother than the 1-frame image
+    lap = lambda img: np.abs(np.diff(img.reshape(64, 64, 4)[..., :3], axis=1)).mean()
+    assert lap(got["color"]) < lap(one["color"])
+
+
+def test_float64_and_float16_fields():
+    import torch
+    base = scenes.blobs_np(24)
+    s32 = H.default_scene(24, 64, 64, rate=0.5, field="blobs")
+    s32.volumes[0].unit_distance = 0.5
+    ref = H.render_cuda(s32)
+    s64 = H.default_scene(24, 64, 64, rate=0.5, field="blobs")
+    s64.volumes[0].unit_distance = 0.5
+    s64.volumes[0].voxels = base.astype(np.float64)
+    s64.volumes[0].data_type = capi.DVR_FLOAT64
+    got = H.render_cuda(s64)
+    assert np.array_equal(ref["color"], got["color"])
+    s16 = H.default_scene(24, 64, 64, rate=0.5, field="blobs")
+    s16.volumes[0].unit_distance = 0.5
+    s16.volumes[0].voxels = base.astype(np.float16)
+    s16.volumes[0].data_type = capi.DVR_FLOAT16
+    got16 = H.render_cuda(s16)
+    s16o = H.default_scene(24, 64, 64, rate=0.5, field="blobs")
+    s16o.volumes[0].unit_distance = 0.5
+    s16o.volumes[0].voxels = base.astype(np.float16).astype(np.float32)
+    want16 = H.render_oracle(s16o)
+    _check(got16, want16, s16, name="f16")
+
+
+def test_device_pointer_field_upload_equals_host_upload():
+    """ANARI_NV_ARRAY_CUDA: a field created from a device pointer renders like one created from host memory."""
+    import torch
+    scene, _, _ = ZOO["ml48_raycast_r0.5"]
+    a = H.render_cuda(scene)
+    v = scene.volumes[0]
+    dev = torch.from_numpy(v.voxels).cuda()
+    f = capi.Field.create_structured(dev.data_ptr(), True, capi.DVR_FLOAT32, v.dims, v.origin, v.spacing)
+    vol = capi.Volume.create(f, v.tf, v.value_range, v.unit_distance, v.vol_id)
+    inst, n = capi.make_instances([vol], None, [v.inst_id])
+    cs = H.CudaScene(scene)
+    try:
+        capi.render(H._params(scene, 0, -1), scene.camera, inst, n, cs.fb)
+        b = cs.download()
+    finally:
+        cs.destroy()
+        vol.destroy()
+        f.destroy()
+    for k in a:
+        assert np.array_equal(a[k], b[k]), k
+
+
+def test_full_size_properties_c2():
+    """BASELINE config 2 sizes (1024^3 f32, 1920x1080): properties that need no oracle run.
+    idempotence (same frameID twice => identical bits), skipping == no skipping, opacity in [0,1],
+    background where the volume is missed, sample count equals the sum over rays of lattice points."""
+    import torch
+    n, W, Hh = 1024, 1920, 1080
+    vol = scenes.marschner_lobb_torch(n, "cuda")
+    f = capi.Field.create_structured(vol.data_ptr(), True, capi.DVR_FLOAT32, (n, n, n), (0, 0, 0), (1, 1, 1))
+    del vol
+    tf = capi.tf_discretize(color=scenes.tsd_default_colormap(256))
+    v = capi.Volume.create(f, tf, (0.0, 1.0), 256.0, 0)
+    inst, ni = capi.make_instances([v], None, [0])
+    pose = scenes.orbit_camera((0, 0, 0), (n - 1,) * 3, W, Hh)
+    cam = capi.camera_perspective(pose.position, pose.direction, pose.up, pose.fovy, pose.aspect)
+    npx = W * Hh
+    accum = torch.empty((npx, 4), dtype=torch.float32, device="cuda")
+    color = torch.empty((npx, 4), dtype=torch.float32, device="cuda")
+    depth = torch.empty(npx, dtype=torch.float32, device="cuda")
+    fb = capi.frame_buffers(accum.data_ptr(), color.data_ptr(), depth.data_ptr())
+    try:
+        outs = []
+        for skip in (False, False, True):
+            p = capi.frame_params(W, Hh, capi.DVR_FORMAT_FLOAT32_VEC4, capi.DVR_INTEGRATOR_RAYCAST, 0, -1, 1, 0.5,
+                                  (0.1, 0.1, 0.1, 1.0), skip=skip)
+            capi.render(p, cam, inst, ni, fb)
+            torch.cuda.synchronize()
+            outs.append((color.clone(), depth.clone()))
+        assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][1], outs[1][1])
+        assert torch.equal(outs[0][0], outs[2][0])
+        c, d = outs[0]
+        miss = d >= 1e29
+        assert 0.85 < miss.float().mean().item() < 0.97
+        assert torch.allclose(c[miss][:, :3], torch.tensor([0.1, 0.1, 0.1], device="cuda"), atol=1e-6)
+        assert c[:, 3].min().item() >= 0.999 and c[:, 3].max().item() <= 1.0 + 1e-5  # opaque background
+        assert torch.isfinite(c).all()
+        st = torch.zeros(4, dtype=torch.int64, device="cuda")
+        capi.render_instrumented(p, cam, inst, ni, fb, st.data_ptr())
+        torch.cuda.synchronize()
+        taken, skipped, rays, cells = st.tolist()
+        assert rays == int((~miss).sum().item())
+        assert cells > 0.98 * 64 ** 3 and skipped == 0
+        assert 300 < taken / rays < 1800  # chord lengths of a 1024^3 cube at 1 voxel per step
+    finally:
+        v.destroy()
+        f.destroy()
