@@ -1,0 +1,161 @@
+"""CPU suite, part 3: the ANARI device library — symbols, object/parameter/lifetime semantics that need
+no GPU, introspection tables, error reporting through the status callback (never exceptions), and the
+reference's multi-threaded object-creation smoke test (tests/api/TestMultiThreadedObjectCreation.cpp)."""
+import ctypes as C
+import os
+import re
+import threading
+
+import numpy as np
+import pytest
+
+from conftest import HAS_GPU
+from visrtx_b200 import anari as A
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_entry_point():
+    hdr = open(os.path.join(ROOT, "include", "anari", "anari.h")).read()
+    hdr += open(os.path.join(ROOT, "include", "anari", "ext", "visrtx_b200.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    declared = set(re.findall(r"\b(anari[A-Z][A-Za-z0-9]+|makeVisRTXDevice|visrtxGet[A-Za-z]+)\s*\(", hdr))
+    assert declared == set(A.API_SYMBOLS)
+    for n in declared:
+        assert hasattr(A.lib, n)
+
+
+def test_load_library_names_and_device_subtypes():
+    d = A.Device()
+    assert A.lib.anariLoadLibrary(b"no_such_library", None, None) is None
+    p = A.lib.anariGetDeviceSubtypes(d.library)
+    assert p[0] == b"default" and not p[1]
+    ext = d.get_property(d.handle, "extension", A.STRING_LIST)
+    for e in ("ANARI_KHR_SPATIAL_FIELD_STRUCTURED_REGULAR", "ANARI_KHR_VOLUME_TRANSFER_FUNCTION1D",
+              "ANARI_KHR_FRAME_ACCUMULATION", "ANARI_NV_FRAME_BUFFERS_CUDA", "ANARI_NV_ARRAY_CUDA"):
+        assert e in ext
+    assert d.get_property(d.handle, "version.major", A.INT32) == 0
+    d.close()
+
+
+def test_direct_device_construction():
+    d = A.Device(via_library=False)  # makeVisRTXDevice, visrtx.h:46-52
+    assert d.handle
+    d.close()
+
+
+def test_object_subtypes_introspection():
+    d = A.Device()
+    assert d.subtypes(A.CAMERA) == ["perspective", "orthographic"]
+    assert d.subtypes(A.SPATIAL_FIELD) == ["structuredRegular"]
+    assert "transferFunction1D" in d.subtypes(A.VOLUME) and "scivis" in d.subtypes(A.VOLUME)
+    assert {"default", "raycast"} <= set(d.subtypes(A.RENDERER))
+    assert d.subtypes(A.WORLD) == []
+    d.close()
+
+
+def test_parameters_and_lifetime_without_gpu():
+    d = A.Device()
+    cam = d.new("Camera", "perspective")
+    d.set(cam, "position", A.FLOAT32_VEC3, (1, 2, 3))
+    d.set(cam, "fovy", A.FLOAT32, 0.5)
+    d.unset(cam, "fovy")
+    d.commit(cam)
+    d.retain(cam)
+    d.release(cam)
+    d.release(cam)
+    vol = d.new("Volume", "transferFunction1D")
+    col = d.new_array1d(np.array([[1, 0, 0], [0, 0, 1]], np.float32), A.FLOAT32_VEC3)
+    d.set(vol, "color", A.ARRAY1D, col)
+    d.release(col)  # the volume's parameter keeps it alive (INTERNAL ref) and privatises the shared data
+    d.commit(vol)
+    d.release(vol)
+    assert not [m for m in d.messages if m[0] <= A.SEVERITY_ERROR]
+    d.close()
+
+
+def test_managed_array_is_zero_initialised_and_mappable():
+    d = A.Device()
+    a = A.lib.anariNewArray1D(d.handle, None, None, None, A.FLOAT32, 16)
+    p = d.map_array(a)
+    v = np.ctypeslib.as_array(C.cast(p, C.POINTER(C.c_float)), shape=(16,))
+    assert np.all(v == 0)
+    v[:] = 3.0
+    d.unmap_array(a)
+    p2 = d.map_array(a)
+    assert np.all(np.ctypeslib.as_array(C.cast(p2, C.POINTER(C.c_float)), shape=(16,)) == 3.0)
+    d.unmap_array(a)
+    d.release(a)
+    d.close()
+
+
+def test_captured_array_deleter_runs_on_release():
+    d = A.Device()
+    calls = []
+    data = np.arange(8, dtype=np.float32)
+    deleter = A.MemoryDeleter(lambda user, mem: calls.append(mem))
+    a = A.lib.anariNewArray1D(d.handle, data.ctypes.data, C.cast(deleter, C.c_void_p), None, A.FLOAT32, 8)
+    d.release(a)
+    assert calls == [data.ctypes.data]
+    d.close()
+
+
+def test_errors_are_reported_not_thrown():
+    d = A.Device()
+    bad = A.lib.anariNewArray1D(d.handle, None, None, None, 424242, 4)
+    assert bad is None
+    assert any(m[0] == A.SEVERITY_ERROR for m in d.messages)
+    d.messages.clear()
+    # frame with nothing attached: render is skipped with an error message
+    f = d.new("Frame")
+    d.commit(f)
+    d.render(f)
+    assert any("skipping render" in m[2] or "failed" in m[2] or "CUDA" in m[2] for m in d.messages)
+    assert d.wait(f) == 1
+    d.release(f)
+    d.close()
+
+
+@pytest.mark.skipif(HAS_GPU, reason="checks the no-device path")
+def test_device_init_failure_is_sticky_and_loud():
+    d = A.Device()
+    d.set(d.handle, "forceInit", A.BOOL, 1)
+    d.commit(d.handle)
+    assert any(m[0] == A.SEVERITY_FATAL_ERROR and "no CPU fallback" in m[2] for m in d.messages)
+    n = len(d.messages)
+    f = d.new("Frame")
+    r = d.new("Renderer", "default")
+    c = d.new("Camera", "perspective")
+    w = d.new("World")
+    for k, t, o in (("renderer", A.RENDERER, r), ("camera", A.CAMERA, c), ("world", A.WORLD, w)):
+        d.set(f, k, t, o)
+    d.commit(f)
+    d.render(f)
+    assert len(d.messages) > n and any("failed to init" in m[2] for m in d.messages[n:])
+    d.close()
+
+
+def test_multithreaded_object_creation():
+    """4 threads x 100 x {camera, world, frame, renderer, volume} create/release concurrently."""
+    d = A.Device()
+    errs = []
+
+    def work():
+        try:
+            for _ in range(100):
+                objs = [d.new("Camera", "perspective"), d.new("World"), d.new("Frame"), d.new("Renderer", "default"),
+                        d.new("Volume", "transferFunction1D"), d.new("Light", "directional"),
+                        d.new("Geometry", "triangle")]
+                for o in objs:
+                    d.commit(o)
+                for o in objs:
+                    d.release(o)
+        except Exception as e:  # pragma: no cover
+            errs.append(e)
+
+    ts = [threading.Thread(target=work) for _ in range(4)]
+    [t.start() for t in ts]
+    [t.join() for t in ts]
+    assert not errs
+    assert not [m for m in d.messages if m[0] == A.SEVERITY_FATAL_ERROR]
+    d.close()

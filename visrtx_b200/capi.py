@@ -10,7 +10,7 @@ import os
 from typing import Optional, Sequence
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libdvr_b200.so")
+LIB_PATH = os.environ.get("DVR_B200_LIB") or os.path.join(_HERE, "libdvr_b200.so")
 
 DVR_TF_SIZE = 256
 DVR_MACROCELL_WIDTH = 16

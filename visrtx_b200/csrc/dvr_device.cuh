@@ -75,19 +75,41 @@ struct BuffersDev
 // ---------------------------------------------------------------------------------------
 // small vector helpers (no glm in the product)
 // ---------------------------------------------------------------------------------------
+// All arithmetic that decides WHICH samples a ray takes (ray set-up, slab test, sample positions) is
+// written with explicit round-to-nearest intrinsics: __fmul_rn/__fadd_rn are never contracted and
+// __fmaf_rn is a fused multiply-add, so every template instantiation of the kernels (skipping on/off,
+// stats, slab) executes bit-identical arithmetic.  The FMA placement follows what nvcc's default
+// contraction produces for the reference's expressions (a*b + c => fma).
 __device__ __forceinline__ float3 f3(float x, float y, float z) { return make_float3(x, y, z); }
-__device__ __forceinline__ float3 operator+(float3 a, float3 b) { return f3(a.x + b.x, a.y + b.y, a.z + b.z); }
-__device__ __forceinline__ float3 operator-(float3 a, float3 b) { return f3(a.x - b.x, a.y - b.y, a.z - b.z); }
-__device__ __forceinline__ float3 operator*(float3 a, float3 b) { return f3(a.x * b.x, a.y * b.y, a.z * b.z); }
-__device__ __forceinline__ float3 operator*(float3 a, float s) { return f3(a.x * s, a.y * s, a.z * s); }
-__device__ __forceinline__ float3 operator*(float s, float3 a) { return f3(a.x * s, a.y * s, a.z * s); }
+__device__ __forceinline__ float3 operator+(float3 a, float3 b)
+{
+  return f3(__fadd_rn(a.x, b.x), __fadd_rn(a.y, b.y), __fadd_rn(a.z, b.z));
+}
+__device__ __forceinline__ float3 operator-(float3 a, float3 b)
+{
+  return f3(__fsub_rn(a.x, b.x), __fsub_rn(a.y, b.y), __fsub_rn(a.z, b.z));
+}
+__device__ __forceinline__ float3 operator*(float3 a, float3 b)
+{
+  return f3(__fmul_rn(a.x, b.x), __fmul_rn(a.y, b.y), __fmul_rn(a.z, b.z));
+}
+__device__ __forceinline__ float3 operator*(float3 a, float s)
+{
+  return f3(__fmul_rn(a.x, s), __fmul_rn(a.y, s), __fmul_rn(a.z, s));
+}
+__device__ __forceinline__ float3 operator*(float s, float3 a) { return a * s; }
+// a*s + b, fused
+__device__ __forceinline__ float3 madd3(float3 a, float s, float3 b)
+{
+  return f3(__fmaf_rn(a.x, s, b.x), __fmaf_rn(a.y, s, b.y), __fmaf_rn(a.z, s, b.z));
+}
 __device__ __forceinline__ float max3(float3 a) { return fmaxf(fmaxf(a.x, a.y), a.z); }
 __device__ __forceinline__ float min3(float3 a) { return fminf(fminf(a.x, a.y), a.z); }
 __device__ __forceinline__ float3 normalize3(float3 v)
 {
-  // glm::normalize = v * inversesqrt(dot(v,v)); glm's CUDA inversesqrt is 1/sqrt(x)
-  const float d = v.x * v.x + v.y * v.y + v.z * v.z;
-  const float inv = 1.0f / sqrtf(d);
+  // glm::normalize = v * inversesqrt(dot(v,v)); glm's inversesqrt is 1/sqrt(x)
+  const float d = __fmaf_rn(v.z, v.z, __fmaf_rn(v.y, v.y, __fmul_rn(v.x, v.x)));
+  const float inv = __fdiv_rn(1.0f, __fsqrt_rn(d));
   return v * inv;
 }
 
@@ -157,7 +179,7 @@ struct Philox
   // _curand_uniform: x * 2^-32 + 2^-33  in (0,1]  (curand_uniform.h:69-72)
   __device__ __forceinline__ static float toUniform(uint32_t x)
   {
-    return (float)x * 2.3283064e-10f + (2.3283064e-10f / 2.0f);
+    return __fmaf_rn((float)x, 2.3283064e-10f, 2.3283064e-10f / 2.0f);
   }
 
   __device__ __forceinline__ float uniform() { return toUniform(next()); }
@@ -179,16 +201,16 @@ struct Philox
 __device__ __forceinline__ float mixf(float a, float b, float t)
 {
   // glm::mix for floats: x * (1 - a) + y * a
-  return a * (1.0f - t) + b * t;
+  return __fmaf_rn(b, t, __fmul_rn(a, __fsub_rn(1.0f, t)));
 }
 
 __device__ __forceinline__ void uniformSampleDisk(float radius, float rx, float ry, float &ox, float &oy)
 {
   // gpu/gpu_math.h uniformSampleDisk: r = sqrt(s.x)*radius, phi = 2*pi*s.y
-  const float r = sqrtf(rx) * radius;
-  const float phi = 2.0f * 3.14159265358979323846f * ry;
-  ox = r * cosf(phi);
-  oy = r * sinf(phi);
+  const float r = __fmul_rn(__fsqrt_rn(rx), radius);
+  const float phi = __fmul_rn(2.0f * 3.14159265358979323846f, ry);
+  ox = __fmul_rn(r, cosf(phi));
+  oy = __fmul_rn(r, sinf(phi));
 }
 
 __device__ __forceinline__ void cameraCreateRay(
@@ -198,18 +220,18 @@ __device__ __forceinline__ void cameraCreateRay(
   sy = mixf(c.region.y, c.region.w, sy);
   if (c.type == 0) {
     org = c.pos;
-    dir = c.p00 + sx * c.du + sy * c.dv;
+    dir = madd3(c.dv, sy, madd3(c.du, sx, c.p00));
     if (c.scaledAperture > 0.f) {
       float lx, ly;
       uniformSampleDisk(c.scaledAperture, rz, rw, lx, ly);
-      const float3 lp = (lx * c.du) + ((ly * c.aspect) * c.dv);
+      const float3 lp = madd3(c.dv, __fmul_rn(ly, c.aspect), lx * c.du);
       org = org + lp;
       dir = dir - lp;
     }
     dir = normalize3(dir);
   } else {
     dir = c.dir;
-    org = c.p00 + sx * c.du + sy * c.dv;
+    org = madd3(c.dv, sy, madd3(c.du, sx, c.p00));
   }
 }
 
@@ -221,17 +243,17 @@ __device__ __forceinline__ float clamp01(float v) { return fminf(fmaxf(v, 0.0f),
 __device__ __forceinline__ float linearToSrgb(float c)
 {
   c = clamp01(c);
-  const float hi = powf(c, 0.41666f) * 1.055f - 0.055f;
-  const float lo = c * 12.92f;
+  const float hi = __fmaf_rn(powf(c, 0.41666f), 1.055f, -0.055f);
+  const float lo = __fmul_rn(c, 12.92f);
   return (c < 0.0031308f) ? lo : hi;
 }
 
 __device__ __forceinline__ uint32_t packUnorm4x8(float r, float g, float b, float a)
 {
-  const uint32_t R = (uint32_t)(unsigned char)roundf(clamp01(r) * 255.0f);
-  const uint32_t G = (uint32_t)(unsigned char)roundf(clamp01(g) * 255.0f);
-  const uint32_t B = (uint32_t)(unsigned char)roundf(clamp01(b) * 255.0f);
-  const uint32_t A = (uint32_t)(unsigned char)roundf(clamp01(a) * 255.0f);
+  const uint32_t R = (uint32_t)(unsigned char)roundf(__fmul_rn(clamp01(r), 255.0f));
+  const uint32_t G = (uint32_t)(unsigned char)roundf(__fmul_rn(clamp01(g), 255.0f));
+  const uint32_t B = (uint32_t)(unsigned char)roundf(__fmul_rn(clamp01(b), 255.0f));
+  const uint32_t A = (uint32_t)(unsigned char)roundf(__fmul_rn(clamp01(a), 255.0f));
   return R | (G << 8) | (B << 16) | (A << 24);
 }
 
@@ -240,11 +262,12 @@ __device__ __forceinline__ void writeOutputColor(
     const BuffersDev &fb, int format, float4 accum, uint32_t idx, int frameIDplusOffset)
 {
   const float div = float(frameIDplusOffset + 1);
-  float4 c = make_float4(accum.x / div, accum.y / div, accum.z / div, accum.w / div);
-  const float m = fmaxf(1e-12f, 1.0f - fmaxf(fmaxf(c.x, c.y), c.z)); // inverseTonemap
-  c.x = c.x / m;
-  c.y = c.y / m;
-  c.z = c.z / m;
+  float4 c = make_float4(__fdiv_rn(accum.x, div), __fdiv_rn(accum.y, div), __fdiv_rn(accum.z, div),
+      __fdiv_rn(accum.w, div));
+  const float m = fmaxf(1e-12f, __fsub_rn(1.0f, fmaxf(fmaxf(c.x, c.y), c.z))); // inverseTonemap
+  c.x = __fdiv_rn(c.x, m);
+  c.y = __fdiv_rn(c.y, m);
+  c.z = __fdiv_rn(c.z, m);
   if (format == 2)
     fb.outU32[idx] = packUnorm4x8(linearToSrgb(c.x), linearToSrgb(c.y), linearToSrgb(c.z), c.w);
   else if (format == 1)
@@ -262,23 +285,23 @@ __device__ __forceinline__ void writeOutputColor(
 // ---------------------------------------------------------------------------------------
 __device__ __forceinline__ float4 tfLookup(const float4 *__restrict__ tf, float coord)
 {
-  const float xb = coord * 256.0f - 0.5f;
-  int q = __float2int_rd(xb * 256.0f + 0.5f);
+  const float xb = __fsub_rn(__fmul_rn(coord, 256.0f), 0.5f);
+  int q = __float2int_rd(__fmaf_rn(xb, 256.0f, 0.5f));
   q = max(0, min(q, 255 * 256));
   const int i = q >> 8;
   const float w1 = (float)(q & 255) * (1.0f / 256.0f);
   const float w0 = 1.0f - w1; // exact
   const float4 a = tf[i];
   const float4 b = tf[min(i + 1, 255)];
-  return make_float4(fmaf(a.x, w0, b.x * w1), fmaf(a.y, w0, b.y * w1), fmaf(a.z, w0, b.z * w1),
-      fmaf(a.w, w0, b.w * w1));
+  return make_float4(__fmaf_rn(a.x, w0, __fmul_rn(b.x, w1)), __fmaf_rn(a.y, w0, __fmul_rn(b.y, w1)),
+      __fmaf_rn(a.z, w0, __fmul_rn(b.z, w1)), __fmaf_rn(a.w, w0, __fmul_rn(b.w, w1)));
 }
 
 // position(v, range): gpu/gpu_math.h:176-180  (clamp, then multiply by the reciprocal)
 __device__ __forceinline__ float rangePosition(float v, float lo, float hi)
 {
   v = fmaxf(lo, fminf(v, hi));
-  return (v - lo) * (1.0f / (hi - lo));
+  return __fmul_rn(__fsub_rn(v, lo), __fdiv_rn(1.0f, __fsub_rn(hi, lo)));
 }
 
 } // namespace dvr

@@ -51,18 +51,18 @@ __device__ __forceinline__ void accumResults(const FrameLaunch &P, uint32_t px, 
   const int frameID = P.frameID + frameIDOffset;
 
   // tonemap: v / (1 + max(0, compMax(v)))
-  const float m = 1.0f + fmaxf(0.0f, fmaxf(fmaxf(color.x, color.y), color.z));
-  const float4 tm = make_float4(color.x / m, color.y / m, color.z / m, color.w);
+  const float m = __fadd_rn(1.0f, fmaxf(0.0f, fmaxf(fmaxf(color.x, color.y), color.z)));
+  const float4 tm = make_float4(__fdiv_rn(color.x, m), __fdiv_rn(color.y, m), __fdiv_rn(color.z, m), color.w);
 
   float4 acc;
   if (init) {
     acc = tm;
   } else {
     acc = fb.accum[idx];
-    acc.x += tm.x;
-    acc.y += tm.y;
-    acc.z += tm.z;
-    acc.w += tm.w;
+    acc.x = __fadd_rn(acc.x, tm.x);
+    acc.y = __fadd_rn(acc.y, tm.y);
+    acc.z = __fadd_rn(acc.z, tm.z);
+    acc.w = __fadd_rn(acc.w, tm.w);
   }
   fb.accum[idx] = acc;
 
@@ -145,8 +145,12 @@ struct TfSelectSingle
 // ----------------------------------------------------------------------------------------------
 // K1: one frame.  Persistent CTAs; every warp pulls 8x4-pixel tiles from a global counter.
 // ----------------------------------------------------------------------------------------------
+#ifndef DVR_OCC
+#define DVR_OCC 3 // minimum resident CTAs per SM the frame kernel is compiled for (register budget)
+#endif
+
 template <bool SKIP, bool STATS, bool SINGLE>
-__global__ void __launch_bounds__(kBlockThreads, 2) dvrFrameKernel(const __grid_constant__ FrameLaunch P)
+__global__ void __launch_bounds__(kBlockThreads, DVR_OCC) dvrFrameKernel(const __grid_constant__ FrameLaunch P)
 {
   __shared__ float4 s_tf[(SINGLE ? 1 : kMaxInlineInstances) * DVR_TF_SIZE];
 
@@ -189,8 +193,8 @@ __global__ void __launch_bounds__(kBlockThreads, 2) dvrFrameKernel(const __grid_
     for (int it = 0; it < P.numIterations; ++it) {
       // makePrimaryRay, cameraCreateRay.h:74-81
       const float4 r = rng.uniform4();
-      const float sx = (centered ? (float)px : (float)px + r.x) * P.invW;
-      const float sy = (centered ? (float)py : (float)py + r.y) * P.invH;
+      const float sx = __fmul_rn(centered ? (float)px : __fadd_rn((float)px, r.x), P.invW);
+      const float sy = __fmul_rn(centered ? (float)py : __fadd_rn((float)py, r.y), P.invH);
       float3 org, dir;
       cameraCreateRay(P.cam, sx, sy, r.z, r.w, org, dir);
 
@@ -212,11 +216,11 @@ __global__ void __launch_bounds__(kBlockThreads, 2) dvrFrameKernel(const __grid_
       const float depth = fminf(1e30f, volumeDepth);
       color = color * opacity;
       const float4 bg = P.background;
-      const float oneMinus = 1.f - opacity;
-      color.x += bg.x * oneMinus;
-      color.y += bg.y * oneMinus;
-      color.z += bg.z * oneMinus;
-      opacity += bg.w * oneMinus;
+      const float oneMinus = __fsub_rn(1.f, opacity);
+      color.x = __fmaf_rn(bg.x, oneMinus, color.x);
+      color.y = __fmaf_rn(bg.y, oneMinus, color.y);
+      color.z = __fmaf_rn(bg.z, oneMinus, color.z);
+      opacity = __fmaf_rn(bg.w, oneMinus, opacity);
       // outputColor/outputOpacity start at 0: accumulateValue(out, c, 0) == c
       accumResults(P, px, py, make_float4(color.x, color.y, color.z, opacity), depth, color, dir, 0u, objID,
           instID, it, initFrame && it == 0);
@@ -294,8 +298,8 @@ __global__ void __launch_bounds__(kBlockThreads, 2) dvrPartialKernel(const __gri
     Philox rng;
     rng.init((unsigned long long)(int)(py * P.width + px), (unsigned long long)P.frameID * 512ull);
     const float4 r = rng.uniform4();
-    const float sx = (centered ? (float)px : (float)px + r.x) * P.invW;
-    const float sy = (centered ? (float)py : (float)py + r.y) * P.invH;
+    const float sx = __fmul_rn(centered ? (float)px : __fadd_rn((float)px, r.x), P.invW);
+    const float sy = __fmul_rn(centered ? (float)py : __fadd_rn((float)py, r.y), P.invH);
     float3 org, dir;
     cameraCreateRay(P.cam, sx, sy, r.z, r.w, org, dir);
     float3 color = f3(0.f, 0.f, 0.f);

@@ -15,6 +15,21 @@ namespace dvr {
 #define DVR_BATCH 4 // field fetches issued back-to-back before compositing (memory-level parallelism)
 #endif
 
+#ifndef DVR_FASTPOW
+#define DVR_FASTPOW 0
+#endif
+// pow(1 - alpha, dt/unitDistance), volumeIntegration.h:93
+__device__ __forceinline__ float stepPow(float x, float e)
+{
+#if DVR_FASTPOW == 0
+  return powf(x, e);
+#elif DVR_FASTPOW == 1
+  return exp2f(e * log2f(x));
+#else
+  return __powf(x, e);
+#endif
+}
+
 struct MarchStats
 {
   unsigned long long taken;
@@ -26,7 +41,7 @@ __device__ __forceinline__ bool intersectVolumeBox(
     const float3 lo, const float3 hi, const float3 org, const float3 dir, float tmin, float tmax,
     float &t0, float &t1)
 {
-  const float3 inv = f3(1.f / dir.x, 1.f / dir.y, 1.f / dir.z);
+  const float3 inv = f3(__fdiv_rn(1.f, dir.x), __fdiv_rn(1.f, dir.y), __fdiv_rn(1.f, dir.z));
   const float3 mins = (lo - org) * inv;
   const float3 maxs = (hi - org) * inv;
   const float3 nears = f3(fminf(mins.x, maxs.x), fminf(mins.y, maxs.y), fminf(mins.z, maxs.z));
@@ -45,13 +60,15 @@ __device__ __forceinline__ bool intersectVolumeBox(
 
 __device__ __forceinline__ float3 xfmPoint(const float *m, float3 p)
 {
-  return f3(m[0] * p.x + m[1] * p.y + m[2] * p.z + m[3], m[4] * p.x + m[5] * p.y + m[6] * p.z + m[7],
-      m[8] * p.x + m[9] * p.y + m[10] * p.z + m[11]);
+  return f3(__fmaf_rn(m[2], p.z, __fmaf_rn(m[1], p.y, __fmaf_rn(m[0], p.x, m[3]))),
+      __fmaf_rn(m[6], p.z, __fmaf_rn(m[5], p.y, __fmaf_rn(m[4], p.x, m[7]))),
+      __fmaf_rn(m[10], p.z, __fmaf_rn(m[9], p.y, __fmaf_rn(m[8], p.x, m[11]))));
 }
 __device__ __forceinline__ float3 xfmVector(const float *m, float3 v)
 {
-  return f3(m[0] * v.x + m[1] * v.y + m[2] * v.z, m[4] * v.x + m[5] * v.y + m[6] * v.z,
-      m[8] * v.x + m[9] * v.y + m[10] * v.z);
+  return f3(__fmaf_rn(m[2], v.z, __fmaf_rn(m[1], v.y, __fmul_rn(m[0], v.x))),
+      __fmaf_rn(m[6], v.z, __fmaf_rn(m[5], v.y, __fmul_rn(m[4], v.x))),
+      __fmaf_rn(m[10], v.z, __fmaf_rn(m[9], v.y, __fmul_rn(m[8], v.x))));
 }
 
 // texture coordinates of an object-space position: sampleSpatialField.h:66-70
@@ -83,9 +100,9 @@ __device__ __forceinline__ void marchSegment(const VolumeDev &v, const float4 *_
     Philox &rng, float3 &color, float &opacity, MarchStats &stats, unsigned int *cellBitmap)
 {
   const FieldDev &f = v.f;
-  const float stepSize = f.stepSize * invSamplingRate;
-  const float exponent = stepSize * v.oneOverUnitDistance;
-  t += stepSize * rng.uniform(); // jitter #2, volumeIntegration.h:83
+  const float stepSize = __fmul_rn(f.stepSize, invSamplingRate);
+  const float exponent = __fmul_rn(stepSize, v.oneOverUnitDistance);
+  t = __fmaf_rn(stepSize, rng.uniform(), t); // jitter #2, volumeIntegration.h:83
 
   const float3 halfSpacing = 0.5f * f.spacing;
   const float vrLo = v.vrLower, vrHi = v.vrUpper;
@@ -98,7 +115,7 @@ __device__ __forceinline__ void marchSegment(const VolumeDev &v, const float4 *_
   if (SLAB) {
     // fast-forward to just before the ray enters the owned z range (sequential adds keep the
     // lattice identical to the single-GPU march)
-    const float3 tc0 = fieldTexCoord(f, halfSpacing, org + dir * t);
+    const float3 tc0 = fieldTexCoord(f, halfSpacing, madd3(dir, t, org));
     const float z0 = tc0.z * (float)f.dims.z - 0.5f;
     float tEnter = t;
     if (dvox.z > 0.f)
@@ -107,7 +124,7 @@ __device__ __forceinline__ void marchSegment(const VolumeDev &v, const float4 *_
       tEnter = t + ((float)f.zOwnEnd - z0) / dvox.z;
     tEnter -= 2.f * stepSize;
     while (t < tEnter && t <= tUpper) {
-      t += stepSize;
+      t = __fadd_rn(t, stepSize);
       if (STATS)
         stats.skipped++;
     }
@@ -115,7 +132,7 @@ __device__ __forceinline__ void marchSegment(const VolumeDev &v, const float4 *_
 
   while (opacity < 0.99f && t <= tUpper) {
     if (SKIP) {
-      const float3 tc = fieldTexCoord(f, halfSpacing, org + dir * t);
+      const float3 tc = fieldTexCoord(f, halfSpacing, madd3(dir, t, org));
       const float3 xb = f3(tc.x * (float)f.dims.x - 0.5f, tc.y * (float)f.dims.y - 0.5f,
           tc.z * (float)f.dims.z - 0.5f);
       const int cx = min(max((int)floorf(xb.x), 0), f.dims.x - 1) >> 4;
@@ -136,7 +153,7 @@ __device__ __forceinline__ void marchSegment(const VolumeDev &v, const float4 *_
         int n = (int)floorf(fminf(dt / stepSize, 1.0e6f)) - 1;
         if (n >= 1) {
           while (n > 0 && t <= tUpper) {
-            t += stepSize;
+            t = __fadd_rn(t, stepSize);
             --n;
             if (STATS)
               stats.skipped++;
@@ -152,13 +169,13 @@ __device__ __forceinline__ void marchSegment(const VolumeDev &v, const float4 *_
 #pragma unroll
     for (int k = 0; k < DVR_BATCH; ++k) {
       ts[k] = tt;
-      tt += stepSize;
+      tt = __fadd_rn(tt, stepSize);
     }
 #pragma unroll
     for (int k = 0; k < DVR_BATCH; ++k) {
       s[k] = __int_as_float(0x7fc00000);
       if (ts[k] <= tUpper) {
-        const float3 p = org + dir * ts[k];
+        const float3 p = madd3(dir, ts[k], org);
         const float3 tc = fieldTexCoord(f, halfSpacing, p);
         bool own = true;
         if (SLAB) {
@@ -186,13 +203,13 @@ __device__ __forceinline__ void marchSegment(const VolumeDev &v, const float4 *_
         const float sv = s[k];
         if (!isnan(sv)) {
           const float4 co = tfLookup(tf, rangePosition(sv, vrLo, vrHi));
-          const float stepTransmittance = powf(1.f - co.w, exponent);
-          const float w = transmittance * (1.f - stepTransmittance);
-          color.x += w * co.x;
-          color.y += w * co.y;
-          color.z += w * co.z;
-          opacity += w;
-          transmittance *= stepTransmittance;
+          const float stepTransmittance = stepPow(__fsub_rn(1.f, co.w), exponent);
+          const float w = __fmul_rn(transmittance, __fsub_rn(1.f, stepTransmittance));
+          color.x = __fmaf_rn(w, co.x, color.x);
+          color.y = __fmaf_rn(w, co.y, color.y);
+          color.z = __fmaf_rn(w, co.z, color.z);
+          opacity = __fadd_rn(opacity, w);
+          transmittance = __fmul_rn(transmittance, stepTransmittance);
         }
       }
     }
@@ -200,7 +217,7 @@ __device__ __forceinline__ void marchSegment(const VolumeDev &v, const float4 *_
 
     if (SLAB) {
       // past the owned range for good?
-      const float3 tc = fieldTexCoord(f, halfSpacing, org + dir * t);
+      const float3 tc = fieldTexCoord(f, halfSpacing, madd3(dir, t, org));
       const float z = tc.z * (float)f.dims.z - 0.5f;
       if ((dvox.z > 0.f && z > (float)f.zOwnEnd + 2.f) || (dvox.z < 0.f && z < (float)f.zOwnBegin - 2.f))
         break;
@@ -260,10 +277,10 @@ __device__ __forceinline__ float rayMarchAllVolumes(const InstanceDev *__restric
     depth = fminf(depth, bt0);
     bt1 = fminf(tfar, bt1);
     // detail::rayMarchVolume: jitter #1 uses the UNSCALED step (volumeIntegration.h:117-120)
-    const float tStart = bt0 + in.v.f.stepSize * rng.uniform();
+    const float tStart = __fmaf_rn(in.v.f.stepSize, rng.uniform(), bt0);
     marchSegment<SKIP, SLAB, STATS>(
         in.v, tfOf(best), bo, bd, tStart, bt1, invSamplingRate, rng, color, opacity, stats, cellBitmap);
-    rayLower = bt1 + 1e-3f;
+    rayLower = __fadd_rn(bt1, 1e-3f);
     last = best;
   } while (opacity < 0.99f);
 

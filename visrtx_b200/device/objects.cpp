@@ -1,0 +1,791 @@
+// objects.cpp — object model implementation (see objects.h).  No arithmetic of the hot path lives
+// here: fields/volumes/cameras are translated to the C-ABI of include/dvr_b200.h.
+#include "objects.h"
+
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <limits>
+
+namespace b200 {
+
+// ---------------------------------------------------------------------------------------------------------
+size_t sizeOfType(ANARIDataType t)
+{
+  if (t >= 1000 && t < 1076) { // scalar/vector families of four
+    static const size_t base[] = {1, 1, 2, 2, 4, 4, 8, 8, 1, 1, 2, 2, 4, 4, 8, 8, 2, 4, 8};
+    const int fam = (t - 1000) / 4, n = (t - 1000) % 4 + 1;
+    return base[fam] * n;
+  }
+  switch (t) {
+  case ANARI_BOOL: return 4; // ANARI bools are int32 on the API
+  case ANARI_DATA_TYPE: return sizeof(ANARIDataType);
+  case ANARI_STRING: return sizeof(char *);
+  case ANARI_VOID_POINTER:
+  case ANARI_FUNCTION_POINTER:
+  case ANARI_MEMORY_DELETER:
+  case ANARI_STATUS_CALLBACK:
+  case ANARI_FRAME_COMPLETION_CALLBACK: return sizeof(void *);
+  case ANARI_UFIXED8_R_SRGB: return 1;
+  case ANARI_UFIXED8_RA_SRGB: return 2;
+  case ANARI_UFIXED8_RGB_SRGB: return 3;
+  case ANARI_UFIXED8_RGBA_SRGB: return 4;
+  case ANARI_INT32_BOX1: return 8;
+  case ANARI_FLOAT32_BOX1: return 8;
+  case ANARI_FLOAT32_BOX2: return 16;
+  case ANARI_FLOAT32_BOX3: return 24;
+  case ANARI_FLOAT32_BOX4: return 32;
+  case ANARI_FLOAT32_MAT2: return 16;
+  case ANARI_FLOAT32_MAT3: return 36;
+  case ANARI_FLOAT32_MAT4: return 64;
+  case ANARI_FLOAT32_MAT2x3: return 24;
+  case ANARI_FLOAT32_MAT3x4: return 48;
+  case ANARI_FLOAT32_QUAT_IJKW: return 16;
+  case ANARI_UINT64_REGION1: return 16;
+  case ANARI_FLOAT64_BOX1: return 16;
+  default: break;
+  }
+  if (isObjectType(t))
+    return sizeof(void *);
+  return 0;
+}
+
+bool isObjectType(ANARIDataType t) { return t >= ANARI_LIBRARY && t <= ANARI_WORLD; }
+
+const char *typeName(ANARIDataType t)
+{
+  switch (t) {
+  case ANARI_FLOAT32: return "ANARI_FLOAT32";
+  case ANARI_FLOAT64: return "ANARI_FLOAT64";
+  case ANARI_FIXED8: return "ANARI_FIXED8";
+  case ANARI_UFIXED8: return "ANARI_UFIXED8";
+  case ANARI_FIXED16: return "ANARI_FIXED16";
+  case ANARI_UFIXED16: return "ANARI_UFIXED16";
+  case ANARI_FLOAT16: return "ANARI_FLOAT16";
+  case ANARI_UINT8: return "ANARI_UINT8";
+  case ANARI_UINT32: return "ANARI_UINT32";
+  case ANARI_FLOAT32_VEC3: return "ANARI_FLOAT32_VEC3";
+  case ANARI_FLOAT32_VEC4: return "ANARI_FLOAT32_VEC4";
+  case ANARI_VOLUME: return "ANARI_VOLUME";
+  case ANARI_INSTANCE: return "ANARI_INSTANCE";
+  default: return "ANARI_<type>";
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Object
+// ---------------------------------------------------------------------------------------------------------
+Object::Object(Device *d, ANARIDataType t, std::string st) : device(d), type(t), subtype(std::move(st)) {}
+
+Object::~Object()
+{
+  for (auto &kv : params)
+    if (kv.second.object)
+      kv.second.object->refDec(RefType::INTERNAL);
+  if (device && device != this)
+    device->removeFromQueue(this);
+}
+
+void Object::refInc(RefType t) { (t == RefType::PUBLIC ? m_public : m_internal)++; }
+
+void Object::refDec(RefType t)
+{
+  auto &c = (t == RefType::PUBLIC ? m_public : m_internal);
+  if (c.load() > 0)
+    c--;
+  if (t == RefType::PUBLIC && m_public.load() == 0 && type >= ANARI_ARRAY && type <= ANARI_ARRAY3D)
+    static_cast<Array *>(this)->privatize();
+  if (m_public.load() == 0 && m_internal.load() == 0)
+    delete this;
+}
+
+void Object::setParam(const char *name, ANARIDataType t, const void *mem)
+{
+  if (!name || !mem)
+    return;
+  Param p;
+  p.type = t;
+  if (t == ANARI_STRING) {
+    const char *s = (const char *)mem;
+    p.bytes.assign(s, s + std::strlen(s) + 1);
+  } else if (isObjectType(t)) {
+    Object *o = *(Object *const *)mem;
+    p.object = o;
+    if (o)
+      o->refInc(RefType::INTERNAL);
+  } else {
+    const size_t n = sizeOfType(t);
+    if (n == 0) {
+      report(ANARI_SEVERITY_WARNING, ANARI_STATUS_INVALID_ARGUMENT, "parameter '%s' has an unknown data type (%d)",
+          name, t);
+      return;
+    }
+    p.bytes.assign((const uint8_t *)mem, (const uint8_t *)mem + n);
+  }
+  auto it = params.find(name);
+  if (it != params.end() && it->second.object)
+    it->second.object->refDec(RefType::INTERNAL);
+  params[name] = std::move(p);
+  parametersChanged = true;
+}
+
+void Object::unsetParam(const char *name)
+{
+  auto it = params.find(name);
+  if (it == params.end())
+    return;
+  if (it->second.object)
+    it->second.object->refDec(RefType::INTERNAL);
+  params.erase(it);
+  parametersChanged = true;
+}
+
+void Object::unsetAllParams()
+{
+  for (auto &kv : params)
+    if (kv.second.object)
+      kv.second.object->refDec(RefType::INTERNAL);
+  params.clear();
+  parametersChanged = true;
+}
+
+const Param *Object::findParam(const std::string &name) const
+{
+  auto it = params.find(name);
+  return it == params.end() ? nullptr : &it->second;
+}
+
+bool Object::getParamRaw(const std::string &name, ANARIDataType t, void *dst, size_t bytes) const
+{
+  const Param *p = findParam(name);
+  if (!p || p->type != t || p->bytes.size() < bytes)
+    return false;
+  std::memcpy(dst, p->bytes.data(), bytes);
+  return true;
+}
+
+std::string Object::getParamString(const std::string &name, const std::string &def) const
+{
+  const Param *p = findParam(name);
+  if (!p || p->type != ANARI_STRING || p->bytes.empty())
+    return def;
+  return std::string((const char *)p->bytes.data());
+}
+
+Object *Object::getParamObject(const std::string &name, ANARIDataType t) const
+{
+  const Param *p = findParam(name);
+  if (!p || !p->object)
+    return nullptr;
+  // ANARI_ARRAY matches any array rank; exact match otherwise
+  if (p->object->type == t)
+    return p->object;
+  if (t == ANARI_ARRAY && p->object->type >= ANARI_ARRAY1D && p->object->type <= ANARI_ARRAY3D)
+    return p->object;
+  return nullptr;
+}
+
+bool Object::getProperty(const std::string &, ANARIDataType, void *, uint64_t, uint32_t) { return false; }
+
+void Object::notifyChanged(Object *)
+{
+  if (device)
+    device->enqueueCommit(this);
+}
+
+void Object::addObserver(Object *o) { m_observers.insert(o); }
+void Object::removeObserver(Object *o) { m_observers.erase(o); }
+void Object::notifyObservers()
+{
+  const auto obs = m_observers; // observers may re-register while being notified
+  for (Object *o : obs)
+    o->notifyChanged(this);
+}
+
+void Object::report(ANARIStatusSeverity sev, ANARIStatusCode code, const char *fmt, ...) const
+{
+  char buf[1024];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  Device *d = device ? device : (Device *)this;
+  d->message(this, sev, code, buf);
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Array
+// ---------------------------------------------------------------------------------------------------------
+static bool pointerIsDevice(const void *p)
+{ // array/Array.cpp:38-66
+  if (!p)
+    return false;
+  cudaPointerAttributes attr{};
+  if (cudaPointerGetAttributes(&attr, p) != cudaSuccess) {
+    cudaGetLastError();
+    return false;
+  }
+  return attr.type == cudaMemoryTypeDevice || attr.type == cudaMemoryTypeManaged;
+}
+
+Array::Array(Device *d, ANARIDataType arrayType, const void *appMemory, ANARIMemoryDeleter deleter,
+    const void *userData, ANARIDataType et, uint64_t n1, uint64_t n2, uint64_t n3)
+    : Object(d, arrayType), elementType(et)
+{
+  dims[0] = n1;
+  dims[1] = n2;
+  dims[2] = n3;
+  if (appMemory) {
+    ownership = deleter ? Ownership::CAPTURED : Ownership::SHARED;
+    m_data = const_cast<void *>(appMemory);
+    m_onDevice = pointerIsDevice(appMemory);
+    m_deleter = deleter;
+    m_deleterPtr = userData;
+    if (isObjectType(et) && m_onDevice) {
+      report(ANARI_SEVERITY_ERROR, ANARI_STATUS_INVALID_OPERATION,
+          "illegal operation: cannot create object arrays from GPU memory");
+      m_data = nullptr;
+    }
+  } else {
+    ownership = Ownership::MANAGED;
+    m_managed.assign(totalBytes(), 0); // zero-initialised (Array.cpp:113-116)
+    m_data = m_managed.data();
+  }
+  if (isObjectType(et) && m_data && !m_onDevice) {
+    // object arrays hold INTERNAL refs on their elements for as long as they reference them
+    for (size_t i = 0; i < totalSize(); ++i)
+      if (Object *o = ((Object **)m_data)[i])
+        o->refInc(RefType::INTERNAL);
+  }
+}
+
+Array::~Array()
+{
+  if (isObjectType(elementType) && m_data && !m_onDevice)
+    for (size_t i = 0; i < totalSize(); ++i)
+      if (Object *o = ((Object **)m_data)[i])
+        o->refDec(RefType::INTERNAL);
+  if (ownership == Ownership::CAPTURED && m_deleter)
+    m_deleter(m_deleterPtr, m_data);
+}
+
+Object *Array::objectAt(size_t i) const
+{
+  if (!isObjectType(elementType) || !m_data || i >= totalSize())
+    return nullptr;
+  return ((Object **)m_data)[i];
+}
+
+void *Array::map()
+{
+  if (m_mapped)
+    report(ANARI_SEVERITY_WARNING, ANARI_STATUS_INVALID_OPERATION, "array mapped again without unmapping");
+  m_mapped = true;
+  if (isObjectType(elementType) && m_data) // elements may be replaced while mapped
+    for (size_t i = 0; i < totalSize(); ++i)
+      if (Object *o = ((Object **)m_data)[i])
+        o->refDec(RefType::INTERNAL);
+  return m_data;
+}
+
+void Array::unmap()
+{
+  if (!m_mapped) {
+    report(ANARI_SEVERITY_WARNING, ANARI_STATUS_INVALID_OPERATION, "array unmapped again without mapping");
+    return;
+  }
+  m_mapped = false;
+  if (isObjectType(elementType) && m_data)
+    for (size_t i = 0; i < totalSize(); ++i)
+      if (Object *o = ((Object **)m_data)[i])
+        o->refInc(RefType::INTERNAL);
+  notifyObservers(); // Array.cpp:152-162: data modified => observing field/volume re-finalises
+}
+
+void Array::privatize()
+{
+  if (ownership != Ownership::SHARED || !m_data || useCount(RefType::INTERNAL) == 0)
+    return;
+  const size_t bytes = totalBytes();
+  if (m_onDevice) {
+    void *copy = nullptr;
+    if (cudaMalloc(&copy, bytes) == cudaSuccess) {
+      cudaMemcpy(copy, m_data, bytes, cudaMemcpyDeviceToDevice);
+      m_data = copy;
+      ownership = Ownership::CAPTURED;
+      m_deleter = [](const void *, const void *mem) { cudaFree(const_cast<void *>(mem)); };
+      m_deleterPtr = nullptr;
+    }
+  } else {
+    m_managed.assign((const uint8_t *)m_data, (const uint8_t *)m_data + bytes);
+    m_data = m_managed.data();
+    ownership = Ownership::MANAGED;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Camera (camera/Camera.cpp:68-76, Perspective.cpp:42-72, Orthographic.cpp:38-52)
+// ---------------------------------------------------------------------------------------------------------
+Camera::Camera(Device *d, const std::string &st) : Object(d, ANARI_CAMERA, st)
+{
+  d->enqueueCommit(this); // cameras commit their defaults even without an explicit commit (Camera.cpp:42-46)
+}
+
+void Camera::commitParameters()
+{
+  float region[4] = {0.f, 0.f, 1.f, 1.f};
+  getParamRaw("imageRegion", ANARI_FLOAT32_BOX2, region, sizeof(region));
+  float pos[3] = {0, 0, 0}, dir[3] = {0, 0, 1}, up[3] = {0, 1, 0};
+  getParamRaw("position", ANARI_FLOAT32_VEC3, pos, sizeof(pos));
+  getParamRaw("direction", ANARI_FLOAT32_VEC3, dir, sizeof(dir));
+  getParamRaw("up", ANARI_FLOAT32_VEC3, up, sizeof(up));
+  const float aspect = getParam<float>("aspect", ANARI_FLOAT32, 1.f);
+  m_valid = true;
+  if (subtype == "perspective") {
+    const float fovy = getParam<float>("fovy", ANARI_FLOAT32, 60.f * 3.14159265358979323846f / 180.f);
+    const float focus = getParam<float>("focusDistance", ANARI_FLOAT32, 1.f);
+    const float aperture = getParam<float>("apertureRadius", ANARI_FLOAT32, 0.f);
+    dvr_camera_perspective(pos, dir, up, fovy, aspect, focus, aperture, region, &cam);
+  } else if (subtype == "orthographic") {
+    const float height = getParam<float>("height", ANARI_FLOAT32, 1.f);
+    dvr_camera_orthographic(pos, dir, up, height, aspect, region, &cam);
+  } else {
+    m_valid = false;
+    report(ANARI_SEVERITY_WARNING, ANARI_STATUS_INVALID_ARGUMENT, "unknown camera subtype '%s'", subtype.c_str());
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// SpatialField: structuredRegular (spatial_field/StructuredRegularField.cpp:90-194)
+// ---------------------------------------------------------------------------------------------------------
+SpatialField::SpatialField(Device *d, const std::string &st) : Object(d, ANARI_SPATIAL_FIELD, st) {}
+SpatialField::~SpatialField()
+{
+  if (m_data)
+    m_data->removeObserver(this);
+  cleanup();
+}
+
+void SpatialField::cleanup()
+{
+  if (m_field) {
+    CudaDeviceScope scope(device);
+    cudaStreamSynchronize((cudaStream_t)device->stream());
+    dvr_field_destroy(m_field);
+    m_field = nullptr;
+  }
+}
+
+void SpatialField::commitParameters()
+{
+  m_origin[0] = m_origin[1] = m_origin[2] = 0.f;
+  m_spacing[0] = m_spacing[1] = m_spacing[2] = 1.f;
+  getParamRaw("origin", ANARI_FLOAT32_VEC3, m_origin, sizeof(m_origin));
+  getParamRaw("spacing", ANARI_FLOAT32_VEC3, m_spacing, sizeof(m_spacing));
+  m_filter = getParamString("filter", "linear");
+  Array *a = static_cast<Array *>(getParamObject("data", ANARI_ARRAY3D));
+  if (m_data.ptr != a) {
+    if (m_data)
+      m_data->removeObserver(this);
+    m_data.reset(a);
+    if (a)
+      a->addObserver(this);
+  }
+}
+
+static int dvrTypeOf(ANARIDataType t)
+{
+  switch (t) {
+  case ANARI_FLOAT32: return DVR_FLOAT32;
+  case ANARI_UFIXED8: return DVR_UFIXED8;
+  case ANARI_FIXED8: return DVR_FIXED8;
+  case ANARI_UFIXED16: return DVR_UFIXED16;
+  case ANARI_FIXED16: return DVR_FIXED16;
+  case ANARI_FLOAT64: return DVR_FLOAT64;
+  case ANARI_FLOAT16: return DVR_FLOAT16; // extension over the reference (BASELINE config 3)
+  default: return -1;
+  }
+}
+
+void SpatialField::finalize()
+{
+  cleanup();
+  if (subtype != "structuredRegular") {
+    report(ANARI_SEVERITY_WARNING, ANARI_STATUS_INVALID_ARGUMENT, "unknown spatial field subtype '%s'",
+        subtype.c_str());
+    return;
+  }
+  if (!m_data) {
+    report(ANARI_SEVERITY_WARNING, ANARI_STATUS_INVALID_ARGUMENT,
+        "missing required parameter 'data' on structuredRegular spatial field");
+    return;
+  }
+  const int dt = dvrTypeOf(m_data->elementType);
+  if (dt < 0) {
+    report(ANARI_SEVERITY_WARNING, ANARI_STATUS_INVALID_ARGUMENT,
+        "invalid data array type encountered in structuredRegular spatial field(%s)", typeName(m_data->elementType));
+    return;
+  }
+  if (!device->initDevice())
+    return;
+  CudaDeviceScope scope(device);
+  const uint32_t dims[3] = {(uint32_t)m_data->dims[0], (uint32_t)m_data->dims[1], (uint32_t)m_data->dims[2]};
+  const int rc = dvr_field_create_structured(m_data->data(), m_data->onDevice() ? 1 : 0, dt, dims, m_origin, m_spacing,
+      m_filter == "nearest" ? DVR_FILTER_NEAREST : DVR_FILTER_LINEAR, device->stream(), &m_field);
+  if (rc != DVR_OK) {
+    m_field = nullptr;
+    report(ANARI_SEVERITY_ERROR, rc == DVR_ERR_OUT_OF_MEMORY ? ANARI_STATUS_OUT_OF_MEMORY : ANARI_STATUS_UNKNOWN_ERROR,
+        "structuredRegular field upload failed: %s", dvr_last_error());
+  }
+}
+
+void SpatialField::bounds(float lo[3], float hi[3]) const
+{
+  if (m_field)
+    dvr_field_bounds(m_field, lo, hi);
+  else {
+    lo[0] = lo[1] = lo[2] = 0.f;
+    hi[0] = hi[1] = hi[2] = 1.f;
+  }
+}
+
+bool SpatialField::getProperty(const std::string &name, ANARIDataType t, void *mem, uint64_t size, uint32_t mask)
+{
+  if (name == "bounds" && t == ANARI_FLOAT32_BOX3 && size >= 24) {
+    if (mask & ANARI_WAIT)
+      device->flushCommits();
+    float b[6];
+    bounds(b, b + 3);
+    std::memcpy(mem, b, 24);
+    return true;
+  }
+  if (name == "valueRange" && t == ANARI_FLOAT32_BOX1 && size >= 8) { // tsd computeScalarRange equivalent
+    if (mask & ANARI_WAIT)
+      device->flushCommits();
+    if (!m_field)
+      return false;
+    CudaDeviceScope scope(device);
+    float r[2];
+    if (dvr_field_value_range(m_field, device->stream(), r) != DVR_OK)
+      return false;
+    std::memcpy(mem, r, 8);
+    return true;
+  }
+  return false;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Volume: transferFunction1D | scivis (scene/volume/Volume.cpp:40-90, TransferFunction1D.cpp:46-150)
+// ---------------------------------------------------------------------------------------------------------
+Volume::Volume(Device *d, const std::string &st) : Object(d, ANARI_VOLUME, st)
+{
+  m_known = (st == "transferFunction1D" || st == "scivis");
+}
+
+Volume::~Volume()
+{
+  if (m_color) m_color->removeObserver(this);
+  if (m_opacity) m_opacity->removeObserver(this);
+  if (m_field) m_field->removeObserver(this);
+  if (m_volume) {
+    CudaDeviceScope scope(device);
+    cudaStreamSynchronize((cudaStream_t)device->stream());
+    dvr_volume_destroy(m_volume);
+  }
+}
+
+void Volume::commitParameters()
+{
+  m_id = getParam<uint32_t>("id", ANARI_UINT32, ~0u);
+  auto observe = [this](Ref<Array> &slot, Array *a) {
+    if (slot.ptr == a)
+      return;
+    if (slot)
+      slot->removeObserver(this);
+    slot.reset(a);
+    if (a)
+      a->addObserver(this);
+  };
+  observe(m_color, static_cast<Array *>(getParamObject("color", ANARI_ARRAY1D)));
+  observe(m_opacity, static_cast<Array *>(getParamObject("opacity", ANARI_ARRAY1D)));
+  m_uniformColor[0] = m_uniformColor[1] = m_uniformColor[2] = m_uniformColor[3] = 1.f;
+  getParamRaw("color", ANARI_FLOAT32_VEC3, m_uniformColor, 12);
+  getParamRaw("color", ANARI_FLOAT32_VEC4, m_uniformColor, 16);
+  m_uniformOpacity = getParam<float>("opacity", ANARI_FLOAT32, 1.f) * m_uniformColor[3];
+  m_unitDistance = getParam<float>("unitDistance", ANARI_FLOAT32, 1.f);
+  SpatialField *f = static_cast<SpatialField *>(getParamObject("value", ANARI_SPATIAL_FIELD));
+  if (m_field.ptr != f) {
+    if (m_field)
+      m_field->removeObserver(this);
+    m_field.reset(f);
+    if (f)
+      f->addObserver(this);
+  }
+  m_valueRange[0] = 0.f;
+  m_valueRange[1] = 1.f;
+  getParamRaw("valueRange", ANARI_FLOAT32_VEC2, m_valueRange, 8);
+  getParamRaw("valueRange", ANARI_FLOAT32_BOX1, m_valueRange, 8);
+  double vr[2];
+  if (getParamRaw("valueRange", ANARI_FLOAT64_BOX1, vr, 16)) {
+    m_valueRange[0] = float(vr[0]);
+    m_valueRange[1] = float(vr[1]);
+  }
+}
+
+void Volume::finalize()
+{
+  if (!m_known) {
+    report(ANARI_SEVERITY_WARNING, ANARI_STATUS_INVALID_ARGUMENT, "unknown volume subtype '%s'", subtype.c_str());
+    return;
+  }
+  if (!m_field) {
+    report(ANARI_SEVERITY_WARNING, ANARI_STATUS_INVALID_ARGUMENT,
+        "missing parameter 'value' on transferFunction1D ANARIVolume");
+    return;
+  }
+  if (!m_field->isValid())
+    return;
+  // discritizeTFData
+  const float *color = nullptr, *opacity = nullptr;
+  size_t nColor = 0, nOpacity = 0;
+  int channels = 4;
+  if (m_color) {
+    if (m_color->onDevice())
+      report(ANARI_SEVERITY_WARNING, ANARI_STATUS_INVALID_ARGUMENT, "tf1D color array must be host memory");
+    else if (m_color->elementType == ANARI_FLOAT32_VEC3 || m_color->elementType == ANARI_FLOAT32_VEC4) {
+      color = (const float *)m_color->data();
+      nColor = m_color->totalSize();
+      channels = m_color->elementType == ANARI_FLOAT32_VEC3 ? 3 : 4;
+    } else
+      report(ANARI_SEVERITY_WARNING, ANARI_STATUS_INVALID_ARGUMENT, "unusable tf1D color array type set (%s)",
+          typeName(m_color->elementType));
+  }
+  if (m_opacity && !m_opacity->onDevice() && m_opacity->elementType == ANARI_FLOAT32) {
+    opacity = (const float *)m_opacity->data();
+    nOpacity = m_opacity->totalSize();
+  }
+  std::vector<float> tf(DVR_TF_SIZE * 4);
+  if (dvr_tf_discretize(color, nColor, channels, opacity, nOpacity, m_uniformColor, m_uniformOpacity, m_valueRange,
+          tf.data())
+      != DVR_OK) {
+    report(ANARI_SEVERITY_WARNING, ANARI_STATUS_INVALID_ARGUMENT, "transfer function rejected: %s", dvr_last_error());
+    return;
+  }
+  CudaDeviceScope scope(device);
+  int rc;
+  if (m_volume && m_volumeField == m_field->handle())
+    rc = dvr_volume_update(m_volume, tf.data(), m_valueRange, m_unitDistance, m_id, device->stream());
+  else {
+    if (m_volume) {
+      cudaStreamSynchronize((cudaStream_t)device->stream());
+      dvr_volume_destroy(m_volume);
+      m_volume = nullptr;
+    }
+    rc = dvr_volume_create(m_field->handle(), tf.data(), m_valueRange, m_unitDistance, m_id, device->stream(), &m_volume);
+    m_volumeField = m_field->handle();
+  }
+  if (rc != DVR_OK)
+    report(ANARI_SEVERITY_ERROR, ANARI_STATUS_UNKNOWN_ERROR, "volume upload failed: %s", dvr_last_error());
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Group / Instance / World
+// ---------------------------------------------------------------------------------------------------------
+Group::Group(Device *d) : Object(d, ANARI_GROUP) {}
+void Group::commitParameters() { m_volumes.reset(static_cast<Array *>(getParamObject("volume", ANARI_ARRAY1D))); }
+std::vector<Volume *> Group::volumes() const
+{
+  std::vector<Volume *> out;
+  if (m_volumes)
+    for (size_t i = 0; i < m_volumes->totalSize(); ++i) {
+      Object *o = m_volumes->objectAt(i);
+      if (o && o->type == ANARI_VOLUME)
+        out.push_back(static_cast<Volume *>(o));
+    }
+  return out;
+}
+
+Instance::Instance(Device *d, const std::string &st) : Object(d, ANARI_INSTANCE, st)
+{
+  static const float ident[12] = {1, 0, 0, 0, 1, 0, 0, 0, 1, 0, 0, 0};
+  std::memcpy(objectToWorld, ident, sizeof(ident));
+}
+
+void Instance::commitParameters()
+{ // scene/Instance.cpp:40-46
+  id = getParam<uint32_t>("id", ANARI_UINT32, ~0u);
+  static const float ident[12] = {1, 0, 0, 0, 1, 0, 0, 0, 1, 0, 0, 0};
+  std::memcpy(objectToWorld, ident, sizeof(ident));
+  float m4[16];
+  if (getParamRaw("transform", ANARI_FLOAT32_MAT4, m4, sizeof(m4))) {
+    for (int c = 0; c < 4; ++c)
+      for (int r = 0; r < 3; ++r)
+        objectToWorld[c * 3 + r] = m4[c * 4 + r];
+  }
+  getParamRaw("transform", ANARI_FLOAT32_MAT3x4, objectToWorld, sizeof(objectToWorld));
+  m_group.reset(static_cast<Group *>(getParamObject("group", ANARI_GROUP)));
+  if (!m_group)
+    report(ANARI_SEVERITY_WARNING, ANARI_STATUS_INVALID_ARGUMENT, "missing 'group' on ANARIInstance");
+}
+
+World::World(Device *d) : Object(d, ANARI_WORLD) {}
+void World::commitParameters()
+{
+  m_zeroVolumes.reset(static_cast<Array *>(getParamObject("volume", ANARI_ARRAY1D)));
+  m_instances.reset(static_cast<Array *>(getParamObject("instance", ANARI_ARRAY1D)));
+}
+
+// inverse of an affine transform given as column-major 4x3 -> row-major 3x4
+static bool invertAffine(const float m[12], float out[12])
+{
+  const double a = m[0], b = m[3], c = m[6], d = m[1], e = m[4], f = m[7], g = m[2], h = m[5], i = m[8];
+  const double tx = m[9], ty = m[10], tz = m[11];
+  const double det = a * (e * i - f * h) - b * (d * i - f * g) + c * (d * h - e * g);
+  if (det == 0.0)
+    return false;
+  const double r[9] = {(e * i - f * h) / det, (c * h - b * i) / det, (b * f - c * e) / det, (f * g - d * i) / det,
+      (a * i - c * g) / det, (c * d - a * f) / det, (d * h - e * g) / det, (b * g - a * h) / det,
+      (a * e - b * d) / det};
+  for (int row = 0; row < 3; ++row) {
+    out[row * 4 + 0] = (float)r[row * 3 + 0];
+    out[row * 4 + 1] = (float)r[row * 3 + 1];
+    out[row * 4 + 2] = (float)r[row * 3 + 2];
+    out[row * 4 + 3] = (float)(-(r[row * 3 + 0] * tx + r[row * 3 + 1] * ty + r[row * 3 + 2] * tz));
+  }
+  return true;
+}
+
+std::vector<FlatInstance> World::flatten(bool warn) const
+{
+  std::vector<FlatInstance> out;
+  static const float ident[12] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0};
+  auto push = [&](Volume *v, const float *w2o, uint32_t instId) {
+    if (!v->isValid()) {
+      if (warn)
+        report(ANARI_SEVERITY_WARNING, ANARI_STATUS_INVALID_ARGUMENT, "skipping invalid volume in world");
+      return;
+    }
+    FlatInstance fi;
+    fi.volume = v;
+    std::memcpy(fi.worldToObject, w2o, sizeof(fi.worldToObject));
+    fi.instId = instId;
+    out.push_back(fi);
+  };
+  if (m_zeroVolumes) // the world's own volumes live in an identity "zero instance" (World.cpp:82-96,117-135)
+    for (size_t i = 0; i < m_zeroVolumes->totalSize(); ++i) {
+      Object *o = m_zeroVolumes->objectAt(i);
+      if (o && o->type == ANARI_VOLUME)
+        push(static_cast<Volume *>(o), ident, ~0u);
+    }
+  if (m_instances)
+    for (size_t i = 0; i < m_instances->totalSize(); ++i) {
+      Object *o = m_instances->objectAt(i);
+      if (!o || o->type != ANARI_INSTANCE)
+        continue;
+      Instance *in = static_cast<Instance *>(o);
+      if (!in->isValid()) {
+        if (warn)
+          report(ANARI_SEVERITY_WARNING, ANARI_STATUS_INVALID_ARGUMENT, "skipping invalid instance in world");
+        continue;
+      }
+      float w2o[12];
+      if (!invertAffine(in->objectToWorld, w2o)) {
+        if (warn)
+          report(ANARI_SEVERITY_WARNING, ANARI_STATUS_INVALID_ARGUMENT, "singular instance transform");
+        continue;
+      }
+      for (Volume *v : in->group()->volumes())
+        push(v, w2o, in->id);
+    }
+  return out;
+}
+
+void World::bounds(float lo[3], float hi[3]) const
+{
+  const float big = std::numeric_limits<float>::max();
+  lo[0] = lo[1] = lo[2] = big;
+  hi[0] = hi[1] = hi[2] = -big;
+  for (const FlatInstance &fi : flatten(false)) {
+    float flo[3], fhi[3];
+    fi.volume->field()->bounds(flo, fhi);
+    // object-space corners -> world: invert the stored world->object (row-major 3x4)
+    float o2w[12];
+    float cm[12];
+    for (int r = 0; r < 3; ++r) {
+      cm[0 * 3 + r] = fi.worldToObject[r * 4 + 0];
+      cm[1 * 3 + r] = fi.worldToObject[r * 4 + 1];
+      cm[2 * 3 + r] = fi.worldToObject[r * 4 + 2];
+      cm[9 + r] = fi.worldToObject[r * 4 + 3];
+    }
+    if (!invertAffine(cm, o2w))
+      continue;
+    for (int k = 0; k < 8; ++k) {
+      const float p[3] = {k & 1 ? fhi[0] : flo[0], k & 2 ? fhi[1] : flo[1], k & 4 ? fhi[2] : flo[2]};
+      for (int r = 0; r < 3; ++r) {
+        const float w = o2w[r * 4] * p[0] + o2w[r * 4 + 1] * p[1] + o2w[r * 4 + 2] * p[2] + o2w[r * 4 + 3];
+        lo[r] = std::min(lo[r], w);
+        hi[r] = std::max(hi[r], w);
+      }
+    }
+  }
+}
+
+bool World::getProperty(const std::string &name, ANARIDataType t, void *mem, uint64_t size, uint32_t mask)
+{
+  if (name == "bounds" && t == ANARI_FLOAT32_BOX3 && size >= 24) { // World.cpp:100-117
+    if (mask & ANARI_WAIT)
+      device->flushCommits();
+    float b[6];
+    bounds(b, b + 3);
+    std::memcpy(mem, b, 24);
+    return true;
+  }
+  return false;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Renderer (renderer/Renderer.cpp:152-170, Raycast.cpp:45-50)
+// ---------------------------------------------------------------------------------------------------------
+Renderer::Renderer(Device *d, const std::string &st) : Object(d, ANARI_RENDERER, st)
+{
+  std::string s = st;
+  if (const char *ov = getenv("VISRTX_OVERRIDE_RENDERER")) // Renderer.cpp:263-266
+    s = ov;
+  subtype = s;
+  m_known = s == "raycast" || s == "default" || s == "directLight" || s == "ao" || s == "dpt"
+      || s == "diffuse_pathtracer";
+  d->enqueueCommit(this);
+}
+
+void Renderer::commitParameters()
+{
+  background[0] = background[1] = background[2] = 0.f;
+  background[3] = 1.f;
+  getParamRaw("background", ANARI_FLOAT32_VEC4, background, 16);
+  if (getParamObject("background", ANARI_ARRAY2D))
+    report(ANARI_SEVERITY_WARNING, ANARI_STATUS_INVALID_ARGUMENT,
+        "image backgrounds are outside the DVR path of this device; using the constant colour");
+  spp = getParam<int>("pixelSamples", ANARI_INT32, 1);
+  checkerboard = getParam<int32_t>("checkerboarding", ANARI_BOOL, 0) != 0;
+  sampleLimit = getParam<int>("sampleLimit", ANARI_INT32, 128);
+  volumeSamplingRate = std::min(std::max(getParam<float>("volumeSamplingRate", ANARI_FLOAT32, 0.125f), 1e-3f), 10.f);
+  macrocellSkipping = getParam<int32_t>("macrocellSkipping", ANARI_BOOL, 1) != 0; // extension; parity-neutral
+  if (checkerboard)
+    spp = 1;
+  integrator = DVR_INTEGRATOR_DEFAULT;
+  if (subtype == "raycast") {
+    integrator = DVR_INTEGRATOR_RAYCAST;
+    sampleLimit = 1; // single-shot renderer
+  }
+  if (!m_known)
+    report(ANARI_SEVERITY_WARNING, ANARI_STATUS_INVALID_ARGUMENT, "unknown renderer subtype '%s'", subtype.c_str());
+  else if (subtype == "dpt" || subtype == "diffuse_pathtracer")
+    report(ANARI_SEVERITY_WARNING, ANARI_STATUS_NO_ERROR,
+        "renderer '%s': delta-tracking path tracing is not built yet; using the fixed-step marcher",
+        subtype.c_str());
+}
+
+} // namespace b200

@@ -1,0 +1,378 @@
+// objects.h — host object model of the B200 DVR ANARI device.
+//
+// Mirrors the part of VisRTX's helium-based object model that the DVR path touches
+// (devices/rtx/{Object,RegisteredObject}.h, array/, camera/, scene/volume/**, scene/{World,Group,Instance}.*,
+// renderer/Renderer.*, frame/Frame.*): string-keyed parameter store, deferred commit
+// (commitParameters + finalize at the next renderFrame / WAIT query), PUBLIC/INTERNAL reference counts,
+// array change observers, accumulation reset on any finalisation.  All GPU work goes through the
+// extern "C" launch layer of include/dvr_b200.h.
+#pragma once
+
+#include <atomic>
+#include <cstdint>
+#include <cstring>
+#include <map>
+#include <memory>
+#include <mutex>
+#include <set>
+#include <string>
+#include <vector>
+
+#include <anari/anari.h>
+#include "../../include/dvr_b200.h"
+
+namespace b200 {
+
+struct Device;
+struct Object;
+
+size_t sizeOfType(ANARIDataType t);
+bool isObjectType(ANARIDataType t);
+const char *typeName(ANARIDataType t);
+
+struct Param
+{
+  ANARIDataType type = ANARI_UNKNOWN;
+  std::vector<uint8_t> bytes; // POD value (or the string incl. terminator)
+  Object *object = nullptr;   // object-typed parameter (holds an INTERNAL ref)
+};
+
+// helium::RefType
+enum class RefType
+{
+  PUBLIC,
+  INTERNAL
+};
+
+struct Object
+{
+  Object(Device *d, ANARIDataType type, std::string subtype = "");
+  virtual ~Object();
+
+  // lifetime (helium::RefCounted): destroyed when both counts reach zero
+  void refInc(RefType t);
+  void refDec(RefType t);
+  int useCount(RefType t) const { return t == RefType::PUBLIC ? m_public.load() : m_internal.load(); }
+
+  // parameters
+  void setParam(const char *name, ANARIDataType type, const void *mem);
+  void unsetParam(const char *name);
+  void unsetAllParams();
+  const Param *findParam(const std::string &name) const;
+  template <typename T>
+  T getParam(const std::string &name, ANARIDataType type, T def) const
+  {
+    const Param *p = findParam(name);
+    if (!p || p->type != type || p->bytes.size() < sizeof(T))
+      return def;
+    T v;
+    std::memcpy(&v, p->bytes.data(), sizeof(T));
+    return v;
+  }
+  bool getParamRaw(const std::string &name, ANARIDataType type, void *dst, size_t bytes) const;
+  std::string getParamString(const std::string &name, const std::string &def) const;
+  Object *getParamObject(const std::string &name, ANARIDataType type) const;
+
+  // commit protocol
+  virtual void commitParameters() {}
+  virtual void finalize() {}
+  virtual bool isValid() const { return true; }
+  virtual int commitPriority() const { return 5; }
+  virtual bool getProperty(const std::string &name, ANARIDataType type, void *mem, uint64_t size, uint32_t mask);
+  virtual void notifyChanged(Object * /*source*/); // an observed array/object changed: re-finalise
+
+  void addObserver(Object *o);
+  void removeObserver(Object *o);
+  void notifyObservers();
+
+  void report(ANARIStatusSeverity sev, ANARIStatusCode code, const char *fmt, ...) const;
+
+  Device *device;
+  ANARIDataType type;
+  std::string subtype;
+  std::map<std::string, Param> params;
+  uint64_t lastFinalized = 0;
+  bool parametersChanged = true;
+
+ private:
+  std::atomic<int> m_public{1};
+  std::atomic<int> m_internal{0};
+  std::set<Object *> m_observers;
+};
+
+// intrusive INTERNAL reference
+template <typename T>
+struct Ref
+{
+  Ref() = default;
+  Ref(const Ref &) = delete;
+  Ref &operator=(const Ref &) = delete;
+  ~Ref() { reset(); }
+  void reset(T *p = nullptr)
+  {
+    if (p)
+      p->refInc(RefType::INTERNAL);
+    if (ptr)
+      ptr->refDec(RefType::INTERNAL);
+    ptr = p;
+  }
+  T *operator->() const { return ptr; }
+  explicit operator bool() const { return ptr != nullptr; }
+  T *ptr = nullptr;
+};
+
+// ---- arrays (devices/rtx/array/Array.cpp) ------------------------------------------------------------------
+enum class Ownership
+{
+  SHARED,
+  CAPTURED,
+  MANAGED
+};
+
+struct Array : Object
+{
+  Array(Device *d, ANARIDataType arrayType, const void *appMemory, ANARIMemoryDeleter deleter, const void *userData,
+      ANARIDataType elementType, uint64_t n1, uint64_t n2, uint64_t n3);
+  ~Array() override;
+  int commitPriority() const override { return 0; }
+  void *map();
+  void unmap();
+  void privatize(); // SHARED array lost its last public ref: copy the app memory (Array.cpp:164-182)
+  const void *data() const { return m_data; }
+  bool onDevice() const { return m_onDevice; }
+  size_t totalSize() const { return (size_t)dims[0] * dims[1] * dims[2]; }
+  size_t totalBytes() const { return totalSize() * sizeOfType(elementType); }
+  Object *objectAt(size_t i) const;
+
+  ANARIDataType elementType;
+  uint64_t dims[3];
+  Ownership ownership;
+
+ private:
+  void *m_data = nullptr;
+  bool m_onDevice = false;
+  ANARIMemoryDeleter m_deleter = nullptr;
+  const void *m_deleterPtr = nullptr;
+  std::vector<uint8_t> m_managed;
+  bool m_mapped = false;
+};
+
+// ---- camera ---------------------------------------------------------------------------------------------------
+struct Camera : Object
+{
+  Camera(Device *d, const std::string &subtype);
+  void commitParameters() override;
+  bool isValid() const override { return m_valid; }
+  int commitPriority() const override { return 1; }
+  DvrCamera cam{};
+
+ private:
+  bool m_valid = false;
+};
+
+// ---- spatial field ---------------------------------------------------------------------------------------------
+struct SpatialField : Object
+{
+  SpatialField(Device *d, const std::string &subtype);
+  ~SpatialField() override;
+  void commitParameters() override;
+  void finalize() override;
+  bool isValid() const override { return m_field != nullptr; }
+  int commitPriority() const override { return 2; }
+  bool getProperty(const std::string &name, ANARIDataType type, void *mem, uint64_t size, uint32_t mask) override;
+  DvrField *handle() const { return m_field; }
+  void bounds(float lo[3], float hi[3]) const;
+
+ private:
+  void cleanup();
+  Ref<Array> m_data;
+  float m_origin[3] = {0, 0, 0};
+  float m_spacing[3] = {1, 1, 1};
+  std::string m_filter = "linear";
+  DvrField *m_field = nullptr;
+};
+
+// ---- volume ------------------------------------------------------------------------------------------------------
+struct Volume : Object
+{
+  Volume(Device *d, const std::string &subtype);
+  ~Volume() override;
+  void commitParameters() override;
+  void finalize() override;
+  bool isValid() const override { return m_volume != nullptr && m_field && m_field->isValid(); }
+  int commitPriority() const override { return 3; }
+  DvrVolume *handle() const { return m_volume; }
+  SpatialField *field() const { return m_field.ptr; }
+  uint32_t id() const { return m_id; }
+
+ private:
+  Ref<Array> m_color, m_opacity;
+  Ref<SpatialField> m_field;
+  float m_uniformColor[4] = {1, 1, 1, 1};
+  float m_uniformOpacity = 1.f;
+  float m_unitDistance = 1.f;
+  float m_valueRange[2] = {0.f, 1.f};
+  uint32_t m_id = ~0u;
+  DvrVolume *m_volume = nullptr;
+  const DvrField *m_volumeField = nullptr;
+  bool m_known = true;
+};
+
+// ---- group / instance / world ---------------------------------------------------------------------------------------
+struct Group : Object
+{
+  Group(Device *d);
+  void commitParameters() override;
+  int commitPriority() const override { return 4; }
+  std::vector<Volume *> volumes() const;
+
+ private:
+  Ref<Array> m_volumes;
+};
+
+struct Instance : Object
+{
+  Instance(Device *d, const std::string &subtype);
+  void commitParameters() override;
+  bool isValid() const override { return (bool)m_group; }
+  int commitPriority() const override { return 5; }
+  Group *group() const { return m_group.ptr; }
+  float objectToWorld[12]; // column-major 4x3 (c0,c1,c2,t) as glm::mat4x3
+  uint32_t id = ~0u;
+
+ private:
+  Ref<Group> m_group;
+};
+
+struct FlatInstance
+{
+  Volume *volume;
+  float worldToObject[12]; // row-major 3x4
+  uint32_t instId;
+};
+
+struct World : Object
+{
+  World(Device *d);
+  void commitParameters() override;
+  int commitPriority() const override { return 6; }
+  bool getProperty(const std::string &name, ANARIDataType type, void *mem, uint64_t size, uint32_t mask) override;
+  // World::rebuildWorld + the zero-instance rule (World.cpp:60-135,202-258)
+  std::vector<FlatInstance> flatten(bool warn) const;
+  void bounds(float lo[3], float hi[3]) const;
+
+ private:
+  Ref<Array> m_zeroVolumes, m_instances;
+};
+
+// ---- renderer ----------------------------------------------------------------------------------------------------
+struct Renderer : Object
+{
+  Renderer(Device *d, const std::string &subtype);
+  void commitParameters() override;
+  bool isValid() const override { return m_known; }
+  int commitPriority() const override { return 1; }
+  float background[4] = {0, 0, 0, 1};
+  int spp = 1;
+  int sampleLimit = 128;
+  bool checkerboard = false;
+  float volumeSamplingRate = 0.125f;
+  int integrator = DVR_INTEGRATOR_DEFAULT;
+  bool macrocellSkipping = true;
+
+ private:
+  bool m_known = true;
+};
+
+// ---- frame ---------------------------------------------------------------------------------------------------------
+struct Frame : Object
+{
+  Frame(Device *d);
+  ~Frame() override;
+  void commitParameters() override;
+  void finalize() override;
+  bool isValid() const override;
+  int commitPriority() const override { return 7; }
+  bool getProperty(const std::string &name, ANARIDataType type, void *mem, uint64_t size, uint32_t mask) override;
+
+  void renderFrame();
+  const void *map(const std::string &channel, uint32_t *w, uint32_t *h, ANARIDataType *type);
+  int ready(ANARIWaitMask m);
+  void wait() const;
+
+ private:
+  void checkAccumulationReset();
+  void freeBuffers();
+  void *download(void *dev, size_t bytes, std::vector<uint8_t> &host);
+
+  Ref<Renderer> m_renderer;
+  Ref<Camera> m_camera;
+  Ref<World> m_world;
+  ANARIFrameCompletionCallback m_callback = nullptr;
+  const void *m_callbackUserPtr = nullptr;
+  ANARIDataType m_colorType = ANARI_UFIXED8_RGBA_SRGB, m_depthType = ANARI_UNKNOWN, m_primIdType = ANARI_UNKNOWN,
+                m_objIdType = ANARI_UNKNOWN, m_instIdType = ANARI_UNKNOWN, m_albedoType = ANARI_UNKNOWN,
+                m_normalType = ANARI_UNKNOWN;
+  uint32_t m_size[2] = {10, 10};
+  int m_format = DVR_FORMAT_UFIXED8_RGBA_SRGB;
+  // device buffers
+  void *m_accum = nullptr, *m_color = nullptr, *m_depth = nullptr, *m_primId = nullptr, *m_objId = nullptr,
+       *m_instId = nullptr, *m_albedoAccum = nullptr, *m_normalAccum = nullptr, *m_albedo = nullptr,
+       *m_normal = nullptr;
+  std::vector<uint8_t> m_hColor, m_hDepth, m_hPrim, m_hObj, m_hInst, m_hAlbedo, m_hNormal;
+  void *m_pinned = nullptr;
+  size_t m_pinnedBytes = 0;
+  void *m_eventStart = nullptr, *m_eventEnd = nullptr;
+  int m_frameID = 0, m_checkerboardID = -1;
+  float m_invFrameID = 1.f;
+  bool m_nextFrameReset = true;
+  bool m_valid = false;
+  bool m_everRendered = false;
+  uint64_t m_lastCommitSeen = 0;
+  float m_duration = 0.f;
+};
+
+// ---- device -----------------------------------------------------------------------------------------------------------
+struct Device : Object
+{
+  Device(ANARIStatusCallback cb, const void *userPtr);
+  ~Device() override;
+  void commitParameters() override; // statusCallback, cudaDevice, forceInit
+  bool getProperty(const std::string &name, ANARIDataType type, void *mem, uint64_t size, uint32_t mask) override;
+
+  bool initDevice(); // lazy CUDA init, sticky failure (VisRTXDevice.cpp:435-458)
+  void enqueueCommit(Object *o);
+  void flushCommits();
+  void removeFromQueue(Object *o);
+  uint64_t newTimeStamp() { return ++m_clock; }
+  uint64_t lastFinalization() const { return m_lastFinalization; }
+  void *stream() const { return m_stream; }
+  int cudaDevice() const { return m_gpuID; }
+
+  void message(const Object *src, ANARIStatusSeverity sev, ANARIStatusCode code, const char *msg) const;
+
+  std::recursive_mutex mutex;
+
+ private:
+  ANARIStatusCallback m_cb = nullptr;
+  const void *m_cbUserPtr = nullptr;
+  ANARIStatusCallback m_defaultCb = nullptr;
+  const void *m_defaultCbUserPtr = nullptr;
+  std::vector<Object *> m_commitQueue;
+  std::atomic<uint64_t> m_clock{0};
+  uint64_t m_lastFinalization = 0;
+  int m_initStatus = 0; // 0 uninitialised, 1 ok, -1 failed
+  int m_desiredGpuID = 0, m_gpuID = -1;
+  void *m_stream = nullptr;
+};
+
+// RAII: every API entry saves / restores the caller's current CUDA device (VisRTXDevice.cpp:790-814)
+struct CudaDeviceScope
+{
+  explicit CudaDeviceScope(Device *d);
+  ~CudaDeviceScope();
+  int prev = -1;
+  bool active = false;
+};
+
+} // namespace b200
