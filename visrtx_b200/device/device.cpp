@@ -243,8 +243,8 @@ void Frame::renderFrame()
   p.numIterations = std::max(m_renderer->spp, 1);
   p.inverseVolumeSamplingRate = 1.f / m_renderer->volumeSamplingRate;
   std::memcpy(p.background, m_renderer->background, sizeof(p.background));
-  p.tileRank = 0;
-  p.tileRanks = 1;
+  p.tileRank = m_renderer->tileRank;
+  p.tileRanks = m_renderer->tileRanks;
   p.useMacrocellSkipping = m_renderer->macrocellSkipping ? 1 : 0;
 
   DvrFrameBuffers b;
@@ -613,7 +613,8 @@ struct ParamInfo
 };
 const ANARIParameter kRendererParams[] = {{"background", ANARI_FLOAT32_VEC4}, {"pixelSamples", ANARI_INT32},
     {"sampleLimit", ANARI_INT32}, {"volumeSamplingRate", ANARI_FLOAT32}, {"checkerboarding", ANARI_BOOL},
-    {"macrocellSkipping", ANARI_BOOL}, {nullptr, ANARI_UNKNOWN}};
+    {"macrocellSkipping", ANARI_BOOL}, {"sortFirstRank", ANARI_INT32}, {"sortFirstRanks", ANARI_INT32},
+    {nullptr, ANARI_UNKNOWN}};
 const ANARIParameter kFieldParams[] = {{"data", ANARI_ARRAY3D}, {"origin", ANARI_FLOAT32_VEC3},
     {"spacing", ANARI_FLOAT32_VEC3}, {"filter", ANARI_STRING}, {nullptr, ANARI_UNKNOWN}};
 const ANARIParameter kVolumeParams[] = {{"value", ANARI_SPATIAL_FIELD}, {"color", ANARI_ARRAY1D},

@@ -773,6 +773,8 @@ void Renderer::commitParameters()
   sampleLimit = getParam<int>("sampleLimit", ANARI_INT32, 128);
   volumeSamplingRate = std::min(std::max(getParam<float>("volumeSamplingRate", ANARI_FLOAT32, 0.125f), 1e-3f), 10.f);
   macrocellSkipping = getParam<int32_t>("macrocellSkipping", ANARI_BOOL, 1) != 0; // extension; parity-neutral
+  tileRank = (uint32_t)std::max(getParam<int>("sortFirstRank", ANARI_INT32, 0), 0);
+  tileRanks = (uint32_t)std::max(getParam<int>("sortFirstRanks", ANARI_INT32, 1), 1);
   if (checkerboard)
     spp = 1;
   integrator = DVR_INTEGRATOR_DEFAULT;

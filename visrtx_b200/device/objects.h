@@ -279,6 +279,8 @@ struct Renderer : Object
   float volumeSamplingRate = 0.125f;
   int integrator = DVR_INTEGRATOR_DEFAULT;
   bool macrocellSkipping = true;
+  // sort-first extension: this device renders only tile rows (row % tileRanks == tileRank)
+  uint32_t tileRank = 0, tileRanks = 1;
 
  private:
   bool m_known = true;
