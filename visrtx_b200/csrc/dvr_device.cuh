@@ -286,7 +286,7 @@ __device__ __forceinline__ void writeOutputColor(
 __device__ __forceinline__ float4 tfLookup(const float4 *__restrict__ tf, float coord)
 {
   const float xb = __fsub_rn(__fmul_rn(coord, 256.0f), 0.5f);
-  int q = __float2int_rd(__fmaf_rn(xb, 256.0f, 0.5f));
+  int q = __float2int_rd(__fmaf_rn(xb, 256.0f, 0.5f)); // NaN converts to 0
   q = max(0, min(q, 255 * 256));
   const int i = q >> 8;
   const float w1 = (float)(q & 255) * (1.0f / 256.0f);

@@ -11,8 +11,11 @@
 namespace dvr {
 
 constexpr int kMaxInlineInstances = 4;
-constexpr int kTileW = 8; // one warp renders an 8x4 pixel tile
-constexpr int kTileH = 4;
+#ifndef DVR_TILE_W
+#define DVR_TILE_W 8 // one warp renders an 8x4 pixel tile
+#endif
+constexpr int kTileW = DVR_TILE_W;
+constexpr int kTileH = 32 / DVR_TILE_W;
 constexpr int kBlockThreads = 256;
 
 // kernel parameter block of the frame kernel (passed by value as __grid_constant__)

@@ -146,7 +146,7 @@ struct TfSelectSingle
 // K1: one frame.  Persistent CTAs; every warp pulls 8x4-pixel tiles from a global counter.
 // ----------------------------------------------------------------------------------------------
 #ifndef DVR_OCC
-#define DVR_OCC 3 // minimum resident CTAs per SM the frame kernel is compiled for (register budget)
+#define DVR_OCC 2 // minimum resident CTAs per SM the frame kernel is compiled for (register budget)
 #endif
 
 template <bool SKIP, bool STATS, bool SINGLE>
@@ -176,7 +176,7 @@ __global__ void __launch_bounds__(kBlockThreads, DVR_OCC) dvrFrameKernel(const _
     const uint32_t tyIdx = tile / P.tilesX, txIdx = tile - tyIdx * P.tilesX;
     if (P.tileRanks > 1u && (tyIdx % P.tileRanks) != P.tileRank)
       continue;
-    const uint32_t lx = txIdx * kTileW + (lane & 7), ly = tyIdx * kTileH + (lane >> 3);
+    const uint32_t lx = txIdx * kTileW + (lane % kTileW), ly = tyIdx * kTileH + (lane / kTileW);
     if (lx >= P.launchW || ly >= P.launchH)
       continue;
     uint32_t px = lx, py = ly;
@@ -204,10 +204,10 @@ __global__ void __launch_bounds__(kBlockThreads, DVR_OCC) dvrFrameKernel(const _
       bool anyHit = false;
       float volumeDepth;
       if (SINGLE)
-        volumeDepth = rayMarchAllVolumes<SKIP, false, STATS>(inst, 1, TfSelectSingle{s_tf}, org, dir, FLT_MAX,
+        volumeDepth = rayMarchAllVolumes<SKIP, false, STATS, true>(P.inl, 1, TfSelectSingle{s_tf}, org, dir, FLT_MAX,
             P.invSamplingRate, rng, color, opacity, objID, instID, st, P.cellBitmap, anyHit);
       else
-        volumeDepth = rayMarchAllVolumes<SKIP, false, STATS>(inst, nInst, TfSelectShared{s_tf, inst}, org, dir,
+        volumeDepth = rayMarchAllVolumes<SKIP, false, STATS, false>(inst, nInst, TfSelectShared{s_tf, inst}, org, dir,
             FLT_MAX, P.invSamplingRate, rng, color, opacity, objID, instID, st, P.cellBitmap, anyHit);
       if (STATS && anyHit)
         raysHit++;
@@ -292,7 +292,7 @@ __global__ void __launch_bounds__(kBlockThreads, 2) dvrPartialKernel(const __gri
   const bool centered = P.integrator == DVR_INTEGRATOR_RAYCAST;
   for (uint32_t tile = nextTile(P.sched, lane); tile < nTiles; tile = nextTile(P.sched, lane)) {
     const uint32_t tyIdx = tile / P.tilesX, txIdx = tile - tyIdx * P.tilesX;
-    const uint32_t px = txIdx * kTileW + (lane & 7), py = tyIdx * kTileH + (lane >> 3);
+    const uint32_t px = txIdx * kTileW + (lane % kTileW), py = tyIdx * kTileH + (lane / kTileW);
     if (px >= P.width || py >= P.height)
       continue;
     Philox rng;
@@ -306,7 +306,7 @@ __global__ void __launch_bounds__(kBlockThreads, 2) dvrPartialKernel(const __gri
     float opacity = 0.f;
     uint32_t objID = ~0u, instID = ~0u;
     bool anyHit = false;
-    const float depth = rayMarchAllVolumes<SKIP, true, false>(&P.inst, 1, TfSelectSingle{s_tf}, org, dir, FLT_MAX,
+    const float depth = rayMarchAllVolumes<SKIP, true, false, true>(&P.inst, 1, TfSelectSingle{s_tf}, org, dir, FLT_MAX,
         P.invSamplingRate, rng, color, opacity, objID, instID, st, nullptr, anyHit);
     const uint32_t idx = px + py * P.width;
     P.partialRgba[idx] = make_float4(color.x, color.y, color.z, opacity);

@@ -106,6 +106,7 @@ __device__ __forceinline__ void marchSegment(const VolumeDev &v, const float4 *_
 
   const float3 halfSpacing = 0.5f * f.spacing;
   const float vrLo = v.vrLower, vrHi = v.vrUpper;
+  const float invRange = __fdiv_rn(1.0f, __fsub_rn(vrHi, vrLo)); // gpu_math.h:176-180, hoisted out of the loop
   float transmittance = 1.f;
 
   // d(voxel coordinate)/dt, used by SKIP/SLAB bookkeeping only (never for the sample position)
@@ -197,20 +198,26 @@ __device__ __forceinline__ void marchSegment(const VolumeDev &v, const float4 *_
         }
       }
     }
+    // classify + opacity correction for the whole batch first (independent chains => ILP), then the
+    // short sequential front-to-back composite with the reference's per-sample termination test
+    float4 co[DVR_BATCH];
+    float st[DVR_BATCH];
 #pragma unroll
     for (int k = 0; k < DVR_BATCH; ++k) {
-      if (opacity < 0.99f && ts[k] <= tUpper) {
-        const float sv = s[k];
-        if (!isnan(sv)) {
-          const float4 co = tfLookup(tf, rangePosition(sv, vrLo, vrHi));
-          const float stepTransmittance = stepPow(__fsub_rn(1.f, co.w), exponent);
-          const float w = __fmul_rn(transmittance, __fsub_rn(1.f, stepTransmittance));
-          color.x = __fmaf_rn(w, co.x, color.x);
-          color.y = __fmaf_rn(w, co.y, color.y);
-          color.z = __fmaf_rn(w, co.z, color.z);
-          opacity = __fadd_rn(opacity, w);
-          transmittance = __fmul_rn(transmittance, stepTransmittance);
-        }
+      const float c = __fmul_rn(__fsub_rn(fmaxf(vrLo, fminf(s[k], vrHi)), vrLo), invRange); // position(s, range)
+      co[k] = tfLookup(tf, c);
+      st[k] = stepPow(__fsub_rn(1.f, co[k].w), exponent);
+    }
+#pragma unroll
+    for (int k = 0; k < DVR_BATCH; ++k) {
+      // s[k] is NaN for lattice points past the segment / not owned / NaN voxels: skipped like the reference
+      if (opacity < 0.99f && !isnan(s[k])) {
+        const float w = __fmul_rn(transmittance, __fsub_rn(1.f, st[k]));
+        color.x = __fmaf_rn(w, co[k].x, color.x);
+        color.y = __fmaf_rn(w, co[k].y, color.y);
+        color.z = __fmaf_rn(w, co[k].z, color.z);
+        opacity = __fadd_rn(opacity, w);
+        transmittance = __fmul_rn(transmittance, st[k]);
       }
     }
     t = tt;
@@ -229,7 +236,9 @@ __device__ __forceinline__ void marchSegment(const VolumeDev &v, const float4 *_
 // loop over the flattened instance list (closest clamped entry first, the volume marched last
 // is excluded from the next search exactly like the lastVolID/lastInstID test of
 // Intersectors_ptx.cu:250-252).
-template <bool SKIP, bool SLAB, bool STATS, typename TfSelect>
+// SINGLE: exactly one instance => every access uses the constant index 0, which keeps the texture
+// handle and field constants warp-uniform (no divergent-handle loop around the TEX instruction).
+template <bool SKIP, bool SLAB, bool STATS, bool SINGLE, typename TfSelect>
 __device__ __forceinline__ float rayMarchAllVolumes(const InstanceDev *__restrict__ inst, const int nInst,
     TfSelect tfOf, const float3 org, const float3 dir, const float tfar, const float invSamplingRate,
     Philox &rng, float3 &color, float &opacity, uint32_t &objID, uint32_t &instID, MarchStats &stats,
@@ -245,10 +254,10 @@ __device__ __forceinline__ float rayMarchAllVolumes(const InstanceDev *__restric
     int best = -1;
     float bt0 = 0.f, bt1 = 0.f;
     float3 bo = org, bd = dir;
-    for (int i = 0; i < nInst; ++i) {
+    for (int i = 0; i < (SINGLE ? 1 : nInst); ++i) {
       if (i == last)
         continue;
-      const InstanceDev &in = inst[i];
+      const InstanceDev &in = inst[SINGLE ? 0 : i];
       float3 lo = org, ld = dir;
       if (!in.identity) {
         lo = xfmPoint(in.xfm, org);
@@ -267,7 +276,7 @@ __device__ __forceinline__ float rayMarchAllVolumes(const InstanceDev *__restric
     }
     if (best < 0)
       break;
-    const InstanceDev &in = inst[best];
+    const InstanceDev &in = inst[SINGLE ? 0 : best];
     if (firstHit) {
       objID = in.v.id;
       instID = in.instId;
@@ -279,7 +288,7 @@ __device__ __forceinline__ float rayMarchAllVolumes(const InstanceDev *__restric
     // detail::rayMarchVolume: jitter #1 uses the UNSCALED step (volumeIntegration.h:117-120)
     const float tStart = __fmaf_rn(in.v.f.stepSize, rng.uniform(), bt0);
     marchSegment<SKIP, SLAB, STATS>(
-        in.v, tfOf(best), bo, bd, tStart, bt1, invSamplingRate, rng, color, opacity, stats, cellBitmap);
+        in.v, tfOf(SINGLE ? 0 : best), bo, bd, tStart, bt1, invSamplingRate, rng, color, opacity, stats, cellBitmap);
     rayLower = __fadd_rn(bt1, 1e-3f);
     last = best;
   } while (opacity < 0.99f);
