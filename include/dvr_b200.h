@@ -273,6 +273,23 @@ int dvr_resolve(const DvrFrameParams *params, const float *partialRgba, const fl
     uint32_t objId, uint32_t instId, const DvrFrameBuffers *buffers, size_t pixelBegin,
     size_t pixelEnd, void *stream);
 
+/* Direct-send compositing fused with the resolve, over peer memory: for pixels [pixelBegin,pixelEnd)
+ * the nSlabs partial images (device pointers, possibly CUDA-IPC / peer mapped, given in ascending z
+ * order of their slabs) are combined front-to-back with `over` — the per-pixel view order is the sign
+ * of the primary ray's z direction — and the result goes through the same tail as dvr_resolve.
+ * buffers->outColor may itself be a peer pointer (the display GPU's frame).  One launch per rank
+ * replaces log2(N) binary-swap rounds + gather. */
+int dvr_composite_resolve_peers(const DvrFrameParams *params, const DvrCamera *camera,
+    const float *const *partialRgba, const float *const *partialDepth, uint32_t nSlabs, uint32_t objId,
+    uint32_t instId, const DvrFrameBuffers *buffers, size_t pixelBegin, size_t pixelEnd, void *stream);
+
+/* ---- CUDA IPC plumbing for one-process-per-GPU sharing of frame / partial buffers ------------- */
+#define DVR_IPC_HANDLE_BYTES 64
+int dvr_ipc_alloc(size_t bytes, void **devPtr, unsigned char handle[DVR_IPC_HANDLE_BYTES]);
+int dvr_ipc_open(const unsigned char handle[DVR_IPC_HANDLE_BYTES], void **devPtr);
+int dvr_ipc_close(void *devPtr);
+int dvr_ipc_free(void *devPtr);
+
 /* ---- map-time helpers ------------------------------------------------------------------ */
 /* Frame::mapAlbedoBuffer / mapNormalBuffer, frame/Frame.cu:521-557: out = accum * invFrameID */
 int dvr_scale_vec3(const float *accumVec3, float *outVec3, size_t nPixels, float scale, void *stream);

@@ -1,0 +1,81 @@
+"""CPU suite, part 4: host logic of the multi-GPU drivers — partition helpers, and the handle exchange /
+barrier plumbing over a real 2-process gloo group (no GPU)."""
+import os
+import subprocess
+import sys
+
+import pytest
+
+from visrtx_b200 import multigpu
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.mark.parametrize("nz,world", [(64, 1), (64, 2), (65, 4), (4096, 8), (7, 7), (100, 3)])
+def test_slab_ranges_partition_every_slice_once(nz, world):
+    r = multigpu.slab_ranges(nz, world)
+    assert len(r) == world and r[0][0] == 0 and r[-1][1] == nz
+    for (a0, a1), (b0, b1) in zip(r, r[1:]):
+        assert a1 == b0 and a1 > a0
+    sizes = [b - a for a, b in r]
+    assert max(sizes) - min(sizes) <= 1
+    for a, b in r:
+        lo, hi = multigpu.resident_range(a, b, nz)
+        assert lo == max(a - 1, 0) and hi == min(b + 1, nz)
+
+
+def test_slab_ranges_rejects_too_many_ranks():
+    with pytest.raises(ValueError):
+        multigpu.slab_ranges(3, 4)
+
+
+@pytest.mark.parametrize("npx,world", [(1920 * 1080, 8), (1920 * 1080, 3), (100, 4), (256, 1), (3840 * 2160, 2)])
+def test_pixel_strips_cover_the_frame(npx, world):
+    s = multigpu.pixel_strips(npx, world)
+    assert s[0][0] == 0 and max(e for _, e in s) == npx
+    covered = 0
+    for (b, e) in s:
+        assert e >= b and b % 256 == 0 or b == npx
+        covered += e - b
+    assert covered == npx
+
+
+def test_tile_rows_interleave():
+    rows = [multigpu.tile_rows_of(r, 3, 1080) for r in range(3)]
+    assert sorted(sum(rows, [])) == list(range(270))
+    assert rows[1][:3] == [1, 4, 7]
+
+
+WORKER = r'''
+import os, sys
+sys.path.insert(0, sys.argv[1])
+import torch, torch.distributed as dist
+from visrtx_b200 import multigpu
+rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+dist.init_process_group("gloo")
+payload = bytes([rank]) * 64 + (b"C" * 64 if rank == 0 else b"")
+got = multigpu.exchange_bytes(dist, payload, world)
+assert [g[:64] for g in got] == [bytes([r]) * 64 for r in range(world)], got
+assert got[0][64:] == b"C" * 64
+bar = multigpu._Barrier(dist, torch, "cpu")
+for _ in range(3):
+    bar()
+assert bar.flag.item() == 0
+z = multigpu.slab_ranges(64, world)[rank]
+t = torch.tensor([z[1] - z[0]])
+dist.all_reduce(t)
+assert t.item() == 64
+dist.destroy_process_group()
+print("HOST_WORKER_OK", rank)
+'''
+
+
+def test_handle_exchange_and_barrier_over_gloo(tmp_path):
+    script = tmp_path / "worker.py"
+    script.write_text(WORKER)
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1", MASTER_PORT="29533", WORLD_SIZE="2")
+    procs = [subprocess.Popen([sys.executable, str(script), ROOT], env=dict(env, RANK=str(r)), stdout=subprocess.PIPE,
+                              stderr=subprocess.PIPE, text=True) for r in range(2)]
+    outs = [p.communicate(timeout=180) for p in procs]
+    for r, (o, e) in enumerate(outs):
+        assert f"HOST_WORKER_OK {r}" in o, e[-2000:]

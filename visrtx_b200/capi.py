@@ -34,6 +34,7 @@ EXPORTED_SYMBOLS = [
     "dvr_volume_create", "dvr_volume_update", "dvr_volume_destroy", "dvr_volume_majorants",
     "dvr_render", "dvr_render_instrumented", "dvr_launch_count",
     "dvr_render_partial", "dvr_composite_over", "dvr_resolve", "dvr_scale_vec3",
+    "dvr_composite_resolve_peers", "dvr_ipc_alloc", "dvr_ipc_open", "dvr_ipc_close", "dvr_ipc_free",
 ]
 
 
@@ -329,3 +330,36 @@ def resolve(params, partial_rgba: int, partial_depth: int, obj_id: int, inst_id:
 def scale_vec3(src: int, dst: int, n_pixels: int, scale: float, stream: int = 0):
     _check(lib.dvr_scale_vec3(C.c_void_p(src), C.c_void_p(dst), C.c_size_t(n_pixels), C.c_float(scale),
                               C.c_void_p(stream)))
+
+
+def composite_resolve_peers(params, camera, partial_rgba_ptrs, partial_depth_ptrs, obj_id: int, inst_id: int,
+                            buffers, begin: int, end: int, stream: int = 0):
+    n = len(partial_rgba_ptrs)
+    rg = (C.c_void_p * n)(*partial_rgba_ptrs)
+    dp = (C.c_void_p * n)(*partial_depth_ptrs) if partial_depth_ptrs else None
+    _check(lib.dvr_composite_resolve_peers(C.byref(params), C.byref(camera), rg, dp, C.c_uint32(n),
+                                           C.c_uint32(obj_id), C.c_uint32(inst_id), C.byref(buffers),
+                                           C.c_size_t(begin), C.c_size_t(end), C.c_void_p(stream)))
+
+
+def ipc_alloc(nbytes: int):
+    """cudaMalloc + cudaIpcGetMemHandle: returns (device pointer, 64-byte handle)."""
+    p = C.c_void_p()
+    h = (C.c_ubyte * 64)()
+    _check(lib.dvr_ipc_alloc(C.c_size_t(nbytes), C.byref(p), h))
+    return p.value, bytes(h)
+
+
+def ipc_open(handle: bytes) -> int:
+    p = C.c_void_p()
+    h = (C.c_ubyte * 64)(*handle)
+    _check(lib.dvr_ipc_open(h, C.byref(p)))
+    return p.value
+
+
+def ipc_close(ptr: int) -> None:
+    _check(lib.dvr_ipc_close(C.c_void_p(ptr)))
+
+
+def ipc_free(ptr: int) -> None:
+    _check(lib.dvr_ipc_free(C.c_void_p(ptr)))

@@ -896,6 +896,99 @@ int dvr_resolve(const DvrFrameParams *p, const float *partialRgba, const float *
   return launchResolve(R, (cudaStream_t)stream);
 }
 
+int dvr_composite_resolve_peers(const DvrFrameParams *p, const DvrCamera *camera, const float *const *partialRgba,
+    const float *const *partialDepth, uint32_t nSlabs, uint32_t objId, uint32_t instId, const DvrFrameBuffers *b,
+    size_t pixelBegin, size_t pixelEnd, void *stream)
+{
+  if (!p || !camera || !partialRgba || !b || !b->colorAccumulation || !b->outColor || nSlabs == 0) {
+    setError("dvr_composite_resolve_peers: null argument");
+    return DVR_ERR_INVALID_ARGUMENT;
+  }
+  if (nSlabs > (uint32_t)kMaxSlabs) {
+    setError("dvr_composite_resolve_peers: at most 16 slabs");
+    return DVR_ERR_UNSUPPORTED;
+  }
+  PeerResolveLaunch L;
+  std::memset(&L, 0, sizeof(L));
+  ResolveLaunch &R = L.r;
+  R.width = p->width;
+  R.height = p->height;
+  R.format = p->format;
+  R.frameID = p->frameID;
+  R.background = make_float4(p->background[0], p->background[1], p->background[2], p->background[3]);
+  R.fb.accum = (float4 *)b->colorAccumulation;
+  R.fb.outU32 = (uint32_t *)b->outColor;
+  R.fb.outF32 = (float4 *)b->outColor;
+  R.fb.depth = b->depth;
+  R.fb.primId = b->primId;
+  R.fb.objId = b->objId;
+  R.fb.instId = b->instId;
+  R.fb.albedo = b->albedo;
+  R.fb.normal = b->normal;
+  R.objId = objId;
+  R.instId = instId;
+  R.pixelBegin = pixelBegin;
+  R.pixelEnd = pixelEnd > (size_t)p->width * p->height ? (size_t)p->width * p->height : pixelEnd;
+  fillCamera(camera, L.cam);
+  L.invW = 1.f / (float)p->width;
+  L.invH = 1.f / (float)p->height;
+  L.nSlabs = (int)nSlabs;
+  for (uint32_t i = 0; i < nSlabs; ++i) {
+    if (!partialRgba[i]) {
+      setError("dvr_composite_resolve_peers: null partial image");
+      return DVR_ERR_INVALID_ARGUMENT;
+    }
+    L.rgba[i] = (const float4 *)partialRgba[i];
+    L.depth[i] = partialDepth ? partialDepth[i] : nullptr;
+  }
+  return launchPeerResolve(L, (cudaStream_t)stream);
+}
+
+int dvr_ipc_alloc(size_t bytes, void **devPtr, unsigned char handle[DVR_IPC_HANDLE_BYTES])
+{
+  static_assert(sizeof(cudaIpcMemHandle_t) == DVR_IPC_HANDLE_BYTES, "IPC handle size");
+  if (!devPtr || !handle || bytes == 0) {
+    setError("dvr_ipc_alloc: bad argument");
+    return DVR_ERR_INVALID_ARGUMENT;
+  }
+  DVR_CUDA(cudaMalloc(devPtr, bytes));
+  cudaIpcMemHandle_t h;
+  cudaError_t e = cudaIpcGetMemHandle(&h, *devPtr);
+  if (e != cudaSuccess) {
+    cudaFree(*devPtr);
+    *devPtr = nullptr;
+    return cudaFail(e, "cudaIpcGetMemHandle");
+  }
+  std::memcpy(handle, &h, sizeof(h));
+  return DVR_OK;
+}
+
+int dvr_ipc_open(const unsigned char handle[DVR_IPC_HANDLE_BYTES], void **devPtr)
+{
+  if (!devPtr || !handle) {
+    setError("dvr_ipc_open: bad argument");
+    return DVR_ERR_INVALID_ARGUMENT;
+  }
+  cudaIpcMemHandle_t h;
+  std::memcpy(&h, handle, sizeof(h));
+  DVR_CUDA(cudaIpcOpenMemHandle(devPtr, h, cudaIpcMemLazyEnablePeerAccess));
+  return DVR_OK;
+}
+
+int dvr_ipc_close(void *devPtr)
+{
+  if (devPtr)
+    DVR_CUDA(cudaIpcCloseMemHandle(devPtr));
+  return DVR_OK;
+}
+
+int dvr_ipc_free(void *devPtr)
+{
+  if (devPtr)
+    DVR_CUDA(cudaFree(devPtr));
+  return DVR_OK;
+}
+
 int dvr_scale_vec3(const float *accumVec3, float *outVec3, size_t nPixels, float scale, void *stream)
 {
   if (!accumVec3 || !outVec3) {

@@ -66,6 +66,17 @@ struct ResolveLaunch
   size_t pixelBegin, pixelEnd;
 };
 
+constexpr int kMaxSlabs = 16;
+struct PeerResolveLaunch
+{
+  ResolveLaunch r;
+  CameraDev cam;
+  float invW, invH;
+  int nSlabs;
+  const float4 *rgba[kMaxSlabs];
+  const float *depth[kMaxSlabs];
+};
+
 // error plumbing -----------------------------------------------------------------------------
 void setError(const std::string &msg);
 int cudaFail(cudaError_t e, const char *what);
@@ -86,6 +97,7 @@ int launchPartial(const PartialLaunch &p, cudaStream_t s);
 int launchResolve(const ResolveLaunch &p, cudaStream_t s);
 int launchCompositeOver(float4 *front, float *frontDepth, const float4 *back, const float *backDepth,
     size_t begin, size_t end, bool backIsInFront, cudaStream_t s);
+int launchPeerResolve(const PeerResolveLaunch &p, cudaStream_t s);
 int launchScaleVec3(const float *in, float *out, size_t n, float scale, cudaStream_t s);
 int launchMacrocellBuild(cudaTextureObject_t pointTex, int3 dims, int zTexBegin, int texDepth, int3 gridDims,
     float2 *ranges, cudaStream_t s);

@@ -422,6 +422,80 @@ int launchResolve(const ResolveLaunch &r, cudaStream_t s)
   return DVR_OK;
 }
 
+// ----------------------------------------------------------------------------------------------
+// sort-last direct send: composite the slabs' partial images (peer loads over NVLink) in per-pixel
+// view order and resolve, in one kernel
+// ----------------------------------------------------------------------------------------------
+__device__ __forceinline__ void resolvePixel(const ResolveLaunch &R, size_t i, float4 pc, float pd)
+{
+  float3 color = f3(pc.x, pc.y, pc.z);
+  float opacity = pc.w;
+  color = color * opacity; // Raycast_ptx.cu:159
+  const float oneMinus = __fsub_rn(1.f, opacity);
+  color.x = __fmaf_rn(R.background.x, oneMinus, color.x);
+  color.y = __fmaf_rn(R.background.y, oneMinus, color.y);
+  color.z = __fmaf_rn(R.background.z, oneMinus, color.z);
+  opacity = __fmaf_rn(R.background.w, oneMinus, opacity);
+  FrameLaunch P{};
+  P.width = R.width;
+  P.height = R.height;
+  P.format = R.format;
+  P.frameID = R.frameID;
+  P.checkerboardID = -1;
+  P.fb = R.fb;
+  const bool hit = pd < 1e30f;
+  const uint32_t px = (uint32_t)(i % R.width), py = (uint32_t)(i / R.width);
+  accumResults(P, px, py, make_float4(color.x, color.y, color.z, opacity), pd, color, f3(0.f, 0.f, 0.f), 0u,
+      hit ? R.objId : ~0u, hit ? R.instId : ~0u, 0, R.frameID == 0);
+}
+
+__global__ void __launch_bounds__(256) dvrPeerResolveKernel(const __grid_constant__ PeerResolveLaunch L)
+{
+  const size_t i = L.r.pixelBegin + blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  if (i >= L.r.pixelEnd)
+    return;
+  const uint32_t px = (uint32_t)(i % L.r.width), py = (uint32_t)(i / L.r.width);
+  float3 org, dir;
+  cameraCreateRay(L.cam, __fmul_rn((float)px, L.invW), __fmul_rn((float)py, L.invH), 0.5f, 0.5f, org, dir);
+  const bool ascending = dir.z >= 0.f; // rays travelling towards +z meet the low-z slab first
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  float depth = 1e30f;
+  // issue all peer loads first (independent), then composite
+  float4 part[kMaxSlabs];
+  float pdep[kMaxSlabs];
+#pragma unroll
+  for (int k = 0; k < kMaxSlabs; ++k) {
+    if (k < L.nSlabs) {
+      const int sidx = ascending ? k : L.nSlabs - 1 - k;
+      part[k] = __ldcv(&L.rgba[sidx][i]); // volatile-cached: another GPU wrote this line
+      pdep[k] = L.depth[sidx] ? __ldcv(&L.depth[sidx][i]) : 1e30f;
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < kMaxSlabs; ++k) {
+    if (k < L.nSlabs) {
+      const float w = __fsub_rn(1.f, acc.w);
+      acc.x = __fmaf_rn(w, part[k].x, acc.x);
+      acc.y = __fmaf_rn(w, part[k].y, acc.y);
+      acc.z = __fmaf_rn(w, part[k].z, acc.z);
+      acc.w = __fmaf_rn(w, part[k].w, acc.w);
+      depth = fminf(depth, pdep[k]);
+    }
+  }
+  resolvePixel(L.r, i, acc, depth);
+}
+
+int launchPeerResolve(const PeerResolveLaunch &p, cudaStream_t s)
+{
+  if (p.r.pixelEnd <= p.r.pixelBegin)
+    return DVR_OK;
+  const size_t n = p.r.pixelEnd - p.r.pixelBegin;
+  dvrPeerResolveKernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(p);
+  DVR_CUDA(cudaGetLastError());
+  countLaunch();
+  return DVR_OK;
+}
+
 __global__ void dvrScaleVec3Kernel(const float *__restrict__ in, float *__restrict__ out, size_t n, float scale)
 {
   const size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;

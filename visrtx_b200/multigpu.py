@@ -1,0 +1,223 @@
+"""Multi-GPU drivers for the DVR path on one NVSwitch box: one process per GPU (torch.distributed is
+plumbing only — rendezvous, handle exchange, stream-ordered barriers).
+
+* sort-first  (volume fits one GPU; BASELINE C2/C3): every rank holds the whole field and renders the
+  tile rows ``row % world == rank``.  The render kernel's colour stores go straight into the display
+  rank's frame through a CUDA-IPC mapped pointer (peer stores over NVLink), so the "gather" is fused
+  into the render launch; accumulation/depth stay sharded with their owner.
+* sort-last   (C4): every rank holds a z-slab (+1 ghost slice each side) and marches its samples of
+  the GLOBAL lattice into a premultiplied partial image; then ONE fused kernel per rank composites its
+  pixel strip from all ranks' partial images (peer loads over NVLink, per-pixel view order) and
+  resolves it into the display rank's frame.  Partial images are double-buffered so one barrier per
+  frame separates "all partials written" from "composite".
+
+The partition helpers are pure Python and tested with gloo on CPU (tests/test_multigpu_host.py).
+"""
+from __future__ import annotations
+
+from typing import List, Sequence, Tuple
+
+
+def slab_ranges(nz: int, world: int) -> List[Tuple[int, int]]:
+    """Balanced, contiguous z-slice ownership [z0, z1) per rank; every slice owned exactly once."""
+    if world < 1 or nz < world:
+        raise ValueError(f"cannot split {nz} slices over {world} ranks")
+    base, rem = divmod(nz, world)
+    out, z = [], 0
+    for r in range(world):
+        n = base + (1 if r < rem else 0)
+        out.append((z, z + n))
+        z += n
+    return out
+
+
+def resident_range(z0: int, z1: int, nz: int) -> Tuple[int, int]:
+    """Slices a slab must hold: its own plus one ghost slice on each side, clamped to the volume."""
+    return max(z0 - 1, 0), min(z1 + 1, nz)
+
+
+def pixel_strips(n_pixels: int, world: int, align: int = 256) -> List[Tuple[int, int]]:
+    """Contiguous pixel ranges for the compositing stage, aligned so that stores stay coalesced."""
+    per = -(-n_pixels // world)
+    per = -(-per // align) * align
+    out = []
+    for r in range(world):
+        b = min(r * per, n_pixels)
+        out.append((b, min(b + per, n_pixels)))
+    return out
+
+
+def tile_rows_of(rank: int, world: int, height: int, tile_h: int = 4) -> List[int]:
+    """Tile rows (of tile_h pixel rows) a rank renders in sort-first mode."""
+    n_rows = -(-height // tile_h)
+    return [r for r in range(n_rows) if r % world == rank]
+
+
+def exchange_bytes(dist, payload: bytes, world: int) -> List[bytes]:
+    """all-gather of one small bytes object per rank (CUDA-IPC handles); works on gloo and nccl."""
+    out = [None] * world
+    dist.all_gather_object(out, payload)
+    return out
+
+
+class _Barrier:
+    """Stream-ordered barrier: a 1-element all-reduce enqueued on the current stream (no host sync)."""
+
+    def __init__(self, dist, torch, device):
+        self.dist = dist
+        self.flag = torch.zeros(1, dtype=torch.int32, device=device)
+
+    def __call__(self):
+        self.dist.all_reduce(self.flag)
+
+
+class SortFirst:
+    """Sort-first driver.  `render(frame_id, camera)` enqueues one frame on the current stream."""
+
+    def __init__(self, capi, torch, dist, rank: int, world: int, device, width: int, height: int, instances,
+                 n_instances: int, fmt: int, integrator: int, rate: float, background, skip: bool = False):
+        self.capi, self.torch, self.dist = capi, torch, dist
+        self.rank, self.world, self.device = rank, world, device
+        self.W, self.H, self.fmt = width, height, fmt
+        self.integrator, self.rate, self.background, self.skip = integrator, rate, background, skip
+        self.instances, self.n_instances = instances, n_instances
+        npx = width * height
+        px_bytes = 16 if fmt == capi.DVR_FORMAT_FLOAT32_VEC4 else 4
+        self.accum = torch.zeros((npx, 4), dtype=torch.float32, device=device)
+        self.depth = torch.zeros(npx, dtype=torch.float32, device=device)
+        self._owned = None
+        if world == 1:
+            self.color_local = torch.zeros(npx * px_bytes // 4, dtype=torch.int32, device=device)
+            self.color_ptr = self.color_local.data_ptr()
+        else:
+            if rank == 0:
+                self._owned, handle = capi.ipc_alloc(npx * px_bytes)
+                self.color_ptr = self._owned
+            else:
+                handle = b""
+            handles = exchange_bytes(dist, handle, world)
+            if rank != 0:
+                self.color_ptr = capi.ipc_open(handles[0])
+        self.fb = capi.frame_buffers(self.accum.data_ptr(), self.color_ptr, self.depth.data_ptr())
+        self.barrier = _Barrier(dist, torch, device) if world > 1 else (lambda: None)
+
+    def params(self, frame_id: int):
+        return self.capi.frame_params(self.W, self.H, self.fmt, self.integrator, frame_id, -1, 1, self.rate,
+                                      self.background, tile_rank=self.rank, tile_ranks=self.world, skip=self.skip)
+
+    def render(self, frame_id: int, camera, stream: int):
+        self.capi.render(self.params(frame_id), camera, self.instances, self.n_instances, self.fb, stream)
+        self.barrier()  # all ranks' tile rows have landed in the display rank's frame
+
+    def color_tensor(self):
+        """Display rank only: the assembled frame as a torch tensor view (copy)."""
+        import ctypes
+        npx = self.W * self.H
+        n32 = npx * (4 if self.fmt == self.capi.DVR_FORMAT_FLOAT32_VEC4 else 1)
+        out = self.torch.empty(n32, dtype=self.torch.int32, device=self.device)
+        ctypes.CDLL("libcudart.so").cudaMemcpy(ctypes.c_void_p(out.data_ptr()), ctypes.c_void_p(self.color_ptr),
+                                               ctypes.c_size_t(n32 * 4), ctypes.c_int(3))
+        return out
+
+    def close(self):
+        self.torch.cuda.synchronize()
+        if self.world > 1:
+            self.dist.barrier()
+            if self.rank != 0:
+                self.capi.ipc_close(self.color_ptr)
+            self.dist.barrier()
+            if self._owned:
+                self.capi.ipc_free(self._owned)
+
+
+class SortLast:
+    """Sort-last driver over z-slabs: partial march + fused peer composite/resolve."""
+
+    def __init__(self, capi, torch, dist, rank: int, world: int, device, width: int, height: int, instance,
+                 obj_id: int, inst_id: int, fmt: int, integrator: int, rate: float, background, skip: bool = False):
+        self.capi, self.torch, self.dist = capi, torch, dist
+        self.rank, self.world, self.device = rank, world, device
+        self.W, self.H, self.fmt = width, height, fmt
+        self.integrator, self.rate, self.background, self.skip = integrator, rate, background, skip
+        self.instance, self.obj_id, self.inst_id = instance, obj_id, inst_id
+        npx = width * height
+        self.npx = npx
+        px_bytes = 16 if fmt == capi.DVR_FORMAT_FLOAT32_VEC4 else 4
+        self.strips = pixel_strips(npx, world)
+        self.accum = torch.zeros((npx, 4), dtype=torch.float32, device=device)
+        self.depth = torch.zeros(npx, dtype=torch.float32, device=device)
+        # my partial images (double-buffered) live in IPC-exportable allocations
+        self._mine, handles = [], []
+        self._peer_open = []
+        if world == 1:
+            self.buf = [torch.zeros((npx, 5), dtype=torch.float32, device=device) for _ in range(2)]
+            self.rgba_ptrs = [[b.data_ptr()] for b in self.buf]
+            self.depth_ptrs = [[b.data_ptr() + npx * 16] for b in self.buf]
+            self.color_local = torch.zeros(npx * px_bytes // 4, dtype=torch.int32, device=device)
+            self.color_ptr = self.color_local.data_ptr()
+            self._color_owned = None
+        else:
+            payload = b""
+            for _ in range(2):
+                p, h = capi.ipc_alloc(npx * 20)
+                self._mine.append(p)
+                payload += h
+            self._color_owned = None
+            if rank == 0:
+                self._color_owned, hc = capi.ipc_alloc(npx * px_bytes)
+                payload += hc
+            all_h = exchange_bytes(dist, payload, world)
+            self.rgba_ptrs, self.depth_ptrs = [[], []], [[], []]
+            for r in range(world):
+                for b in range(2):
+                    if r == rank:
+                        p = self._mine[b]
+                    else:
+                        p = capi.ipc_open(all_h[r][64 * b:64 * (b + 1)])
+                        self._peer_open.append(p)
+                    self.rgba_ptrs[b].append(p)
+                    self.depth_ptrs[b].append(p + npx * 16)
+            if rank == 0:
+                self.color_ptr = self._color_owned
+            else:
+                self.color_ptr = capi.ipc_open(all_h[0][128:192])
+                self._peer_open.append(self.color_ptr)
+        self.fb = capi.frame_buffers(self.accum.data_ptr(), self.color_ptr, self.depth.data_ptr())
+        self.barrier = _Barrier(dist, torch, device) if world > 1 else (lambda: None)
+        self.frame_parity = 0
+
+    def params(self, frame_id: int):
+        return self.capi.frame_params(self.W, self.H, self.fmt, self.integrator, frame_id, -1, 1, self.rate,
+                                      self.background, skip=self.skip)
+
+    def render(self, frame_id: int, camera, stream: int):
+        b = self.frame_parity
+        self.frame_parity ^= 1
+        p = self.params(frame_id)
+        self.capi.render_partial(p, camera, self.instance, self.rgba_ptrs[b][self.rank], self.depth_ptrs[b][self.rank],
+                                 stream)
+        self.barrier()  # every slab's partial image of this frame is complete
+        lo, hi = self.strips[self.rank]
+        self.capi.composite_resolve_peers(p, camera, self.rgba_ptrs[b], self.depth_ptrs[b], self.obj_id, self.inst_id,
+                                          self.fb, lo, hi, stream)
+        self.barrier()  # every strip has landed in the display rank's frame
+
+    def color_tensor(self):
+        import ctypes
+        n32 = self.npx * (4 if self.fmt == self.capi.DVR_FORMAT_FLOAT32_VEC4 else 1)
+        out = self.torch.empty(n32, dtype=self.torch.int32, device=self.device)
+        ctypes.CDLL("libcudart.so").cudaMemcpy(ctypes.c_void_p(out.data_ptr()), ctypes.c_void_p(self.color_ptr),
+                                               ctypes.c_size_t(n32 * 4), ctypes.c_int(3))
+        return out
+
+    def close(self):
+        self.torch.cuda.synchronize()
+        if self.world > 1:
+            self.dist.barrier()
+            for p in self._peer_open:
+                self.capi.ipc_close(p)
+            self.dist.barrier()
+            for p in self._mine:
+                self.capi.ipc_free(p)
+            if self._color_owned:
+                self.capi.ipc_free(self._color_owned)
