@@ -284,14 +284,32 @@ def run_ours(args, torch, dist, rank, world):
 
     mode = args.mode
     if mode == "auto":
-        mode = "sort-first" if n ** 3 * 4 <= 64e9 else "sort-last"
-    if world == 1:
+        # sort-last (z-slabs) also wins when the volume fits one GPU: it shortens every ray by 1/N, while
+        # sort-first leaves the longest ray (the kernel's critical path) untouched (profiles/r01_multigpu.md)
+        mode = "sort-last"
+    if world == 1 and mode != "sort-last":
         mode = "single"
 
     t_setup = time.perf_counter()
-    vol = make_scene(args, torch, device)
-    field = capi.Field.create_structured(vol.data_ptr(), True, capi.DVR_FLOAT32, (n, n, n), (0, 0, 0), (1, 1, 1),
-                                         capi.DVR_FILTER_LINEAR, stream)
+    vol = None
+    if mode == "sort-last":
+        from visrtx_b200 import multigpu as _mg
+        z0, z1 = _mg.slab_ranges(n, world)[rank]
+        r0, r1 = _mg.resident_range(z0, z1, n)
+        field = capi.Field.create_slab(0, True, capi.DVR_FLOAT32, (n, n, n), z0, z1, (0, 0, 0), (1, 1, 1),
+                                       capi.DVR_FILTER_LINEAR, stream)
+        chunk = 32
+        for zc in range(r0, r1, chunk):  # generate + upload in chunks: the slab is never staged twice in HBM
+            ze = min(zc + chunk, r1)
+            part = make_scene(args, torch, device, z_begin=zc, z_end=ze)
+            field.upload_slices(part.data_ptr(), True, zc - r0, ze - zc, stream)
+            torch.cuda.synchronize()
+            del part
+        field.build_macrocells(stream)
+    else:
+        vol = make_scene(args, torch, device)
+        field = capi.Field.create_structured(vol.data_ptr(), True, capi.DVR_FLOAT32, (n, n, n), (0, 0, 0), (1, 1, 1),
+                                             capi.DVR_FILTER_LINEAR, stream)
     torch.cuda.synchronize()
     tf = capi.tf_discretize(color=scenes.tsd_default_colormap(256))
     volume = capi.Volume.create(field, tf, (0.0, 1.0), args.unit_distance, 0, stream)
@@ -299,44 +317,38 @@ def run_ours(args, torch, dist, rank, world):
     cam, _ = orbit(args)
     setup_s = time.perf_counter() - t_setup
 
-    accum = torch.zeros((npx, 4), dtype=torch.float32, device=device)
-    color = torch.zeros(npx, dtype=torch.int32, device=device)
-    depth = torch.zeros(npx, dtype=torch.float32, device=device)
-    fb = capi.frame_buffers(accum.data_ptr(), color.data_ptr(), depth.data_ptr())
+    from visrtx_b200 import multigpu
+    FMT, INTEG, BG = capi.DVR_FORMAT_UFIXED8_RGBA_SRGB, capi.DVR_INTEGRATOR_DEFAULT, (0.1, 0.1, 0.1, 1.0)
+    if mode == "sort-last":
+        driver = multigpu.SortLast(capi, torch, dist, rank, world, device, W, H, inst, 0, 0, FMT, INTEG, args.rate, BG,
+                                   skip=bool(args.skip))
+    else:
+        driver = multigpu.SortFirst(capi, torch, dist, rank, world, device, W, H, inst, ninst, FMT, INTEG, args.rate,
+                                    BG, skip=bool(args.skip), tile_band=int(os.environ.get("DVR_TILE_BAND", "1")))
+    fb = driver.fb
     host_color = torch.empty(npx, dtype=torch.int32, pin_memory=True)
 
     def params(frame_id):
-        return capi.frame_params(W, H, capi.DVR_FORMAT_UFIXED8_RGBA_SRGB, capi.DVR_INTEGRATOR_DEFAULT, frame_id, -1, 1,
-                                 args.rate, (0.1, 0.1, 0.1, 1.0), tile_rank=rank if mode == "sort-first" else 0,
-                                 tile_ranks=world if mode == "sort-first" else 1, skip=bool(args.skip))
-
-    gather_bufs = None
-    if mode == "sort-first":
-        gather_bufs = [torch.empty_like(color) for _ in range(world)] if rank == 0 else None
-
-    def exchange():
-        # sort-first: every rank rendered tile rows (ty % world == rank) into its own full-size buffer;
-        # rank 0 assembles the frame (one gather of the sRGB8 colour channel)
-        if mode != "sort-first":
-            return
-        dist.gather(color, gather_bufs, dst=0)
-        if rank == 0:
-            rows = color.view(H // 4 if H % 4 == 0 else -1, 4, W) if H % 4 == 0 else None
-            if rows is not None:
-                for r in range(1, world):
-                    src = gather_bufs[r].view(H // 4, 4, W)
-                    rows[r::world] = src[r::world]
+        return driver.params(frame_id)
 
     def step(frame_id):
-        capi.render(params(frame_id), cam, inst, ninst, fb, stream)
-        exchange()
+        driver.render(frame_id, cam, stream)
 
     # ---- untimed instrumented launch: samples / touched macrocells of this workload
     stats_t = torch.zeros(4, dtype=torch.int64, device=device)
     p_stats = params(0)
     p_stats.tileRank, p_stats.tileRanks = 0, 1
-    capi.render_instrumented(p_stats, cam, inst, ninst, fb, stats_t.data_ptr(), stream)
-    torch.cuda.synchronize()
+    scratch_color = torch.zeros(npx, dtype=torch.int32, device=device)
+    fb_stats = capi.frame_buffers(driver.accum.data_ptr(), scratch_color.data_ptr(), driver.depth.data_ptr())
+    if mode == "sort-last":
+        capi.render_partial_instrumented(p_stats, cam, inst, driver.rgba_ptrs[0][rank], driver.depth_ptrs[0][rank],
+                                         stats_t.data_ptr(), stream)
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.all_reduce(stats_t)  # samples / touched cells summed over the slabs
+    else:
+        capi.render_instrumented(p_stats, cam, inst, ninst, fb_stats, stats_t.data_ptr(), stream)
+        torch.cuda.synchronize()
     samples, skipped, rays_hit, cells = stats_t.tolist()
 
     # ---- device-timed region (clocks are sampled from here to the end of the e2e loop: the timed
@@ -369,14 +381,19 @@ def run_ours(args, torch, dist, rank, world):
     fps = 1000.0 / ms_per_step
 
     # ---- kernel-only duration for the roofline (render launches only, no exchange)
+    if mode == "sort-last":
+        krender = lambda fid: capi.render_partial(params(fid), cam, inst, driver.rgba_ptrs[0][rank],
+                                                  driver.depth_ptrs[0][rank], stream)
+    else:
+        krender = lambda fid: capi.render(params(fid), cam, inst, ninst, fb_stats, stream)
     for i in range(3):
-        capi.render(params(1 + i), cam, inst, ninst, fb, stream)
+        krender(1 + i)
     torch.cuda.synchronize()
     k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     kn = max(10, min(args.steps, 50))
     k0.record()
     for i in range(kn):
-        capi.render(params(10 + i), cam, inst, ninst, fb, stream)
+        krender(10 + i)
     k1.record()
     torch.cuda.synchronize()
     kernel_ms = k0.elapsed_time(k1) / kn
@@ -385,17 +402,30 @@ def run_ours(args, torch, dist, rank, world):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         kernel_ms = float(t.item())
 
-    # ---- end-to-end through the public API (ANARI C API of the device library) with host buffers:
-    # every step re-commits a moved camera, renders, waits and maps channel.color to host memory
-    e2e = AnariE2E(args, torch, device, vol, rank, world, mode)
+    # ---- end-to-end with host buffers.  N=1: through the ANARI C API of the device library (what an
+    # application calls).  N>1: the multi-GPU driver (C-ABI) with a moved camera every step and the
+    # display rank mapping the assembled frame to pinned host memory.
+    import ctypes as _C
+    _cudart = _C.CDLL("libcudart.so")
+    if world == 1 and mode == "single":
+        e2e = AnariE2E(args, torch, device, vol, rank, world, mode)
+        e2e_step = e2e.step
+        e2e_what = ("ANARI C API of libanari_library_visrtx_b200.so: anariSetParameter(camera)+anariCommitParameters"
+                    "+anariRenderFrame+anariFrameReady(WAIT)+anariMapFrame(channel.color -> host) per step, wall "
+                    "clock; the volume is an ANARI_NV_ARRAY_CUDA shared array uploaded once")
+    else:
+        e2e = None
 
-    def e2e_step(i):
-        e2e.step(i)
-        exchange_e2e()
+        def e2e_step(i):
+            cam_i, _ = orbit(args, az_deg=30.0 + 0.05 * i)
+            driver.render(0, cam_i, stream)
+            if rank == 0:
+                _cudart.cudaMemcpyAsync(_C.c_void_p(host_color.data_ptr()), _C.c_void_p(driver.color_ptr),
+                                        _C.c_size_t(npx * 4), _C.c_int(2), _C.c_void_p(stream))
+            torch.cuda.synchronize()
 
-    def exchange_e2e():
-        if mode == "sort-first":
-            dist.barrier()
+        e2e_what = (f"{mode} driver over the C-ABI: moved camera (kernel parameter upload) + render on {world} GPUs + "
+                    "assembled colour frame copied to pinned host memory on the display rank every step, wall clock")
 
     for i in range(3):
         e2e_step(i)
@@ -414,15 +444,17 @@ def run_ours(args, torch, dist, rank, world):
         t = torch.tensor([e2e_s], dtype=torch.float64, device=device)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e_s = float(t.item())
-    e2e_bytes = e2e.bytes_per_step()
-    e2e.close()
+    e2e_bytes = e2e.bytes_per_step() if e2e is not None else (2048 * world, npx * 4)
+    if e2e is not None:
+        e2e.close()
     e2e_fps = ne2e / e2e_s
     clocks = sampler.stop() if rank == 0 else None
 
     peak, peak_src = measured_peak()
     bframe = bytes_per_frame(args, cells)
-    share = 1.0 / world if mode == "sort-first" else 1.0
-    achieved = bframe / (kernel_ms * 1e-3) / 1e9  # GB/s (whole volume is swept by every rank in sort-first)
+    share = 1.0 / world
+    # per-GPU achieved bandwidth: every rank reads ~1/N of the touched voxels (its tile rows / its slab)
+    achieved = bframe * share / (kernel_ms * 1e-3) / 1e9
     out = {
         "metric": "DVR frames/s, 1080p, 1024^3 f32 volume (Gsamples/s in extra)",
         "value": fps, "unit": "frames/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
@@ -440,9 +472,7 @@ def run_ours(args, torch, dist, rank, world):
         "gpu_launches": int(launches),
         "e2e": {"value": e2e_fps, "unit": "frames/s", "h2d_bytes_per_step": e2e_bytes[0],
                 "d2h_bytes_per_step": e2e_bytes[1],
-                "what": "ANARI C API of libanari_library_visrtx_b200.so: anariSetParameter(camera)+anariCommitParameters"
-                        "+anariRenderFrame+anariFrameReady(WAIT)+anariMapFrame(channel.color -> host) per step, "
-                        "wall clock; the volume is an ANARI_NV_ARRAY_CUDA shared array uploaded once"},
+                "what": e2e_what},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": None, "peak_source": peak_src, "kernel": "dvrFrameKernel",
                      "kernel_ms": kernel_ms, "algorithmic_bytes": bframe,
@@ -454,15 +484,15 @@ def run_ours(args, torch, dist, rank, world):
     if clocks is not None:
         out["clocks"] = clocks
 
-    if rank == 0 and world == 1 and args.extra:
+    if rank == 0 and world == 1 and mode == "single" and args.extra:
         out["extra"]["variants"] = measure_variants(args, torch, capi, scenes, field, cam, inst, ninst, fb, stream, stats_t)
-    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+    if rank == 0 and world == 1 and vol is not None and not args.no_cpu_baseline:
         try:
             out["cpu_baseline"] = cpu_baseline(args, torch, vol, samples)
         except Exception as e:  # the oracle is optional at bench time
             out["cpu_baseline"] = {"value": None, "unit": "frames/s", "cores": os.cpu_count(), "kind": "port",
                                    "sample": f"unavailable: {e}"}
-    if rank == 0 and world == 1 and args.extra:
+    if rank == 0 and world == 1 and vol is not None and args.extra:
         try:
             out["extra"]["ref_gpu_fps"] = ref_gpu_fps(args, torch, vol, min(args.steps, 30))
         except Exception as e:

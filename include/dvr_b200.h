@@ -143,7 +143,8 @@ typedef struct DvrFrameParams
   uint32_t tileRank, tileRanks; /* 0,1 = everything */
   /* options of the new implementation (all parity-neutral) */
   int32_t useMacrocellSkipping; /* skip fully transparent macrocells on the same sample lattice */
-  int32_t _reserved[3];
+  int32_t tileBand;             /* sort-first: consecutive tile rows per band owned by one rank (0/1 = finest) */
+  int32_t _reserved[2];
 } DvrFrameParams;
 
 /* per-launch counters, filled only by dvr_render_instrumented (device memory, 64-bit each) */
@@ -198,10 +199,16 @@ int dvr_field_create_structured(const void *data, int dataIsDevice, int dataType
     int filter /*DvrFilter*/, void *stream, DvrField **out);
 /* Same, but only z-slices [zBegin, zEnd) (+ ghost layers clamped to the volume) of a global
  * dims[] volume are resident: the sort-last slab of SURVEY 8e.  data points at the first
- * RESIDENT slice (ghost included): slice index max(zBegin-1,0). */
+ * RESIDENT slice (ghost included): slice index max(zBegin-1,0).  data == NULL allocates only (see
+ * dvr_field_upload_slices). */
 int dvr_field_create_structured_slab(const void *data, int dataIsDevice, int dataType,
     const uint32_t globalDims[3], uint32_t zBegin, uint32_t zEnd, const float origin[3],
     const float spacing[3], int filter, void *stream, DvrField **out);
+/* Chunked fill of a slab field created with data == NULL (volumes too large to stage twice in HBM):
+ * copies nSlices z-slices into resident slices [firstResidentSlice, +nSlices); element type = the
+ * field's.  Call dvr_field_build_macrocells once all slices are in. */
+int dvr_field_upload_slices(DvrField *f, const void *data, int dataIsDevice, uint32_t firstResidentSlice,
+    uint32_t nSlices, void *stream);
 int dvr_field_destroy(DvrField *f);
 /* SpatialField::bounds / stepSize, StructuredRegularField.cpp:166-178 */
 int dvr_field_bounds(const DvrField *f, float lower[3], float upper[3]);
@@ -263,6 +270,10 @@ unsigned long long dvr_launch_count(void);
  * numIterations==1 and a single volume instance. */
 int dvr_render_partial(const DvrFrameParams *params, const DvrCamera *camera,
     const DvrVolumeInstance *instance, float *partialRgba, float *partialDepth, void *stream);
+/* same launch with counters (samplesTaken/Skipped, macrocellsTouched of this slab); never timed */
+int dvr_render_partial_instrumented(const DvrFrameParams *params, const DvrCamera *camera,
+    const DvrVolumeInstance *instance, float *partialRgba, float *partialDepth, DvrRenderStats *statsDev,
+    void *stream);
 /* front-to-back `over` of two partial images for pixels [pixelBegin,pixelEnd):
  * front = front over back (in place on front); depth = min.  Pointers may be peer-mapped. */
 int dvr_composite_over(float *frontRgba, float *frontDepth, const float *backRgba,
@@ -282,6 +293,39 @@ int dvr_resolve(const DvrFrameParams *params, const float *partialRgba, const fl
 int dvr_composite_resolve_peers(const DvrFrameParams *params, const DvrCamera *camera,
     const float *const *partialRgba, const float *const *partialDepth, uint32_t nSlabs, uint32_t objId,
     uint32_t instId, const DvrFrameBuffers *buffers, size_t pixelBegin, size_t pixelEnd, void *stream);
+
+/* Device-side cross-GPU ordering without host or NCCL involvement.  A flag is a 32-bit word in
+ * (CUDA-IPC shared) device memory holding the number of the last frame its producer completed.
+ *   signal[i]  : words written with `value` when the launch has finished all its work (system-scope
+ *                release by the last retiring warp / block) — typically one word in every peer's flag table
+ *   wait       : local flag table; the launch does not touch peer data before wait[i] >= waitValue for all
+ *                i < nWait (bounded spin, ~2 s, then the launch gives up and sets *errorFlag if non-NULL)
+ * Used by the *_sync variants below and dvr_wait_flags. */
+typedef struct DvrPeerSync
+{
+  uint32_t nSignal;
+  uint32_t signalValue;
+  unsigned int *signal[16];
+  uint32_t nWait;
+  uint32_t waitValue;
+  const unsigned int *wait;
+  unsigned int *errorFlag;
+} DvrPeerSync;
+
+/* dvr_render_partial + signal when the partial image is complete */
+int dvr_render_partial_sync(const DvrFrameParams *params, const DvrCamera *camera,
+    const DvrVolumeInstance *instance, float *partialRgba, float *partialDepth, const DvrPeerSync *sync,
+    void *stream);
+/* dvr_composite_resolve_peers that (a) waits for every slab's "partial complete" flag inside the kernel,
+ * (b) skips the peer loads of pixels whose primary ray (regenerated with the same Philox stream as the
+ * partial march) misses the volume's bounds, (c) signals "strip resolved" at the end.  instance = the
+ * volume instance whose slabs are being composited (bounds + transform for (b)). */
+int dvr_composite_resolve_peers_sync(const DvrFrameParams *params, const DvrCamera *camera,
+    const DvrVolumeInstance *instance, const float *const *partialRgba, const float *const *partialDepth,
+    uint32_t nSlabs, uint32_t objId, uint32_t instId, const DvrFrameBuffers *buffers, size_t pixelBegin,
+    size_t pixelEnd, const DvrPeerSync *sync, void *stream);
+/* one-thread kernel: returns (in stream order) once flags[i] >= value for all i < n (bounded spin) */
+int dvr_wait_flags(const unsigned int *flags, uint32_t n, uint32_t value, unsigned int *errorFlag, void *stream);
 
 /* ---- CUDA IPC plumbing for one-process-per-GPU sharing of frame / partial buffers ------------- */
 #define DVR_IPC_HANDLE_BYTES 64

@@ -28,13 +28,14 @@ DVR_INTEGRATOR_RAYCAST, DVR_INTEGRATOR_DEFAULT = 0, 1
 EXPORTED_SYMBOLS = [
     "dvr_last_error", "dvr_version", "dvr_device_count", "dvr_set_device", "dvr_device_info",
     "dvr_camera_perspective", "dvr_camera_orthographic", "dvr_tf_discretize",
-    "dvr_field_create_structured", "dvr_field_create_structured_slab", "dvr_field_destroy",
+    "dvr_field_create_structured", "dvr_field_create_structured_slab", "dvr_field_upload_slices", "dvr_field_destroy",
     "dvr_field_bounds", "dvr_field_step_size", "dvr_field_device_bytes", "dvr_field_build_macrocells",
     "dvr_field_macrocells", "dvr_field_value_range",
     "dvr_volume_create", "dvr_volume_update", "dvr_volume_destroy", "dvr_volume_majorants",
     "dvr_render", "dvr_render_instrumented", "dvr_launch_count",
-    "dvr_render_partial", "dvr_composite_over", "dvr_resolve", "dvr_scale_vec3",
-    "dvr_composite_resolve_peers", "dvr_ipc_alloc", "dvr_ipc_open", "dvr_ipc_close", "dvr_ipc_free",
+    "dvr_render_partial", "dvr_render_partial_instrumented", "dvr_composite_over", "dvr_resolve", "dvr_scale_vec3",
+    "dvr_composite_resolve_peers", "dvr_render_partial_sync", "dvr_composite_resolve_peers_sync", "dvr_wait_flags",
+    "dvr_ipc_alloc", "dvr_ipc_open", "dvr_ipc_close", "dvr_ipc_free",
 ]
 
 
@@ -66,12 +67,27 @@ class DvrFrameParams(C.Structure):
                 ("frameID", C.c_int32), ("checkerboardID", C.c_int32), ("numIterations", C.c_int32),
                 ("inverseVolumeSamplingRate", C.c_float), ("background", C.c_float * 4),
                 ("tileRank", C.c_uint32), ("tileRanks", C.c_uint32), ("useMacrocellSkipping", C.c_int32),
-                ("_reserved", C.c_int32 * 3)]
+                ("tileBand", C.c_int32), ("_reserved", C.c_int32 * 2)]
 
 
 class DvrRenderStats(C.Structure):
     _fields_ = [("samplesTaken", C.c_ulonglong), ("samplesSkipped", C.c_ulonglong), ("raysHit", C.c_ulonglong),
                 ("macrocellsTouched", C.c_ulonglong)]
+
+
+class DvrPeerSync(C.Structure):
+    _fields_ = [("nSignal", C.c_uint32), ("signalValue", C.c_uint32), ("signal", C.c_void_p * 16),
+                ("nWait", C.c_uint32), ("waitValue", C.c_uint32), ("wait", C.c_void_p), ("errorFlag", C.c_void_p)]
+
+
+def peer_sync(signal_ptrs=(), signal_value=0, wait_ptr=0, n_wait=0, wait_value=0, error_flag=0) -> "DvrPeerSync":
+    s = DvrPeerSync()
+    s.nSignal, s.signalValue = len(signal_ptrs), int(signal_value) & 0xFFFFFFFF
+    for i, p in enumerate(signal_ptrs):
+        s.signal[i] = p
+    s.nWait, s.waitValue, s.wait = int(n_wait), int(wait_value) & 0xFFFFFFFF, wait_ptr or None
+    s.errorFlag = error_flag or None
+    return s
 
 
 IDENTITY_3X4 = (1.0, 0.0, 0.0, 0.0, 0.0, 1.0, 0.0, 0.0, 0.0, 0.0, 1.0, 0.0)
@@ -194,6 +210,11 @@ class Field:
                                                     C.c_int(filter_mode), C.c_void_p(stream), C.byref(h)))
         return Field(h)
 
+    def upload_slices(self, data_ptr: int, is_device: bool, first_resident_slice: int, n_slices: int,
+                      stream: int = 0) -> None:
+        _check(lib.dvr_field_upload_slices(self.handle, C.c_void_p(data_ptr), C.c_int(1 if is_device else 0),
+                                           C.c_uint32(first_resident_slice), C.c_uint32(n_slices), C.c_void_p(stream)))
+
     def destroy(self) -> None:
         if self.handle:
             lib.dvr_field_destroy(self.handle)
@@ -276,7 +297,7 @@ def make_instances(volumes: Sequence[Volume], xfms=None, inst_ids=None):
 
 def frame_params(width, height, fmt=DVR_FORMAT_UFIXED8_RGBA_SRGB, integrator=DVR_INTEGRATOR_RAYCAST, frame_id=0,
                  checkerboard_id=-1, num_iterations=1, volume_sampling_rate=0.125, background=(0.0, 0.0, 0.0, 1.0),
-                 tile_rank=0, tile_ranks=1, skip=False) -> DvrFrameParams:
+                 tile_rank=0, tile_ranks=1, skip=False, tile_band=1) -> DvrFrameParams:
     p = DvrFrameParams()
     p.width, p.height, p.format, p.integrator = int(width), int(height), int(fmt), int(integrator)
     p.frameID, p.checkerboardID, p.numIterations = int(frame_id), int(checkerboard_id), int(num_iterations)
@@ -285,6 +306,7 @@ def frame_params(width, height, fmt=DVR_FORMAT_UFIXED8_RGBA_SRGB, integrator=DVR
     p.background = _f4(*background)
     p.tileRank, p.tileRanks = int(tile_rank), int(tile_ranks)
     p.useMacrocellSkipping = 1 if skip else 0
+    p.tileBand = int(tile_band)
     return p
 
 
@@ -311,6 +333,13 @@ def render_instrumented(params, camera, instances, n_instances, buffers, stats_d
 def render_partial(params, camera, instance, partial_rgba: int, partial_depth: int, stream: int = 0):
     _check(lib.dvr_render_partial(C.byref(params), C.byref(camera), instance, C.c_void_p(partial_rgba),
                                   C.c_void_p(partial_depth), C.c_void_p(stream)))
+
+
+def render_partial_instrumented(params, camera, instance, partial_rgba: int, partial_depth: int, stats_dev_ptr: int,
+                                stream: int = 0):
+    _check(lib.dvr_render_partial_instrumented(C.byref(params), C.byref(camera), instance, C.c_void_p(partial_rgba),
+                                               C.c_void_p(partial_depth), C.c_void_p(stats_dev_ptr),
+                                               C.c_void_p(stream)))
 
 
 def composite_over(front_rgba: int, front_depth: int, back_rgba: int, back_depth: int, begin: int, end: int,
@@ -363,3 +392,24 @@ def ipc_close(ptr: int) -> None:
 
 def ipc_free(ptr: int) -> None:
     _check(lib.dvr_ipc_free(C.c_void_p(ptr)))
+
+
+def render_partial_sync(params, camera, instance, partial_rgba: int, partial_depth: int, sync: DvrPeerSync,
+                        stream: int = 0):
+    _check(lib.dvr_render_partial_sync(C.byref(params), C.byref(camera), instance, C.c_void_p(partial_rgba),
+                                       C.c_void_p(partial_depth), C.byref(sync), C.c_void_p(stream)))
+
+
+def composite_resolve_peers_sync(params, camera, instance, partial_rgba_ptrs, partial_depth_ptrs, obj_id: int,
+                                 inst_id: int, buffers, begin: int, end: int, sync: DvrPeerSync, stream: int = 0):
+    n = len(partial_rgba_ptrs)
+    rg = (C.c_void_p * n)(*partial_rgba_ptrs)
+    dp = (C.c_void_p * n)(*partial_depth_ptrs) if partial_depth_ptrs else None
+    _check(lib.dvr_composite_resolve_peers_sync(C.byref(params), C.byref(camera), instance, rg, dp, C.c_uint32(n),
+                                                C.c_uint32(obj_id), C.c_uint32(inst_id), C.byref(buffers),
+                                                C.c_size_t(begin), C.c_size_t(end), C.byref(sync), C.c_void_p(stream)))
+
+
+def wait_flags(flags_ptr: int, n: int, value: int, error_flag: int = 0, stream: int = 0):
+    _check(lib.dvr_wait_flags(C.c_void_p(flags_ptr), C.c_uint32(n), C.c_uint32(int(value) & 0xFFFFFFFF),
+                              C.c_void_p(error_flag or None), C.c_void_p(stream)))

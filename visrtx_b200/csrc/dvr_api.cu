@@ -90,6 +90,7 @@ struct DvrField
   float2 *ranges = nullptr;
   size_t nCells = 0;
   size_t voxelBytes = 0;
+  size_t texElementSize = 0;
   int device = 0;
 };
 
@@ -336,9 +337,14 @@ static int createFieldImpl(const void *data, int dataIsDevice, int dataType, con
     uint32_t zBegin, uint32_t zEnd, const float origin[3], const float spacing[3], int filter, void *stream,
     DvrField **out)
 {
-  if (!data || !gdims || !origin || !spacing || !out) {
+  if (!gdims || !origin || !spacing || !out) {
     setError("dvr_field_create: null argument");
     return DVR_ERR_INVALID_ARGUMENT;
+  }
+  const bool deferredUpload = data == nullptr; // slab API only: slices arrive through dvr_field_upload_slices
+  if (deferredUpload && dataType == DVR_FLOAT64) {
+    setError("dvr_field_create: deferred upload does not support FLOAT64");
+    return DVR_ERR_UNSUPPORTED;
   }
   const size_t esz = elementSize(dataType);
   if (esz == 0) {
@@ -405,15 +411,18 @@ static int createFieldImpl(const void *data, int dataIsDevice, int dataType, con
     delete f;
     return cudaFail(e, "cudaMalloc3DArray");
   }
-  cudaMemcpy3DParms cp;
-  std::memset(&cp, 0, sizeof(cp));
-  cp.srcPtr = make_cudaPitchedPtr(const_cast<void *>(src), gdims[0] * texEsz, gdims[0], gdims[1]);
-  cp.dstArray = f->array;
-  cp.extent = make_cudaExtent(gdims[0], gdims[1], texDepth);
-  cp.kind = dataIsDevice ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
-  e = cudaMemcpy3DAsync(&cp, s);
-  if (e == cudaSuccess && (!dataIsDevice || converted))
-    e = cudaStreamSynchronize(s); // the caller's host buffer / our temporary may go away
+  f->texElementSize = texEsz;
+  if (!deferredUpload) {
+    cudaMemcpy3DParms cp;
+    std::memset(&cp, 0, sizeof(cp));
+    cp.srcPtr = make_cudaPitchedPtr(const_cast<void *>(src), gdims[0] * texEsz, gdims[0], gdims[1]);
+    cp.dstArray = f->array;
+    cp.extent = make_cudaExtent(gdims[0], gdims[1], texDepth);
+    cp.kind = dataIsDevice ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
+    e = cudaMemcpy3DAsync(&cp, s);
+    if (e == cudaSuccess && (!dataIsDevice || converted))
+      e = cudaStreamSynchronize(s); // the caller's host buffer / our temporary may go away
+  }
   cudaFree(converted);
   if (e != cudaSuccess) {
     cudaFreeArray(f->array);
@@ -468,7 +477,7 @@ static int createFieldImpl(const void *data, int dataIsDevice, int dataType, con
     return cudaFail(e, "cudaMalloc(macrocell ranges)");
   }
   d.valueRanges = f->ranges;
-  const int rc = dvr_field_build_macrocells(f, stream);
+  const int rc = deferredUpload ? DVR_OK : dvr_field_build_macrocells(f, stream);
   if (rc != DVR_OK) {
     dvr_field_destroy(f);
     return rc;
@@ -480,8 +489,8 @@ static int createFieldImpl(const void *data, int dataIsDevice, int dataType, con
 int dvr_field_create_structured(const void *data, int dataIsDevice, int dataType, const uint32_t dims[3],
     const float origin[3], const float spacing[3], int filter, void *stream, DvrField **out)
 {
-  if (!dims) {
-    setError("dvr_field_create_structured: null dims");
+  if (!dims || !data) {
+    setError("dvr_field_create_structured: null data / dims");
     return DVR_ERR_INVALID_ARGUMENT;
   }
   return createFieldImpl(data, dataIsDevice, dataType, dims, 0, dims[2], origin, spacing, filter, stream, out);
@@ -496,6 +505,27 @@ int dvr_field_create_structured_slab(const void *data, int dataIsDevice, int dat
     return DVR_ERR_INVALID_ARGUMENT;
   }
   return createFieldImpl(data, dataIsDevice, dataType, globalDims, zBegin, zEnd, origin, spacing, filter, stream, out);
+}
+
+int dvr_field_upload_slices(DvrField *f, const void *data, int dataIsDevice, uint32_t firstResidentSlice,
+    uint32_t nSlices, void *stream)
+{
+  if (!f || !data || nSlices == 0 || firstResidentSlice + nSlices > (uint32_t)f->dev.texDepth) {
+    setError("dvr_field_upload_slices: bad argument / slice range");
+    return DVR_ERR_INVALID_ARGUMENT;
+  }
+  cudaStream_t s = (cudaStream_t)stream;
+  cudaMemcpy3DParms cp;
+  std::memset(&cp, 0, sizeof(cp));
+  cp.srcPtr = make_cudaPitchedPtr(const_cast<void *>(data), f->dev.dims.x * f->texElementSize, f->dev.dims.x, f->dev.dims.y);
+  cp.dstArray = f->array;
+  cp.dstPos = make_cudaPos(0, 0, firstResidentSlice);
+  cp.extent = make_cudaExtent(f->dev.dims.x, f->dev.dims.y, nSlices);
+  cp.kind = dataIsDevice ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
+  DVR_CUDA(cudaMemcpy3DAsync(&cp, s));
+  if (!dataIsDevice)
+    DVR_CUDA(cudaStreamSynchronize(s));
+  return DVR_OK;
 }
 
 int dvr_field_destroy(DvrField *f)
@@ -727,6 +757,7 @@ static int renderImpl(const DvrFrameParams *p, const DvrCamera *camera, const Dv
   L.background = make_float4(p->background[0], p->background[1], p->background[2], p->background[3]);
   L.tileRank = p->tileRanks > 1 ? p->tileRank : 0;
   L.tileRanks = p->tileRanks > 1 ? p->tileRanks : 1;
+  L.tileBand = p->tileBand > 1 ? (uint32_t)p->tileBand : 1u;
   L.launchW = p->checkerboardID >= 0 ? (p->width + 1) / 2 : p->width; // Frame.cu:287-288
   L.launchH = p->checkerboardID >= 0 ? (p->height + 1) / 2 : p->height;
   L.tilesX = (L.launchW + kTileW - 1) / kTileW;
@@ -814,8 +845,33 @@ int dvr_render_instrumented(const DvrFrameParams *params, const DvrCamera *camer
 
 // ---- sort-last -------------------------------------------------------------------------------------------
 
-int dvr_render_partial(const DvrFrameParams *p, const DvrCamera *camera, const DvrVolumeInstance *instance,
-    float *partialRgba, float *partialDepth, void *stream)
+static int fillSync(const DvrPeerSync *in, SyncDev &out)
+{
+  std::memset(&out, 0, sizeof(out));
+  if (!in)
+    return DVR_OK;
+  if (in->nSignal > (uint32_t)kMaxSlabs || in->nWait > (uint32_t)kMaxSlabs || (in->nWait && !in->wait)) {
+    setError("DvrPeerSync: at most 16 signal/wait flags; wait table must not be null");
+    return DVR_ERR_INVALID_ARGUMENT;
+  }
+  out.nSignal = in->nSignal;
+  out.signalValue = in->signalValue;
+  for (uint32_t i = 0; i < in->nSignal; ++i) {
+    if (!in->signal[i]) {
+      setError("DvrPeerSync: null signal flag");
+      return DVR_ERR_INVALID_ARGUMENT;
+    }
+    out.signal[i] = in->signal[i];
+  }
+  out.nWait = in->nWait;
+  out.waitValue = in->waitValue;
+  out.wait = in->wait;
+  out.errorFlag = in->errorFlag;
+  return DVR_OK;
+}
+
+static int renderPartialImpl(const DvrFrameParams *p, const DvrCamera *camera, const DvrVolumeInstance *instance,
+    float *partialRgba, float *partialDepth, DvrRenderStats *statsDev, void *stream, const DvrPeerSync *sync = nullptr)
 {
   if (!p || !camera || !instance || !instance->volume || !partialRgba || !partialDepth) {
     setError("dvr_render_partial: null argument");
@@ -829,6 +885,7 @@ int dvr_render_partial(const DvrFrameParams *p, const DvrCamera *camera, const D
     setError("dvr_render_partial: no CUDA device (this library has no CPU fallback)");
     return DVR_ERR_NO_DEVICE;
   }
+  cudaStream_t s = (cudaStream_t)stream;
   PartialLaunch L;
   std::memset(&L, 0, sizeof(L));
   L.width = p->width;
@@ -845,12 +902,64 @@ int dvr_render_partial(const DvrFrameParams *p, const DvrCamera *camera, const D
   L.partialRgba = (float4 *)partialRgba;
   L.partialDepth = partialDepth;
   L.skip = p->useMacrocellSkipping;
+  {
+    const int rcs = fillSync(sync, L.sync);
+    if (rcs != DVR_OK)
+      return rcs;
+  }
   L.sched = acquireSchedSlot();
   if (!L.sched) {
     setError("dvr_render_partial: could not allocate scheduler scratch");
     return DVR_ERR_CUDA;
   }
-  return launchPartial(L, (cudaStream_t)stream);
+  unsigned int *bitmap = nullptr;
+  size_t nWords = 0;
+  if (statsDev) {
+    DVR_CUDA(cudaMemsetAsync(statsDev, 0, sizeof(DvrRenderStats), s));
+    nWords = (instance->volume->field->nCells + 31) / 32;
+    DVR_CUDA(cudaMallocAsync(&bitmap, nWords * 4, s));
+    DVR_CUDA(cudaMemsetAsync(bitmap, 0, nWords * 4, s));
+    L.stats = statsDev;
+    L.cellBitmap = bitmap;
+  }
+  int rc = launchPartial(L, s);
+  if (bitmap) {
+    if (rc == DVR_OK)
+      rc = launchPopcount(bitmap, nWords, &statsDev->macrocellsTouched, s);
+    cudaFreeAsync(bitmap, s);
+  }
+  return rc;
+}
+
+int dvr_render_partial(const DvrFrameParams *p, const DvrCamera *camera, const DvrVolumeInstance *instance,
+    float *partialRgba, float *partialDepth, void *stream)
+{
+  return renderPartialImpl(p, camera, instance, partialRgba, partialDepth, nullptr, stream);
+}
+
+int dvr_render_partial_sync(const DvrFrameParams *p, const DvrCamera *camera, const DvrVolumeInstance *instance,
+    float *partialRgba, float *partialDepth, const DvrPeerSync *sync, void *stream)
+{
+  return renderPartialImpl(p, camera, instance, partialRgba, partialDepth, nullptr, stream, sync);
+}
+
+int dvr_wait_flags(const unsigned int *flags, uint32_t n, uint32_t value, unsigned int *errorFlag, void *stream)
+{
+  if (!flags || n == 0) {
+    setError("dvr_wait_flags: null argument");
+    return DVR_ERR_INVALID_ARGUMENT;
+  }
+  return launchWaitFlags(flags, n, value, errorFlag, (cudaStream_t)stream);
+}
+
+int dvr_render_partial_instrumented(const DvrFrameParams *p, const DvrCamera *camera,
+    const DvrVolumeInstance *instance, float *partialRgba, float *partialDepth, DvrRenderStats *statsDev, void *stream)
+{
+  if (!statsDev) {
+    setError("dvr_render_partial_instrumented: statsDev is null");
+    return DVR_ERR_INVALID_ARGUMENT;
+  }
+  return renderPartialImpl(p, camera, instance, partialRgba, partialDepth, statsDev, stream);
 }
 
 int dvr_composite_over(float *frontRgba, float *frontDepth, const float *backRgba, const float *backDepth,
@@ -896,9 +1005,10 @@ int dvr_resolve(const DvrFrameParams *p, const float *partialRgba, const float *
   return launchResolve(R, (cudaStream_t)stream);
 }
 
-int dvr_composite_resolve_peers(const DvrFrameParams *p, const DvrCamera *camera, const float *const *partialRgba,
-    const float *const *partialDepth, uint32_t nSlabs, uint32_t objId, uint32_t instId, const DvrFrameBuffers *b,
-    size_t pixelBegin, size_t pixelEnd, void *stream)
+static int compositeResolveImpl(const DvrFrameParams *p, const DvrCamera *camera, const DvrVolumeInstance *instance,
+    const float *const *partialRgba, const float *const *partialDepth, uint32_t nSlabs, uint32_t objId,
+    uint32_t instId, const DvrFrameBuffers *b, size_t pixelBegin, size_t pixelEnd, const DvrPeerSync *sync,
+    void *stream)
 {
   if (!p || !camera || !partialRgba || !b || !b->colorAccumulation || !b->outColor || nSlabs == 0) {
     setError("dvr_composite_resolve_peers: null argument");
@@ -941,7 +1051,38 @@ int dvr_composite_resolve_peers(const DvrFrameParams *p, const DvrCamera *camera
     L.rgba[i] = (const float4 *)partialRgba[i];
     L.depth[i] = partialDepth ? partialDepth[i] : nullptr;
   }
+  L.integrator = p->integrator;
+  L.identity = 1u;
+  if (instance && instance->volume && instance->volume->field) {
+    InstanceDev tmp;
+    fillInstance(*instance, tmp);
+    L.cull = 1;
+    L.boundsLo = tmp.v.f.boundsLo;
+    L.boundsHi = tmp.v.f.boundsHi;
+    std::memcpy(L.xfm, tmp.xfm, sizeof(L.xfm));
+    L.identity = tmp.identity;
+  }
+  const int rcs = fillSync(sync, L.sync);
+  if (rcs != DVR_OK)
+    return rcs;
   return launchPeerResolve(L, (cudaStream_t)stream);
+}
+
+int dvr_composite_resolve_peers(const DvrFrameParams *p, const DvrCamera *camera, const float *const *partialRgba,
+    const float *const *partialDepth, uint32_t nSlabs, uint32_t objId, uint32_t instId, const DvrFrameBuffers *b,
+    size_t pixelBegin, size_t pixelEnd, void *stream)
+{
+  return compositeResolveImpl(p, camera, nullptr, partialRgba, partialDepth, nSlabs, objId, instId, b, pixelBegin,
+      pixelEnd, nullptr, stream);
+}
+
+int dvr_composite_resolve_peers_sync(const DvrFrameParams *p, const DvrCamera *camera,
+    const DvrVolumeInstance *instance, const float *const *partialRgba, const float *const *partialDepth,
+    uint32_t nSlabs, uint32_t objId, uint32_t instId, const DvrFrameBuffers *b, size_t pixelBegin, size_t pixelEnd,
+    const DvrPeerSync *sync, void *stream)
+{
+  return compositeResolveImpl(p, camera, instance, partialRgba, partialDepth, nSlabs, objId, instId, b, pixelBegin,
+      pixelEnd, sync, stream);
 }
 
 int dvr_ipc_alloc(size_t bytes, void **devPtr, unsigned char handle[DVR_IPC_HANDLE_BYTES])

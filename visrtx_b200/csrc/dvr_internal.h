@@ -17,6 +17,18 @@ constexpr int kMaxInlineInstances = 4;
 constexpr int kTileW = DVR_TILE_W;
 constexpr int kTileH = 32 / DVR_TILE_W;
 constexpr int kBlockThreads = 256;
+constexpr int kMaxSlabs = 16;
+
+// cross-GPU flags of one launch (DvrPeerSync of the C-ABI)
+struct SyncDev
+{
+  uint32_t nSignal, signalValue;
+  unsigned int *signal[kMaxSlabs];
+  uint32_t nWait, waitValue;
+  const unsigned int *wait;
+  unsigned int *errorFlag;
+};
+
 
 // kernel parameter block of the frame kernel (passed by value as __grid_constant__)
 struct FrameLaunch
@@ -26,7 +38,7 @@ struct FrameLaunch
   int format, integrator, frameID, checkerboardID, numIterations;
   float invSamplingRate;
   float4 background;
-  uint32_t tileRank, tileRanks;
+  uint32_t tileRank, tileRanks, tileBand;
   uint32_t launchW, launchH; // pixel-sample grid actually launched (half size when checkerboarding)
   uint32_t tilesX, tilesY;
   CameraDev cam;
@@ -52,6 +64,9 @@ struct PartialLaunch
   float *partialDepth;
   unsigned int *sched;
   int skip;
+  DvrRenderStats *stats;    // instrumented variant only
+  unsigned int *cellBitmap; // instrumented variant only
+  SyncDev sync;             // sync variant: signal peers when the partial image is complete
 };
 
 struct ResolveLaunch
@@ -66,7 +81,6 @@ struct ResolveLaunch
   size_t pixelBegin, pixelEnd;
 };
 
-constexpr int kMaxSlabs = 16;
 struct PeerResolveLaunch
 {
   ResolveLaunch r;
@@ -75,6 +89,13 @@ struct PeerResolveLaunch
   int nSlabs;
   const float4 *rgba[kMaxSlabs];
   const float *depth[kMaxSlabs];
+  // sync variant
+  SyncDev sync;
+  int cull;                   // regenerate the primary ray and skip peer loads when it misses the bounds
+  int integrator;
+  float3 boundsLo, boundsHi;
+  float xfm[12];
+  uint32_t identity;
 };
 
 // error plumbing -----------------------------------------------------------------------------
@@ -98,6 +119,8 @@ int launchResolve(const ResolveLaunch &p, cudaStream_t s);
 int launchCompositeOver(float4 *front, float *frontDepth, const float4 *back, const float *backDepth,
     size_t begin, size_t end, bool backIsInFront, cudaStream_t s);
 int launchPeerResolve(const PeerResolveLaunch &p, cudaStream_t s);
+int launchSignalFlags(const SyncDev &sy, cudaStream_t s);
+int launchWaitFlags(const unsigned int *flags, uint32_t n, uint32_t value, unsigned int *errorFlag, cudaStream_t s);
 int launchScaleVec3(const float *in, float *out, size_t n, float scale, cudaStream_t s);
 int launchMacrocellBuild(cudaTextureObject_t pointTex, int3 dims, int zTexBegin, int texDepth, int3 gridDims,
     float2 *ranges, cudaStream_t s);

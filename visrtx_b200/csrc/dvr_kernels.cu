@@ -32,6 +32,73 @@ __device__ __forceinline__ void retireWarp(unsigned int *sched, int lane)
   }
 }
 
+// ---- cross-GPU flags (DvrPeerSync) ----------------------------------------------------------
+__device__ __forceinline__ void signalPeers(const SyncDev &sy)
+{
+  __threadfence_system(); // everything this GPU wrote for the frame is visible system-wide first
+  for (uint32_t i = 0; i < sy.nSignal; ++i)
+    *((volatile unsigned int *)sy.signal[i]) = sy.signalValue;
+  __threadfence_system();
+}
+
+// bounded spin (about 2 s at 1.9 GHz): a missing producer must not hang the GPU
+__device__ __forceinline__ bool waitFlags(const unsigned int *flags, uint32_t n, uint32_t value, unsigned int *err)
+{
+  const long long t0 = clock64();
+  for (uint32_t i = 0; i < n; ++i) {
+    while ((int)(*((volatile const unsigned int *)&flags[i]) - value) < 0) {
+      __nanosleep(200);
+      if (clock64() - t0 > 4000000000ll) {
+        if (err)
+          *err = 1u;
+        return false;
+      }
+    }
+  }
+  __threadfence_system();
+  return true;
+}
+
+// retireWarp + signal from the last warp of the grid
+__device__ __forceinline__ void retireWarpAndSignal(unsigned int *sched, int lane, const SyncDev &sy)
+{
+  if (lane == 0) {
+    const unsigned int totalWarps = gridDim.x * (blockDim.x >> 5);
+    __threadfence();
+    const unsigned int done = atomicAdd(&sched[1], 1u);
+    if (done == totalWarps - 1u) {
+      sched[0] = 0u;
+      sched[1] = 0u;
+      __threadfence();
+      if (sy.nSignal)
+        signalPeers(sy);
+    }
+  }
+}
+
+__global__ void dvrSignalFlagsKernel(const __grid_constant__ SyncDev sy) { signalPeers(sy); }
+
+int launchSignalFlags(const SyncDev &sy, cudaStream_t s)
+{
+  dvrSignalFlagsKernel<<<1, 1, 0, s>>>(sy);
+  DVR_CUDA(cudaGetLastError());
+  countLaunch();
+  return DVR_OK;
+}
+
+__global__ void dvrWaitFlagsKernel(const unsigned int *flags, uint32_t n, uint32_t value, unsigned int *err)
+{
+  waitFlags(flags, n, value, err);
+}
+
+int launchWaitFlags(const unsigned int *flags, uint32_t n, uint32_t value, unsigned int *errorFlag, cudaStream_t s)
+{
+  dvrWaitFlagsKernel<<<1, 1, 0, s>>>(flags, n, value, errorFlag);
+  DVR_CUDA(cudaGetLastError());
+  countLaunch();
+  return DVR_OK;
+}
+
 __device__ __forceinline__ unsigned long long warpSum(unsigned long long v)
 {
 #pragma unroll
@@ -42,7 +109,14 @@ __device__ __forceinline__ unsigned long long warpSum(unsigned long long v)
 
 // accumResults, gpu/gpu_util.h:393-443, for one pixel-sample.  `init` replaces the cleared
 // buffers of Frame::newFrame (Frame.cu:609-647): 0 + x and min(FLT_MAX, x) are written directly.
-__device__ __forceinline__ void accumResults(const FrameLaunch &P, uint32_t px, uint32_t py, float4 color,
+struct AccumCtx
+{
+  uint32_t width, height;
+  int format, frameID, checkerboardID;
+  BuffersDev fb;
+};
+
+__device__ __forceinline__ void accumResults(const AccumCtx &P, uint32_t px, uint32_t py, float4 color,
     float depth, float3 albedo, float3 normal, uint32_t primID, uint32_t objID, uint32_t instID,
     int frameIDOffset, bool init)
 {
@@ -171,10 +245,11 @@ __global__ void __launch_bounds__(kBlockThreads, DVR_OCC) dvrFrameKernel(const _
   const uint32_t nTiles = P.tilesX * P.tilesY;
   const bool centered = P.integrator == DVR_INTEGRATOR_RAYCAST;
   const bool initFrame = P.frameID == 0 && P.checkerboardID <= 0;
+  const AccumCtx actx{P.width, P.height, P.format, P.frameID, P.checkerboardID, P.fb};
 
   for (uint32_t tile = nextTile(P.sched, lane); tile < nTiles; tile = nextTile(P.sched, lane)) {
     const uint32_t tyIdx = tile / P.tilesX, txIdx = tile - tyIdx * P.tilesX;
-    if (P.tileRanks > 1u && (tyIdx % P.tileRanks) != P.tileRank)
+    if (P.tileRanks > 1u && ((tyIdx / P.tileBand) % P.tileRanks) != P.tileRank)
       continue;
     const uint32_t lx = txIdx * kTileW + (lane % kTileW), ly = tyIdx * kTileH + (lane / kTileW);
     if (lx >= P.launchW || ly >= P.launchH)
@@ -222,7 +297,7 @@ __global__ void __launch_bounds__(kBlockThreads, DVR_OCC) dvrFrameKernel(const _
       color.z = __fmaf_rn(bg.z, oneMinus, color.z);
       opacity = __fmaf_rn(bg.w, oneMinus, opacity);
       // outputColor/outputOpacity start at 0: accumulateValue(out, c, 0) == c
-      accumResults(P, px, py, make_float4(color.x, color.y, color.z, opacity), depth, color, dir, 0u, objID,
+      accumResults(actx, px, py, make_float4(color.x, color.y, color.z, opacity), depth, color, dir, 0u, objID,
           instID, it, initFrame && it == 0);
     }
   }
@@ -278,7 +353,7 @@ int launchFrame(const FrameLaunch &p, bool skip, bool stats, cudaStream_t s)
 // ----------------------------------------------------------------------------------------------
 // sort-last partial render: premultiplied (C,A) + entry depth of ONE slab on the global lattice
 // ----------------------------------------------------------------------------------------------
-template <bool SKIP>
+template <bool SKIP, bool STATS>
 __global__ void __launch_bounds__(kBlockThreads, 2) dvrPartialKernel(const __grid_constant__ PartialLaunch P)
 {
   __shared__ float4 s_tf[DVR_TF_SIZE];
@@ -306,41 +381,49 @@ __global__ void __launch_bounds__(kBlockThreads, 2) dvrPartialKernel(const __gri
     float opacity = 0.f;
     uint32_t objID = ~0u, instID = ~0u;
     bool anyHit = false;
-    const float depth = rayMarchAllVolumes<SKIP, true, false, true>(&P.inst, 1, TfSelectSingle{s_tf}, org, dir, FLT_MAX,
-        P.invSamplingRate, rng, color, opacity, objID, instID, st, nullptr, anyHit);
+    const float depth = rayMarchAllVolumes<SKIP, true, STATS, true>(&P.inst, 1, TfSelectSingle{s_tf}, org, dir, FLT_MAX,
+        P.invSamplingRate, rng, color, opacity, objID, instID, st, P.cellBitmap, anyHit);
     const uint32_t idx = px + py * P.width;
     P.partialRgba[idx] = make_float4(color.x, color.y, color.z, opacity);
     P.partialDepth[idx] = fminf(1e30f, depth);
   }
-  retireWarp(P.sched, lane);
+  if (STATS) {
+    const unsigned long long a = warpSum(st.taken), b = warpSum(st.skipped);
+    if (lane == 0 && P.stats) {
+      atomicAdd(&P.stats->samplesTaken, a);
+      atomicAdd(&P.stats->samplesSkipped, b);
+    }
+  }
+  retireWarpAndSignal(P.sched, lane, P.sync);
 }
 
-int launchPartial(const PartialLaunch &p, cudaStream_t s)
+template <bool SKIP, bool STATS>
+static int launchPartialT(const PartialLaunch &p, cudaStream_t s)
 {
-  static int bps[2] = {0, 0};
-  const int k = p.skip ? 1 : 0;
-  if (bps[k] == 0) {
-    if (k)
-      DVR_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps[k], dvrPartialKernel<true>, kBlockThreads, 0));
-    else
-      DVR_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps[k], dvrPartialKernel<false>, kBlockThreads, 0));
-    if (bps[k] < 1)
-      bps[k] = 1;
+  static int bps = 0;
+  if (bps == 0) {
+    DVR_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, dvrPartialKernel<SKIP, STATS>, kBlockThreads, 0));
+    if (bps < 1)
+      bps = 1;
   }
   const uint32_t nTiles = p.tilesX * p.tilesY;
-  uint32_t grid = (uint32_t)(smCount() * bps[k]);
+  uint32_t grid = (uint32_t)(smCount() * bps);
   const uint32_t need = (nTiles + 7) / 8;
   if (grid > need)
     grid = need;
   if (grid == 0)
     grid = 1;
-  if (k)
-    dvrPartialKernel<true><<<grid, kBlockThreads, 0, s>>>(p);
-  else
-    dvrPartialKernel<false><<<grid, kBlockThreads, 0, s>>>(p);
+  dvrPartialKernel<SKIP, STATS><<<grid, kBlockThreads, 0, s>>>(p);
   DVR_CUDA(cudaGetLastError());
   countLaunch();
   return DVR_OK;
+}
+
+int launchPartial(const PartialLaunch &p, cudaStream_t s)
+{
+  if (p.stats)
+    return p.skip ? launchPartialT<true, true>(p, s) : launchPartialT<false, true>(p, s);
+  return p.skip ? launchPartialT<true, false>(p, s) : launchPartialT<false, false>(p, s);
 }
 
 // ----------------------------------------------------------------------------------------------
@@ -398,13 +481,7 @@ __global__ void dvrResolveKernel(const __grid_constant__ ResolveLaunch R)
   color.z += R.background.z * oneMinus;
   opacity += R.background.w * oneMinus;
 
-  FrameLaunch P{};
-  P.width = R.width;
-  P.height = R.height;
-  P.format = R.format;
-  P.frameID = R.frameID;
-  P.checkerboardID = -1;
-  P.fb = R.fb;
+  const AccumCtx P{R.width, R.height, R.format, R.frameID, -1, R.fb};
   const bool hit = pd < 1e30f;
   const uint32_t px = (uint32_t)(i % R.width), py = (uint32_t)(i / R.width);
   accumResults(P, px, py, make_float4(color.x, color.y, color.z, opacity), pd, color, f3(0.f, 0.f, 0.f), 0u,
@@ -436,13 +513,7 @@ __device__ __forceinline__ void resolvePixel(const ResolveLaunch &R, size_t i, f
   color.y = __fmaf_rn(R.background.y, oneMinus, color.y);
   color.z = __fmaf_rn(R.background.z, oneMinus, color.z);
   opacity = __fmaf_rn(R.background.w, oneMinus, opacity);
-  FrameLaunch P{};
-  P.width = R.width;
-  P.height = R.height;
-  P.format = R.format;
-  P.frameID = R.frameID;
-  P.checkerboardID = -1;
-  P.fb = R.fb;
+  const AccumCtx P{R.width, R.height, R.format, R.frameID, -1, R.fb};
   const bool hit = pd < 1e30f;
   const uint32_t px = (uint32_t)(i % R.width), py = (uint32_t)(i / R.width);
   accumResults(P, px, py, make_float4(color.x, color.y, color.z, opacity), pd, color, f3(0.f, 0.f, 0.f), 0u,
@@ -452,47 +523,76 @@ __device__ __forceinline__ void resolvePixel(const ResolveLaunch &R, size_t i, f
 __global__ void __launch_bounds__(256) dvrPeerResolveKernel(const __grid_constant__ PeerResolveLaunch L)
 {
   const size_t i = L.r.pixelBegin + blockIdx.x * (size_t)blockDim.x + threadIdx.x;
-  if (i >= L.r.pixelEnd)
-    return;
-  const uint32_t px = (uint32_t)(i % L.r.width), py = (uint32_t)(i / L.r.width);
-  float3 org, dir;
-  cameraCreateRay(L.cam, __fmul_rn((float)px, L.invW), __fmul_rn((float)py, L.invH), 0.5f, 0.5f, org, dir);
-  const bool ascending = dir.z >= 0.f; // rays travelling towards +z meet the low-z slab first
-  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-  float depth = 1e30f;
-  // issue all peer loads first (independent), then composite
-  float4 part[kMaxSlabs];
-  float pdep[kMaxSlabs];
-#pragma unroll
-  for (int k = 0; k < kMaxSlabs; ++k) {
-    if (k < L.nSlabs) {
-      const int sidx = ascending ? k : L.nSlabs - 1 - k;
-      part[k] = __ldcv(&L.rgba[sidx][i]); // volatile-cached: another GPU wrote this line
-      pdep[k] = L.depth[sidx] ? __ldcv(&L.depth[sidx][i]) : 1e30f;
+  if (i < L.r.pixelEnd) {
+    const uint32_t px = (uint32_t)(i % L.r.width), py = (uint32_t)(i / L.r.width);
+    // the primary ray exactly as the partial march generated it (same Philox stream, same arithmetic)
+    Philox rng;
+    rng.init((unsigned long long)(int)(py * L.r.width + px), (unsigned long long)L.r.frameID * 512ull);
+    const float4 r = rng.uniform4();
+    const bool centered = L.integrator == DVR_INTEGRATOR_RAYCAST;
+    const float sx = __fmul_rn(centered ? (float)px : __fadd_rn((float)px, r.x), L.invW);
+    const float sy = __fmul_rn(centered ? (float)py : __fadd_rn((float)py, r.y), L.invH);
+    float3 org, dir;
+    cameraCreateRay(L.cam, sx, sy, r.z, r.w, org, dir);
+    float3 lo = org, ld = dir;
+    if (!L.identity) {
+      lo = xfmPoint(L.xfm, org);
+      ld = xfmVector(L.xfm, dir);
     }
-  }
-#pragma unroll
-  for (int k = 0; k < kMaxSlabs; ++k) {
-    if (k < L.nSlabs) {
-      const float w = __fsub_rn(1.f, acc.w);
-      acc.x = __fmaf_rn(w, part[k].x, acc.x);
-      acc.y = __fmaf_rn(w, part[k].y, acc.y);
-      acc.z = __fmaf_rn(w, part[k].z, acc.z);
-      acc.w = __fmaf_rn(w, part[k].w, acc.w);
-      depth = fminf(depth, pdep[k]);
+    bool hit = true;
+    if (L.cull) {
+      float t0, t1;
+      hit = intersectVolumeBox(L.boundsLo, L.boundsHi, lo, ld, 0.f, FLT_MAX, t0, t1);
     }
+    const bool ascending = ld.z >= 0.f; // rays travelling towards +z (object space) meet the low-z slab first
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    float depth = 1e30f;
+    if (hit) {
+      // (b) issue all peer loads first (independent), then composite front to back
+      float4 part[kMaxSlabs];
+      float pdep[kMaxSlabs];
+#pragma unroll
+      for (int k = 0; k < kMaxSlabs; ++k) {
+        if (k < L.nSlabs) {
+          const int sidx = ascending ? k : L.nSlabs - 1 - k;
+          part[k] = __ldcv(&L.rgba[sidx][i]); // volatile load: another GPU wrote this line
+          pdep[k] = L.depth[sidx] ? __ldcv(&L.depth[sidx][i]) : 1e30f;
+        }
+      }
+#pragma unroll
+      for (int k = 0; k < kMaxSlabs; ++k) {
+        if (k < L.nSlabs) {
+          const float w = __fsub_rn(1.f, acc.w);
+          acc.x = __fmaf_rn(w, part[k].x, acc.x);
+          acc.y = __fmaf_rn(w, part[k].y, acc.y);
+          acc.z = __fmaf_rn(w, part[k].z, acc.z);
+          acc.w = __fmaf_rn(w, part[k].w, acc.w);
+          depth = fminf(depth, pdep[k]);
+        }
+      }
+    }
+    resolvePixel(L.r, i, acc, depth);
   }
-  resolvePixel(L.r, i, acc, depth);
 }
 
 int launchPeerResolve(const PeerResolveLaunch &p, cudaStream_t s)
 {
-  if (p.r.pixelEnd <= p.r.pixelBegin)
-    return DVR_OK;
-  const size_t n = p.r.pixelEnd - p.r.pixelBegin;
-  dvrPeerResolveKernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(p);
-  DVR_CUDA(cudaGetLastError());
-  countLaunch();
+  // The cross-GPU ordering of the sync variant brackets the launch with two one-thread kernels: a single
+  // system-scope wait before (instead of one fence per CTA) and a single release after (the kernel
+  // boundary orders every peer store of the composite before the flag).
+  if (p.sync.nWait) {
+    const int rc = launchWaitFlags(p.sync.wait, p.sync.nWait, p.sync.waitValue, p.sync.errorFlag, s);
+    if (rc != DVR_OK)
+      return rc;
+  }
+  if (p.r.pixelEnd > p.r.pixelBegin) {
+    const size_t n = p.r.pixelEnd - p.r.pixelBegin;
+    dvrPeerResolveKernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(p);
+    DVR_CUDA(cudaGetLastError());
+    countLaunch();
+  }
+  if (p.sync.nSignal)
+    return launchSignalFlags(p.sync, s);
   return DVR_OK;
 }
 

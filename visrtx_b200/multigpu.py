@@ -75,12 +75,14 @@ class SortFirst:
     """Sort-first driver.  `render(frame_id, camera)` enqueues one frame on the current stream."""
 
     def __init__(self, capi, torch, dist, rank: int, world: int, device, width: int, height: int, instances,
-                 n_instances: int, fmt: int, integrator: int, rate: float, background, skip: bool = False):
+                 n_instances: int, fmt: int, integrator: int, rate: float, background, skip: bool = False,
+                 tile_band: int = 1):
         self.capi, self.torch, self.dist = capi, torch, dist
         self.rank, self.world, self.device = rank, world, device
         self.W, self.H, self.fmt = width, height, fmt
         self.integrator, self.rate, self.background, self.skip = integrator, rate, background, skip
         self.instances, self.n_instances = instances, n_instances
+        self.tile_band = tile_band
         npx = width * height
         px_bytes = 16 if fmt == capi.DVR_FORMAT_FLOAT32_VEC4 else 4
         self.accum = torch.zeros((npx, 4), dtype=torch.float32, device=device)
@@ -103,7 +105,8 @@ class SortFirst:
 
     def params(self, frame_id: int):
         return self.capi.frame_params(self.W, self.H, self.fmt, self.integrator, frame_id, -1, 1, self.rate,
-                                      self.background, tile_rank=self.rank, tile_ranks=self.world, skip=self.skip)
+                                      self.background, tile_rank=self.rank, tile_ranks=self.world, skip=self.skip,
+                                      tile_band=self.tile_band)
 
     def render(self, frame_id: int, camera, stream: int):
         self.capi.render(self.params(frame_id), camera, self.instances, self.n_instances, self.fb, stream)
@@ -131,7 +134,17 @@ class SortFirst:
 
 
 class SortLast:
-    """Sort-last driver over z-slabs: partial march + fused peer composite/resolve."""
+    """Sort-last driver over z-slabs: partial march + fused peer composite/resolve.
+
+    Cross-GPU ordering is done ON THE DEVICE with flags in CUDA-IPC shared memory (DvrPeerSync): the
+    partial kernel's last warp publishes "partial f complete" into every rank's flag table, the composite
+    kernel spins on its local table before touching peer data and publishes "strip f resolved"; a
+    one-thread wait kernel keeps a rank from overwriting a partial buffer that a slower rank may still be
+    reading (two frames back, the buffers alternate) and lets the display rank wait for the full frame.
+    No host synchronisation and no NCCL call on the per-frame path.
+    """
+
+    FLAG_WORDS = 64  # [0:16] partial-complete per source rank, [16:32] strip-resolved per source rank, [32] error
 
     def __init__(self, capi, torch, dist, rank: int, world: int, device, width: int, height: int, instance,
                  obj_id: int, inst_id: int, fmt: int, integrator: int, rate: float, background, skip: bool = False):
@@ -146,28 +159,33 @@ class SortLast:
         self.strips = pixel_strips(npx, world)
         self.accum = torch.zeros((npx, 4), dtype=torch.float32, device=device)
         self.depth = torch.zeros(npx, dtype=torch.float32, device=device)
-        # my partial images (double-buffered) live in IPC-exportable allocations
-        self._mine, handles = [], []
-        self._peer_open = []
+        self._mine, self._peer_open = [], []
+        self._color_owned = None
+        self.frames = 0
         if world == 1:
             self.buf = [torch.zeros((npx, 5), dtype=torch.float32, device=device) for _ in range(2)]
             self.rgba_ptrs = [[b.data_ptr()] for b in self.buf]
             self.depth_ptrs = [[b.data_ptr() + npx * 16] for b in self.buf]
             self.color_local = torch.zeros(npx * px_bytes // 4, dtype=torch.int32, device=device)
             self.color_ptr = self.color_local.data_ptr()
-            self._color_owned = None
+            self.flag_ptrs = None
         else:
             payload = b""
             for _ in range(2):
                 p, h = capi.ipc_alloc(npx * 20)
                 self._mine.append(p)
                 payload += h
-            self._color_owned = None
+            fp, fh = capi.ipc_alloc(self.FLAG_WORDS * 4)
+            self._mine.append(fp)
+            import ctypes
+            ctypes.CDLL("libcudart.so").cudaMemset(ctypes.c_void_p(fp), 0, ctypes.c_size_t(self.FLAG_WORDS * 4))
+            torch.cuda.synchronize()
+            payload += fh
             if rank == 0:
                 self._color_owned, hc = capi.ipc_alloc(npx * px_bytes)
                 payload += hc
             all_h = exchange_bytes(dist, payload, world)
-            self.rgba_ptrs, self.depth_ptrs = [[], []], [[], []]
+            self.rgba_ptrs, self.depth_ptrs, self.flag_ptrs = [[], []], [[], []], []
             for r in range(world):
                 for b in range(2):
                     if r == rank:
@@ -177,30 +195,61 @@ class SortLast:
                         self._peer_open.append(p)
                     self.rgba_ptrs[b].append(p)
                     self.depth_ptrs[b].append(p + npx * 16)
+                if r == rank:
+                    self.flag_ptrs.append(fp)
+                else:
+                    q = capi.ipc_open(all_h[r][128:192])
+                    self._peer_open.append(q)
+                    self.flag_ptrs.append(q)
             if rank == 0:
                 self.color_ptr = self._color_owned
             else:
-                self.color_ptr = capi.ipc_open(all_h[0][128:192])
+                self.color_ptr = capi.ipc_open(all_h[0][192:256])
                 self._peer_open.append(self.color_ptr)
+            dist.barrier()  # every table is zeroed and mapped before the first signal can arrive
         self.fb = capi.frame_buffers(self.accum.data_ptr(), self.color_ptr, self.depth.data_ptr())
-        self.barrier = _Barrier(dist, torch, device) if world > 1 else (lambda: None)
         self.frame_parity = 0
 
     def params(self, frame_id: int):
         return self.capi.frame_params(self.W, self.H, self.fmt, self.integrator, frame_id, -1, 1, self.rate,
                                       self.background, skip=self.skip)
 
-    def render(self, frame_id: int, camera, stream: int):
+    def render(self, frame_id: int, camera, stream: int, wait_display: bool = True):
+        capi = self.capi
         b = self.frame_parity
         self.frame_parity ^= 1
+        self.frames += 1
+        seq = self.frames  # monotonically increasing frame number carried by the flags
         p = self.params(frame_id)
-        self.capi.render_partial(p, camera, self.instance, self.rgba_ptrs[b][self.rank], self.depth_ptrs[b][self.rank],
-                                 stream)
-        self.barrier()  # every slab's partial image of this frame is complete
         lo, hi = self.strips[self.rank]
-        self.capi.composite_resolve_peers(p, camera, self.rgba_ptrs[b], self.depth_ptrs[b], self.obj_id, self.inst_id,
-                                          self.fb, lo, hi, stream)
-        self.barrier()  # every strip has landed in the display rank's frame
+        if self.world == 1:
+            capi.render_partial(p, camera, self.instance, self.rgba_ptrs[b][0], self.depth_ptrs[b][0], stream)
+            capi.composite_resolve_peers(p, camera, self.rgba_ptrs[b], self.depth_ptrs[b], self.obj_id, self.inst_id,
+                                         self.fb, lo, hi, stream)
+            return
+        me, W = self.rank, self.world
+        my_flags = self.flag_ptrs[me]
+        err = my_flags + 32 * 4
+        if seq > 2:  # partial buffer b was last read by the composites of frame seq-2
+            capi.wait_flags(my_flags + 16 * 4, W, seq - 2, err, stream)
+        sync_p = capi.peer_sync(signal_ptrs=[self.flag_ptrs[r] + me * 4 for r in range(W)], signal_value=seq)
+        capi.render_partial_sync(p, camera, self.instance, self.rgba_ptrs[b][me], self.depth_ptrs[b][me], sync_p, stream)
+        sync_c = capi.peer_sync(signal_ptrs=[self.flag_ptrs[r] + (16 + me) * 4 for r in range(W)], signal_value=seq,
+                                wait_ptr=my_flags, n_wait=W, wait_value=seq, error_flag=err)
+        capi.composite_resolve_peers_sync(p, camera, self.instance, self.rgba_ptrs[b], self.depth_ptrs[b], self.obj_id,
+                                          self.inst_id, self.fb, lo, hi, sync_c, stream)
+        if me == 0 and wait_display:  # the display rank's stream continues once every strip has landed
+            capi.wait_flags(my_flags + 16 * 4, W, seq, err, stream)
+
+    def check_errors(self):
+        """True when a bounded spin gave up (a producer never signalled)."""
+        if self.world == 1:
+            return False
+        import ctypes
+        v = ctypes.c_uint32()
+        ctypes.CDLL("libcudart.so").cudaMemcpy(ctypes.byref(v), ctypes.c_void_p(self.flag_ptrs[self.rank] + 32 * 4),
+                                               ctypes.c_size_t(4), ctypes.c_int(2))
+        return v.value != 0
 
     def color_tensor(self):
         import ctypes
