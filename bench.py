@@ -50,13 +50,25 @@ def parse_args():
     ap.add_argument("--rate", type=float, default=0.5, help="volumeSamplingRate (0.5 => 1 voxel per step)")
     ap.add_argument("--unit-distance", type=float, default=256.0,
                     help="TF unitDistance in voxels; 256 = semi-transparent, every ray crosses the volume")
-    ap.add_argument("--field", default="ml", choices=["ml"])
-    ap.add_argument("--skip", type=int, default=0, help="macrocell skipping (no effect on the dense field)")
+    ap.add_argument("--field", default="ml", choices=["ml", "shells"])
+    ap.add_argument("--config", default="c2", choices=["c2", "c3", "c4"],
+                    help="BASELINE.json config preset: c2 = 1024^3 f32 1080p (headline); c3 = 2048^3 16-bit sparse shells, "
+                         "3840x2160, macrocell skipping; c4 = 4096^3 f32 sort-last (needs >= 2 GPUs)")
+    ap.add_argument("--skip", type=int, default=-1,
+                    help="macrocell skipping: 1/0; default -1 = off for the dense C2/C4 fields, on for C3")
     ap.add_argument("--mode", default="auto", choices=["auto", "sort-first", "sort-last"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-rows", type=int, default=0, help="rows of the CPU-baseline band (0 = auto)")
     ap.add_argument("--extra", type=int, default=1, help="also measure the secondary variants (N=1 only)")
-    return ap.parse_args()
+    a = ap.parse_args()
+    if a.config == "c3":
+        a.size, a.width, a.height, a.field = 2048, 3840, 2160, "shells"
+        a.skip = 1 if a.skip < 0 else a.skip
+        a.unit_distance = 8.0
+    elif a.config == "c4":
+        a.size, a.unit_distance, a.mode = 4096, 1024.0, "sort-last"
+    a.skip = max(a.skip, 0)
+    return a
 
 
 # ---------------------------------------------------------------------------------------------------------
@@ -111,11 +123,38 @@ class ClockSampler:
 
 # ---------------------------------------------------------------------------------------------------------
 def make_scene(args, torch, device, z_begin=0, z_end=None):
-    """C2: Marschner-Lobb evaluated on a size^3 lattice, origin 0, spacing 1, generated in HBM."""
+    """Analytic field on a size^3 lattice, origin 0, spacing 1, generated in HBM.
+    ml: Marschner-Lobb f32 (dense).  shells: 12 thin Gaussian shells, UFIXED16 (sparse, C3)."""
     from visrtx_b200 import scenes
     n = args.size
-    vol = scenes.marschner_lobb_torch(n, device, z_begin=z_begin, z_end=z_end, nz_total=n)
-    return vol
+    if args.field == "shells":
+        assert z_begin == 0 and z_end is None, "the sparse field is generated whole"
+        return scenes.shells_torch(n, device)
+    return scenes.marschner_lobb_torch(n, device, z_begin=z_begin, z_end=z_end, nz_total=n)
+
+
+def scene_dtype(args):
+    from visrtx_b200 import capi
+    return capi.DVR_UFIXED16 if args.field == "shells" else capi.DVR_FLOAT32
+
+
+def voxel_bytes(args):
+    return 2 if args.field == "shells" else 4
+
+
+def scene_colormap(args):
+    from visrtx_b200 import scenes
+    return scenes.sparse_colormap(256, 0.5) if args.field == "shells" else scenes.tsd_default_colormap(256)
+
+
+def workload_name(args):
+    n, W, H = args.size, args.width, args.height
+    field = ("UFIXED16 sparse shells (12 Gaussian shells r=96*n/2048 voxels, zero elsewhere)" if args.field == "shells"
+             else "f32 Marschner-Lobb (dense)")
+    tfn = "sparse map (alpha 0 below 0.5)" if args.field == "shells" else "TSD default map"
+    return (f"{args.config.upper()}: {n}^3 {field} structuredRegular + transferFunction1D ({tfn}, unitDistance "
+            f"{args.unit_distance:g} voxels), {W}x{H}, default renderer 1 spp progressive, volumeSamplingRate "
+            f"{args.rate:g} (step {0.5 / args.rate:g} voxel), orbit camera az30/el20 at 2|diag|, fovy 60")
 
 
 def orbit(args, az_deg=30.0):
@@ -125,9 +164,16 @@ def orbit(args, az_deg=30.0):
     return capi.camera_perspective(pose.position, pose.direction, pose.up, pose.fovy, pose.aspect), pose
 
 
-def bytes_per_frame(args, cells_touched: int, fmt_bytes: int = 4) -> int:
-    # N_vox_touched * sizeof(voxel) + N_px * (32 accum RW + colour + 8 depth RW) + 4 KiB TF
-    return cells_touched * 16 ** 3 * 4 + args.width * args.height * (32 + fmt_bytes + 8) + 4096
+def bytes_per_frame(args, cells_touched: int, samples: int = 0, fmt_bytes: int = 4):
+    """N_vox_touched * sizeof(voxel) + N_px * (32 accum RW + colour + 8 depth RW) + 4 KiB TF, with
+    N_vox_touched = voxels of the macrocells the rays fetched from.  When rays are many voxels apart (C4 at
+    1080p: 15 voxels) that over-counts: a sample cannot pull more than 4 32-byte sectors, so the voxel term is
+    capped at samples * 128 B.  Returns (bytes, which_model)."""
+    frame = args.width * args.height * (32 + fmt_bytes + 8) + 4096
+    cell_model = cells_touched * 16 ** 3 * voxel_bytes(args)
+    if samples and samples * 128 < cell_model:
+        return samples * 128 + frame, "sector cap: samples*128B (rays sparser than macrocells)"
+    return cell_model + frame, "macrocells touched * 16^3 * sizeof(voxel) (SURVEY 8d)"
 
 
 def measured_peak():
@@ -145,8 +191,10 @@ def cpu_baseline(args, torch, vol_dev, samples_per_frame: int):
     import oracle_binding as ob
     from visrtx_b200 import capi, scenes
     n = args.size
-    host = vol_dev.cpu().numpy()  # (z,y,x) f32
-    tf = capi.tf_discretize(color=scenes.tsd_default_colormap(256))
+    host = vol_dev.cpu().numpy()  # (z,y,x)
+    if args.field == "shells":  # UFIXED16 stored as int16 bits -> what cudaReadModeNormalizedFloat hands the filter
+        host = (host.view(np.uint16).astype(np.float32) / np.float32(65535.0))
+    tf = capi.tf_discretize(color=scene_colormap(args))
     cam, _ = orbit(args)
     vols = (ob.OracleVolume * 1)()
     o = vols[0]
@@ -206,12 +254,12 @@ class AnariE2E:
         d.set(d.handle, "cudaDevice", A.INT32, device.index)
         d.commit(d.handle)
         torch.cuda.synchronize()
-        self.data = d.new_array3d_device(vol_dev.data_ptr(), A.FLOAT32, n, n, n)
+        self.data = d.new_array3d_device(vol_dev.data_ptr(), A.UFIXED16 if args.field == "shells" else A.FLOAT32, n, n, n)
         self.field = d.new("SpatialField", "structuredRegular")
         d.set(self.field, "data", A.ARRAY3D, self.data)
         d.commit(self.field)
         self.volume = d.new("Volume", "transferFunction1D")
-        self.color = d.new_array1d(scenes.tsd_default_colormap(256), A.FLOAT32_VEC4)
+        self.color = d.new_array1d(scene_colormap(args), A.FLOAT32_VEC4)
         d.set(self.volume, "color", A.ARRAY1D, self.color)
         d.set(self.volume, "value", A.SPATIAL_FIELD, self.field)
         d.set(self.volume, "unitDistance", A.FLOAT32, args.unit_distance)
@@ -286,8 +334,8 @@ def run_ours(args, torch, dist, rank, world):
     if mode == "auto":
         # sort-last (z-slabs) also wins when the volume fits one GPU: it shortens every ray by 1/N, while
         # sort-first leaves the longest ray (the kernel's critical path) untouched (profiles/r01_multigpu.md)
-        mode = "sort-last"
-    if world == 1 and mode != "sort-last":
+        mode = "sort-last" if world > 1 else "single"
+    if world == 1 and mode == "sort-first":
         mode = "single"
 
     t_setup = time.perf_counter()
@@ -296,7 +344,7 @@ def run_ours(args, torch, dist, rank, world):
         from visrtx_b200 import multigpu as _mg
         z0, z1 = _mg.slab_ranges(n, world)[rank]
         r0, r1 = _mg.resident_range(z0, z1, n)
-        field = capi.Field.create_slab(0, True, capi.DVR_FLOAT32, (n, n, n), z0, z1, (0, 0, 0), (1, 1, 1),
+        field = capi.Field.create_slab(0, True, scene_dtype(args), (n, n, n), z0, z1, (0, 0, 0), (1, 1, 1),
                                        capi.DVR_FILTER_LINEAR, stream)
         chunk = 32
         for zc in range(r0, r1, chunk):  # generate + upload in chunks: the slab is never staged twice in HBM
@@ -308,10 +356,10 @@ def run_ours(args, torch, dist, rank, world):
         field.build_macrocells(stream)
     else:
         vol = make_scene(args, torch, device)
-        field = capi.Field.create_structured(vol.data_ptr(), True, capi.DVR_FLOAT32, (n, n, n), (0, 0, 0), (1, 1, 1),
+        field = capi.Field.create_structured(vol.data_ptr(), True, scene_dtype(args), (n, n, n), (0, 0, 0), (1, 1, 1),
                                              capi.DVR_FILTER_LINEAR, stream)
     torch.cuda.synchronize()
-    tf = capi.tf_discretize(color=scenes.tsd_default_colormap(256))
+    tf = capi.tf_discretize(color=scene_colormap(args))
     volume = capi.Volume.create(field, tf, (0.0, 1.0), args.unit_distance, 0, stream)
     inst, ninst = capi.make_instances([volume], None, [0])
     cam, _ = orbit(args)
@@ -451,22 +499,19 @@ def run_ours(args, torch, dist, rank, world):
     clocks = sampler.stop() if rank == 0 else None
 
     peak, peak_src = measured_peak()
-    bframe = bytes_per_frame(args, cells)
+    bframe, bmodel = bytes_per_frame(args, cells, samples)
     share = 1.0 / world
     # per-GPU achieved bandwidth: every rank reads ~1/N of the touched voxels (its tile rows / its slab)
     achieved = bframe * share / (kernel_ms * 1e-3) / 1e9
     out = {
-        "metric": "DVR frames/s, 1080p, 1024^3 f32 volume (Gsamples/s in extra)",
+        "metric": "DVR frames/s, 1080p, 1024^3 f32 volume (Gsamples/s in extra)" if args.config == "c2" else f"DVR frames/s, config {args.config}",
         "value": fps, "unit": "frames/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
-        "dtype": "f32", "data": "synthetic (analytic Marschner-Lobb field generated in HBM)",
+        "dtype": "f32", "data": "synthetic (analytic field generated in HBM: " + args.field + ")",
         "config": {
-            "workload": f"C2: {n}^3 f32 structuredRegular + transferFunction1D (TSD default map, unitDistance "
-                        f"{args.unit_distance:g} voxels), {W}x{H}, default renderer 1 spp progressive, "
-                        f"volumeSamplingRate {args.rate:g} (step {0.5 / args.rate:g} voxel), orbit camera az30/el20 "
-                        f"at 2|diag|, fovy 60",
+            "workload": workload_name(args),
             "parallelism": mode + (f"x{world}" if world > 1 else ""),
-            "l2": f"input volume {n ** 3 * 4 / 2 ** 30:.1f} GiB >> 126 MB L2; no flush needed",
+            "l2": f"input volume {n ** 3 * voxel_bytes(args) / 2 ** 30:.1f} GiB >> 126 MB L2; no flush needed",
             "macrocell_skipping": bool(args.skip),
         },
         "gpu_launches": int(launches),
@@ -475,7 +520,7 @@ def run_ours(args, torch, dist, rank, world):
                 "what": e2e_what},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": None, "peak_source": peak_src, "kernel": "dvrFrameKernel",
-                     "kernel_ms": kernel_ms, "algorithmic_bytes": bframe,
+                     "kernel_ms": kernel_ms, "algorithmic_bytes": bframe, "bytes_model": bmodel,
                      "macrocells_touched": int(cells), "macrocells_total": int(math.ceil(n / 16) ** 3)},
         "extra": {"samples_per_frame": int(samples), "gsamples_per_s": samples * fps / 1e9 * (1 if world == 1 else 1),
                   "rays_hit": int(rays_hit), "bytes_per_sample": bframe / max(samples, 1), "setup_s": setup_s,
@@ -503,7 +548,7 @@ def run_ours(args, torch, dist, rank, world):
 def measure_variants(args, torch, capi, scenes, field, cam, inst, ninst, fb, stream, stats_t):
     """Secondary numbers (same scene): other sampling rates and the opaque BASELINE.md-literal TF."""
     res = {}
-    tf = capi.tf_discretize(color=scenes.tsd_default_colormap(256))
+    tf = capi.tf_discretize(color=scene_colormap(args))
     for name, rate, ud in (("rate0.125_ud256", 0.125, args.unit_distance), ("rate1.0_ud256", 1.0, args.unit_distance),
                            ("rate0.5_ud1_opaque", 0.5, 1.0)):
         v = capi.Volume.create(field, tf, (0.0, 1.0), ud, 0, stream)
@@ -522,7 +567,7 @@ def measure_variants(args, torch, capi, scenes, field, cam, inst, ninst, fb, str
         e1.record()
         torch.cuda.synchronize()
         ms = e0.elapsed_time(e1) / 20
-        bf = bytes_per_frame(args, cells)
+        bf, _ = bytes_per_frame(args, cells, samples)
         res[name] = {"fps": 1000.0 / ms, "ms": ms, "samples_per_frame": samples, "gsamples_per_s": samples / ms / 1e6,
                      "macrocells_touched": cells, "algorithmic_GBps": bf / ms / 1e6}
         v.destroy()
@@ -537,10 +582,10 @@ def _refgpu_objects(args, torch, vol_dev):
     lib = ob.refgpu()
     n = args.size
     f = C.c_void_p()
-    rc = lib.refgpu_field_create(C.c_void_p(vol_dev.data_ptr()), C.c_int(capi.DVR_FLOAT32), (C.c_uint32 * 3)(n, n, n),
+    rc = lib.refgpu_field_create(C.c_void_p(vol_dev.data_ptr()), C.c_int(scene_dtype(args)), (C.c_uint32 * 3)(n, n, n),
                                  (C.c_float * 3)(0, 0, 0), (C.c_float * 3)(1, 1, 1), C.c_int(0), C.byref(f))
     assert rc == 0, lib.refgpu_last_error()
-    tf = capi.tf_discretize(color=scenes.tsd_default_colormap(256))
+    tf = capi.tf_discretize(color=scene_colormap(args))
     v = C.c_void_p()
     rc = lib.refgpu_volume_create(f, tf.ctypes.data_as(C.c_void_p), (C.c_float * 2)(0, 1), C.c_float(args.unit_distance),
                                   C.c_uint32(0), C.byref(v))
@@ -591,13 +636,11 @@ def run_reference(args, torch, dist, rank, world):
     n, W, H = args.size, args.width, args.height
     npx = W * H
     vol = make_scene(args, torch, device)
-    base = {"impl": "reference", "metric": "DVR frames/s, 1080p, 1024^3 f32 volume (Gsamples/s in extra)",
+    base = {"impl": "reference", "metric": "DVR frames/s, 1080p, 1024^3 f32 volume (Gsamples/s in extra)" if args.config == "c2" else f"DVR frames/s, config {args.config}",
             "unit": "frames/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic (analytic Marschner-Lobb field generated in HBM)"}
-    workload = (f"C2: {n}^3 f32 structuredRegular + transferFunction1D (TSD default map, unitDistance "
-                f"{args.unit_distance:g} voxels), {W}x{H}, default renderer 1 spp progressive, volumeSamplingRate "
-                f"{args.rate:g}, orbit camera az30/el20 at 2|diag|, fovy 60")
+    workload = workload_name(args)
     if not ob.have_ref_gpu():
         # fall back to the CPU port
         cb = cpu_baseline(args, torch, vol, 1)
@@ -606,9 +649,9 @@ def run_reference(args, torch, dist, rank, world):
         # with the GPU-measured samples per frame when libdvr is present
         from visrtx_b200 import scenes
         stream = torch.cuda.current_stream().cuda_stream
-        field = capi.Field.create_structured(vol.data_ptr(), True, capi.DVR_FLOAT32, (n, n, n), (0, 0, 0), (1, 1, 1),
+        field = capi.Field.create_structured(vol.data_ptr(), True, scene_dtype(args), (n, n, n), (0, 0, 0), (1, 1, 1),
                                              capi.DVR_FILTER_LINEAR, stream)
-        tf = capi.tf_discretize(color=scenes.tsd_default_colormap(256))
+        tf = capi.tf_discretize(color=scene_colormap(args))
         v = capi.Volume.create(field, tf, (0.0, 1.0), args.unit_distance, 0, stream)
         inst, ninst = capi.make_instances([v], None, [0])
         accum = torch.zeros((npx, 4), dtype=torch.float32, device=device)

@@ -127,8 +127,8 @@ def test_macrocell_skipping_actually_skips_and_majorants_are_conservative():
         for cz in range(gz):
             for cy in range(gy):
                 for cx in range(gx):
-                    blk = vox[max(cz * 16 - 1, 0):cz * 16 + 17, max(cy * 16 - 1, 0):cy * 16 + 17,
-                              max(cx * 16 - 1, 0):cx * 16 + 17]
+                    blk = vox[max(cz * 16 - 1, 0):cz * 16 + 18, max(cy * 16 - 1, 0):cy * 16 + 18,
+                              max(cx * 16 - 1, 0):cx * 16 + 18]
                     assert r[cz, cy, cx, 0] == blk.min() and r[cz, cy, cx, 1] == blk.max()
         lo, hi = cs.fields[0].value_range()
         assert lo == vox.min() and hi == vox.max()

@@ -3,9 +3,9 @@
 //
 // K4 is one pass over the voxels (read through a point-sampled view of the same 3-D array the
 // marcher filters, so fixed-point formats are seen exactly as the filter sees them).  Cell c
-// covers voxel indices [16c-1, 16c+16] per axis (clamped): every trilinear fetch whose lower tap
-// index falls in [16c, 16c+15] reads only those voxels, and the one-voxel apron on the low side
-// absorbs texture-unit coordinate rounding.  The reference's build samples the wrong coordinates
+// covers voxel indices [16c-1, 16c+17] per axis (clamped): every trilinear fetch whose lower tap
+// index falls in [16c, 16c+15] reads voxels [16c, 16c+16]; the extra voxel on either side absorbs
+// the difference between the marcher's fp32 cell test and the texture unit's own coordinate rounding.  The reference's build samples the wrong coordinates
 //  and is deliberately not reproduced.
 #include "dvr_internal.h"
 
@@ -15,9 +15,9 @@ __global__ void __launch_bounds__(256) dvrMacrocellRangeKernel(cudaTextureObject
     int zTexBegin, int texDepth, int3 gridDims, float2 *__restrict__ ranges)
 {
   const int cx = blockIdx.x, cy = blockIdx.y, cz = blockIdx.z;
-  const int x0 = max(cx * 16 - 1, 0), x1 = min(cx * 16 + 16, dims.x - 1);
-  const int y0 = max(cy * 16 - 1, 0), y1 = min(cy * 16 + 16, dims.y - 1);
-  const int z0 = max(cz * 16 - 1, 0), z1 = min(cz * 16 + 16, dims.z - 1);
+  const int x0 = max(cx * 16 - 1, 0), x1 = min(cx * 16 + 17, dims.x - 1);
+  const int y0 = max(cy * 16 - 1, 0), y1 = min(cy * 16 + 17, dims.y - 1);
+  const int z0 = max(cz * 16 - 1, 0), z1 = min(cz * 16 + 17, dims.z - 1);
   const int nx = x1 - x0 + 1, ny = y1 - y0 + 1, nz = z1 - z0 + 1;
   const int n = nx * ny * nz;
   float lo = FLT_MAX, hi = -FLT_MAX;

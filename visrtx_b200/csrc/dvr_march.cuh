@@ -150,17 +150,17 @@ __device__ __forceinline__ void marchSegment(const VolumeDev &v, const float4 *_
         const float ey = dvox.y != 0.f ? (by - xb.y) / dvox.y : FLT_MAX;
         const float ez = dvox.z != 0.f ? (bz - xb.z) / dvox.z : FLT_MAX;
         const float dt = fminf(fminf(ex, ey), ez);
-        // whole steps that stay strictly inside the cell, one step of safety margin
-        int n = (int)floorf(fminf(dt / stepSize, 1.0e6f)) - 1;
-        if (n >= 1) {
-          while (n > 0 && t <= tUpper) {
-            t = __fadd_rn(t, stepSize);
-            --n;
-            if (STATS)
-              stats.skipped++;
-          }
-          continue;
+        // Whole steps that stay strictly inside the cell (one step of safety margin); at least THIS lattice
+        // point is skippable on its own: the cell containing its lower tap has majorant 0, so its fetch
+        // would classify to alpha == 0 exactly and contribute nothing.
+        int n = max((int)floorf(fminf(dt / stepSize, 1.0e6f)) - 1, 1);
+        while (n > 0 && t <= tUpper) {
+          t = __fadd_rn(t, stepSize);
+          --n;
+          if (STATS)
+            stats.skipped++;
         }
+        continue;
       }
     }
 
