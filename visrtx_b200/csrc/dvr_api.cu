@@ -99,6 +99,8 @@ struct DvrVolume
   const DvrField *field = nullptr;
   float4 *tf = nullptr;
   float *maxOpacities = nullptr;
+  float *maxOpacitiesCoarse = nullptr;
+  int3 coarseDims{0, 0, 0};
   float vrLo = 0.f, vrHi = 1.f, oneOverUnitDistance = 1.f;
   uint32_t id = ~0u;
 };
@@ -636,7 +638,10 @@ int dvr_volume_update(DvrVolume *v, const float *tfRgba, const float valueRange[
   v->vrHi = valueRange[1];
   v->oneOverUnitDistance = 1.0f / unitDistance;
   v->id = id;
-  return launchMajorants(v->field->ranges, v->field->nCells, v->tf, v->vrLo, v->vrHi, v->maxOpacities, s);
+  const int rc = launchMajorants(v->field->ranges, v->field->nCells, v->tf, v->vrLo, v->vrHi, v->maxOpacities, s);
+  if (rc != DVR_OK)
+    return rc;
+  return launchMajorantsCoarse(v->maxOpacities, v->field->dev.gridDims, v->maxOpacitiesCoarse, v->coarseDims, s);
 }
 
 int dvr_volume_create(const DvrField *field, const float *tfRgba, const float valueRange[2], float unitDistance,
@@ -651,6 +656,10 @@ int dvr_volume_create(const DvrField *field, const float *tfRgba, const float va
   cudaError_t e = cudaMalloc(&v->tf, DVR_TF_SIZE * sizeof(float4));
   if (e == cudaSuccess)
     e = cudaMalloc(&v->maxOpacities, field->nCells * sizeof(float));
+  const int3 g = field->dev.gridDims;
+  v->coarseDims = make_int3((g.x + 3) / 4, (g.y + 3) / 4, (g.z + 3) / 4);
+  if (e == cudaSuccess)
+    e = cudaMalloc(&v->maxOpacitiesCoarse, (size_t)v->coarseDims.x * v->coarseDims.y * v->coarseDims.z * sizeof(float));
   if (e != cudaSuccess) {
     dvr_volume_destroy(v);
     return cudaFail(e, "cudaMalloc(volume)");
@@ -670,6 +679,7 @@ int dvr_volume_destroy(DvrVolume *v)
     return DVR_OK;
   if (v->tf) cudaFree(v->tf);
   if (v->maxOpacities) cudaFree(v->maxOpacities);
+  if (v->maxOpacitiesCoarse) cudaFree(v->maxOpacitiesCoarse);
   delete v;
   return DVR_OK;
 }
@@ -709,6 +719,8 @@ static void fillInstance(const DvrVolumeInstance &in, InstanceDev &d)
   d.v.oneOverUnitDistance = v->oneOverUnitDistance;
   d.v.id = v->id;
   d.v.maxOpacities = v->maxOpacities;
+  d.v.maxOpacitiesCoarse = v->maxOpacitiesCoarse;
+  d.v.coarseDims = v->coarseDims;
   static const float ident[12] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0};
   std::memcpy(d.xfm, in.worldToObject, sizeof(d.xfm));
   d.instId = in.instanceId;

@@ -43,6 +43,8 @@ struct VolumeDev
   float oneOverUnitDistance;
   uint32_t id;
   const float *maxOpacities; // per macrocell: max TF alpha over the cell's range
+  const float *maxOpacitiesCoarse; // per 4x4x4 block of macrocells (64^3 voxels): max of the children
+  int3 coarseDims;
 };
 
 struct InstanceDev

@@ -126,6 +126,7 @@ int launchMacrocellBuild(cudaTextureObject_t pointTex, int3 dims, int zTexBegin,
     float2 *ranges, cudaStream_t s);
 int launchMajorants(const float2 *ranges, size_t nCells, const float4 *tf, float vrLo, float vrHi,
     float *maxOpacities, cudaStream_t s);
+int launchMajorantsCoarse(const float *fine, int3 gridDims, float *coarse, int3 coarseDims, cudaStream_t s);
 int launchRangeReduce(const float2 *ranges, size_t nCells, float2 *out, cudaStream_t s);
 int launchPopcount(const unsigned int *bitmap, size_t nWords, unsigned long long *out, cudaStream_t s);
 int launchConvertToFloat(const void *src, int dataType, float *dst, size_t n, cudaStream_t s);

@@ -101,6 +101,33 @@ int launchMajorants(const float2 *ranges, size_t nCells, const float4 *tf, float
   return DVR_OK;
 }
 
+// coarse level of the skipping hierarchy: max over each 4x4x4 block of macrocells
+__global__ void dvrMajorantCoarseKernel(const float *__restrict__ fine, int3 g, float *__restrict__ coarse, int3 cg)
+{
+  const size_t c = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  const size_t n = (size_t)cg.x * cg.y * cg.z;
+  if (c >= n)
+    return;
+  const int X = (int)(c % cg.x), Y = (int)((c / cg.x) % cg.y), Z = (int)(c / ((size_t)cg.x * cg.y));
+  float m = 0.f;
+  for (int z = Z * 4; z < min(Z * 4 + 4, g.z); ++z)
+    for (int y = Y * 4; y < min(Y * 4 + 4, g.y); ++y)
+      for (int x = X * 4; x < min(X * 4 + 4, g.x); ++x)
+        m = fmaxf(m, fine[((size_t)z * g.y + y) * g.x + x]);
+  coarse[c] = m;
+}
+
+int launchMajorantsCoarse(const float *fine, int3 gridDims, float *coarse, int3 coarseDims, cudaStream_t s)
+{
+  const size_t n = (size_t)coarseDims.x * coarseDims.y * coarseDims.z;
+  if (n == 0)
+    return DVR_OK;
+  dvrMajorantCoarseKernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(fine, gridDims, coarse, coarseDims);
+  DVR_CUDA(cudaGetLastError());
+  countLaunch();
+  return DVR_OK;
+}
+
 // global (min,max) over the macrocell ranges: one CTA, strided
 __global__ void dvrRangeReduceKernel(const float2 *__restrict__ ranges, size_t nCells, float2 *out)
 {

@@ -139,13 +139,20 @@ __device__ __forceinline__ void marchSegment(const VolumeDev &v, const float4 *_
       const int cx = min(max((int)floorf(xb.x), 0), f.dims.x - 1) >> 4;
       const int cy = min(max((int)floorf(xb.y), 0), f.dims.y - 1) >> 4;
       const int cz = min(max((int)floorf(xb.z), 0), f.dims.z - 1) >> 4;
+      // two-level test: a 64^3-voxel block of macrocells first (long empty runs in one hop), then the
+      // 16^3 macrocell; both loads are issued together
       const float majorant = __ldg(&v.maxOpacities[(size_t)cz * f.gridDims.x * f.gridDims.y
           + (size_t)cy * f.gridDims.x + cx]);
+      const float coarse = __ldg(&v.maxOpacitiesCoarse[(size_t)(cz >> 2) * v.coarseDims.x * v.coarseDims.y
+          + (size_t)(cy >> 2) * v.coarseDims.x + (cx >> 2)]);
       if (majorant <= 0.f) {
-        // distance (in t) to the nearest face of this macrocell along the ray
-        const float bx = dvox.x > 0.f ? (float)((cx + 1) << 4) : (float)(cx << 4);
-        const float by = dvox.y > 0.f ? (float)((cy + 1) << 4) : (float)(cy << 4);
-        const float bz = dvox.z > 0.f ? (float)((cz + 1) << 4) : (float)(cz << 4);
+        // distance (in t) to the nearest face of the empty region along the ray
+        const int sh = coarse <= 0.f ? 6 : 4;
+        const int rx = coarse <= 0.f ? (cx >> 2) : cx, ry = coarse <= 0.f ? (cy >> 2) : cy,
+                  rz = coarse <= 0.f ? (cz >> 2) : cz;
+        const float bx = dvox.x > 0.f ? (float)((rx + 1) << sh) : (float)(rx << sh);
+        const float by = dvox.y > 0.f ? (float)((ry + 1) << sh) : (float)(ry << sh);
+        const float bz = dvox.z > 0.f ? (float)((rz + 1) << sh) : (float)(rz << sh);
         const float ex = dvox.x != 0.f ? (bx - xb.x) / dvox.x : FLT_MAX;
         const float ey = dvox.y != 0.f ? (by - xb.y) / dvox.y : FLT_MAX;
         const float ez = dvox.z != 0.f ? (bz - xb.z) / dvox.z : FLT_MAX;
