@@ -209,6 +209,12 @@ int dvr_field_create_structured_slab(const void *data, int dataIsDevice, int dat
  * field's.  Call dvr_field_build_macrocells once all slices are in. */
 int dvr_field_upload_slices(DvrField *f, const void *data, int dataIsDevice, uint32_t firstResidentSlice,
     uint32_t nSlices, void *stream);
+/* NvdbRegularField::finalize, spatial_field/NvdbRegularField.cpp:64-160: `gridData` is one serialized
+ * NanoVDB grid (the ANARI "nanovdb" field's UINT8 `data` array); GridType::Float only (the quantised
+ * Fp4/Fp8/Fp16/FpN types of sampleSpatialField.h:107-109 are not built yet -> DVR_ERR_UNSUPPORTED).  The
+ * buffer is copied to 32-byte aligned device memory; bounds = the grid's world bounding box, step =
+ * min(voxelSize)/2; macrocells cover the index bounding box. */
+int dvr_field_create_nanovdb(const void *gridData, size_t bytes, int dataIsDevice, void *stream, DvrField **out);
 int dvr_field_destroy(DvrField *f);
 /* SpatialField::bounds / stepSize, StructuredRegularField.cpp:166-178 */
 int dvr_field_bounds(const DvrField *f, float lower[3], float upper[3]);

@@ -152,10 +152,91 @@ inline void texAxis(float u, int N, int &i0, int &i1, int &k)
   i1 = std::min(i0 + 1, N - 1);
 }
 
+// ---- NanoVDB float grids: SpatialFieldSampler<nanovdb::Grid<NanoTree<float>>>, sampleSpatialField.h:80-109 ----
+// Restated against the published NanoVDB 32.7 binary layout (the reference's vendored headers are not
+// linked here; layout constants are static_assert-checked in oracle/ref_host/ref_host.cpp):
+//   GridData 672 B (Map at 296: mInvMatF +36, mVecF +72), TreeData 64 B (mNodeOffset[3] = root), RootData<float>
+//   64 B + 32-byte tiles {key u64, child i64, state u32, value f32}; upper 32^3 (child mask +4128, table +8256),
+//   lower 16^3 (child mask +544, table +1088), leaf 8^3 (values +96).
+struct Nvdb
+{
+  const uint8_t *root = nullptr;
+  uint32_t tiles = 0;
+  float background = 0.f;
+  float invMat[9], vec[3];
+
+  template <typename T>
+  static T rd(const uint8_t *p)
+  {
+    T v;
+    std::memcpy(&v, p, sizeof(T));
+    return v;
+  }
+  void open(const uint8_t *blob)
+  {
+    const int64_t rootOff = 672 + rd<int64_t>(blob + 672 + 24);
+    root = blob + rootOff;
+    tiles = rd<uint32_t>(root + 24);
+    background = rd<float>(root + 28);
+    for (int i = 0; i < 9; ++i)
+      invMat[i] = rd<float>(blob + 296 + 36 + 4 * i);
+    for (int i = 0; i < 3; ++i)
+      vec[i] = rd<float>(blob + 296 + 72 + 4 * i);
+  }
+  static bool maskOn(const uint8_t *mask, uint32_t n) { return (rd<uint64_t>(mask + 8 * (n >> 6)) >> (n & 63)) & 1; }
+  // Tree::getValue -> RootNode::getValue -> InternalNode::getValue -> LeafNode::getValue (NanoVDB.h:2947-2953,3528-3532)
+  float getValue(int x, int y, int z) const
+  {
+    const uint64_t key = (uint64_t)((uint32_t)z >> 12) | ((uint64_t)((uint32_t)y >> 12) << 21)
+        | ((uint64_t)((uint32_t)x >> 12) << 42);
+    const uint8_t *tile = nullptr;
+    for (uint32_t i = 0; i < tiles; ++i)
+      if (rd<uint64_t>(root + 64 + 32 * (size_t)i) == key) {
+        tile = root + 64 + 32 * (size_t)i;
+        break;
+      }
+    if (!tile)
+      return background;
+    const int64_t child = rd<int64_t>(tile + 8);
+    if (child == 0)
+      return rd<float>(tile + 20);
+    const uint8_t *upper = root + child;
+    uint32_t n = (uint32_t)((((x & 4095) >> 7) << 10) | (((y & 4095) >> 7) << 5) | ((z & 4095) >> 7));
+    if (!maskOn(upper + 32 + 4096, n))
+      return rd<float>(upper + 8256 + 8 * (size_t)n);
+    const uint8_t *lower = upper + rd<int64_t>(upper + 8256 + 8 * (size_t)n);
+    n = (uint32_t)((((x & 127) >> 3) << 8) | (((y & 127) >> 3) << 4) | ((z & 127) >> 3));
+    if (!maskOn(lower + 32 + 512, n))
+      return rd<float>(lower + 1088 + 8 * (size_t)n);
+    const uint8_t *leaf = lower + rd<int64_t>(lower + 1088 + 8 * (size_t)n);
+    return rd<float>(leaf + 96 + 4 * (size_t)(((x & 7) << 6) | ((y & 7) << 3) | (z & 7)));
+  }
+  // worldToIndexF(Vec3d) = matMult(mInvMatF, xyz - mVecF): subtraction in double, fmaf chain in float (Math.h:905-910)
+  float sample(V3 p) const
+  {
+    const float fx = (float)((double)p.x - (double)vec[0]), fy = (float)((double)p.y - (double)vec[1]),
+                fz = (float)((double)p.z - (double)vec[2]);
+    const float ix = std::fmaf(fx, invMat[0], std::fmaf(fy, invMat[1], fz * invMat[2]));
+    const float iy = std::fmaf(fx, invMat[3], std::fmaf(fy, invMat[4], fz * invMat[5]));
+    const float iz = std::fmaf(fx, invMat[6], std::fmaf(fy, invMat[7], fz * invMat[8]));
+    // SampleFromVoxels<Acc,1>: ijk = floor, uvw = xyz - ijk (double), lerp a + float(w)*(b-a), z innermost
+    const double dx = ix, dy = iy, dz = iz;
+    const int i = (int)std::floor(dx), j = (int)std::floor(dy), k = (int)std::floor(dz);
+    const float u = (float)(dx - i), v = (float)(dy - j), w = (float)(dz - k);
+    auto lerp = [](float a, float b, float t) { return a + t * (b - a); };
+    const float v000 = getValue(i, j, k), v001 = getValue(i, j, k + 1), v011 = getValue(i, j + 1, k + 1),
+                v010 = getValue(i, j + 1, k), v100 = getValue(i + 1, j, k), v101 = getValue(i + 1, j, k + 1),
+                v111 = getValue(i + 1, j + 1, k + 1), v110 = getValue(i + 1, j + 1, k);
+    return lerp(lerp(lerp(v000, v001, w), lerp(v010, v011, w), v), lerp(lerp(v100, v101, w), lerp(v110, v111, w), v), u);
+  }
+};
+
 struct Field
 {
   const float *vox;
   int nx, ny, nz;
+  Nvdb nvdb;
+  bool isNvdb = false;
   V3 origin, spacing, invSpacing, lo, hi;
   float stepSize;
   bool nearest;
@@ -203,6 +284,8 @@ struct Field
   // SpatialFieldSampler<cudaTextureObject_t>::operator(), sampleSpatialField.h:66-71
   float sample(V3 p) const
   {
+    if (isNvdb)
+      return nvdb.sample(p);
     const V3 tc = ((p - origin) + 0.5f * spacing) * invSpacing;
     return tex(tc.x, tc.y, tc.z);
   }
@@ -464,6 +547,13 @@ void accumResults(const Frame &f, uint32_t px, uint32_t py, const float color[4]
 
 extern "C" {
 
+float oracle_nvdb_sample(const void *grid, float x, float y, float z)
+{
+  Nvdb n;
+  n.open((const uint8_t *)grid);
+  return n.sample({x, y, z});
+}
+
 float oracle_tex3d(const float *voxels, const int dims[3], float u, float v, float w)
 {
   Field f{};
@@ -518,6 +608,17 @@ int oracle_render(const DvrFrameParams *params, const DvrCamera *camera, const O
         o.origin[2] + ((float)o.dims[2] - 1.f) * o.spacing[2]};
     v.f.stepSize = std::fmin(std::fmin(o.spacing[0] / 2.f, o.spacing[1] / 2.f), o.spacing[2] / 2.f);
     v.f.nearest = o.filterNearest != 0;
+    if (o.nvdbGrid) { // NvdbRegularField: bounds = world bbox, step = min(voxelSize)/2 (NvdbRegularField.cpp:105-127)
+      const uint8_t *blob = (const uint8_t *)o.nvdbGrid;
+      v.f.isNvdb = true;
+      v.f.nvdb.open(blob);
+      double wb[6], vs[3];
+      std::memcpy(wb, blob + 560, sizeof(wb));
+      std::memcpy(vs, blob + 608, sizeof(vs));
+      v.f.lo = {(float)wb[0], (float)wb[1], (float)wb[2]};
+      v.f.hi = {(float)wb[3], (float)wb[4], (float)wb[5]};
+      v.f.stepSize = std::fmin(std::fmin((float)vs[0], (float)vs[1]), (float)vs[2]) / 2.0f;
+    }
     v.tf = o.tf;
     v.vrLo = o.valueRange[0];
     v.vrHi = o.valueRange[1];

@@ -25,6 +25,7 @@ typedef struct OracleVolume
   float worldToObject[12];
   uint32_t instanceId;
   int32_t zOwnBegin, zOwnEnd; /* 0,0 = whole volume; otherwise only these cell slices are sampled */
+  const void *nvdbGrid;       /* non-NULL: a serialized NanoVDB float grid ("nanovdb" field); voxels/dims unused */
 } OracleVolume;
 
 typedef struct OracleBuffers
@@ -42,6 +43,7 @@ int oracle_camera_orthographic(const float pos[3], const float dir[3], const flo
     float aspect, const float region[4], DvrCamera *out);
 int oracle_tf_discretize(const float *color, size_t nColor, int colorChannels, const float *opacity,
     size_t nOpacity, const float uniformColor[4], float uniformOpacity, const float valueRange[2], float *outRgba);
+float oracle_nvdb_sample(const void *grid, float x, float y, float z);
 float oracle_tex3d(const float *voxels, const int dims[3], float u, float v, float w);
 void oracle_tex1d_tf(const float *tf, float coord, float out[4]);
 void oracle_philox_block(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]);

@@ -153,6 +153,7 @@ struct RefField
 {
   cudaArray_t arr = nullptr;
   cudaTextureObject_t tex = 0;
+  void *nvdb = nullptr;
   SpatialFieldGPUData gpu{};
   box3 bounds;
   float stepSize = 0.f;
@@ -224,11 +225,37 @@ int refgpu_field_create(const void *hostVoxels, int dataType, const uint32_t dim
   return 0;
 }
 
+// NvdbRegularField::finalize + gpuData (spatial_field/NvdbRegularField.cpp:64-143): one serialized grid
+int refgpu_field_create_nvdb(const void *hostBlob, size_t bytes, RefField **out)
+{
+  auto *f = new RefField();
+  const auto *meta = reinterpret_cast<const nanovdb::GridData *>(hostBlob);
+  if (!meta->isValid() || meta->mGridCount != 1) {
+    snprintf(g_err, sizeof(g_err), "invalid NanoVDB buffer");
+    return -1;
+  }
+  RCK(cudaMalloc(&f->nvdb, bytes));
+  RCK(cudaMemcpy(f->nvdb, hostBlob, bytes, cudaMemcpyHostToDevice));
+  const auto &wb = meta->mWorldBBox;
+  f->bounds = box3(vec3(wb.min()[0], wb.min()[1], wb.min()[2]), vec3(wb.max()[0], wb.max()[1], wb.max()[2]));
+  const vec3 voxelSize(meta->mVoxelSize[0], meta->mVoxelSize[1], meta->mVoxelSize[2]);
+  f->stepSize = glm::compMin(voxelSize) / 2.0f;
+  f->gpu.type = SpatialFieldType::NANOVDB_REGULAR;
+  f->gpu.data.nvdbRegular.voxelSize = voxelSize;
+  f->gpu.data.nvdbRegular.origin = f->bounds.lower;
+  f->gpu.data.nvdbRegular.gridData = f->nvdb;
+  f->gpu.data.nvdbRegular.gridType = meta->mGridType;
+  f->gpu.grid = UniformGridData{};
+  *out = f;
+  return 0;
+}
+
 int refgpu_field_destroy(RefField *f)
 {
   if (!f) return 0;
   if (f->tex) cudaDestroyTextureObject(f->tex);
   if (f->arr) cudaFreeArray(f->arr);
+  if (f->nvdb) cudaFree(f->nvdb);
   delete f;
   return 0;
 }

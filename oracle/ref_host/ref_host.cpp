@@ -51,3 +51,81 @@ extern "C" int refhost_position(float v, float lo, float hi, float *out)
   *out = position(v, box1(lo, hi));
   return 0;
 }
+
+// ---- NanoVDB (vendored with the reference, external/nanovdb 32.7.0) ---------------------------------------
+// Synthetic fog-sphere grids for the NanoVDB sampler tests (BASELINE config C5), plus compile-time checks
+// of the binary layout the product's own tree reader (visrtx_b200/csrc/dvr_nanovdb.cuh) assumes.
+#include <nanovdb/NanoVDB.h>
+#include <nanovdb/tools/CreatePrimitives.h>
+#include <nanovdb/math/SampleFromVoxels.h>
+#include <cstring>
+
+namespace {
+using LeafF = nanovdb::NanoLeaf<float>;
+using LowerF = nanovdb::NanoLower<float>;
+using UpperF = nanovdb::NanoUpper<float>;
+using RootF = nanovdb::NanoRoot<float>;
+static_assert(sizeof(nanovdb::GridData) == 672, "GridData");
+static_assert(sizeof(nanovdb::TreeData) == 64, "TreeData");
+static_assert(offsetof(nanovdb::GridData, mMap) == 296, "mMap");
+static_assert(offsetof(nanovdb::GridData, mWorldBBox) == 560, "mWorldBBox");
+static_assert(offsetof(nanovdb::GridData, mVoxelSize) == 608, "mVoxelSize");
+static_assert(offsetof(nanovdb::GridData, mGridType) == 636, "mGridType");
+static_assert(offsetof(nanovdb::Map, mInvMatF) == 36 && offsetof(nanovdb::Map, mVecF) == 72, "Map");
+static_assert(sizeof(RootF::DataType) == 64, "RootData<float>");
+static_assert(sizeof(RootF::DataType::Tile) == 32, "Root tile");
+static_assert(sizeof(UpperF::DataType) == 270400, "upper node");
+static_assert(sizeof(LowerF::DataType) == 33856, "lower node");
+static_assert(sizeof(LeafF::DataType) == 2144, "leaf node");
+static_assert(offsetof(UpperF::DataType, mTable) == 8256, "upper table");
+static_assert(offsetof(UpperF::DataType, mChildMask) == 32 + 4096, "upper child mask");
+static_assert(offsetof(LowerF::DataType, mTable) == 1088, "lower table");
+static_assert(offsetof(LowerF::DataType, mChildMask) == 32 + 512, "lower child mask");
+static_assert(offsetof(LeafF::DataType, mValues) == 96, "leaf values");
+#ifndef NANOVDB_USE_SINGLE_ROOT_KEY
+#error "the product's reader assumes 64-bit root keys"
+#endif
+} // namespace
+
+// returns the byte size; copies min(size, capacity) bytes of the grid buffer into out (may be NULL to query)
+extern "C" size_t refhost_nvdb_fog_sphere(double radius, double voxelSize, double halfWidth, const double center[3],
+    void *out, size_t capacity)
+{
+  auto h = nanovdb::tools::createFogVolumeSphere<float>(
+      radius, nanovdb::Vec3d(center[0], center[1], center[2]), voxelSize, halfWidth);
+  const size_t n = h.size();
+  if (out)
+    std::memcpy(out, h.data(), n < capacity ? n : capacity);
+  return n;
+}
+
+// the reference's own sampler on the host (sampleSpatialField.h:80-109 uses exactly these calls)
+extern "C" int refhost_nvdb_sample(const void *gridBlob, const float *xyzWorld, int n, float *out)
+{
+  const auto *grid = reinterpret_cast<const nanovdb::NanoGrid<float> *>(gridBlob);
+  auto acc = grid->getAccessor();
+  auto sampler = nanovdb::math::createSampler<1>(acc);
+  for (int i = 0; i < n; ++i) {
+    const auto loc = nanovdb::Vec3d(xyzWorld[3 * i], xyzWorld[3 * i + 1], xyzWorld[3 * i + 2]);
+    out[i] = sampler(nanovdb::math::Vec3d(grid->worldToIndexF(loc)));
+  }
+  return 0;
+}
+
+extern "C" int refhost_nvdb_info(const void *gridBlob, double worldBBox[6], double voxelSize[3], int indexBBox[6],
+    unsigned *gridType, unsigned long long *activeVoxels)
+{
+  const auto *grid = reinterpret_cast<const nanovdb::NanoGrid<float> *>(gridBlob);
+  const auto wb = grid->worldBBox();
+  const auto ib = grid->indexBBox();
+  for (int i = 0; i < 3; ++i) {
+    worldBBox[i] = wb.min()[i];
+    worldBBox[3 + i] = wb.max()[i];
+    voxelSize[i] = grid->voxelSize()[i];
+    indexBBox[i] = ib.min()[i];
+    indexBBox[3 + i] = ib.max()[i];
+  }
+  *gridType = (unsigned)grid->gridType();
+  *activeVoxels = grid->activeVoxelCount();
+  return 0;
+}

@@ -51,6 +51,7 @@ class VolumeDesc:
     vol_id: int = 0xFFFFFFFF
     inst_id: int = 0xFFFFFFFF
     world_to_object: Optional[tuple] = None
+    nvdb: Optional[np.ndarray] = None  # serialized NanoVDB float grid (uint8): the field is a "nanovdb" field
 
     @property
     def dims(self):
@@ -58,6 +59,9 @@ class VolumeDesc:
         return (nx, ny, nz)
 
     def bounds(self):
+        if self.nvdb is not None:
+            wb = self.nvdb[560:608].view(np.float64)
+            return wb[:3].astype(np.float32), wb[3:].astype(np.float32)
         lo = np.asarray(self.origin, dtype=np.float32)
         hi = lo + (np.asarray(self.dims, dtype=np.float32) - np.float32(1.0)) * np.asarray(self.spacing, np.float32)
         return lo, hi
@@ -119,6 +123,10 @@ def render_oracle(scene: SceneDesc, frames=1, checkerboard=False, slab=None, sta
         tf = np.ascontiguousarray(v.tf, np.float32)
         keep += [f32, tf]
         o = vols[i]
+        if v.nvdb is not None:
+            blob = np.ascontiguousarray(v.nvdb)
+            keep.append(blob)
+            o.nvdbGrid = blob.ctypes.data_as(C.c_void_p)
         o.voxels = f32.ctypes.data_as(C.c_void_p)
         o.dims = (C.c_int32 * 3)(*v.dims)
         o.origin = (C.c_float * 3)(*v.origin)
@@ -181,7 +189,10 @@ class CudaScene:
         for v in scene.volumes:
             vox = np.ascontiguousarray(v.voxels.astype(_NP_TYPES[v.data_type], copy=False))
             filt = capi.DVR_FILTER_NEAREST if v.nearest else capi.DVR_FILTER_LINEAR
-            if slab is None:
+            if v.nvdb is not None:
+                blob = np.ascontiguousarray(v.nvdb)
+                f = capi.Field.create_nanovdb(blob.ctypes.data, blob.nbytes, False)
+            elif slab is None:
                 f = capi.Field.create_structured(vox.ctypes.data, False, v.data_type, v.dims, v.origin, v.spacing, filt)
             else:
                 zb, ze = slab
@@ -259,9 +270,14 @@ def render_refgpu(scene: SceneDesc, frames=1, checkerboard=False):
         vox = np.ascontiguousarray(v.voxels.astype(_NP_TYPES[v.data_type], copy=False))
         keep.append(vox)
         f = C.c_void_p()
-        rc = lib.refgpu_field_create(vox.ctypes.data_as(C.c_void_p), C.c_int(v.data_type), (C.c_uint32 * 3)(*v.dims),
-                                     (C.c_float * 3)(*v.origin), (C.c_float * 3)(*v.spacing),
-                                     C.c_int(1 if v.nearest else 0), C.byref(f))
+        if v.nvdb is not None:
+            blob = np.ascontiguousarray(v.nvdb)
+            keep.append(blob)
+            rc = lib.refgpu_field_create_nvdb(blob.ctypes.data_as(C.c_void_p), C.c_size_t(blob.nbytes), C.byref(f))
+        else:
+            rc = lib.refgpu_field_create(vox.ctypes.data_as(C.c_void_p), C.c_int(v.data_type),
+                                         (C.c_uint32 * 3)(*v.dims), (C.c_float * 3)(*v.origin),
+                                         (C.c_float * 3)(*v.spacing), C.c_int(1 if v.nearest else 0), C.byref(f))
         assert rc == 0, lib.refgpu_last_error()
         tf = np.ascontiguousarray(v.tf, np.float32)
         h = C.c_void_p()
@@ -400,6 +416,17 @@ def scene_zoo():
                                        region=(0.1, 0.2, 0.8, 0.9))
     s.volumes[0].unit_distance = 1.0
     zoo["camera_inside_region"] = (s, 1, False)
+    # NanoVDB fog spheres (BASELINE config C5, small): committed fixture generated with the reference's NanoVDB
+    import os
+    fog = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "nvdb_fog_spheres.npz"))
+    for key, ud, rate in (("r20", 4.0, 0.5), ("r12_vs025", 1.0, 1.0)):
+        v = VolumeDesc(np.zeros((1, 1, 1), np.float32), nvdb=fog[key], tf=capi.tf_discretize(
+            color=scenes.tsd_default_colormap(256)), unit_distance=ud, vol_id=31, inst_id=2)
+        lo, hi = v.bounds()
+        pose = scenes.orbit_camera(lo, hi, W, H, dist_scale=1.0)
+        cam = capi.camera_perspective(pose.position, pose.direction, pose.up, pose.fovy, pose.aspect)
+        zoo[f"nvdb_fog_{key}"] = (SceneDesc([v], W, H, cam, volume_sampling_rate=rate,
+                                            integrator=capi.DVR_INTEGRATOR_DEFAULT), 2, False)
     # empty world (no volume instance): background only
     s = default_scene(8, 40, 24, rate=0.5)
     s.volumes = []

@@ -25,7 +25,7 @@ class OracleVolume(C.Structure):
                 ("spacing", C.c_float * 3), ("filterNearest", C.c_int32), ("tf", C.c_void_p),
                 ("valueRange", C.c_float * 2), ("unitDistance", C.c_float), ("id", C.c_uint32),
                 ("worldToObject", C.c_float * 12), ("instanceId", C.c_uint32), ("zOwnBegin", C.c_int32),
-                ("zOwnEnd", C.c_int32)]
+                ("zOwnEnd", C.c_int32), ("nvdbGrid", C.c_void_p)]
 
 
 class OracleBuffers(C.Structure):
@@ -49,6 +49,7 @@ def cpu():
     if _cpu is None:
         _cpu = C.CDLL(CPU_LIB)
         _cpu.oracle_tex3d.restype = C.c_float
+        _cpu.oracle_nvdb_sample.restype = C.c_float
     return _cpu
 
 
@@ -146,3 +147,30 @@ def philox_uniforms(seed: int, offset: int, n: int) -> np.ndarray:
     out = np.empty(n, dtype=np.float32)
     cpu().oracle_philox_uniforms(C.c_uint64(seed), C.c_uint64(offset), C.c_int(n), out.ctypes.data_as(C.c_void_p))
     return out
+
+
+def nvdb_fog_sphere(radius=20.0, voxel_size=1.0, half_width=3.0, center=(0.0, 0.0, 0.0)) -> np.ndarray:
+    """A serialized NanoVDB float fog-sphere grid from the reference's vendored NanoVDB (needs libref_host.so)."""
+    lib = refhost()
+    lib.refhost_nvdb_fog_sphere.restype = C.c_size_t
+    ctr = (C.c_double * 3)(*center)
+    n = lib.refhost_nvdb_fog_sphere(C.c_double(radius), C.c_double(voxel_size), C.c_double(half_width), ctr, None,
+                                    C.c_size_t(0))
+    buf = np.zeros(n, np.uint8)
+    lib.refhost_nvdb_fog_sphere(C.c_double(radius), C.c_double(voxel_size), C.c_double(half_width), ctr,
+                                buf.ctypes.data_as(C.c_void_p), C.c_size_t(n))
+    return buf
+
+
+def nvdb_sample_reference(blob: np.ndarray, xyz: np.ndarray) -> np.ndarray:
+    xyz = np.ascontiguousarray(xyz, np.float32)
+    out = np.empty(len(xyz), np.float32)
+    refhost().refhost_nvdb_sample(blob.ctypes.data_as(C.c_void_p), xyz.ctypes.data_as(C.c_void_p), C.c_int(len(xyz)),
+                                  out.ctypes.data_as(C.c_void_p))
+    return out
+
+
+def nvdb_sample_oracle(blob: np.ndarray, xyz: np.ndarray) -> np.ndarray:
+    lib = cpu()
+    p = blob.ctypes.data_as(C.c_void_p)
+    return np.array([lib.oracle_nvdb_sample(p, C.c_float(a), C.c_float(b), C.c_float(c)) for a, b, c in xyz], np.float32)

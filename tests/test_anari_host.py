@@ -47,7 +47,7 @@ def test_direct_device_construction():
 def test_object_subtypes_introspection():
     d = A.Device()
     assert d.subtypes(A.CAMERA) == ["perspective", "orthographic"]
-    assert d.subtypes(A.SPATIAL_FIELD) == ["structuredRegular"]
+    assert d.subtypes(A.SPATIAL_FIELD) == ["structuredRegular", "nanovdb"]
     assert "transferFunction1D" in d.subtypes(A.VOLUME) and "scivis" in d.subtypes(A.VOLUME)
     assert {"default", "raycast"} <= set(d.subtypes(A.RENDERER))
     assert d.subtypes(A.WORLD) == []

@@ -277,3 +277,62 @@ def test_field_value_range_property_and_float16_extension():
     s.render()
     assert not _errors(s.d)
     s.close()
+
+
+def test_nanovdb_field_through_anari_matches_cabi():
+    """anariNewSpatialField("nanovdb") with a UINT8 Array1D holding one serialized grid (NvdbRegularField)."""
+    import os
+    fog = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "nvdb_fog_spheres.npz"))
+    blob = np.ascontiguousarray(fog["r20"])
+    scene, frames, _ = H.scene_zoo()["nvdb_fog_r20"]
+    scene.volumes[0].inst_id = 0xFFFFFFFF
+    want = H.render_cuda(scene, frames=1)
+    d = A.Device()
+    data = d.new_array1d(blob, A.UINT8)
+    field = d.new("SpatialField", "nanovdb")
+    d.set(field, "data", A.ARRAY1D, data)
+    d.commit(field)
+    vol = d.new("Volume", "transferFunction1D")
+    col = d.new_array1d(scenes.tsd_default_colormap(256), A.FLOAT32_VEC4)
+    d.set(vol, "color", A.ARRAY1D, col)
+    d.set(vol, "value", A.SPATIAL_FIELD, field)
+    d.set(vol, "unitDistance", A.FLOAT32, 4.0)
+    d.set(vol, "id", A.UINT32, 31)
+    d.commit(vol)
+    world = d.new("World")
+    vols = d.new_object_array([vol], A.VOLUME)
+    d.set(world, "volume", A.ARRAY1D, vols)
+    d.commit(world)
+    b = d.get_property(world, "bounds", A.FLOAT32_BOX3)
+    assert b == (-20.0, -20.0, -20.0, 21.0, 21.0, 21.0)
+    pose = scenes.orbit_camera(b[:3], b[3:], scene.width, scene.height, dist_scale=1.0)
+    cam = d.new("Camera", "perspective")
+    for k, t, v in (("position", A.FLOAT32_VEC3, pose.position), ("direction", A.FLOAT32_VEC3, pose.direction),
+                    ("up", A.FLOAT32_VEC3, pose.up), ("fovy", A.FLOAT32, pose.fovy), ("aspect", A.FLOAT32, pose.aspect)):
+        d.set(cam, k, t, v)
+    d.commit(cam)
+    ren = d.new("Renderer", "default")
+    d.set(ren, "background", A.FLOAT32_VEC4, (0.1, 0.1, 0.1, 1.0))
+    d.set(ren, "volumeSamplingRate", A.FLOAT32, 0.5)
+    d.commit(ren)
+    frame = d.new("Frame")
+    d.set(frame, "size", A.UINT32_VEC2, (scene.width, scene.height))
+    d.set(frame, "channel.color", A.DATA_TYPE, A.UFIXED8_RGBA_SRGB)
+    d.set(frame, "channel.depth", A.DATA_TYPE, A.FLOAT32)
+    for k, t, o in (("renderer", A.RENDERER, ren), ("camera", A.CAMERA, cam), ("world", A.WORLD, world)):
+        d.set(frame, k, t, o)
+    d.commit(frame)
+    d.render(frame)
+    d.wait(frame)
+    color, _, _, _ = d.map_frame(frame, "channel.color")
+    assert not _errors(d), d.messages
+    assert np.array_equal(color, want["color"])
+    # a non-float grid type is refused with a warning, not a crash
+    bad = blob.copy()
+    bad[636:640] = np.frombuffer(np.uint32(15).tobytes(), np.uint8)  # GridType::Fp16
+    f2 = d.new("SpatialField", "nanovdb")
+    d.set(f2, "data", A.ARRAY1D, d.new_array1d(bad, A.UINT8))
+    d.commit(f2)
+    d.render(frame)
+    assert any("only GridType::Float" in m[2] for m in d.messages)
+    d.close()

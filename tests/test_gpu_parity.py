@@ -58,7 +58,8 @@ def test_cuda_matches_oracle_cpu(name):
     _check(got, want, scene, frames, name=name)
 
 
-@pytest.mark.parametrize("name", ["ml48_raycast_r0.5", "two_volumes_lens", "ml32_checkerboard_p6", "blobs32_u16"])
+@pytest.mark.parametrize("name", ["ml48_raycast_r0.5", "two_volumes_lens", "ml32_checkerboard_p6", "blobs32_u16",
+                                  "nvdb_fog_r20"])
 def test_cuda_matches_reference_device_code_live(name):
     if not ob.have_ref_gpu():
         pytest.skip("oracle/_ref/libref_gpu_dvr.so not present")
@@ -67,8 +68,8 @@ def test_cuda_matches_reference_device_code_live(name):
     want = H.render_refgpu(scene, frames=frames, checkerboard=cb)
     _check(got, want, scene, frames, strict=True, name=name)
     # most pixels agree to the last bit of the float accumulation buffer
-    # (the thin-lens + instance-transform scene has more places where FMA contraction may differ)
-    assert (got["accum"] == want["accum"]).all(axis=-1).mean() > (0.8 if name == "two_volumes_lens" else 0.9)
+    # (the thin-lens + instance-transform and the NanoVDB scenes have more places where FMA contraction may differ)
+    assert (got["accum"] == want["accum"]).all(axis=-1).mean() > (0.8 if name in ("two_volumes_lens", "nvdb_fog_r20") else 0.9)
 
 
 def test_config_c1_full_size():
@@ -81,7 +82,8 @@ def test_config_c1_full_size():
         _check(got, H.render_refgpu(scene), scene, strict=True, name="C1/O-gpu")
 
 
-@pytest.mark.parametrize("name", ["ml48_raycast_r1.0", "blobs48_translucent", "two_volumes_lens", "blobs32_u8"])
+@pytest.mark.parametrize("name", ["ml48_raycast_r1.0", "blobs48_translucent", "two_volumes_lens", "blobs32_u8",
+                                  "nvdb_fog_r20", "nvdb_fog_r12_vs025"])
 def test_macrocell_skipping_is_bit_identical(name):
     scene, frames, cb = ZOO[name]
     if name.startswith("blobs"):

@@ -28,7 +28,8 @@ DVR_INTEGRATOR_RAYCAST, DVR_INTEGRATOR_DEFAULT = 0, 1
 EXPORTED_SYMBOLS = [
     "dvr_last_error", "dvr_version", "dvr_device_count", "dvr_set_device", "dvr_device_info",
     "dvr_camera_perspective", "dvr_camera_orthographic", "dvr_tf_discretize",
-    "dvr_field_create_structured", "dvr_field_create_structured_slab", "dvr_field_upload_slices", "dvr_field_destroy",
+    "dvr_field_create_structured", "dvr_field_create_structured_slab", "dvr_field_upload_slices", "dvr_field_create_nanovdb",
+    "dvr_field_destroy",
     "dvr_field_bounds", "dvr_field_step_size", "dvr_field_device_bytes", "dvr_field_build_macrocells",
     "dvr_field_macrocells", "dvr_field_value_range",
     "dvr_volume_create", "dvr_volume_update", "dvr_volume_destroy", "dvr_volume_majorants",
@@ -208,6 +209,13 @@ class Field:
                                                     C.c_int(data_type), _u3(*global_dims), C.c_uint32(z_begin),
                                                     C.c_uint32(z_end), _f3(*origin), _f3(*spacing),
                                                     C.c_int(filter_mode), C.c_void_p(stream), C.byref(h)))
+        return Field(h)
+
+    @staticmethod
+    def create_nanovdb(data_ptr: int, nbytes: int, is_device: bool = False, stream: int = 0) -> "Field":
+        h = C.c_void_p()
+        _check(lib.dvr_field_create_nanovdb(C.c_void_p(data_ptr), C.c_size_t(nbytes), C.c_int(1 if is_device else 0),
+                                            C.c_void_p(stream), C.byref(h)))
         return Field(h)
 
     def upload_slices(self, data_ptr: int, is_device: bool, first_resident_slice: int, n_slices: int,

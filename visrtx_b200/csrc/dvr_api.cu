@@ -91,6 +91,7 @@ struct DvrField
   size_t nCells = 0;
   size_t voxelBytes = 0;
   size_t texElementSize = 0;
+  void *nvdbBlob = nullptr; // NanoVDB fields: device copy of the serialized grid
   int device = 0;
 };
 
@@ -509,10 +510,136 @@ int dvr_field_create_structured_slab(const void *data, int dataIsDevice, int dat
   return createFieldImpl(data, dataIsDevice, dataType, globalDims, zBegin, zEnd, origin, spacing, filter, stream, out);
 }
 
+// ---- NanoVDB ---------------------------------------------------------------------------------------------
+extern "C++" {
+namespace {
+template <typename T>
+T rd(const uint8_t *p, size_t off)
+{
+  T v;
+  std::memcpy(&v, p + off, sizeof(T));
+  return v;
+}
+} // namespace
+}
+
+int dvr_field_create_nanovdb(const void *gridData, size_t bytes, int dataIsDevice, void *stream, DvrField **out)
+{
+  if (!gridData || !out || bytes < 672 + 64 + 64) {
+    setError("dvr_field_create_nanovdb: null argument or buffer smaller than a NanoVDB grid header");
+    return DVR_ERR_INVALID_ARGUMENT;
+  }
+  if (dvr_device_count() <= 0) {
+    setError("dvr_field_create_nanovdb: no CUDA device (this library has no CPU fallback)");
+    return DVR_ERR_NO_DEVICE;
+  }
+  cudaStream_t s = (cudaStream_t)stream;
+  // header to the host: GridData (672 B) + TreeData (64 B)
+  uint8_t head[736];
+  if (dataIsDevice)
+    DVR_CUDA(cudaMemcpy(head, gridData, sizeof(head), cudaMemcpyDeviceToHost));
+  else
+    std::memcpy(head, gridData, sizeof(head));
+  const uint64_t magic = rd<uint64_t>(head, 0);
+  const uint64_t kMagicNumb = 0x304244566f6e614eull, kMagicGrid = 0x314244566f6e614eull;
+  if (magic != kMagicNumb && magic != kMagicGrid) {
+    setError("dvr_field_create_nanovdb: not a NanoVDB grid buffer (bad magic)");
+    return DVR_ERR_INVALID_ARGUMENT;
+  }
+  if (rd<uint32_t>(head, 28) != 1u) {
+    setError("dvr_field_create_nanovdb: the buffer must hold a single grid (NvdbRegularField.cpp:99-103)");
+    return DVR_ERR_INVALID_ARGUMENT;
+  }
+  const uint64_t gridSize = rd<uint64_t>(head, 32);
+  if (gridSize > bytes) {
+    setError("dvr_field_create_nanovdb: grid size exceeds the buffer");
+    return DVR_ERR_INVALID_ARGUMENT;
+  }
+  const uint32_t gridType = rd<uint32_t>(head, 636);
+  if (gridType != 1u) { // nanovdb::GridType::Float
+    setError("dvr_field_create_nanovdb: only GridType::Float grids are supported (Fp4/Fp8/Fp16/FpN are not built yet)");
+    return DVR_ERR_UNSUPPORTED;
+  }
+  const int64_t rootOff = 672 + rd<int64_t>(head, 672 + 24); // TreeData::mNodeOffset[3]
+  if (rootOff < 736 || (uint64_t)rootOff + 64 > gridSize) {
+    setError("dvr_field_create_nanovdb: corrupt tree offsets");
+    return DVR_ERR_INVALID_ARGUMENT;
+  }
+  uint8_t root[64];
+  if (dataIsDevice)
+    DVR_CUDA(cudaMemcpy(root, (const uint8_t *)gridData + rootOff, sizeof(root), cudaMemcpyDeviceToHost));
+  else
+    std::memcpy(root, (const uint8_t *)gridData + rootOff, sizeof(root));
+
+  auto *f = new DvrField();
+  cudaGetDevice(&f->device);
+  cudaError_t e = cudaMalloc(&f->nvdbBlob, gridSize);
+  if (e != cudaSuccess) {
+    delete f;
+    return cudaFail(e, "cudaMalloc(nanovdb grid)");
+  }
+  e = cudaMemcpyAsync(f->nvdbBlob, gridData, gridSize, dataIsDevice ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, s);
+  if (e == cudaSuccess && !dataIsDevice)
+    e = cudaStreamSynchronize(s);
+  if (e != cudaSuccess) {
+    dvr_field_destroy(f);
+    return cudaFail(e, "cudaMemcpy(nanovdb grid)");
+  }
+  f->voxelBytes = gridSize;
+
+  FieldDev &d = f->dev;
+  std::memset(&d, 0, sizeof(d));
+  d.kind = FIELD_NANOVDB;
+  d.nv.root = (const uint8_t *)f->nvdbBlob + rootOff;
+  d.nv.tileCount = rd<uint32_t>(root, 24);
+  d.nv.background = rd<float>(root, 28);
+  for (int i = 0; i < 9; ++i)
+    d.nv.invMat[i] = rd<float>(head, 296 + 36 + 4 * i);
+  for (int i = 0; i < 3; ++i)
+    d.nv.vec[i] = rd<float>(head, 296 + 72 + 4 * i);
+  const int bmin[3] = {rd<int32_t>(root, 0), rd<int32_t>(root, 4), rd<int32_t>(root, 8)};
+  const int bmax[3] = {rd<int32_t>(root, 12), rd<int32_t>(root, 16), rd<int32_t>(root, 20)};
+  d.nv.bboxMin = make_int3(bmin[0], bmin[1], bmin[2]);
+  d.dims = make_int3(std::max(bmax[0] - bmin[0] + 1, 1), std::max(bmax[1] - bmin[1] + 1, 1),
+      std::max(bmax[2] - bmin[2] + 1, 1));
+  // bounds = worldBBox, voxelSize -> step (NvdbRegularField.cpp:105-113,124-127)
+  double wb[6], vs[3];
+  for (int i = 0; i < 6; ++i)
+    wb[i] = rd<double>(head, 560 + 8 * i);
+  for (int i = 0; i < 3; ++i)
+    vs[i] = rd<double>(head, 608 + 8 * i);
+  d.boundsLo = make_float3((float)wb[0], (float)wb[1], (float)wb[2]);
+  d.boundsHi = make_float3((float)wb[3], (float)wb[4], (float)wb[5]);
+  d.origin = d.boundsLo;
+  d.spacing = make_float3((float)vs[0], (float)vs[1], (float)vs[2]);
+  d.invSpacing = make_float3(1.f / d.spacing.x, 1.f / d.spacing.y, 1.f / d.spacing.z);
+  d.stepSize = std::fmin(std::fmin(d.spacing.x, d.spacing.y), d.spacing.z) / 2.0f;
+  d.zOwnBegin = 0;
+  d.zOwnEnd = d.dims.z;
+  d.zTexBegin = 0;
+  d.texDepth = d.dims.z;
+  d.gridDims = make_int3((d.dims.x + 15) / 16, (d.dims.y + 15) / 16, (d.dims.z + 15) / 16);
+  f->nCells = (size_t)d.gridDims.x * d.gridDims.y * d.gridDims.z;
+  e = cudaMalloc(&f->ranges, f->nCells * sizeof(float2));
+  if (e != cudaSuccess) {
+    dvr_field_destroy(f);
+    return cudaFail(e, "cudaMalloc(macrocell ranges)");
+  }
+  d.valueRanges = f->ranges;
+  const int rc = dvr_field_build_macrocells(f, stream);
+  if (rc != DVR_OK) {
+    dvr_field_destroy(f);
+    return rc;
+  }
+  *out = f;
+  return DVR_OK;
+}
+
 int dvr_field_upload_slices(DvrField *f, const void *data, int dataIsDevice, uint32_t firstResidentSlice,
     uint32_t nSlices, void *stream)
 {
-  if (!f || !data || nSlices == 0 || firstResidentSlice + nSlices > (uint32_t)f->dev.texDepth) {
+  if (!f || f->dev.kind != FIELD_STRUCTURED || !data || nSlices == 0
+      || firstResidentSlice + nSlices > (uint32_t)f->dev.texDepth) {
     setError("dvr_field_upload_slices: bad argument / slice range");
     return DVR_ERR_INVALID_ARGUMENT;
   }
@@ -538,6 +665,7 @@ int dvr_field_destroy(DvrField *f)
   if (f->pointTex) cudaDestroyTextureObject(f->pointTex);
   if (f->array) cudaFreeArray(f->array);
   if (f->ranges) cudaFree(f->ranges);
+  if (f->nvdbBlob) cudaFree(f->nvdbBlob);
   delete f;
   return DVR_OK;
 }
@@ -579,6 +707,8 @@ int dvr_field_build_macrocells(DvrField *f, void *stream)
     setError("dvr_field_build_macrocells: null field");
     return DVR_ERR_INVALID_ARGUMENT;
   }
+  if (f->dev.kind == FIELD_NANOVDB)
+    return launchMacrocellBuildNvdb(f->dev, f->ranges, (cudaStream_t)stream);
   return launchMacrocellBuild(
       f->pointTex, f->dev.dims, f->dev.zTexBegin, f->dev.texDepth, f->dev.gridDims, f->ranges, (cudaStream_t)stream);
 }

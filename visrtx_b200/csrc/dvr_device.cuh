@@ -9,7 +9,15 @@
 #include <stdint.h>
 #include <float.h>
 
+#include "dvr_nanovdb.cuh"
+
 namespace dvr {
+
+enum FieldKind : int
+{
+  FIELD_STRUCTURED = 0, // 3-D array texture (structuredRegular)
+  FIELD_NANOVDB = 1     // NanoVDB float grid in linear device memory ("nanovdb")
+};
 
 // ---------------------------------------------------------------------------------------
 // POD descriptions of the scene as the kernels see it
@@ -32,6 +40,9 @@ struct FieldDev
   // macrocells (16^3 voxels), x-fastest
   int3 gridDims;
   const float2 *valueRanges; // (min,max) of every value a fetch inside the cell can return
+  // NanoVDB fields: dims = extent of the index bounding box, voxel coordinate = index - nv.bboxMin
+  int kind;
+  NvdbDev nv;
 };
 
 struct VolumeDev

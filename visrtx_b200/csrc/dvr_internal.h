@@ -124,6 +124,7 @@ int launchWaitFlags(const unsigned int *flags, uint32_t n, uint32_t value, unsig
 int launchScaleVec3(const float *in, float *out, size_t n, float scale, cudaStream_t s);
 int launchMacrocellBuild(cudaTextureObject_t pointTex, int3 dims, int zTexBegin, int texDepth, int3 gridDims,
     float2 *ranges, cudaStream_t s);
+int launchMacrocellBuildNvdb(const FieldDev &f, float2 *ranges, cudaStream_t s);
 int launchMajorants(const float2 *ranges, size_t nCells, const float4 *tf, float vrLo, float vrHi,
     float *maxOpacities, cudaStream_t s);
 int launchMajorantsCoarse(const float *fine, int3 gridDims, float *coarse, int3 coarseDims, cudaStream_t s);

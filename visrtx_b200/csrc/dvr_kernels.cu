@@ -223,7 +223,8 @@ struct TfSelectSingle
 #define DVR_OCC 2 // minimum resident CTAs per SM the frame kernel is compiled for (register budget)
 #endif
 
-template <bool SKIP, bool STATS, bool SINGLE>
+// KIND: FIELD_STRUCTURED / FIELD_NANOVDB for the single-volume kernels, -1 for the multi-volume kernel
+template <bool SKIP, bool STATS, bool SINGLE, int KIND>
 __global__ void __launch_bounds__(kBlockThreads, DVR_OCC) dvrFrameKernel(const __grid_constant__ FrameLaunch P)
 {
   __shared__ float4 s_tf[(SINGLE ? 1 : kMaxInlineInstances) * DVR_TF_SIZE];
@@ -279,10 +280,10 @@ __global__ void __launch_bounds__(kBlockThreads, DVR_OCC) dvrFrameKernel(const _
       bool anyHit = false;
       float volumeDepth;
       if (SINGLE)
-        volumeDepth = rayMarchAllVolumes<SKIP, false, STATS, true>(P.inl, 1, TfSelectSingle{s_tf}, org, dir, FLT_MAX,
+        volumeDepth = rayMarchAllVolumes<SKIP, false, STATS, true, KIND>(P.inl, 1, TfSelectSingle{s_tf}, org, dir, FLT_MAX,
             P.invSamplingRate, rng, color, opacity, objID, instID, st, P.cellBitmap, anyHit);
       else
-        volumeDepth = rayMarchAllVolumes<SKIP, false, STATS, false>(inst, nInst, TfSelectShared{s_tf, inst}, org, dir,
+        volumeDepth = rayMarchAllVolumes<SKIP, false, STATS, false, -1>(inst, nInst, TfSelectShared{s_tf, inst}, org, dir,
             FLT_MAX, P.invSamplingRate, rng, color, opacity, objID, instID, st, P.cellBitmap, anyHit);
       if (STATS && anyHit)
         raysHit++;
@@ -313,13 +314,13 @@ __global__ void __launch_bounds__(kBlockThreads, DVR_OCC) dvrFrameKernel(const _
   retireWarp(P.sched, lane);
 }
 
-template <bool SKIP, bool STATS, bool SINGLE>
+template <bool SKIP, bool STATS, bool SINGLE, int KIND>
 static int launchFrameT(const FrameLaunch &p, cudaStream_t s)
 {
   static int blocksPerSm = 0;
   if (blocksPerSm == 0) {
     DVR_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(
-        &blocksPerSm, dvrFrameKernel<SKIP, STATS, SINGLE>, kBlockThreads, 0));
+        &blocksPerSm, dvrFrameKernel<SKIP, STATS, SINGLE, KIND>, kBlockThreads, 0));
     if (blocksPerSm < 1)
       blocksPerSm = 1;
   }
@@ -331,23 +332,27 @@ static int launchFrameT(const FrameLaunch &p, cudaStream_t s)
     grid = need;
   if (grid == 0)
     grid = 1;
-  dvrFrameKernel<SKIP, STATS, SINGLE><<<grid, kBlockThreads, 0, s>>>(p);
+  dvrFrameKernel<SKIP, STATS, SINGLE, KIND><<<grid, kBlockThreads, 0, s>>>(p);
   DVR_CUDA(cudaGetLastError());
   countLaunch();
   return DVR_OK;
 }
 
+template <bool SKIP, bool STATS>
+static int launchFrameK(const FrameLaunch &p, cudaStream_t s)
+{
+  if (p.nInst != 1)
+    return launchFrameT<SKIP, STATS, false, -1>(p, s);
+  if (p.inl[0].v.f.kind == FIELD_NANOVDB)
+    return launchFrameT<SKIP, STATS, true, FIELD_NANOVDB>(p, s);
+  return launchFrameT<SKIP, STATS, true, FIELD_STRUCTURED>(p, s);
+}
+
 int launchFrame(const FrameLaunch &p, bool skip, bool stats, cudaStream_t s)
 {
-  const bool single = p.nInst == 1;
-  if (stats) {
-    if (skip)
-      return single ? launchFrameT<true, true, true>(p, s) : launchFrameT<true, true, false>(p, s);
-    return single ? launchFrameT<false, true, true>(p, s) : launchFrameT<false, true, false>(p, s);
-  }
-  if (skip)
-    return single ? launchFrameT<true, false, true>(p, s) : launchFrameT<true, false, false>(p, s);
-  return single ? launchFrameT<false, false, true>(p, s) : launchFrameT<false, false, false>(p, s);
+  if (stats)
+    return skip ? launchFrameK<true, true>(p, s) : launchFrameK<false, true>(p, s);
+  return skip ? launchFrameK<true, false>(p, s) : launchFrameK<false, false>(p, s);
 }
 
 // ----------------------------------------------------------------------------------------------
@@ -381,7 +386,7 @@ __global__ void __launch_bounds__(kBlockThreads, 2) dvrPartialKernel(const __gri
     float opacity = 0.f;
     uint32_t objID = ~0u, instID = ~0u;
     bool anyHit = false;
-    const float depth = rayMarchAllVolumes<SKIP, true, STATS, true>(&P.inst, 1, TfSelectSingle{s_tf}, org, dir, FLT_MAX,
+    const float depth = rayMarchAllVolumes<SKIP, true, STATS, true, FIELD_STRUCTURED>(&P.inst, 1, TfSelectSingle{s_tf}, org, dir, FLT_MAX,
         P.invSamplingRate, rng, color, opacity, objID, instID, st, P.cellBitmap, anyHit);
     const uint32_t idx = px + py * P.width;
     P.partialRgba[idx] = make_float4(color.x, color.y, color.z, opacity);

@@ -61,6 +61,54 @@ int launchMacrocellBuild(cudaTextureObject_t pointTex, int3 dims, int zTexBegin,
   return DVR_OK;
 }
 
+// K4 for NanoVDB grids: same cell definition in index space relative to the index bounding box; voxels
+// outside the box are read through the tree (tile / background values), exactly what a fetch would see.
+__global__ void __launch_bounds__(256) dvrMacrocellRangeNvdbKernel(const __grid_constant__ FieldDev f,
+    float2 *__restrict__ ranges)
+{
+  const int cx = blockIdx.x, cy = blockIdx.y, cz = blockIdx.z;
+  const int x0 = cx * 16 - 1, y0 = cy * 16 - 1, z0 = cz * 16 - 1;
+  const int nn = 19;
+  NvdbCache cache;
+  cache.reset();
+  float lo = FLT_MAX, hi = -FLT_MAX;
+  for (int i = threadIdx.x; i < nn * nn * nn; i += blockDim.x) {
+    // z fastest (NanoVDB leaf order) so consecutive threads share leaves
+    const int z = z0 + i % nn, y = y0 + (i / nn) % nn, x = x0 + i / (nn * nn);
+    const float v = nvdbGetValue(f.nv, cache, x + f.nv.bboxMin.x, y + f.nv.bboxMin.y, z + f.nv.bboxMin.z);
+    lo = fminf(lo, v);
+    hi = fmaxf(hi, v);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    lo = fminf(lo, __shfl_xor_sync(0xffffffffu, lo, o));
+    hi = fmaxf(hi, __shfl_xor_sync(0xffffffffu, hi, o));
+  }
+  __shared__ float slo[8], shi[8];
+  const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+  if (l == 0) {
+    slo[w] = lo;
+    shi[w] = hi;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int i = 1; i < 8; ++i) {
+      lo = fminf(lo, slo[i]);
+      hi = fmaxf(hi, shi[i]);
+    }
+    ranges[((size_t)cz * f.gridDims.y + cy) * f.gridDims.x + cx] = make_float2(lo, hi);
+  }
+}
+
+int launchMacrocellBuildNvdb(const FieldDev &f, float2 *ranges, cudaStream_t s)
+{
+  dim3 grid(f.gridDims.x, f.gridDims.y, f.gridDims.z);
+  dvrMacrocellRangeNvdbKernel<<<grid, 256, 0, s>>>(f, ranges);
+  DVR_CUDA(cudaGetLastError());
+  countLaunch();
+  return DVR_OK;
+}
+
 // K5: majorant = max TF alpha the marcher's lookup can return for any value in the cell's range.
 // UniformGrid.cu:55-90 restated with (a) the volume's own valueRange (quirk Q8) and (b) the
 // texel interval derived from the same coordinate mapping tfLookup() uses, widened by one texel.

@@ -88,13 +88,40 @@ __device__ __forceinline__ float fieldFetch(const FieldDev &f, float3 tc)
   return tex3D<float>(f.tex, tc.x, tc.y, tc.z);
 }
 
+// Sampling coordinate of an object-space position: normalised texture coordinate (structuredRegular) or
+// index-space coordinate (NanoVDB); sampleSpatialField.h:66-70 / :91-95.
+template <int KIND>
+__device__ __forceinline__ float3 fieldCoord(const FieldDev &f, const float3 halfSpacing, float3 p)
+{
+  if (KIND == FIELD_NANOVDB)
+    return nvdbWorldToIndex(f.nv, p);
+  return fieldTexCoord(f, halfSpacing, p);
+}
+
+// continuous voxel coordinate whose floor is the lower tap index (macrocell / slab bookkeeping only)
+template <int KIND>
+__device__ __forceinline__ float3 coordToVoxel(const FieldDev &f, float3 c)
+{
+  if (KIND == FIELD_NANOVDB)
+    return f3(c.x - (float)f.nv.bboxMin.x, c.y - (float)f.nv.bboxMin.y, c.z - (float)f.nv.bboxMin.z);
+  return f3(c.x * (float)f.dims.x - 0.5f, c.y * (float)f.dims.y - 0.5f, c.z * (float)f.dims.z - 0.5f);
+}
+
+template <int KIND, bool SLAB>
+__device__ __forceinline__ float fieldSample(const FieldDev &f, NvdbCache &cache, float3 c)
+{
+  if (KIND == FIELD_NANOVDB)
+    return nvdbSampleTrilinear(f.nv, cache, c);
+  return fieldFetch<SLAB>(f, c);
+}
+
 // One volume segment [tLower(after jitter #1), tUpper] of one ray.
 //   SKIP : consult the per-macrocell majorants and step over fully transparent cells on the
 //          SAME sample lattice (t advances by repeated `t += step`, so the taken samples are
 //          bit-identical to the unskipped march)
 //   SLAB : only samples whose cell slice lies in [zOwnBegin,zOwnEnd) are taken (sort-last)
 //   STATS: count samples
-template <bool SKIP, bool SLAB, bool STATS>
+template <bool SKIP, bool SLAB, bool STATS, int KIND>
 __device__ __forceinline__ void marchSegment(const VolumeDev &v, const float4 *__restrict__ tf,
     const float3 org, const float3 dir, float t, const float tUpper, const float invSamplingRate,
     Philox &rng, float3 &color, float &opacity, MarchStats &stats, unsigned int *cellBitmap)
@@ -110,8 +137,17 @@ __device__ __forceinline__ void marchSegment(const VolumeDev &v, const float4 *_
   float transmittance = 1.f;
 
   // d(voxel coordinate)/dt, used by SKIP/SLAB bookkeeping only (never for the sample position)
-  const float3 dvox = f3(dir.x * f.invSpacing.x * (float)f.dims.x, dir.y * f.invSpacing.y * (float)f.dims.y,
-      dir.z * f.invSpacing.z * (float)f.dims.z);
+  float3 dvox;
+  if (KIND == FIELD_NANOVDB)
+    dvox = f3(dir.x * f.nv.invMat[0] + dir.y * f.nv.invMat[1] + dir.z * f.nv.invMat[2],
+        dir.x * f.nv.invMat[3] + dir.y * f.nv.invMat[4] + dir.z * f.nv.invMat[5],
+        dir.x * f.nv.invMat[6] + dir.y * f.nv.invMat[7] + dir.z * f.nv.invMat[8]);
+  else
+    dvox = f3(dir.x * f.invSpacing.x * (float)f.dims.x, dir.y * f.invSpacing.y * (float)f.dims.y,
+        dir.z * f.invSpacing.z * (float)f.dims.z);
+  NvdbCache nvCache;
+  if (KIND == FIELD_NANOVDB)
+    nvCache.reset();
 
   if (SLAB) {
     // fast-forward to just before the ray enters the owned z range (sequential adds keep the
@@ -133,9 +169,7 @@ __device__ __forceinline__ void marchSegment(const VolumeDev &v, const float4 *_
 
   while (opacity < 0.99f && t <= tUpper) {
     if (SKIP) {
-      const float3 tc = fieldTexCoord(f, halfSpacing, madd3(dir, t, org));
-      const float3 xb = f3(tc.x * (float)f.dims.x - 0.5f, tc.y * (float)f.dims.y - 0.5f,
-          tc.z * (float)f.dims.z - 0.5f);
+      const float3 xb = coordToVoxel<KIND>(f, fieldCoord<KIND>(f, halfSpacing, madd3(dir, t, org)));
       const int cx = min(max((int)floorf(xb.x), 0), f.dims.x - 1) >> 4;
       const int cy = min(max((int)floorf(xb.y), 0), f.dims.y - 1) >> 4;
       const int cz = min(max((int)floorf(xb.z), 0), f.dims.z - 1) >> 4;
@@ -184,20 +218,21 @@ __device__ __forceinline__ void marchSegment(const VolumeDev &v, const float4 *_
       s[k] = __int_as_float(0x7fc00000);
       if (ts[k] <= tUpper) {
         const float3 p = madd3(dir, ts[k], org);
-        const float3 tc = fieldTexCoord(f, halfSpacing, p);
+        const float3 tc = fieldCoord<KIND>(f, halfSpacing, p);
         bool own = true;
         if (SLAB) {
           const int zc = min(max((int)floorf(tc.z * (float)f.dims.z - 0.5f), 0), f.dims.z - 1);
           own = zc >= f.zOwnBegin && zc < f.zOwnEnd;
         }
         if (own) {
-          s[k] = fieldFetch<SLAB>(f, tc);
+          s[k] = fieldSample<KIND, SLAB>(f, nvCache, tc);
           if (STATS) {
             stats.taken++;
             if (cellBitmap) {
-              const int cx = min(max((int)floorf(tc.x * (float)f.dims.x - 0.5f), 0), f.dims.x - 1) >> 4;
-              const int cy = min(max((int)floorf(tc.y * (float)f.dims.y - 0.5f), 0), f.dims.y - 1) >> 4;
-              const int cz = min(max((int)floorf(tc.z * (float)f.dims.z - 0.5f), 0), f.dims.z - 1) >> 4;
+              const float3 xv = coordToVoxel<KIND>(f, tc);
+              const int cx = min(max((int)floorf(xv.x), 0), f.dims.x - 1) >> 4;
+              const int cy = min(max((int)floorf(xv.y), 0), f.dims.y - 1) >> 4;
+              const int cz = min(max((int)floorf(xv.z), 0), f.dims.z - 1) >> 4;
               const size_t c = (size_t)cz * f.gridDims.x * f.gridDims.y + (size_t)cy * f.gridDims.x + cx;
               atomicOr(&cellBitmap[c >> 5], 1u << (c & 31));
             }
@@ -245,7 +280,8 @@ __device__ __forceinline__ void marchSegment(const VolumeDev &v, const float4 *_
 // Intersectors_ptx.cu:250-252).
 // SINGLE: exactly one instance => every access uses the constant index 0, which keeps the texture
 // handle and field constants warp-uniform (no divergent-handle loop around the TEX instruction).
-template <bool SKIP, bool SLAB, bool STATS, bool SINGLE, typename TfSelect>
+// KIND: field kind known at compile time (single-volume kernels), or -1 = decide per instance.
+template <bool SKIP, bool SLAB, bool STATS, bool SINGLE, int KIND, typename TfSelect>
 __device__ __forceinline__ float rayMarchAllVolumes(const InstanceDev *__restrict__ inst, const int nInst,
     TfSelect tfOf, const float3 org, const float3 dir, const float tfar, const float invSamplingRate,
     Philox &rng, float3 &color, float &opacity, uint32_t &objID, uint32_t &instID, MarchStats &stats,
@@ -294,8 +330,12 @@ __device__ __forceinline__ float rayMarchAllVolumes(const InstanceDev *__restric
     bt1 = fminf(tfar, bt1);
     // detail::rayMarchVolume: jitter #1 uses the UNSCALED step (volumeIntegration.h:117-120)
     const float tStart = __fmaf_rn(in.v.f.stepSize, rng.uniform(), bt0);
-    marchSegment<SKIP, SLAB, STATS>(
-        in.v, tfOf(SINGLE ? 0 : best), bo, bd, tStart, bt1, invSamplingRate, rng, color, opacity, stats, cellBitmap);
+    if (KIND == FIELD_NANOVDB || (KIND < 0 && in.v.f.kind == FIELD_NANOVDB))
+      marchSegment<SKIP, false, STATS, FIELD_NANOVDB>(
+          in.v, tfOf(SINGLE ? 0 : best), bo, bd, tStart, bt1, invSamplingRate, rng, color, opacity, stats, cellBitmap);
+    else
+      marchSegment<SKIP, SLAB, STATS, FIELD_STRUCTURED>(
+          in.v, tfOf(SINGLE ? 0 : best), bo, bd, tStart, bt1, invSamplingRate, rng, color, opacity, stats, cellBitmap);
     rayLower = __fadd_rn(bt1, 1e-3f);
     last = best;
   } while (opacity < 0.99f);

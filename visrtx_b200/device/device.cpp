@@ -539,7 +539,7 @@ static const char *kExtensions[] = {"ANARI_KHR_CAMERA_ORTHOGRAPHIC", "ANARI_KHR_
     "ANARI_KHR_FRAME_ACCUMULATION", "ANARI_KHR_FRAME_CHANNEL_PRIMITIVE_ID", "ANARI_KHR_FRAME_CHANNEL_OBJECT_ID",
     "ANARI_KHR_FRAME_CHANNEL_INSTANCE_ID", "ANARI_KHR_FRAME_CHANNEL_ALBEDO", "ANARI_KHR_FRAME_CHANNEL_NORMAL",
     "ANARI_KHR_FRAME_COMPLETION_CALLBACK", "ANARI_KHR_INSTANCE_TRANSFORM", "ANARI_KHR_SPATIAL_FIELD_STRUCTURED_REGULAR",
-    "ANARI_KHR_VOLUME_TRANSFER_FUNCTION1D", "ANARI_KHR_RENDERER_BACKGROUND_COLOR", "ANARI_KHR_DEVICE_SYNCHRONIZATION",
+    "ANARI_KHR_VOLUME_TRANSFER_FUNCTION1D", "ANARI_VISRTX_SPATIAL_FIELD_NANOVDB", "ANARI_KHR_RENDERER_BACKGROUND_COLOR", "ANARI_KHR_DEVICE_SYNCHRONIZATION",
     "ANARI_NV_ARRAY_CUDA", "ANARI_NV_FRAME_BUFFERS_CUDA", "ANARI_VISRTX_CUDA_OUTPUT_BUFFERS", "ANARI_VISRTX_ARRAY_CUDA",
     nullptr};
 
@@ -599,7 +599,7 @@ ANARIObject make(ANARIDevice d, A &&...a)
 
 // introspection tables (subset of the code-generated queries of the reference, visrtx_device.json)
 const char *kCameraTypes[] = {"perspective", "orthographic", nullptr};
-const char *kFieldTypes[] = {"structuredRegular", nullptr};
+const char *kFieldTypes[] = {"structuredRegular", "nanovdb", nullptr};
 const char *kVolumeTypes[] = {"transferFunction1D", "scivis", nullptr};
 const char *kRendererTypes[] = {"default", "raycast", "ao", "directLight", "dpt", nullptr};
 const char *kInstanceTypes[] = {"transform", nullptr};
@@ -670,6 +670,7 @@ int visrtxGetObjectExtensions(VisRTXExtensions *e, ANARIDevice, ANARIDataType, c
   std::memset(e, 0, sizeof(*e));
   e->VISRTX_ARRAY_CUDA = 1;
   e->VISRTX_CUDA_OUTPUT_BUFFERS = 1;
+  e->VISRTX_SPATIAL_FIELD_NANOVDB = 1;
   return 1;
 }
 int visrtxGetInstanceExtensions(VisRTXExtensions *e, ANARIDevice d, ANARIObject)

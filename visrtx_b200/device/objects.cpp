@@ -386,7 +386,7 @@ void SpatialField::commitParameters()
   getParamRaw("origin", ANARI_FLOAT32_VEC3, m_origin, sizeof(m_origin));
   getParamRaw("spacing", ANARI_FLOAT32_VEC3, m_spacing, sizeof(m_spacing));
   m_filter = getParamString("filter", "linear");
-  Array *a = static_cast<Array *>(getParamObject("data", ANARI_ARRAY3D));
+  Array *a = static_cast<Array *>(getParamObject("data", subtype == "nanovdb" ? ANARI_ARRAY1D : ANARI_ARRAY3D));
   if (m_data.ptr != a) {
     if (m_data)
       m_data->removeObserver(this);
@@ -413,6 +413,29 @@ static int dvrTypeOf(ANARIDataType t)
 void SpatialField::finalize()
 {
   cleanup();
+  if (subtype == "nanovdb") { // spatial_field/NvdbRegularField.cpp:64-113
+    if (!m_data) {
+      report(ANARI_SEVERITY_WARNING, ANARI_STATUS_INVALID_ARGUMENT,
+          "missing required parameter 'data' on NanoVDB regular spatial field");
+      return;
+    }
+    if (m_data->elementType != ANARI_UINT8) {
+      report(ANARI_SEVERITY_WARNING, ANARI_STATUS_INVALID_ARGUMENT,
+          "invalid data array type encountered in NanoVDB spatial field(%s)", typeName(m_data->elementType));
+      return;
+    }
+    if (!device->initDevice())
+      return;
+    CudaDeviceScope scope(device);
+    const int rc = dvr_field_create_nanovdb(m_data->data(), m_data->totalBytes(), m_data->onDevice() ? 1 : 0,
+        device->stream(), &m_field);
+    if (rc != DVR_OK) {
+      m_field = nullptr;
+      report(rc == DVR_ERR_UNSUPPORTED ? ANARI_SEVERITY_WARNING : ANARI_SEVERITY_ERROR, ANARI_STATUS_INVALID_ARGUMENT,
+          "NanoVDB field rejected: %s", dvr_last_error());
+    }
+    return;
+  }
   if (subtype != "structuredRegular") {
     report(ANARI_SEVERITY_WARNING, ANARI_STATUS_INVALID_ARGUMENT, "unknown spatial field subtype '%s'",
         subtype.c_str());
