@@ -50,8 +50,8 @@ def parse_args():
     ap.add_argument("--rate", type=float, default=0.5, help="volumeSamplingRate (0.5 => 1 voxel per step)")
     ap.add_argument("--unit-distance", type=float, default=256.0,
                     help="TF unitDistance in voxels; 256 = semi-transparent, every ray crosses the volume")
-    ap.add_argument("--field", default="ml", choices=["ml", "shells"])
-    ap.add_argument("--config", default="c2", choices=["c2", "c3", "c4"],
+    ap.add_argument("--field", default="ml", choices=["ml", "shells", "fog"])
+    ap.add_argument("--config", default="c2", choices=["c2", "c3", "c4", "c5"],
                     help="BASELINE.json config preset: c2 = 1024^3 f32 1080p (headline); c3 = 2048^3 16-bit sparse shells, "
                          "3840x2160, macrocell skipping; c4 = 4096^3 f32 sort-last (needs >= 2 GPUs)")
     ap.add_argument("--skip", type=int, default=-1,
@@ -67,6 +67,9 @@ def parse_args():
         a.unit_distance = 8.0
     elif a.config == "c4":
         a.size, a.unit_distance, a.mode = 4096, 1024.0, "sort-last"
+    elif a.config == "c5":  # NanoVDB fog sphere r=200 voxels, 1080p, progressive accumulation
+        a.field, a.size, a.unit_distance = "fog", 401, 64.0
+        a.skip = 1 if a.skip < 0 else a.skip
     a.skip = max(a.skip, 0)
     return a
 
@@ -130,6 +133,9 @@ def make_scene(args, torch, device, z_begin=0, z_end=None):
     if args.field == "shells":
         assert z_begin == 0 and z_end is None, "the sparse field is generated whole"
         return scenes.shells_torch(n, device)
+    if args.field == "fog":  # a serialized NanoVDB float grid (host numpy uint8), written by our own writer
+        from visrtx_b200 import nvdb_writer
+        return nvdb_writer.fog_sphere(radius=(n - 1) / 2.0, voxel_size=1.0, half_width=3.0)
     return scenes.marschner_lobb_torch(n, device, z_begin=z_begin, z_end=z_end, nz_total=n)
 
 
@@ -142,6 +148,23 @@ def voxel_bytes(args):
     return 2 if args.field == "shells" else 4
 
 
+def scene_bounds(args):
+    """object-space bounds of the field (what dvr_field_bounds returns)."""
+    n = args.size
+    if args.field == "fog":
+        r = (n - 1) // 2
+        return (-float(r) + 1.0,) * 3, (float(r),) * 3  # world bbox of the active voxels [-199, 200) for r=200
+    return (0.0, 0.0, 0.0), (n - 1.0,) * 3
+
+
+def create_field(args, capi, vol, stream):
+    n = args.size
+    if args.field == "fog":
+        return capi.Field.create_nanovdb(vol.ctypes.data, vol.nbytes, False, stream)
+    return capi.Field.create_structured(vol.data_ptr(), True, scene_dtype(args), (n, n, n), (0, 0, 0), (1, 1, 1),
+                                        capi.DVR_FILTER_LINEAR, stream)
+
+
 def scene_colormap(args):
     from visrtx_b200 import scenes
     return scenes.sparse_colormap(256, 0.5) if args.field == "shells" else scenes.tsd_default_colormap(256)
@@ -151,6 +174,11 @@ def workload_name(args):
     n, W, H = args.size, args.width, args.height
     field = ("UFIXED16 sparse shells (12 Gaussian shells r=96*n/2048 voxels, zero elsewhere)" if args.field == "shells"
              else "f32 Marschner-Lobb (dense)")
+    if args.field == "fog":
+        return (f"{args.config.upper()}: NanoVDB float fog sphere r={(n - 1) // 2} voxels (index bbox {n}^3, 33.5 M active "
+                f"voxels at r=200) + transferFunction1D (TSD default map, unitDistance {args.unit_distance:g}), {W}x{H}, "
+                f"default renderer 1 spp progressive accumulation, volumeSamplingRate {args.rate:g}, orbit camera "
+                f"az30/el20 at 2|diag|, fovy 60")
     tfn = "sparse map (alpha 0 below 0.5)" if args.field == "shells" else "TSD default map"
     return (f"{args.config.upper()}: {n}^3 {field} structuredRegular + transferFunction1D ({tfn}, unitDistance "
             f"{args.unit_distance:g} voxels), {W}x{H}, default renderer 1 spp progressive, volumeSamplingRate "
@@ -159,8 +187,8 @@ def workload_name(args):
 
 def orbit(args, az_deg=30.0):
     from visrtx_b200 import capi, scenes
-    n = args.size
-    pose = scenes.orbit_camera((0, 0, 0), (n - 1, n - 1, n - 1), args.width, args.height, az_deg=az_deg)
+    lo, hi = scene_bounds(args)
+    pose = scenes.orbit_camera(lo, hi, args.width, args.height, az_deg=az_deg)
     return capi.camera_perspective(pose.position, pose.direction, pose.up, pose.fovy, pose.aspect), pose
 
 
@@ -191,7 +219,7 @@ def cpu_baseline(args, torch, vol_dev, samples_per_frame: int):
     import oracle_binding as ob
     from visrtx_b200 import capi, scenes
     n = args.size
-    host = vol_dev.cpu().numpy()  # (z,y,x)
+    host = vol_dev if args.field == "fog" else vol_dev.cpu().numpy()  # (z,y,x) voxels, or the NanoVDB blob
     if args.field == "shells":  # UFIXED16 stored as int16 bits -> what cudaReadModeNormalizedFloat hands the filter
         host = (host.view(np.uint16).astype(np.float32) / np.float32(65535.0))
     tf = capi.tf_discretize(color=scene_colormap(args))
@@ -199,6 +227,8 @@ def cpu_baseline(args, torch, vol_dev, samples_per_frame: int):
     vols = (ob.OracleVolume * 1)()
     o = vols[0]
     o.voxels = host.ctypes.data_as(C.c_void_p)
+    if args.field == "fog":
+        o.nvdbGrid = host.ctypes.data_as(C.c_void_p)
     o.dims = (C.c_int32 * 3)(n, n, n)
     o.origin = (C.c_float * 3)(0, 0, 0)
     o.spacing = (C.c_float * 3)(1, 1, 1)
@@ -254,9 +284,15 @@ class AnariE2E:
         d.set(d.handle, "cudaDevice", A.INT32, device.index)
         d.commit(d.handle)
         torch.cuda.synchronize()
-        self.data = d.new_array3d_device(vol_dev.data_ptr(), A.UFIXED16 if args.field == "shells" else A.FLOAT32, n, n, n)
-        self.field = d.new("SpatialField", "structuredRegular")
-        d.set(self.field, "data", A.ARRAY3D, self.data)
+        if args.field == "fog":
+            self.data = d.new_array1d(vol_dev, A.UINT8)
+            self.field = d.new("SpatialField", "nanovdb")
+            d.set(self.field, "data", A.ARRAY1D, self.data)
+        else:
+            self.data = d.new_array3d_device(vol_dev.data_ptr(), A.UFIXED16 if args.field == "shells" else A.FLOAT32,
+                                             n, n, n)
+            self.field = d.new("SpatialField", "structuredRegular")
+            d.set(self.field, "data", A.ARRAY3D, self.data)
         d.commit(self.field)
         self.volume = d.new("Volume", "transferFunction1D")
         self.color = d.new_array1d(scene_colormap(args), A.FLOAT32_VEC4)
@@ -356,8 +392,7 @@ def run_ours(args, torch, dist, rank, world):
         field.build_macrocells(stream)
     else:
         vol = make_scene(args, torch, device)
-        field = capi.Field.create_structured(vol.data_ptr(), True, scene_dtype(args), (n, n, n), (0, 0, 0), (1, 1, 1),
-                                             capi.DVR_FILTER_LINEAR, stream)
+        field = create_field(args, capi, vol, stream)
     torch.cuda.synchronize()
     tf = capi.tf_discretize(color=scene_colormap(args))
     volume = capi.Volume.create(field, tf, (0.0, 1.0), args.unit_distance, 0, stream)
@@ -511,7 +546,8 @@ def run_ours(args, torch, dist, rank, world):
         "config": {
             "workload": workload_name(args),
             "parallelism": mode + (f"x{world}" if world > 1 else ""),
-            "l2": f"input volume {n ** 3 * voxel_bytes(args) / 2 ** 30:.1f} GiB >> 126 MB L2; no flush needed",
+            "l2": (f"NanoVDB grid {vol.nbytes / 1e6:.0f} MB > 126 MB L2; no flush" if args.field == "fog" else
+                   f"input volume {n ** 3 * voxel_bytes(args) / 2 ** 30:.1f} GiB >> 126 MB L2; no flush needed"),
             "macrocell_skipping": bool(args.skip),
         },
         "gpu_launches": int(launches),
@@ -582,8 +618,12 @@ def _refgpu_objects(args, torch, vol_dev):
     lib = ob.refgpu()
     n = args.size
     f = C.c_void_p()
-    rc = lib.refgpu_field_create(C.c_void_p(vol_dev.data_ptr()), C.c_int(scene_dtype(args)), (C.c_uint32 * 3)(n, n, n),
-                                 (C.c_float * 3)(0, 0, 0), (C.c_float * 3)(1, 1, 1), C.c_int(0), C.byref(f))
+    if args.field == "fog":
+        rc = lib.refgpu_field_create_nvdb(vol_dev.ctypes.data_as(C.c_void_p), C.c_size_t(vol_dev.nbytes), C.byref(f))
+    else:
+        rc = lib.refgpu_field_create(C.c_void_p(vol_dev.data_ptr()), C.c_int(scene_dtype(args)),
+                                     (C.c_uint32 * 3)(n, n, n), (C.c_float * 3)(0, 0, 0), (C.c_float * 3)(1, 1, 1),
+                                     C.c_int(0), C.byref(f))
     assert rc == 0, lib.refgpu_last_error()
     tf = capi.tf_discretize(color=scene_colormap(args))
     v = C.c_void_p()
@@ -605,7 +645,7 @@ def ref_gpu_fps(args, torch, vol_dev, steps):
     from visrtx_b200 import capi
     lib, sc, _ = _refgpu_objects(args, torch, vol_dev)
     npx = args.width * args.height
-    dev = vol_dev.device
+    dev = torch.device("cuda", torch.cuda.current_device())
     accum = torch.zeros((npx, 4), dtype=torch.float32, device=dev)
     color = torch.zeros(npx, dtype=torch.int32, device=dev)
     depth = torch.zeros(npx, dtype=torch.float32, device=dev)
@@ -649,8 +689,7 @@ def run_reference(args, torch, dist, rank, world):
         # with the GPU-measured samples per frame when libdvr is present
         from visrtx_b200 import scenes
         stream = torch.cuda.current_stream().cuda_stream
-        field = capi.Field.create_structured(vol.data_ptr(), True, scene_dtype(args), (n, n, n), (0, 0, 0), (1, 1, 1),
-                                             capi.DVR_FILTER_LINEAR, stream)
+        field = create_field(args, capi, vol, stream)
         tf = capi.tf_discretize(color=scene_colormap(args))
         v = capi.Volume.create(field, tf, (0.0, 1.0), args.unit_distance, 0, stream)
         inst, ninst = capi.make_instances([v], None, [0])

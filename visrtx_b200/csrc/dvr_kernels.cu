@@ -224,8 +224,11 @@ struct TfSelectSingle
 #endif
 
 // KIND: FIELD_STRUCTURED / FIELD_NANOVDB for the single-volume kernels, -1 for the multi-volume kernel
+#ifndef DVR_OCC_NVDB
+#define DVR_OCC_NVDB 3 // the NanoVDB march chases pointers; A/B on C5 (batch 1): 3/4/5/6 CTAs = 810/732/642/612 fps
+#endif
 template <bool SKIP, bool STATS, bool SINGLE, int KIND>
-__global__ void __launch_bounds__(kBlockThreads, DVR_OCC) dvrFrameKernel(const __grid_constant__ FrameLaunch P)
+__global__ void __launch_bounds__(kBlockThreads, (KIND == FIELD_NANOVDB ? DVR_OCC_NVDB : DVR_OCC)) dvrFrameKernel(const __grid_constant__ FrameLaunch P)
 {
   __shared__ float4 s_tf[(SINGLE ? 1 : kMaxInlineInstances) * DVR_TF_SIZE];
 

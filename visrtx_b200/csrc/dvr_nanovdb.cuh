@@ -134,14 +134,31 @@ __device__ __forceinline__ float nvdbSampleTrilinear(const NvdbDev &g, NvdbCache
   const float fi = floorf(idx.x), fj = floorf(idx.y), fk = floorf(idx.z);
   const int i = (int)fi, j = (int)fj, k = (int)fk;
   const float u = __fsub_rn(idx.x, fi), v = __fsub_rn(idx.y, fj), w = __fsub_rn(idx.z, fk);
-  const float v000 = nvdbGetValue(g, c, i, j, k);
-  const float v001 = nvdbGetValue(g, c, i, j, k + 1);
-  const float v011 = nvdbGetValue(g, c, i, j + 1, k + 1);
-  const float v010 = nvdbGetValue(g, c, i, j + 1, k);
-  const float v100 = nvdbGetValue(g, c, i + 1, j, k);
-  const float v101 = nvdbGetValue(g, c, i + 1, j, k + 1);
-  const float v111 = nvdbGetValue(g, c, i + 1, j + 1, k + 1);
-  const float v110 = nvdbGetValue(g, c, i + 1, j + 1, k);
+  float v000, v001, v011, v010, v100, v101, v111, v110;
+  v000 = nvdbGetValue(g, c, i, j, k); // positions the leaf cache on the stencil's base voxel
+  if (((i & 7) < 7) & ((j & 7) < 7) & ((k & 7) < 7)) {
+    // whole stencil inside the cached leaf (or constant region): seven independent loads, no tree walk
+    if (c.leaf) {
+      const float *lv = reinterpret_cast<const float *>(c.leaf + kNvdbLeafValues)
+          + (uint32_t)(((i & 7) << 6) | ((j & 7) << 3) | (k & 7));
+      v001 = lv[1];
+      v010 = lv[8];
+      v011 = lv[9];
+      v100 = lv[64];
+      v101 = lv[65];
+      v110 = lv[72];
+      v111 = lv[73];
+    } else
+      v001 = v010 = v011 = v100 = v101 = v110 = v111 = c.leafTile;
+  } else {
+    v001 = nvdbGetValue(g, c, i, j, k + 1);
+    v011 = nvdbGetValue(g, c, i, j + 1, k + 1);
+    v010 = nvdbGetValue(g, c, i, j + 1, k);
+    v100 = nvdbGetValue(g, c, i + 1, j, k);
+    v101 = nvdbGetValue(g, c, i + 1, j, k + 1);
+    v111 = nvdbGetValue(g, c, i + 1, j + 1, k + 1);
+    v110 = nvdbGetValue(g, c, i + 1, j + 1, k);
+  }
 #define DVR_LERP(a, b, t) __fmaf_rn((t), __fsub_rn((b), (a)), (a))
   const float r = DVR_LERP(DVR_LERP(DVR_LERP(v000, v001, w), DVR_LERP(v010, v011, w), v),
       DVR_LERP(DVR_LERP(v100, v101, w), DVR_LERP(v110, v111, w), v), u);
