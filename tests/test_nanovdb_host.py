@@ -41,3 +41,39 @@ def test_grid_header_fields():
     assert blob[636:640].view(np.uint32)[0] == 1  # GridType::Float
     wb = blob[560:608].view(np.float64)
     assert tuple(wb) == (-20.0, -20.0, -20.0, 21.0, 21.0, 21.0)
+
+
+def test_own_nanovdb_writer_is_read_back_by_the_oracle_and_by_the_reference():
+    """visrtx_b200.nvdb_writer output: sampled by O-cpu it equals dense trilinear interpolation of the source
+    block; when the reference's NanoVDB is available (libref_host.so) the real library reads it back too."""
+    import ctypes as C
+    from visrtx_b200 import nvdb_writer as W
+    rng = np.random.default_rng(11)
+    dense = rng.random((21, 13, 30)).astype(np.float32)
+    dense[dense < 0.4] = 0.0  # sparse: background voxels are not stored
+    origin = (-9, 4, -17)
+    blob = W.write_float_grid(dense, index_origin=origin, voxel_size=0.5, world_origin=(1.0, -2.0, 0.25))
+    assert blob.nbytes % 32 == 0 and blob[:8].tobytes() == b"NanoVDB0"
+    pts_idx = rng.random((4000, 3)) * (np.array(dense.shape) + 3) - 2 + np.array(origin)
+    xyz = (pts_idx * 0.5 + np.array([1.0, -2.0, 0.25])).astype(np.float32)
+    got = ob.nvdb_sample_oracle(blob, xyz)
+    # dense trilinear ground truth in index space
+    pi = (xyz.astype(np.float64) - np.array([1.0, -2.0, 0.25])) / 0.5
+    i0 = np.floor(pi).astype(int)
+    u = pi - i0
+    want = np.zeros(len(xyz))
+    for dx in (0, 1):
+        for dy in (0, 1):
+            for dz in (0, 1):
+                w = (u[:, 0] if dx else 1 - u[:, 0]) * (u[:, 1] if dy else 1 - u[:, 1]) * (u[:, 2] if dz else 1 - u[:, 2])
+                ii = i0 + np.array([dx, dy, dz]) - np.array(origin)
+                ok = ((ii >= 0) & (ii < np.array(dense.shape))).all(axis=1)
+                vals = np.where(ok, dense[np.clip(ii[:, 0], 0, 20), np.clip(ii[:, 1], 0, 12), np.clip(ii[:, 2], 0, 29)], 0.0)
+                want += w * vals
+    assert np.abs(got - want).max() < 2e-6
+    if ob.have_ref_host():
+        assert np.abs(ob.nvdb_sample_reference(blob, xyz) - got).max() <= 2.4e-7
+        lib = ob.refhost()
+        wb, vs, ib, gt, av = (C.c_double * 6)(), (C.c_double * 3)(), (C.c_int * 6)(), C.c_uint(), C.c_ulonglong()
+        lib.refhost_nvdb_info(blob.ctypes.data_as(C.c_void_p), wb, vs, ib, C.byref(gt), C.byref(av))
+        assert gt.value == 1 and av.value == int((dense != 0).sum()) and tuple(vs) == (0.5, 0.5, 0.5)
