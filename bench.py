@@ -204,6 +204,22 @@ def bytes_per_frame(args, cells_touched: int, samples: int = 0, fmt_bytes: int =
     return cell_model + frame, "macrocells touched * 16^3 * sizeof(voxel) (SURVEY 8d)"
 
 
+def traffic_key(args, mode):
+    return (f"{args.config}:{args.field}:{args.size}:{args.width}x{args.height}:rate{args.rate:g}:"
+            f"ud{args.unit_distance:g}:skip{int(bool(args.skip))}:{mode}")
+
+
+def measured_traffic(args, mode):
+    """DRAM bytes per launch of the dominant kernel from the committed `ncu --set full` capture of this exact
+    workload (profiles/traffic.json: dram__bytes_read.sum + dram__bytes_write.sum), else None."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+            e = json.load(f).get(traffic_key(args, mode))
+        return None if e is None else int(e["dram_bytes_per_launch"])
+    except (OSError, ValueError, KeyError):
+        return None
+
+
 def measured_peak():
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
@@ -563,7 +579,7 @@ def run_ours(args, torch, dist, rank, world):
                 "d2h_bytes_per_step": e2e_bytes[1],
                 "what": e2e_what},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": None, "peak_source": peak_src, "kernel": "dvrFrameKernel",
+                     "traffic": measured_traffic(args, mode), "peak_source": peak_src, "kernel": "dvrFrameKernel",
                      "kernel_ms": kernel_ms, "algorithmic_bytes": bframe, "bytes_model": bmodel,
                      "macrocells_touched": int(cells), "macrocells_total": int(math.ceil(n / 16) ** 3)},
         "extra": {"samples_per_frame": int(samples), "gsamples_per_s": samples * fps / 1e9 * (1 if world == 1 else 1),
@@ -586,6 +602,11 @@ def run_ours(args, torch, dist, rank, world):
             out["extra"]["ref_gpu_fps"] = ref_gpu_fps(args, torch, vol, min(args.steps, 30))
         except Exception as e:
             out["extra"]["ref_gpu_fps"] = f"unavailable: {e}"
+        if mode == "single":
+            try:
+                out["extra"]["dpt"] = measure_dpt(args, torch, capi, field, cam, fb, stream, vol)
+            except Exception as e:
+                out["extra"]["dpt"] = f"unavailable: {e}"
     return out
 
 
@@ -618,8 +639,52 @@ def measure_variants(args, torch, capi, scenes, field, cam, inst, ninst, fb, str
     return res
 
 
+DPT_OPACITY = (0.0, 0.02)  # TF alpha ramp of the dpt variant: mean free path >= 25 voxels, multiple scattering
+
+
+def measure_dpt(args, torch, capi, field, cam, fb, stream, vol_dev):
+    """The `dpt` renderer (delta tracking, maxDepth 5) on the same field/camera, next to O-gpu running the
+    reference's tracker over the same majorant grid."""
+    import numpy as np
+    tf = capi.tf_discretize(color=scene_colormap(args), opacity=np.asarray(DPT_OPACITY, np.float32))
+    v = capi.Volume.create(field, tf, (0.0, 1.0), args.unit_distance, 0, stream)
+    ins, nn = capi.make_instances([v], None, [0])
+    mk = lambda fid: capi.frame_params(args.width, args.height, capi.DVR_FORMAT_UFIXED8_RGBA_SRGB,
+                                       capi.DVR_INTEGRATOR_DPT, fid, -1, 1, args.rate, (0.1, 0.1, 0.1, 1.0))
+    dims, maj_ptr = v.dda_majorants(stream)
+    for i in range(3):
+        capi.render(mk(i), cam, ins, nn, fb, stream)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(20):
+        capi.render(mk(3 + i), cam, ins, nn, fb, stream)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / 20
+    res = {"fps": 1000.0 / ms, "ms": ms, "max_depth": 5, "tf_opacity_ramp": list(DPT_OPACITY),
+           "grid_dims": list(dims)}
+    try:
+        lib, sc, (rf, rv) = _refgpu_objects(args, torch, vol_dev, tf=tf, grid=(dims, maj_ptr))
+        for i in range(2):
+            lib.refgpu_render(C.byref(mk(i)), C.byref(cam), sc, C.byref(fb), C.c_void_p(stream))
+        torch.cuda.synchronize()
+        e0.record()
+        for i in range(10):
+            lib.refgpu_render(C.byref(mk(2 + i)), C.byref(cam), sc, C.byref(fb), C.c_void_p(stream))
+        e1.record()
+        torch.cuda.synchronize()
+        res["ref_gpu_fps"] = 10 * 1000.0 / e0.elapsed_time(e1)
+        lib.refgpu_scene_destroy(sc)
+        lib.refgpu_volume_destroy(rv)
+        lib.refgpu_field_destroy(rf)
+    except Exception as e:
+        res["ref_gpu_fps"] = f"unavailable: {e}"
+    v.destroy()
+    return res
+
+
 # ---------------------------------------------------------------------------------------------------------
-def _refgpu_objects(args, torch, vol_dev):
+def _refgpu_objects(args, torch, vol_dev, tf=None, grid=None):
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     import oracle_binding as ob
     from visrtx_b200 import capi, scenes
@@ -633,11 +698,15 @@ def _refgpu_objects(args, torch, vol_dev):
                                      (C.c_uint32 * 3)(n, n, n), (C.c_float * 3)(0, 0, 0), (C.c_float * 3)(1, 1, 1),
                                      C.c_int(0), C.byref(f))
     assert rc == 0, lib.refgpu_last_error()
-    tf = capi.tf_discretize(color=scene_colormap(args))
+    if tf is None:
+        tf = capi.tf_discretize(color=scene_colormap(args))
     v = C.c_void_p()
     rc = lib.refgpu_volume_create(f, tf.ctypes.data_as(C.c_void_p), (C.c_float * 2)(0, 1), C.c_float(args.unit_distance),
                                   C.c_uint32(0), C.byref(v))
     assert rc == 0, lib.refgpu_last_error()
+    if grid is not None:  # delta-tracking grid (dims, device or host pointer to the majorants)
+        rc = lib.refgpu_volume_set_grid(v, (C.c_int * 3)(*grid[0]), C.c_void_p(grid[1]))
+        assert rc == 0, lib.refgpu_last_error()
     inst = (ob.RefInstance * 1)()
     inst[0].volume = v
     inst[0].worldToObject = (C.c_float * 12)(*capi.IDENTITY_3X4)

@@ -80,7 +80,11 @@ typedef enum DvrCameraType
 typedef enum DvrIntegrator
 {
   DVR_INTEGRATOR_RAYCAST = 0, /* centred pixel, 1 sample */
-  DVR_INTEGRATOR_DEFAULT = 1  /* jittered pixel, spp loop */
+  DVR_INTEGRATOR_DEFAULT = 1, /* jittered pixel, spp loop */
+  /* `dpt` / `diffuse_pathtracer`: delta (Woodcock) tracking through the majorant grid, isotropic
+   * scattering, Russian roulette, ambient light (renderer/DiffusePathTracer_ptx.cu:82-215,
+   * gpu/volumeIntegration.h:167-296,352-389, gpu/dda.h:43-121) */
+  DVR_INTEGRATOR_DPT = 2
 } DvrIntegrator;
 
 /* ---- opaque device objects ------------------------------------------------------ */
@@ -144,7 +148,11 @@ typedef struct DvrFrameParams
   /* options of the new implementation (all parity-neutral) */
   int32_t useMacrocellSkipping; /* skip fully transparent macrocells on the same sample lattice */
   int32_t tileBand;             /* sort-first: consecutive tile rows per band owned by one rank (0/1 = finest) */
-  int32_t _reserved[2];
+  /* DVR_INTEGRATOR_DPT only (DiffusePathTracer.cpp:44-54, Renderer.cpp:159-161) */
+  int32_t maxDepth;             /* "maxDepth", clamped to [1,256]; 0 => 5 */
+  float ambientRadiance;        /* "ambientRadiance" (dpt default 1) */
+  float occlusionDistance;      /* "ambientOcclusionDistance"; 0 => 1e20 */
+  int32_t _reserved[3];
 } DvrFrameParams;
 
 /* per-launch counters, filled only by dvr_render_instrumented (device memory, 64-bit each) */
@@ -247,6 +255,11 @@ int dvr_volume_update(DvrVolume *v, const float *tfRgba, const float valueRange[
 int dvr_volume_destroy(DvrVolume *v);
 /* device pointer to float[nMacrocells] majorants (max TF alpha over the cell's value range) */
 int dvr_volume_majorants(const DvrVolume *v, const float **maxOpacitiesDev);
+/* The delta-tracking grid the dpt integrator walks (UniformGridData of gpu/gpu_objects.h:395-401 as
+ * filled by UniformGrid::init/buildGrid/computeMaxOpacities, UniformGrid.cu:143-258): dims = ceil(field
+ * dims / 16) cells dividing the field bounds evenly; *maxOpacitiesDev = device float[dims.x*dims.y*dims.z].
+ * Built on first use (this call or the first DVR_INTEGRATOR_DPT frame) and after dvr_volume_update. */
+int dvr_volume_dda_majorants(DvrVolume *v, void *stream, uint32_t dims[3], const float **maxOpacitiesDev);
 
 /* ---- the hot path ------------------------------------------------------------------- */
 

@@ -464,6 +464,248 @@ float rayMarchAllVolumes(const std::vector<Volume> &vols, V3 org, V3 dir, float 
   return depth;
 }
 
+// ---- dpt renderer: delta (Woodcock) tracking -----------------------------------------------------------
+// The grid: the reference's geometry (UniformGrid::init, UniformGrid.cu:152-154: ceil(dims/16) cells dividing
+// the field bounds evenly).  Its content is NOT the reference's build (SURVEY quirks Q7/Q8 make that one
+// non-conservative, i.e. the reference's own images are biased); it is the conservative build the product
+// documents in DESIGN.md: per cell the min/max over every voxel a trilinear stencil inside the cell can touch
+// (one voxel of margin), majorant = max TF alpha over the texels those values can address.
+struct DdaGrid
+{
+  int gx = 0, gy = 0, gz = 0;
+  std::vector<float> maj;
+};
+
+DdaGrid buildDdaGrid(const Volume &v)
+{
+  DdaGrid g;
+  int nx = v.f.nx, ny = v.f.ny, nz = v.f.nz, bx = 0, by = 0, bz = 0;
+  float sx, sy, sz; // voxel units spanned by the bounds
+  if (v.f.isNvdb) {
+    int32_t bb[6];
+    std::memcpy(bb, v.f.nvdb.root, sizeof(bb)); // RootData::mBBox (index space)
+    bx = bb[0]; by = bb[1]; bz = bb[2];
+    nx = std::max(bb[3] - bb[0] + 1, 1); ny = std::max(bb[4] - bb[1] + 1, 1); nz = std::max(bb[5] - bb[2] + 1, 1);
+    sx = (float)nx; sy = (float)ny; sz = (float)nz;
+  } else {
+    sx = (float)nx - 1.f; sy = (float)ny - 1.f; sz = (float)nz - 1.f;
+  }
+  g.gx = (nx + 15) / 16; g.gy = (ny + 15) / 16; g.gz = (nz + 15) / 16;
+  const float wx = sx / (float)g.gx, wy = sy / (float)g.gy, wz = sz / (float)g.gz;
+  g.maj.assign((size_t)g.gx * g.gy * g.gz, 0.f);
+#pragma omp parallel for collapse(2) schedule(dynamic, 1)
+  for (int cz = 0; cz < g.gz; ++cz)
+    for (int cy = 0; cy < g.gy; ++cy)
+      for (int cx = 0; cx < g.gx; ++cx) {
+        int x0 = (int)std::floor(cx * wx) - 1, x1 = (int)std::ceil((cx + 1) * wx) + 1;
+        int y0 = (int)std::floor(cy * wy) - 1, y1 = (int)std::ceil((cy + 1) * wy) + 1;
+        int z0 = (int)std::floor(cz * wz) - 1, z1 = (int)std::ceil((cz + 1) * wz) + 1;
+        if (!v.f.isNvdb) {
+          x0 = std::max(x0, 0); y0 = std::max(y0, 0); z0 = std::max(z0, 0);
+          x1 = std::min(x1, nx - 1); y1 = std::min(y1, ny - 1); z1 = std::min(z1, nz - 1);
+        }
+        float lo = std::numeric_limits<float>::max(), hi = -std::numeric_limits<float>::max();
+        for (int z = z0; z <= z1; ++z)
+          for (int y = y0; y <= y1; ++y)
+            for (int x = x0; x <= x1; ++x) {
+              const float s = v.f.isNvdb ? v.f.nvdb.getValue(x + bx, y + by, z + bz) : v.f.at(x, y, z);
+              lo = std::fmin(lo, s);
+              hi = std::fmax(hi, s);
+            }
+        float m = 0.f;
+        if (lo <= hi) {
+          const float c0 = position(lo, v.vrLo, v.vrHi), c1 = position(hi, v.vrLo, v.vrHi);
+          int i0 = (int)std::floor(c0 * 256.0f - 0.5f) - 1, i1 = (int)std::floor(c1 * 256.0f - 0.5f) + 2;
+          i0 = std::max(0, std::min(i0, DVR_TF_SIZE - 1));
+          i1 = std::max(0, std::min(i1, DVR_TF_SIZE - 1));
+          for (int i = i0; i <= i1; ++i)
+            m = std::fmax(m, v.tf[4 * i + 3]);
+        }
+        g.maj[((size_t)cz * g.gy + cy) * g.gx + cx] = m;
+      }
+  return g;
+}
+
+// _sampleDistance (volumeIntegration.h:167-238) + dda3 (dda.h:43-121) + projectOnGrid (uniformGrid.h:44-50)
+float sampleDistanceSegment(const Volume &v, const DdaGrid &g, V3 lorg, V3 ldir, float tLower, float tUpper,
+    Philox &rng, V3 &albedo, float &extinction, float &tr, uint64_t &samples)
+{
+  const float stepSize = v.f.stepSize;
+  float t_out = tUpper;
+  tr = 1.f;
+  const V3 oorg = lorg + ldir * tLower;
+  const float rayUpper = tUpper - tLower;
+  const V3 rcp = {ldir.x != 0.f ? 1.f / ldir.x : 0.f, ldir.y != 0.f ? 1.f / ldir.y : 0.f,
+      ldir.z != 0.f ? 1.f / ldir.z : 0.f};
+  const V3 lo = (v.f.lo - oorg) * rcp, hi = (v.f.hi - oorg) * rcp;
+  const V3 tnear = {std::fmin(lo.x, hi.x), std::fmin(lo.y, hi.y), std::fmin(lo.z, hi.z)};
+  const V3 tfar = {std::fmax(lo.x, hi.x), std::fmax(lo.y, hi.y), std::fmax(lo.z, hi.z)};
+  const V3 v01 = {(oorg.x - v.f.lo.x) / (v.f.hi.x - v.f.lo.x), (oorg.y - v.f.lo.y) / (v.f.hi.y - v.f.lo.y),
+      (oorg.z - v.f.lo.z) / (v.f.hi.z - v.f.lo.z)};
+  int c[3] = {std::min(std::max((int)(v01.x * (float)g.gx), 0), g.gx - 1),
+      std::min(std::max((int)(v01.y * (float)g.gy), 0), g.gy - 1),
+      std::min(std::max((int)(v01.z * (float)g.gz), 0), g.gz - 1)};
+  const int gd[3] = {g.gx, g.gy, g.gz};
+  const float d[3] = {ldir.x, ldir.y, ldir.z};
+  const float tn[3] = {tnear.x, tnear.y, tnear.z}, tf_[3] = {tfar.x, tfar.y, tfar.z};
+  float dist[3], tnext[3];
+  int step[3], stop[3];
+  for (int a = 0; a < 3; ++a) {
+    dist[a] = (tf_[a] - tn[a]) / (float)gd[a];
+    step[a] = d[a] > 0.f ? 1 : -1;
+    stop[a] = d[a] > 0.f ? gd[a] : -1;
+    tnext[a] = std::fmaf((float)(d[a] > 0.f ? c[a] + 1 : gd[a] - c[a]), dist[a], tn[a]);
+  }
+  float t0 = 0.f;
+  while (true) {
+    const float tmin3 = std::fmin(std::fmin(tnext[0], tnext[1]), tnext[2]);
+    const float t1 = std::fmin(tmin3, rayUpper);
+    const float majorant = g.maj[((size_t)c[2] * g.gy + c[1]) * g.gx + c[0]];
+    float t = t0;
+    while (majorant > 0.f) {
+      t = std::fmaf(-(std::log(1.f - rng.uniform()) / majorant), stepSize, t);
+      if (t >= t1)
+        break;
+      const V3 p = lorg + ldir * (t + tLower);
+      const float s = v.f.sample(p);
+      samples++;
+      if (!std::isnan(s)) {
+        float co[4];
+        tfFetch(v.tf, position(s, v.vrLo, v.vrHi), co);
+        albedo = {co[0], co[1], co[2]};
+        extinction = co[3];
+        const float u = rng.uniform();
+        if (extinction >= u * majorant) {
+          tr = 0.f;
+          t_out = t;
+          return t_out + tLower;
+        }
+      }
+    }
+    bool out = false;
+    for (int a = 0; a < 3 && !out; ++a)
+      if (tnext[a] == tmin3) {
+        tnext[a] += dist[a];
+        c[a] += step[a];
+        if (c[a] == stop[a])
+          out = true;
+      }
+    if (out)
+      break;
+    t0 = t1;
+  }
+  return t_out + tLower;
+}
+
+// sampleDistanceAllVolumes, volumeIntegration.h:352-389
+float sampleDistanceAllVolumes(const std::vector<Volume> &vols, const std::vector<DdaGrid> &grids, V3 org, V3 dir,
+    float tmin, float tfar, Philox &rng, V3 &albedo, float &extinction, float &transmittance, uint64_t &samples)
+{
+  float rayLower = tmin;
+  float depth = tfar;
+  transmittance = 1.f;
+  int last = -1;
+  while (true) {
+    int best = -1;
+    float bt0 = 0.f, bt1 = 0.f;
+    V3 bo = org, bd = dir;
+    for (int i = 0; i < (int)vols.size(); ++i) {
+      if (i == last)
+        continue;
+      V3 lo = org, ld = dir;
+      if (!vols[i].identity) {
+        lo = xfmPoint(vols[i].xfm, org);
+        ld = xfmVector(vols[i].xfm, dir);
+      }
+      float t0, t1;
+      if (!intersectVolume(vols[i], lo, ld, rayLower, tfar, t0, t1))
+        continue;
+      if (best < 0 || t0 < bt0) {
+        best = i;
+        bt0 = t0;
+        bt1 = t1;
+        bo = lo;
+        bd = ld;
+      }
+    }
+    if (best < 0)
+      break;
+    bt1 = std::fmin(tfar, bt1);
+    V3 alb{0.f, 0.f, 0.f};
+    float ext = 0.f, tr = 0.f;
+    const float dd = sampleDistanceSegment(vols[best], grids[best], bo, bd, bt0, bt1, rng, alb, ext, tr, samples);
+    if (dd < depth) {
+      depth = dd;
+      albedo = alb;
+      extinction = ext;
+      transmittance = tr;
+    }
+    rayLower = bt1 + 1e-3f;
+    last = best;
+  }
+  return depth;
+}
+
+// computeOrthonormalBasis / sampleUnitSphere, gpu_util.h:205-243
+V3 sampleUnitSphere(Philox &rng, V3 n)
+{
+  const float cost = 1.f - 2.f * rng.uniform();
+  const float sint = std::sqrt(std::fmax(0.f, 1.f - cost * cost));
+  const float phi = 2.f * 3.14159265358979323846f * rng.uniform();
+  const float sign = n.z >= 0.0f ? 1.0f : -1.0f;
+  const float a = -1.0f / (sign + n.z);
+  const float b = n.x * n.y * a;
+  const V3 u = {1.0f + sign * n.x * n.x * a, sign * b, -sign * n.x};
+  const V3 w = {b, sign + n.y * n.y * a, -n.y};
+  const float sx = sint * std::cos(phi), sy = sint * std::sin(phi), sz = -cost;
+  return {u.x * sx + w.x * sy + n.x * sz, u.y * sx + w.y * sy + n.y * sz, u.z * sx + w.z * sy + n.z * sz};
+}
+
+struct DptPath // PathData, DiffusePathTracer_ptx.cu:45-50 (declared OUTSIDE the numIterations loop)
+{
+  int depth = 0;
+  V3 Lw{1.f, 1.f, 1.f};
+};
+
+// the bounce loop of DiffusePathTracer_ptx.cu:111-196 for a world without surfaces
+V3 dptTracePath(const std::vector<Volume> &vols, const std::vector<DdaGrid> &grids, V3 org, V3 dir,
+    const DvrFrameParams &P, Philox &rng, DptPath &path, uint64_t &samples)
+{
+  const int maxDepth = P.maxDepth <= 0 ? 5 : std::min(P.maxDepth, 256);
+  const float occl = P.occlusionDistance > 0.f ? P.occlusionDistance : 1e20f;
+  float tmin = 0.f, tmax = std::numeric_limits<float>::max();
+  while (true) {
+    V3 volumeColor{0.f, 0.f, 0.f};
+    float volumeOpacity = 0.f, Tr = 0.f;
+    const float volumeDepth =
+        sampleDistanceAllVolumes(vols, grids, org, dir, tmin, tmax, rng, volumeColor, volumeOpacity, Tr, samples);
+    if (!(Tr < 1.f))
+      break;
+    if (path.depth++ >= maxDepth) {
+      path.Lw = {0.f, 0.f, 0.f};
+      break;
+    }
+    const V3 pos = org + dir * volumeDepth;
+    path.Lw = path.Lw * volumeColor;
+    const float Pr = cmax(path.Lw);
+    if (Pr < .2f) {
+      if (rng.uniform() > Pr) {
+        path.Lw = {0.f, 0.f, 0.f};
+        break;
+      }
+      path.Lw = {path.Lw.x / Pr, path.Lw.y / Pr, path.Lw.z / Pr};
+    }
+    const V3 scatter = sampleUnitSphere(rng, V3{-dir.x, -dir.y, -dir.z});
+    org = pos;
+    dir = scatter;
+    tmin = 0.f;
+    tmax = occl;
+  }
+  if (path.depth)
+    return path.Lw * P.ambientRadiance;
+  return {P.background[0], P.background[1], P.background[2]};
+}
+
 inline float clamp01(float v) { return std::fmin(std::fmax(v, 0.f), 1.f); }
 inline float toSrgb(float c)
 {
@@ -543,6 +785,45 @@ void accumResults(const Frame &f, uint32_t px, uint32_t py, const float color[4]
   }
 }
 
+void makeVolume(const OracleVolume &o, Volume &v)
+{
+  v.f.vox = o.voxels;
+  v.f.nx = o.dims[0];
+  v.f.ny = o.dims[1];
+  v.f.nz = o.dims[2];
+  v.f.origin = v3(o.origin);
+  v.f.spacing = v3(o.spacing);
+  v.f.invSpacing = {1.f / (o.spacing[0] * (float)o.dims[0]), 1.f / (o.spacing[1] * (float)o.dims[1]),
+      1.f / (o.spacing[2] * (float)o.dims[2])};
+  v.f.lo = v.f.origin;
+  v.f.hi = {o.origin[0] + ((float)o.dims[0] - 1.f) * o.spacing[0], o.origin[1] + ((float)o.dims[1] - 1.f) * o.spacing[1],
+      o.origin[2] + ((float)o.dims[2] - 1.f) * o.spacing[2]};
+  v.f.stepSize = std::fmin(std::fmin(o.spacing[0] / 2.f, o.spacing[1] / 2.f), o.spacing[2] / 2.f);
+  v.f.nearest = o.filterNearest != 0;
+  if (o.nvdbGrid) { // NvdbRegularField: bounds = world bbox, step = min(voxelSize)/2 (NvdbRegularField.cpp:105-127)
+    const uint8_t *blob = (const uint8_t *)o.nvdbGrid;
+    v.f.isNvdb = true;
+    v.f.nvdb.open(blob);
+    double wb[6], vs[3];
+    std::memcpy(wb, blob + 560, sizeof(wb));
+    std::memcpy(vs, blob + 608, sizeof(vs));
+    v.f.lo = {(float)wb[0], (float)wb[1], (float)wb[2]};
+    v.f.hi = {(float)wb[3], (float)wb[4], (float)wb[5]};
+    v.f.stepSize = std::fmin(std::fmin((float)vs[0], (float)vs[1]), (float)vs[2]) / 2.0f;
+  }
+  v.tf = o.tf;
+  v.vrLo = o.valueRange[0];
+  v.vrHi = o.valueRange[1];
+  v.oneOverUnitDistance = 1.0f / o.unitDistance;
+  v.id = o.id;
+  v.instId = o.instanceId;
+  std::memcpy(v.xfm, o.worldToObject, sizeof(v.xfm));
+  static const float ident[12] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0};
+  v.identity = std::memcmp(v.xfm, ident, sizeof(ident)) == 0;
+  v.zOwnBegin = o.zOwnEnd > o.zOwnBegin ? o.zOwnBegin : 0;
+  v.zOwnEnd = o.zOwnEnd > o.zOwnBegin ? o.zOwnEnd : o.dims[2];
+}
+
 } // namespace
 
 extern "C" {
@@ -592,45 +873,8 @@ int oracle_render(const DvrFrameParams *params, const DvrCamera *camera, const O
     return -1;
   const DvrFrameParams &P = *params;
   std::vector<Volume> vols(nVolumes);
-  for (int i = 0; i < nVolumes; ++i) {
-    const OracleVolume &o = volumes[i];
-    Volume &v = vols[i];
-    v.f.vox = o.voxels;
-    v.f.nx = o.dims[0];
-    v.f.ny = o.dims[1];
-    v.f.nz = o.dims[2];
-    v.f.origin = v3(o.origin);
-    v.f.spacing = v3(o.spacing);
-    v.f.invSpacing = {1.f / (o.spacing[0] * (float)o.dims[0]), 1.f / (o.spacing[1] * (float)o.dims[1]),
-        1.f / (o.spacing[2] * (float)o.dims[2])};
-    v.f.lo = v.f.origin;
-    v.f.hi = {o.origin[0] + ((float)o.dims[0] - 1.f) * o.spacing[0], o.origin[1] + ((float)o.dims[1] - 1.f) * o.spacing[1],
-        o.origin[2] + ((float)o.dims[2] - 1.f) * o.spacing[2]};
-    v.f.stepSize = std::fmin(std::fmin(o.spacing[0] / 2.f, o.spacing[1] / 2.f), o.spacing[2] / 2.f);
-    v.f.nearest = o.filterNearest != 0;
-    if (o.nvdbGrid) { // NvdbRegularField: bounds = world bbox, step = min(voxelSize)/2 (NvdbRegularField.cpp:105-127)
-      const uint8_t *blob = (const uint8_t *)o.nvdbGrid;
-      v.f.isNvdb = true;
-      v.f.nvdb.open(blob);
-      double wb[6], vs[3];
-      std::memcpy(wb, blob + 560, sizeof(wb));
-      std::memcpy(vs, blob + 608, sizeof(vs));
-      v.f.lo = {(float)wb[0], (float)wb[1], (float)wb[2]};
-      v.f.hi = {(float)wb[3], (float)wb[4], (float)wb[5]};
-      v.f.stepSize = std::fmin(std::fmin((float)vs[0], (float)vs[1]), (float)vs[2]) / 2.0f;
-    }
-    v.tf = o.tf;
-    v.vrLo = o.valueRange[0];
-    v.vrHi = o.valueRange[1];
-    v.oneOverUnitDistance = 1.0f / o.unitDistance;
-    v.id = o.id;
-    v.instId = o.instanceId;
-    std::memcpy(v.xfm, o.worldToObject, sizeof(v.xfm));
-    static const float ident[12] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0};
-    v.identity = std::memcmp(v.xfm, ident, sizeof(ident)) == 0;
-    v.zOwnBegin = o.zOwnEnd > o.zOwnBegin ? o.zOwnBegin : 0;
-    v.zOwnEnd = o.zOwnEnd > o.zOwnBegin ? o.zOwnEnd : o.dims[2];
-  }
+  for (int i = 0; i < nVolumes; ++i)
+    makeVolume(volumes[i], vols[i]);
   Camera cam;
   cam.type = camera->type;
   std::memcpy(cam.region, camera->region, sizeof(cam.region));
@@ -664,6 +908,11 @@ int oracle_render(const DvrFrameParams *params, const DvrCamera *camera, const O
   const float invW = 1.f / (float)P.width, invH = 1.f / (float)P.height;
   const int y0 = rowBegin > 0 ? rowBegin : 0, y1 = (rowEnd > 0 && rowEnd < launchH) ? rowEnd : launchH;
   uint64_t samples = 0;
+  const bool dpt = P.integrator == DVR_INTEGRATOR_DPT;
+  std::vector<DdaGrid> grids;
+  if (dpt)
+    for (const Volume &v : vols)
+      grids.push_back(buildDdaGrid(v));
 
 #pragma omp parallel for schedule(dynamic, 1) reduction(+ : samples)
   for (int ly = y0; ly < y1; ++ly) {
@@ -674,6 +923,7 @@ int oracle_render(const DvrFrameParams *params, const DvrCamera *camera, const O
         continue;
       Philox rng;
       rng.init((uint64_t)(int64_t)(int)(y * (int)P.width + x), 0, (uint64_t)((int64_t)P.frameID * 512));
+      DptPath path;
       for (int it = 0; it < iters; ++it) {
         float r[4];
         rng.uniform4(r);
@@ -681,6 +931,14 @@ int oracle_render(const DvrFrameParams *params, const DvrCamera *camera, const O
         const float sy = (centered ? (float)y : (float)y + r[1]) * invH;
         V3 org, dir;
         cameraCreateRay(cam, sx, sy, r[2], r[3], org, dir);
+        if (dpt) { // DiffusePathTracer_ptx.cu:96-215: depth / ids keep their initial values (tmax, ~0u)
+          const float nrm[3] = {dir.x, dir.y, dir.z};
+          const V3 c = dptTracePath(vols, grids, org, dir, P, rng, path, samples);
+          const float c4[4] = {c.x, c.y, c.z, 1.f};
+          const float alb[3] = {P.background[0], P.background[1], P.background[2]};
+          accumResults(F, (uint32_t)x, (uint32_t)y, c4, std::numeric_limits<float>::max(), alb, nrm, ~0u, ~0u, ~0u, it);
+          continue;
+        }
         V3 color{0.f, 0.f, 0.f};
         float opacity = 0.f;
         uint32_t objID = ~0u, instID = ~0u;
@@ -702,6 +960,25 @@ int oracle_render(const DvrFrameParams *params, const DvrCamera *camera, const O
   }
   if (samplesOut)
     *samplesOut = samples;
+  return 0;
+}
+
+// the delta-tracking grid the dpt restatement walks (dims + majorants), for checking the product's grid
+int oracle_dda_majorants(const OracleVolume *volume, int32_t dims[3], float *out, size_t capacity)
+{
+  if (!volume || !dims)
+    return -1;
+  Volume v;
+  makeVolume(*volume, v);
+  const DdaGrid g = buildDdaGrid(v);
+  dims[0] = g.gx;
+  dims[1] = g.gy;
+  dims[2] = g.gz;
+  if (out) {
+    if (capacity < g.maj.size())
+      return -2;
+    std::memcpy(out, g.maj.data(), g.maj.size() * sizeof(float));
+  }
   return 0;
 }
 

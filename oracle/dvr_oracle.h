@@ -52,6 +52,9 @@ void oracle_philox_uniforms(uint64_t seed, uint64_t offset, int n, float *out);
 int oracle_render(const DvrFrameParams *params, const DvrCamera *camera, const OracleVolume *volumes, int nVolumes,
     const OracleBuffers *buffers, uint64_t *samplesOut, int rowBegin, int rowEnd);
 
+/* dpt renderer: the delta-tracking grid (ceil(dims/16) cells over the bounds) with conservative majorants */
+int oracle_dda_majorants(const OracleVolume *volume, int32_t dims[3], float *out, size_t capacity);
+
 #ifdef __cplusplus
 }
 #endif

@@ -136,6 +136,68 @@ __global__ void refgpu_raygen(int centerPixel)
   }
 }
 
+// raygen of the dpt renderer for a volume-only world: renderer/DiffusePathTracer_ptx.cu:82-215 with the
+// surface branch (intersectSurface always misses here) removed.  sampleDistanceAllVolumes, _sampleDistance,
+// dda3, sampleUnitSphere and accumResults are the reference's own.
+struct RefPathData // DiffusePathTracer_ptx.cu:45-50 without the surface Hit
+{
+  int depth{0};
+  vec3 Lw{1.f};
+};
+
+__global__ void refgpu_raygen_dpt()
+{
+  auto &rendererParams = frameData.renderer;
+  auto &dptParams = rendererParams.params.dpt;
+  RefPathData pathData;
+  auto ss = createScreenSample(frameData);
+  if (pixelOutOfFrame(ss.pixel, frameData.fb))
+    return;
+  for (int i = 0; i < frameData.renderer.numIterations; i++) {
+    auto ray = makePrimaryRay(ss);
+    auto tmax = ray.t.upper;
+    const auto bg = getBackground(frameData, ss.screen, ray.dir);
+    vec3 outColor(bg);
+    vec3 outNormal = ray.dir;
+    float outDepth = tmax;
+    uint32_t primID = ~0u, objID = ~0u, instID = ~0u;
+    while (true) {
+      float volumeOpacity = 0.f;
+      vec3 volumeColor(0.f);
+      float Tr = 0.f;
+      uint32_t vObjID = ~0u, vInstID = ~0u;
+      const float volumeDepth = sampleDistanceAllVolumes(
+          ss, ray, 0 /*RayType::DIFFUSE_RADIANCE*/, ray.t.upper, volumeColor, volumeOpacity, Tr, vObjID, vInstID);
+      const bool volumeHit = Tr < 1.f;
+      if (!volumeHit)
+        break;
+      if (pathData.depth++ >= dptParams.maxDepth) {
+        pathData.Lw = vec3(0.f);
+        break;
+      }
+      const vec3 pos = ray.org + volumeDepth * ray.dir;
+      pathData.Lw *= volumeColor;
+      float P = glm::compMax(pathData.Lw);
+      if (P < .2f) {
+        if (curand_uniform(&ss.rs) > P) {
+          pathData.Lw = vec3(0.f);
+          break;
+        }
+        pathData.Lw /= P;
+      }
+      const vec3 scatterDir = sampleUnitSphere(ss.rs, -ray.dir);
+      ray.org = pos;
+      ray.dir = scatterDir;
+      ray.t.lower = 0.f;
+      ray.t.upper = rendererParams.occlusionDistance;
+      // the reference's `if (pathData.depth == 0)` block can never run after the increment above
+    }
+    vec3 Ld(rendererParams.ambientIntensity);
+    vec3 color = pathData.depth ? pathData.Lw * Ld : vec3(bg);
+    accumResults(frameData.fb, ss.pixel, vec4(color, 1.f), outDepth, outColor, outNormal, primID, objID, instID, i);
+  }
+}
+
 template <typename T>
 __global__ void refgpu_fill(T *p, size_t n, T v)
 {
@@ -164,6 +226,8 @@ struct RefVolume
   cudaArray_t arr = nullptr;
   cudaTextureObject_t tex = 0;
   VolumeGPUData gpu{};
+  ivec3 gridDims{0};            // injected delta-tracking grid (refgpu_volume_set_grid)
+  float *maxOpacities = nullptr;
 };
 
 static thread_local char g_err[512];
@@ -295,9 +359,24 @@ int refgpu_volume_create(RefField *field, const float *tfRgba, const float value
   return 0;
 }
 
+// The delta-tracking grid of the volume's field (UniformGridData).  The reference builds it in
+// UniformGrid.cu with two defects (non-conservative cell ranges, majorants from the wrong value
+// range) that make its tracker biased; the checker therefore walks the SAME reference tracker code over a grid
+// handed in by the test (the product's own grid), which isolates the tracker from the grid build.
+int refgpu_volume_set_grid(RefVolume *v, const int dims[3], const float *hostMaxOpacities)
+{
+  const size_t n = (size_t)dims[0] * dims[1] * dims[2];
+  if (v->maxOpacities) cudaFree(v->maxOpacities);
+  RCK(cudaMalloc(&v->maxOpacities, n * sizeof(float)));
+  RCK(cudaMemcpy(v->maxOpacities, hostMaxOpacities, n * sizeof(float), cudaMemcpyDefault)); // host or device source
+  v->gridDims = ivec3(dims[0], dims[1], dims[2]);
+  return 0;
+}
+
 int refgpu_volume_destroy(RefVolume *v)
 {
   if (!v) return 0;
+  if (v->maxOpacities) cudaFree(v->maxOpacities);
   if (v->tex) cudaDestroyTextureObject(v->tex);
   if (v->arr) cudaFreeArray(v->arr);
   delete v;
@@ -323,6 +402,7 @@ struct RefScene
   RefInstanceXfm *xfms = nullptr;
   CameraGPUData *camera = nullptr;
   int n = 0;
+  bool hasGrid = true;
 };
 
 int refgpu_scene_create(const RefInstance *inst, int n, RefScene **out)
@@ -338,6 +418,11 @@ int refgpu_scene_create(const RefInstance *inst, int n, RefScene **out)
   static const float ident[12] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0};
   for (int i = 0; i < n; ++i) {
     fields[i] = inst[i].volume->field->gpu;
+    fields[i].grid.dims = inst[i].volume->gridDims;
+    fields[i].grid.worldBounds = inst[i].volume->field->bounds;
+    fields[i].grid.maxOpacities = inst[i].volume->maxOpacities;
+    if (!inst[i].volume->maxOpacities)
+      s->hasGrid = false;
     vols[i] = inst[i].volume->gpu;
     vols[i].data.tf1d.field = i;
     idx[i] = i;
@@ -420,8 +505,9 @@ int refgpu_render(const DvrFrameParams *p, const DvrCamera *c, RefScene *scene, 
   fd.renderer.backgroundMode = BackgroundMode::COLOR;
   fd.renderer.background.color = vec4(p->background[0], p->background[1], p->background[2], p->background[3]);
   fd.renderer.ambientColor = vec3(1.f);
-  fd.renderer.ambientIntensity = 1.f;
-  fd.renderer.occlusionDistance = 1e20f;
+  fd.renderer.ambientIntensity = p->ambientRadiance;
+  fd.renderer.occlusionDistance = p->occlusionDistance > 0.f ? p->occlusionDistance : 1e20f;
+  fd.renderer.params.dpt.maxDepth = p->maxDepth <= 0 ? 5 : (p->maxDepth > 256 ? 256 : p->maxDepth);
   fd.renderer.cullTriangleBF = false;
   fd.renderer.inverseVolumeSamplingRate = p->inverseVolumeSamplingRate;
   fd.renderer.numIterations = p->checkerboardID >= 0 ? 1 : (p->numIterations > 1 ? p->numIterations : 1);
@@ -449,7 +535,15 @@ int refgpu_render(const DvrFrameParams *p, const DvrCamera *c, RefScene *scene, 
   const uint32_t lw = p->checkerboardID >= 0 ? (p->width + 1) / 2 : p->width;
   const uint32_t lh = p->checkerboardID >= 0 ? (p->height + 1) / 2 : p->height;
   dim3 block(16, 8), grid((lw + 15) / 16, (lh + 7) / 8);
-  refgpu_raygen<<<grid, block, 0, s>>>(p->integrator == DVR_INTEGRATOR_RAYCAST ? 1 : 0);
+  if (p->integrator == DVR_INTEGRATOR_DPT) {
+    for (int i = 0; i < scene->n; ++i)
+      if (!scene->hasGrid) {
+        snprintf(g_err, sizeof(g_err), "dpt needs refgpu_volume_set_grid on every volume");
+        return -1;
+      }
+    refgpu_raygen_dpt<<<grid, block, 0, s>>>();
+  } else
+    refgpu_raygen<<<grid, block, 0, s>>>(p->integrator == DVR_INTEGRATOR_RAYCAST ? 1 : 0);
   RCK(cudaGetLastError());
   return 0;
 }

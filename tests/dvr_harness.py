@@ -79,6 +79,9 @@ class SceneDesc:
     background: tuple = (0.1, 0.1, 0.1, 1.0)
     num_iterations: int = 1
     channels: tuple = ("depth", "primId", "objId", "instId")
+    max_depth: int = 5  # dpt integrator only
+    ambient_radiance: float = 1.0
+    occlusion_distance: float = 1e20
 
 
 def default_scene(n=64, width=256, height=256, rate=0.5, field="ml", **kw) -> SceneDesc:
@@ -109,13 +112,13 @@ def _alloc_np(scene: SceneDesc):
 
 def _params(scene, frame_id, cb, **kw):
     return capi.frame_params(scene.width, scene.height, scene.fmt, scene.integrator, frame_id, cb,
-                             scene.num_iterations, scene.volume_sampling_rate, scene.background, **kw)
+                             scene.num_iterations, scene.volume_sampling_rate, scene.background,
+                             max_depth=scene.max_depth, ambient_radiance=scene.ambient_radiance,
+                             occlusion_distance=scene.occlusion_distance, **kw)
 
 
 # ------------------------------------------------------------------------------------------------------------
-def render_oracle(scene: SceneDesc, frames=1, checkerboard=False, slab=None, state=None, return_samples=False):
-    """O-cpu; `frames` successive renderFrame calls with accumulation (Frame::newFrame bookkeeping)."""
-    out = state or _alloc_np(scene)
+def _oracle_volumes(scene: SceneDesc, slab=None):
     vols = (ob.OracleVolume * max(len(scene.volumes), 1))()
     keep = []
     for i, v in enumerate(scene.volumes):
@@ -140,6 +143,27 @@ def render_oracle(scene: SceneDesc, frames=1, checkerboard=False, slab=None, sta
         o.instanceId = v.inst_id
         if slab is not None:
             o.zOwnBegin, o.zOwnEnd = slab
+    return vols, keep
+
+
+def oracle_dda_grids(scene: SceneDesc):
+    """[(dims, float32[gz,gy,gx])] of O-cpu's delta-tracking grids, one per volume."""
+    vols, keep = _oracle_volumes(scene)
+    out = []
+    for i in range(len(scene.volumes)):
+        dims = (C.c_int32 * 3)()
+        assert ob.cpu().oracle_dda_majorants(C.byref(vols[i]), dims, None, C.c_size_t(0)) == 0
+        a = np.zeros(dims[0] * dims[1] * dims[2], np.float32)
+        assert ob.cpu().oracle_dda_majorants(C.byref(vols[i]), dims, a.ctypes.data_as(C.c_void_p),
+                                             C.c_size_t(a.size)) == 0
+        out.append((tuple(dims), a.reshape(dims[2], dims[1], dims[0])))
+    return out
+
+
+def render_oracle(scene: SceneDesc, frames=1, checkerboard=False, slab=None, state=None, return_samples=False):
+    """O-cpu; `frames` successive renderFrame calls with accumulation (Frame::newFrame bookkeeping)."""
+    out = state or _alloc_np(scene)
+    vols, keep = _oracle_volumes(scene, slab)
     b = ob.OracleBuffers()
     b.colorAccumulation = out["accum"].ctypes.data_as(C.c_void_p)
     b.outColor = out["color"].ctypes.data_as(C.c_void_p)
@@ -231,6 +255,18 @@ class CudaScene:
         capi.render(p, self.scene.camera, self.instances, self.n, self.fb)
         return None
 
+    def dda_grids(self):
+        """[(dims, float32[nz,ny,nx] majorants)] of the delta-tracking grids (built on demand)."""
+        out = []
+        for v in self.volumes:
+            dims, ptr = v.dda_majorants()
+            n = dims[0] * dims[1] * dims[2]
+            a = np.zeros(n, np.float32)
+            self.torch.cuda.synchronize()
+            C.CDLL("libcudart.so").cudaMemcpy(a.ctypes.data_as(C.c_void_p), C.c_void_p(ptr), C.c_size_t(n * 4), C.c_int(2))
+            out.append((dims, a.reshape(dims[2], dims[1], dims[0])))
+        return out
+
     def download(self):
         self.torch.cuda.synchronize()
         out = {}
@@ -259,8 +295,9 @@ def render_cuda(scene: SceneDesc, frames=1, checkerboard=False, skip=False):
 
 
 # ------------------------------------------------------------------------------------------------------------
-def render_refgpu(scene: SceneDesc, frames=1, checkerboard=False):
-    """O-gpu: the reference's device headers (tex3D / tex1D / cuRAND) on the same GPU."""
+def render_refgpu(scene: SceneDesc, frames=1, checkerboard=False, grids=None):
+    """O-gpu: the reference's device headers (tex3D / tex1D / cuRAND) on the same GPU.
+    grids: per volume (dims, majorants) of the delta-tracking grid (dpt integrator only)."""
     import torch
     lib = ob.refgpu()
     fields, vols = [], []
@@ -284,6 +321,11 @@ def render_refgpu(scene: SceneDesc, frames=1, checkerboard=False):
         rc = lib.refgpu_volume_create(f, tf.ctypes.data_as(C.c_void_p), (C.c_float * 2)(*v.value_range),
                                       C.c_float(v.unit_distance), C.c_uint32(v.vol_id), C.byref(h))
         assert rc == 0, lib.refgpu_last_error()
+        if grids is not None:
+            gd, gm = grids[i]
+            gm = np.ascontiguousarray(gm, np.float32)
+            rc = lib.refgpu_volume_set_grid(h, (C.c_int * 3)(*gd), gm.ctypes.data_as(C.c_void_p))
+            assert rc == 0, lib.refgpu_last_error()
         fields.append(f)
         vols.append(h)
         inst[i].volume = h
@@ -432,3 +474,50 @@ def scene_zoo():
     s.volumes = []
     zoo["empty_world"] = (s, 1, False)
     return zoo
+
+
+# ------------------------------------------------------------------------------------------------------------
+# scenes for the dpt renderer (delta tracking); golden fixture: tests/golden/refgpu_dpt.npz
+# ------------------------------------------------------------------------------------------------------------
+DPT_KINDS = ("ml40", "ml77", "nvdb", "two")
+DPT_GOLDEN_FRAMES = 8
+
+
+def dpt_scene(kind, wh=96, **kw) -> SceneDesc:
+    if kind == "nvdb":
+        from visrtx_b200 import nvdb_writer
+        blob = nvdb_writer.fog_sphere(30.0)
+        tf = capi.tf_discretize(color=scenes.tsd_default_colormap(256),
+                                opacity=np.linspace(0.0, 0.6, 16, dtype=np.float32))
+        v = VolumeDesc(np.zeros((1, 1, 1), np.float32), tf=tf, nvdb=blob, unit_distance=1.0)
+        lo, hi = v.bounds()
+        pose = scenes.orbit_camera(lo, hi, wh, wh, dist_scale=1.2)
+        cam = capi.camera_perspective(pose.position, pose.direction, pose.up, pose.fovy, pose.aspect)
+        return SceneDesc([v], wh, wh, cam, fmt=capi.DVR_FORMAT_FLOAT32_VEC4, integrator=capi.DVR_INTEGRATOR_DPT,
+                         channels=("depth", "objId", "albedo", "normal"), **kw)
+    if kind == "two":
+        s, _, _ = scene_zoo()["two_volumes_lens"]
+        s.integrator = capi.DVR_INTEGRATOR_DPT
+        s.num_iterations = 1
+        s.fmt = capi.DVR_FORMAT_FLOAT32_VEC4
+        if wh != 96:
+            raise ValueError("the two-volume scene is fixed at 96x96")
+        for k, v in kw.items():
+            setattr(s, k, v)
+        return s
+    n = {"ml40": 40, "ml77": 77}[kind]
+    s = default_scene(n, wh, wh, integrator=capi.DVR_INTEGRATOR_DPT, fmt=capi.DVR_FORMAT_FLOAT32_VEC4,
+                      channels=("depth", "objId", "albedo", "normal"), **kw)
+    # a piecewise opacity so that the grid has empty, thin and dense cells
+    s.volumes[0].tf = capi.tf_discretize(color=scenes.tsd_default_colormap(256),
+                                         opacity=np.array([0.0, 0.05, 0.8, 0.1, 1.0], np.float32))
+    return s
+
+
+def frac_close(a, b, fmt, tol=2.0):
+    """fraction of pixels whose colour differs by <= tol/255"""
+    if fmt == capi.DVR_FORMAT_FLOAT32_VEC4:
+        d = np.abs(a - b).max(axis=-1) * 255.0
+    else:
+        d = np.abs(unpack_rgba8(a) - unpack_rgba8(b)).max(axis=-1)
+    return float((d <= tol).mean())

@@ -32,6 +32,20 @@ def main():
     np.savez_compressed(os.path.join(dst, "refgpu_scenes.npz"), **out)
     print("wrote", os.path.join(dst, "refgpu_scenes.npz"))
 
+    # dpt renderer: the reference's tracker (O-gpu) over O-cpu's majorant grid (the product's grid is tested
+    # to be bit-identical to it); frame 0 colour + the accumulation of DPT_GOLDEN_FRAMES frames
+    dpt = {}
+    for kind in H.DPT_KINDS:
+        scene = H.dpt_scene(kind)
+        grids = H.oracle_dda_grids(scene)
+        r1 = H.render_refgpu(scene, frames=1, grids=grids)
+        rn = H.render_refgpu(scene, frames=H.DPT_GOLDEN_FRAMES, grids=grids)
+        dpt[f"{kind}/color1"] = r1["color"]
+        dpt[f"{kind}/accum"] = rn["accum"]
+        print("dpt", kind, float(r1["color"][:, :3].mean()))
+    np.savez_compressed(os.path.join(dst, "refgpu_dpt.npz"), **dpt)
+    print("wrote", os.path.join(dst, "refgpu_dpt.npz"))
+
 
 if __name__ == "__main__":
     main()

@@ -30,7 +30,7 @@ def test_struct_layouts_match_header_sizes():
     assert C.sizeof(capi.DvrCamera) == 4 + 16 + 12 * 6 + 8
     assert C.sizeof(capi.DvrVolumeInstance) == 8 + 48 + 8
     assert C.sizeof(capi.DvrFrameBuffers) == 8 * 8
-    assert C.sizeof(capi.DvrFrameParams) == 4 * 8 + 16 + 8 + 4 + 4 + 8
+    assert C.sizeof(capi.DvrFrameParams) == 4 * 8 + 16 + 8 + 4 + 4 + 12 + 12
     assert C.sizeof(capi.DvrRenderStats) == 32
 
 

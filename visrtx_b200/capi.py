@@ -22,7 +22,7 @@ DVR_FLOAT32, DVR_UFIXED8, DVR_FIXED8, DVR_UFIXED16, DVR_FIXED16, DVR_FLOAT64, DV
 DVR_FILTER_LINEAR, DVR_FILTER_NEAREST = 0, 1
 DVR_FORMAT_FLOAT32_VEC4, DVR_FORMAT_UFIXED8_VEC4, DVR_FORMAT_UFIXED8_RGBA_SRGB = 0, 1, 2
 DVR_CAMERA_PERSPECTIVE, DVR_CAMERA_ORTHOGRAPHIC = 0, 1
-DVR_INTEGRATOR_RAYCAST, DVR_INTEGRATOR_DEFAULT = 0, 1
+DVR_INTEGRATOR_RAYCAST, DVR_INTEGRATOR_DEFAULT, DVR_INTEGRATOR_DPT = 0, 1, 2
 
 # every symbol include/dvr_b200.h declares (tests check the library exports all of them)
 EXPORTED_SYMBOLS = [
@@ -33,6 +33,7 @@ EXPORTED_SYMBOLS = [
     "dvr_field_bounds", "dvr_field_step_size", "dvr_field_device_bytes", "dvr_field_build_macrocells",
     "dvr_field_macrocells", "dvr_field_value_range",
     "dvr_volume_create", "dvr_volume_update", "dvr_volume_destroy", "dvr_volume_majorants",
+    "dvr_volume_dda_majorants",
     "dvr_render", "dvr_render_instrumented", "dvr_launch_count",
     "dvr_render_partial", "dvr_render_partial_instrumented", "dvr_composite_over", "dvr_resolve", "dvr_scale_vec3",
     "dvr_composite_resolve_peers", "dvr_render_partial_sync", "dvr_composite_resolve_peers_sync", "dvr_wait_flags",
@@ -68,7 +69,8 @@ class DvrFrameParams(C.Structure):
                 ("frameID", C.c_int32), ("checkerboardID", C.c_int32), ("numIterations", C.c_int32),
                 ("inverseVolumeSamplingRate", C.c_float), ("background", C.c_float * 4),
                 ("tileRank", C.c_uint32), ("tileRanks", C.c_uint32), ("useMacrocellSkipping", C.c_int32),
-                ("tileBand", C.c_int32), ("_reserved", C.c_int32 * 2)]
+                ("tileBand", C.c_int32), ("maxDepth", C.c_int32), ("ambientRadiance", C.c_float),
+                ("occlusionDistance", C.c_float), ("_reserved", C.c_int32 * 3)]
 
 
 class DvrRenderStats(C.Structure):
@@ -286,6 +288,13 @@ class Volume:
         _check(lib.dvr_volume_majorants(self.handle, C.byref(p)))
         return p.value
 
+    def dda_majorants(self, stream: int = 0):
+        """(dims, device pointer) of the delta-tracking grid; builds it if needed."""
+        p = C.c_void_p()
+        dims = (C.c_uint32 * 3)()
+        _check(lib.dvr_volume_dda_majorants(self.handle, C.c_void_p(stream), dims, C.byref(p)))
+        return tuple(dims), p.value
+
     def destroy(self) -> None:
         if self.handle:
             lib.dvr_volume_destroy(self.handle)
@@ -305,7 +314,8 @@ def make_instances(volumes: Sequence[Volume], xfms=None, inst_ids=None):
 
 def frame_params(width, height, fmt=DVR_FORMAT_UFIXED8_RGBA_SRGB, integrator=DVR_INTEGRATOR_RAYCAST, frame_id=0,
                  checkerboard_id=-1, num_iterations=1, volume_sampling_rate=0.125, background=(0.0, 0.0, 0.0, 1.0),
-                 tile_rank=0, tile_ranks=1, skip=False, tile_band=1) -> DvrFrameParams:
+                 tile_rank=0, tile_ranks=1, skip=False, tile_band=1, max_depth=5, ambient_radiance=1.0,
+                 occlusion_distance=1e20) -> DvrFrameParams:
     p = DvrFrameParams()
     p.width, p.height, p.format, p.integrator = int(width), int(height), int(fmt), int(integrator)
     p.frameID, p.checkerboardID, p.numIterations = int(frame_id), int(checkerboard_id), int(num_iterations)
@@ -315,6 +325,7 @@ def frame_params(width, height, fmt=DVR_FORMAT_UFIXED8_RGBA_SRGB, integrator=DVR
     p.tileRank, p.tileRanks = int(tile_rank), int(tile_ranks)
     p.useMacrocellSkipping = 1 if skip else 0
     p.tileBand = int(tile_band)
+    p.maxDepth, p.ambientRadiance, p.occlusionDistance = int(max_depth), float(ambient_radiance), float(occlusion_distance)
     return p
 
 

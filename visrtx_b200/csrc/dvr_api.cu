@@ -102,6 +102,9 @@ struct DvrVolume
   float *maxOpacities = nullptr;
   float *maxOpacitiesCoarse = nullptr;
   int3 coarseDims{0, 0, 0};
+  float *ddaMaxOpacities = nullptr; // delta-tracking grid (built on first use by the dpt integrator)
+  float2 *ddaRanges = nullptr;
+  bool ddaValid = false;
   float vrLo = 0.f, vrHi = 1.f, oneOverUnitDistance = 1.f;
   uint32_t id = ~0u;
 };
@@ -768,6 +771,7 @@ int dvr_volume_update(DvrVolume *v, const float *tfRgba, const float valueRange[
   v->vrHi = valueRange[1];
   v->oneOverUnitDistance = 1.0f / unitDistance;
   v->id = id;
+  v->ddaValid = false;
   const int rc = launchMajorants(v->field->ranges, v->field->nCells, v->tf, v->vrLo, v->vrHi, v->maxOpacities, s);
   if (rc != DVR_OK)
     return rc;
@@ -810,7 +814,27 @@ int dvr_volume_destroy(DvrVolume *v)
   if (v->tf) cudaFree(v->tf);
   if (v->maxOpacities) cudaFree(v->maxOpacities);
   if (v->maxOpacitiesCoarse) cudaFree(v->maxOpacitiesCoarse);
+  if (v->ddaMaxOpacities) cudaFree(v->ddaMaxOpacities);
+  if (v->ddaRanges) cudaFree(v->ddaRanges);
   delete v;
+  return DVR_OK;
+}
+
+static int ensureDdaGrid(DvrVolume *v, cudaStream_t s);
+
+int dvr_volume_dda_majorants(DvrVolume *v, void *stream, uint32_t dims[3], const float **maxOpacitiesDev)
+{
+  if (!v || !dims || !maxOpacitiesDev) {
+    setError("dvr_volume_dda_majorants: null argument");
+    return DVR_ERR_INVALID_ARGUMENT;
+  }
+  const int rc = ensureDdaGrid(v, (cudaStream_t)stream);
+  if (rc != DVR_OK)
+    return rc;
+  dims[0] = (uint32_t)v->field->dev.gridDims.x;
+  dims[1] = (uint32_t)v->field->dev.gridDims.y;
+  dims[2] = (uint32_t)v->field->dev.gridDims.z;
+  *maxOpacitiesDev = v->ddaMaxOpacities;
   return DVR_OK;
 }
 
@@ -851,10 +875,39 @@ static void fillInstance(const DvrVolumeInstance &in, InstanceDev &d)
   d.v.maxOpacities = v->maxOpacities;
   d.v.maxOpacitiesCoarse = v->maxOpacitiesCoarse;
   d.v.coarseDims = v->coarseDims;
+  d.v.ddaMaxOpacities = v->ddaMaxOpacities;
+  d.v.ddaDims = v->field->dev.gridDims; // ceil(dims/16), UniformGrid.cu:152-154
   static const float ident[12] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0};
   std::memcpy(d.xfm, in.worldToObject, sizeof(d.xfm));
   d.instId = in.instanceId;
   d.identity = std::memcmp(in.worldToObject, ident, sizeof(ident)) == 0 ? 1u : 0u;
+}
+
+// UniformGrid::init/buildGrid/computeMaxOpacities for the delta tracker: the reference's grid geometry
+// (gridDims cells dividing the bounds evenly) with conservative content.  Built lazily per volume.
+static int ensureDdaGrid(DvrVolume *v, cudaStream_t s)
+{
+  if (v->ddaValid)
+    return DVR_OK;
+  const DvrField *f = v->field;
+  const int3 g = f->dev.gridDims;
+  const size_t n = f->nCells;
+  if (!v->ddaRanges)
+    DVR_CUDA(cudaMalloc(&v->ddaRanges, n * sizeof(float2)));
+  if (!v->ddaMaxOpacities)
+    DVR_CUDA(cudaMalloc(&v->ddaMaxOpacities, n * sizeof(float)));
+  // voxel units spanned by the bounds: dims-1 for node-centred structured fields, dims for NanoVDB boxes
+  const float3 span = f->dev.kind == FIELD_NANOVDB
+      ? make_float3((float)f->dev.dims.x, (float)f->dev.dims.y, (float)f->dev.dims.z)
+      : make_float3((float)f->dev.dims.x - 1.f, (float)f->dev.dims.y - 1.f, (float)f->dev.dims.z - 1.f);
+  const float3 w = make_float3(span.x / (float)g.x, span.y / (float)g.y, span.z / (float)g.z);
+  int rc = launchDdaRangeBuild(f->dev, f->pointTex, g, w, v->ddaRanges, s);
+  if (rc != DVR_OK)
+    return rc;
+  rc = launchMajorants(v->ddaRanges, n, v->tf, v->vrLo, v->vrHi, v->ddaMaxOpacities, s);
+  if (rc == DVR_OK)
+    v->ddaValid = true;
+  return rc;
 }
 
 static int renderImpl(const DvrFrameParams *p, const DvrCamera *camera, const DvrVolumeInstance *instances,
@@ -869,7 +922,7 @@ static int renderImpl(const DvrFrameParams *p, const DvrCamera *camera, const Dv
     return DVR_ERR_INVALID_ARGUMENT;
   }
   if (p->width == 0 || p->height == 0 || p->numIterations < 1 || p->format < 0 || p->format > 2
-      || p->checkerboardID > 3) {
+      || p->checkerboardID > 3 || p->integrator < 0 || p->integrator > DVR_INTEGRATOR_DPT) {
     setError("dvr_render: invalid frame parameters");
     return DVR_ERR_INVALID_ARGUMENT;
   }
@@ -897,6 +950,15 @@ static int renderImpl(const DvrFrameParams *p, const DvrCamera *camera, const Dv
   L.numIterations = p->checkerboardID >= 0 ? 1 : p->numIterations; // Renderer.cpp:168-169
   L.invSamplingRate = p->inverseVolumeSamplingRate;
   L.background = make_float4(p->background[0], p->background[1], p->background[2], p->background[3]);
+  L.maxDepth = p->maxDepth <= 0 ? 5 : (p->maxDepth > 256 ? 256 : p->maxDepth);
+  L.ambientIntensity = p->ambientRadiance;
+  L.occlusionDistance = p->occlusionDistance > 0.f ? p->occlusionDistance : 1e20f;
+  if (p->integrator == DVR_INTEGRATOR_DPT)
+    for (uint32_t i = 0; i < nInstances; ++i) {
+      const int rcg = ensureDdaGrid(const_cast<DvrVolume *>(instances[i].volume), s);
+      if (rcg != DVR_OK)
+        return rcg;
+    }
   L.tileRank = p->tileRanks > 1 ? p->tileRank : 0;
   L.tileRanks = p->tileRanks > 1 ? p->tileRanks : 1;
   L.tileBand = p->tileBand > 1 ? (uint32_t)p->tileBand : 1u;

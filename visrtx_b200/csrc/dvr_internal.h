@@ -38,6 +38,8 @@ struct FrameLaunch
   int format, integrator, frameID, checkerboardID, numIterations;
   float invSamplingRate;
   float4 background;
+  int maxDepth;
+  float ambientIntensity, occlusionDistance;
   uint32_t tileRank, tileRanks, tileBand;
   uint32_t launchW, launchH; // pixel-sample grid actually launched (half size when checkerboarding)
   uint32_t tilesX, tilesY;
@@ -125,6 +127,9 @@ int launchScaleVec3(const float *in, float *out, size_t n, float scale, cudaStre
 int launchMacrocellBuild(cudaTextureObject_t pointTex, int3 dims, int zTexBegin, int texDepth, int3 gridDims,
     float2 *ranges, cudaStream_t s);
 int launchMacrocellBuildNvdb(const FieldDev &f, float2 *ranges, cudaStream_t s);
+// value ranges on the delta-tracking grid: gridDims cells dividing `spanVoxels` voxel units evenly per axis
+int launchDdaRangeBuild(const FieldDev &f, cudaTextureObject_t pointTex, int3 gridDims, float3 cellWidthVoxels,
+    float2 *ranges, cudaStream_t s);
 int launchMajorants(const float2 *ranges, size_t nCells, const float4 *tf, float vrLo, float vrHi,
     float *maxOpacities, cudaStream_t s);
 int launchMajorantsCoarse(const float *fine, int3 gridDims, float *coarse, int3 coarseDims, cudaStream_t s);

@@ -3,6 +3,7 @@
 // Target: sm_100a only.  See DESIGN.md for the layout / scheduling rationale.
 #include "dvr_internal.h"
 #include "dvr_march.cuh"
+#include "dvr_dpt.cuh"
 
 namespace dvr {
 
@@ -227,7 +228,7 @@ struct TfSelectSingle
 #ifndef DVR_OCC_NVDB
 #define DVR_OCC_NVDB 3 // the NanoVDB march chases pointers; A/B on C5 (batch 1): 3/4/5/6 CTAs = 810/732/642/612 fps
 #endif
-template <bool SKIP, bool STATS, bool SINGLE, int KIND>
+template <bool SKIP, bool STATS, bool SINGLE, int KIND, bool DPT>
 __global__ void __launch_bounds__(kBlockThreads, (KIND == FIELD_NANOVDB ? DVR_OCC_NVDB : DVR_OCC)) dvrFrameKernel(const __grid_constant__ FrameLaunch P)
 {
   __shared__ float4 s_tf[(SINGLE ? 1 : kMaxInlineInstances) * DVR_TF_SIZE];
@@ -268,6 +269,7 @@ __global__ void __launch_bounds__(kBlockThreads, (KIND == FIELD_NANOVDB ? DVR_OC
 
     Philox rng;
     rng.init((unsigned long long)(int)(py * P.width + px), (unsigned long long)P.frameID * 512ull);
+    DptPath path{0, f3(1.f, 1.f, 1.f)}; // PathData lives outside the iteration loop in the reference
 
     for (int it = 0; it < P.numIterations; ++it) {
       // makePrimaryRay, cameraCreateRay.h:74-81
@@ -276,6 +278,22 @@ __global__ void __launch_bounds__(kBlockThreads, (KIND == FIELD_NANOVDB ? DVR_OC
       const float sy = __fmul_rn(centered ? (float)py : __fadd_rn((float)py, r.y), P.invH);
       float3 org, dir;
       cameraCreateRay(P.cam, sx, sy, r.z, r.w, org, dir);
+
+      if (DPT) {
+        // DiffusePathTracer_ptx.cu:96-215: colour = Lw * ambient (or the background when nothing scattered),
+        // alpha 1; depth / ids are never set by the reference's loop (its `depth == 0` test runs after the
+        // increment), so depth stays tmax and the ids ~0u; albedo channel = background, normal = primary dir
+        float3 c;
+        if (SINGLE)
+          c = dptTracePath<true, KIND>(P.inl, 1, TfSelectSingle{s_tf}, org, dir, P.maxDepth, P.occlusionDistance,
+              P.ambientIntensity, P.background, rng, path);
+        else
+          c = dptTracePath<false, -1>(inst, nInst, TfSelectShared{s_tf, inst}, org, dir, P.maxDepth,
+              P.occlusionDistance, P.ambientIntensity, P.background, rng, path);
+        accumResults(actx, px, py, make_float4(c.x, c.y, c.z, 1.f), FLT_MAX,
+            f3(P.background.x, P.background.y, P.background.z), dir, ~0u, ~0u, ~0u, it, initFrame && it == 0);
+        continue;
+      }
 
       float3 color = f3(0.f, 0.f, 0.f);
       float opacity = 0.f;
@@ -317,13 +335,13 @@ __global__ void __launch_bounds__(kBlockThreads, (KIND == FIELD_NANOVDB ? DVR_OC
   retireWarp(P.sched, lane);
 }
 
-template <bool SKIP, bool STATS, bool SINGLE, int KIND>
+template <bool SKIP, bool STATS, bool SINGLE, int KIND, bool DPT>
 static int launchFrameT(const FrameLaunch &p, cudaStream_t s)
 {
   static int blocksPerSm = 0;
   if (blocksPerSm == 0) {
     DVR_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(
-        &blocksPerSm, dvrFrameKernel<SKIP, STATS, SINGLE, KIND>, kBlockThreads, 0));
+        &blocksPerSm, dvrFrameKernel<SKIP, STATS, SINGLE, KIND, DPT>, kBlockThreads, 0));
     if (blocksPerSm < 1)
       blocksPerSm = 1;
   }
@@ -335,7 +353,7 @@ static int launchFrameT(const FrameLaunch &p, cudaStream_t s)
     grid = need;
   if (grid == 0)
     grid = 1;
-  dvrFrameKernel<SKIP, STATS, SINGLE, KIND><<<grid, kBlockThreads, 0, s>>>(p);
+  dvrFrameKernel<SKIP, STATS, SINGLE, KIND, DPT><<<grid, kBlockThreads, 0, s>>>(p);
   DVR_CUDA(cudaGetLastError());
   countLaunch();
   return DVR_OK;
@@ -345,14 +363,21 @@ template <bool SKIP, bool STATS>
 static int launchFrameK(const FrameLaunch &p, cudaStream_t s)
 {
   if (p.nInst != 1)
-    return launchFrameT<SKIP, STATS, false, -1>(p, s);
+    return launchFrameT<SKIP, STATS, false, -1, false>(p, s);
   if (p.inl[0].v.f.kind == FIELD_NANOVDB)
-    return launchFrameT<SKIP, STATS, true, FIELD_NANOVDB>(p, s);
-  return launchFrameT<SKIP, STATS, true, FIELD_STRUCTURED>(p, s);
+    return launchFrameT<SKIP, STATS, true, FIELD_NANOVDB, false>(p, s);
+  return launchFrameT<SKIP, STATS, true, FIELD_STRUCTURED, false>(p, s);
 }
 
 int launchFrame(const FrameLaunch &p, bool skip, bool stats, cudaStream_t s)
 {
+  if (p.integrator == DVR_INTEGRATOR_DPT) { // delta tracking: no fixed-step lattice, so no SKIP/STATS variants
+    if (p.nInst != 1)
+      return launchFrameT<false, false, false, -1, true>(p, s);
+    if (p.inl[0].v.f.kind == FIELD_NANOVDB)
+      return launchFrameT<false, false, true, FIELD_NANOVDB, true>(p, s);
+    return launchFrameT<false, false, true, FIELD_STRUCTURED, true>(p, s);
+  }
   if (stats)
     return skip ? launchFrameK<true, true>(p, s) : launchFrameK<false, true>(p, s);
   return skip ? launchFrameK<true, false>(p, s) : launchFrameK<false, false>(p, s);

@@ -109,6 +109,70 @@ int launchMacrocellBuildNvdb(const FieldDev &f, float2 *ranges, cudaStream_t s)
   return DVR_OK;
 }
 
+// Value ranges on the delta-tracking (DDA) grid: the reference's geometry — gridDims cells dividing the
+// field bounds evenly (UniformGrid.cu:152-154, dda.h) — so a cell is `w` voxel units wide with w generally
+// not an integer.  Cell c covers lower-tap indices floor(c*w) .. ceil((c+1)*w); one extra voxel each side.
+__global__ void __launch_bounds__(256) dvrDdaRangeKernel(const __grid_constant__ FieldDev f,
+    cudaTextureObject_t pointTex, int3 g, float3 w, float2 *__restrict__ ranges)
+{
+  const int cx = blockIdx.x, cy = blockIdx.y, cz = blockIdx.z;
+  int x0 = (int)floorf(cx * w.x) - 1, x1 = (int)ceilf((cx + 1) * w.x) + 1;
+  int y0 = (int)floorf(cy * w.y) - 1, y1 = (int)ceilf((cy + 1) * w.y) + 1;
+  int z0 = (int)floorf(cz * w.z) - 1, z1 = (int)ceilf((cz + 1) * w.z) + 1;
+  const bool nvdb = f.kind == FIELD_NANOVDB;
+  if (!nvdb) {
+    x0 = max(x0, 0); y0 = max(y0, 0); z0 = max(z0, 0);
+    x1 = min(x1, f.dims.x - 1); y1 = min(y1, f.dims.y - 1); z1 = min(z1, f.dims.z - 1);
+  }
+  const int nx = x1 - x0 + 1, ny = y1 - y0 + 1, nz = z1 - z0 + 1;
+  const int n = nx * ny * nz;
+  NvdbCache cache;
+  cache.reset();
+  float lo = FLT_MAX, hi = -FLT_MAX;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    float v;
+    if (nvdb) {
+      const int z = z0 + i % nz, y = y0 + (i / nz) % ny, x = x0 + i / (nz * ny);
+      v = nvdbGetValue(f.nv, cache, x + f.nv.bboxMin.x, y + f.nv.bboxMin.y, z + f.nv.bboxMin.z);
+    } else {
+      const int x = x0 + i % nx, y = y0 + (i / nx) % ny, z = z0 + i / (nx * ny);
+      const int zl = min(max(z - f.zTexBegin, 0), f.texDepth - 1);
+      v = tex3D<float>(pointTex, (float)x + 0.5f, (float)y + 0.5f, (float)zl + 0.5f);
+    }
+    lo = fminf(lo, v);
+    hi = fmaxf(hi, v);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    lo = fminf(lo, __shfl_xor_sync(0xffffffffu, lo, o));
+    hi = fmaxf(hi, __shfl_xor_sync(0xffffffffu, hi, o));
+  }
+  __shared__ float slo[8], shi[8];
+  const int wp = threadIdx.x >> 5, l = threadIdx.x & 31;
+  if (l == 0) {
+    slo[wp] = lo;
+    shi[wp] = hi;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int i = 1; i < 8; ++i) {
+      lo = fminf(lo, slo[i]);
+      hi = fmaxf(hi, shi[i]);
+    }
+    ranges[((size_t)cz * g.y + cy) * g.x + cx] = make_float2(lo, hi);
+  }
+}
+
+int launchDdaRangeBuild(const FieldDev &f, cudaTextureObject_t pointTex, int3 gridDims, float3 cellWidthVoxels,
+    float2 *ranges, cudaStream_t s)
+{
+  dim3 grid(gridDims.x, gridDims.y, gridDims.z);
+  dvrDdaRangeKernel<<<grid, 256, 0, s>>>(f, pointTex, gridDims, cellWidthVoxels, ranges);
+  DVR_CUDA(cudaGetLastError());
+  countLaunch();
+  return DVR_OK;
+}
+
 // K5: majorant = max TF alpha the marcher's lookup can return for any value in the cell's range.
 // UniformGrid.cu:55-90 restated with (a) the volume's own valueRange (quirk Q8) and (b) the
 // texel interval derived from the same coordinate mapping tfLookup() uses, widened by one texel.

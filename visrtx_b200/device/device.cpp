@@ -246,6 +246,9 @@ void Frame::renderFrame()
   p.tileRank = m_renderer->tileRank;
   p.tileRanks = m_renderer->tileRanks;
   p.useMacrocellSkipping = m_renderer->macrocellSkipping ? 1 : 0;
+  p.maxDepth = m_renderer->maxDepth;
+  p.ambientRadiance = m_renderer->ambientRadiance;
+  p.occlusionDistance = m_renderer->occlusionDistance;
 
   DvrFrameBuffers b;
   b.colorAccumulation = (float *)m_accum;
@@ -614,6 +617,7 @@ struct ParamInfo
 const ANARIParameter kRendererParams[] = {{"background", ANARI_FLOAT32_VEC4}, {"pixelSamples", ANARI_INT32},
     {"sampleLimit", ANARI_INT32}, {"volumeSamplingRate", ANARI_FLOAT32}, {"checkerboarding", ANARI_BOOL},
     {"macrocellSkipping", ANARI_BOOL}, {"sortFirstRank", ANARI_INT32}, {"sortFirstRanks", ANARI_INT32},
+    {"maxDepth", ANARI_INT32}, {"ambientRadiance", ANARI_FLOAT32}, {"ambientOcclusionDistance", ANARI_FLOAT32},
     {nullptr, ANARI_UNKNOWN}};
 const ANARIParameter kFieldParams[] = {{"data", ANARI_ARRAY3D}, {"origin", ANARI_FLOAT32_VEC3},
     {"spacing", ANARI_FLOAT32_VEC3}, {"filter", ANARI_STRING}, {nullptr, ANARI_UNKNOWN}};

@@ -805,12 +805,15 @@ void Renderer::commitParameters()
     integrator = DVR_INTEGRATOR_RAYCAST;
     sampleLimit = 1; // single-shot renderer
   }
+  if (subtype == "dpt" || subtype == "diffuse_pathtracer") { // DiffusePathTracer.cpp:41-53
+    integrator = DVR_INTEGRATOR_DPT;
+    maxDepth = std::min(std::max(getParam<int>("maxDepth", ANARI_INT32, 5), 1), 256);
+  }
+  // Renderer.cpp:159-161; the dpt renderer's default ambient radiance is 1 (DiffusePathTracer.cpp:41)
+  ambientRadiance = getParam<float>("ambientRadiance", ANARI_FLOAT32, integrator == DVR_INTEGRATOR_DPT ? 1.f : 0.f);
+  occlusionDistance = getParam<float>("ambientOcclusionDistance", ANARI_FLOAT32, 1e20f);
   if (!m_known)
     report(ANARI_SEVERITY_WARNING, ANARI_STATUS_INVALID_ARGUMENT, "unknown renderer subtype '%s'", subtype.c_str());
-  else if (subtype == "dpt" || subtype == "diffuse_pathtracer")
-    report(ANARI_SEVERITY_WARNING, ANARI_STATUS_NO_ERROR,
-        "renderer '%s': delta-tracking path tracing is not built yet; using the fixed-step marcher",
-        subtype.c_str());
 }
 
 } // namespace b200

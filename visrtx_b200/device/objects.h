@@ -278,6 +278,9 @@ struct Renderer : Object
   bool checkerboard = false;
   float volumeSamplingRate = 0.125f;
   int integrator = DVR_INTEGRATOR_DEFAULT;
+  int maxDepth = 5;                // dpt only
+  float ambientRadiance = 0.f;     // dpt only (the marching renderers have no lighting term for volumes)
+  float occlusionDistance = 1e20f; // dpt only
   bool macrocellSkipping = true;
   // sort-first extension: this device renders only tile rows (row % tileRanks == tileRank)
   uint32_t tileRank = 0, tileRanks = 1;
