@@ -511,6 +511,9 @@ def dpt_scene(kind, wh=96, **kw) -> SceneDesc:
     # a piecewise opacity so that the grid has empty, thin and dense cells
     s.volumes[0].tf = capi.tf_discretize(color=scenes.tsd_default_colormap(256),
                                          opacity=np.array([0.0, 0.05, 0.8, 0.1, 1.0], np.float32))
+    lo, hi = s.volumes[0].bounds()
+    pose = scenes.orbit_camera(lo, hi, wh, wh, az_deg=40.0, el_deg=25.0, dist_scale=0.8)  # volume fills the frame
+    s.camera = capi.camera_perspective(pose.position, pose.direction, pose.up, pose.fovy, pose.aspect)
     return s
 
 

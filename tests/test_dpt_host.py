@@ -11,6 +11,8 @@ known-answer tests that need neither a GPU nor the reference binary:
 O-cpu is test infrastructure; the product's CUDA tracker is compared with it (and with O-gpu) in
 tests/test_gpu_dpt.py.
 """
+import os
+
 import numpy as np
 import pytest
 
@@ -136,3 +138,19 @@ def test_dda_grid_nanovdb_geometry():
     n = int(round(float(hi[0] - lo[0])))
     assert dims == ((n + 15) // 16,) * 3  # NvdbRegularField.cpp:153: the index bounding box's extent
     assert maj.min() < 1e-3 and maj.max() > 0.9  # corner cells of a sphere's bounding box are empty
+
+
+@pytest.mark.parametrize("kind", H.DPT_KINDS)
+def test_oracle_dpt_matches_golden_reference_tracker(kind):
+    """tests/golden/refgpu_dpt.npz was rendered ON A B200 by O-gpu — the reference's unmodified
+    sampleDistanceAllVolumes / _sampleDistance / dda3 / sampleUnitSphere / accumResults — over this grid.
+    Same Philox stream and same statement, so O-cpu reproduces it pixel for pixel except where an ulp of
+    libm-vs-CUDA logf/sinf/cosf or of the software texture unit flips an accept/reject test."""
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "refgpu_dpt.npz"))
+    s = H.dpt_scene(kind)
+    one = H.render_oracle(s, frames=1)
+    acc = H.render_oracle(s, frames=H.DPT_GOLDEN_FRAMES)
+    assert H.frac_close(one["color"], g[f"{kind}/color1"], s.fmt) >= 0.99, kind
+    assert float(np.mean(one["color"] == g[f"{kind}/color1"])) >= 0.95, kind
+    mae = np.abs(acc["accum"] - g[f"{kind}/accum"]).mean() / H.DPT_GOLDEN_FRAMES
+    assert mae < 1e-3, (kind, mae)
