@@ -60,6 +60,8 @@ def parse_args():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-rows", type=int, default=0, help="rows of the CPU-baseline band (0 = auto)")
     ap.add_argument("--extra", type=int, default=1, help="also measure the secondary variants (N=1 only)")
+    ap.add_argument("--nvdb-codec", default="float", choices=["float", "fp4", "fp8", "fp16", "fpn"],
+                    help="c5 only: NanoVDB grid type of the fog sphere (quantised by visrtx_b200.nvdb_writer)")
     a = ap.parse_args()
     if a.config == "c3":
         a.size, a.width, a.height, a.field = 2048, 3840, 2160, "shells"
@@ -135,7 +137,7 @@ def make_scene(args, torch, device, z_begin=0, z_end=None):
         return scenes.shells_torch(n, device)
     if args.field == "fog":  # a serialized NanoVDB float grid (host numpy uint8), written by our own writer
         from visrtx_b200 import nvdb_writer
-        return nvdb_writer.fog_sphere(radius=(n - 1) / 2.0, voxel_size=1.0, half_width=3.0)
+        return nvdb_writer.fog_sphere(radius=(n - 1) / 2.0, voxel_size=1.0, half_width=3.0, codec=args.nvdb_codec)
     return scenes.marschner_lobb_torch(n, device, z_begin=z_begin, z_end=z_end, nz_total=n)
 
 
@@ -175,7 +177,7 @@ def workload_name(args):
     field = ("UFIXED16 sparse shells (12 Gaussian shells r=96*n/2048 voxels, zero elsewhere)" if args.field == "shells"
              else "f32 Marschner-Lobb (dense)")
     if args.field == "fog":
-        return (f"{args.config.upper()}: NanoVDB float fog sphere r={(n - 1) // 2} voxels (index bbox {n}^3, 33.5 M active "
+        return (f"{args.config.upper()}: NanoVDB {args.nvdb_codec} fog sphere r={(n - 1) // 2} voxels (index bbox {n}^3, 33.5 M active "
                 f"voxels at r=200) + transferFunction1D (TSD default map, unitDistance {args.unit_distance:g}), {W}x{H}, "
                 f"default renderer 1 spp progressive accumulation, volumeSamplingRate {args.rate:g}, orbit camera "
                 f"az30/el20 at 2|diag|, fovy 60")
@@ -205,7 +207,8 @@ def bytes_per_frame(args, cells_touched: int, samples: int = 0, fmt_bytes: int =
 
 
 def traffic_key(args, mode):
-    return (f"{args.config}:{args.field}:{args.size}:{args.width}x{args.height}:rate{args.rate:g}:"
+    codec = f":{args.nvdb_codec}" if args.field == "fog" and args.nvdb_codec != "float" else ""
+    return (f"{args.config}:{args.field}{codec}:{args.size}:{args.width}x{args.height}:rate{args.rate:g}:"
             f"ud{args.unit_distance:g}:skip{int(bool(args.skip))}:{mode}")
 
 

@@ -164,6 +164,8 @@ struct Nvdb
   uint32_t tiles = 0;
   float background = 0.f;
   float invMat[9], vec[3];
+  int codecLog2Bits = 0; // quantised grids: log2(bits per code); -1 = FpN (per leaf, mFlags >> 5)
+  bool quant = false;
 
   template <typename T>
   static T rd(const uint8_t *p)
@@ -182,6 +184,26 @@ struct Nvdb
       invMat[i] = rd<float>(blob + 296 + 36 + 4 * i);
     for (int i = 0; i < 3; ++i)
       vec[i] = rd<float>(blob + 296 + 72 + 4 * i);
+    // GridData::mGridType (NanoVDB.h:220-235): Float 1, Fp4 13, Fp8 14, Fp16 15, FpN 16
+    switch (rd<uint32_t>(blob + 636)) {
+    case 13: quant = true; codecLog2Bits = 2; break;
+    case 14: quant = true; codecLog2Bits = 3; break;
+    case 15: quant = true; codecLog2Bits = 4; break;
+    case 16: quant = true; codecLog2Bits = -1; break;
+    default: quant = false; break;
+    }
+  }
+  // LeafData<Fp4|Fp8|Fp16|FpN>::getValue (NanoVDB.h:3897-4040): code * mQuantum + mMinimum, evaluated as one
+  // fused multiply-add like the device code nvcc generates for the reference
+  float leafValue(const uint8_t *leaf, uint32_t n) const
+  {
+    if (!quant)
+      return rd<float>(leaf + 96 + 4 * (size_t)n);
+    const int b = codecLog2Bits >= 0 ? codecLog2Bits : (int)(leaf[15] >> 5);
+    uint32_t code = rd<uint32_t>(leaf + 96 + 4 * (size_t)(n >> (5 - b)));
+    code >>= (n & ((32u >> b) - 1u)) << b;
+    code &= (1u << (1u << b)) - 1u;
+    return std::fmaf((float)code, rd<float>(leaf + 84), rd<float>(leaf + 80));
   }
   static bool maskOn(const uint8_t *mask, uint32_t n) { return (rd<uint64_t>(mask + 8 * (n >> 6)) >> (n & 63)) & 1; }
   // Tree::getValue -> RootNode::getValue -> InternalNode::getValue -> LeafNode::getValue (NanoVDB.h:2947-2953,3528-3532)
@@ -209,7 +231,7 @@ struct Nvdb
     if (!maskOn(lower + 32 + 512, n))
       return rd<float>(lower + 1088 + 8 * (size_t)n);
     const uint8_t *leaf = lower + rd<int64_t>(lower + 1088 + 8 * (size_t)n);
-    return rd<float>(leaf + 96 + 4 * (size_t)(((x & 7) << 6) | ((y & 7) << 3) | (z & 7)));
+    return leafValue(leaf, (uint32_t)(((x & 7) << 6) | ((y & 7) << 3) | (z & 7)));
   }
   // worldToIndexF(Vec3d) = matMult(mInvMatF, xyz - mVecF): subtraction in double, fmaf chain in float (Math.h:905-910)
   float sample(V3 p) const

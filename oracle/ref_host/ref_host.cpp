@@ -99,10 +99,25 @@ extern "C" size_t refhost_nvdb_fog_sphere(double radius, double voxelSize, doubl
   return n;
 }
 
-// the reference's own sampler on the host (sampleSpatialField.h:80-109 uses exactly these calls)
-extern "C" int refhost_nvdb_sample(const void *gridBlob, const float *xyzWorld, int n, float *out)
+// quantised grid types (GridType 13..16): the same sphere through the real CreateNanoGrid quantiser.
+// gridType: 1 Float, 13 Fp4, 14 Fp8, 15 Fp16, 16 FpN (tolerance < 0 = NanoVDB's default oracle tolerance)
+namespace {
+static_assert(sizeof(nanovdb::NanoLeaf<nanovdb::Fp4>::DataType) == 96 + 256, "Fp4 leaf");
+static_assert(sizeof(nanovdb::NanoLeaf<nanovdb::Fp8>::DataType) == 96 + 512, "Fp8 leaf");
+static_assert(sizeof(nanovdb::NanoLeaf<nanovdb::Fp16>::DataType) == 96 + 1024, "Fp16 leaf");
+static_assert(sizeof(nanovdb::NanoLeaf<nanovdb::FpN>::DataType) == 96, "FpN leaf header");
+static_assert(offsetof(nanovdb::NanoLeaf<nanovdb::Fp8>::DataType, mMinimum) == 80, "mMinimum");
+static_assert(offsetof(nanovdb::NanoLeaf<nanovdb::Fp8>::DataType, mQuantum) == 84, "mQuantum");
+static_assert(offsetof(nanovdb::NanoLeaf<nanovdb::Fp8>::DataType, mFlags) == 15, "mFlags");
+static_assert(offsetof(nanovdb::NanoLeaf<nanovdb::Fp8>::DataType, mCode) == 96, "mCode");
+static_assert(sizeof(nanovdb::NanoUpper<nanovdb::Fp4>::DataType) == 270400, "upper node (Fp)");
+static_assert(sizeof(nanovdb::NanoLower<nanovdb::FpN>::DataType) == 33856, "lower node (Fp)");
+static_assert(sizeof(nanovdb::NanoRoot<nanovdb::Fp16>::DataType) == 64, "root (Fp)");
+
+template <typename BuildT>
+int sampleGrid(const void *gridBlob, const float *xyzWorld, int n, float *out)
 {
-  const auto *grid = reinterpret_cast<const nanovdb::NanoGrid<float> *>(gridBlob);
+  const auto *grid = reinterpret_cast<const nanovdb::NanoGrid<BuildT> *>(gridBlob);
   auto acc = grid->getAccessor();
   auto sampler = nanovdb::math::createSampler<1>(acc);
   for (int i = 0; i < n; ++i) {
@@ -110,6 +125,49 @@ extern "C" int refhost_nvdb_sample(const void *gridBlob, const float *xyzWorld, 
     out[i] = sampler(nanovdb::math::Vec3d(grid->worldToIndexF(loc)));
   }
   return 0;
+}
+} // namespace
+
+extern "C" size_t refhost_nvdb_fog_sphere_typed(unsigned gridType, double radius, double voxelSize, double halfWidth,
+    const double center[3], float tolerance, void *out, size_t capacity)
+{
+  const nanovdb::Vec3d c(center[0], center[1], center[2]);
+  nanovdb::GridHandle<> h;
+  switch (gridType) {
+  case 1: h = nanovdb::tools::createFogVolumeSphere<float>(radius, c, voxelSize, halfWidth); break;
+  case 13: h = nanovdb::tools::createFogVolumeSphere<nanovdb::Fp4>(radius, c, voxelSize, halfWidth); break;
+  case 14: h = nanovdb::tools::createFogVolumeSphere<nanovdb::Fp8>(radius, c, voxelSize, halfWidth); break;
+  case 15: h = nanovdb::tools::createFogVolumeSphere<nanovdb::Fp16>(radius, c, voxelSize, halfWidth); break;
+  case 16:
+    h = nanovdb::tools::createFogVolumeSphere<nanovdb::FpN>(radius, c, voxelSize, halfWidth, nanovdb::Vec3d(0.0),
+        "sphere_fog", nanovdb::tools::StatsMode::Default, nanovdb::CheckMode::Default, tolerance, false);
+    break;
+  default: return 0;
+  }
+  const size_t n = h.size();
+  if (out)
+    std::memcpy(out, h.data(), n < capacity ? n : capacity);
+  return n;
+}
+
+// the reference's own sampler on the host (sampleSpatialField.h:80-109 uses exactly these calls), dispatched on
+// the grid type like gpu/volumeIntegration.h:128-159
+extern "C" int refhost_nvdb_sample(const void *gridBlob, const float *xyzWorld, int n, float *out)
+{
+  switch (reinterpret_cast<const nanovdb::GridData *>(gridBlob)->mGridType) {
+  case nanovdb::GridType::Float: return sampleGrid<float>(gridBlob, xyzWorld, n, out);
+  case nanovdb::GridType::Fp4: return sampleGrid<nanovdb::Fp4>(gridBlob, xyzWorld, n, out);
+  case nanovdb::GridType::Fp8: return sampleGrid<nanovdb::Fp8>(gridBlob, xyzWorld, n, out);
+  case nanovdb::GridType::Fp16: return sampleGrid<nanovdb::Fp16>(gridBlob, xyzWorld, n, out);
+  case nanovdb::GridType::FpN: return sampleGrid<nanovdb::FpN>(gridBlob, xyzWorld, n, out);
+  default: return -1;
+  }
+}
+
+// GridData::isValid + whole-buffer validation the way NvdbRegularField::finalize relies on it
+extern "C" int refhost_nvdb_is_valid(const void *gridBlob)
+{
+  return reinterpret_cast<const nanovdb::GridData *>(gridBlob)->isValid() ? 1 : 0;
 }
 
 extern "C" int refhost_nvdb_info(const void *gridBlob, double worldBBox[6], double voxelSize[3], int indexBBox[6],

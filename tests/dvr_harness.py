@@ -469,6 +469,16 @@ def scene_zoo():
         cam = capi.camera_perspective(pose.position, pose.direction, pose.up, pose.fovy, pose.aspect)
         zoo[f"nvdb_fog_{key}"] = (SceneDesc([v], W, H, cam, volume_sampling_rate=rate,
                                             integrator=capi.DVR_INTEGRATOR_DEFAULT), 2, False)
+    # quantised NanoVDB grids (Fp4 / Fp8 / Fp16 / FpN), quantised by NanoVDB itself (make_nvdb_fixtures.py)
+    quant = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "nvdb_quant_spheres.npz"))
+    for key in ("fp4", "fp8", "fp16", "fpn"):
+        v = VolumeDesc(np.zeros((1, 1, 1), np.float32), nvdb=quant[key], tf=capi.tf_discretize(
+            color=scenes.tsd_default_colormap(256)), unit_distance=3.0, vol_id=32, inst_id=4)
+        lo, hi = v.bounds()
+        pose = scenes.orbit_camera(lo, hi, W, H, az_deg=50.0, dist_scale=0.9)
+        cam = capi.camera_perspective(pose.position, pose.direction, pose.up, pose.fovy, pose.aspect)
+        zoo[f"nvdb_{key}_r14"] = (SceneDesc([v], W, H, cam, volume_sampling_rate=0.5,
+                                            integrator=capi.DVR_INTEGRATOR_DEFAULT), 2, False)
     # empty world (no volume instance): background only
     s = default_scene(8, 40, 24, rate=0.5)
     s.volumes = []

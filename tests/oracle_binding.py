@@ -162,6 +162,28 @@ def nvdb_fog_sphere(radius=20.0, voxel_size=1.0, half_width=3.0, center=(0.0, 0.
     return buf
 
 
+NVDB_GRID_TYPES = {"float": 1, "fp4": 13, "fp8": 14, "fp16": 15, "fpn": 16}  # nanovdb::GridType
+
+
+def nvdb_fog_sphere_typed(grid_type="fp8", radius=20.0, voxel_size=1.0, half_width=3.0, center=(0.0, 0.0, 0.0),
+                          tolerance=-1.0) -> np.ndarray:
+    """Same sphere through NanoVDB's own quantiser: Fp4 / Fp8 / Fp16 / FpN grids (needs libref_host.so)."""
+    lib = refhost()
+    lib.refhost_nvdb_fog_sphere_typed.restype = C.c_size_t
+    ctr = (C.c_double * 3)(*center)
+    args = (C.c_uint(NVDB_GRID_TYPES[grid_type]), C.c_double(radius), C.c_double(voxel_size), C.c_double(half_width),
+            ctr, C.c_float(tolerance))
+    n = lib.refhost_nvdb_fog_sphere_typed(*args, None, C.c_size_t(0))
+    assert n > 0
+    buf = np.zeros(n, np.uint8)
+    lib.refhost_nvdb_fog_sphere_typed(*args, buf.ctypes.data_as(C.c_void_p), C.c_size_t(n))
+    return buf
+
+
+def nvdb_is_valid_reference(blob: np.ndarray) -> bool:
+    return bool(refhost().refhost_nvdb_is_valid(blob.ctypes.data_as(C.c_void_p)))
+
+
 def nvdb_sample_reference(blob: np.ndarray, xyz: np.ndarray) -> np.ndarray:
     xyz = np.ascontiguousarray(xyz, np.float32)
     out = np.empty(len(xyz), np.float32)

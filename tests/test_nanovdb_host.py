@@ -24,6 +24,54 @@ def test_oracle_nanovdb_sampler_matches_reference_samples(key):
     assert (got == want).mean() > 0.9
 
 
+@pytest.mark.parametrize("key", ["fp4", "fp8", "fp16", "fpn"])
+def test_oracle_quantised_grid_sampler_matches_reference_samples(key):
+    """Fp4 / Fp8 / Fp16 / FpN grids quantised by NanoVDB itself (tests/golden/make_nvdb_fixtures.py); the reference
+    values come from its own NanoGrid<FpX> accessors + SampleFromVoxels, dispatched like volumeIntegration.h:128-159."""
+    blob = np.ascontiguousarray(np.load(os.path.join(GOLD, "nvdb_quant_spheres.npz"))[key])
+    ref = np.load(os.path.join(GOLD, "nvdb_reference_samples.npz"))
+    assert blob[636:640].view(np.uint32)[0] == ob.NVDB_GRID_TYPES[key]
+    got = ob.nvdb_sample_oracle(blob, ref[key + "_xyz"])
+    want = ref[key + "_val"]
+    assert (want != 0).mean() > 0.2
+    assert np.abs(got - want).max() <= 2.4e-7
+    assert (got == want).mean() > 0.9
+
+
+def test_quantised_fixtures_are_what_the_reference_generates():
+    if not ob.have_ref_host():
+        pytest.skip("oracle/_ref/libref_host.so not built")
+    quant = np.load(os.path.join(GOLD, "nvdb_quant_spheres.npz"))
+    ref = np.load(os.path.join(GOLD, "nvdb_reference_samples.npz"))
+    for key in ("fp4", "fp8", "fp16", "fpn"):
+        fresh = ob.nvdb_fog_sphere_typed(key, 14.0)
+        if key != "fpn":  # NanoVDB leaves the slack of its worst-case FpN allocation uninitialised: bytes differ per run
+            assert np.array_equal(fresh, quant[key]), key
+        for blob in (fresh, np.ascontiguousarray(quant[key])):
+            assert np.array_equal(ob.nvdb_sample_reference(blob, ref[key + "_xyz"]), ref[key + "_val"]), key
+
+
+@pytest.mark.parametrize("codec,tol", [("fp4", 1.0 / 30 + 1e-6), ("fp8", 1.0 / 510 + 1e-6), ("fp16", 1e-5), ("fpn", 1e-3)])
+def test_own_writer_quantised_codecs(codec, tol):
+    """visrtx_b200.nvdb_writer with a quantised codec: the grid decodes (O-cpu; the real NanoVDB when present) to
+    the float grid within half a quantum (fixed widths) / the requested tolerance (FpN)."""
+    from visrtx_b200 import nvdb_writer as W
+    rng = np.random.default_rng(17)
+    xyz = (rng.random((3000, 3)) * 44 - 22).astype(np.float32)
+    base = ob.nvdb_sample_oracle(W.fog_sphere(18.0), xyz)
+    blob = W.fog_sphere(18.0, codec=codec, tolerance=1e-3)
+    assert blob[636:640].view(np.uint32)[0] == W.GRID_TYPES[codec]
+    got = ob.nvdb_sample_oracle(blob, xyz)
+    assert np.abs(got - base).max() <= tol
+    if codec != "fp16":
+        assert np.abs(got - base).max() > 0  # it really is quantised
+    if ob.have_ref_host():
+        assert ob.nvdb_is_valid_reference(blob)
+        assert np.abs(ob.nvdb_sample_reference(blob, xyz) - got).max() <= 2.4e-7
+    if codec == "fpn":  # variable leaf sizes: homogeneous interior leaves take 1 bit
+        assert blob.nbytes < W.fog_sphere(18.0, codec="fp8").nbytes * 1.3
+
+
 def test_fixture_is_what_the_reference_generates():
     if not ob.have_ref_host():
         pytest.skip("oracle/_ref/libref_host.so not built")

@@ -559,8 +559,18 @@ int dvr_field_create_nanovdb(const void *gridData, size_t bytes, int dataIsDevic
     return DVR_ERR_INVALID_ARGUMENT;
   }
   const uint32_t gridType = rd<uint32_t>(head, 636);
-  if (gridType != 1u) { // nanovdb::GridType::Float
-    setError("dvr_field_create_nanovdb: only GridType::Float grids are supported (Fp4/Fp8/Fp16/FpN are not built yet)");
+  // nanovdb::GridType: Float = 1, Fp4 = 13, Fp8 = 14, Fp16 = 15, FpN = 16 — the five types the reference's
+  // marcher dispatches on (gpu/volumeIntegration.h:128-159); anything else renders nothing there.
+  int codecLog2Bits = 0;
+  bool quant = true;
+  switch (gridType) {
+  case 1u: quant = false; break;
+  case 13u: codecLog2Bits = 2; break;
+  case 14u: codecLog2Bits = 3; break;
+  case 15u: codecLog2Bits = 4; break;
+  case 16u: codecLog2Bits = -1; break;
+  default:
+    setError("dvr_field_create_nanovdb: unsupported GridType (Float, Fp4, Fp8, Fp16 and FpN are)");
     return DVR_ERR_UNSUPPORTED;
   }
   const int64_t rootOff = 672 + rd<int64_t>(head, 672 + 24); // TreeData::mNodeOffset[3]
@@ -592,7 +602,8 @@ int dvr_field_create_nanovdb(const void *gridData, size_t bytes, int dataIsDevic
 
   FieldDev &d = f->dev;
   std::memset(&d, 0, sizeof(d));
-  d.kind = FIELD_NANOVDB;
+  d.kind = quant ? FIELD_NANOVDB_QUANT : FIELD_NANOVDB;
+  d.nv.codecLog2Bits = codecLog2Bits;
   d.nv.root = (const uint8_t *)f->nvdbBlob + rootOff;
   d.nv.tileCount = rd<uint32_t>(root, 24);
   d.nv.background = rd<float>(root, 28);
@@ -710,7 +721,7 @@ int dvr_field_build_macrocells(DvrField *f, void *stream)
     setError("dvr_field_build_macrocells: null field");
     return DVR_ERR_INVALID_ARGUMENT;
   }
-  if (f->dev.kind == FIELD_NANOVDB)
+  if (f->dev.kind >= FIELD_NANOVDB)
     return launchMacrocellBuildNvdb(f->dev, f->ranges, (cudaStream_t)stream);
   return launchMacrocellBuild(
       f->pointTex, f->dev.dims, f->dev.zTexBegin, f->dev.texDepth, f->dev.gridDims, f->ranges, (cudaStream_t)stream);
@@ -897,7 +908,7 @@ static int ensureDdaGrid(DvrVolume *v, cudaStream_t s)
   if (!v->ddaMaxOpacities)
     DVR_CUDA(cudaMalloc(&v->ddaMaxOpacities, n * sizeof(float)));
   // voxel units spanned by the bounds: dims-1 for node-centred structured fields, dims for NanoVDB boxes
-  const float3 span = f->dev.kind == FIELD_NANOVDB
+  const float3 span = f->dev.kind >= FIELD_NANOVDB
       ? make_float3((float)f->dev.dims.x, (float)f->dev.dims.y, (float)f->dev.dims.z)
       : make_float3((float)f->dev.dims.x - 1.f, (float)f->dev.dims.y - 1.f, (float)f->dev.dims.z - 1.f);
   const float3 w = make_float3(span.x / (float)g.x, span.y / (float)g.y, span.z / (float)g.z);

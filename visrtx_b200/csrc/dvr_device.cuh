@@ -16,7 +16,8 @@ namespace dvr {
 enum FieldKind : int
 {
   FIELD_STRUCTURED = 0, // 3-D array texture (structuredRegular)
-  FIELD_NANOVDB = 1     // NanoVDB float grid in linear device memory ("nanovdb")
+  FIELD_NANOVDB = 1,    // NanoVDB float grid in linear device memory ("nanovdb")
+  FIELD_NANOVDB_QUANT = 2 // NanoVDB Fp4 / Fp8 / Fp16 / FpN grid (codes decoded per tap)
 };
 
 // ---------------------------------------------------------------------------------------

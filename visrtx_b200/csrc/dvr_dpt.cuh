@@ -55,7 +55,7 @@ __device__ __forceinline__ float sampleDistanceSegment(const VolumeDev &v, const
   const float vrLo = v.vrLower, vrHi = v.vrUpper;
   const float invRange = __fdiv_rn(1.0f, __fsub_rn(vrHi, vrLo));
   NvdbCache nvCache;
-  if (KIND == FIELD_NANOVDB)
+  if (KIND >= FIELD_NANOVDB)
     nvCache.reset();
 
   // objRay: origin moved to the entry point, interval [0, tUpper - tLower]
@@ -176,7 +176,9 @@ __device__ __forceinline__ float sampleDistanceAllVolumes(const InstanceDev *__r
     float3 alb = f3(0.f, 0.f, 0.f);
     float ext = 0.f, tr = 0.f;
     float d;
-    if (KIND == FIELD_NANOVDB || (KIND < 0 && in.v.f.kind == FIELD_NANOVDB))
+    if (KIND == FIELD_NANOVDB_QUANT || (KIND < 0 && in.v.f.kind == FIELD_NANOVDB_QUANT))
+      d = sampleDistanceSegment<FIELD_NANOVDB_QUANT>(in.v, tfOf(SINGLE ? 0 : best), bo, bd, bt0, bt1, rng, alb, ext, tr);
+    else if (KIND == FIELD_NANOVDB || (KIND < 0 && in.v.f.kind == FIELD_NANOVDB))
       d = sampleDistanceSegment<FIELD_NANOVDB>(in.v, tfOf(SINGLE ? 0 : best), bo, bd, bt0, bt1, rng, alb, ext, tr);
     else
       d = sampleDistanceSegment<FIELD_STRUCTURED>(in.v, tfOf(SINGLE ? 0 : best), bo, bd, bt0, bt1, rng, alb, ext, tr);

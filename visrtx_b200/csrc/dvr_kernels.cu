@@ -228,9 +228,17 @@ struct TfSelectSingle
 #ifndef DVR_OCC_NVDB
 #define DVR_OCC_NVDB 3 // the NanoVDB march chases pointers; A/B on C5 (batch 1): 3/4/5/6 CTAs = 810/732/642/612 fps
 #endif
-template <bool SKIP, bool STATS, bool SINGLE, int KIND, bool DPT>
-__global__ void __launch_bounds__(kBlockThreads, (KIND == FIELD_NANOVDB ? DVR_OCC_NVDB : DVR_OCC)) dvrFrameKernel(const __grid_constant__ FrameLaunch P)
+// G: depth lanes per ray (see marchSegment); the warp's 8x4 tile is then rendered in G passes of 32/G pixels.
+#ifndef DVR_DEPTH_LANES
+#define DVR_DEPTH_LANES 1
+#endif
+#ifndef DVR_DEPTH_LANES_NVDB
+#define DVR_DEPTH_LANES_NVDB 1
+#endif
+template <bool SKIP, bool STATS, bool SINGLE, int KIND, bool DPT, int G>
+__global__ void __launch_bounds__(kBlockThreads, (KIND >= FIELD_NANOVDB ? DVR_OCC_NVDB : DVR_OCC)) dvrFrameKernel(const __grid_constant__ FrameLaunch P)
 {
+  static_assert(!(DPT && G != 1) && !(!SINGLE && G != 1), "depth lanes: single-volume marching kernels only");
   __shared__ float4 s_tf[(SINGLE ? 1 : kMaxInlineInstances) * DVR_TF_SIZE];
 
   const int lane = threadIdx.x & 31;
@@ -256,7 +264,10 @@ __global__ void __launch_bounds__(kBlockThreads, (KIND == FIELD_NANOVDB ? DVR_OC
     const uint32_t tyIdx = tile / P.tilesX, txIdx = tile - tyIdx * P.tilesX;
     if (P.tileRanks > 1u && ((tyIdx / P.tileBand) % P.tileRanks) != P.tileRank)
       continue;
-    const uint32_t lx = txIdx * kTileW + (lane % kTileW), ly = tyIdx * kTileH + (lane / kTileW);
+   for (int pass = 0; pass < G; ++pass) {
+    // G == 1: lane = pixel of the tile.  G > 1: lane / G = pixel within this pass, lane % G = depth slot.
+    const int pix = G == 1 ? lane : pass * (32 / G) + lane / G;
+    const uint32_t lx = txIdx * kTileW + (pix % kTileW), ly = tyIdx * kTileH + (pix / kTileW);
     if (lx >= P.launchW || ly >= P.launchH)
       continue;
     uint32_t px = lx, py = ly;
@@ -301,12 +312,13 @@ __global__ void __launch_bounds__(kBlockThreads, (KIND == FIELD_NANOVDB ? DVR_OC
       bool anyHit = false;
       float volumeDepth;
       if (SINGLE)
-        volumeDepth = rayMarchAllVolumes<SKIP, false, STATS, true, KIND>(P.inl, 1, TfSelectSingle{s_tf}, org, dir, FLT_MAX,
-            P.invSamplingRate, rng, color, opacity, objID, instID, st, P.cellBitmap, anyHit);
+        volumeDepth = rayMarchAllVolumes<SKIP, false, STATS, true, KIND, G>(P.inl, 1, TfSelectSingle{s_tf}, org, dir,
+            FLT_MAX, P.invSamplingRate, rng, color, opacity, objID, instID, st, P.cellBitmap, anyHit);
       else
         volumeDepth = rayMarchAllVolumes<SKIP, false, STATS, false, -1>(inst, nInst, TfSelectShared{s_tf, inst}, org, dir,
             FLT_MAX, P.invSamplingRate, rng, color, opacity, objID, instID, st, P.cellBitmap, anyHit);
-      if (STATS && anyHit)
+      const bool writer = G == 1 || (lane & (G - 1)) == 0; // every depth lane holds the same result; one stores it
+      if (STATS && anyHit && writer)
         raysHit++;
 
       // Raycast_ptx.cu:139-166 (no-surface branch)
@@ -319,9 +331,11 @@ __global__ void __launch_bounds__(kBlockThreads, (KIND == FIELD_NANOVDB ? DVR_OC
       color.z = __fmaf_rn(bg.z, oneMinus, color.z);
       opacity = __fmaf_rn(bg.w, oneMinus, opacity);
       // outputColor/outputOpacity start at 0: accumulateValue(out, c, 0) == c
-      accumResults(actx, px, py, make_float4(color.x, color.y, color.z, opacity), depth, color, dir, 0u, objID,
-          instID, it, initFrame && it == 0);
+      if (writer)
+        accumResults(actx, px, py, make_float4(color.x, color.y, color.z, opacity), depth, color, dir, 0u, objID,
+            instID, it, initFrame && it == 0);
     }
+   } // pass
   }
 
   if (STATS) {
@@ -338,10 +352,11 @@ __global__ void __launch_bounds__(kBlockThreads, (KIND == FIELD_NANOVDB ? DVR_OC
 template <bool SKIP, bool STATS, bool SINGLE, int KIND, bool DPT>
 static int launchFrameT(const FrameLaunch &p, cudaStream_t s)
 {
+  constexpr int G = (DPT || !SINGLE) ? 1 : (KIND >= FIELD_NANOVDB ? DVR_DEPTH_LANES_NVDB : DVR_DEPTH_LANES);
   static int blocksPerSm = 0;
   if (blocksPerSm == 0) {
     DVR_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(
-        &blocksPerSm, dvrFrameKernel<SKIP, STATS, SINGLE, KIND, DPT>, kBlockThreads, 0));
+        &blocksPerSm, dvrFrameKernel<SKIP, STATS, SINGLE, KIND, DPT, G>, kBlockThreads, 0));
     if (blocksPerSm < 1)
       blocksPerSm = 1;
   }
@@ -353,7 +368,7 @@ static int launchFrameT(const FrameLaunch &p, cudaStream_t s)
     grid = need;
   if (grid == 0)
     grid = 1;
-  dvrFrameKernel<SKIP, STATS, SINGLE, KIND, DPT><<<grid, kBlockThreads, 0, s>>>(p);
+  dvrFrameKernel<SKIP, STATS, SINGLE, KIND, DPT, G><<<grid, kBlockThreads, 0, s>>>(p);
   DVR_CUDA(cudaGetLastError());
   countLaunch();
   return DVR_OK;
@@ -366,6 +381,11 @@ static int launchFrameK(const FrameLaunch &p, cudaStream_t s)
     return launchFrameT<SKIP, STATS, false, -1, false>(p, s);
   if (p.inl[0].v.f.kind == FIELD_NANOVDB)
     return launchFrameT<SKIP, STATS, true, FIELD_NANOVDB, false>(p, s);
+  if (p.inl[0].v.f.kind == FIELD_NANOVDB_QUANT) {
+    if (STATS) // instrumentation is not worth a dedicated instantiation: the multi-volume kernel dispatches at run time
+      return launchFrameT<SKIP, STATS, false, -1, false>(p, s);
+    return launchFrameT<SKIP, false, true, FIELD_NANOVDB_QUANT, false>(p, s);
+  }
   return launchFrameT<SKIP, STATS, true, FIELD_STRUCTURED, false>(p, s);
 }
 
@@ -376,6 +396,8 @@ int launchFrame(const FrameLaunch &p, bool skip, bool stats, cudaStream_t s)
       return launchFrameT<false, false, false, -1, true>(p, s);
     if (p.inl[0].v.f.kind == FIELD_NANOVDB)
       return launchFrameT<false, false, true, FIELD_NANOVDB, true>(p, s);
+    if (p.inl[0].v.f.kind == FIELD_NANOVDB_QUANT)
+      return launchFrameT<false, false, true, FIELD_NANOVDB_QUANT, true>(p, s);
     return launchFrameT<false, false, true, FIELD_STRUCTURED, true>(p, s);
   }
   if (stats)

@@ -75,7 +75,9 @@ __global__ void __launch_bounds__(256) dvrMacrocellRangeNvdbKernel(const __grid_
   for (int i = threadIdx.x; i < nn * nn * nn; i += blockDim.x) {
     // z fastest (NanoVDB leaf order) so consecutive threads share leaves
     const int z = z0 + i % nn, y = y0 + (i / nn) % nn, x = x0 + i / (nn * nn);
-    const float v = nvdbGetValue(f.nv, cache, x + f.nv.bboxMin.x, y + f.nv.bboxMin.y, z + f.nv.bboxMin.z);
+    const float v = f.kind == FIELD_NANOVDB_QUANT
+        ? nvdbGetValue<true>(f.nv, cache, x + f.nv.bboxMin.x, y + f.nv.bboxMin.y, z + f.nv.bboxMin.z)
+        : nvdbGetValue<false>(f.nv, cache, x + f.nv.bboxMin.x, y + f.nv.bboxMin.y, z + f.nv.bboxMin.z);
     lo = fminf(lo, v);
     hi = fmaxf(hi, v);
   }
@@ -119,7 +121,7 @@ __global__ void __launch_bounds__(256) dvrDdaRangeKernel(const __grid_constant__
   int x0 = (int)floorf(cx * w.x) - 1, x1 = (int)ceilf((cx + 1) * w.x) + 1;
   int y0 = (int)floorf(cy * w.y) - 1, y1 = (int)ceilf((cy + 1) * w.y) + 1;
   int z0 = (int)floorf(cz * w.z) - 1, z1 = (int)ceilf((cz + 1) * w.z) + 1;
-  const bool nvdb = f.kind == FIELD_NANOVDB;
+  const bool nvdb = f.kind >= FIELD_NANOVDB;
   if (!nvdb) {
     x0 = max(x0, 0); y0 = max(y0, 0); z0 = max(z0, 0);
     x1 = min(x1, f.dims.x - 1); y1 = min(y1, f.dims.y - 1); z1 = min(z1, f.dims.z - 1);
@@ -133,7 +135,9 @@ __global__ void __launch_bounds__(256) dvrDdaRangeKernel(const __grid_constant__
     float v;
     if (nvdb) {
       const int z = z0 + i % nz, y = y0 + (i / nz) % ny, x = x0 + i / (nz * ny);
-      v = nvdbGetValue(f.nv, cache, x + f.nv.bboxMin.x, y + f.nv.bboxMin.y, z + f.nv.bboxMin.z);
+      v = f.kind == FIELD_NANOVDB_QUANT
+          ? nvdbGetValue<true>(f.nv, cache, x + f.nv.bboxMin.x, y + f.nv.bboxMin.y, z + f.nv.bboxMin.z)
+          : nvdbGetValue<false>(f.nv, cache, x + f.nv.bboxMin.x, y + f.nv.bboxMin.y, z + f.nv.bboxMin.z);
     } else {
       const int x = x0 + i % nx, y = y0 + (i / nx) % ny, z = z0 + i / (nx * ny);
       const int zl = min(max(z - f.zTexBegin, 0), f.texDepth - 1);

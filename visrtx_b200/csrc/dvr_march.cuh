@@ -96,7 +96,7 @@ __device__ __forceinline__ float fieldFetch(const FieldDev &f, float3 tc)
 template <int KIND>
 __device__ __forceinline__ float3 fieldCoord(const FieldDev &f, const float3 halfSpacing, float3 p)
 {
-  if (KIND == FIELD_NANOVDB)
+  if (KIND >= FIELD_NANOVDB)
     return nvdbWorldToIndex(f.nv, p);
   return fieldTexCoord(f, halfSpacing, p);
 }
@@ -105,7 +105,7 @@ __device__ __forceinline__ float3 fieldCoord(const FieldDev &f, const float3 hal
 template <int KIND>
 __device__ __forceinline__ float3 coordToVoxel(const FieldDev &f, float3 c)
 {
-  if (KIND == FIELD_NANOVDB)
+  if (KIND >= FIELD_NANOVDB)
     return f3(c.x - (float)f.nv.bboxMin.x, c.y - (float)f.nv.bboxMin.y, c.z - (float)f.nv.bboxMin.z);
   return f3(c.x * (float)f.dims.x - 0.5f, c.y * (float)f.dims.y - 0.5f, c.z * (float)f.dims.z - 0.5f);
 }
@@ -113,8 +113,10 @@ __device__ __forceinline__ float3 coordToVoxel(const FieldDev &f, float3 c)
 template <int KIND, bool SLAB>
 __device__ __forceinline__ float fieldSample(const FieldDev &f, NvdbCache &cache, float3 c)
 {
+  if (KIND == FIELD_NANOVDB_QUANT)
+    return nvdbSampleTrilinear<true>(f.nv, cache, c);
   if (KIND == FIELD_NANOVDB)
-    return nvdbSampleTrilinear(f.nv, cache, c);
+    return nvdbSampleTrilinear<false>(f.nv, cache, c);
   return fieldFetch<SLAB>(f, c);
 }
 
@@ -124,12 +126,22 @@ __device__ __forceinline__ float fieldSample(const FieldDev &f, NvdbCache &cache
 //          bit-identical to the unskipped march)
 //   SLAB : only samples whose cell slice lies in [zOwnBegin,zOwnEnd) are taken (sort-last)
 //   STATS: count samples
-template <bool SKIP, bool SLAB, bool STATS, int KIND>
+//   G    : depth lanes.  G > 1: G adjacent lanes of the warp (lane % G = depth slot) march the SAME ray; every
+//          lane carries the ray's full state redundantly (bit-identical arithmetic), lane g fetches and classifies
+//          the lattice points j with j % G == g of each iteration, and all G lanes then run the reference's
+//          sequential front-to-back composite over the iteration's BATCH*G samples in lattice order, reading each
+//          classified sample from its owner with a sub-warp shuffle.  The image is bit-identical to G == 1; the
+//          dependent-latency chain of a ray is G times shorter and adjacent lanes fetch adjacent voxels.
+template <bool SKIP, bool SLAB, bool STATS, int KIND, int G = 1>
 __device__ __forceinline__ void marchSegment(const VolumeDev &v, const float4 *__restrict__ tf,
     const float3 org, const float3 dir, float t, const float tUpper, const float invSamplingRate,
     Philox &rng, float3 &color, float &opacity, MarchStats &stats, unsigned int *cellBitmap)
 {
-  constexpr int BATCH = KIND == FIELD_NANOVDB ? DVR_BATCH_NVDB : DVR_BATCH;
+  constexpr int BATCH = KIND >= FIELD_NANOVDB ? DVR_BATCH_NVDB : DVR_BATCH;
+  constexpr int NS = BATCH * G; // lattice points per iteration of this ray
+  static_assert(G == 1 || G == 2 || G == 4 || G == 8 || G == 16 || G == 32, "depth lanes must divide the warp");
+  const int g = G > 1 ? (int)(threadIdx.x & (G - 1)) : 0;
+  const unsigned gmask = G >= 32 ? 0xffffffffu : (((1u << G) - 1u) << ((threadIdx.x & 31u) - (unsigned)g));
   const FieldDev &f = v.f;
   const float stepSize = __fmul_rn(f.stepSize, invSamplingRate);
   const float exponent = __fmul_rn(stepSize, v.oneOverUnitDistance);
@@ -142,7 +154,7 @@ __device__ __forceinline__ void marchSegment(const VolumeDev &v, const float4 *_
 
   // d(voxel coordinate)/dt, used by SKIP/SLAB bookkeeping only (never for the sample position)
   float3 dvox;
-  if (KIND == FIELD_NANOVDB)
+  if (KIND >= FIELD_NANOVDB)
     dvox = f3(dir.x * f.nv.invMat[0] + dir.y * f.nv.invMat[1] + dir.z * f.nv.invMat[2],
         dir.x * f.nv.invMat[3] + dir.y * f.nv.invMat[4] + dir.z * f.nv.invMat[5],
         dir.x * f.nv.invMat[6] + dir.y * f.nv.invMat[7] + dir.z * f.nv.invMat[8]);
@@ -150,7 +162,7 @@ __device__ __forceinline__ void marchSegment(const VolumeDev &v, const float4 *_
     dvox = f3(dir.x * f.invSpacing.x * (float)f.dims.x, dir.y * f.invSpacing.y * (float)f.dims.y,
         dir.z * f.invSpacing.z * (float)f.dims.z);
   NvdbCache nvCache;
-  if (KIND == FIELD_NANOVDB)
+  if (KIND >= FIELD_NANOVDB)
     nvCache.reset();
 
   if (SLAB) {
@@ -166,7 +178,7 @@ __device__ __forceinline__ void marchSegment(const VolumeDev &v, const float4 *_
     tEnter -= 2.f * stepSize;
     while (t < tEnter && t <= tUpper) {
       t = __fadd_rn(t, stepSize);
-      if (STATS)
+      if (STATS && g == 0)
         stats.skipped++;
     }
   }
@@ -202,7 +214,7 @@ __device__ __forceinline__ void marchSegment(const VolumeDev &v, const float4 *_
         while (n > 0 && t <= tUpper) {
           t = __fadd_rn(t, stepSize);
           --n;
-          if (STATS)
+          if (STATS && g == 0)
             stats.skipped++;
         }
         continue;
@@ -213,8 +225,9 @@ __device__ __forceinline__ void marchSegment(const VolumeDev &v, const float4 *_
     float s[BATCH];
     float tt = t;
 #pragma unroll
-    for (int k = 0; k < BATCH; ++k) {
-      ts[k] = tt;
+    for (int j = 0; j < NS; ++j) { // the lattice by repeated addition, exactly the reference's `t += step`
+      if (G == 1 || (j % G) == g)
+        ts[j / G] = tt;
       tt = __fadd_rn(tt, stepSize);
     }
 #pragma unroll
@@ -253,17 +266,27 @@ __device__ __forceinline__ void marchSegment(const VolumeDev &v, const float4 *_
       const float c = __fmul_rn(__fsub_rn(fmaxf(vrLo, fminf(s[k], vrHi)), vrLo), invRange); // position(s, range)
       co[k] = tfLookup(tf, c);
       st[k] = stepPow(__fsub_rn(1.f, co[k].w), exponent);
+      // s[k] is NaN for lattice points past the segment / not owned / NaN voxels: skipped like the reference
+      if (isnan(s[k]))
+        st[k] = s[k];
     }
 #pragma unroll
-    for (int k = 0; k < BATCH; ++k) {
-      // s[k] is NaN for lattice points past the segment / not owned / NaN voxels: skipped like the reference
-      if (opacity < 0.99f && !isnan(s[k])) {
-        const float w = __fmul_rn(transmittance, __fsub_rn(1.f, st[k]));
-        color.x = __fmaf_rn(w, co[k].x, color.x);
-        color.y = __fmaf_rn(w, co[k].y, color.y);
-        color.z = __fmaf_rn(w, co[k].z, color.z);
+    for (int j = 0; j < NS; ++j) {
+      const int k = j / G;
+      float cr = co[k].x, cg = co[k].y, cb = co[k].z, stj = st[k];
+      if (G > 1) { // sample j lives in depth lane j % G
+        cr = __shfl_sync(gmask, cr, j % G, G);
+        cg = __shfl_sync(gmask, cg, j % G, G);
+        cb = __shfl_sync(gmask, cb, j % G, G);
+        stj = __shfl_sync(gmask, stj, j % G, G);
+      }
+      if (opacity < 0.99f && !isnan(stj)) {
+        const float w = __fmul_rn(transmittance, __fsub_rn(1.f, stj));
+        color.x = __fmaf_rn(w, cr, color.x);
+        color.y = __fmaf_rn(w, cg, color.y);
+        color.z = __fmaf_rn(w, cb, color.z);
         opacity = __fadd_rn(opacity, w);
-        transmittance = __fmul_rn(transmittance, st[k]);
+        transmittance = __fmul_rn(transmittance, stj);
       }
     }
     t = tt;
@@ -285,7 +308,7 @@ __device__ __forceinline__ void marchSegment(const VolumeDev &v, const float4 *_
 // SINGLE: exactly one instance => every access uses the constant index 0, which keeps the texture
 // handle and field constants warp-uniform (no divergent-handle loop around the TEX instruction).
 // KIND: field kind known at compile time (single-volume kernels), or -1 = decide per instance.
-template <bool SKIP, bool SLAB, bool STATS, bool SINGLE, int KIND, typename TfSelect>
+template <bool SKIP, bool SLAB, bool STATS, bool SINGLE, int KIND, int G = 1, typename TfSelect>
 __device__ __forceinline__ float rayMarchAllVolumes(const InstanceDev *__restrict__ inst, const int nInst,
     TfSelect tfOf, const float3 org, const float3 dir, const float tfar, const float invSamplingRate,
     Philox &rng, float3 &color, float &opacity, uint32_t &objID, uint32_t &instID, MarchStats &stats,
@@ -334,11 +357,14 @@ __device__ __forceinline__ float rayMarchAllVolumes(const InstanceDev *__restric
     bt1 = fminf(tfar, bt1);
     // detail::rayMarchVolume: jitter #1 uses the UNSCALED step (volumeIntegration.h:117-120)
     const float tStart = __fmaf_rn(in.v.f.stepSize, rng.uniform(), bt0);
-    if (KIND == FIELD_NANOVDB || (KIND < 0 && in.v.f.kind == FIELD_NANOVDB))
-      marchSegment<SKIP, false, STATS, FIELD_NANOVDB>(
+    if (KIND == FIELD_NANOVDB_QUANT || (KIND < 0 && in.v.f.kind == FIELD_NANOVDB_QUANT))
+      marchSegment<SKIP, false, STATS, FIELD_NANOVDB_QUANT, G>(
+          in.v, tfOf(SINGLE ? 0 : best), bo, bd, tStart, bt1, invSamplingRate, rng, color, opacity, stats, cellBitmap);
+    else if (KIND == FIELD_NANOVDB || (KIND < 0 && in.v.f.kind == FIELD_NANOVDB))
+      marchSegment<SKIP, false, STATS, FIELD_NANOVDB, G>(
           in.v, tfOf(SINGLE ? 0 : best), bo, bd, tStart, bt1, invSamplingRate, rng, color, opacity, stats, cellBitmap);
     else
-      marchSegment<SKIP, SLAB, STATS, FIELD_STRUCTURED>(
+      marchSegment<SKIP, SLAB, STATS, FIELD_STRUCTURED, G>(
           in.v, tfOf(SINGLE ? 0 : best), bo, bd, tStart, bt1, invSamplingRate, rng, color, opacity, stats, cellBitmap);
     rayLower = __fadd_rn(bt1, 1e-3f);
     last = best;

@@ -1,4 +1,5 @@
-// dvr_nanovdb.cuh — device-side reader + trilinear sampler for NanoVDB float grids (BASELINE config C5).
+// dvr_nanovdb.cuh — device-side reader + trilinear sampler for NanoVDB float grids (BASELINE config C5) and
+// the quantised grid types Fp4 / Fp8 / Fp16 / FpN (gpu/volumeIntegration.h:128-159 dispatches the same five).
 //
 // Replaces SpatialFieldSampler<nanovdb::Grid<NanoTree<float>>> (gpu/sampleSpatialField.h:80-109), which
 // calls grid->worldToIndexF() and nanovdb::math::SampleFromVoxels<Accessor,1> of the NanoVDB 32.7.0
@@ -14,16 +15,6 @@
 
 namespace dvr {
 
-struct NvdbDev
-{
-  const uint8_t *root; // RootData<float>
-  uint32_t tileCount;
-  float background;
-  float invMat[9]; // Map::mInvMatF
-  float vec[3];    // Map::mVecF
-  int3 bboxMin;    // index-space bounding box of the active values (RootData::mBBox)
-};
-
 // byte offsets of the layout (see header comment)
 enum : uint32_t
 {
@@ -36,6 +27,17 @@ enum : uint32_t
   kNvdbLeafValues = 96
 };
 
+struct NvdbDev
+{
+  const uint8_t *root; // RootData<float>
+  uint32_t tileCount;
+  float background;
+  float invMat[9]; // Map::mInvMatF
+  float vec[3];    // Map::mVecF
+  int3 bboxMin;    // index-space bounding box of the active values (RootData::mBBox)
+  int codecLog2Bits; // quantised grids: log2(bits per code) — Fp4 2, Fp8 3, Fp16 4, FpN -1 (per leaf: mFlags >> 5)
+};
+
 // per-thread cache of the last visited lower node and leaf (the 8 taps of a trilinear stencil almost
 // always share them) — the role nanovdb::ReadAccessor plays in the reference
 struct NvdbCache
@@ -45,13 +47,42 @@ struct NvdbCache
   float leafTile;
   int nx, ny, nz;          // lower-node key (coords >> 7)
   const uint8_t *lower;
+  float qMin, qQuantum;    // quantised grids: LeafFnBase::mMinimum / mQuantum of the cached leaf
+  int qLog2Bits;           //                  log2(bits per code) of the cached leaf
   __device__ __forceinline__ void reset()
   {
     lx = ly = lz = nx = ny = nz = 0x7fffffff;
     leaf = lower = nullptr;
     leafTile = 0.f;
+    qMin = qQuantum = 0.f;
+    qLog2Bits = 0;
   }
 };
+
+// Quantised leaves: LeafFnBase (96 B: bbox 16 B with mFlags at byte 15, value mask 64 B, float mMinimum @80,
+// float mQuantum @84, 4 x u16 stats) followed by the packed codes.  The header of the cached leaf is read once.
+__device__ __forceinline__ void nvdbCacheLeafHeader(const NvdbDev &g, NvdbCache &c)
+{
+  const float2 mq = *reinterpret_cast<const float2 *>(c.leaf + 80);
+  c.qMin = mq.x;
+  c.qQuantum = mq.y;
+  c.qLog2Bits = g.codecLog2Bits >= 0 ? g.codecLog2Bits : (int)(c.leaf[15] >> 5);
+}
+
+// Leaf value n (0..511) of the cached leaf.  LeafData<Fp4|Fp8|Fp16|FpN>::getValue: code * mQuantum + mMinimum
+// (one fused multiply-add on the GPU); float leaves: mValues[n].
+template <bool QUANT>
+__device__ __forceinline__ float nvdbLeafValue(const NvdbCache &c, uint32_t n)
+{
+  if (QUANT) {
+    const int b = c.qLog2Bits;
+    uint32_t code = reinterpret_cast<const uint32_t *>(c.leaf + kNvdbLeafValues)[n >> (5 - b)];
+    code >>= (n & ((32u >> b) - 1u)) << b;
+    code &= (1u << (1u << b)) - 1u;
+    return __fmaf_rn((float)code, c.qQuantum, c.qMin);
+  }
+  return *reinterpret_cast<const float *>(c.leaf + kNvdbLeafValues + 4u * n);
+}
 
 __device__ __forceinline__ bool nvdbMaskOn(const uint8_t *mask, uint32_t n)
 {
@@ -60,13 +91,13 @@ __device__ __forceinline__ bool nvdbMaskOn(const uint8_t *mask, uint32_t n)
 }
 
 // Tree::getValue(ijk): value of the voxel regardless of its active state (inactive => tile / background value)
+template <bool QUANT = false>
 __device__ __forceinline__ float nvdbGetValue(const NvdbDev &g, NvdbCache &c, int x, int y, int z)
 {
   const int kx = x >> 3, ky = y >> 3, kz = z >> 3;
   if (kx == c.lx && ky == c.ly && kz == c.lz) {
     if (c.leaf)
-      return *reinterpret_cast<const float *>(
-          c.leaf + kNvdbLeafValues + 4u * (uint32_t)(((x & 7) << 6) | ((y & 7) << 3) | (z & 7)));
+      return nvdbLeafValue<QUANT>(c, (uint32_t)(((x & 7) << 6) | ((y & 7) << 3) | (z & 7)));
     return c.leafTile;
   }
   const uint8_t *lower = nullptr;
@@ -111,8 +142,9 @@ __device__ __forceinline__ float nvdbGetValue(const NvdbDev &g, NvdbCache &c, in
     return c.leafTile;
   }
   c.leaf = lower + *reinterpret_cast<const int64_t *>(entry);
-  return *reinterpret_cast<const float *>(
-      c.leaf + kNvdbLeafValues + 4u * (uint32_t)(((x & 7) << 6) | ((y & 7) << 3) | (z & 7)));
+  if (QUANT)
+    nvdbCacheLeafHeader(g, c);
+  return nvdbLeafValue<QUANT>(c, (uint32_t)(((x & 7) << 6) | ((y & 7) << 3) | (z & 7)));
 }
 
 // grid->worldToIndexF(Vec3d(location)) : Map::applyInverseMapF -> math::matMult(const float*, Vec3d)
@@ -129,35 +161,35 @@ __device__ __forceinline__ float3 nvdbWorldToIndex(const NvdbDev &g, float3 p)
 
 // SampleFromVoxels<Acc,1>::operator()(Vec3d): ijk = floor(xyz), uvw = xyz - ijk, stencil of 8 getValue
 // calls, nested lerps a + w*(b - a) with z innermost (math/SampleFromVoxels.h:201-242)
+template <bool QUANT = false>
 __device__ __forceinline__ float nvdbSampleTrilinear(const NvdbDev &g, NvdbCache &c, float3 idx)
 {
   const float fi = floorf(idx.x), fj = floorf(idx.y), fk = floorf(idx.z);
   const int i = (int)fi, j = (int)fj, k = (int)fk;
   const float u = __fsub_rn(idx.x, fi), v = __fsub_rn(idx.y, fj), w = __fsub_rn(idx.z, fk);
   float v000, v001, v011, v010, v100, v101, v111, v110;
-  v000 = nvdbGetValue(g, c, i, j, k); // positions the leaf cache on the stencil's base voxel
+  v000 = nvdbGetValue<QUANT>(g, c, i, j, k); // positions the leaf cache on the stencil's base voxel
   if (((i & 7) < 7) & ((j & 7) < 7) & ((k & 7) < 7)) {
     // whole stencil inside the cached leaf (or constant region): seven independent loads, no tree walk
     if (c.leaf) {
-      const float *lv = reinterpret_cast<const float *>(c.leaf + kNvdbLeafValues)
-          + (uint32_t)(((i & 7) << 6) | ((j & 7) << 3) | (k & 7));
-      v001 = lv[1];
-      v010 = lv[8];
-      v011 = lv[9];
-      v100 = lv[64];
-      v101 = lv[65];
-      v110 = lv[72];
-      v111 = lv[73];
+      const uint32_t n = (uint32_t)(((i & 7) << 6) | ((j & 7) << 3) | (k & 7));
+      v001 = nvdbLeafValue<QUANT>(c, n + 1);
+      v010 = nvdbLeafValue<QUANT>(c, n + 8);
+      v011 = nvdbLeafValue<QUANT>(c, n + 9);
+      v100 = nvdbLeafValue<QUANT>(c, n + 64);
+      v101 = nvdbLeafValue<QUANT>(c, n + 65);
+      v110 = nvdbLeafValue<QUANT>(c, n + 72);
+      v111 = nvdbLeafValue<QUANT>(c, n + 73);
     } else
       v001 = v010 = v011 = v100 = v101 = v110 = v111 = c.leafTile;
   } else {
-    v001 = nvdbGetValue(g, c, i, j, k + 1);
-    v011 = nvdbGetValue(g, c, i, j + 1, k + 1);
-    v010 = nvdbGetValue(g, c, i, j + 1, k);
-    v100 = nvdbGetValue(g, c, i + 1, j, k);
-    v101 = nvdbGetValue(g, c, i + 1, j, k + 1);
-    v111 = nvdbGetValue(g, c, i + 1, j + 1, k + 1);
-    v110 = nvdbGetValue(g, c, i + 1, j + 1, k);
+    v001 = nvdbGetValue<QUANT>(g, c, i, j, k + 1);
+    v011 = nvdbGetValue<QUANT>(g, c, i, j + 1, k + 1);
+    v010 = nvdbGetValue<QUANT>(g, c, i, j + 1, k);
+    v100 = nvdbGetValue<QUANT>(g, c, i + 1, j, k);
+    v101 = nvdbGetValue<QUANT>(g, c, i + 1, j, k + 1);
+    v111 = nvdbGetValue<QUANT>(g, c, i + 1, j + 1, k + 1);
+    v110 = nvdbGetValue<QUANT>(g, c, i + 1, j + 1, k);
   }
 #define DVR_LERP(a, b, t) __fmaf_rn((t), __fsub_rn((b), (a)), (a))
   const float r = DVR_LERP(DVR_LERP(DVR_LERP(v000, v001, w), DVR_LERP(v010, v011, w), v),

@@ -1,4 +1,6 @@
-"""Minimal NanoVDB writer: serialises a dense float32 block as a sparse NanoVDB ``GridType::Float`` grid.
+"""Minimal NanoVDB writer: serialises a dense float32 block as a sparse NanoVDB grid — ``GridType::Float`` or
+one of the quantised types Fp4 / Fp8 / Fp16 / FpN (per-leaf ``min + code * quantum`` codes of 4 / 8 / 16 / a
+per-leaf 1..16 bits).
 
 Used to create synthetic "nanovdb" spatial fields (BASELINE config C5: a fog sphere) without the NanoVDB
 library: the layout follows the published NanoVDB 32.7 binary format — GridData (672 B), TreeData (64 B),
@@ -19,10 +21,61 @@ _UPPER, _LOWER, _LEAF = 270400, 33856, 2144
 _UPPER_TABLE, _LOWER_TABLE, _LEAF_VALUES = 8256, 1088, 96
 _MAGIC_NUMB = 0x304244566F6E614E  # "NanoVDB0"
 _MAGIC_GRID = 0x314244566F6E614E  # "NanoVDB1"
+GRID_TYPES = {"float": 1, "fp4": 13, "fp8": 14, "fp16": 15, "fpn": 16}  # nanovdb::GridType
+_FIXED_BITS = {"fp4": 4, "fp8": 8, "fp16": 16}
+
+
+def _quantise_leaves(leaf_vals: np.ndarray, codec: str, tolerance: float):
+    """Per leaf: (bits, minimum, quantum, codes) with value ~= minimum + code * quantum (LeafFnBase, NanoVDB.h).
+    Fixed types use their bit width; FpN picks per leaf the smallest of 1/2/4/8/16 bits whose reconstruction
+    error stays within ``tolerance`` (NanoVDB's AbsDiff oracle does the same job)."""
+    n = len(leaf_vals)
+    vmin = leaf_vals.min(axis=1).astype(np.float32)
+    vmax = leaf_vals.max(axis=1).astype(np.float32)
+    span = (vmax - vmin).astype(np.float32)
+
+    def encode(bits):
+        units = np.float32((1 << bits) - 1)
+        quantum = (span / units).astype(np.float32)
+        enc = np.where(span > 0, units / np.where(span > 0, span, 1), 0).astype(np.float32)
+        codes = np.floor(enc[:, None] * (leaf_vals - vmin[:, None]) + np.float32(0.5))
+        codes = np.clip(codes, 0, float(units)).astype(np.uint32)
+        return quantum, codes
+
+    if codec in _FIXED_BITS:
+        b = _FIXED_BITS[codec]
+        q, c = encode(b)
+        return np.full(n, b, np.int32), vmin, q, c
+    bits = np.full(n, 16, np.int32)
+    quantum = np.zeros(n, np.float32)
+    codes = np.zeros((n, 512), np.uint32)
+    done = np.zeros(n, bool)
+    for b in (1, 2, 4, 8, 16):
+        q, c = encode(b)
+        err = np.abs(vmin[:, None] + c.astype(np.float32) * q[:, None] - leaf_vals).max(axis=1)
+        take = ~done & ((err <= tolerance) | (b == 16))
+        bits[take], quantum[take], codes[take] = b, q[take], c[take]
+        done |= take
+    return bits, vmin, quantum, codes
+
+
+def _pack_codes(codes: np.ndarray, bits: int) -> np.ndarray:
+    """(m,512) codes -> (m, 64*bits) bytes, code i in bits [i*bits, (i+1)*bits) of the little-endian stream."""
+    if bits == 16:
+        return np.ascontiguousarray(codes.astype("<u2")).view(np.uint8).reshape(len(codes), 1024)
+    if bits == 8:
+        return codes.astype(np.uint8)
+    per = 8 // bits
+    c = codes.reshape(len(codes), 512 // per, per).astype(np.uint8)
+    out = np.zeros(c.shape[:2], np.uint8)
+    for k in range(per):
+        out |= c[:, :, k] << (k * bits)
+    return out
 
 
 def write_float_grid(values: np.ndarray, index_origin=(0, 0, 0), voxel_size: float = 1.0, world_origin=(0.0, 0.0, 0.0),
-                     background: float = 0.0, name: str = "density", grid_class: int = 2) -> np.ndarray:
+                     background: float = 0.0, name: str = "density", grid_class: int = 2, codec: str = "float",
+                     tolerance: float = 1e-3) -> np.ndarray:
     """values[x, y, z] (float32) holds the voxel at index ``index_origin + (x, y, z)``; voxels equal to
     ``background`` are inactive and are not stored.  world = voxel_size * index + world_origin.
     Returns the serialised grid as a uint8 array (32-byte multiple)."""
@@ -54,11 +107,21 @@ def write_float_grid(values: np.ndarray, index_origin=(0, 0, 0), voxel_size: flo
     upper_of_lower = upper_of_lower.ravel()
     n_leaf, n_lower, n_upper = len(leaf_origin), len(lowers), len(uppers)
 
+    if codec not in GRID_TYPES:
+        raise ValueError(f"codec must be one of {sorted(GRID_TYPES)}")
+    leaf_vals = blocks[bidx[:, 0], bidx[:, 1], bidx[:, 2]].reshape(n_leaf, 512)
+    if codec == "float":
+        leaf_size = np.full(n_leaf, _LEAF, np.int64)
+    else:
+        q_bits, q_min, q_quantum, q_codes = _quantise_leaves(leaf_vals, codec, tolerance)
+        leaf_size = 96 + 64 * q_bits.astype(np.int64)
+    leaf_off = np.concatenate([[0], np.cumsum(leaf_size)[:-1]]).astype(np.int64)  # relative to the first leaf
+
     off_root = _GRID + _TREE
     off_upper = off_root + _ROOT + _TILE * n_upper
     off_lower = off_upper + _UPPER * n_upper
     off_leaf = off_lower + _LOWER * n_lower
-    total = off_leaf + _LEAF * n_leaf
+    total = off_leaf + int(leaf_size.sum())
     buf = np.zeros(total, dtype=np.uint8)
 
     def put(off, arr):
@@ -96,7 +159,7 @@ def write_float_grid(values: np.ndarray, index_origin=(0, 0, 0), voxel_size: flo
     wmax = (bb_max.astype(np.float64) + 1.0) * s_ + np.asarray(world_origin, np.float64)
     put(560, np.concatenate([wmin, wmax]))
     put(608, np.array([s_, s_, s_], np.float64))
-    put(632, np.array([grid_class, 1], np.uint32))  # GridClass (2 = FogVolume), GridType::Float
+    put(632, np.array([grid_class, GRID_TYPES[codec]], np.uint32))  # GridClass (2 = FogVolume), GridType
     put(640, np.array([total], np.int64))  # blind metadata offset = grid size (none)
     put(648, np.array([0, 0], np.uint32))
     put(656, np.array([0, _MAGIC_GRID], np.uint64))
@@ -149,27 +212,42 @@ def write_float_grid(values: np.ndarray, index_origin=(0, 0, 0), voxel_size: flo
         set_bits(base + 32 + 512, n, 64)
         table = np.zeros(4096, np.int64)
         table[:] = int(bgbits)
-        table[n] = (off_leaf + _LEAF * kids) - base
+        table[n] = (off_leaf + leaf_off[kids]) - base
         put(base + _LOWER_TABLE, table)
         put(base + 32 + 1024, np.array([vmin, vmax, 0.0, 0.0], np.float32))
 
-    # ---- leaves (vectorised)
-    leaf_vals = blocks[bidx[:, 0], bidx[:, 1], bidx[:, 2]].reshape(n_leaf, 512)
+    # ---- leaves (vectorised per leaf size)
     leaf_act = active[bidx[:, 0], bidx[:, 1], bidx[:, 2]].reshape(n_leaf, 512)
-    leaves = buf[off_leaf:].reshape(n_leaf, _LEAF)
-    leaves[:, 0:12] = np.ascontiguousarray(leaf_origin.astype(np.int32)).view(np.uint8).reshape(n_leaf, 12)
-    leaves[:, 12:15] = 7
-    leaves[:, 15] = 0
     bits = np.packbits(leaf_act.astype(np.uint8), axis=1, bitorder="little")  # bit n of word n>>6 == voxel n
-    leaves[:, 16:80] = bits
-    mm = np.stack([leaf_vals.min(axis=1), leaf_vals.max(axis=1), np.zeros(n_leaf, np.float32),
-                   np.zeros(n_leaf, np.float32)], axis=1).astype(np.float32)
-    leaves[:, 80:96] = np.ascontiguousarray(mm).view(np.uint8).reshape(n_leaf, 16)
-    leaves[:, _LEAF_VALUES:] = np.ascontiguousarray(leaf_vals).view(np.uint8).reshape(n_leaf, 2048)
+    head = np.zeros((n_leaf, 96), np.uint8)
+    head[:, 0:12] = np.ascontiguousarray(leaf_origin.astype(np.int32)).view(np.uint8).reshape(n_leaf, 12)
+    head[:, 12:15] = 7
+    head[:, 16:80] = bits
+    if codec == "float":
+        mm = np.stack([leaf_vals.min(axis=1), leaf_vals.max(axis=1), np.zeros(n_leaf, np.float32),
+                       np.zeros(n_leaf, np.float32)], axis=1).astype(np.float32)
+        head[:, 80:96] = np.ascontiguousarray(mm).view(np.uint8).reshape(n_leaf, 16)
+        leaves = buf[off_leaf:].reshape(n_leaf, _LEAF)
+        leaves[:, :96] = head
+        leaves[:, _LEAF_VALUES:] = np.ascontiguousarray(leaf_vals).view(np.uint8).reshape(n_leaf, 2048)
+        return buf
+    # quantised leaf = LeafFnBase: ... float mMinimum @80, float mQuantum @84, u16 mMin,mMax,mAvg,mDev @88
+    log2b = {1: 0, 2: 1, 4: 2, 8: 3, 16: 4}
+    head[:, 15] = np.array([log2b[int(b)] << 5 for b in q_bits], np.uint8) if codec == "fpn" else 0
+    head[:, 80:84] = np.ascontiguousarray(q_min).view(np.uint8).reshape(n_leaf, 4)
+    head[:, 84:88] = np.ascontiguousarray(q_quantum).view(np.uint8).reshape(n_leaf, 4)
+    cmax = ((1 << q_bits.astype(np.int64)) - 1).astype(np.uint16)
+    head[:, 90:92] = np.ascontiguousarray(cmax).view(np.uint8).reshape(n_leaf, 2)  # mMax (mMin = 0)
+    for b in np.unique(q_bits):
+        sel = np.where(q_bits == b)[0]
+        packed = _pack_codes(q_codes[sel], int(b))
+        rows = (off_leaf + leaf_off[sel])[:, None] + np.arange(96 + 64 * int(b))[None, :]
+        buf[rows] = np.concatenate([head[sel], packed], axis=1)
     return buf
 
 
-def fog_sphere(radius: float = 100.0, voxel_size: float = 1.0, half_width: float = 3.0) -> np.ndarray:
+def fog_sphere(radius: float = 100.0, voxel_size: float = 1.0, half_width: float = 3.0, codec: str = "float",
+               tolerance: float = 1e-3) -> np.ndarray:
     """A fog-volume sphere like nanovdb::tools::createFogVolumeSphere: density 1 inside, falling linearly to 0
     over ``half_width`` voxels at the surface, 0 (background, inactive) outside."""
     r = radius / voxel_size
@@ -178,4 +256,5 @@ def fog_sphere(radius: float = 100.0, voxel_size: float = 1.0, half_width: float
     x, y, z = np.meshgrid(c, c, c, indexing="ij", sparse=True)
     d = r - np.sqrt(x * x + y * y + z * z)  # signed distance to the surface in voxels (positive inside)
     dens = np.clip(d / np.float32(half_width), 0.0, 1.0).astype(np.float32)
-    return write_float_grid(dens, index_origin=(-n, -n, -n), voxel_size=voxel_size, name="sphere_fog")
+    return write_float_grid(dens, index_origin=(-n, -n, -n), voxel_size=voxel_size, name="sphere_fog", codec=codec,
+                            tolerance=tolerance)
