@@ -187,3 +187,68 @@ extern "C" int refhost_nvdb_info(const void *gridBlob, double worldBBox[6], doub
   *activeVoxels = grid->activeVoxelCount();
   return 0;
 }
+
+// ---- .nvdb FILES written by the reference's own NanoVDB I/O (nanovdb::io::writeGrid) -------------------------
+// Fixtures for the product's import_NVDB restatement: codec 0 = NONE, 1 = ZIP (zlib).  raw != 0 writes the bare
+// grid buffer instead (GridHandle::write), which nanovdb::io::readGrid accepts as well.
+#define NANOVDB_USE_ZIP 1
+#include <nanovdb/io/IO.h>
+#include <nanovdb/tools/GridStats.h>
+
+extern "C" int refhost_nvdb_write_file(const char *path, unsigned gridType, double radius, int codec, int raw)
+{
+  const nanovdb::Vec3d c(0.0);
+  nanovdb::GridHandle<> h;
+  switch (gridType) {
+  case 1: h = nanovdb::tools::createFogVolumeSphere<float>(radius, c, 1.0, 3.0); break;
+  case 13: h = nanovdb::tools::createFogVolumeSphere<nanovdb::Fp4>(radius, c, 1.0, 3.0); break;
+  case 14: h = nanovdb::tools::createFogVolumeSphere<nanovdb::Fp8>(radius, c, 1.0, 3.0); break;
+  case 15: h = nanovdb::tools::createFogVolumeSphere<nanovdb::Fp16>(radius, c, 1.0, 3.0); break;
+  case 16: h = nanovdb::tools::createFogVolumeSphere<nanovdb::FpN>(radius, c, 1.0, 3.0); break;
+  default: return -1;
+  }
+  try {
+    if (raw) {
+      std::ofstream os(path, std::ios::out | std::ios::binary);
+      os.write((const char *)h.data(), h.size());
+    } else
+      nanovdb::io::writeGrid(path, h, codec == 1 ? nanovdb::io::Codec::ZIP : nanovdb::io::Codec::NONE);
+  } catch (const std::exception &) {
+    return -2;
+  }
+  return 0;
+}
+
+// what import_NVDB.cpp:25-88 reads back: readGrid + (updateGridStats when the grid has no min/max) + root min/max
+extern "C" int refhost_nvdb_read_file(const char *path, void *out, size_t capacity, size_t *size, float minMax[2])
+{
+  try {
+    auto grid = nanovdb::io::readGrid(path);
+    auto metadata = grid.gridMetaData();
+    minMax[0] = std::numeric_limits<float>::max();
+    minMax[1] = std::numeric_limits<float>::lowest();
+#define REFHOST_CASE(T)                                                                       \
+  {                                                                                           \
+    if (!metadata->hasMinMax())                                                               \
+      nanovdb::tools::updateGridStats(grid.grid<T>(), nanovdb::tools::StatsMode::MinMax);     \
+    minMax[0] = grid.grid<T>()->tree().root().minimum();                                      \
+    minMax[1] = grid.grid<T>()->tree().root().maximum();                                      \
+    break;                                                                                    \
+  }
+    switch (metadata->gridType()) {
+    case nanovdb::GridType::Fp4: REFHOST_CASE(nanovdb::Fp4)
+    case nanovdb::GridType::Fp8: REFHOST_CASE(nanovdb::Fp8)
+    case nanovdb::GridType::Fp16: REFHOST_CASE(nanovdb::Fp16)
+    case nanovdb::GridType::FpN: REFHOST_CASE(nanovdb::FpN)
+    case nanovdb::GridType::Float: REFHOST_CASE(float)
+    default: break;
+    }
+#undef REFHOST_CASE
+    *size = grid.size();
+    if (out)
+      std::memcpy(out, grid.data(), grid.size() < capacity ? grid.size() : capacity);
+  } catch (const std::exception &) {
+    return -2;
+  }
+  return 0;
+}

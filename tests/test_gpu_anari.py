@@ -327,9 +327,9 @@ def test_nanovdb_field_through_anari_matches_cabi():
     color, _, _, _ = d.map_frame(frame, "channel.color")
     assert not _errors(d), d.messages
     assert np.array_equal(color, want["color"])
-    # a non-float grid type is refused with a warning, not a crash
+    # a grid type outside Float / Fp4 / Fp8 / Fp16 / FpN is refused with a warning, not a crash
     bad = blob.copy()
-    bad[636:640] = np.frombuffer(np.uint32(15).tobytes(), np.uint8)  # GridType::Fp16
+    bad[636:640] = np.frombuffer(np.uint32(2).tobytes(), np.uint8)  # GridType::Double
     f2 = d.new("SpatialField", "nanovdb")
     d.set(f2, "data", A.ARRAY1D, d.new_array1d(bad, A.UINT8))
     d.commit(f2)
