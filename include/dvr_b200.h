@@ -357,6 +357,28 @@ int dvr_ipc_free(void *devPtr);
 /* Frame::mapAlbedoBuffer / mapNormalBuffer, frame/Frame.cu:521-557: out = accum * invFrameID */
 int dvr_scale_vec3(const float *accumVec3, float *outVec3, size_t nPixels, float scale, void *stream);
 
+/* ---- frame post passes on device buffers ----------------------------------
+ * What TSD's render pipeline runs on the channels it maps through ANARI_NV_FRAME_BUFFERS_CUDA
+ * (the .cpp files of tsd/src/render_pipeline/passes).  All pointers are device pointers (the `...CUDA` channel maps or
+ * pipeline buffers); launches are stream-ordered. */
+/* convertFloatColorBuffer, AnariSceneRenderPass.cpp:15-20: uint8(clamp(v,0,1) * 255) per component */
+int dvr_post_convert_float_color(const float *rgbaF32, uint32_t *rgba8, size_t nPixels, void *stream);
+/* compositeFrame, AnariSceneRenderPass.cpp:30-46: take the incoming pixel when firstPass or when it is closer;
+ * idIn / idOut may be NULL together */
+int dvr_post_composite_depth(uint32_t *colorOut, float *depthOut, uint32_t *idOut, const uint32_t *colorIn,
+    const float *depthIn, const uint32_t *idIn, size_t nPixels, int firstPass, void *stream);
+/* computeOutline + shadePixel, OutlineRenderPass.cpp:13-46: a pixel whose 3x3 neighbourhood holds 2..7 pixels of
+ * objectId == outlineId is blended 80 % towards orange (1, .5, 0).  The reference's unsigned `max(0u, y - 1)`
+ * wraps on row / column 0, so those never get an outline — reproduced. */
+int dvr_post_outline(uint32_t *rgba8, const uint32_t *objectId, uint32_t width, uint32_t height, uint32_t outlineId,
+    void *stream);
+/* computeDepthImage, VisualizeDepthPass.cpp:13-21: grey = clamp(depth / maxDepth, 0, 1), alpha 1 */
+int dvr_post_visualize_depth(uint32_t *rgba8, const float *depth, size_t nPixels, float maxDepth, void *stream);
+/* pick operation of PickPass.cpp: what is under pixel (x, y) — copies one depth and one id to the host
+ * (synchronises the stream); objectId may be NULL (id = ~0u) */
+int dvr_post_pick(const float *depth, const uint32_t *objectId, uint32_t width, uint32_t height, uint32_t x, uint32_t y,
+    float *depthOut, uint32_t *idOut, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

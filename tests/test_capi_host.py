@@ -119,3 +119,30 @@ def test_product_does_not_reference_the_oracle():
     import subprocess
     out = subprocess.run(["ldd", capi.LIB_PATH], capture_output=True, text=True).stdout
     assert "oracle" not in out and "ref_" not in out
+
+
+def test_post_pass_oracle_known_answers():
+    """oracle/post_oracle.py (numpy restatement of TSD's render-pipeline passes) on hand-computed cases."""
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle"))
+    import post_oracle as PO
+    # convertFloatColorBuffer: uint8(clamp(v) * 255) truncates
+    assert PO.convert_float_color(np.array([[0.0, 1.0, 0.5, 2.0]], np.float32))[0] == (0 | 255 << 8 | 127 << 16 | 255 << 24)
+    # shadePixel: 20 % of the pixel + 80 % of (1, .5, 0, 1), truncated to bytes
+    assert PO.shade_pixel(np.array([0xFF000000], np.uint32))[0] == (204 | 102 << 8 | 0 << 16 | 255 << 24)
+    assert PO.shade_pixel(np.array([0xFFFFFFFF], np.uint32))[0] == (255 | 153 << 8 | 50 << 16 | 255 << 24)  # 1 - .8f = .19999999
+    # computeOutline: 3x3 counts 2..7 only; row 0 / column 0 never (unsigned wrap of `y - 1`)
+    ids = np.zeros((5, 5), np.uint32)
+    ids[1:4, 1:4] = 9
+    col = np.zeros(25, np.uint32)
+    out = PO.outline(col, ids.ravel(), 5, 5, 9).reshape(5, 5)
+    assert (out[0] == 0).all() and (out[:, 0] == 0).all()
+    assert out[2, 2] == 0  # centre: all 9 neighbours inside -> not an edge
+    assert out[1, 1] != 0 and out[4, 4] == 0 and out[4, 3] != 0  # counts 4, 1 and 2
+    # computeDepthImage: grey ramp, alpha 255; inf clamps to white
+    v = PO.visualize_depth(np.array([0.0, 3.0, 6.0, np.inf], np.float32), 6.0)
+    assert v.tolist() == [0xFF000000, 0xFF7F7F7F, 0xFFFFFFFF, 0xFFFFFFFF]
+    # compositeFrame keeps the closer pixel
+    c, d, i = PO.composite_depth(np.array([1, 2], np.uint32), np.array([0.5, 0.5], np.float32), np.array([8, 8], np.uint32),
+                                 np.array([3, 4], np.uint32), np.array([0.25, 0.75], np.float32), np.array([9, 9], np.uint32), False)
+    assert c.tolist() == [3, 2] and d.tolist() == [0.25, 0.5] and i.tolist() == [9, 8]

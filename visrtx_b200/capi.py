@@ -34,6 +34,8 @@ EXPORTED_SYMBOLS = [
     "dvr_field_macrocells", "dvr_field_value_range",
     "dvr_volume_create", "dvr_volume_update", "dvr_volume_destroy", "dvr_volume_majorants",
     "dvr_volume_dda_majorants",
+    "dvr_post_convert_float_color", "dvr_post_composite_depth", "dvr_post_outline", "dvr_post_visualize_depth",
+    "dvr_post_pick",
     "dvr_render", "dvr_render_instrumented", "dvr_launch_count",
     "dvr_render_partial", "dvr_render_partial_instrumented", "dvr_composite_over", "dvr_resolve", "dvr_scale_vec3",
     "dvr_composite_resolve_peers", "dvr_render_partial_sync", "dvr_composite_resolve_peers_sync", "dvr_wait_flags",
@@ -432,3 +434,33 @@ def composite_resolve_peers_sync(params, camera, instance, partial_rgba_ptrs, pa
 def wait_flags(flags_ptr: int, n: int, value: int, error_flag: int = 0, stream: int = 0):
     _check(lib.dvr_wait_flags(C.c_void_p(flags_ptr), C.c_uint32(n), C.c_uint32(int(value) & 0xFFFFFFFF),
                               C.c_void_p(error_flag or None), C.c_void_p(stream)))
+
+
+# ---- frame post passes (tsd/src/render_pipeline/passes) on device pointers ------------------------------------
+def post_convert_float_color(rgba_f32_ptr: int, rgba8_ptr: int, n_pixels: int, stream: int = 0):
+    _check(lib.dvr_post_convert_float_color(C.c_void_p(rgba_f32_ptr), C.c_void_p(rgba8_ptr), C.c_size_t(n_pixels),
+                                            C.c_void_p(stream)))
+
+
+def post_composite_depth(color_out: int, depth_out: int, id_out: int, color_in: int, depth_in: int, id_in: int,
+                         n_pixels: int, first_pass: bool, stream: int = 0):
+    _check(lib.dvr_post_composite_depth(C.c_void_p(color_out), C.c_void_p(depth_out), C.c_void_p(id_out or None),
+                                        C.c_void_p(color_in), C.c_void_p(depth_in), C.c_void_p(id_in or None),
+                                        C.c_size_t(n_pixels), C.c_int(1 if first_pass else 0), C.c_void_p(stream)))
+
+
+def post_outline(rgba8_ptr: int, object_id_ptr: int, width: int, height: int, outline_id: int, stream: int = 0):
+    _check(lib.dvr_post_outline(C.c_void_p(rgba8_ptr), C.c_void_p(object_id_ptr), C.c_uint32(width), C.c_uint32(height),
+                                C.c_uint32(outline_id), C.c_void_p(stream)))
+
+
+def post_visualize_depth(rgba8_ptr: int, depth_ptr: int, n_pixels: int, max_depth: float, stream: int = 0):
+    _check(lib.dvr_post_visualize_depth(C.c_void_p(rgba8_ptr), C.c_void_p(depth_ptr), C.c_size_t(n_pixels),
+                                        C.c_float(max_depth), C.c_void_p(stream)))
+
+
+def post_pick(depth_ptr: int, object_id_ptr: int, width: int, height: int, x: int, y: int, stream: int = 0):
+    d, i = C.c_float(), C.c_uint32()
+    _check(lib.dvr_post_pick(C.c_void_p(depth_ptr), C.c_void_p(object_id_ptr or None), C.c_uint32(width),
+                             C.c_uint32(height), C.c_uint32(x), C.c_uint32(y), C.byref(d), C.byref(i), C.c_void_p(stream)))
+    return d.value, i.value
