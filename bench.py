@@ -798,11 +798,13 @@ def run_reference(args, torch, dist, rank, world):
     mk = lambda fid: capi.frame_params(W, H, capi.DVR_FORMAT_UFIXED8_RGBA_SRGB, capi.DVR_INTEGRATOR_DEFAULT, fid, -1, 1,
                                        args.rate, (0.1, 0.1, 0.1, 1.0))
     cam, _ = orbit(args)
+    # clocks are sampled from the warm-up to the end of the e2e loop (the timed region alone can be shorter than
+    # one 200 ms nvidia-smi period)
+    sampler = ClockSampler(device.index)
+    sampler.start()
     for i in range(args.warmup):
         lib.refgpu_render(C.byref(mk(i)), C.byref(cam), sc, C.byref(fb), C.c_void_p(stream))
     torch.cuda.synchronize()
-    sampler = ClockSampler(device.index)
-    sampler.start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for i in range(args.steps):
@@ -810,7 +812,6 @@ def run_reference(args, torch, dist, rank, world):
     e1.record()
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / args.steps
-    clocks = sampler.stop()
 
     def e2e_step(i):
         cam_i, _ = orbit(args, az_deg=30.0 + 0.05 * i)
@@ -824,6 +825,7 @@ def run_reference(args, torch, dist, rank, world):
     for i in range(args.steps):
         e2e_step(i)
     e2e_fps = args.steps / (time.perf_counter() - t0)
+    clocks = sampler.stop()
     base.update({
         "value": 1000.0 / ms, "ms_per_step": ms,
         "config": {"workload": workload, "parallelism": "single (the reference has no multi-GPU path)",
