@@ -522,7 +522,9 @@ def run_ours(args, torch, dist, rank, world):
         e2e_step = e2e.step
         e2e_what = ("ANARI C API of libanari_library_visrtx_b200.so: anariSetParameter(camera)+anariCommitParameters"
                     "+anariRenderFrame+anariFrameReady(WAIT)+anariMapFrame(channel.color -> host) per step, wall "
-                    "clock; the volume is an ANARI_NV_ARRAY_CUDA shared array uploaded once")
+                    "clock; the volume is an ANARI_NV_ARRAY_CUDA shared array uploaded once; after the first host map "
+                    "the device streams the encoded colour into pinned host memory during the launch "
+                    "(DvrFrameBuffers::outColorMirror), so the device->host bytes overlap the march")
     else:
         e2e = None
 

@@ -129,6 +129,11 @@ typedef struct DvrFrameBuffers
   uint32_t *instId;
   float *albedo; /* vec3[W*H] accumulation */
   float *normal; /* vec3[W*H] accumulation */
+  /* Optional second destination of the encoded colour, same layout as outColor: every pixel the launch writes to
+   * outColor is also stored here.  Meant for device-accessible pinned HOST memory (cudaHostAlloc): the frame then
+   * reaches the host through posted PCIe writes overlapped with the march instead of a copy after it — what
+   * Frame::map("channel.color") needs (frame/Frame.cu:312-330 maps the colour buffer to the host). NULL = off. */
+  void *outColorMirror;
 } DvrFrameBuffers;
 
 /* FramebufferGPUData + the RendererGPUData members this path reads

@@ -29,7 +29,7 @@ def test_struct_layouts_match_header_sizes():
     # sizes the C compiler gives the PODs (checked against ctypes mirrors; a mismatch would corrupt launches)
     assert C.sizeof(capi.DvrCamera) == 4 + 16 + 12 * 6 + 8
     assert C.sizeof(capi.DvrVolumeInstance) == 8 + 48 + 8
-    assert C.sizeof(capi.DvrFrameBuffers) == 8 * 8
+    assert C.sizeof(capi.DvrFrameBuffers) == 9 * 8
     assert C.sizeof(capi.DvrFrameParams) == 4 * 8 + 16 + 8 + 4 + 4 + 12 + 12
     assert C.sizeof(capi.DvrRenderStats) == 32
 

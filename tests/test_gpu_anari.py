@@ -336,3 +336,46 @@ def test_nanovdb_field_through_anari_matches_cabi():
     d.render(frame)
     assert any("unsupported GridType" in m[2] for m in d.messages)
     d.close()
+
+
+def test_host_colour_streaming_equals_copy_path():
+    """After the first host map of channel.color the device streams the encoded colour into pinned host memory
+    during the launch (DvrFrameBuffers::outColorMirror).  Streamed frames must equal the device buffer and the
+    C-ABI renders bit for bit, for every colour format, through resets and sampleLimit stops."""
+    import torch
+    for ctype, fmt in ((A.UFIXED8_RGBA_SRGB, capi.DVR_FORMAT_UFIXED8_RGBA_SRGB), (A.FLOAT32_VEC4, capi.DVR_FORMAT_FLOAT32_VEC4),
+                       (A.UFIXED8_VEC4, capi.DVR_FORMAT_UFIXED8_VEC4)):
+        s = AnariScene(40, 72, 56, "default", 0.5, color_type=ctype, channels=("depth",))
+        d = s.d
+        scene = H.default_scene(40, 72, 56, rate=0.5, integrator=capi.DVR_INTEGRATOR_DEFAULT, fmt=fmt)
+        scene.volumes[0].inst_id = 0xFFFFFFFF
+        for frames in (1, 2, 3):  # frame 1: copy path; frames 2, 3: streamed
+            s.render()
+            host, w, h, _ = d.map_frame(s.frame, "channel.color")
+            host = np.array(host, copy=True)
+            ptr, _, _, _ = d.map_frame(s.frame, "channel.colorCUDA")
+            nbytes = w * h * (16 if fmt == capi.DVR_FORMAT_FLOAT32_VEC4 else 4)
+            dev = torch.empty(nbytes, dtype=torch.uint8, device="cuda")
+            C.CDLL("libcudart.so").cudaMemcpy(C.c_void_p(dev.data_ptr()), C.c_void_p(ptr), C.c_size_t(nbytes), C.c_int(3))
+            assert np.array_equal(np.ascontiguousarray(host).view(np.uint8).ravel(), dev.cpu().numpy()), (fmt, frames)
+            ref = H.render_cuda(scene, frames=frames)
+            assert np.array_equal(host.reshape(ref["color"].shape), ref["color"]), (fmt, frames)
+        # a parameter change resets accumulation: the streamed frame is frame 0 again
+        d.set(s.renderer, "background", A.FLOAT32_VEC4, (0.3, 0.2, 0.1, 1.0))
+        d.commit(s.renderer)
+        s.render()
+        host, _, _, _ = d.map_frame(s.frame, "channel.color")
+        scene.background = (0.3, 0.2, 0.1, 1.0)
+        ref = H.render_cuda(scene, frames=1)
+        assert np.array_equal(np.asarray(host).reshape(ref["color"].shape), ref["color"])
+        # sampleLimit reached: no launch, the mapped image stays the last one
+        d.set(s.renderer, "sampleLimit", A.INT32, 1)
+        d.commit(s.renderer)
+        s.render()
+        s.render()  # frameID 0 and 1 are rendered; from then on frameID >= sampleLimit stops (Frame.cu:251-253)
+        last = np.array(d.map_frame(s.frame, "channel.color")[0], copy=True)
+        s.render()
+        again = np.array(d.map_frame(s.frame, "channel.color")[0], copy=True)
+        assert np.array_equal(last, again)
+        assert not _errors(d), d.messages
+        s.close()

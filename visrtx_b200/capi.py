@@ -63,7 +63,7 @@ class DvrVolumeInstance(C.Structure):
 class DvrFrameBuffers(C.Structure):
     _fields_ = [("colorAccumulation", C.c_void_p), ("outColor", C.c_void_p), ("depth", C.c_void_p),
                 ("primId", C.c_void_p), ("objId", C.c_void_p), ("instId", C.c_void_p), ("albedo", C.c_void_p),
-                ("normal", C.c_void_p)]
+                ("normal", C.c_void_p), ("outColorMirror", C.c_void_p)]
 
 
 class DvrFrameParams(C.Structure):
@@ -332,8 +332,9 @@ def frame_params(width, height, fmt=DVR_FORMAT_UFIXED8_RGBA_SRGB, integrator=DVR
 
 
 def frame_buffers(accum: int, out_color: int, depth: int = 0, prim: int = 0, obj: int = 0, inst: int = 0,
-                  albedo: int = 0, normal: int = 0) -> DvrFrameBuffers:
+                  albedo: int = 0, normal: int = 0, color_mirror: int = 0) -> DvrFrameBuffers:
     b = DvrFrameBuffers()
+    b.outColorMirror = color_mirror or None
     b.colorAccumulation, b.outColor = accum or None, out_color or None
     b.depth, b.primId, b.objId, b.instId = depth or None, prim or None, obj or None, inst or None
     b.albedo, b.normal = albedo or None, normal or None

@@ -981,6 +981,7 @@ static int renderImpl(const DvrFrameParams *p, const DvrCamera *camera, const Dv
   L.fb.accum = (float4 *)b->colorAccumulation;
   L.fb.outU32 = (uint32_t *)b->outColor;
   L.fb.outF32 = (float4 *)b->outColor;
+  L.fb.outMirror = b->outColorMirror;
   L.fb.depth = b->depth;
   L.fb.primId = b->primId;
   L.fb.objId = b->objId;
@@ -1205,6 +1206,7 @@ int dvr_resolve(const DvrFrameParams *p, const float *partialRgba, const float *
   R.fb.accum = (float4 *)b->colorAccumulation;
   R.fb.outU32 = (uint32_t *)b->outColor;
   R.fb.outF32 = (float4 *)b->outColor;
+  R.fb.outMirror = b->outColorMirror;
   R.fb.depth = b->depth;
   R.fb.primId = b->primId;
   R.fb.objId = b->objId;
@@ -1244,6 +1246,7 @@ static int compositeResolveImpl(const DvrFrameParams *p, const DvrCamera *camera
   R.fb.accum = (float4 *)b->colorAccumulation;
   R.fb.outU32 = (uint32_t *)b->outColor;
   R.fb.outF32 = (float4 *)b->outColor;
+  R.fb.outMirror = b->outColorMirror;
   R.fb.depth = b->depth;
   R.fb.primId = b->primId;
   R.fb.objId = b->objId;

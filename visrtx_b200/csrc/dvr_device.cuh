@@ -84,6 +84,7 @@ struct BuffersDev
   float4 *accum;
   uint32_t *outU32;
   float4 *outF32;
+  void *outMirror; // optional second destination of the encoded colour (pinned host memory), same layout
   float *depth;
   uint32_t *primId, *objId, *instId;
   float *albedo, *normal; // packed vec3
@@ -285,12 +286,17 @@ __device__ __forceinline__ void writeOutputColor(
   c.x = __fdiv_rn(c.x, m);
   c.y = __fdiv_rn(c.y, m);
   c.z = __fdiv_rn(c.z, m);
-  if (format == 2)
-    fb.outU32[idx] = packUnorm4x8(linearToSrgb(c.x), linearToSrgb(c.y), linearToSrgb(c.z), c.w);
-  else if (format == 1)
-    fb.outU32[idx] = packUnorm4x8(c.x, c.y, c.z, c.w);
-  else
+  if (format == 0) {
     fb.outF32[idx] = c;
+    if (fb.outMirror)
+      __stcs(reinterpret_cast<float4 *>(fb.outMirror) + idx, c);
+    return;
+  }
+  const uint32_t v = format == 2 ? packUnorm4x8(linearToSrgb(c.x), linearToSrgb(c.y), linearToSrgb(c.z), c.w)
+                                 : packUnorm4x8(c.x, c.y, c.z, c.w);
+  fb.outU32[idx] = v;
+  if (fb.outMirror)
+    __stcs(reinterpret_cast<uint32_t *>(fb.outMirror) + idx, v);
 }
 
 // ---------------------------------------------------------------------------------------

@@ -100,6 +100,7 @@ void Frame::finalize()
     wait();
   CudaDeviceScope scope(device);
   freeBuffers();
+  m_pinnedHoldsFrame = false;
 
   if (m_colorType == ANARI_FLOAT32_VEC4)
     m_format = DVR_FORMAT_FLOAT32_VEC4;
@@ -253,6 +254,13 @@ void Frame::renderFrame()
   DvrFrameBuffers b;
   b.colorAccumulation = (float *)m_accum;
   b.outColor = m_color;
+  b.outColorMirror = nullptr;
+  m_pinnedHoldsFrame = false;
+  if (m_streamColorToHost
+      && ensurePinned((size_t)m_size[0] * m_size[1] * (m_format == DVR_FORMAT_FLOAT32_VEC4 ? 16 : 4))) {
+    b.outColorMirror = m_pinned;
+    m_pinnedHoldsFrame = true;
+  }
   b.depth = (float *)m_depth;
   b.primId = (uint32_t *)m_primId;
   b.objId = (uint32_t *)m_objId;
@@ -276,26 +284,38 @@ void Frame::renderFrame()
   cudaEventRecord((cudaEvent_t)m_eventEnd, stream);
 }
 
+bool Frame::ensurePinned(size_t bytes)
+{
+  if (m_pinnedBytes >= bytes && m_pinned)
+    return true;
+  if (m_pinned)
+    cudaFreeHost(m_pinned);
+  m_pinned = nullptr;
+  m_pinnedBytes = 0;
+  if (cudaMallocHost(&m_pinned, bytes) != cudaSuccess) {
+    cudaGetLastError();
+    m_pinned = nullptr;
+    return false;
+  }
+  m_pinnedBytes = bytes;
+  return true;
+}
+
 void *Frame::download(void *dev, size_t bytes, std::vector<uint8_t> &host)
 {
   if (!dev)
     return nullptr;
   CudaDeviceScope scope(device);
-  // staged through one pinned buffer so the copy runs at full PCIe rate
-  if (m_pinnedBytes < bytes) {
-    if (m_pinned)
-      cudaFreeHost(m_pinned);
-    m_pinned = nullptr;
-    if (cudaMallocHost(&m_pinned, bytes) != cudaSuccess) {
-      cudaGetLastError();
-      m_pinnedBytes = 0;
-    } else
-      m_pinnedBytes = bytes;
-  }
-  if (m_pinned && &host == &m_hColor) { // colour is mapped every frame: hand out the pinned buffer directly
-    cudaMemcpyAsync(m_pinned, dev, bytes, cudaMemcpyDeviceToHost, (cudaStream_t)device->stream());
-    cudaStreamSynchronize((cudaStream_t)device->stream());
-    return m_pinned;
+  if (&host == &m_hColor) { // colour is mapped every frame: hand out the pinned buffer directly
+    if (m_pinnedHoldsFrame && m_pinned)
+      return m_pinned; // the launch already streamed this frame's colour to the host (wait() has run)
+    m_streamColorToHost = true; // from the next launch on
+    if (ensurePinned(bytes)) {
+      cudaMemcpyAsync(m_pinned, dev, bytes, cudaMemcpyDeviceToHost, (cudaStream_t)device->stream());
+      cudaStreamSynchronize((cudaStream_t)device->stream());
+      m_pinnedHoldsFrame = true; // until the next launch
+      return m_pinned;
+    }
   }
   host.resize(bytes);
   cudaMemcpy(host.data(), dev, bytes, cudaMemcpyDeviceToHost);

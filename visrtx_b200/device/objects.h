@@ -325,8 +325,13 @@ struct Frame : Object
        *m_instId = nullptr, *m_albedoAccum = nullptr, *m_normalAccum = nullptr, *m_albedo = nullptr,
        *m_normal = nullptr;
   std::vector<uint8_t> m_hColor, m_hDepth, m_hPrim, m_hObj, m_hInst, m_hAlbedo, m_hNormal;
-  void *m_pinned = nullptr;
+  void *m_pinned = nullptr; // pinned host copy of the colour channel (device-accessible under UVA)
   size_t m_pinnedBytes = 0;
+  // Once the application has mapped channel.color to the host, later launches also stream the encoded colour
+  // straight into m_pinned (DvrFrameBuffers::outColorMirror), so the next map needs no copy after the march.
+  bool m_streamColorToHost = false;
+  bool m_pinnedHoldsFrame = false;
+  bool ensurePinned(size_t bytes);
   void *m_eventStart = nullptr, *m_eventEnd = nullptr;
   int m_frameID = 0, m_checkerboardID = -1;
   float m_invFrameID = 1.f;
