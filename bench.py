@@ -431,10 +431,12 @@ def run_ours(args, torch, dist, rank, world):
     FMT, INTEG, BG = capi.DVR_FORMAT_UFIXED8_RGBA_SRGB, capi.DVR_INTEGRATOR_DEFAULT, (0.1, 0.1, 0.1, 1.0)
     if mode == "sort-last":
         driver = multigpu.SortLast(capi, torch, dist, rank, world, device, W, H, inst, 0, 0, FMT, INTEG, args.rate, BG,
-                                   skip=bool(args.skip))
+                                   skip=bool(args.skip), host_mirror=world > 1)
     else:
         driver = multigpu.SortFirst(capi, torch, dist, rank, world, device, W, H, inst, ninst, FMT, INTEG, args.rate,
-                                    BG, skip=bool(args.skip), tile_band=int(os.environ.get("DVR_TILE_BAND", "1")))
+                                    BG, skip=bool(args.skip), tile_band=int(os.environ.get("DVR_TILE_BAND", "1")),
+                                    host_mirror=world > 1)
+    driver.stream_to_host(False)  # the device-timed region keeps every byte in HBM; e2e turns the host stream on
     fb = driver.fb
     host_color = torch.empty(npx, dtype=torch.int32, pin_memory=True)
 
@@ -531,13 +533,22 @@ def run_ours(args, torch, dist, rank, world):
         def e2e_step(i):
             cam_i, _ = orbit(args, az_deg=30.0 + 0.05 * i)
             driver.render(0, cam_i, stream)
-            if rank == 0:
+            if rank == 0 and driver.host_frame is None:
                 _cudart.cudaMemcpyAsync(_C.c_void_p(host_color.data_ptr()), _C.c_void_p(driver.color_ptr),
                                         _C.c_size_t(npx * 4), _C.c_int(2), _C.c_void_p(stream))
             torch.cuda.synchronize()
+            if rank == 0 and driver.host_frame is not None:  # read the result on the host
+                e2e_state["checksum"] ^= int(host_view[npx // 2])
 
-        e2e_what = (f"{mode} driver over the C-ABI: moved camera (kernel parameter upload) + render on {world} GPUs + "
-                    "assembled colour frame copied to pinned host memory on the display rank every step, wall clock")
+        e2e_state = {"checksum": 0}
+        driver.stream_to_host(True)
+        host_view = driver.host_frame.numpy() if driver.host_frame is not None else None
+        e2e_what = (f"{mode} driver over the C-ABI: moved camera (kernel parameter upload) + render on {world} GPUs; "
+                    "every rank's final-colour stores also go to one pinned host frame shared by all processes "
+                    "(POSIX shm + cudaHostRegister, DvrFrameBuffers::outColorMirror), read on the display rank "
+                    "every step, wall clock" if driver.host_frame is not None else
+                    f"{mode} driver over the C-ABI: moved camera + render on {world} GPUs + assembled colour frame "
+                    "copied to pinned host memory on the display rank every step, wall clock")
 
     for i in range(3):
         e2e_step(i)

@@ -35,15 +35,20 @@ def main():
     # ---- sort-first: replicated field, interleaved tile rows, peer stores into rank 0's frame
     cs = H.CudaScene(scene, device=f"cuda:{local}")
     sf = multigpu.SortFirst(capi, torch, dist, rank, world, device, scene.width, scene.height, cs.instances, cs.n,
-                            scene.fmt, scene.integrator, scene.volume_sampling_rate, scene.background)
+                            scene.fmt, scene.integrator, scene.volume_sampling_rate, scene.background, host_mirror=True)
     for fid in range(3):
         sf.render(fid, scene.camera, stream)
     torch.cuda.synchronize()
+    dist.barrier()
     if rank == 0:
         got = sf.color_tensor().cpu().numpy().view(np.uint32)
         same = np.array_equal(got, single["color"])
         print(f"[sort-first x{world}] bit-identical to single GPU: {same}")
         ok &= same
+        # the shared pinned host frame every rank streamed its tile rows into holds the same image
+        same_host = np.array_equal(np.array(sf.host_frame.numpy(), copy=True), got)
+        print(f"[sort-first x{world}] shared host frame == device frame: {same_host}")
+        ok &= same_host
     sf.close()
     cs.destroy()
 
@@ -52,12 +57,17 @@ def main():
     z0, z1 = multigpu.slab_ranges(nz, world)[rank]
     cs = H.CudaScene(scene, slab=(z0, z1) if world > 1 else None, device=f"cuda:{local}")
     sl = multigpu.SortLast(capi, torch, dist, rank, world, device, scene.width, scene.height, cs.instances, v.vol_id,
-                           v.inst_id, scene.fmt, scene.integrator, scene.volume_sampling_rate, scene.background)
+                           v.inst_id, scene.fmt, scene.integrator, scene.volume_sampling_rate, scene.background,
+                           host_mirror=True)
     for fid in range(3):
         sl.render(fid, scene.camera, stream)
     torch.cuda.synchronize()
+    dist.barrier()
     if rank == 0:
         got = sl.color_tensor().cpu().numpy().view(np.uint32)
+        same_host = np.array_equal(np.array(sl.host_frame.numpy(), copy=True), got)
+        print(f"[sort-last x{world}] shared host frame == device frame: {same_host}")
+        ok &= same_host
         d = np.abs(H.unpack_rgba8(got) - H.unpack_rgba8(single["color"])).max(axis=-1)
         good = (d <= 1).mean() >= 0.999 and d.max() <= 3
         print(f"[sort-last x{world}] max diff {d.max()}/255, frac<=1/255 {(d <= 1).mean():.5f}: {good}")

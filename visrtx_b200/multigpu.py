@@ -60,6 +60,61 @@ def exchange_bytes(dist, payload: bytes, world: int) -> List[bytes]:
     return out
 
 
+class SharedHostFrame:
+    """One host copy of the display frame that EVERY rank's GPU can store into: a POSIX shared-memory segment
+    created by rank 0, mapped by all ranks and pinned + device-mapped in each process (cudaHostRegister).  Its
+    device address goes into DvrFrameBuffers::outColorMirror, so each rank's resolve / render kernel streams its
+    pixels of the final image to the host during the launch — the multi-process version of the single-GPU host
+    streaming; no device->host copy after the frame."""
+
+    def __init__(self, dist, rank: int, world: int, nbytes: int):
+        import ctypes
+        from multiprocessing import shared_memory
+        self.rank, self.nbytes = rank, nbytes
+        name = ""
+        if rank == 0:
+            self.shm = shared_memory.SharedMemory(create=True, size=nbytes)
+            name = self.shm.name
+        names = exchange_bytes(dist, name.encode(), world) if world > 1 else [name.encode()]
+        if rank != 0:
+            self.shm = shared_memory.SharedMemory(name=names[0].decode())
+            try:  # the creator unlinks the segment; attachments must not be tracked (Python < 3.13 has no track=False)
+                from multiprocessing import resource_tracker
+                resource_tracker.unregister(self.shm._name, "shared_memory")
+            except Exception:
+                pass
+        self._cudart = ctypes.CDLL("libcudart.so")
+        self.host_ptr = ctypes.addressof(ctypes.c_char.from_buffer(self.shm.buf))
+        # cudaHostRegisterPortable | cudaHostRegisterMapped
+        rc = self._cudart.cudaHostRegister(ctypes.c_void_p(self.host_ptr), ctypes.c_size_t(nbytes), ctypes.c_uint(1 | 2))
+        if rc != 0:
+            raise RuntimeError(f"cudaHostRegister failed ({rc})")
+        dp = ctypes.c_void_p()
+        rc = self._cudart.cudaHostGetDevicePointer(ctypes.byref(dp), ctypes.c_void_p(self.host_ptr), ctypes.c_uint(0))
+        if rc != 0:
+            raise RuntimeError(f"cudaHostGetDevicePointer failed ({rc})")
+        self.dev_ptr = dp.value
+
+    def numpy(self, dtype="uint32"):
+        import numpy as np
+        return np.frombuffer(self.shm.buf, dtype=dtype, count=self.nbytes // np.dtype(dtype).itemsize)
+
+    def close(self, dist=None):
+        import ctypes
+        self._cudart.cudaHostUnregister(ctypes.c_void_p(self.host_ptr))
+        if dist is not None:
+            dist.barrier()
+        try:
+            self.shm.close()
+        except BufferError:  # a numpy view is still alive; the segment goes away with the process
+            pass
+        if self.rank == 0:
+            try:
+                self.shm.unlink()
+            except FileNotFoundError:
+                pass
+
+
 class _Barrier:
     """Stream-ordered barrier: a 1-element all-reduce enqueued on the current stream (no host sync)."""
 
@@ -76,7 +131,7 @@ class SortFirst:
 
     def __init__(self, capi, torch, dist, rank: int, world: int, device, width: int, height: int, instances,
                  n_instances: int, fmt: int, integrator: int, rate: float, background, skip: bool = False,
-                 tile_band: int = 1):
+                 tile_band: int = 1, host_mirror: bool = False):
         self.capi, self.torch, self.dist = capi, torch, dist
         self.rank, self.world, self.device = rank, world, device
         self.W, self.H, self.fmt = width, height, fmt
@@ -100,13 +155,21 @@ class SortFirst:
             handles = exchange_bytes(dist, handle, world)
             if rank != 0:
                 self.color_ptr = capi.ipc_open(handles[0])
-        self.fb = capi.frame_buffers(self.accum.data_ptr(), self.color_ptr, self.depth.data_ptr())
+        self.host_frame = SharedHostFrame(dist, rank, world, npx * px_bytes) if host_mirror else None
+        self._fb_plain = capi.frame_buffers(self.accum.data_ptr(), self.color_ptr, self.depth.data_ptr())
+        self._fb_mirror = capi.frame_buffers(self.accum.data_ptr(), self.color_ptr, self.depth.data_ptr(),
+                                             color_mirror=self.host_frame.dev_ptr) if self.host_frame else None
+        self.fb = self._fb_mirror or self._fb_plain
         self.barrier = _Barrier(dist, torch, device) if world > 1 else (lambda: None)
 
     def params(self, frame_id: int):
         return self.capi.frame_params(self.W, self.H, self.fmt, self.integrator, frame_id, -1, 1, self.rate,
                                       self.background, tile_rank=self.rank, tile_ranks=self.world, skip=self.skip,
                                       tile_band=self.tile_band)
+
+    def stream_to_host(self, on: bool):
+        """Route the final colour also into the shared host frame (needs host_mirror=True at construction)."""
+        self.fb = self._fb_mirror if (on and self._fb_mirror is not None) else self._fb_plain
 
     def render(self, frame_id: int, camera, stream: int):
         self.capi.render(self.params(frame_id), camera, self.instances, self.n_instances, self.fb, stream)
@@ -124,6 +187,8 @@ class SortFirst:
 
     def close(self):
         self.torch.cuda.synchronize()
+        if self.host_frame:
+            self.host_frame.close(self.dist if self.world > 1 else None)
         if self.world > 1:
             self.dist.barrier()
             if self.rank != 0:
@@ -147,7 +212,8 @@ class SortLast:
     FLAG_WORDS = 64  # [0:16] partial-complete per source rank, [16:32] strip-resolved per source rank, [32] error
 
     def __init__(self, capi, torch, dist, rank: int, world: int, device, width: int, height: int, instance,
-                 obj_id: int, inst_id: int, fmt: int, integrator: int, rate: float, background, skip: bool = False):
+                 obj_id: int, inst_id: int, fmt: int, integrator: int, rate: float, background, skip: bool = False,
+                 host_mirror: bool = False):
         self.capi, self.torch, self.dist = capi, torch, dist
         self.rank, self.world, self.device = rank, world, device
         self.W, self.H, self.fmt = width, height, fmt
@@ -207,12 +273,20 @@ class SortLast:
                 self.color_ptr = capi.ipc_open(all_h[0][192:256])
                 self._peer_open.append(self.color_ptr)
             dist.barrier()  # every table is zeroed and mapped before the first signal can arrive
-        self.fb = capi.frame_buffers(self.accum.data_ptr(), self.color_ptr, self.depth.data_ptr())
+        self.host_frame = SharedHostFrame(dist, rank, world, npx * px_bytes) if host_mirror else None
+        self._fb_plain = capi.frame_buffers(self.accum.data_ptr(), self.color_ptr, self.depth.data_ptr())
+        self._fb_mirror = capi.frame_buffers(self.accum.data_ptr(), self.color_ptr, self.depth.data_ptr(),
+                                             color_mirror=self.host_frame.dev_ptr) if self.host_frame else None
+        self.fb = self._fb_mirror or self._fb_plain
         self.frame_parity = 0
 
     def params(self, frame_id: int):
         return self.capi.frame_params(self.W, self.H, self.fmt, self.integrator, frame_id, -1, 1, self.rate,
                                       self.background, skip=self.skip)
+
+    def stream_to_host(self, on: bool):
+        """Route the final colour also into the shared host frame (needs host_mirror=True at construction)."""
+        self.fb = self._fb_mirror if (on and self._fb_mirror is not None) else self._fb_plain
 
     def render(self, frame_id: int, camera, stream: int, wait_display: bool = True):
         capi = self.capi
@@ -261,6 +335,8 @@ class SortLast:
 
     def close(self):
         self.torch.cuda.synchronize()
+        if self.host_frame:
+            self.host_frame.close(self.dist if self.world > 1 else None)
         if self.world > 1:
             self.dist.barrier()
             for p in self._peer_open:
