@@ -638,6 +638,10 @@ def run_ours(args, torch, dist, rank, world):
                 out["extra"]["dpt"] = measure_dpt(args, torch, capi, field, cam, fb, stream, vol)
             except Exception as e:
                 out["extra"]["dpt"] = f"unavailable: {e}"
+    if driver is not None and getattr(driver, "host_frame", None) is not None:
+        host_view = None  # drop the numpy view before the shared segment is unmapped
+        driver.host_frame.close(dist if world > 1 else None)
+        driver.host_frame = None
     return out
 
 
