@@ -157,7 +157,8 @@ typedef struct DvrFrameParams
   int32_t maxDepth;             /* "maxDepth", clamped to [1,256]; 0 => 5 */
   float ambientRadiance;        /* "ambientRadiance" (dpt default 1) */
   float occlusionDistance;      /* "ambientOcclusionDistance"; 0 => 1e20 */
-  int32_t _reserved[3];
+  int32_t dptReferenceGrid;     /* DPT only: != 0 walks the grid built the reference's way (see dvr_volume_dda_majorants) */
+  int32_t _reserved[2];
 } DvrFrameParams;
 
 /* per-launch counters, filled only by dvr_render_instrumented (device memory, 64-bit each) */
@@ -263,8 +264,13 @@ int dvr_volume_majorants(const DvrVolume *v, const float **maxOpacitiesDev);
 /* The delta-tracking grid the dpt integrator walks (UniformGridData of gpu/gpu_objects.h:395-401 as
  * filled by UniformGrid::init/buildGrid/computeMaxOpacities, UniformGrid.cu:143-258): dims = ceil(field
  * dims / 16) cells dividing the field bounds evenly; *maxOpacitiesDev = device float[dims.x*dims.y*dims.z].
- * Built on first use (this call or the first DVR_INTEGRATOR_DPT frame) and after dvr_volume_update. */
-int dvr_volume_dda_majorants(DvrVolume *v, void *stream, uint32_t dims[3], const float **maxOpacitiesDev);
+ * Built on first use (this call or the first DVR_INTEGRATOR_DPT frame) and after dvr_volume_update.
+ * referenceBuild == 0 (default): conservative content (value ranges over every voxel a trilinear stencil in the
+ * cell can touch, classified with the volume's own value range).  referenceBuild != 0: the content the
+ * reference itself computes — buildGridGPU's one sample octet per macrocell at [0,1] coordinates and
+ * computeMaxOpacities with the default {0,1} range — for bit-level comparison with VisRTX. */
+int dvr_volume_dda_majorants(DvrVolume *v, int32_t referenceBuild, void *stream, uint32_t dims[3],
+    const float **maxOpacitiesDev);
 
 /* ---- the hot path ------------------------------------------------------------------- */
 

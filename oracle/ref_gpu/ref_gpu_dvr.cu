@@ -23,6 +23,9 @@
 #include "gpu/createScreenSample.h"
 #include "gpu/volumeIntegration.h"
 
+// the reference's own majorant-grid build (host class + kernels), compiled from where it lies
+#include "scene/volume/space_skipping/UniformGrid.cu"
+
 #include "dvr_b200.h" // POD parameter structs only (DvrFrameParams, DvrCamera, DvrFrameBuffers)
 
 using namespace visrtx;
@@ -219,6 +222,7 @@ struct RefField
   SpatialFieldGPUData gpu{};
   box3 bounds;
   float stepSize = 0.f;
+  ivec3 dims{0}; // what the field passes to UniformGrid::init (voxel counts / NanoVDB index-bbox extent)
 };
 struct RefVolume
 {
@@ -285,6 +289,7 @@ int refgpu_field_create(const void *hostVoxels, int dataType, const uint32_t dim
   f->gpu.grid = UniformGridData{};
   f->bounds = box3(o, o + ((vec3(dims[0], dims[1], dims[2]) - 1.f) * sp));
   f->stepSize = glm::compMin(sp / 2.f);
+  f->dims = ivec3(dims[0], dims[1], dims[2]);
   *out = f;
   return 0;
 }
@@ -310,6 +315,10 @@ int refgpu_field_create_nvdb(const void *hostBlob, size_t bytes, RefField **out)
   f->gpu.data.nvdbRegular.gridData = f->nvdb;
   f->gpu.data.nvdbRegular.gridType = meta->mGridType;
   f->gpu.grid = UniformGridData{};
+  {
+    const auto gridSize = meta->indexBBox().dim(); // NvdbRegularField.cpp:152-153
+    f->dims = ivec3(gridSize[0], gridSize[1], gridSize[2]);
+  }
   *out = f;
   return 0;
 }
@@ -370,6 +379,39 @@ int refgpu_volume_set_grid(RefVolume *v, const int dims[3], const float *hostMax
   RCK(cudaMalloc(&v->maxOpacities, n * sizeof(float)));
   RCK(cudaMemcpy(v->maxOpacities, hostMaxOpacities, n * sizeof(float), cudaMemcpyDefault)); // host or device source
   v->gridDims = ivec3(dims[0], dims[1], dims[2]);
+  return 0;
+}
+
+// The reference's OWN grid, defects included: StructuredRegularField::buildGrid / NvdbRegularField::buildGrid
+// (init + buildGrid on the field's gpuData) followed by TransferFunction1D::finalize's
+// computeMaxOpacities(stream, tfTex, tfDim) with the default {0,1} range (TransferFunction1D.cpp:74-77).
+// Optionally copies the majorants to the host.
+int refgpu_volume_build_reference_grid(RefVolume *v, int dimsOut[3], float *hostOut, size_t capacity)
+{
+  UniformGrid g;
+  g.init(v->field->dims, v->field->bounds);
+  g.buildGrid(v->field->gpu);
+  RCK(cudaDeviceSynchronize());
+  g.computeMaxOpacities(nullptr, v->tex, DVR_TF_SIZE);
+  RCK(cudaDeviceSynchronize());
+  RCK(cudaGetLastError());
+  if (v->maxOpacities) cudaFree(v->maxOpacities);
+  v->maxOpacities = g.m_maxOpacities; // ownership moves to the volume
+  v->gridDims = g.m_dims;
+  cudaFree(g.m_valueRanges);
+  const size_t n = (size_t)g.m_dims.x * g.m_dims.y * g.m_dims.z;
+  if (dimsOut) {
+    dimsOut[0] = g.m_dims.x;
+    dimsOut[1] = g.m_dims.y;
+    dimsOut[2] = g.m_dims.z;
+  }
+  if (hostOut) {
+    if (capacity < n) {
+      snprintf(g_err, sizeof(g_err), "capacity %zu < %zu cells", capacity, n);
+      return -2;
+    }
+    RCK(cudaMemcpy(hostOut, v->maxOpacities, n * sizeof(float), cudaMemcpyDeviceToHost));
+  }
   return 0;
 }
 

@@ -82,6 +82,7 @@ class SceneDesc:
     max_depth: int = 5  # dpt integrator only
     ambient_radiance: float = 1.0
     occlusion_distance: float = 1e20
+    dpt_reference_grid: bool = False  # walk the grid content the reference builds (Q7/Q8)
 
 
 def default_scene(n=64, width=256, height=256, rate=0.5, field="ml", **kw) -> SceneDesc:
@@ -114,7 +115,8 @@ def _params(scene, frame_id, cb, **kw):
     return capi.frame_params(scene.width, scene.height, scene.fmt, scene.integrator, frame_id, cb,
                              scene.num_iterations, scene.volume_sampling_rate, scene.background,
                              max_depth=scene.max_depth, ambient_radiance=scene.ambient_radiance,
-                             occlusion_distance=scene.occlusion_distance, **kw)
+                             occlusion_distance=scene.occlusion_distance,
+                             dpt_reference_grid=scene.dpt_reference_grid, **kw)
 
 
 # ------------------------------------------------------------------------------------------------------------
@@ -255,11 +257,11 @@ class CudaScene:
         capi.render(p, self.scene.camera, self.instances, self.n, self.fb)
         return None
 
-    def dda_grids(self):
+    def dda_grids(self, reference_build=False):
         """[(dims, float32[nz,ny,nx] majorants)] of the delta-tracking grids (built on demand)."""
         out = []
         for v in self.volumes:
-            dims, ptr = v.dda_majorants()
+            dims, ptr = v.dda_majorants(reference_build=reference_build)
             n = dims[0] * dims[1] * dims[2]
             a = np.zeros(n, np.float32)
             self.torch.cuda.synchronize()
@@ -295,12 +297,14 @@ def render_cuda(scene: SceneDesc, frames=1, checkerboard=False, skip=False):
 
 
 # ------------------------------------------------------------------------------------------------------------
-def render_refgpu(scene: SceneDesc, frames=1, checkerboard=False, grids=None):
+def render_refgpu(scene: SceneDesc, frames=1, checkerboard=False, grids=None, return_grids=False):
     """O-gpu: the reference's device headers (tex3D / tex1D / cuRAND) on the same GPU.
-    grids: per volume (dims, majorants) of the delta-tracking grid (dpt integrator only)."""
+    grids: per volume (dims, majorants) of the delta-tracking grid (dpt integrator only), or the string
+    "reference": every volume gets the grid the reference's own UniformGrid code builds for it."""
     import torch
     lib = ob.refgpu()
     fields, vols = [], []
+    ref_grids = []
     inst = (ob.RefInstance * max(len(scene.volumes), 1))()
     keep = []
     for i, v in enumerate(scene.volumes):
@@ -321,7 +325,15 @@ def render_refgpu(scene: SceneDesc, frames=1, checkerboard=False, grids=None):
         rc = lib.refgpu_volume_create(f, tf.ctypes.data_as(C.c_void_p), (C.c_float * 2)(*v.value_range),
                                       C.c_float(v.unit_distance), C.c_uint32(v.vol_id), C.byref(h))
         assert rc == 0, lib.refgpu_last_error()
-        if grids is not None:
+        if isinstance(grids, str) and grids == "reference":
+            gdims = (C.c_int * 3)()
+            rc = lib.refgpu_volume_build_reference_grid(h, gdims, None, C.c_size_t(0))
+            assert rc == 0, lib.refgpu_last_error()
+            gm = np.zeros(gdims[0] * gdims[1] * gdims[2], np.float32)
+            rc = lib.refgpu_volume_build_reference_grid(h, gdims, gm.ctypes.data_as(C.c_void_p), C.c_size_t(gm.size))
+            assert rc == 0, lib.refgpu_last_error()
+            ref_grids.append((tuple(gdims), gm.reshape(gdims[2], gdims[1], gdims[0])))
+        elif grids is not None:
             gd, gm = grids[i]
             gm = np.ascontiguousarray(gm, np.float32)
             rc = lib.refgpu_volume_set_grid(h, (C.c_int * 3)(*gd), gm.ctypes.data_as(C.c_void_p))
@@ -361,6 +373,8 @@ def render_refgpu(scene: SceneDesc, frames=1, checkerboard=False, grids=None):
         lib.refgpu_volume_destroy(h)
     for f in fields:
         lib.refgpu_field_destroy(f)
+    if return_grids:
+        return out, ref_grids
     return out
 
 

@@ -72,7 +72,7 @@ class DvrFrameParams(C.Structure):
                 ("inverseVolumeSamplingRate", C.c_float), ("background", C.c_float * 4),
                 ("tileRank", C.c_uint32), ("tileRanks", C.c_uint32), ("useMacrocellSkipping", C.c_int32),
                 ("tileBand", C.c_int32), ("maxDepth", C.c_int32), ("ambientRadiance", C.c_float),
-                ("occlusionDistance", C.c_float), ("_reserved", C.c_int32 * 3)]
+                ("occlusionDistance", C.c_float), ("dptReferenceGrid", C.c_int32), ("_reserved", C.c_int32 * 2)]
 
 
 class DvrRenderStats(C.Structure):
@@ -290,11 +290,13 @@ class Volume:
         _check(lib.dvr_volume_majorants(self.handle, C.byref(p)))
         return p.value
 
-    def dda_majorants(self, stream: int = 0):
-        """(dims, device pointer) of the delta-tracking grid; builds it if needed."""
+    def dda_majorants(self, stream: int = 0, reference_build: bool = False):
+        """(dims, device pointer) of the delta-tracking grid; builds it if needed.  reference_build: the content
+        the reference computes (quirks Q7/Q8) instead of the conservative one."""
         p = C.c_void_p()
         dims = (C.c_uint32 * 3)()
-        _check(lib.dvr_volume_dda_majorants(self.handle, C.c_void_p(stream), dims, C.byref(p)))
+        _check(lib.dvr_volume_dda_majorants(self.handle, C.c_int32(1 if reference_build else 0), C.c_void_p(stream),
+                                            dims, C.byref(p)))
         return tuple(dims), p.value
 
     def destroy(self) -> None:
@@ -317,7 +319,7 @@ def make_instances(volumes: Sequence[Volume], xfms=None, inst_ids=None):
 def frame_params(width, height, fmt=DVR_FORMAT_UFIXED8_RGBA_SRGB, integrator=DVR_INTEGRATOR_RAYCAST, frame_id=0,
                  checkerboard_id=-1, num_iterations=1, volume_sampling_rate=0.125, background=(0.0, 0.0, 0.0, 1.0),
                  tile_rank=0, tile_ranks=1, skip=False, tile_band=1, max_depth=5, ambient_radiance=1.0,
-                 occlusion_distance=1e20) -> DvrFrameParams:
+                 occlusion_distance=1e20, dpt_reference_grid=False) -> DvrFrameParams:
     p = DvrFrameParams()
     p.width, p.height, p.format, p.integrator = int(width), int(height), int(fmt), int(integrator)
     p.frameID, p.checkerboardID, p.numIterations = int(frame_id), int(checkerboard_id), int(num_iterations)
@@ -328,6 +330,7 @@ def frame_params(width, height, fmt=DVR_FORMAT_UFIXED8_RGBA_SRGB, integrator=DVR
     p.useMacrocellSkipping = 1 if skip else 0
     p.tileBand = int(tile_band)
     p.maxDepth, p.ambientRadiance, p.occlusionDistance = int(max_depth), float(ambient_radiance), float(occlusion_distance)
+    p.dptReferenceGrid = 1 if dpt_reference_grid else 0
     return p
 
 

@@ -105,6 +105,7 @@ struct DvrVolume
   float *ddaMaxOpacities = nullptr; // delta-tracking grid (built on first use by the dpt integrator)
   float2 *ddaRanges = nullptr;
   bool ddaValid = false;
+  bool ddaReference = false; // content of the current grid: the reference's build (Q7/Q8) or the conservative one
   float vrLo = 0.f, vrHi = 1.f, oneOverUnitDistance = 1.f;
   uint32_t id = ~0u;
 };
@@ -831,15 +832,16 @@ int dvr_volume_destroy(DvrVolume *v)
   return DVR_OK;
 }
 
-static int ensureDdaGrid(DvrVolume *v, cudaStream_t s);
+static int ensureDdaGrid(DvrVolume *v, bool referenceBuild, cudaStream_t s);
 
-int dvr_volume_dda_majorants(DvrVolume *v, void *stream, uint32_t dims[3], const float **maxOpacitiesDev)
+int dvr_volume_dda_majorants(DvrVolume *v, int32_t referenceBuild, void *stream, uint32_t dims[3],
+    const float **maxOpacitiesDev)
 {
   if (!v || !dims || !maxOpacitiesDev) {
     setError("dvr_volume_dda_majorants: null argument");
     return DVR_ERR_INVALID_ARGUMENT;
   }
-  const int rc = ensureDdaGrid(v, (cudaStream_t)stream);
+  const int rc = ensureDdaGrid(v, referenceBuild != 0, (cudaStream_t)stream);
   if (rc != DVR_OK)
     return rc;
   dims[0] = (uint32_t)v->field->dev.gridDims.x;
@@ -896,9 +898,9 @@ static void fillInstance(const DvrVolumeInstance &in, InstanceDev &d)
 
 // UniformGrid::init/buildGrid/computeMaxOpacities for the delta tracker: the reference's grid geometry
 // (gridDims cells dividing the bounds evenly) with conservative content.  Built lazily per volume.
-static int ensureDdaGrid(DvrVolume *v, cudaStream_t s)
+static int ensureDdaGrid(DvrVolume *v, bool referenceBuild, cudaStream_t s)
 {
-  if (v->ddaValid)
+  if (v->ddaValid && v->ddaReference == referenceBuild)
     return DVR_OK;
   const DvrField *f = v->field;
   const int3 g = f->dev.gridDims;
@@ -912,12 +914,19 @@ static int ensureDdaGrid(DvrVolume *v, cudaStream_t s)
       ? make_float3((float)f->dev.dims.x, (float)f->dev.dims.y, (float)f->dev.dims.z)
       : make_float3((float)f->dev.dims.x - 1.f, (float)f->dev.dims.y - 1.f, (float)f->dev.dims.z - 1.f);
   const float3 w = make_float3(span.x / (float)g.x, span.y / (float)g.y, span.z / (float)g.z);
-  int rc = launchDdaRangeBuild(f->dev, f->pointTex, g, w, v->ddaRanges, s);
-  if (rc != DVR_OK)
-    return rc;
-  rc = launchMajorants(v->ddaRanges, n, v->tf, v->vrLo, v->vrHi, v->ddaMaxOpacities, s);
-  if (rc == DVR_OK)
+  int rc;
+  if (referenceBuild)
+    rc = launchReferenceGridBuild(f->dev, g, v->tf, v->ddaRanges, v->ddaMaxOpacities, s);
+  else {
+    rc = launchDdaRangeBuild(f->dev, f->pointTex, g, w, v->ddaRanges, s);
+    if (rc != DVR_OK)
+      return rc;
+    rc = launchMajorants(v->ddaRanges, n, v->tf, v->vrLo, v->vrHi, v->ddaMaxOpacities, s);
+  }
+  if (rc == DVR_OK) {
     v->ddaValid = true;
+    v->ddaReference = referenceBuild;
+  }
   return rc;
 }
 
@@ -966,7 +975,7 @@ static int renderImpl(const DvrFrameParams *p, const DvrCamera *camera, const Dv
   L.occlusionDistance = p->occlusionDistance > 0.f ? p->occlusionDistance : 1e20f;
   if (p->integrator == DVR_INTEGRATOR_DPT)
     for (uint32_t i = 0; i < nInstances; ++i) {
-      const int rcg = ensureDdaGrid(const_cast<DvrVolume *>(instances[i].volume), s);
+      const int rcg = ensureDdaGrid(const_cast<DvrVolume *>(instances[i].volume), p->dptReferenceGrid != 0, s);
       if (rcg != DVR_OK)
         return rcg;
     }

@@ -8,6 +8,7 @@
 // the difference between the marcher's fp32 cell test and the texture unit's own coordinate rounding.  The reference's build samples the wrong coordinates
 //  and is deliberately not reproduced.
 #include "dvr_internal.h"
+#include "dvr_march.cuh"
 
 namespace dvr {
 
@@ -174,6 +175,125 @@ int launchDdaRangeBuild(const FieldDev &f, cudaTextureObject_t pointTex, int3 gr
   dvrDdaRangeKernel<<<grid, 256, 0, s>>>(f, pointTex, gridDims, cellWidthVoxels, ranges);
   DVR_CUDA(cudaGetLastError());
   countLaunch();
+  return DVR_OK;
+}
+
+// ---- the reference's own delta-tracking grid, defects included (opt-in: DvrFrameParams::dptReferenceGrid) -------
+// buildGridGPU (UniformGrid.cu:92-150) runs one thread per MACROCELL: it takes the max of the field at the eight
+// points (cellID +- .5) / gridDims — coordinates in [0,1] that it hands to the sampler as object-space positions
+//  — and splats that one value as both range ends into the cells its bounds project onto.
+// computeMaxOpacitiesGPU (UniformGrid.cu:55-90) then classifies the ranges with the DEFAULT value range {0,1}
+// (Q8) over texels int(lo*255) .. int(hi*255)+1.  Reproduced operation for operation so that a dpt frame can be
+// made to match the real reference bit for bit; the default grid (above) is the conservative one.
+__device__ __forceinline__ void atomicMinFloat(float *address, float val)
+{ // gpu_util.h:108-117
+  int ret = __float_as_int(*address);
+  while (val < __int_as_float(ret)) {
+    const int old = ret;
+    if ((ret = atomicCAS((int *)address, old, __float_as_int(val))) == old)
+      break;
+  }
+}
+__device__ __forceinline__ void atomicMaxFloat(float *address, float val)
+{ // gpu_util.h:119-128
+  int ret = __float_as_int(*address);
+  while (val > __int_as_float(ret)) {
+    const int old = ret;
+    if ((ret = atomicCAS((int *)address, old, __float_as_int(val))) == old)
+      break;
+  }
+}
+
+__global__ void dvrRefGridInvalidateKernel(float2 *__restrict__ ranges, size_t n)
+{ // invalidateRangesGPU, UniformGrid.cu:44-53
+  const size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  if (i < n)
+    ranges[i] = make_float2(+1e30f, -1e30f);
+}
+
+__device__ __forceinline__ int3 projectOnGridRef(float3 V, int3 dims, float3 lo, float3 hi)
+{ // uniformGrid.h:44-50
+  const float3 v01 = make_float3(__fdiv_rn(__fsub_rn(V.x, lo.x), __fsub_rn(hi.x, lo.x)),
+      __fdiv_rn(__fsub_rn(V.y, lo.y), __fsub_rn(hi.y, lo.y)), __fdiv_rn(__fsub_rn(V.z, lo.z), __fsub_rn(hi.z, lo.z)));
+  return make_int3(min(max((int)__fmul_rn(v01.x, (float)dims.x), 0), dims.x - 1),
+      min(max((int)__fmul_rn(v01.y, (float)dims.y), 0), dims.y - 1),
+      min(max((int)__fmul_rn(v01.z, (float)dims.z), 0), dims.z - 1));
+}
+
+__global__ void dvrRefGridBuildKernel(const __grid_constant__ FieldDev f, int3 dims, float2 *__restrict__ ranges)
+{
+  const size_t tid = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  const size_t n = (size_t)dims.x * dims.y * dims.z;
+  if (tid >= n)
+    return;
+  const int3 id = make_int3((int)(tid % dims.x), (int)(tid / dims.x % dims.y), (int)(tid / ((size_t)dims.x * dims.y)));
+  const float3 lo = f.boundsLo, hi = f.boundsHi;
+  const float3 ext = make_float3(__fdiv_rn(__fsub_rn(hi.x, lo.x), (float)dims.x), __fdiv_rn(__fsub_rn(hi.y, lo.y), (float)dims.y),
+      __fdiv_rn(__fsub_rn(hi.z, lo.z), (float)dims.z));
+  // voxelBounds: lower + id * ext (one fused multiply-add on the GPU), upper = that + ext
+  const float3 bl = make_float3(__fmaf_rn((float)id.x, ext.x, lo.x), __fmaf_rn((float)id.y, ext.y, lo.y),
+      __fmaf_rn((float)id.z, ext.z, lo.z));
+  const float3 bu = make_float3(__fadd_rn(bl.x, ext.x), __fadd_rn(bl.y, ext.y), __fadd_rn(bl.z, ext.z));
+  const float3 halfSpacing = 0.5f * f.spacing;
+  NvdbCache cache;
+  cache.reset();
+  float v = -1e30f;
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    // the corner order of UniformGrid.cu:119-126 does not matter for a max
+    const float3 tc = make_float3(__fdiv_rn(__fadd_rn((float)id.x, (k & 1) ? .5f : -.5f), (float)dims.x),
+        __fdiv_rn(__fadd_rn((float)id.y, (k & 2) ? .5f : -.5f), (float)dims.y),
+        __fdiv_rn(__fadd_rn((float)id.z, (k & 4) ? .5f : -.5f), (float)dims.z));
+    float s;
+    if (f.kind == FIELD_NANOVDB_QUANT)
+      s = nvdbSampleTrilinear<true>(f.nv, cache, nvdbWorldToIndex(f.nv, tc));
+    else if (f.kind == FIELD_NANOVDB)
+      s = nvdbSampleTrilinear<false>(f.nv, cache, nvdbWorldToIndex(f.nv, tc));
+    else {
+      const float3 c = fieldTexCoord(f, halfSpacing, tc);
+      s = tex3D<float>(f.tex, c.x, c.y, c.z);
+    }
+    v = fmaxf(v, s);
+  }
+  const int3 a = projectOnGridRef(bl, dims, lo, hi), b = projectOnGridRef(bu, dims, lo, hi);
+  for (int z = a.z; z <= b.z; ++z)
+    for (int y = a.y; y <= b.y; ++y)
+      for (int x = a.x; x <= b.x; ++x) {
+        float2 *r = &ranges[(size_t)z * dims.x * dims.y + (size_t)y * dims.x + x];
+        atomicMinFloat(&r->x, v);
+        atomicMaxFloat(&r->y, v);
+      }
+}
+
+__global__ void dvrRefGridMajorantKernel(const float2 *__restrict__ ranges, size_t nCells, const float4 *__restrict__ tf,
+    float *__restrict__ maxOpacities)
+{ // computeMaxOpacitiesGPU with xfRange = {0,1}; tex1D at texel centres (i + .5)/256 returns the table entry
+  const size_t c = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  if (c >= nCells)
+    return;
+  const float2 r = ranges[c];
+  if (r.y < r.x) {
+    maxOpacities[c] = 0.f;
+    return;
+  }
+  const int lo = min(max((int)__fmul_rn(r.x, 255.f), 0), 255);
+  const int hi = min(max((int)__fmul_rn(r.y, 255.f) + 1, 0), 255);
+  float m = 0.f;
+  for (int i = lo; i <= hi; ++i)
+    m = fmaxf(m, __ldg(&tf[i]).w);
+  maxOpacities[c] = m;
+}
+
+int launchReferenceGridBuild(const FieldDev &f, int3 gridDims, const float4 *tf, float2 *ranges, float *maxOpacities,
+    cudaStream_t s)
+{
+  const size_t n = (size_t)gridDims.x * gridDims.y * gridDims.z;
+  const unsigned blocks = (unsigned)((n + 255) / 256);
+  dvrRefGridInvalidateKernel<<<blocks, 256, 0, s>>>(ranges, n);
+  dvrRefGridBuildKernel<<<blocks, 256, 0, s>>>(f, gridDims, ranges);
+  dvrRefGridMajorantKernel<<<blocks, 256, 0, s>>>(ranges, n, tf, maxOpacities);
+  DVR_CUDA(cudaGetLastError());
+  countLaunch(3);
   return DVR_OK;
 }
 

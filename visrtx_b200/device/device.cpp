@@ -248,6 +248,7 @@ void Frame::renderFrame()
   p.tileRanks = m_renderer->tileRanks;
   p.useMacrocellSkipping = m_renderer->macrocellSkipping ? 1 : 0;
   p.maxDepth = m_renderer->maxDepth;
+  p.dptReferenceGrid = m_renderer->dptReferenceGrid ? 1 : 0;
   p.ambientRadiance = m_renderer->ambientRadiance;
   p.occlusionDistance = m_renderer->occlusionDistance;
 
@@ -638,6 +639,7 @@ const ANARIParameter kRendererParams[] = {{"background", ANARI_FLOAT32_VEC4}, {"
     {"sampleLimit", ANARI_INT32}, {"volumeSamplingRate", ANARI_FLOAT32}, {"checkerboarding", ANARI_BOOL},
     {"macrocellSkipping", ANARI_BOOL}, {"sortFirstRank", ANARI_INT32}, {"sortFirstRanks", ANARI_INT32},
     {"maxDepth", ANARI_INT32}, {"ambientRadiance", ANARI_FLOAT32}, {"ambientOcclusionDistance", ANARI_FLOAT32},
+    {"dptReferenceGrid", ANARI_BOOL},
     {nullptr, ANARI_UNKNOWN}};
 const ANARIParameter kFieldParams[] = {{"data", ANARI_ARRAY3D}, {"origin", ANARI_FLOAT32_VEC3},
     {"spacing", ANARI_FLOAT32_VEC3}, {"filter", ANARI_STRING}, {nullptr, ANARI_UNKNOWN}};

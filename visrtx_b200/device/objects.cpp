@@ -808,6 +808,8 @@ void Renderer::commitParameters()
   if (subtype == "dpt" || subtype == "diffuse_pathtracer") { // DiffusePathTracer.cpp:41-53
     integrator = DVR_INTEGRATOR_DPT;
     maxDepth = std::min(std::max(getParam<int>("maxDepth", ANARI_INT32, 5), 1), 256);
+    // extension: walk the grid content the reference itself builds (Q7/Q8) instead of the conservative one
+    dptReferenceGrid = getParam<int32_t>("dptReferenceGrid", ANARI_BOOL, 0) != 0;
   }
   // Renderer.cpp:159-161; the dpt renderer's default ambient radiance is 1 (DiffusePathTracer.cpp:41)
   ambientRadiance = getParam<float>("ambientRadiance", ANARI_FLOAT32, integrator == DVR_INTEGRATOR_DPT ? 1.f : 0.f);

@@ -279,6 +279,7 @@ struct Renderer : Object
   float volumeSamplingRate = 0.125f;
   int integrator = DVR_INTEGRATOR_DEFAULT;
   int maxDepth = 5;                // dpt only
+  bool dptReferenceGrid = false;   // dpt only (extension)
   float ambientRadiance = 0.f;     // dpt only (the marching renderers have no lighting term for volumes)
   float occlusionDistance = 1e20f; // dpt only
   bool macrocellSkipping = true;
