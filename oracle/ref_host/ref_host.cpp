@@ -252,3 +252,18 @@ extern "C" int refhost_nvdb_read_file(const char *path, void *out, size_t capaci
   }
   return 0;
 }
+
+// a segment file holding TWO grids (float fog sphere r = radius, then an Fp8 sphere r = radius + 1), written by
+// nanovdb::io::writeGrids — import_NVDB reads grid #0 of such files (readGrid(file, n = 0))
+extern "C" int refhost_nvdb_write_two_grid_file(const char *path, double radius, int codec)
+{
+  try {
+    std::vector<nanovdb::GridHandle<>> handles;
+    handles.push_back(nanovdb::tools::createFogVolumeSphere<float>(radius, nanovdb::Vec3d(0.0), 1.0, 3.0));
+    handles.push_back(nanovdb::tools::createFogVolumeSphere<nanovdb::Fp8>(radius + 1.0, nanovdb::Vec3d(0.0), 1.0, 3.0));
+    nanovdb::io::writeGrids(path, handles, codec == 1 ? nanovdb::io::Codec::ZIP : nanovdb::io::Codec::NONE);
+  } catch (const std::exception &) {
+    return -2;
+  }
+  return 0;
+}

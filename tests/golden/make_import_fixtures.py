@@ -55,6 +55,15 @@ def main():
                 out["grid/" + name] = grid
             out["minmax/" + name] = mm
             print(name, out["file/" + name].nbytes, "bytes on disk ->", grid.nbytes, "grid bytes, min/max", mm)
+        # two grids in one segment file (writeGrids): the importer takes grid #0
+        for name, codec in (("two_grids_zip.nvdb", 1),):
+            p = os.path.join(tmp, name)
+            assert lib.refhost_nvdb_write_two_grid_file(p.encode(), C.c_double(5.0), C.c_int(codec)) == 0
+            out["file/" + name] = np.fromfile(p, np.uint8)
+            grid, mm = read_back(lib, p)
+            out["grid/" + name] = grid
+            out["minmax/" + name] = mm
+            print(name, out["file/" + name].nbytes, "bytes on disk ->", grid.nbytes, "grid bytes (grid #0), min/max", mm)
         # a grid that carries no min/max statistics: raw buffer from our own writer (flags == 0)
         rng = np.random.default_rng(23)
         dense = (rng.random((9, 14, 11)) * 0.8 + 0.1).astype(np.float32)
