@@ -368,6 +368,13 @@ int dvr_ipc_free(void *devPtr);
 /* Frame::mapAlbedoBuffer / mapNormalBuffer, frame/Frame.cu:521-557: out = accum * invFrameID */
 int dvr_scale_vec3(const float *accumVec3, float *outVec3, size_t nPixels, float scale, void *stream);
 
+/* ---- self-test ------------------------------------------------------------------------------------
+ * Empty-space skipping advances a ray over n lattice points in closed form (per float binade) instead of n
+ * dependent `t += step` additions; the lattice must stay bit-identical to the reference's loop
+ * (gpu/volumeIntegration.h:86-102).  Runs both on `count` pseudo-random operand sets on the device and returns
+ * the number that differ (must be 0). */
+int dvr_selftest_lattice_advance(uint32_t count, uint64_t seed, uint32_t *mismatchesOut, void *stream);
+
 /* ---- frame post passes on device buffers ----------------------------------
  * What TSD's render pipeline runs on the channels it maps through ANARI_NV_FRAME_BUFFERS_CUDA
  * (the .cpp files of tsd/src/render_pipeline/passes).  All pointers are device pointers (the `...CUDA` channel maps or

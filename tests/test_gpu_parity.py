@@ -301,3 +301,9 @@ def test_full_size_properties_c2():
     finally:
         v.destroy()
         f.destroy()
+
+
+def test_closed_form_lattice_advance_is_bit_identical_to_the_add_loop():
+    """4 M pseudo-random (t, step, n, tUpper) sets, incl. power-of-two steps (round-to-even ties), tiny and huge t."""
+    for seed in (1, 77, 2024, 999983):
+        assert capi.selftest_lattice_advance(1 << 20, seed) == 0

@@ -35,7 +35,7 @@ EXPORTED_SYMBOLS = [
     "dvr_volume_create", "dvr_volume_update", "dvr_volume_destroy", "dvr_volume_majorants",
     "dvr_volume_dda_majorants",
     "dvr_post_convert_float_color", "dvr_post_composite_depth", "dvr_post_outline", "dvr_post_visualize_depth",
-    "dvr_post_pick",
+    "dvr_post_pick", "dvr_selftest_lattice_advance",
     "dvr_render", "dvr_render_instrumented", "dvr_launch_count",
     "dvr_render_partial", "dvr_render_partial_instrumented", "dvr_composite_over", "dvr_resolve", "dvr_scale_vec3",
     "dvr_composite_resolve_peers", "dvr_render_partial_sync", "dvr_composite_resolve_peers_sync", "dvr_wait_flags",
@@ -468,3 +468,10 @@ def post_pick(depth_ptr: int, object_id_ptr: int, width: int, height: int, x: in
     _check(lib.dvr_post_pick(C.c_void_p(depth_ptr), C.c_void_p(object_id_ptr or None), C.c_uint32(width),
                              C.c_uint32(height), C.c_uint32(x), C.c_uint32(y), C.byref(d), C.byref(i), C.c_void_p(stream)))
     return d.value, i.value
+
+
+def selftest_lattice_advance(count: int = 1 << 20, seed: int = 1, stream: int = 0) -> int:
+    """Number of operand sets on which the closed-form lattice advance differs from the literal add loop (0)."""
+    m = C.c_uint32(0xFFFFFFFF)
+    _check(lib.dvr_selftest_lattice_advance(C.c_uint32(count), C.c_uint64(seed), C.byref(m), C.c_void_p(stream)))
+    return m.value

@@ -1357,6 +1357,31 @@ int dvr_ipc_free(void *devPtr)
   return DVR_OK;
 }
 
+int dvr_selftest_lattice_advance(uint32_t count, uint64_t seed, uint32_t *mismatchesOut, void *stream)
+{
+  if (!mismatchesOut) {
+    setError("dvr_selftest_lattice_advance: null argument");
+    return DVR_ERR_INVALID_ARGUMENT;
+  }
+  if (dvr_device_count() <= 0) {
+    setError("dvr_selftest_lattice_advance: no CUDA device (this library has no CPU fallback)");
+    return DVR_ERR_NO_DEVICE;
+  }
+  unsigned int *d = nullptr;
+  DVR_CUDA(cudaMalloc(&d, sizeof(unsigned int)));
+  cudaStream_t s = (cudaStream_t)stream;
+  cudaMemsetAsync(d, 0, sizeof(unsigned int), s);
+  int rc = count ? launchSelftestLattice(count, seed, d, s) : DVR_OK;
+  if (rc == DVR_OK) {
+    const cudaError_t e = cudaMemcpyAsync(mismatchesOut, d, sizeof(unsigned int), cudaMemcpyDeviceToHost, s);
+    const cudaError_t e2 = cudaStreamSynchronize(s);
+    if (e != cudaSuccess || e2 != cudaSuccess)
+      rc = cudaFail(e != cudaSuccess ? e : e2, "dvr_selftest_lattice_advance");
+  }
+  cudaFree(d);
+  return rc;
+}
+
 int dvr_scale_vec3(const float *accumVec3, float *outVec3, size_t nPixels, float scale, void *stream)
 {
   if (!accumVec3 || !outVec3) {

@@ -406,6 +406,48 @@ int launchFrame(const FrameLaunch &p, bool skip, bool stats, cudaStream_t s)
 }
 
 // ----------------------------------------------------------------------------------------------
+// self-test of latticeAdvance(): closed form vs the literal `while (n > 0 && t <= tUpper) t += step` loop on
+// pseudo-random operands (Philox), including power-of-two steps (round-to-even ties) and tiny / huge t
+__global__ void dvrSelftestLatticeKernel(uint32_t count, unsigned long long seed, unsigned int *mismatches)
+{
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= count)
+    return;
+  Philox rng;
+  rng.init(seed + i, 0ull);
+  const float4 r = rng.uniform4();
+  const float4 q = rng.uniform4();
+  float t, step;
+  switch (i % 5u) {
+  case 0: t = r.x * 4000.f; step = r.y * 2.f + 1e-3f; break;
+  case 1: t = r.x * 10.f; step = exp2f(floorf(r.y * 15.f) - 12.f); break;
+  case 2: t = exp2f(floorf(r.x * 17.f) - 3.f) * (1.f + r.z); step = exp2f(floorf(r.y * 24.f) - 20.f) * 1.5f; break;
+  case 3: t = r.x * 1e-3f; step = r.y * 0.1f; break;
+  default: t = r.x * 3000.f + 1000.f; step = 1.f; break;
+  }
+  const int n = 1 + (int)(q.x * 3000.f);
+  const float tUpper = t + q.y * step * (float)n * 1.5f;
+  float a = t;
+  int ka = 0;
+  for (int k = n; k > 0 && a <= tUpper; --k) {
+    a = __fadd_rn(a, step);
+    ++ka;
+  }
+  int kb;
+  const float b = latticeAdvance(t, step, n, tUpper, kb);
+  if (__float_as_int(a) != __float_as_int(b) || ka != kb)
+    atomicAdd(mismatches, 1u);
+}
+
+int launchSelftestLattice(uint32_t count, unsigned long long seed, unsigned int *mismatches, cudaStream_t s)
+{
+  dvrSelftestLatticeKernel<<<(count + 255) / 256, 256, 0, s>>>(count, seed, mismatches);
+  DVR_CUDA(cudaGetLastError());
+  countLaunch();
+  return DVR_OK;
+}
+
+// ----------------------------------------------------------------------------------------------
 // sort-last partial render: premultiplied (C,A) + entry depth of ONE slab on the global lattice
 // ----------------------------------------------------------------------------------------------
 template <bool SKIP, bool STATS>

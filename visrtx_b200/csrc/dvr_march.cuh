@@ -120,6 +120,62 @@ __device__ __forceinline__ float fieldSample(const FieldDev &f, NvdbCache &cache
   return fieldFetch<SLAB>(f, c);
 }
 
+// `while (n > 0 && t <= tUpper) { t += step; --n; }` — the reference's lattice is DEFINED by repeated float
+// addition, so skipped lattice points must land on exactly the values that loop produces.  Inside one binade
+// [2^e, 2^(e+1)) every float is a multiple of the same ulp u, so each round-to-nearest add moves t by the same
+// amount inc = fl(t + step) - t (a multiple of u) unless t + step falls exactly half-way between two floats
+// (ties-to-even alternates).  Hence k further adds give t + k*inc exactly as long as the results stay in the
+// binade: one real add measures inc, the rest of the binade is jumped in closed form (exact in double), and the
+// add that crosses into the next binade is again a real one.  O(binades crossed) instead of O(n); bit-identical
+// to the loop (tests: skipping on/off, sort-last).
+__device__ __forceinline__ float latticeAdvance(float t, const float step, int n, const float tUpper, int &taken)
+{
+  taken = 0;
+  while (n > 0 && t <= tUpper) {
+    const float t0 = t;
+    t = __fadd_rn(t0, step); // a real step
+    ++taken;
+    --n;
+    if (n == 0 || !(t <= tUpper))
+      break;
+    const float inc = __fsub_rn(t, t0); // exact: both are multiples of the binade's ulp
+    const int e0 = (__float_as_int(t0) >> 23) & 0xff, e1 = (__float_as_int(t) >> 23) & 0xff;
+    const int es = (__float_as_int(step) >> 23) & 0xff;
+    if (!(t0 > 0.f) || e0 != e1 || e1 == 0 || e1 == 0xff || e1 - es > 28 || es - e1 > 1)
+      continue; // crossing a binade (or degenerate operands): keep taking real steps
+    if (!(inc > 0.f)) { // step is below half an ulp of t: the loop would spin in place for all remaining adds
+      taken += n;
+      n = 0;
+      break;
+    }
+    const double u = __longlong_as_double((long long)(e1 - 127 - 23 + 1023) << 52); // ulp of the binade
+    const double err = ((double)t0 + (double)step) - (double)t;                       // exact
+    if (fabs(err) * 2.0 == u)
+      continue; // a tie: round-to-even makes the increment alternate
+    const double td = (double)t, incd = (double)inc;
+    const double top = __longlong_as_double((long long)(e1 - 127 + 1 + 1023) << 52); // 2^(e+1)
+    long long kb = (long long)floor((top - td) / incd); // adds whose RESULT stays below 2^(e+1)
+    while (kb > 0 && td + (double)kb * incd >= top)
+      --kb;
+    while (td + (double)(kb + 1) * incd < top)
+      ++kb;
+    long long ku = (long long)floor(((double)tUpper - td) / incd) + 1; // adds the loop executes before t > tUpper
+    while (ku > 1 && td + (double)(ku - 1) * incd > (double)tUpper)
+      --ku;
+    while (td + (double)ku * incd <= (double)tUpper)
+      ++ku;
+    long long k = kb < ku ? kb : ku;
+    if (k > (long long)n)
+      k = n;
+    if (k > 0) {
+      t = (float)(td + (double)k * incd); // exact: a multiple of u below 2^(e+1)
+      taken += (int)k;
+      n -= (int)k;
+    }
+  }
+  return t;
+}
+
 // One volume segment [tLower(after jitter #1), tUpper] of one ray.
 //   SKIP : consult the per-macrocell majorants and step over fully transparent cells on the
 //          SAME sample lattice (t advances by repeated `t += step`, so the taken samples are
@@ -210,13 +266,11 @@ __device__ __forceinline__ void marchSegment(const VolumeDev &v, const float4 *_
         // Whole steps that stay strictly inside the cell (one step of safety margin); at least THIS lattice
         // point is skippable on its own: the cell containing its lower tap has majorant 0, so its fetch
         // would classify to alpha == 0 exactly and contribute nothing.
-        int n = max((int)floorf(fminf(dt / stepSize, 1.0e6f)) - 1, 1);
-        while (n > 0 && t <= tUpper) {
-          t = __fadd_rn(t, stepSize);
-          --n;
-          if (STATS && g == 0)
-            stats.skipped++;
-        }
+        const int n = max((int)floorf(fminf(dt / stepSize, 1.0e6f)) - 1, 1);
+        int taken;
+        t = latticeAdvance(t, stepSize, n, tUpper, taken);
+        if (STATS && g == 0)
+          stats.skipped += (unsigned long long)taken;
         continue;
       }
     }
