@@ -102,6 +102,8 @@ struct DvrVolume
   float *maxOpacities = nullptr;
   float *maxOpacitiesCoarse = nullptr;
   int3 coarseDims{0, 0, 0};
+  float *maxOpacitiesCoarse2 = nullptr; // 256^3-voxel blocks
+  int3 coarse2Dims{0, 0, 0};
   float *ddaMaxOpacities = nullptr; // delta-tracking grid (built on first use by the dpt integrator)
   float2 *ddaRanges = nullptr;
   bool ddaValid = false;
@@ -787,7 +789,10 @@ int dvr_volume_update(DvrVolume *v, const float *tfRgba, const float valueRange[
   const int rc = launchMajorants(v->field->ranges, v->field->nCells, v->tf, v->vrLo, v->vrHi, v->maxOpacities, s);
   if (rc != DVR_OK)
     return rc;
-  return launchMajorantsCoarse(v->maxOpacities, v->field->dev.gridDims, v->maxOpacitiesCoarse, v->coarseDims, s);
+  const int rc2 = launchMajorantsCoarse(v->maxOpacities, v->field->dev.gridDims, v->maxOpacitiesCoarse, v->coarseDims, s);
+  if (rc2 != DVR_OK)
+    return rc2;
+  return launchMajorantsCoarse(v->maxOpacitiesCoarse, v->coarseDims, v->maxOpacitiesCoarse2, v->coarse2Dims, s);
 }
 
 int dvr_volume_create(const DvrField *field, const float *tfRgba, const float valueRange[2], float unitDistance,
@@ -806,6 +811,10 @@ int dvr_volume_create(const DvrField *field, const float *tfRgba, const float va
   v->coarseDims = make_int3((g.x + 3) / 4, (g.y + 3) / 4, (g.z + 3) / 4);
   if (e == cudaSuccess)
     e = cudaMalloc(&v->maxOpacitiesCoarse, (size_t)v->coarseDims.x * v->coarseDims.y * v->coarseDims.z * sizeof(float));
+  v->coarse2Dims = make_int3((v->coarseDims.x + 3) / 4, (v->coarseDims.y + 3) / 4, (v->coarseDims.z + 3) / 4);
+  if (e == cudaSuccess)
+    e = cudaMalloc(&v->maxOpacitiesCoarse2,
+        (size_t)v->coarse2Dims.x * v->coarse2Dims.y * v->coarse2Dims.z * sizeof(float));
   if (e != cudaSuccess) {
     dvr_volume_destroy(v);
     return cudaFail(e, "cudaMalloc(volume)");
@@ -826,6 +835,7 @@ int dvr_volume_destroy(DvrVolume *v)
   if (v->tf) cudaFree(v->tf);
   if (v->maxOpacities) cudaFree(v->maxOpacities);
   if (v->maxOpacitiesCoarse) cudaFree(v->maxOpacitiesCoarse);
+  if (v->maxOpacitiesCoarse2) cudaFree(v->maxOpacitiesCoarse2);
   if (v->ddaMaxOpacities) cudaFree(v->ddaMaxOpacities);
   if (v->ddaRanges) cudaFree(v->ddaRanges);
   delete v;
@@ -888,6 +898,8 @@ static void fillInstance(const DvrVolumeInstance &in, InstanceDev &d)
   d.v.maxOpacities = v->maxOpacities;
   d.v.maxOpacitiesCoarse = v->maxOpacitiesCoarse;
   d.v.coarseDims = v->coarseDims;
+  d.v.maxOpacitiesCoarse2 = v->maxOpacitiesCoarse2;
+  d.v.coarse2Dims = v->coarse2Dims;
   d.v.ddaMaxOpacities = v->ddaMaxOpacities;
   d.v.ddaDims = v->field->dev.gridDims; // ceil(dims/16), UniformGrid.cu:152-154
   static const float ident[12] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0};

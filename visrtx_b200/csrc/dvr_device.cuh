@@ -57,6 +57,8 @@ struct VolumeDev
   const float *maxOpacities; // per macrocell: max TF alpha over the cell's range
   const float *maxOpacitiesCoarse; // per 4x4x4 block of macrocells (64^3 voxels): max of the children
   int3 coarseDims;
+  const float *maxOpacitiesCoarse2; // per 4x4x4 block of those (256^3 voxels)
+  int3 coarse2Dims;
   // delta-tracking grid in the reference's geometry (ceil(dims/16) cells dividing the bounds evenly)
   const float *ddaMaxOpacities;
   int3 ddaDims;

@@ -152,18 +152,28 @@ __device__ __forceinline__ float latticeAdvance(float t, const float step, int n
     const double err = ((double)t0 + (double)step) - (double)t;                       // exact
     if (fabs(err) * 2.0 == u)
       continue; // a tie: round-to-even makes the increment alternate
+    // Step counts are estimated in fp32 (one reciprocal) and then made exact with double compares; an estimate
+    // beyond the n adds still wanted needs no correction.
     const double td = (double)t, incd = (double)inc;
     const double top = __longlong_as_double((long long)(e1 - 127 + 1 + 1023) << 52); // 2^(e+1)
-    long long kb = (long long)floor((top - td) / incd); // adds whose RESULT stays below 2^(e+1)
-    while (kb > 0 && td + (double)kb * incd >= top)
-      --kb;
-    while (td + (double)(kb + 1) * incd < top)
-      ++kb;
-    long long ku = (long long)floor(((double)tUpper - td) / incd) + 1; // adds the loop executes before t > tUpper
-    while (ku > 1 && td + (double)(ku - 1) * incd > (double)tUpper)
-      --ku;
-    while (td + (double)ku * incd <= (double)tUpper)
-      ++ku;
+    const float rinc = __frcp_rn(inc);
+    const float lim = (float)n + 2.f;
+    // kb: adds whose RESULT stays below 2^(e+1)
+    long long kb = (long long)fminf(floorf(__fmul_rn((float)(top - td), rinc)), lim);
+    if (kb <= (long long)n + 1) {
+      while (kb > 0 && td + (double)kb * incd >= top)
+        --kb;
+      while (td + (double)(kb + 1) * incd < top)
+        ++kb;
+    }
+    // ku: adds the loop executes before t > tUpper
+    long long ku = (long long)fminf(floorf(__fmul_rn((float)((double)tUpper - td), rinc)) + 1.f, lim);
+    if (ku <= (long long)n + 1) {
+      while (ku > 1 && td + (double)(ku - 1) * incd > (double)tUpper)
+        --ku;
+      while (td + (double)ku * incd <= (double)tUpper)
+        ++ku;
+    }
     long long k = kb < ku ? kb : ku;
     if (k > (long long)n)
       k = n;
@@ -217,6 +227,9 @@ __device__ __forceinline__ void marchSegment(const VolumeDev &v, const float4 *_
   else
     dvox = f3(dir.x * f.invSpacing.x * (float)f.dims.x, dir.y * f.invSpacing.y * (float)f.dims.y,
         dir.z * f.invSpacing.z * (float)f.dims.z);
+  const float3 invDvox = f3(dvox.x != 0.f ? 1.f / dvox.x : 0.f, dvox.y != 0.f ? 1.f / dvox.y : 0.f,
+      dvox.z != 0.f ? 1.f / dvox.z : 0.f);
+  const float invStep = 1.f / stepSize;
   NvdbCache nvCache;
   if (KIND >= FIELD_NANOVDB)
     nvCache.reset();
@@ -245,28 +258,31 @@ __device__ __forceinline__ void marchSegment(const VolumeDev &v, const float4 *_
       const int cx = min(max((int)floorf(xb.x), 0), f.dims.x - 1) >> 4;
       const int cy = min(max((int)floorf(xb.y), 0), f.dims.y - 1) >> 4;
       const int cz = min(max((int)floorf(xb.z), 0), f.dims.z - 1) >> 4;
-      // two-level test: a 64^3-voxel block of macrocells first (long empty runs in one hop), then the
-      // 16^3 macrocell; both loads are issued together
+      // three-level test: the 256^3- and 64^3-voxel blocks first (long empty runs in one hop), then the 16^3
+      // macrocell; the loads are issued together
       const float majorant = __ldg(&v.maxOpacities[(size_t)cz * f.gridDims.x * f.gridDims.y
           + (size_t)cy * f.gridDims.x + cx]);
       const float coarse = __ldg(&v.maxOpacitiesCoarse[(size_t)(cz >> 2) * v.coarseDims.x * v.coarseDims.y
           + (size_t)(cy >> 2) * v.coarseDims.x + (cx >> 2)]);
+      const float coarse2 = __ldg(&v.maxOpacitiesCoarse2[(size_t)(cz >> 4) * v.coarse2Dims.x * v.coarse2Dims.y
+          + (size_t)(cy >> 4) * v.coarse2Dims.x + (cx >> 4)]);
       if (majorant <= 0.f) {
         // distance (in t) to the nearest face of the empty region along the ray
-        const int sh = coarse <= 0.f ? 6 : 4;
-        const int rx = coarse <= 0.f ? (cx >> 2) : cx, ry = coarse <= 0.f ? (cy >> 2) : cy,
-                  rz = coarse <= 0.f ? (cz >> 2) : cz;
+        const int lvl = coarse2 <= 0.f ? 4 : (coarse <= 0.f ? 2 : 0); // cell-index shift of the empty region
+        const int sh = 4 + lvl;
+        const int rx = cx >> lvl, ry = cy >> lvl, rz = cz >> lvl;
         const float bx = dvox.x > 0.f ? (float)((rx + 1) << sh) : (float)(rx << sh);
         const float by = dvox.y > 0.f ? (float)((ry + 1) << sh) : (float)(ry << sh);
         const float bz = dvox.z > 0.f ? (float)((rz + 1) << sh) : (float)(rz << sh);
-        const float ex = dvox.x != 0.f ? (bx - xb.x) / dvox.x : FLT_MAX;
-        const float ey = dvox.y != 0.f ? (by - xb.y) / dvox.y : FLT_MAX;
-        const float ez = dvox.z != 0.f ? (bz - xb.z) / dvox.z : FLT_MAX;
+        // (reciprocals hoisted out of the loop: dt only sizes the hop, one whole step of margin absorbs its rounding)
+        const float ex = dvox.x != 0.f ? (bx - xb.x) * invDvox.x : FLT_MAX;
+        const float ey = dvox.y != 0.f ? (by - xb.y) * invDvox.y : FLT_MAX;
+        const float ez = dvox.z != 0.f ? (bz - xb.z) * invDvox.z : FLT_MAX;
         const float dt = fminf(fminf(ex, ey), ez);
         // Whole steps that stay strictly inside the cell (one step of safety margin); at least THIS lattice
         // point is skippable on its own: the cell containing its lower tap has majorant 0, so its fetch
         // would classify to alpha == 0 exactly and contribute nothing.
-        const int n = max((int)floorf(fminf(dt / stepSize, 1.0e6f)) - 1, 1);
+        const int n = max((int)floorf(fminf(dt * invStep, 1.0e6f)) - 1, 1);
         int taken;
         t = latticeAdvance(t, stepSize, n, tUpper, taken);
         if (STATS && g == 0)
