@@ -245,10 +245,14 @@ __device__ __forceinline__ void marchSegment(const VolumeDev &v, const float4 *_
     else if (dvox.z < 0.f)
       tEnter = t + ((float)f.zOwnEnd - z0) / dvox.z;
     tEnter -= 2.f * stepSize;
-    while (t < tEnter && t <= tUpper) {
-      t = __fadd_rn(t, stepSize);
+    // `while (t < tEnter && t <= tUpper) t += step`, in closed form (t < x  <=>  t <= the float just below x)
+    if (t < tEnter && t <= tUpper && tEnter == tEnter) {
+      const float below = __int_as_float(__float_as_int(tEnter) + (tEnter > 0.f ? -1 : (tEnter < 0.f ? 1 : 0)));
+      const float bound = fminf(tUpper, tEnter == 0.f ? -FLT_MIN : below);
+      int taken;
+      t = latticeAdvance(t, stepSize, 0x7fffffff, bound, taken);
       if (STATS && g == 0)
-        stats.skipped++;
+        stats.skipped += (unsigned long long)taken;
     }
   }
 
