@@ -136,6 +136,15 @@ typedef struct DvrFrameBuffers
   void *outColorMirror;
 } DvrFrameBuffers;
 
+/* Empty-space skipping never changes a pixel (skipped lattice points classify to alpha == 0 exactly), so the
+ * mode is purely a speed choice. */
+typedef enum DvrSkipMode
+{
+  DVR_SKIP_OFF = 0,
+  DVR_SKIP_ON = 1,
+  DVR_SKIP_AUTO = 2 /* on when >= 1/64 of a volume's macrocells are empty under its transfer function */
+} DvrSkipMode;
+
 /* FramebufferGPUData + the RendererGPUData members this path reads
  * (gpu/gpu_objects.h:609-655, Renderer.cpp:191-207) */
 typedef struct DvrFrameParams
@@ -151,7 +160,7 @@ typedef struct DvrFrameParams
   /* sort-first: only pixels with y in [rowBegin,rowEnd) and tiles owned by this rank are rendered */
   uint32_t tileRank, tileRanks; /* 0,1 = everything */
   /* options of the new implementation (all parity-neutral) */
-  int32_t useMacrocellSkipping; /* skip fully transparent macrocells on the same sample lattice */
+  int32_t useMacrocellSkipping; /* DvrSkipMode: skip fully transparent macrocells on the same sample lattice */
   int32_t tileBand;             /* sort-first: consecutive tile rows per band owned by one rank (0/1 = finest) */
   /* DVR_INTEGRATOR_DPT only (DiffusePathTracer.cpp:44-54, Renderer.cpp:159-161) */
   int32_t maxDepth;             /* "maxDepth", clamped to [1,256]; 0 => 5 */

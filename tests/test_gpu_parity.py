@@ -307,3 +307,29 @@ def test_closed_form_lattice_advance_is_bit_identical_to_the_add_loop():
     """4 M pseudo-random (t, step, n, tUpper) sets, incl. power-of-two steps (round-to-even ties), tiny and huge t."""
     for seed in (1, 77, 2024, 999983):
         assert capi.selftest_lattice_advance(1 << 20, seed) == 0
+
+
+def test_automatic_skipping_mode_picks_by_emptiness_and_never_changes_pixels():
+    dense = H.default_scene(48, 96, 64, rate=0.5)  # Marschner-Lobb + default map: no empty macrocell
+    sparse = H.default_scene(64, 96, 64, rate=0.5)
+    vox = np.zeros((64, 64, 64), np.float32)
+    vox[20:44, 20:44, 20:44] = scenes.blobs_np(24)  # a blob in the middle of empty space
+    sparse.volumes[0].voxels = vox
+    sparse.volumes[0].tf = capi.tf_discretize(color=scenes.sparse_colormap(256, 0.2))
+    for scene, expect_skips in ((dense, False), (sparse, True)):
+        cs = H.CudaScene(scene)
+        try:
+            p = H._params(scene, 0, -1, skip="auto")
+            assert p.useMacrocellSkipping == capi.DVR_SKIP_AUTO
+            import torch
+            st = torch.zeros(4, dtype=torch.int64, device="cuda")
+            capi.render_instrumented(p, scene.camera, cs.instances, cs.n, cs.fb, st.data_ptr())
+            torch.cuda.synchronize()
+            auto = cs.download()
+            skipped = int(st[1].item())
+        finally:
+            cs.destroy()
+        assert (skipped > 0) == expect_skips
+        ref = H.render_cuda(scene, skip=False)
+        for k in ref:
+            assert np.array_equal(auto[k], ref[k]), k

@@ -23,6 +23,7 @@ DVR_FILTER_LINEAR, DVR_FILTER_NEAREST = 0, 1
 DVR_FORMAT_FLOAT32_VEC4, DVR_FORMAT_UFIXED8_VEC4, DVR_FORMAT_UFIXED8_RGBA_SRGB = 0, 1, 2
 DVR_CAMERA_PERSPECTIVE, DVR_CAMERA_ORTHOGRAPHIC = 0, 1
 DVR_INTEGRATOR_RAYCAST, DVR_INTEGRATOR_DEFAULT, DVR_INTEGRATOR_DPT = 0, 1, 2
+DVR_SKIP_OFF, DVR_SKIP_ON, DVR_SKIP_AUTO = 0, 1, 2
 
 # every symbol include/dvr_b200.h declares (tests check the library exports all of them)
 EXPORTED_SYMBOLS = [
@@ -327,7 +328,7 @@ def frame_params(width, height, fmt=DVR_FORMAT_UFIXED8_RGBA_SRGB, integrator=DVR
     p.inverseVolumeSamplingRate = float(np.float32(1.0) / np.float32(volume_sampling_rate))
     p.background = _f4(*background)
     p.tileRank, p.tileRanks = int(tile_rank), int(tile_ranks)
-    p.useMacrocellSkipping = 1 if skip else 0
+    p.useMacrocellSkipping = DVR_SKIP_AUTO if skip == "auto" else (DVR_SKIP_ON if skip else DVR_SKIP_OFF)
     p.tileBand = int(tile_band)
     p.maxDepth, p.ambientRadiance, p.occlusionDistance = int(max_depth), float(ambient_radiance), float(occlusion_distance)
     p.dptReferenceGrid = 1 if dpt_reference_grid else 0

@@ -102,6 +102,7 @@ struct DvrVolume
   float *maxOpacities = nullptr;
   float *maxOpacitiesCoarse = nullptr;
   int3 coarseDims{0, 0, 0};
+  float emptyFraction = 0.f;            // share of macrocells with majorant 0 under the current TF
   float *maxOpacitiesCoarse2 = nullptr; // 256^3-voxel blocks
   int3 coarse2Dims{0, 0, 0};
   float *ddaMaxOpacities = nullptr; // delta-tracking grid (built on first use by the dpt integrator)
@@ -126,6 +127,10 @@ static float3 hcross(float3 a, float3 b)
 static float3 hscale(float3 a, float s) { return make_float3(a.x * s, a.y * s, a.z * s); }
 static float3 hsub(float3 a, float3 b) { return make_float3(a.x - b.x, a.y - b.y, a.z - b.z); }
 static void st3(float *d, float3 v) { d[0] = v.x; d[1] = v.y; d[2] = v.z; }
+
+// DVR_SKIP_AUTO: use the skipping kernel when at least this share of the macrocells is empty (on fully dense
+// data the test per lattice point costs ~6 %: C2 1068 vs 1007 frames/s)
+static constexpr float kSkipAutoThreshold = 1.f / 64.f;
 
 extern "C" {
 
@@ -792,7 +797,19 @@ int dvr_volume_update(DvrVolume *v, const float *tfRgba, const float valueRange[
   const int rc2 = launchMajorantsCoarse(v->maxOpacities, v->field->dev.gridDims, v->maxOpacitiesCoarse, v->coarseDims, s);
   if (rc2 != DVR_OK)
     return rc2;
-  return launchMajorantsCoarse(v->maxOpacitiesCoarse, v->coarseDims, v->maxOpacitiesCoarse2, v->coarse2Dims, s);
+  const int rc3 = launchMajorantsCoarse(v->maxOpacitiesCoarse, v->coarseDims, v->maxOpacitiesCoarse2, v->coarse2Dims, s);
+  if (rc3 != DVR_OK)
+    return rc3;
+  // how much of the volume skipping could exploit (drives DVR_SKIP_AUTO)
+  unsigned long long *dCount = nullptr, hCount = 0;
+  DVR_CUDA(cudaMallocAsync(&dCount, sizeof(unsigned long long), s));
+  DVR_CUDA(cudaMemsetAsync(dCount, 0, sizeof(unsigned long long), s));
+  const int rc4 = launchCountEmpty(v->maxOpacities, v->field->nCells, dCount, s);
+  DVR_CUDA(cudaMemcpyAsync(&hCount, dCount, sizeof(hCount), cudaMemcpyDeviceToHost, s));
+  DVR_CUDA(cudaFreeAsync(dCount, s));
+  DVR_CUDA(cudaStreamSynchronize(s));
+  v->emptyFraction = v->field->nCells ? (float)((double)hCount / (double)v->field->nCells) : 0.f;
+  return rc4;
 }
 
 int dvr_volume_create(const DvrField *field, const float *tfRgba, const float valueRange[2], float unitDistance,
@@ -1011,7 +1028,10 @@ static int renderImpl(const DvrFrameParams *p, const DvrCamera *camera, const Dv
   L.fb.normal = b->normal;
   L.nInst = (int)nInstances;
 
-  bool skip = p->useMacrocellSkipping != 0;
+  bool skip = p->useMacrocellSkipping == DVR_SKIP_ON;
+  if (p->useMacrocellSkipping == DVR_SKIP_AUTO) // images are identical either way: pick the faster kernel
+    for (uint32_t i = 0; i < nInstances; ++i)
+      skip = skip || instances[i].volume->emptyFraction >= kSkipAutoThreshold;
   if (nInstances <= (uint32_t)kMaxInlineInstances) {
     for (uint32_t i = 0; i < nInstances; ++i)
       fillInstance(instances[i], L.inl[i]);
@@ -1138,7 +1158,8 @@ static int renderPartialImpl(const DvrFrameParams *p, const DvrCamera *camera, c
   fillInstance(*instance, L.inst);
   L.partialRgba = (float4 *)partialRgba;
   L.partialDepth = partialDepth;
-  L.skip = p->useMacrocellSkipping;
+  L.skip = p->useMacrocellSkipping == DVR_SKIP_ON
+      || (p->useMacrocellSkipping == DVR_SKIP_AUTO && instance->volume->emptyFraction >= kSkipAutoThreshold);
   {
     const int rcs = fillSync(sync, L.sync);
     if (rcs != DVR_OK)

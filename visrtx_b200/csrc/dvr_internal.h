@@ -130,6 +130,7 @@ int launchMacrocellBuildNvdb(const FieldDev &f, float2 *ranges, cudaStream_t s);
 // value ranges on the delta-tracking grid: gridDims cells dividing `spanVoxels` voxel units evenly per axis
 int launchDdaRangeBuild(const FieldDev &f, cudaTextureObject_t pointTex, int3 gridDims, float3 cellWidthVoxels,
     float2 *ranges, cudaStream_t s);
+int launchCountEmpty(const float *maxOpacities, size_t n, unsigned long long *out, cudaStream_t s);
 int launchSelftestLattice(uint32_t count, unsigned long long seed, unsigned int *mismatches, cudaStream_t s);
 int launchReferenceGridBuild(const FieldDev &f, int3 gridDims, const float4 *tf, float2 *ranges, float *maxOpacities,
     cudaStream_t s);

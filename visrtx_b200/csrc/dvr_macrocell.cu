@@ -410,6 +410,32 @@ __global__ void dvrPopcountKernel(const unsigned int *__restrict__ bitmap, size_
     atomicAdd(out, c);
 }
 
+__global__ void dvrCountEmptyKernel(const float *__restrict__ maxOpacities, size_t n, unsigned long long *out)
+{
+  unsigned long long c = 0;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+    c += maxOpacities[i] <= 0.f ? 1ull : 0ull;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1)
+    c += __shfl_xor_sync(0xffffffffu, c, o);
+  if ((threadIdx.x & 31) == 0 && c)
+    atomicAdd(out, c);
+}
+
+// number of macrocells whose majorant is 0 (what skipping can exploit), counted on the device
+int launchCountEmpty(const float *maxOpacities, size_t n, unsigned long long *out, cudaStream_t s)
+{
+  if (n == 0)
+    return DVR_OK;
+  unsigned blocks = (unsigned)((n + 255) / 256);
+  if (blocks > 1184)
+    blocks = 1184;
+  dvrCountEmptyKernel<<<blocks, 256, 0, s>>>(maxOpacities, n, out);
+  DVR_CUDA(cudaGetLastError());
+  countLaunch();
+  return DVR_OK;
+}
+
 int launchPopcount(const unsigned int *bitmap, size_t nWords, unsigned long long *out, cudaStream_t s)
 {
   if (nWords == 0)

@@ -246,7 +246,7 @@ void Frame::renderFrame()
   std::memcpy(p.background, m_renderer->background, sizeof(p.background));
   p.tileRank = m_renderer->tileRank;
   p.tileRanks = m_renderer->tileRanks;
-  p.useMacrocellSkipping = m_renderer->macrocellSkipping ? 1 : 0;
+  p.useMacrocellSkipping = m_renderer->macrocellSkipping;
   p.maxDepth = m_renderer->maxDepth;
   p.dptReferenceGrid = m_renderer->dptReferenceGrid ? 1 : 0;
   p.ambientRadiance = m_renderer->ambientRadiance;

@@ -795,7 +795,10 @@ void Renderer::commitParameters()
   checkerboard = getParam<int32_t>("checkerboarding", ANARI_BOOL, 0) != 0;
   sampleLimit = getParam<int>("sampleLimit", ANARI_INT32, 128);
   volumeSamplingRate = std::min(std::max(getParam<float>("volumeSamplingRate", ANARI_FLOAT32, 0.125f), 1e-3f), 10.f);
-  macrocellSkipping = getParam<int32_t>("macrocellSkipping", ANARI_BOOL, 1) != 0; // extension; parity-neutral
+  { // extension; image-neutral.  Unset: the device decides per volume (DVR_SKIP_AUTO)
+    const int32_t ms = getParam<int32_t>("macrocellSkipping", ANARI_BOOL, -1);
+    macrocellSkipping = ms < 0 ? DVR_SKIP_AUTO : (ms ? DVR_SKIP_ON : DVR_SKIP_OFF);
+  }
   tileRank = (uint32_t)std::max(getParam<int>("sortFirstRank", ANARI_INT32, 0), 0);
   tileRanks = (uint32_t)std::max(getParam<int>("sortFirstRanks", ANARI_INT32, 1), 1);
   if (checkerboard)

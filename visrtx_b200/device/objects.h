@@ -282,7 +282,7 @@ struct Renderer : Object
   bool dptReferenceGrid = false;   // dpt only (extension)
   float ambientRadiance = 0.f;     // dpt only (the marching renderers have no lighting term for volumes)
   float occlusionDistance = 1e20f; // dpt only
-  bool macrocellSkipping = true;
+  int macrocellSkipping = DVR_SKIP_AUTO;
   // sort-first extension: this device renders only tile rows (row % tileRanks == tileRank)
   uint32_t tileRank = 0, tileRanks = 1;
 
