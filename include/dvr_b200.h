@@ -84,7 +84,9 @@ typedef enum DvrIntegrator
   /* `dpt` / `diffuse_pathtracer`: delta (Woodcock) tracking through the majorant grid, isotropic
    * scattering, Russian roulette, ambient light (renderer/DiffusePathTracer_ptx.cu:82-215,
    * gpu/volumeIntegration.h:167-296,352-389, gpu/dda.h:43-121) */
-  DVR_INTEGRATOR_DPT = 2
+  DVR_INTEGRATOR_DPT = 2,
+  /* `test`: no scene access — colour = primary ray direction, depth 1 (renderer/Test_ptx.cu:52-69) */
+  DVR_INTEGRATOR_TEST = 3
 } DvrIntegrator;
 
 /* ---- opaque device objects ------------------------------------------------------ */

@@ -953,6 +953,13 @@ int oracle_render(const DvrFrameParams *params, const DvrCamera *camera, const O
         const float sy = (centered ? (float)y : (float)y + r[1]) * invH;
         V3 org, dir;
         cameraCreateRay(cam, sx, sy, r[2], r[3], org, dir);
+        if (P.integrator == DVR_INTEGRATOR_TEST) { // Test_ptx.cu:52-69
+          const float c4[4] = {dir.x, dir.y, dir.z, 1.f};
+          const float alb[3] = {dir.x, dir.y, dir.z};
+          const float nrm[3] = {-dir.x, -dir.y, -dir.z};
+          accumResults(F, (uint32_t)x, (uint32_t)y, c4, 1.f, alb, nrm, ~0u, ~0u, ~0u, 0);
+          break;
+        }
         if (dpt) { // DiffusePathTracer_ptx.cu:96-215: depth / ids keep their initial values (tmax, ~0u)
           const float nrm[3] = {dir.x, dir.y, dir.z};
           const V3 c = dptTracePath(vols, grids, org, dir, P, rng, path, samples);

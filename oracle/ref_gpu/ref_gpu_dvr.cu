@@ -201,6 +201,16 @@ __global__ void refgpu_raygen_dpt()
   }
 }
 
+// raygen of the `test` renderer, renderer/Test_ptx.cu:52-69 verbatim
+__global__ void refgpu_raygen_test()
+{
+  auto ss = createScreenSample(frameData);
+  if (pixelOutOfFrame(ss.pixel, frameData.fb))
+    return;
+  auto ray = makePrimaryRay(ss);
+  accumResults(frameData.fb, ss.pixel, vec4(ray.dir, 1.f), 1.f, ray.dir, -ray.dir, ~0u, ~0u, ~0u);
+}
+
 template <typename T>
 __global__ void refgpu_fill(T *p, size_t n, T v)
 {
@@ -577,7 +587,9 @@ int refgpu_render(const DvrFrameParams *p, const DvrCamera *c, RefScene *scene, 
   const uint32_t lw = p->checkerboardID >= 0 ? (p->width + 1) / 2 : p->width;
   const uint32_t lh = p->checkerboardID >= 0 ? (p->height + 1) / 2 : p->height;
   dim3 block(16, 8), grid((lw + 15) / 16, (lh + 7) / 8);
-  if (p->integrator == DVR_INTEGRATOR_DPT) {
+  if (p->integrator == DVR_INTEGRATOR_TEST)
+    refgpu_raygen_test<<<grid, block, 0, s>>>();
+  else if (p->integrator == DVR_INTEGRATOR_DPT) {
     for (int i = 0; i < scene->n; ++i)
       if (!scene->hasGrid) {
         snprintf(g_err, sizeof(g_err), "dpt needs refgpu_volume_set_grid on every volume");

@@ -110,3 +110,34 @@ def test_transparent_and_opaque_transfer_functions():
     solid = np.ones((256, 4), np.float32)
     _compare(_scene(vox, tf=solid, unit_distance=1e-3), name="alpha 1, tiny unitDistance")  # ERT after one sample
     _compare(_scene(vox, tf=solid, unit_distance=1e6), name="alpha 1, huge unitDistance")  # pow(0, ~0)
+
+
+def test_the_test_renderer_paints_ray_directions():
+    """`test` renderer (renderer/Test_ptx.cu): colour = jittered primary ray direction, depth 1, no scene access."""
+    vox = scenes.blobs_np(16)
+    s = _scene(vox, integrator=capi.DVR_INTEGRATOR_TEST, fmt=capi.DVR_FORMAT_FLOAT32_VEC4,
+               channels=("depth", "objId", "albedo", "normal"))
+    got = H.render_cuda(s, frames=2)
+    want = H.render_oracle(s, frames=2)
+    np.testing.assert_allclose(got["color"], want["color"], atol=2e-6)
+    np.testing.assert_allclose(got["normal"], want["normal"], atol=4e-6)
+    assert np.all(got["depth"] == 1.0) and np.all(got["objId"] == 0xFFFFFFFF)
+    acc = got["accum"][:, :3].reshape(s.height, s.width, 3)[s.height // 2, s.width // 2] / 2  # two frames
+    d = np.asarray(s.camera.dir)
+    assert np.abs(acc - d / (1 + max(0.0, d.max()))).max() < 0.03  # the tonemapped direction of the centre ray
+    if ob.have_ref_gpu():
+        ref = H.render_refgpu(s, frames=2)
+        for k in ("depth", "objId"):
+            assert np.array_equal(got[k], ref[k]), k
+        for k in ("color", "accum", "albedo", "normal"):  # same ray set-up as every other renderer: last-bit agreement
+            np.testing.assert_allclose(got[k], ref[k], atol=1e-6, err_msg=k)
+            assert (got[k] == ref[k]).mean() > 0.9, k
+    # through ANARI
+    from test_gpu_anari import AnariScene
+    from visrtx_b200 import anari as A
+    a = AnariScene(16, 64, 48, "test", 0.5, color_type=A.FLOAT32_VEC4, channels=("depth",))
+    a.render()
+    color, w, h, _ = a.d.map_frame(a.frame, "channel.color")
+    assert not [m for m in a.d.messages if m[0] <= A.SEVERITY_WARNING], a.d.messages
+    assert np.all(np.asarray(color).reshape(-1, 4)[:, 3] == 1.0)
+    a.close()

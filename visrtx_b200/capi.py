@@ -22,7 +22,7 @@ DVR_FLOAT32, DVR_UFIXED8, DVR_FIXED8, DVR_UFIXED16, DVR_FIXED16, DVR_FLOAT64, DV
 DVR_FILTER_LINEAR, DVR_FILTER_NEAREST = 0, 1
 DVR_FORMAT_FLOAT32_VEC4, DVR_FORMAT_UFIXED8_VEC4, DVR_FORMAT_UFIXED8_RGBA_SRGB = 0, 1, 2
 DVR_CAMERA_PERSPECTIVE, DVR_CAMERA_ORTHOGRAPHIC = 0, 1
-DVR_INTEGRATOR_RAYCAST, DVR_INTEGRATOR_DEFAULT, DVR_INTEGRATOR_DPT = 0, 1, 2
+DVR_INTEGRATOR_RAYCAST, DVR_INTEGRATOR_DEFAULT, DVR_INTEGRATOR_DPT, DVR_INTEGRATOR_TEST = 0, 1, 2, 3
 DVR_SKIP_OFF, DVR_SKIP_ON, DVR_SKIP_AUTO = 0, 1, 2
 
 # every symbol include/dvr_b200.h declares (tests check the library exports all of them)

@@ -971,7 +971,7 @@ static int renderImpl(const DvrFrameParams *p, const DvrCamera *camera, const Dv
     return DVR_ERR_INVALID_ARGUMENT;
   }
   if (p->width == 0 || p->height == 0 || p->numIterations < 1 || p->format < 0 || p->format > 2
-      || p->checkerboardID > 3 || p->integrator < 0 || p->integrator > DVR_INTEGRATOR_DPT) {
+      || p->checkerboardID > 3 || p->integrator < 0 || p->integrator > DVR_INTEGRATOR_TEST) {
     setError("dvr_render: invalid frame parameters");
     return DVR_ERR_INVALID_ARGUMENT;
   }

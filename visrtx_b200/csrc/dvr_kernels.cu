@@ -290,6 +290,11 @@ __global__ void __launch_bounds__(kBlockThreads, (KIND >= FIELD_NANOVDB ? DVR_OC
       float3 org, dir;
       cameraCreateRay(P.cam, sx, sy, r.z, r.w, org, dir);
 
+      if (DPT && P.integrator == DVR_INTEGRATOR_TEST) { // Test_ptx.cu:52-69: one sample, no scene access
+        accumResults(actx, px, py, make_float4(dir.x, dir.y, dir.z, 1.f), 1.f, dir, f3(-dir.x, -dir.y, -dir.z), ~0u,
+            ~0u, ~0u, 0, initFrame);
+        break;
+      }
       if (DPT) {
         // DiffusePathTracer_ptx.cu:96-215: colour = Lw * ambient (or the background when nothing scattered),
         // alpha 1; depth / ids are never set by the reference's loop (its `depth == 0` test runs after the
@@ -391,7 +396,8 @@ static int launchFrameK(const FrameLaunch &p, cudaStream_t s)
 
 int launchFrame(const FrameLaunch &p, bool skip, bool stats, cudaStream_t s)
 {
-  if (p.integrator == DVR_INTEGRATOR_DPT) { // delta tracking: no fixed-step lattice, so no SKIP/STATS variants
+  if (p.integrator == DVR_INTEGRATOR_DPT || p.integrator == DVR_INTEGRATOR_TEST) {
+    // delta tracking has no fixed-step lattice (no SKIP/STATS variants); the test renderer shares the instantiation
     if (p.nInst != 1)
       return launchFrameT<false, false, false, -1, true>(p, s);
     if (p.inl[0].v.f.kind == FIELD_NANOVDB)

@@ -625,7 +625,7 @@ ANARIObject make(ANARIDevice d, A &&...a)
 const char *kCameraTypes[] = {"perspective", "orthographic", nullptr};
 const char *kFieldTypes[] = {"structuredRegular", "nanovdb", nullptr};
 const char *kVolumeTypes[] = {"transferFunction1D", "scivis", nullptr};
-const char *kRendererTypes[] = {"default", "raycast", "ao", "directLight", "dpt", nullptr};
+const char *kRendererTypes[] = {"default", "raycast", "ao", "directLight", "dpt", "test", nullptr};
 const char *kInstanceTypes[] = {"transform", nullptr};
 const char *kNone[] = {nullptr};
 const char *kDeviceTypes[] = {"default", nullptr};

@@ -779,7 +779,7 @@ Renderer::Renderer(Device *d, const std::string &st) : Object(d, ANARI_RENDERER,
     s = ov;
   subtype = s;
   m_known = s == "raycast" || s == "default" || s == "directLight" || s == "ao" || s == "dpt"
-      || s == "diffuse_pathtracer";
+      || s == "diffuse_pathtracer" || s == "test";
   d->enqueueCommit(this);
 }
 
@@ -808,6 +808,8 @@ void Renderer::commitParameters()
     integrator = DVR_INTEGRATOR_RAYCAST;
     sampleLimit = 1; // single-shot renderer
   }
+  if (subtype == "test") // Test_ptx.cu: colour = primary ray direction
+    integrator = DVR_INTEGRATOR_TEST;
   if (subtype == "dpt" || subtype == "diffuse_pathtracer") { // DiffusePathTracer.cpp:41-53
     integrator = DVR_INTEGRATOR_DPT;
     maxDepth = std::min(std::max(getParam<int>("maxDepth", ANARI_INT32, 5), 1), 256);
