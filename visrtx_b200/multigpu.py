@@ -279,6 +279,7 @@ class SortLast:
                                              color_mirror=self.host_frame.dev_ptr) if self.host_frame else None
         self.fb = self._fb_mirror or self._fb_plain
         self.frame_parity = 0
+        self._hot = None
 
     def params(self, frame_id: int):
         return self.capi.frame_params(self.W, self.H, self.fmt, self.integrator, frame_id, -1, 1, self.rate,
@@ -304,16 +305,39 @@ class SortLast:
         me, W = self.rank, self.world
         my_flags = self.flag_ptrs[me]
         err = my_flags + 32 * 4
+        if self._hot is None:  # per-frame host work is pointer/struct reuse only: everything below is built once
+            import ctypes as C
+            L = capi.lib
+            self._hot = {
+                "p": self.params(0),
+                "sync_p": capi.peer_sync(signal_ptrs=[self.flag_ptrs[r] + me * 4 for r in range(W)], signal_value=0),
+                "sync_c": capi.peer_sync(signal_ptrs=[self.flag_ptrs[r] + (16 + me) * 4 for r in range(W)], signal_value=0,
+                                         wait_ptr=my_flags, n_wait=W, wait_value=0, error_flag=err),
+                "rg": [(C.c_void_p * W)(*self.rgba_ptrs[k]) for k in range(2)],
+                "dp": [(C.c_void_p * W)(*self.depth_ptrs[k]) for k in range(2)],
+                "mine_rg": [C.c_void_p(self.rgba_ptrs[k][me]) for k in range(2)],
+                "mine_dp": [C.c_void_p(self.depth_ptrs[k][me]) for k in range(2)],
+                "resolved": C.c_void_p(my_flags + 16 * 4), "err": C.c_void_p(err), "W": C.c_uint32(W),
+                "obj": C.c_uint32(self.obj_id), "inst": C.c_uint32(self.inst_id),
+                "lo": C.c_size_t(lo), "hi": C.c_size_t(hi), "C": C, "L": L,
+            }
+        h = self._hot
+        C, L = h["C"], h["L"]
+        p, sync_p, sync_c = h["p"], h["sync_p"], h["sync_c"]
+        p.frameID = frame_id
+        sync_p.signalValue = sync_c.signalValue = sync_c.waitValue = seq & 0xFFFFFFFF
+        st = C.c_void_p(stream)
+        pr, cr, fbr = C.byref(p), C.byref(camera), C.byref(self.fb)
+        rc = 0
         if seq > 2:  # partial buffer b was last read by the composites of frame seq-2
-            capi.wait_flags(my_flags + 16 * 4, W, seq - 2, err, stream)
-        sync_p = capi.peer_sync(signal_ptrs=[self.flag_ptrs[r] + me * 4 for r in range(W)], signal_value=seq)
-        capi.render_partial_sync(p, camera, self.instance, self.rgba_ptrs[b][me], self.depth_ptrs[b][me], sync_p, stream)
-        sync_c = capi.peer_sync(signal_ptrs=[self.flag_ptrs[r] + (16 + me) * 4 for r in range(W)], signal_value=seq,
-                                wait_ptr=my_flags, n_wait=W, wait_value=seq, error_flag=err)
-        capi.composite_resolve_peers_sync(p, camera, self.instance, self.rgba_ptrs[b], self.depth_ptrs[b], self.obj_id,
-                                          self.inst_id, self.fb, lo, hi, sync_c, stream)
+            rc |= L.dvr_wait_flags(h["resolved"], h["W"], C.c_uint32((seq - 2) & 0xFFFFFFFF), h["err"], st)
+        rc |= L.dvr_render_partial_sync(pr, cr, self.instance, h["mine_rg"][b], h["mine_dp"][b], C.byref(sync_p), st)
+        rc |= L.dvr_composite_resolve_peers_sync(pr, cr, self.instance, h["rg"][b], h["dp"][b], h["W"], h["obj"], h["inst"],
+                                                 fbr, h["lo"], h["hi"], C.byref(sync_c), st)
         if me == 0 and wait_display:  # the display rank's stream continues once every strip has landed
-            capi.wait_flags(my_flags + 16 * 4, W, seq, err, stream)
+            rc |= L.dvr_wait_flags(h["resolved"], h["W"], C.c_uint32(seq & 0xFFFFFFFF), h["err"], st)
+        if rc != 0:
+            raise RuntimeError(f"sort-last frame {seq}: {capi.last_error()}")
 
     def check_errors(self):
         """True when a bounded spin gave up (a producer never signalled)."""
