@@ -169,7 +169,11 @@ typedef struct DvrFrameParams
   float ambientRadiance;        /* "ambientRadiance" (dpt default 1) */
   float occlusionDistance;      /* "ambientOcclusionDistance"; 0 => 1e20 */
   int32_t dptReferenceGrid;     /* DPT only: != 0 walks the grid built the reference's way (see dvr_volume_dda_majorants) */
-  int32_t _reserved[2];
+  /* dvr_render_partial* only: != 0 renders (and WRITES) only the tiles inside the screen-space rectangle of the
+   * volume's bounds; pixels outside keep whatever the partial buffers held.  For consumers that cull by themselves
+   * — dvr_composite_resolve_peers* regenerates each primary ray and never reads a pixel whose ray misses. */
+  int32_t partialCullToBounds;
+  int32_t _reserved[1];
 } DvrFrameParams;
 
 /* per-launch counters, filled only by dvr_render_instrumented (device memory, 64-bit each) */

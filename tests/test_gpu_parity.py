@@ -333,3 +333,51 @@ def test_automatic_skipping_mode_picks_by_emptiness_and_never_changes_pixels():
         ref = H.render_cuda(scene, skip=False)
         for k in ref:
             assert np.array_equal(auto[k], ref[k]), k
+
+
+def test_partial_march_confined_to_the_screen_rectangle_of_the_bounds():
+    """partialCullToBounds: tiles outside the projected box are neither marched nor written.  Every pixel whose ray
+    hits the volume must still be produced (conservative rectangle): compared with the full-frame partial on
+    cameras outside / far / cropped / orthographic / inside (inside and thin-lens fall back to the whole frame)."""
+    import torch
+    n = 32
+    vox = scenes.blobs_np(n)
+    W, Hh = 200, 144
+    cams = []
+    for az, el, dist in ((30, 20, 2.0), (200, -35, 1.2), (95, 5, 3.5), (10, 80, 1.6)):
+        v = H.default_scene(n, W, Hh, field="blobs").volumes[0]
+        lo, hi = v.bounds()
+        pose = scenes.orbit_camera(lo, hi, W, Hh, az_deg=az, el_deg=el, dist_scale=dist)
+        cams.append(capi.camera_perspective(pose.position, pose.direction, pose.up, pose.fovy, pose.aspect))
+        cams.append(capi.camera_perspective(pose.position, pose.direction, pose.up, pose.fovy, pose.aspect,
+                                            region=(0.2, 0.1, 0.9, 0.75)))
+    cams.append(capi.camera_orthographic((0.3, 0.2, 5.0), (0.0, 0.0, -1.0), (0.0, 1.0, 0.0), 4.0, W / Hh))
+    cams.append(capi.camera_orthographic((4.0, 3.0, 5.0), (-0.5, -0.4, -0.7), (0.0, 1.0, 0.0), 1.5, W / Hh))
+    cams.append(capi.camera_perspective((0.1, 0.0, 0.2), (0.0, 0.0, -1.0), (0.0, 1.0, 0.0), 1.0, W / Hh))  # inside
+    cams.append(capi.camera_perspective((0.0, 0.0, 4.0), (0.0, 0.0, -1.0), (0.0, 1.0, 0.0), 0.6, W / Hh, 4.0, 0.1))  # lens
+    cams.append(capi.camera_perspective((0.0, 0.0, 4.0), (0.0, 0.0, 1.0), (0.0, 1.0, 0.0), 0.6, W / Hh))  # looking away
+    npx = W * Hh
+    culled_any = False
+    for ci, cam in enumerate(cams):
+        scene = H.default_scene(n, W, Hh, rate=0.5, field="blobs", integrator=capi.DVR_INTEGRATOR_DEFAULT)
+        scene.camera = cam
+        cs = H.CudaScene(scene)
+        try:
+            full_rgba = torch.zeros((npx, 4), dtype=torch.float32, device="cuda")
+            full_depth = torch.zeros(npx, dtype=torch.float32, device="cuda")
+            capi.render_partial(H._params(scene, 0, -1), cam, cs.instances, full_rgba.data_ptr(), full_depth.data_ptr())
+            cut_rgba = torch.full((npx, 4), float("nan"), dtype=torch.float32, device="cuda")
+            cut_depth = torch.full((npx,), float("nan"), dtype=torch.float32, device="cuda")
+            capi.render_partial(H._params(scene, 0, -1, partial_cull_to_bounds=True), cam, cs.instances,
+                                cut_rgba.data_ptr(), cut_depth.data_ptr())
+            torch.cuda.synchronize()
+        finally:
+            cs.destroy()
+        fr, fd = full_rgba.cpu().numpy(), full_depth.cpu().numpy()
+        cr, cd = cut_rgba.cpu().numpy(), cut_depth.cpu().numpy()
+        written = ~np.isnan(cd)
+        hit = fd < 1e29  # pixels whose ray entered the bounds
+        assert np.all(written[hit]), (ci, int((hit & ~written).sum()))
+        assert np.array_equal(cr[written], fr[written]) and np.array_equal(cd[written], fd[written]), ci
+        culled_any |= bool((~written).any())
+    assert culled_any  # the far cameras really skip most of the frame

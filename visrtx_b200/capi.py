@@ -73,7 +73,7 @@ class DvrFrameParams(C.Structure):
                 ("inverseVolumeSamplingRate", C.c_float), ("background", C.c_float * 4),
                 ("tileRank", C.c_uint32), ("tileRanks", C.c_uint32), ("useMacrocellSkipping", C.c_int32),
                 ("tileBand", C.c_int32), ("maxDepth", C.c_int32), ("ambientRadiance", C.c_float),
-                ("occlusionDistance", C.c_float), ("dptReferenceGrid", C.c_int32), ("_reserved", C.c_int32 * 2)]
+                ("occlusionDistance", C.c_float), ("dptReferenceGrid", C.c_int32), ("partialCullToBounds", C.c_int32), ("_reserved", C.c_int32 * 1)]
 
 
 class DvrRenderStats(C.Structure):
@@ -320,7 +320,7 @@ def make_instances(volumes: Sequence[Volume], xfms=None, inst_ids=None):
 def frame_params(width, height, fmt=DVR_FORMAT_UFIXED8_RGBA_SRGB, integrator=DVR_INTEGRATOR_RAYCAST, frame_id=0,
                  checkerboard_id=-1, num_iterations=1, volume_sampling_rate=0.125, background=(0.0, 0.0, 0.0, 1.0),
                  tile_rank=0, tile_ranks=1, skip=False, tile_band=1, max_depth=5, ambient_radiance=1.0,
-                 occlusion_distance=1e20, dpt_reference_grid=False) -> DvrFrameParams:
+                 occlusion_distance=1e20, dpt_reference_grid=False, partial_cull_to_bounds=False) -> DvrFrameParams:
     p = DvrFrameParams()
     p.width, p.height, p.format, p.integrator = int(width), int(height), int(fmt), int(integrator)
     p.frameID, p.checkerboardID, p.numIterations = int(frame_id), int(checkerboard_id), int(num_iterations)
@@ -332,6 +332,7 @@ def frame_params(width, height, fmt=DVR_FORMAT_UFIXED8_RGBA_SRGB, integrator=DVR
     p.tileBand = int(tile_band)
     p.maxDepth, p.ambientRadiance, p.occlusionDistance = int(max_depth), float(ambient_radiance), float(occlusion_distance)
     p.dptReferenceGrid = 1 if dpt_reference_grid else 0
+    p.partialCullToBounds = 1 if partial_cull_to_bounds else 0
     return p
 
 

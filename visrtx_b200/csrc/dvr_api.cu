@@ -1127,6 +1127,59 @@ static int fillSync(const DvrPeerSync *in, SyncDev &out)
   return DVR_OK;
 }
 
+// Conservative pixel rectangle that contains every pixel whose (jittered) primary ray can hit the instance's
+// bounds: the projection of the 8 box corners through the camera model of cameraCreateRay, padded by 2 pixels.
+// Returns false (=> whole frame) whenever the bound cannot be trusted: thin-lens cameras, a transformed instance,
+// a corner behind the eye, a degenerate camera basis.
+static bool screenRectOfBounds(const DvrCamera *c, const DvrVolumeInstance *in, uint32_t W, uint32_t H, int rect[4])
+{
+  static const float ident[12] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0};
+  if (std::memcmp(in->worldToObject, ident, sizeof(ident)) != 0 || c->scaledAperture > 0.f)
+    return false;
+  const float3 lo = in->volume->field->dev.boundsLo, hi = in->volume->field->dev.boundsHi;
+  const double rw = (double)c->region[2] - c->region[0], rh = (double)c->region[3] - c->region[1];
+  if (!(std::fabs(rw) > 1e-12) || !(std::fabs(rh) > 1e-12))
+    return false;
+  const bool persp = c->type == DVR_CAMERA_PERSPECTIVE;
+  // columns of the 3x3 system: du, dv, and p00 (perspective) or dir (orthographic)
+  const double a[3] = {c->du[0], c->du[1], c->du[2]}, b[3] = {c->dv[0], c->dv[1], c->dv[2]};
+  const double k[3] = {persp ? c->p00[0] : c->dir[0], persp ? c->p00[1] : c->dir[1], persp ? c->p00[2] : c->dir[2]};
+  const double det = a[0] * (b[1] * k[2] - b[2] * k[1]) - b[0] * (a[1] * k[2] - a[2] * k[1]) + k[0] * (a[1] * b[2] - a[2] * b[1]);
+  if (!(std::fabs(det) > 1e-30))
+    return false;
+  double xmin = 1e300, xmax = -1e300, ymin = 1e300, ymax = -1e300;
+  for (int i = 0; i < 8; ++i) {
+    const double P[3] = {(i & 1) ? hi.x : lo.x, (i & 2) ? hi.y : lo.y, (i & 4) ? hi.z : lo.z};
+    const double o[3] = {persp ? c->pos[0] : c->p00[0], persp ? c->pos[1] : c->p00[1], persp ? c->pos[2] : c->p00[2]};
+    const double r[3] = {P[0] - o[0], P[1] - o[1], P[2] - o[2]};
+    // Cramer: r = x*a + y*b + z*k
+    const double x = (r[0] * (b[1] * k[2] - b[2] * k[1]) - b[0] * (r[1] * k[2] - r[2] * k[1]) + k[0] * (r[1] * b[2] - r[2] * b[1])) / det;
+    const double y = (a[0] * (r[1] * k[2] - r[2] * k[1]) - r[0] * (a[1] * k[2] - a[2] * k[1]) + k[0] * (a[1] * r[2] - a[2] * r[1])) / det;
+    const double z = (a[0] * (b[1] * r[2] - b[2] * r[1]) - b[0] * (a[1] * r[2] - a[2] * r[1]) + r[0] * (a[1] * b[2] - a[2] * b[1])) / det;
+    double sx = x, sy = y;
+    if (persp) {
+      if (!(z > 1e-6)) // a corner beside or behind the eye: the projection is unbounded
+        return false;
+      sx = x / z;
+      sy = y / z;
+    }
+    // undo the image-region mapping of cameraCreateRay (sx' = mix(region.x, region.z, sx))
+    const double u = (sx - c->region[0]) / rw * (double)W, v = (sy - c->region[1]) / rh * (double)H;
+    if (!(u == u) || !(v == v))
+      return false;
+    xmin = std::min(xmin, u);
+    xmax = std::max(xmax, u);
+    ymin = std::min(ymin, v);
+    ymax = std::max(ymax, v);
+  }
+  const double pad = 2.0; // pixel jitter is < 1 pixel; the rest is rounding head-room
+  rect[0] = (int)std::floor(std::max(xmin - pad, 0.0));
+  rect[1] = (int)std::floor(std::max(ymin - pad, 0.0));
+  rect[2] = (int)std::ceil(std::min(xmax + pad, (double)W));
+  rect[3] = (int)std::ceil(std::min(ymax + pad, (double)H));
+  return true;
+}
+
 static int renderPartialImpl(const DvrFrameParams *p, const DvrCamera *camera, const DvrVolumeInstance *instance,
     float *partialRgba, float *partialDepth, DvrRenderStats *statsDev, void *stream, const DvrPeerSync *sync = nullptr)
 {
@@ -1154,6 +1207,20 @@ static int renderPartialImpl(const DvrFrameParams *p, const DvrCamera *camera, c
   L.invSamplingRate = p->inverseVolumeSamplingRate;
   L.tilesX = (p->width + kTileW - 1) / kTileW;
   L.tilesY = (p->height + kTileH - 1) / kTileH;
+  L.tileX0 = L.tileY0 = 0;
+  L.tilesW = L.tilesX;
+  L.tilesH = L.tilesY;
+  int rect[4];
+  if (p->partialCullToBounds && screenRectOfBounds(camera, instance, p->width, p->height, rect)) {
+    if (rect[2] <= rect[0] || rect[3] <= rect[1]) { // the volume is off screen: nothing to march
+      L.tilesW = L.tilesH = 0;
+    } else {
+      L.tileX0 = (uint32_t)rect[0] / kTileW;
+      L.tileY0 = (uint32_t)rect[1] / kTileH;
+      L.tilesW = ((uint32_t)rect[2] + kTileW - 1) / kTileW - L.tileX0;
+      L.tilesH = ((uint32_t)rect[3] + kTileH - 1) / kTileH - L.tileY0;
+    }
+  }
   fillCamera(camera, L.cam);
   fillInstance(*instance, L.inst);
   L.partialRgba = (float4 *)partialRgba;

@@ -60,6 +60,7 @@ struct PartialLaunch
   int integrator, frameID;
   float invSamplingRate;
   uint32_t tilesX, tilesY;
+  uint32_t tileX0, tileY0, tilesW, tilesH; // tile window actually rendered (partialCullToBounds), else the whole frame
   CameraDev cam;
   InstanceDev inst;
   float4 *partialRgba;

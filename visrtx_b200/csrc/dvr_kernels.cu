@@ -466,10 +466,10 @@ __global__ void __launch_bounds__(kBlockThreads, 2) dvrPartialKernel(const __gri
   __syncthreads();
 
   MarchStats st{0ull, 0ull};
-  const uint32_t nTiles = P.tilesX * P.tilesY;
+  const uint32_t nTiles = P.tilesW * P.tilesH;
   const bool centered = P.integrator == DVR_INTEGRATOR_RAYCAST;
   for (uint32_t tile = nextTile(P.sched, lane); tile < nTiles; tile = nextTile(P.sched, lane)) {
-    const uint32_t tyIdx = tile / P.tilesX, txIdx = tile - tyIdx * P.tilesX;
+    const uint32_t tyIdx = P.tileY0 + tile / P.tilesW, txIdx = P.tileX0 + tile % P.tilesW;
     const uint32_t px = txIdx * kTileW + (lane % kTileW), py = tyIdx * kTileH + (lane / kTileW);
     if (px >= P.width || py >= P.height)
       continue;
@@ -509,7 +509,7 @@ static int launchPartialT(const PartialLaunch &p, cudaStream_t s)
     if (bps < 1)
       bps = 1;
   }
-  const uint32_t nTiles = p.tilesX * p.tilesY;
+  const uint32_t nTiles = p.tilesW * p.tilesH;
   uint32_t grid = (uint32_t)(smCount() * bps);
   const uint32_t need = (nTiles + 7) / 8;
   if (grid > need)

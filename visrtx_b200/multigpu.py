@@ -282,8 +282,10 @@ class SortLast:
         self._hot = None
 
     def params(self, frame_id: int):
+        # the synchronised fused composite (world > 1) regenerates every primary ray and never reads a pixel whose ray
+        # misses the bounds, so the partial march may confine itself to the screen rectangle of the volume
         return self.capi.frame_params(self.W, self.H, self.fmt, self.integrator, frame_id, -1, 1, self.rate,
-                                      self.background, skip=self.skip)
+                                      self.background, skip=self.skip, partial_cull_to_bounds=self.world > 1)
 
     def stream_to_host(self, on: bool):
         """Route the final colour also into the shared host frame (needs host_mirror=True at construction)."""
