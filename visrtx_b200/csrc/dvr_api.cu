@@ -959,6 +959,59 @@ static int ensureDdaGrid(DvrVolume *v, bool referenceBuild, cudaStream_t s)
   return rc;
 }
 
+// Conservative pixel rectangle that contains every pixel whose (jittered) primary ray can hit the instance's
+// bounds: the projection of the 8 box corners through the camera model of cameraCreateRay, padded by 2 pixels.
+// Returns false (=> whole frame) whenever the bound cannot be trusted: thin-lens cameras, a transformed instance,
+// a corner behind the eye, a degenerate camera basis.
+static bool screenRectOfBounds(const DvrCamera *c, const DvrVolumeInstance *in, uint32_t W, uint32_t H, int rect[4])
+{
+  static const float ident[12] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0};
+  if (std::memcmp(in->worldToObject, ident, sizeof(ident)) != 0 || c->scaledAperture > 0.f)
+    return false;
+  const float3 lo = in->volume->field->dev.boundsLo, hi = in->volume->field->dev.boundsHi;
+  const double rw = (double)c->region[2] - c->region[0], rh = (double)c->region[3] - c->region[1];
+  if (!(std::fabs(rw) > 1e-12) || !(std::fabs(rh) > 1e-12))
+    return false;
+  const bool persp = c->type == DVR_CAMERA_PERSPECTIVE;
+  // columns of the 3x3 system: du, dv, and p00 (perspective) or dir (orthographic)
+  const double a[3] = {c->du[0], c->du[1], c->du[2]}, b[3] = {c->dv[0], c->dv[1], c->dv[2]};
+  const double k[3] = {persp ? c->p00[0] : c->dir[0], persp ? c->p00[1] : c->dir[1], persp ? c->p00[2] : c->dir[2]};
+  const double det = a[0] * (b[1] * k[2] - b[2] * k[1]) - b[0] * (a[1] * k[2] - a[2] * k[1]) + k[0] * (a[1] * b[2] - a[2] * b[1]);
+  if (!(std::fabs(det) > 1e-30))
+    return false;
+  double xmin = 1e300, xmax = -1e300, ymin = 1e300, ymax = -1e300;
+  for (int i = 0; i < 8; ++i) {
+    const double P[3] = {(i & 1) ? hi.x : lo.x, (i & 2) ? hi.y : lo.y, (i & 4) ? hi.z : lo.z};
+    const double o[3] = {persp ? c->pos[0] : c->p00[0], persp ? c->pos[1] : c->p00[1], persp ? c->pos[2] : c->p00[2]};
+    const double r[3] = {P[0] - o[0], P[1] - o[1], P[2] - o[2]};
+    // Cramer: r = x*a + y*b + z*k
+    const double x = (r[0] * (b[1] * k[2] - b[2] * k[1]) - b[0] * (r[1] * k[2] - r[2] * k[1]) + k[0] * (r[1] * b[2] - r[2] * b[1])) / det;
+    const double y = (a[0] * (r[1] * k[2] - r[2] * k[1]) - r[0] * (a[1] * k[2] - a[2] * k[1]) + k[0] * (a[1] * r[2] - a[2] * r[1])) / det;
+    const double z = (a[0] * (b[1] * r[2] - b[2] * r[1]) - b[0] * (a[1] * r[2] - a[2] * r[1]) + r[0] * (a[1] * b[2] - a[2] * b[1])) / det;
+    double sx = x, sy = y;
+    if (persp) {
+      if (!(z > 1e-6)) // a corner beside or behind the eye: the projection is unbounded
+        return false;
+      sx = x / z;
+      sy = y / z;
+    }
+    // undo the image-region mapping of cameraCreateRay (sx' = mix(region.x, region.z, sx))
+    const double u = (sx - c->region[0]) / rw * (double)W, v = (sy - c->region[1]) / rh * (double)H;
+    if (!(u == u) || !(v == v))
+      return false;
+    xmin = std::min(xmin, u);
+    xmax = std::max(xmax, u);
+    ymin = std::min(ymin, v);
+    ymax = std::max(ymax, v);
+  }
+  const double pad = 2.0; // pixel jitter is < 1 pixel; the rest is rounding head-room
+  rect[0] = (int)std::floor(std::max(xmin - pad, 0.0));
+  rect[1] = (int)std::floor(std::max(ymin - pad, 0.0));
+  rect[2] = (int)std::ceil(std::min(xmax + pad, (double)W));
+  rect[3] = (int)std::ceil(std::min(ymax + pad, (double)H));
+  return true;
+}
+
 static int renderImpl(const DvrFrameParams *p, const DvrCamera *camera, const DvrVolumeInstance *instances,
     uint32_t nInstances, const DvrFrameBuffers *b, DvrRenderStats *statsDev, bool stats, void *stream)
 {
@@ -1028,6 +1081,29 @@ static int renderImpl(const DvrFrameParams *p, const DvrCamera *camera, const Dv
   L.fb.normal = b->normal;
   L.nInst = (int)nInstances;
 
+  // background-only pixels without ray set-up (marching integrators; not when the ray direction is an output)
+  L.missValid = 0;
+  if ((p->integrator == DVR_INTEGRATOR_RAYCAST || p->integrator == DVR_INTEGRATOR_DEFAULT) && !b->normal) {
+    int u[4] = {(int)p->width, (int)p->height, 0, 0};
+    bool ok = true;
+    for (uint32_t i = 0; i < nInstances && ok; ++i) {
+      int r[4];
+      ok = screenRectOfBounds(camera, &instances[i], p->width, p->height, r);
+      if (ok && r[2] > r[0] && r[3] > r[1]) {
+        u[0] = std::min(u[0], r[0]);
+        u[1] = std::min(u[1], r[1]);
+        u[2] = std::max(u[2], r[2]);
+        u[3] = std::max(u[3], r[3]);
+      }
+    }
+    if (ok) {
+      L.missValid = 1;
+      L.missX0 = u[0];
+      L.missY0 = u[1];
+      L.missX1 = u[2];
+      L.missY1 = u[3];
+    }
+  }
   bool skip = p->useMacrocellSkipping == DVR_SKIP_ON;
   if (p->useMacrocellSkipping == DVR_SKIP_AUTO) // images are identical either way: pick the faster kernel
     for (uint32_t i = 0; i < nInstances; ++i)
@@ -1125,59 +1201,6 @@ static int fillSync(const DvrPeerSync *in, SyncDev &out)
   out.wait = in->wait;
   out.errorFlag = in->errorFlag;
   return DVR_OK;
-}
-
-// Conservative pixel rectangle that contains every pixel whose (jittered) primary ray can hit the instance's
-// bounds: the projection of the 8 box corners through the camera model of cameraCreateRay, padded by 2 pixels.
-// Returns false (=> whole frame) whenever the bound cannot be trusted: thin-lens cameras, a transformed instance,
-// a corner behind the eye, a degenerate camera basis.
-static bool screenRectOfBounds(const DvrCamera *c, const DvrVolumeInstance *in, uint32_t W, uint32_t H, int rect[4])
-{
-  static const float ident[12] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0};
-  if (std::memcmp(in->worldToObject, ident, sizeof(ident)) != 0 || c->scaledAperture > 0.f)
-    return false;
-  const float3 lo = in->volume->field->dev.boundsLo, hi = in->volume->field->dev.boundsHi;
-  const double rw = (double)c->region[2] - c->region[0], rh = (double)c->region[3] - c->region[1];
-  if (!(std::fabs(rw) > 1e-12) || !(std::fabs(rh) > 1e-12))
-    return false;
-  const bool persp = c->type == DVR_CAMERA_PERSPECTIVE;
-  // columns of the 3x3 system: du, dv, and p00 (perspective) or dir (orthographic)
-  const double a[3] = {c->du[0], c->du[1], c->du[2]}, b[3] = {c->dv[0], c->dv[1], c->dv[2]};
-  const double k[3] = {persp ? c->p00[0] : c->dir[0], persp ? c->p00[1] : c->dir[1], persp ? c->p00[2] : c->dir[2]};
-  const double det = a[0] * (b[1] * k[2] - b[2] * k[1]) - b[0] * (a[1] * k[2] - a[2] * k[1]) + k[0] * (a[1] * b[2] - a[2] * b[1]);
-  if (!(std::fabs(det) > 1e-30))
-    return false;
-  double xmin = 1e300, xmax = -1e300, ymin = 1e300, ymax = -1e300;
-  for (int i = 0; i < 8; ++i) {
-    const double P[3] = {(i & 1) ? hi.x : lo.x, (i & 2) ? hi.y : lo.y, (i & 4) ? hi.z : lo.z};
-    const double o[3] = {persp ? c->pos[0] : c->p00[0], persp ? c->pos[1] : c->p00[1], persp ? c->pos[2] : c->p00[2]};
-    const double r[3] = {P[0] - o[0], P[1] - o[1], P[2] - o[2]};
-    // Cramer: r = x*a + y*b + z*k
-    const double x = (r[0] * (b[1] * k[2] - b[2] * k[1]) - b[0] * (r[1] * k[2] - r[2] * k[1]) + k[0] * (r[1] * b[2] - r[2] * b[1])) / det;
-    const double y = (a[0] * (r[1] * k[2] - r[2] * k[1]) - r[0] * (a[1] * k[2] - a[2] * k[1]) + k[0] * (a[1] * r[2] - a[2] * r[1])) / det;
-    const double z = (a[0] * (b[1] * r[2] - b[2] * r[1]) - b[0] * (a[1] * r[2] - a[2] * r[1]) + r[0] * (a[1] * b[2] - a[2] * b[1])) / det;
-    double sx = x, sy = y;
-    if (persp) {
-      if (!(z > 1e-6)) // a corner beside or behind the eye: the projection is unbounded
-        return false;
-      sx = x / z;
-      sy = y / z;
-    }
-    // undo the image-region mapping of cameraCreateRay (sx' = mix(region.x, region.z, sx))
-    const double u = (sx - c->region[0]) / rw * (double)W, v = (sy - c->region[1]) / rh * (double)H;
-    if (!(u == u) || !(v == v))
-      return false;
-    xmin = std::min(xmin, u);
-    xmax = std::max(xmax, u);
-    ymin = std::min(ymin, v);
-    ymax = std::max(ymax, v);
-  }
-  const double pad = 2.0; // pixel jitter is < 1 pixel; the rest is rounding head-room
-  rect[0] = (int)std::floor(std::max(xmin - pad, 0.0));
-  rect[1] = (int)std::floor(std::max(ymin - pad, 0.0));
-  rect[2] = (int)std::ceil(std::min(xmax + pad, (double)W));
-  rect[3] = (int)std::ceil(std::min(ymax + pad, (double)H));
-  return true;
 }
 
 static int renderPartialImpl(const DvrFrameParams *p, const DvrCamera *camera, const DvrVolumeInstance *instance,

@@ -43,6 +43,9 @@ struct FrameLaunch
   uint32_t tileRank, tileRanks, tileBand;
   uint32_t launchW, launchH; // pixel-sample grid actually launched (half size when checkerboarding)
   uint32_t tilesX, tilesY;
+  // Pixels outside [missX0,missX1) x [missY0,missY1) cannot hit any volume (conservative screen rectangle of all
+  // instance bounds): they take the background without generating a ray.  missValid == 0: no such knowledge.
+  int missValid, missX0, missY0, missX1, missY1;
   CameraDev cam;
   BuffersDev fb;
   int nInst;

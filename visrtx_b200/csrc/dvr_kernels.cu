@@ -278,6 +278,17 @@ __global__ void __launch_bounds__(kBlockThreads, (KIND >= FIELD_NANOVDB ? DVR_OC
     if (px >= P.width || py >= P.height)
       continue;
 
+    if (!DPT && P.missValid
+        && ((int)px < P.missX0 || (int)px >= P.missX1 || (int)py < P.missY0 || (int)py >= P.missY1)) {
+      // No ray of this pixel can enter a volume: what the march + Raycast_ptx.cu:139-166 produce for a miss, bit for
+      // bit (colour 0*0 + bg*(1-0) = bg, depth min(1e30, tmax), ids ~0u), without Philox or camera work.  Launches
+      // that need the ray direction (normal channel) never set missValid.
+      const float4 bg = P.background;
+      for (int it = 0; it < P.numIterations; ++it)
+        accumResults(actx, px, py, bg, 1e30f, f3(bg.x, bg.y, bg.z), f3(0.f, 0.f, 0.f), 0u, ~0u, ~0u, it,
+            initFrame && it == 0);
+      continue;
+    }
     Philox rng;
     rng.init((unsigned long long)(int)(py * P.width + px), (unsigned long long)P.frameID * 512ull);
     DptPath path{0, f3(1.f, 1.f, 1.f)}; // PathData lives outside the iteration loop in the reference
