@@ -1411,6 +1411,14 @@ static int compositeResolveImpl(const DvrFrameParams *p, const DvrCamera *camera
     L.boundsHi = tmp.v.f.boundsHi;
     std::memcpy(L.xfm, tmp.xfm, sizeof(L.xfm));
     L.identity = tmp.identity;
+    int rect[4];
+    if (screenRectOfBounds(camera, instance, p->width, p->height, rect)) {
+      L.missValid = 1;
+      L.missX0 = rect[0];
+      L.missY0 = rect[1];
+      L.missX1 = rect[2];
+      L.missY1 = rect[3];
+    }
   }
   const int rcs = fillSync(sync, L.sync);
   if (rcs != DVR_OK)

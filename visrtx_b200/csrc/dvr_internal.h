@@ -98,6 +98,7 @@ struct PeerResolveLaunch
   // sync variant
   SyncDev sync;
   int cull;                   // regenerate the primary ray and skip peer loads when it misses the bounds
+  int missValid, missX0, missY0, missX1, missY1; // pixels outside this rectangle miss without regenerating the ray
   int integrator;
   float3 boundsLo, boundsHi;
   float xfm[12];

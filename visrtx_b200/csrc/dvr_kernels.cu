@@ -639,26 +639,32 @@ __global__ void __launch_bounds__(256) dvrPeerResolveKernel(const __grid_constan
   const size_t i = L.r.pixelBegin + blockIdx.x * (size_t)blockDim.x + threadIdx.x;
   if (i < L.r.pixelEnd) {
     const uint32_t px = (uint32_t)(i % L.r.width), py = (uint32_t)(i / L.r.width);
-    // the primary ray exactly as the partial march generated it (same Philox stream, same arithmetic)
-    Philox rng;
-    rng.init((unsigned long long)(int)(py * L.r.width + px), (unsigned long long)L.r.frameID * 512ull);
-    const float4 r = rng.uniform4();
-    const bool centered = L.integrator == DVR_INTEGRATOR_RAYCAST;
-    const float sx = __fmul_rn(centered ? (float)px : __fadd_rn((float)px, r.x), L.invW);
-    const float sy = __fmul_rn(centered ? (float)py : __fadd_rn((float)py, r.y), L.invH);
-    float3 org, dir;
-    cameraCreateRay(L.cam, sx, sy, r.z, r.w, org, dir);
-    float3 lo = org, ld = dir;
-    if (!L.identity) {
-      lo = xfmPoint(L.xfm, org);
-      ld = xfmVector(L.xfm, dir);
-    }
     bool hit = true;
-    if (L.cull) {
-      float t0, t1;
-      hit = intersectVolumeBox(L.boundsLo, L.boundsHi, lo, ld, 0.f, FLT_MAX, t0, t1);
+    bool ascending = true;
+    if (L.cull && L.missValid
+        && ((int)px < L.missX0 || (int)px >= L.missX1 || (int)py < L.missY0 || (int)py >= L.missY1)) {
+      hit = false; // outside the screen rectangle of the bounds: no ray of this pixel can hit
+    } else {
+      // the primary ray exactly as the partial march generated it (same Philox stream, same arithmetic)
+      Philox rng;
+      rng.init((unsigned long long)(int)(py * L.r.width + px), (unsigned long long)L.r.frameID * 512ull);
+      const float4 r = rng.uniform4();
+      const bool centered = L.integrator == DVR_INTEGRATOR_RAYCAST;
+      const float sx = __fmul_rn(centered ? (float)px : __fadd_rn((float)px, r.x), L.invW);
+      const float sy = __fmul_rn(centered ? (float)py : __fadd_rn((float)py, r.y), L.invH);
+      float3 org, dir;
+      cameraCreateRay(L.cam, sx, sy, r.z, r.w, org, dir);
+      float3 lo = org, ld = dir;
+      if (!L.identity) {
+        lo = xfmPoint(L.xfm, org);
+        ld = xfmVector(L.xfm, dir);
+      }
+      if (L.cull) {
+        float t0, t1;
+        hit = intersectVolumeBox(L.boundsLo, L.boundsHi, lo, ld, 0.f, FLT_MAX, t0, t1);
+      }
+      ascending = ld.z >= 0.f; // rays travelling towards +z (object space) meet the low-z slab first
     }
-    const bool ascending = ld.z >= 0.f; // rays travelling towards +z (object space) meet the low-z slab first
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
     float depth = 1e30f;
     if (hit) {
