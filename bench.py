@@ -416,7 +416,11 @@ def run_ours(args, torch, dist, rank, world):
     vol = None
     if mode == "sort-last":
         from visrtx_b200 import multigpu as _mg
-        z0, z1 = _mg.slab_ranges(n, world)[rank]
+        # slabs of equal WORK for the benchmark camera (sample density falls off as 1/r^2 from the eye), not of
+        # equal thickness: see multigpu.view_balanced_slab_ranges
+        _lo, _hi = scene_bounds(args)
+        _, _pose0 = orbit(args)
+        z0, z1 = _mg.view_balanced_slab_ranges(n, world, _lo, _hi, _pose0.position)[rank]
         r0, r1 = _mg.resident_range(z0, z1, n)
         field = capi.Field.create_slab(0, True, scene_dtype(args), (n, n, n), z0, z1, (0, 0, 0), (1, 1, 1),
                                        capi.DVR_FILTER_LINEAR, stream)
@@ -601,6 +605,9 @@ def run_ours(args, torch, dist, rank, world):
         "config": {
             "workload": workload_name(args),
             "parallelism": mode + (f"x{world}" if world > 1 else ""),
+            **({"slabs": "z-slabs of equal work for the initial camera (sample density ~ 1/r^2 from the eye), "
+                         "not of equal thickness (multigpu.view_balanced_slab_ranges)"}
+               if mode == "sort-last" and world > 1 else {}),
             "l2": (f"NanoVDB grid {vol.nbytes / 1e6:.0f} MB > 126 MB L2; no flush" if args.field == "fog" else
                    f"input volume {n ** 3 * voxel_bytes(args) / 2 ** 30:.1f} GiB >> 126 MB L2; no flush needed"),
             "macrocell_skipping": bool(args.skip),

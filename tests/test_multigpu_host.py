@@ -79,3 +79,31 @@ def test_handle_exchange_and_barrier_over_gloo(tmp_path):
     outs = [p.communicate(timeout=180) for p in procs]
     for r, (o, e) in enumerate(outs):
         assert f"HOST_WORKER_OK {r}" in o, e[-2000:]
+
+
+def test_view_balanced_slabs_partition_and_equalise_the_inverse_square_weight():
+    nz, world = 1024, 8
+    lo, hi = (0.0, 0.0, 0.0), (1023.0, 1023.0, 1023.0)
+    eye = (511.5 + 0.47 * 3544, 511.5 + 0.34 * 3544, 511.5 + 0.81 * 3544)  # the benchmark orbit: 2|diag| away
+    r = multigpu.view_balanced_slab_ranges(nz, world, lo, hi, eye)
+    assert r[0][0] == 0 and r[-1][1] == nz and all(a[1] == b[0] for a, b in zip(r, r[1:]))
+    sizes = [b - a for a, b in r]
+    assert min(sizes) >= 2 and sizes[0] > sizes[-1]  # the slab farthest from the eye (low z) is the thickest
+
+    def weight(a, b):
+        tot = 0.0
+        for k in range(a, b):
+            z = (k + 0.5) * 1023.0 / nz
+            tot += sum(1.0 / ((x - eye[0]) ** 2 + (y - eye[1]) ** 2 + (z - eye[2]) ** 2)
+                       for x in (100.0, 511.5, 900.0) for y in (100.0, 511.5, 900.0))
+        return tot
+    ws = [weight(a, b) for a, b in r]
+    assert max(ws) / min(ws) < 1.05
+    uniform = [weight(a, b) for a, b in multigpu.slab_ranges(nz, world)]
+    assert max(uniform) / min(uniform) > 1.5  # what equal-thickness slabs cost at this camera
+    assert multigpu.view_balanced_slab_ranges(nz, world, lo, hi, None) == multigpu.slab_ranges(nz, world)
+    tiny = multigpu.view_balanced_slab_ranges(16, 8, lo, hi, (511.5, 511.5, 1030.0))
+    assert [b - a for a, b in tiny] == [2] * 8
+    import pytest
+    with pytest.raises(ValueError):
+        multigpu.view_balanced_slab_ranges(15, 8, lo, hi, eye)

@@ -31,6 +31,50 @@ def slab_ranges(nz: int, world: int) -> List[Tuple[int, int]]:
     return out
 
 
+def view_balanced_slab_ranges(nz: int, world: int, bounds_lo, bounds_hi, eye=None, min_slices: int = 2
+                              ) -> List[Tuple[int, int]]:
+    """z-slice ownership balanced by WORK for a perspective camera at `eye` (object space).
+
+    Lattice samples are uniform along each ray, and rays are uniform per solid angle, so the sample density in
+    space falls off as 1/r^2 from the eye: the slab nearest the camera holds up to (r_far/r_near)^2 times the samples
+    of the farthest one (1.76x at the 2|diag| benchmark orbit).  Slices are weighted by the mean 1/r^2 over their
+    area and the boundaries are put at equal cumulative weight.  eye=None (orthographic) gives `slab_ranges`.
+    The partition is static: it suits a camera that stays near the pose it was computed for."""
+    if eye is None:
+        return slab_ranges(nz, world)
+    if world < 1 or nz < world * min_slices:
+        raise ValueError(f"cannot split {nz} slices over {world} ranks with >= {min_slices} slices each")
+    lo = [float(v) for v in bounds_lo]
+    hi = [float(v) for v in bounds_hi]
+    ex, ey, ez = (float(v) for v in eye)
+    g = 12
+    xs = [lo[0] + (hi[0] - lo[0]) * (i + 0.5) / g for i in range(g)]
+    ys = [lo[1] + (hi[1] - lo[1]) * (j + 0.5) / g for j in range(g)]
+    w = []
+    for k in range(nz):
+        z = lo[2] + (hi[2] - lo[2]) * (k + 0.5) / nz
+        acc = 0.0
+        for x in xs:
+            for y in ys:
+                r2 = (x - ex) ** 2 + (y - ey) ** 2 + (z - ez) ** 2
+                acc += 1.0 / max(r2, 1e-12)
+        w.append(acc)
+    total = sum(w)
+    cuts, run, target = [0], 0.0, 1
+    for k in range(nz):
+        run += w[k]
+        while target < world and run >= total * target / world:
+            cuts.append(k + 1)
+            target += 1
+    cuts = cuts[:world] + [nz]
+    # enforce the minimum thickness front to back, then back to front
+    for i in range(1, world):
+        cuts[i] = max(cuts[i], cuts[i - 1] + min_slices)
+    for i in range(world - 1, 0, -1):
+        cuts[i] = min(cuts[i], cuts[i + 1] - min_slices)
+    return [(cuts[i], cuts[i + 1]) for i in range(world)]
+
+
 def resident_range(z0: int, z1: int, nz: int) -> Tuple[int, int]:
     """Slices a slab must hold: its own plus one ghost slice on each side, clamped to the volume."""
     return max(z0 - 1, 0), min(z1 + 1, nz)
