@@ -383,6 +383,16 @@ int dvr_ipc_free(void *devPtr);
 /* Frame::mapAlbedoBuffer / mapNormalBuffer, frame/Frame.cu:521-557: out = accum * invFrameID */
 int dvr_scale_vec3(const float *accumVec3, float *outVec3, size_t nPixels, float scale, void *stream);
 
+/* ---- host helper ------------------------------------------------------------------------------------
+ * The conservative pixel rectangle [x0,x1) x [y0,y1) outside which no primary ray of `camera` (jitter included) can
+ * hit the axis-aligned box: the projection of the 8 corners through the camera model of gpu/cameraCreateRay.h:38-81
+ * (perspective / orthographic, image region), padded by 2 pixels.  The frame kernel gives pixels outside it the
+ * background without ray set-up, and the sort-last partial march skips them.  Pure host arithmetic (no GPU).
+ * Returns 1 and the rectangle, or 0 and the whole frame when no bound can be trusted (thin-lens camera, a corner
+ * beside or behind the eye, degenerate camera basis); < 0 on bad arguments. */
+int dvr_bounds_screen_rect(const DvrCamera *camera, const float boundsLo[3], const float boundsHi[3], uint32_t width,
+    uint32_t height, int32_t rect[4]);
+
 /* ---- self-test ------------------------------------------------------------------------------------
  * Empty-space skipping advances a ray over n lattice points in closed form (per float binade) instead of n
  * dependent `t += step` additions; the lattice must stay bit-identical to the reference's loop

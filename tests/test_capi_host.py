@@ -146,3 +146,59 @@ def test_post_pass_oracle_known_answers():
     c, d, i = PO.composite_depth(np.array([1, 2], np.uint32), np.array([0.5, 0.5], np.float32), np.array([8, 8], np.uint32),
                                  np.array([3, 4], np.uint32), np.array([0.25, 0.75], np.float32), np.array([9, 9], np.uint32), False)
     assert c.tolist() == [3, 2] and d.tolist() == [0.25, 0.5] and i.tolist() == [9, 8]
+
+
+def test_bounds_screen_rect_is_conservative_for_random_cameras_and_boxes():
+    """Every pixel with ANY jittered primary ray hitting the box must lie inside dvr_bounds_screen_rect (checked with
+    numpy rays built from the same DvrCamera: 5 x 5 jitter positions per pixel incl. the pixel corners)."""
+    rng = np.random.default_rng(42)
+    W, Hh = 96, 64
+    valid_seen = invalid_seen = shrunk = 0
+    for trial in range(120):
+        lo = rng.uniform(-2, 1, 3)
+        hi = lo + rng.uniform(0.2, 2.5, 3)
+        ctr = 0.5 * (lo + hi)
+        pos = ctr + rng.normal(size=3) * rng.uniform(0.5, 8.0)
+        look = ctr + rng.normal(size=3) * 0.8 - pos
+        look /= np.linalg.norm(look)
+        up = (0.0, 1.0, 0.0) if abs(look[1]) < 0.95 else (1.0, 0.0, 0.0)
+        region = None if trial % 3 else tuple(sorted(rng.uniform(0, 1, 2))[i] for i in (0, 0, 1, 1))
+        if region is not None:
+            a, b = sorted(rng.uniform(0, 1, 2)); c, d = sorted(rng.uniform(0, 1, 2))
+            region = (a, c, max(b, a + 0.05), max(d, c + 0.05))
+        if trial % 4 == 3:
+            cam = capi.camera_orthographic(tuple(pos), tuple(look), up, float(rng.uniform(1, 6)), W / Hh, region=region)
+        else:
+            cam = capi.camera_perspective(tuple(pos), tuple(look), up, float(rng.uniform(0.3, 1.6)), W / Hh, region=region)
+        ok, (x0, y0, x1, y1) = capi.bounds_screen_rect(cam, lo, hi, W, Hh)
+        if not ok:
+            invalid_seen += 1
+            assert (x0, y0, x1, y1) == (0, 0, W, Hh)
+            continue
+        valid_seen += 1
+        shrunk += (x1 - x0) * (y1 - y0) < W * Hh
+        hit = np.zeros((Hh, W), bool)
+        reg = np.asarray(cam.region, np.float64)
+        for jx in np.linspace(0.0, 0.999, 5):
+            for jy in np.linspace(0.0, 0.999, 5):
+                sx = (np.arange(W) + jx) / W
+                sy = (np.arange(Hh) + jy) / Hh
+                SX, SY = np.meshgrid(reg[0] + (reg[2] - reg[0]) * sx, reg[1] + (reg[3] - reg[1]) * sy)
+                if cam.type == capi.DVR_CAMERA_PERSPECTIVE:
+                    dirs = np.asarray(cam.p00)[None, None] + SX[..., None] * np.asarray(cam.du) + SY[..., None] * np.asarray(cam.dv)
+                    org = np.broadcast_to(np.asarray(cam.pos, np.float64), dirs.shape)
+                else:
+                    org = np.asarray(cam.p00)[None, None] + SX[..., None] * np.asarray(cam.du) + SY[..., None] * np.asarray(cam.dv)
+                    dirs = np.broadcast_to(np.asarray(cam.dir, np.float64), org.shape)
+                with np.errstate(divide="ignore", invalid="ignore"):
+                    t0 = (lo - org) / dirs
+                    t1 = (hi - org) / dirs
+                tn = np.minimum(t0, t1).max(-1)
+                tf = np.maximum(t0, t1).min(-1)
+                hit |= (tn < tf) & (tf >= 0)
+        ys, xs = np.nonzero(hit)
+        if len(xs):
+            assert xs.min() >= x0 and xs.max() < x1 and ys.min() >= y0 and ys.max() < y1, (trial, (x0, y0, x1, y1))
+    assert valid_seen > 40 and invalid_seen > 5 and shrunk > 20
+    lens = capi.camera_perspective((0, 0, 5), (0, 0, -1), (0, 1, 0), 0.8, W / Hh, 4.0, 0.1)
+    assert capi.bounds_screen_rect(lens, (-1, -1, -1), (1, 1, 1), W, Hh) == (False, (0, 0, W, Hh))

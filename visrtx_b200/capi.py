@@ -36,7 +36,7 @@ EXPORTED_SYMBOLS = [
     "dvr_volume_create", "dvr_volume_update", "dvr_volume_destroy", "dvr_volume_majorants",
     "dvr_volume_dda_majorants",
     "dvr_post_convert_float_color", "dvr_post_composite_depth", "dvr_post_outline", "dvr_post_visualize_depth",
-    "dvr_post_pick", "dvr_selftest_lattice_advance",
+    "dvr_post_pick", "dvr_selftest_lattice_advance", "dvr_bounds_screen_rect",
     "dvr_render", "dvr_render_instrumented", "dvr_launch_count",
     "dvr_render_partial", "dvr_render_partial_instrumented", "dvr_composite_over", "dvr_resolve", "dvr_scale_vec3",
     "dvr_composite_resolve_peers", "dvr_render_partial_sync", "dvr_composite_resolve_peers_sync", "dvr_wait_flags",
@@ -477,3 +477,12 @@ def selftest_lattice_advance(count: int = 1 << 20, seed: int = 1, stream: int = 
     m = C.c_uint32(0xFFFFFFFF)
     _check(lib.dvr_selftest_lattice_advance(C.c_uint32(count), C.c_uint64(seed), C.byref(m), C.c_void_p(stream)))
     return m.value
+
+
+def bounds_screen_rect(camera: DvrCamera, lo, hi, width: int, height: int):
+    """(valid, (x0, y0, x1, y1)): the conservative pixel rectangle of an axis-aligned box (host arithmetic only)."""
+    r = (C.c_int32 * 4)()
+    rc = lib.dvr_bounds_screen_rect(C.byref(camera), _f3(*lo), _f3(*hi), C.c_uint32(width), C.c_uint32(height), r)
+    if rc < 0:
+        _check(rc)
+    return bool(rc), tuple(r)

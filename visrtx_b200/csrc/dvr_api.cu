@@ -963,12 +963,20 @@ static int ensureDdaGrid(DvrVolume *v, bool referenceBuild, cudaStream_t s)
 // bounds: the projection of the 8 box corners through the camera model of cameraCreateRay, padded by 2 pixels.
 // Returns false (=> whole frame) whenever the bound cannot be trusted: thin-lens cameras, a transformed instance,
 // a corner behind the eye, a degenerate camera basis.
+static bool screenRectOfBox(const DvrCamera *c, const float3 lo, const float3 hi, uint32_t W, uint32_t H, int rect[4]);
+
 static bool screenRectOfBounds(const DvrCamera *c, const DvrVolumeInstance *in, uint32_t W, uint32_t H, int rect[4])
 {
   static const float ident[12] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0};
-  if (std::memcmp(in->worldToObject, ident, sizeof(ident)) != 0 || c->scaledAperture > 0.f)
+  if (std::memcmp(in->worldToObject, ident, sizeof(ident)) != 0)
     return false;
-  const float3 lo = in->volume->field->dev.boundsLo, hi = in->volume->field->dev.boundsHi;
+  return screenRectOfBox(c, in->volume->field->dev.boundsLo, in->volume->field->dev.boundsHi, W, H, rect);
+}
+
+static bool screenRectOfBox(const DvrCamera *c, const float3 lo, const float3 hi, uint32_t W, uint32_t H, int rect[4])
+{
+  if (c->scaledAperture > 0.f)
+    return false;
   const double rw = (double)c->region[2] - c->region[0], rh = (double)c->region[3] - c->region[1];
   if (!(std::fabs(rw) > 1e-12) || !(std::fabs(rh) > 1e-12))
     return false;
@@ -1486,6 +1494,21 @@ int dvr_ipc_free(void *devPtr)
   if (devPtr)
     DVR_CUDA(cudaFree(devPtr));
   return DVR_OK;
+}
+
+int dvr_bounds_screen_rect(const DvrCamera *camera, const float boundsLo[3], const float boundsHi[3], uint32_t width,
+    uint32_t height, int32_t rect[4])
+{
+  if (!camera || !boundsLo || !boundsHi || !rect || width == 0 || height == 0) {
+    setError("dvr_bounds_screen_rect: invalid argument");
+    return DVR_ERR_INVALID_ARGUMENT;
+  }
+  int r[4] = {0, 0, (int)width, (int)height};
+  const bool ok = screenRectOfBox(camera, make_float3(boundsLo[0], boundsLo[1], boundsLo[2]),
+      make_float3(boundsHi[0], boundsHi[1], boundsHi[2]), width, height, r);
+  for (int i = 0; i < 4; ++i)
+    rect[i] = r[i];
+  return ok ? 1 : 0;
 }
 
 int dvr_selftest_lattice_advance(uint32_t count, uint64_t seed, uint32_t *mismatchesOut, void *stream)
