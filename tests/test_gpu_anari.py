@@ -379,3 +379,52 @@ def test_host_colour_streaming_equals_copy_path():
         assert np.array_equal(last, again)
         assert not _errors(d), d.messages
         s.close()
+
+
+def test_array1d_region_parameters_begin_end():
+    """Array1D honours `begin` / `end` (array/Array1D.cpp:43-66): consumers see elements [begin, end) only — the
+    transfer function's colour control points and the world's volume list."""
+    n = 32
+    cmap = np.array([[9, 9, 9, 9], [1, 0, 0, 0.0], [0, 1, 0, 0.5], [0, 0, 1, 1.0], [7, 7, 7, 7], [5, 5, 5, 5]], np.float32)
+    s = AnariScene(n, 64, 48, "raycast", 0.5)
+    d = s.d
+    arr = d.new_array1d(cmap, A.FLOAT32_VEC4)
+    d.set(arr, "begin", A.UINT64, 1)
+    d.set(arr, "end", A.UINT64, 4)
+    d.commit(arr)
+    d.set(s.volume, "color", A.ARRAY1D, arr)
+    d.commit(s.volume)
+    s.render()
+    got, _, _, _ = d.map_frame(s.frame, "channel.color")
+    ref = AnariScene(n, 64, 48, "raycast", 0.5)
+    mid = ref.d.new_array1d(np.ascontiguousarray(cmap[1:4]), A.FLOAT32_VEC4)
+    ref.d.set(ref.volume, "color", A.ARRAY1D, mid)
+    ref.d.commit(ref.volume)
+    ref.render()
+    want, _, _, _ = ref.d.map_frame(ref.frame, "channel.color")
+    assert np.array_equal(got, want)
+    # swapped bounds warn and are swapped; a later change of the window re-finalises the volume (accumulation resets)
+    d.set(arr, "begin", A.UINT64, 4)
+    d.set(arr, "end", A.UINT64, 1)
+    d.commit(arr)
+    s.render()
+    again, _, _, _ = d.map_frame(s.frame, "channel.color")
+    assert np.array_equal(again, want) and any("swapping" in m[2] for m in d.messages)
+    d.set(arr, "begin", A.UINT64, 2)
+    d.set(arr, "end", A.UINT64, 5)
+    d.commit(arr)
+    s.render()
+    other, _, _, _ = d.map_frame(s.frame, "channel.color")
+    assert not np.array_equal(other, want) and d.get_property(s.frame, "numSamples", A.INT32) == 0
+    # object arrays: the world renders only the volumes inside the window
+    two = d.new_object_array([s.volume, s.volume], A.VOLUME)
+    d.set(two, "begin", A.UINT64, 1)
+    d.commit(two)
+    d.set(s.world, "volume", A.ARRAY1D, two)
+    d.commit(s.world)
+    s.render()
+    one_vol, _, _, _ = d.map_frame(s.frame, "channel.color")
+    assert np.array_equal(one_vol, other)  # one instance of the volume, not two overlapping ones
+    assert not _errors(d), d.messages
+    s.close()
+    ref.close()

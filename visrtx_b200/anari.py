@@ -22,7 +22,7 @@ STRING_LIST, PARAMETER_LIST = 150, 152
 STATUS_CALLBACK, FRAME_COMPLETION_CALLBACK = 202, 203
 DEVICE, ARRAY1D, ARRAY2D, ARRAY3D, CAMERA, FRAME, GROUP, INSTANCE, RENDERER, SPATIAL_FIELD, VOLUME, WORLD = (
     501, 504, 505, 506, 507, 508, 510, 511, 514, 517, 518, 519)
-UINT8, INT32, UINT32, UINT32_VEC2 = 1004, 1016, 1020, 1021
+UINT8, INT32, UINT32, UINT32_VEC2, UINT64 = 1004, 1016, 1020, 1021, 1028
 FIXED8, UFIXED8, UFIXED8_VEC4, FIXED16, UFIXED16 = 1032, 1036, 1039, 1040, 1044
 FLOAT16, FLOAT32, FLOAT32_VEC2, FLOAT32_VEC3, FLOAT32_VEC4, FLOAT64 = 1064, 1068, 1069, 1070, 1071, 1072
 UFIXED8_RGBA_SRGB = 2003
@@ -167,6 +167,8 @@ class Device:
             buf = C.c_int32(int(value))
         elif dtype == UINT32:
             buf = C.c_uint32(int(value))
+        elif dtype == UINT64:
+            buf = C.c_uint64(int(value))
         elif dtype == FLOAT32:
             buf = C.c_float(float(value))
         elif dtype in (VOID_POINTER, FRAME_COMPLETION_CALLBACK, STATUS_CALLBACK) or 500 <= dtype <= 519:

@@ -233,11 +233,13 @@ static bool pointerIsDevice(const void *p)
 
 Array::Array(Device *d, ANARIDataType arrayType, const void *appMemory, ANARIMemoryDeleter deleter,
     const void *userData, ANARIDataType et, uint64_t n1, uint64_t n2, uint64_t n3)
-    : Object(d, arrayType), elementType(et)
+    : Object(d, arrayType), elementType(et), m_arrayType(arrayType)
 {
   dims[0] = n1;
   dims[1] = n2;
   dims[2] = n3;
+  m_begin = 0;
+  m_end = (size_t)(n1 * n2 * n3);
   if (appMemory) {
     ownership = deleter ? Ownership::CAPTURED : Ownership::SHARED;
     m_data = const_cast<void *>(appMemory);
@@ -289,6 +291,28 @@ void *Array::map()
       if (Object *o = ((Object **)m_data)[i])
         o->refDec(RefType::INTERNAL);
   return m_data;
+}
+
+void Array::commitParameters()
+{ // Array1D::commitParameters / finalize, array/Array1D.cpp:43-66
+  if (m_arrayType != ANARI_ARRAY1D)
+    return;
+  const size_t capacity = totalSize();
+  if (capacity == 0)
+    return;
+  size_t b = (size_t)getParam<uint64_t>("begin", ANARI_UINT64, 0);
+  size_t e = (size_t)getParam<uint64_t>("end", ANARI_UINT64, (uint64_t)capacity);
+  b = std::min(std::max(b, (size_t)0), capacity - 1);
+  e = std::min(std::max(e, (size_t)1), capacity);
+  if (b > e) {
+    report(ANARI_SEVERITY_WARNING, ANARI_STATUS_INVALID_ARGUMENT, "array 'begin' is not less than 'end', swapping values");
+    std::swap(b, e);
+  }
+  if (b != m_begin || e != m_end) {
+    m_begin = b;
+    m_end = e;
+    notifyObservers(); // markDataModified + notifyChangeObservers
+  }
 }
 
 void Array::unmap()
@@ -579,16 +603,16 @@ void Volume::finalize()
     if (m_color->onDevice())
       report(ANARI_SEVERITY_WARNING, ANARI_STATUS_INVALID_ARGUMENT, "tf1D color array must be host memory");
     else if (m_color->elementType == ANARI_FLOAT32_VEC3 || m_color->elementType == ANARI_FLOAT32_VEC4) {
-      color = (const float *)m_color->data();
-      nColor = m_color->totalSize();
+      color = (const float *)m_color->regionData();
+      nColor = m_color->regionSize();
       channels = m_color->elementType == ANARI_FLOAT32_VEC3 ? 3 : 4;
     } else
       report(ANARI_SEVERITY_WARNING, ANARI_STATUS_INVALID_ARGUMENT, "unusable tf1D color array type set (%s)",
           typeName(m_color->elementType));
   }
   if (m_opacity && !m_opacity->onDevice() && m_opacity->elementType == ANARI_FLOAT32) {
-    opacity = (const float *)m_opacity->data();
-    nOpacity = m_opacity->totalSize();
+    opacity = (const float *)m_opacity->regionData();
+    nOpacity = m_opacity->regionSize();
   }
   std::vector<float> tf(DVR_TF_SIZE * 4);
   if (dvr_tf_discretize(color, nColor, channels, opacity, nOpacity, m_uniformColor, m_uniformOpacity, m_valueRange,
@@ -623,8 +647,8 @@ std::vector<Volume *> Group::volumes() const
 {
   std::vector<Volume *> out;
   if (m_volumes)
-    for (size_t i = 0; i < m_volumes->totalSize(); ++i) {
-      Object *o = m_volumes->objectAt(i);
+    for (size_t i = 0; i < m_volumes->regionSize(); ++i) {
+      Object *o = m_volumes->regionObjectAt(i);
       if (o && o->type == ANARI_VOLUME)
         out.push_back(static_cast<Volume *>(o));
     }
@@ -698,14 +722,14 @@ std::vector<FlatInstance> World::flatten(bool warn) const
     out.push_back(fi);
   };
   if (m_zeroVolumes) // the world's own volumes live in an identity "zero instance" (World.cpp:82-96,117-135)
-    for (size_t i = 0; i < m_zeroVolumes->totalSize(); ++i) {
-      Object *o = m_zeroVolumes->objectAt(i);
+    for (size_t i = 0; i < m_zeroVolumes->regionSize(); ++i) {
+      Object *o = m_zeroVolumes->regionObjectAt(i);
       if (o && o->type == ANARI_VOLUME)
         push(static_cast<Volume *>(o), ident, ~0u);
     }
   if (m_instances)
-    for (size_t i = 0; i < m_instances->totalSize(); ++i) {
-      Object *o = m_instances->objectAt(i);
+    for (size_t i = 0; i < m_instances->regionSize(); ++i) {
+      Object *o = m_instances->regionObjectAt(i);
       if (!o || o->type != ANARI_INSTANCE)
         continue;
       Instance *in = static_cast<Instance *>(o);

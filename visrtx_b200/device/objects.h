@@ -135,6 +135,7 @@ struct Array : Object
       ANARIDataType elementType, uint64_t n1, uint64_t n2, uint64_t n3);
   ~Array() override;
   int commitPriority() const override { return 0; }
+  void commitParameters() override; // Array1D "begin" / "end" region (array/Array1D.cpp:43-66)
   void *map();
   void unmap();
   void privatize(); // SHARED array lost its last public ref: copy the app memory (Array.cpp:164-182)
@@ -143,6 +144,11 @@ struct Array : Object
   size_t totalSize() const { return (size_t)dims[0] * dims[1] * dims[2]; }
   size_t totalBytes() const { return totalSize() * sizeOfType(elementType); }
   Object *objectAt(size_t i) const;
+  // the [begin, end) window of a 1-D array: what its consumers see (Array1D::size / begin())
+  size_t regionBegin() const { return m_begin; }
+  size_t regionSize() const { return m_end - m_begin; }
+  const void *regionData() const { return (const uint8_t *)m_data + m_begin * sizeOfType(elementType); }
+  Object *regionObjectAt(size_t i) const { return objectAt(m_begin + i); }
 
   ANARIDataType elementType;
   uint64_t dims[3];
@@ -155,6 +161,8 @@ struct Array : Object
   const void *m_deleterPtr = nullptr;
   std::vector<uint8_t> m_managed;
   bool m_mapped = false;
+  size_t m_begin = 0, m_end = 0;
+  ANARIDataType m_arrayType;
 };
 
 // ---- camera ---------------------------------------------------------------------------------------------------
