@@ -104,3 +104,62 @@ def test_visualize_depth_and_pick_on_a_real_frame():
     want = PO.outline(before, np.asarray(host_ids).ravel(), w, h, 7)
     assert np.array_equal(_host(after, np.uint32), want) and (want != before).sum() > 20
     s.close()
+
+
+def test_tsd_render_pipeline_flow_on_the_device():
+    """The call sequence of TSD's AnariSceneRenderPass (tsd/src/render_pipeline/passes/AnariSceneRenderPass.cpp:
+    79-96 constructor, 139-166 setEnableIDs, 207-262 render / copyFrameData) followed by the outline pass, on the
+    CUDA channel maps: `accumulation` frame parameter, channel.objectId switched on and off with
+    anariUnsetParameter, anariDiscardFrame + wait, anariFrameReady(NO_WAIT) polling, depth-tested composite."""
+    import ctypes as C
+    import torch
+    s = AnariScene(40, 96, 64, "default", 0.5, channels=("depth",))
+    d, f = s.d, s.frame
+    d.set(f, "accumulation", A.BOOL, 1)  # AnariSceneRenderPass.cpp:85 (accepted; accumulation is always on)
+    d.commit(f)
+    w, h = 96, 64
+    n = w * h
+    inf = float("inf")
+    pipe_color = torch.zeros(n, dtype=torch.int32, device="cuda")
+    pipe_depth = torch.full((n,), inf, dtype=torch.float32, device="cuda")
+    pipe_ids = torch.full((n,), -1, dtype=torch.int32, device="cuda")
+
+    def copy_frame_data(enable_ids):
+        cptr, cw, ch, ct = d.map_frame(f, "channel.colorCUDA")
+        dptr, _, _, _ = d.map_frame(f, "channel.depthCUDA")
+        assert (cw, ch, ct) == (w, h, A.UFIXED8_RGBA_SRGB)
+        iptr = d.map_frame(f, "channel.objectIdCUDA")[0] if enable_ids else None
+        capi.post_composite_depth(pipe_color.data_ptr(), pipe_depth.data_ptr(), pipe_ids.data_ptr() if iptr else 0,
+                                  cptr, dptr, iptr or 0, n, True)
+        torch.cuda.synchronize()
+        return iptr
+
+    # first frame: render + wait, then poll-and-resubmit like render() does
+    d.render(f)
+    d.wait(f)
+    assert A.lib.anariFrameReady(d.handle, f, A.NO_WAIT) == 1
+    assert copy_frame_data(False) is None
+    d.render(f)
+    # enable IDs: discard + wait, set the channel, commit, render + wait (setEnableIDs(true))
+    A.lib.anariDiscardFrame(d.handle, f)
+    d.wait(f)
+    d.set(f, "channel.objectId", A.DATA_TYPE, A.UINT32)
+    d.commit(f)
+    d.render(f)
+    d.wait(f)
+    assert copy_frame_data(True)
+    ids = _host(pipe_ids, np.uint32)
+    assert set(np.unique(ids)) == {7, 0xFFFFFFFF}
+    before = _host(pipe_color, np.uint32).copy()
+    capi.post_outline(pipe_color.data_ptr(), pipe_ids.data_ptr(), w, h, 7)
+    torch.cuda.synchronize()
+    assert np.array_equal(_host(pipe_color, np.uint32), PO.outline(before, ids, w, h, 7))
+    # disable IDs again: the channel disappears from the frame (setEnableIDs(false))
+    d.unset(f, "channel.objectId")
+    d.commit(f)
+    d.render(f)
+    d.wait(f)
+    ptr, _, _, t = d.map_frame(f, "channel.objectIdCUDA")
+    assert ptr is None and t == A.UNKNOWN
+    assert not [m for m in d.messages if m[0] <= A.SEVERITY_ERROR], d.messages
+    s.close()
