@@ -28,7 +28,7 @@ int cudaFail(cudaError_t e, const char *what)
 
 void countLaunch(unsigned n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 
-// per-device scheduler counters: a ring of {nextTile, warpsDone} pairs, always zero between launches
+// per-device scheduler counters: a ring of {nextTile, warpsDone, nextRowItem, pad} slots, always zero between launches
 struct DeviceScratch
 {
   unsigned int *sched = nullptr;
@@ -36,6 +36,9 @@ struct DeviceScratch
   int sms = 0;
   InstanceDev *extInstances = nullptr;
   size_t extCapacity = 0;
+  // auxiliary stream of the background sweep + fork / join events (created on first use)
+  cudaStream_t sweepStream = nullptr;
+  cudaEvent_t sweepFork = nullptr, sweepJoin = nullptr;
 };
 static std::mutex g_scratchMutex;
 static DeviceScratch g_scratch[64];
@@ -49,9 +52,9 @@ static DeviceScratch *scratch()
   std::lock_guard<std::mutex> lock(g_scratchMutex);
   DeviceScratch &s = g_scratch[dev];
   if (!s.sched) {
-    if (cudaMalloc(&s.sched, kSchedSlots * 2 * sizeof(unsigned int)) != cudaSuccess)
+    if (cudaMalloc(&s.sched, kSchedSlots * 4 * sizeof(unsigned int)) != cudaSuccess)
       return nullptr;
-    cudaMemset(s.sched, 0, kSchedSlots * 2 * sizeof(unsigned int));
+    cudaMemset(s.sched, 0, kSchedSlots * 4 * sizeof(unsigned int));
     cudaDeviceGetAttribute(&s.sms, cudaDevAttrMultiProcessorCount, dev);
   }
   return &s;
@@ -63,9 +66,50 @@ unsigned int *acquireSchedSlot()
   if (!s)
     return nullptr;
   std::lock_guard<std::mutex> lock(g_scratchMutex);
-  unsigned int *p = s->sched + 2 * (s->next % kSchedSlots);
+  unsigned int *p = s->sched + 4 * (s->next % kSchedSlots);
   s->next++;
   return p;
+}
+
+// Runs the background sweep of one frame on the device's auxiliary stream, ordered after everything already
+// enqueued on `s`; the caller enqueues the frame kernel on `s` and then calls joinBackgroundSweep.
+// The auxiliary stream first waits for everything already enqueued on `s` (fork), the sweep kernel is then enqueued
+// on it before or after the frame kernel's own launch on `s`, and `s` finally waits for the sweep (join).
+static int forkBackgroundSweep(cudaStream_t s)
+{
+  DeviceScratch *sc = scratch();
+  if (!sc)
+    return DVR_ERR_CUDA;
+  {
+    std::lock_guard<std::mutex> lock(g_scratchMutex);
+    if (!sc->sweepStream) {
+      DVR_CUDA(cudaStreamCreateWithFlags(&sc->sweepStream, cudaStreamNonBlocking));
+      DVR_CUDA(cudaEventCreateWithFlags(&sc->sweepFork, cudaEventDisableTiming));
+      DVR_CUDA(cudaEventCreateWithFlags(&sc->sweepJoin, cudaEventDisableTiming));
+    }
+  }
+  DVR_CUDA(cudaEventRecord(sc->sweepFork, s));
+  DVR_CUDA(cudaStreamWaitEvent(sc->sweepStream, sc->sweepFork, 0));
+  return DVR_OK;
+}
+
+static int enqueueBackgroundSweep(const FrameLaunch &L)
+{
+  DeviceScratch *sc = scratch();
+  if (!sc || !sc->sweepStream)
+    return DVR_ERR_CUDA;
+  const int rc = launchBackgroundSweep(L, sc->sweepStream);
+  DVR_CUDA(cudaEventRecord(sc->sweepJoin, sc->sweepStream));
+  return rc;
+}
+
+static int joinBackgroundSweep(cudaStream_t s)
+{
+  DeviceScratch *sc = scratch();
+  if (!sc || !sc->sweepJoin)
+    return DVR_ERR_CUDA;
+  DVR_CUDA(cudaStreamWaitEvent(s, sc->sweepJoin, 0));
+  return DVR_OK;
 }
 
 int smCount()
@@ -1112,6 +1156,35 @@ static int renderImpl(const DvrFrameParams *p, const DvrCamera *camera, const Dv
       L.missY1 = u[3];
     }
   }
+  // Tile window + background sweep: when the rectangle is known (and the launch grid is the pixel grid), the 8x4
+  // tiles cover only the tile-aligned rectangle; everything outside is swept by a second, thin kernel in row-major
+  // order (coalesced 512 B / 128 B stores for the accumulation and the mirrored colour buffer instead of 32-byte
+  // tile rows) on an auxiliary stream, concurrently with the march.
+  L.tileX0 = L.tileY0 = 0;
+  L.tilesW = L.tilesX;
+  L.tilesH = L.tilesY;
+  L.sweepOutside = 0;
+  if (L.missValid && p->checkerboardID < 0 && p->tileRanks <= 1 && !stats) {
+    const int W = (int)p->width, H = (int)p->height;
+    int x0 = std::min(std::max(L.missX0, 0), W), y0 = std::min(std::max(L.missY0, 0), H);
+    int x1 = std::min(std::max(L.missX1, x0), W), y1 = std::min(std::max(L.missY1, y0), H);
+    x0 = x0 / kTileW * kTileW;
+    y0 = y0 / kTileH * kTileH;
+    x1 = std::min((x1 + kTileW - 1) / kTileW * kTileW, (int)L.tilesX * kTileW);
+    y1 = std::min((y1 + kTileH - 1) / kTileH * kTileH, (int)L.tilesY * kTileH);
+    // worth a second launch only when a good part of the frame lies outside
+    if ((size_t)(x1 - x0) * (size_t)(y1 - y0) * 4 <= (size_t)W * (size_t)H * 3) {
+      L.missX0 = x0;
+      L.missY0 = y0;
+      L.missX1 = x1;
+      L.missY1 = y1;
+      L.tileX0 = (uint32_t)(x0 / kTileW);
+      L.tileY0 = (uint32_t)(y0 / kTileH);
+      L.tilesW = (uint32_t)((x1 - x0) / kTileW);
+      L.tilesH = (uint32_t)((y1 - y0) / kTileH);
+      L.sweepOutside = 1;
+    }
+  }
   bool skip = p->useMacrocellSkipping == DVR_SKIP_ON;
   if (p->useMacrocellSkipping == DVR_SKIP_AUTO) // images are identical either way: pick the faster kernel
     for (uint32_t i = 0; i < nInstances; ++i)
@@ -1154,12 +1227,34 @@ static int renderImpl(const DvrFrameParams *p, const DvrCamera *camera, const Dv
   }
 
   int rc = DVR_OK;
-  if (nInstances == 0) {
-    // a world without volumes still clears to the background (Raycast_ptx.cu:139-166 with no hit)
-    L.nInst = 0;
-    rc = launchFrame(L, false, stats, s);
-  } else
-    rc = launchFrame(L, skip, stats, s);
+  {
+    // the fork / join events are per device: one frame at a time enqueues its sweep (host-side enqueue only)
+    static std::mutex sweepMutex;
+    std::unique_lock<std::mutex> sweepLock(sweepMutex, std::defer_lock);
+    // device-only frames: sweep first (wide, short); mirrored frames: march first, then the thin PCIe-bound sweep
+    const bool sweepFirst = L.sweepOutside && !L.fb.outMirror;
+    if (L.sweepOutside) {
+      sweepLock.lock();
+      rc = forkBackgroundSweep(s);
+      if (rc == DVR_OK && sweepFirst)
+        rc = enqueueBackgroundSweep(L);
+    }
+    if (rc == DVR_OK) {
+      if (nInstances == 0) {
+        // a world without volumes still clears to the background (Raycast_ptx.cu:139-166 with no hit)
+        L.nInst = 0;
+        rc = launchFrame(L, false, stats, s);
+      } else
+        rc = launchFrame(L, skip, stats, s);
+    }
+    if (L.sweepOutside && !sweepFirst && rc == DVR_OK)
+      rc = enqueueBackgroundSweep(L);
+    if (L.sweepOutside) {
+      const int rcj = joinBackgroundSweep(s);
+      if (rc == DVR_OK)
+        rc = rcj;
+    }
+  }
 
   if (stats && bitmap) {
     if (rc == DVR_OK)

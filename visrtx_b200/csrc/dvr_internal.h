@@ -46,6 +46,10 @@ struct FrameLaunch
   // Pixels outside [missX0,missX1) x [missY0,missY1) cannot hit any volume (conservative screen rectangle of all
   // instance bounds): they take the background without generating a ray.  missValid == 0: no such knowledge.
   int missValid, missX0, missY0, missX1, missY1;
+  // tiles actually scheduled: the tile-aligned rectangle above when sweepOutside is set (the pixels outside it are
+  // then handled by dvrBackgroundSweepKernel), else the whole launch grid
+  uint32_t tileX0, tileY0, tilesW, tilesH;
+  int sweepOutside;
   CameraDev cam;
   BuffersDev fb;
   int nInst;
@@ -121,6 +125,7 @@ int smCount();
 
 // launchers (defined in the .cu files) --------------------------------------------------------
 int launchFrame(const FrameLaunch &p, bool skip, bool stats, cudaStream_t s);
+int launchBackgroundSweep(const FrameLaunch &p, cudaStream_t s);
 int launchPartial(const PartialLaunch &p, cudaStream_t s);
 int launchResolve(const ResolveLaunch &p, cudaStream_t s);
 int launchCompositeOver(float4 *front, float *frontDepth, const float4 *back, const float *backDepth,

@@ -28,6 +28,7 @@ __device__ __forceinline__ void retireWarp(unsigned int *sched, int lane)
     if (done == totalWarps - 1u) {
       sched[0] = 0u;
       sched[1] = 0u;
+      sched[2] = 0u;
       __threadfence();
     }
   }
@@ -70,6 +71,7 @@ __device__ __forceinline__ void retireWarpAndSignal(unsigned int *sched, int lan
     if (done == totalWarps - 1u) {
       sched[0] = 0u;
       sched[1] = 0u;
+      sched[2] = 0u;
       __threadfence();
       if (sy.nSignal)
         signalPeers(sy);
@@ -255,13 +257,15 @@ __global__ void __launch_bounds__(kBlockThreads, (KIND >= FIELD_NANOVDB ? DVR_OC
 
   MarchStats st{0ull, 0ull};
   unsigned long long raysHit = 0ull;
-  const uint32_t nTiles = P.tilesX * P.tilesY;
+  const uint32_t nTiles = P.tilesW * P.tilesH;
   const bool centered = P.integrator == DVR_INTEGRATOR_RAYCAST;
   const bool initFrame = P.frameID == 0 && P.checkerboardID <= 0;
   const AccumCtx actx{P.width, P.height, P.format, P.frameID, P.checkerboardID, P.fb};
 
   for (uint32_t tile = nextTile(P.sched, lane); tile < nTiles; tile = nextTile(P.sched, lane)) {
-    const uint32_t tyIdx = tile / P.tilesX, txIdx = tile - tyIdx * P.tilesX;
+    // only the tile window is scheduled (the whole launch grid unless the launcher knows the screen rectangle of the
+    // volumes; the pixels outside it are then swept by dvrBackgroundSweepKernel on a second stream)
+    const uint32_t tyIdx = P.tileY0 + tile / P.tilesW, txIdx = P.tileX0 + tile % P.tilesW;
     if (P.tileRanks > 1u && ((tyIdx / P.tileBand) % P.tileRanks) != P.tileRank)
       continue;
    for (int pass = 0; pass < G; ++pass) {
@@ -365,6 +369,44 @@ __global__ void __launch_bounds__(kBlockThreads, (KIND >= FIELD_NANOVDB ? DVR_OC
   retireWarp(P.sched, lane);
 }
 
+// Background sweep: every pixel outside the tile-aligned screen rectangle of the volumes gets what a missed ray
+// produces (see the in-kernel fast path above), one thread per pixel in row-major order — fully coalesced 512 B
+// accumulation and 128 B colour / mirror stores.  Runs on a second stream next to the frame kernel, which then
+// schedules only the tiles inside the rectangle.
+__global__ void __launch_bounds__(256) dvrBackgroundSweepKernel(const __grid_constant__ FrameLaunch P)
+{
+  const bool initFrame = P.frameID == 0 && P.checkerboardID <= 0;
+  const AccumCtx actx{P.width, P.height, P.format, P.frameID, P.checkerboardID, P.fb};
+  const float4 bg = P.background;
+  const size_t n = (size_t)P.width * P.height;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    const uint32_t y = (uint32_t)(i / P.width), x = (uint32_t)(i - (size_t)y * P.width);
+    if ((int)y >= P.missY0 && (int)y < P.missY1 && (int)x >= P.missX0 && (int)x < P.missX1)
+      continue; // the tiles own the inside
+    for (int it = 0; it < P.numIterations; ++it)
+      accumResults(actx, x, y, bg, 1e30f, f3(bg.x, bg.y, bg.z), f3(0.f, 0.f, 0.f), 0u, ~0u, ~0u, it, initFrame && it == 0);
+  }
+}
+
+int launchBackgroundSweep(const FrameLaunch &p, cudaStream_t s)
+{
+  const size_t n = (size_t)p.width * p.height;
+  if (p.fb.outMirror) {
+    // Colour is mirrored to pinned host memory: the sweep is bound by PCIe, not by the SMs.  A thin grid of small
+    // CTAs (64 threads, ~3 K registers) fits beside the frame kernel's two resident CTAs per SM, so its posted
+    // stores drain over the whole march instead of holding a CTA slot of the march hostage.
+    dvrBackgroundSweepKernel<<<(unsigned)smCount() * 2u, 64, 0, s>>>(p);
+  } else {
+    // device-only: a wide grid that is done in a few tens of microseconds and then frees the SMs
+    const unsigned want = (unsigned)((n + 255) / 256);
+    const unsigned cap = (unsigned)smCount() * 2u;
+    dvrBackgroundSweepKernel<<<want < cap ? want : cap, 256, 0, s>>>(p);
+  }
+  DVR_CUDA(cudaGetLastError());
+  countLaunch();
+  return DVR_OK;
+}
+
 template <bool SKIP, bool STATS, bool SINGLE, int KIND, bool DPT>
 static int launchFrameT(const FrameLaunch &p, cudaStream_t s)
 {
@@ -376,7 +418,7 @@ static int launchFrameT(const FrameLaunch &p, cudaStream_t s)
     if (blocksPerSm < 1)
       blocksPerSm = 1;
   }
-  const uint32_t nTiles = p.tilesX * p.tilesY;
+  const uint32_t nTiles = p.tilesW * p.tilesH;
   const uint32_t warpsPerBlock = kBlockThreads / 32;
   uint32_t grid = (uint32_t)(smCount() * blocksPerSm);
   const uint32_t need = (nTiles + warpsPerBlock - 1) / warpsPerBlock;
