@@ -529,6 +529,25 @@ def run_ours(args, torch, dist, rank, world):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         kernel_ms = float(t.item())
 
+    # ---- per-frame distribution (SURVEY 8d timing protocol): progressive accumulation vs single-shot (reset each
+    # frame), one CUDA-event pair per frame, median and p95
+    frame_dist = None
+    if world == 1 and args.extra:
+        frame_dist = {}
+        for label, fid_of in (("progressive", lambda i: 100 + i), ("single_shot", lambda i: 0)):
+            evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(100)]
+            for i in range(5):
+                step(fid_of(i))
+            torch.cuda.synchronize()
+            for i, (a_, b_) in enumerate(evs):
+                a_.record()
+                step(fid_of(i))
+                b_.record()
+            torch.cuda.synchronize()
+            ts = sorted(a_.elapsed_time(b_) for a_, b_ in evs)
+            frame_dist[label] = {"median_ms": ts[len(ts) // 2], "p95_ms": ts[int(len(ts) * 0.95)], "min_ms": ts[0],
+                                 "frames": len(ts)}
+
     # ---- end-to-end with host buffers.  N=1: through the ANARI C API of the device library (what an
     # application calls).  N>1: the multi-GPU driver (C-ABI) with a moved camera every step and the
     # display rank mapping the assembled frame to pinned host memory.
@@ -626,6 +645,8 @@ def run_ours(args, torch, dist, rank, world):
     }
     if clocks is not None:
         out["clocks"] = clocks
+    if frame_dist is not None:
+        out["extra"]["frame_time_ms"] = frame_dist
 
     if rank == 0 and world == 1 and mode == "single" and args.extra:
         out["extra"]["variants"] = measure_variants(args, torch, capi, scenes, field, cam, inst, ninst, fb, stream, stats_t)
