@@ -413,6 +413,7 @@ def run_ours(args, torch, dist, rank, world):
         mode = "single"
 
     t_setup = time.perf_counter()
+    field_commit_ms = None
     vol = None
     if mode == "sort-last":
         from visrtx_b200 import multigpu as _mg
@@ -434,7 +435,12 @@ def run_ours(args, torch, dist, rank, world):
         field.build_macrocells(stream)
     else:
         vol = make_scene(args, torch, device)
+        torch.cuda.synchronize()
+        t_commit = time.perf_counter()
         field = create_field(args, capi, vol, stream)
+        torch.cuda.synchronize()
+        # what a time-varying field pays per update: array allocation + copy into it + macrocell ranges (K4)
+        field_commit_ms = (time.perf_counter() - t_commit) * 1e3
     torch.cuda.synchronize()
     tf = capi.tf_discretize(color=scene_colormap(args))
     volume = capi.Volume.create(field, tf, (0.0, 1.0), args.unit_distance, 0, stream)
@@ -647,6 +653,8 @@ def run_ours(args, torch, dist, rank, world):
         out["clocks"] = clocks
     if frame_dist is not None:
         out["extra"]["frame_time_ms"] = frame_dist
+    if field_commit_ms is not None:
+        out["extra"]["field_commit_ms"] = field_commit_ms
 
     if rank == 0 and world == 1 and mode == "single" and args.extra:
         out["extra"]["variants"] = measure_variants(args, torch, capi, scenes, field, cam, inst, ninst, fb, stream, stats_t)

@@ -238,9 +238,18 @@ int dvr_field_create_structured_slab(const void *data, int dataIsDevice, int dat
  * field's.  Call dvr_field_build_macrocells once all slices are in. */
 int dvr_field_upload_slices(DvrField *f, const void *data, int dataIsDevice, uint32_t firstResidentSlice,
     uint32_t nSlices, void *stream);
+/* Re-finalisation of a whole structuredRegular field whose `data` changed while dims, element type and filter
+ * did not (time-varying / in-situ fields).  The reference re-runs StructuredRegularField::finalize on every
+ * commit of the field — cleanup, cudaMalloc3DArray, copy, grid rebuild (StructuredRegularField.cpp:98-159) —
+ * here the 3-D array, its texture views and the macrocell storage are kept: one copy into the array and one
+ * macrocell build (straight from `data` when that is linear f32 device memory).  origin / spacing may change.
+ * The caller then calls dvr_volume_update on every volume bound to the field (its majorants derive from the
+ * ranges).  DVR_ERR_UNSUPPORTED for slabs, NanoVDB, FLOAT64 or a different dataType: destroy + create instead. */
+int dvr_field_update_structured(DvrField *f, const void *data, int dataIsDevice, int dataType,
+    const float origin[3], const float spacing[3], void *stream);
 /* NvdbRegularField::finalize, spatial_field/NvdbRegularField.cpp:64-160: `gridData` is one serialized
- * NanoVDB grid (the ANARI "nanovdb" field's UINT8 `data` array); GridType::Float only (the quantised
- * Fp4/Fp8/Fp16/FpN types of sampleSpatialField.h:107-109 are not built yet -> DVR_ERR_UNSUPPORTED).  The
+ * NanoVDB grid (the ANARI "nanovdb" field's UINT8 `data` array); GridType Float, Fp4, Fp8, Fp16 and FpN
+ * (sampleSpatialField.h:107-109), anything else -> DVR_ERR_UNSUPPORTED.  The
  * buffer is copied to 32-byte aligned device memory; bounds = the grid's world bounding box, step =
  * min(voxelSize)/2; macrocells cover the index bounding box. */
 int dvr_field_create_nanovdb(const void *gridData, size_t bytes, int dataIsDevice, void *stream, DvrField **out);

@@ -2,6 +2,7 @@
 time-varying CUDA-pointer fields as the reference's animated_volume demo drives them
 (tsd/apps/interactive/demos/animated_volume/SolverControls.cpp:159-214: in-place CUDA updates between map/unmap,
 and swapping the field's `data` between two device arrays)."""
+import ctypes as C
 import os
 
 import numpy as np
@@ -135,7 +136,100 @@ def test_time_varying_cuda_pointer_field():
     first.render()
     want0, _, _, _ = first.d.map_frame(first.frame, "channel.color")
     assert np.array_equal(img2, want0)
+    # (3) a data array of another shape cannot refresh in place: field and volume are rebuilt
+    m = 24
+    small = scenes.marschner_lobb_np(m)
+    buf_s = torch.from_numpy(small).cuda()
+    other_s = d.new_array3d_device(buf_s.data_ptr(), A.FLOAT32, m, m, m)
+    d.set(s.field, "data", A.ARRAY3D, other_s)
+    d.commit(s.field)
+    img3, n3 = shot(1)
+    assert n3 == 0 and not np.array_equal(img3, img2)
+    ref3 = AnariScene(m, 80, 60, "default", 0.5, vox=small)
+    sp = 2.0 / (n - 1)
+    ref3.d.set(ref3.field, "spacing", A.FLOAT32_VEC3, (sp, sp, sp))
+    ref3.d.commit(ref3.field)
+    ref3.d.set(ref3.volume, "unitDistance", A.FLOAT32, sp)
+    ref3.d.commit(ref3.volume)
+    for k in ("position", "direction", "up"):
+        ref3.d.set(ref3.camera, k, A.FLOAT32_VEC3, getattr(s.pose, k))
+    ref3.d.commit(ref3.camera)
+    ref3.render()
+    want3, _, _, _ = ref3.d.map_frame(ref3.frame, "channel.color")
+    assert np.array_equal(img3, want3)
+    # ... and back to the original shape
+    d.set(s.field, "data", A.ARRAY3D, other)
+    d.commit(s.field)
+    img4, _ = shot(1)
+    assert np.array_equal(img4, want0)
     assert not _errors(d), d.messages
     d.release(other)
-    for x in (s, ref, first):
+    d.release(other_s)
+    for x in (s, ref, first, ref3):
         x.close()
+
+
+@pytest.mark.parametrize("elem", ["f32_device", "f32_host", "ufixed8_host", "f16_device"])
+def test_field_update_in_place_equals_fresh_field(elem):
+    """dvr_field_update_structured + dvr_volume_update == destroying and re-creating field and volume: same frame,
+    same macrocell ranges, for device and host data, including a change of origin / spacing."""
+    import torch
+    n = 40
+    a0 = scenes.marschner_lobb_np(n)
+    a1 = np.ascontiguousarray(a0[::-1, ::-1, :])
+    dt = capi.DVR_FLOAT32
+    if elem == "ufixed8_host":
+        a0, a1 = ((a * 255).astype(np.uint8) for a in (a0, a1))
+        dt = capi.DVR_UFIXED8
+    elif elem == "f16_device":
+        a0, a1 = (a.astype(np.float16) for a in (a0, a1))
+        dt = capi.DVR_FLOAT16
+    on_dev = elem.endswith("device")
+    keep = []
+
+    def ptr(a):
+        if on_dev:
+            t = torch.from_numpy(a).cuda()
+            keep.append(t)
+            return t.data_ptr()
+        return a.ctypes.data
+
+    sp0, sp1 = 2.0 / (n - 1), 1.5 / (n - 1)
+    tf = capi.tf_discretize(color=scenes.tsd_default_colormap(256))
+    f = capi.Field.create_structured(ptr(a0), on_dev, dt, (n, n, n), (-1, -1, -1), (sp0,) * 3)
+    v = capi.Volume.create(f, tf, (0.0, 1.0), sp0, 3)
+    f.update_structured(ptr(a1), on_dev, dt, (-0.75, -0.75, -0.75), (sp1,) * 3)
+    v.update(tf, (0.0, 1.0), sp0, 3)
+    g = capi.Field.create_structured(ptr(a1), on_dev, dt, (n, n, n), (-0.75, -0.75, -0.75), (sp1,) * 3)
+    w = capi.Volume.create(g, tf, (0.0, 1.0), sp0, 3)
+    assert f.bounds() == g.bounds() and f.step_size() == g.step_size()
+
+    def ranges(fld):
+        (gx, gy, gz), p = fld.macrocells()
+        r = torch.empty((gz, gy, gx, 2), dtype=torch.float32, device="cuda")
+        torch.cuda.synchronize()
+        C.CDLL("libcudart.so").cudaMemcpy(C.c_void_p(r.data_ptr()), C.c_void_p(p), C.c_size_t(r.numel() * 4), C.c_int(3))
+        return r.cpu().numpy()
+
+    assert np.array_equal(ranges(f), ranges(g))
+    pose = scenes.orbit_camera((-1, -1, -1), (1, 1, 1), 96, 64)
+    cam = capi.camera_perspective(pose.position, pose.direction, pose.up, pose.fovy, pose.aspect)
+    npx = 96 * 64
+    imgs = []
+    for vol in (v, w):
+        inst, ni = capi.make_instances([vol], None, [0])
+        accum = torch.zeros((npx, 4), dtype=torch.float32, device="cuda")
+        color = torch.zeros(npx, dtype=torch.int32, device="cuda")
+        fb = capi.frame_buffers(accum.data_ptr(), color.data_ptr())
+        params = capi.frame_params(96, 64, capi.DVR_FORMAT_UFIXED8_RGBA_SRGB, capi.DVR_INTEGRATOR_RAYCAST, background=(0.1, 0.1, 0.1, 1.0),
+                                   volume_sampling_rate=0.5)
+        capi.render(params, cam, inst, ni, fb)
+        torch.cuda.synchronize()
+        imgs.append(color.cpu().numpy())
+    assert np.array_equal(imgs[0], imgs[1])
+    assert len(np.unique(imgs[0])) > 50
+    # a slab, a NanoVDB grid or another element type do not update in place
+    with pytest.raises(capi.DvrError):
+        f.update_structured(ptr(a1), on_dev, capi.DVR_FIXED16, (0, 0, 0), (1, 1, 1))
+    for o in (v, w, f, g):
+        o.destroy()

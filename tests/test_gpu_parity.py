@@ -381,3 +381,47 @@ def test_partial_march_confined_to_the_screen_rectangle_of_the_bounds():
         assert np.array_equal(cr[written], fr[written]) and np.array_equal(cd[written], fd[written]), ci
         culled_any |= bool((~written).any())
     assert culled_any  # the far cameras really skip most of the frame
+
+
+def _field_ranges(f):
+    import ctypes
+    import torch
+    (gx, gy, gz), ptr = f.macrocells()
+    rng = torch.empty((gz, gy, gx, 2), dtype=torch.float32, device="cuda")
+    torch.cuda.synchronize()
+    ctypes.CDLL("libcudart.so").cudaMemcpy(ctypes.c_void_p(rng.data_ptr()), ctypes.c_void_p(ptr),
+                                           ctypes.c_size_t(rng.numel() * 4), ctypes.c_int(3))
+    return rng.cpu().numpy()
+
+
+@pytest.mark.parametrize("dims", [(70, 33, 50), (128, 40, 37), (260, 19, 65), (16, 16, 16), (4, 1, 1), (516, 35, 34)])
+def test_macrocell_build_from_device_memory_matches_texture_build(dims):
+    """K4 has two builds: through the point-sampled array (host data, fixed point, slabs) and the separable one straight
+    from linear f32 device memory (in-situ / time-varying fields).  Same ranges, bit for bit, NaNs dropped alike;
+    dims cover the scalar x pass (x % 4 != 0), the vectorised one, several 128-voxel segments and ragged last cells."""
+    import torch
+    nx, ny, nz = dims
+    g = np.random.default_rng(nx * 7 + ny)
+    vox = g.standard_normal((nz, ny, nx)).astype(np.float32)
+    if vox.size > 64:
+        vox.reshape(-1)[g.integers(0, vox.size, 5)] = np.nan
+    dev = torch.from_numpy(vox).cuda()
+    a = capi.Field.create_structured(vox.ctypes.data, False, capi.DVR_FLOAT32, dims, (0, 0, 0), (1, 1, 1))
+    b = capi.Field.create_structured(dev.data_ptr(), True, capi.DVR_FLOAT32, dims, (0, 0, 0), (1, 1, 1))
+    # an unaligned device pointer takes the scalar x pass
+    pad = torch.empty(vox.size + 1, dtype=torch.float32, device="cuda")
+    pad[1:] = dev.reshape(-1)
+    c = capi.Field.create_structured(pad.data_ptr() + 4, True, capi.DVR_FLOAT32, dims, (0, 0, 0), (1, 1, 1))
+    try:
+        ra, rb, rc = _field_ranges(a), _field_ranges(b), _field_ranges(c)
+        assert ra.shape == ((nz + 15) // 16, (ny + 15) // 16, (nx + 15) // 16, 2)
+        assert np.array_equal(ra, rb) and np.array_equal(ra, rc)
+        for cz, cy, cx in np.ndindex(*ra.shape[:3]):
+            blk = vox[max(cz * 16 - 1, 0):cz * 16 + 18, max(cy * 16 - 1, 0):cy * 16 + 18,
+                      max(cx * 16 - 1, 0):cx * 16 + 18]
+            assert rb[cz, cy, cx, 0] == np.nanmin(blk) and rb[cz, cy, cx, 1] == np.nanmax(blk)
+        assert a.value_range() == b.value_range()
+    finally:
+        a.destroy()
+        b.destroy()
+        c.destroy()

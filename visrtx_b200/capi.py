@@ -29,7 +29,7 @@ DVR_SKIP_OFF, DVR_SKIP_ON, DVR_SKIP_AUTO = 0, 1, 2
 EXPORTED_SYMBOLS = [
     "dvr_last_error", "dvr_version", "dvr_device_count", "dvr_set_device", "dvr_device_info",
     "dvr_camera_perspective", "dvr_camera_orthographic", "dvr_tf_discretize",
-    "dvr_field_create_structured", "dvr_field_create_structured_slab", "dvr_field_upload_slices", "dvr_field_create_nanovdb",
+    "dvr_field_create_structured", "dvr_field_create_structured_slab", "dvr_field_upload_slices", "dvr_field_update_structured", "dvr_field_create_nanovdb",
     "dvr_field_destroy",
     "dvr_field_bounds", "dvr_field_step_size", "dvr_field_device_bytes", "dvr_field_build_macrocells",
     "dvr_field_macrocells", "dvr_field_value_range",
@@ -227,6 +227,13 @@ class Field:
                       stream: int = 0) -> None:
         _check(lib.dvr_field_upload_slices(self.handle, C.c_void_p(data_ptr), C.c_int(1 if is_device else 0),
                                            C.c_uint32(first_resident_slice), C.c_uint32(n_slices), C.c_void_p(stream)))
+
+    def update_structured(self, data_ptr: int, is_device: bool, data_type: int, origin, spacing,
+                          stream: int = 0) -> None:
+        """In-place refresh of a whole structured field (same dims / type / filter); volumes bound to it then need
+        Volume.update."""
+        _check(lib.dvr_field_update_structured(self.handle, C.c_void_p(data_ptr), C.c_int(1 if is_device else 0),
+                                               C.c_int(data_type), _f3(*origin), _f3(*spacing), C.c_void_p(stream)))
 
     def destroy(self) -> None:
         if self.handle:

@@ -2,6 +2,7 @@
 // Host-side object state (3-D array + texture objects, macrocell buffers, TF tables) and the
 // parameter translation from the POD structs of the C-ABI to the kernel parameter blocks.
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <atomic>
 #include <mutex>
@@ -39,6 +40,10 @@ struct DeviceScratch
   // auxiliary stream of the background sweep + fork / join events (created on first use)
   cudaStream_t sweepStream = nullptr;
   cudaEvent_t sweepFork = nullptr, sweepJoin = nullptr;
+  // stream-ordered scratch (macrocell build intermediates, visibility bitmaps ...): a private pool that keeps its
+  // pages across synchronisations.  The default pool hands freed memory back to the driver at every sync, which
+  // costs milliseconds per field refresh.
+  cudaMemPool_t pool = nullptr;
 };
 static std::mutex g_scratchMutex;
 static DeviceScratch g_scratch[64];
@@ -58,6 +63,34 @@ static DeviceScratch *scratch()
     cudaDeviceGetAttribute(&s.sms, cudaDevAttrMultiProcessorCount, dev);
   }
   return &s;
+}
+
+cudaError_t scratchAllocAsync(void **p, size_t bytes, cudaStream_t stream)
+{
+  DeviceScratch *s = scratch();
+  if (s) {
+    std::lock_guard<std::mutex> lock(g_scratchMutex);
+    if (!s->pool) {
+      int dev = 0;
+      cudaGetDevice(&dev);
+      cudaMemPoolProps props;
+      std::memset(&props, 0, sizeof(props));
+      props.allocType = cudaMemAllocationTypePinned;
+      props.handleTypes = cudaMemHandleTypeNone;
+      props.location.type = cudaMemLocationTypeDevice;
+      props.location.id = dev;
+      if (cudaMemPoolCreate(&s->pool, &props) == cudaSuccess) {
+        uint64_t keep = 1ull << 30;
+        cudaMemPoolSetAttribute(s->pool, cudaMemPoolAttrReleaseThreshold, &keep);
+      } else {
+        cudaGetLastError();
+        s->pool = nullptr;
+      }
+    }
+  }
+  if (s && s->pool)
+    return cudaMallocFromPoolAsync(p, bytes, s->pool, stream);
+  return cudaMallocAsync(p, bytes, stream);
 }
 
 unsigned int *acquireSchedSlot()
@@ -130,6 +163,7 @@ struct DvrField
   cudaArray_t array = nullptr;
   cudaTextureObject_t tex = 0;      // filtering view (clamp, normalised)
   cudaTextureObject_t pointTex = 0; // point view, unnormalised (macrocell build)
+  cudaSurfaceObject_t surf = 0;     // whole f32 fields: store view, so a refresh from device memory is one fused pass
   FieldDev dev{};
   float2 *ranges = nullptr;
   size_t nCells = 0;
@@ -137,6 +171,7 @@ struct DvrField
   size_t texElementSize = 0;
   void *nvdbBlob = nullptr; // NanoVDB fields: device copy of the serialized grid
   int device = 0;
+  int dataType = -1; // structured fields: the DvrDataType handed to create
 };
 
 struct DvrVolume
@@ -391,6 +426,21 @@ static size_t elementSize(int t)
   }
 }
 
+// origin / spacing derived members of a structured field, StructuredRegularField.cpp:166-189
+static void setFieldGeometry(FieldDev &d, const uint32_t gdims[3], const float origin[3], const float spacing[3])
+{
+  d.origin = v3(origin);
+  d.spacing = v3(spacing);
+  d.dims = make_int3((int)gdims[0], (int)gdims[1], (int)gdims[2]);
+  // 1 / (spacing * dims), StructuredRegularField.cpp:188-189
+  d.invSpacing = make_float3(1.f / (spacing[0] * (float)gdims[0]), 1.f / (spacing[1] * (float)gdims[1]),
+      1.f / (spacing[2] * (float)gdims[2]));
+  d.boundsLo = d.origin;
+  d.boundsHi = make_float3(origin[0] + ((float)gdims[0] - 1.f) * spacing[0],
+      origin[1] + ((float)gdims[1] - 1.f) * spacing[1], origin[2] + ((float)gdims[2] - 1.f) * spacing[2]);
+  d.stepSize = std::fmin(std::fmin(spacing[0] / 2.f, spacing[1] / 2.f), spacing[2] / 2.f);
+}
+
 static int createFieldImpl(const void *data, int dataIsDevice, int dataType, const uint32_t gdims[3],
     uint32_t zBegin, uint32_t zEnd, const float origin[3], const float spacing[3], int filter, void *stream,
     DvrField **out)
@@ -463,14 +513,33 @@ static int createFieldImpl(const void *data, int dataIsDevice, int dataType, con
   else if (texType == DVR_FIXED8 || texType == DVR_FIXED16)
     kind = cudaChannelFormatKindSigned;
   const cudaChannelFormatDesc desc = cudaCreateChannelDesc((int)texEsz * 8, 0, 0, 0, kind);
-  cudaError_t e = cudaMalloc3DArray(&f->array, &desc, make_cudaExtent(gdims[0], gdims[1], texDepth));
+  // whole f32 fields get a surface view as well: device-memory input is then uploaded by the macrocell pass itself
+  static const bool surfaceUpload = [] {
+    const char *v = std::getenv("DVR_B200_SURFACE_UPLOAD");
+    return !(v && v[0] == '0');
+  }();
+  const bool wantSurface = surfaceUpload && whole && dataType == DVR_FLOAT32;
+  cudaError_t e = cudaMalloc3DArray(&f->array, &desc, make_cudaExtent(gdims[0], gdims[1], texDepth),
+      wantSurface ? cudaArraySurfaceLoadStore : cudaArrayDefault);
   if (e != cudaSuccess) {
     cudaFree(converted);
     delete f;
     return cudaFail(e, "cudaMalloc3DArray");
   }
   f->texElementSize = texEsz;
-  if (!deferredUpload) {
+  if (wantSurface) {
+    cudaResourceDesc sd;
+    std::memset(&sd, 0, sizeof(sd));
+    sd.resType = cudaResourceTypeArray;
+    sd.res.array.array = f->array;
+    if (cudaCreateSurfaceObject(&f->surf, &sd) != cudaSuccess) {
+      cudaGetLastError();
+      f->surf = 0;
+    }
+  }
+  const bool fusedUpload = !deferredUpload && f->surf && dataIsDevice
+      && macrocellLinearIsVectorisable(data, make_int3((int)gdims[0], (int)gdims[1], (int)gdims[2]));
+  if (!deferredUpload && !fusedUpload) {
     cudaMemcpy3DParms cp;
     std::memset(&cp, 0, sizeof(cp));
     cp.srcPtr = make_cudaPitchedPtr(const_cast<void *>(src), gdims[0] * texEsz, gdims[0], gdims[1]);
@@ -483,6 +552,8 @@ static int createFieldImpl(const void *data, int dataIsDevice, int dataType, con
   }
   cudaFree(converted);
   if (e != cudaSuccess) {
+    if (f->surf)
+      cudaDestroySurfaceObject(f->surf);
     cudaFreeArray(f->array);
     delete f;
     return cudaFail(e, "cudaMemcpy3D");
@@ -513,16 +584,8 @@ static int createFieldImpl(const void *data, int dataIsDevice, int dataType, con
 
   FieldDev &d = f->dev;
   d.tex = f->tex;
-  d.origin = v3(origin);
-  d.spacing = v3(spacing);
-  d.dims = make_int3((int)gdims[0], (int)gdims[1], (int)gdims[2]);
-  // 1 / (spacing * dims), StructuredRegularField.cpp:188-189
-  d.invSpacing = make_float3(1.f / (spacing[0] * (float)gdims[0]), 1.f / (spacing[1] * (float)gdims[1]),
-      1.f / (spacing[2] * (float)gdims[2]));
-  d.boundsLo = d.origin;
-  d.boundsHi = make_float3(origin[0] + ((float)gdims[0] - 1.f) * spacing[0],
-      origin[1] + ((float)gdims[1] - 1.f) * spacing[1], origin[2] + ((float)gdims[2] - 1.f) * spacing[2]);
-  d.stepSize = std::fmin(std::fmin(spacing[0] / 2.f, spacing[1] / 2.f), spacing[2] / 2.f);
+  f->dataType = dataType;
+  setFieldGeometry(d, gdims, origin, spacing);
   d.zOwnBegin = whole ? 0 : (int)zBegin;
   d.zOwnEnd = whole ? (int)gdims[2] : (int)zEnd;
   d.zTexBegin = (int)zTexBegin;
@@ -535,7 +598,16 @@ static int createFieldImpl(const void *data, int dataIsDevice, int dataType, con
     return cudaFail(e, "cudaMalloc(macrocell ranges)");
   }
   d.valueRanges = f->ranges;
-  const int rc = deferredUpload ? DVR_OK : dvr_field_build_macrocells(f, stream);
+  int rc = DVR_OK;
+  if (!deferredUpload) {
+    // whole f32 field handed over as linear device memory (ANARI_NV_ARRAY_CUDA, in-situ updates): separable build
+    // straight from that memory; everything else reads the array through its point-sampled view
+    if (dataIsDevice && dataType == DVR_FLOAT32 && whole)
+      rc = launchMacrocellBuildLinear((const float *)data, d.dims, d.gridDims, f->ranges, fusedUpload ? f->surf : 0,
+          (cudaStream_t)stream);
+    else
+      rc = dvr_field_build_macrocells(f, stream);
+  }
   if (rc != DVR_OK) {
     dvr_field_destroy(f);
     return rc;
@@ -723,12 +795,43 @@ int dvr_field_upload_slices(DvrField *f, const void *data, int dataIsDevice, uin
   return DVR_OK;
 }
 
+int dvr_field_update_structured(DvrField *f, const void *data, int dataIsDevice, int dataType, const float origin[3],
+    const float spacing[3], void *stream)
+{
+  if (!f || !data || !origin || !spacing) {
+    setError("dvr_field_update_structured: null argument");
+    return DVR_ERR_INVALID_ARGUMENT;
+  }
+  const FieldDev &d0 = f->dev;
+  if (d0.kind != FIELD_STRUCTURED || d0.zTexBegin != 0 || d0.texDepth != d0.dims.z || dataType != f->dataType
+      || dataType == DVR_FLOAT64) {
+    setError("dvr_field_update_structured: only a whole structuredRegular field of unchanged element type (not "
+             "FLOAT64) updates in place; destroy and create instead");
+    return DVR_ERR_UNSUPPORTED;
+  }
+  cudaStream_t s = (cudaStream_t)stream;
+  const uint32_t gdims[3] = {(uint32_t)d0.dims.x, (uint32_t)d0.dims.y, (uint32_t)d0.dims.z};
+  setFieldGeometry(f->dev, gdims, origin, spacing);
+  const bool linear = dataIsDevice && dataType == DVR_FLOAT32;
+  const bool fused = linear && f->surf && macrocellLinearIsVectorisable(data, f->dev.dims);
+  if (!fused) {
+    const int up = dvr_field_upload_slices(f, data, dataIsDevice, 0, gdims[2], stream);
+    if (up != DVR_OK)
+      return up;
+  }
+  if (linear)
+    return launchMacrocellBuildLinear((const float *)data, f->dev.dims, f->dev.gridDims, f->ranges,
+        fused ? f->surf : 0, s);
+  return dvr_field_build_macrocells(f, stream);
+}
+
 int dvr_field_destroy(DvrField *f)
 {
   if (!f)
     return DVR_OK;
   if (f->tex) cudaDestroyTextureObject(f->tex);
   if (f->pointTex) cudaDestroyTextureObject(f->pointTex);
+  if (f->surf) cudaDestroySurfaceObject(f->surf);
   if (f->array) cudaFreeArray(f->array);
   if (f->ranges) cudaFree(f->ranges);
   if (f->nvdbBlob) cudaFree(f->nvdbBlob);
@@ -846,7 +949,7 @@ int dvr_volume_update(DvrVolume *v, const float *tfRgba, const float valueRange[
     return rc3;
   // how much of the volume skipping could exploit (drives DVR_SKIP_AUTO)
   unsigned long long *dCount = nullptr, hCount = 0;
-  DVR_CUDA(cudaMallocAsync(&dCount, sizeof(unsigned long long), s));
+  DVR_CUDA(scratchAllocAsync((void **)&dCount, sizeof(unsigned long long), s));
   DVR_CUDA(cudaMemsetAsync(dCount, 0, sizeof(unsigned long long), s));
   const int rc4 = launchCountEmpty(v->maxOpacities, v->field->nCells, dCount, s);
   DVR_CUDA(cudaMemcpyAsync(&hCount, dCount, sizeof(hCount), cudaMemcpyDeviceToHost, s));
@@ -1197,7 +1300,7 @@ static int renderImpl(const DvrFrameParams *p, const DvrCamera *camera, const Dv
     for (uint32_t i = 0; i < nInstances; ++i)
       fillInstance(instances[i], tmp[i]);
     InstanceDev *ext = nullptr;
-    DVR_CUDA(cudaMallocAsync(&ext, nInstances * sizeof(InstanceDev), s));
+    DVR_CUDA(scratchAllocAsync((void **)&ext, nInstances * sizeof(InstanceDev), s));
     DVR_CUDA(cudaMemcpyAsync(ext, tmp.data(), nInstances * sizeof(InstanceDev), cudaMemcpyHostToDevice, s));
     DVR_CUDA(cudaStreamSynchronize(s));
     L.ext = ext;
@@ -1219,7 +1322,7 @@ static int renderImpl(const DvrFrameParams *p, const DvrCamera *camera, const Dv
     if (nInstances >= 1) {
       const size_t nCells = instances[0].volume->field->nCells;
       nWords = (nCells + 31) / 32;
-      DVR_CUDA(cudaMallocAsync(&bitmap, nWords * 4, s));
+      DVR_CUDA(scratchAllocAsync((void **)&bitmap, nWords * 4, s));
       DVR_CUDA(cudaMemsetAsync(bitmap, 0, nWords * 4, s));
     }
     L.stats = statsDev;
@@ -1368,7 +1471,7 @@ static int renderPartialImpl(const DvrFrameParams *p, const DvrCamera *camera, c
   if (statsDev) {
     DVR_CUDA(cudaMemsetAsync(statsDev, 0, sizeof(DvrRenderStats), s));
     nWords = (instance->volume->field->nCells + 31) / 32;
-    DVR_CUDA(cudaMallocAsync(&bitmap, nWords * 4, s));
+    DVR_CUDA(scratchAllocAsync((void **)&bitmap, nWords * 4, s));
     DVR_CUDA(cudaMemsetAsync(bitmap, 0, nWords * 4, s));
     L.stats = statsDev;
     L.cellBitmap = bitmap;

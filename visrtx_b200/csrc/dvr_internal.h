@@ -122,6 +122,8 @@ int cudaFail(cudaError_t e, const char *what);
 void countLaunch(unsigned n = 1);
 unsigned int *acquireSchedSlot(); // device pair of counters, zero on entry to every launch
 int smCount();
+// stream-ordered scratch from the library's own pool (released with cudaFreeAsync)
+cudaError_t scratchAllocAsync(void **p, size_t bytes, cudaStream_t stream);
 
 // launchers (defined in the .cu files) --------------------------------------------------------
 int launchFrame(const FrameLaunch &p, bool skip, bool stats, cudaStream_t s);
@@ -136,6 +138,9 @@ int launchWaitFlags(const unsigned int *flags, uint32_t n, uint32_t value, unsig
 int launchScaleVec3(const float *in, float *out, size_t n, float scale, cudaStream_t s);
 int launchMacrocellBuild(cudaTextureObject_t pointTex, int3 dims, int zTexBegin, int texDepth, int3 gridDims,
     float2 *ranges, cudaStream_t s);
+bool macrocellLinearIsVectorisable(const void *voxels, int3 dims);
+int launchMacrocellBuildLinear(const float *voxels, int3 dims, int3 gridDims, float2 *ranges,
+    cudaSurfaceObject_t uploadTo, cudaStream_t s);
 int launchMacrocellBuildNvdb(const FieldDev &f, float2 *ranges, cudaStream_t s);
 // value ranges on the delta-tracking grid: gridDims cells dividing `spanVoxels` voxel units evenly per axis
 int launchDdaRangeBuild(const FieldDev &f, cudaTextureObject_t pointTex, int3 gridDims, float3 cellWidthVoxels,

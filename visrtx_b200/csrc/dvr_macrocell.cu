@@ -7,6 +7,8 @@
 // index falls in [16c, 16c+15] reads voxels [16c, 16c+16]; the extra voxel on either side absorbs
 // the difference between the marcher's fp32 cell test and the texture unit's own coordinate rounding.  The reference's build samples the wrong coordinates
 //  and is deliberately not reproduced.
+#include <algorithm>
+
 #include "dvr_internal.h"
 #include "dvr_march.cuh"
 
@@ -59,6 +61,223 @@ int launchMacrocellBuild(cudaTextureObject_t pointTex, int3 dims, int zTexBegin,
   dvrMacrocellRangeKernel<<<grid, 256, 0, s>>>(pointTex, dims, zTexBegin, texDepth, gridDims, ranges);
   DVR_CUDA(cudaGetLastError());
   countLaunch();
+  return DVR_OK;
+}
+
+// ---- K4, separable variant for f32 fields that arrive as LINEAR device memory (in-situ / time-varying fields) ---
+// The apron window [16c-1, 16c+17] is a box, so min/max separate: x (reads every voxel once, coalesced), then y,
+// then z over ever smaller intermediates.  Same values as the texture variant (min/max of the same floats), a
+// fraction of its time: the field re-finalisation of a time-varying volume is dominated by this build.
+__global__ void __launch_bounds__(256) dvrRangeXKernel(const float *__restrict__ vox, int3 dims, int gx, int z0, int nz,
+    float2 *__restrict__ outX)
+{ // one thread per (cx, y, z): consecutive threads = consecutive cells of one row
+  const size_t n = (size_t)gx * dims.y * nz;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    const int cx = (int)(i % gx), y = (int)((i / gx) % dims.y), z = z0 + (int)(i / ((size_t)gx * dims.y));
+    const int x0 = max(cx * 16 - 1, 0), x1 = min(cx * 16 + 17, dims.x - 1);
+    const float *row = vox + ((size_t)z * dims.y + y) * dims.x;
+    float lo = FLT_MAX, hi = -FLT_MAX;
+    for (int x = x0; x <= x1; ++x) {
+      const float v = __ldg(row + x);
+      lo = fminf(lo, v); // fminf / fmaxf drop NaNs like the texture variant
+      hi = fmaxf(hi, v);
+    }
+    outX[i] = make_float2(lo, hi);
+  }
+}
+
+__global__ void __launch_bounds__(256) dvrRangeYKernel(const float2 *__restrict__ inX, int ny, int gx, int gy, int nz,
+    float2 *__restrict__ outY)
+{ // one thread per (cx, cy, z)
+  const size_t n = (size_t)gx * gy * nz;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    const int cx = (int)(i % gx), cy = (int)((i / gx) % gy), z = (int)(i / ((size_t)gx * gy));
+    const int y0 = max(cy * 16 - 1, 0), y1 = min(cy * 16 + 17, ny - 1);
+    float lo = FLT_MAX, hi = -FLT_MAX;
+    for (int y = y0; y <= y1; ++y) {
+      const float2 r = inX[((size_t)z * ny + y) * gx + cx];
+      lo = fminf(lo, r.x);
+      hi = fmaxf(hi, r.y);
+    }
+    outY[i] = make_float2(lo, hi);
+  }
+}
+
+__global__ void __launch_bounds__(256) dvrRangeZKernel(const float2 *__restrict__ inY, int nz, int3 g, float2 *__restrict__ ranges)
+{ // one thread per cell
+  const size_t n = (size_t)g.x * g.y * g.z;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    const int cz = (int)(i / ((size_t)g.x * g.y));
+    const size_t xy = i % ((size_t)g.x * g.y);
+    const int z0 = max(cz * 16 - 1, 0), z1 = min(cz * 16 + 17, nz - 1);
+    float lo = FLT_MAX, hi = -FLT_MAX;
+    for (int z = z0; z <= z1; ++z) {
+      const float2 r = inY[(size_t)z * g.x * g.y + xy];
+      lo = fminf(lo, r.x);
+      hi = fmaxf(hi, r.y);
+    }
+    ranges[i] = make_float2(lo, hi);
+  }
+}
+
+// x and y passes fused, optionally with the upload into the 3-D array (UPLOAD): one CTA per (128-voxel segment,
+// 16-row band, kRangeSlicesPerCta slices) = 8 cells of each of those slices.  Its 8 warps share the band's <= 19 rows (apron rows included); every
+// lane loads one float4 (full 512-byte requests), stores it to the array through the surface when the row belongs to
+// the band proper, and the x reduction runs on shuffles (aprons: voxel 16c-1 from the lane on the left,
+// 16c+16 / 16c+17 from the next group, from memory only at segment ends); rows are then folded in registers
+// and across warps in shared memory.  The apron rows are fetched by two bands, close in launch order, from L2.
+constexpr int kRangeSlicesPerCta = 4;
+
+template <bool UPLOAD>
+__global__ void __launch_bounds__(256) dvrRangeXYKernel(const float *__restrict__ vox, cudaSurfaceObject_t surf,
+    int3 dims, int gx, int gy, float2 *__restrict__ outY)
+{
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int nseg = (dims.x + 127) >> 7;
+  const int seg = blockIdx.x % nseg;
+  const int cy = (blockIdx.x / nseg) % gy;
+  const int zFirst = (blockIdx.x / (nseg * gy)) * kRangeSlicesPerCta;
+  const int zLast = min(zFirst + kRangeSlicesPerCta, dims.z) - 1;
+  const int y0 = max(cy * 16 - 1, 0), y1 = min(cy * 16 + 17, dims.y - 1);
+  const int x = (seg << 7) + (lane << 2);
+  const bool in = x < dims.x;
+  const int nextLane = (lane & ~3) + 4;
+  __shared__ float2 part[2][8][8];
+
+  // this warp's rows of one slice: y0 + warp + 8k, k < 3.  The loads of slice z+1 are in flight while slice z is
+  // stored and reduced (the pass is latency-bound otherwise: one dependent load -> store chain per warp).
+  float4 cur[3], nxt[3];
+  auto fetch = [&](int z, float4 (&v)[3]) {
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      const int y = y0 + warp + 8 * k;
+      v[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (in && y <= y1)
+        v[k] = __ldg(reinterpret_cast<const float4 *>(vox + ((size_t)z * dims.y + y) * dims.x + x));
+    }
+  };
+  fetch(zFirst, cur);
+  for (int z = zFirst; z <= zLast; ++z) {
+    if (z < zLast)
+      fetch(z + 1, nxt);
+    float accLo = FLT_MAX, accHi = -FLT_MAX;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      const int y = y0 + warp + 8 * k;
+      if (y > y1) // warp-uniform
+        break;
+      const float4 v = cur[k];
+      const float *row = vox + ((size_t)z * dims.y + y) * dims.x;
+      if (UPLOAD && in && (y >> 4) == cy)
+        surf3Dwrite(v, surf, x * (int)sizeof(float), y, z);
+      float lo = in ? fminf(fminf(v.x, v.y), fminf(v.z, v.w)) : FLT_MAX;
+      float hi = in ? fmaxf(fmaxf(v.x, v.y), fmaxf(v.z, v.w)) : -FLT_MAX;
+      lo = fminf(lo, __shfl_xor_sync(0xffffffffu, lo, 1));
+      hi = fmaxf(hi, __shfl_xor_sync(0xffffffffu, hi, 1));
+      lo = fminf(lo, __shfl_xor_sync(0xffffffffu, lo, 2));
+      hi = fmaxf(hi, __shfl_xor_sync(0xffffffffu, hi, 2));
+      const float left = __shfl_up_sync(0xffffffffu, v.w, 1);
+      const float r0 = __shfl_sync(0xffffffffu, v.x, nextLane & 31);
+      const float r1 = __shfl_sync(0xffffffffu, v.y, nextLane & 31);
+      if ((lane & 3) == 0 && in) {
+        if (lane > 0) {
+          lo = fminf(lo, left);
+          hi = fmaxf(hi, left);
+        } else if (x > 0) {
+          const float l = __ldg(row + x - 1);
+          lo = fminf(lo, l);
+          hi = fmaxf(hi, l);
+        }
+        if (x + 16 < dims.x) { // dims.x % 4 == 0: 16c+16 in range implies 16c+17 in range
+          float a = r0, b = r1;
+          if (nextLane == 32) {
+            a = __ldg(row + x + 16);
+            b = __ldg(row + x + 17);
+          }
+          lo = fminf(fminf(lo, a), b);
+          hi = fmaxf(fmaxf(hi, a), b);
+        }
+        accLo = fminf(accLo, lo);
+        accHi = fmaxf(accHi, hi);
+      }
+    }
+    float2(*p)[8] = part[z & 1]; // double-buffered: one barrier per slice
+    if ((lane & 3) == 0)
+      p[warp][lane >> 2] = make_float2(accLo, accHi);
+    __syncthreads();
+    if (threadIdx.x < 8) {
+      const int cx = seg * 8 + threadIdx.x;
+      if (cx < gx) {
+        float lo = FLT_MAX, hi = -FLT_MAX;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) {
+          lo = fminf(lo, p[w][threadIdx.x].x);
+          hi = fmaxf(hi, p[w][threadIdx.x].y);
+        }
+        outY[((size_t)z * gy + cy) * gx + cx] = make_float2(lo, hi);
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < 3; ++k)
+      cur[k] = nxt[k];
+  }
+}
+
+bool macrocellLinearIsVectorisable(const void *voxels, int3 dims)
+{
+  return dims.x % 4 == 0 && (reinterpret_cast<uintptr_t>(voxels) & 15u) == 0
+      && (size_t)((dims.x + 127) / 128) * ((dims.y + 15) / 16) * dims.z < 0x7fffffffull; // grid.x
+}
+
+// voxels: linear f32 device memory, x fastest, the WHOLE field (no slab).  uploadTo != 0 (only when
+// macrocellLinearIsVectorisable): the same pass also writes the voxels into that surface (the field's 3-D array), so
+// a field refresh reads its input once.  Scratch: gx*gy*nz float2 for the y-reduced slices (+ one z-chunk of
+// x-reduced rows on the scalar route).
+int launchMacrocellBuildLinear(const float *voxels, int3 dims, int3 gridDims, float2 *ranges,
+    cudaSurfaceObject_t uploadTo, cudaStream_t s)
+{
+  const int gx = gridDims.x, gy = gridDims.y;
+  const bool vec = macrocellLinearIsVectorisable(voxels, dims);
+  if (uploadTo && !vec)
+    return cudaFail(cudaErrorInvalidValue, "macrocell build (linear): fused upload needs the vectorised route");
+  const int zChunk = 32;
+  float2 *bufX = nullptr, *bufY = nullptr;
+  if (!vec)
+    DVR_CUDA(scratchAllocAsync((void **)&bufX, (size_t)gx * dims.y * zChunk * sizeof(float2), s));
+  cudaError_t e = scratchAllocAsync((void **)&bufY, (size_t)gx * gy * dims.z * sizeof(float2), s);
+  if (e != cudaSuccess) {
+    if (bufX)
+      cudaFreeAsync(bufX, s);
+    return cudaFail(e, "cudaMallocAsync(macrocell scratch)");
+  }
+  const unsigned cap = (unsigned)smCount() * 16u;
+  if (vec) {
+    const unsigned units = (unsigned)((size_t)((dims.x + 127) / 128) * gy
+        * ((dims.z + kRangeSlicesPerCta - 1) / kRangeSlicesPerCta));
+    if (uploadTo)
+      dvrRangeXYKernel<true><<<units, 256, 0, s>>>(voxels, uploadTo, dims, gx, gy, bufY);
+    else
+      dvrRangeXYKernel<false><<<units, 256, 0, s>>>(voxels, 0, dims, gx, gy, bufY);
+    countLaunch();
+  } else {
+    for (int z0 = 0; z0 < dims.z; z0 += zChunk) {
+      const int nz = min(zChunk, dims.z - z0);
+      const size_t nX = (size_t)gx * dims.y * nz, nY = (size_t)gx * gy * nz;
+      dvrRangeXKernel<<<(unsigned)std::min<size_t>((nX + 255) / 256, cap), 256, 0, s>>>(voxels, dims, gx, z0, nz, bufX);
+      dvrRangeYKernel<<<(unsigned)std::min<size_t>((nY + 255) / 256, cap), 256, 0, s>>>(bufX, dims.y, gx, gy, nz,
+          bufY + (size_t)z0 * gx * gy);
+      countLaunch(2);
+    }
+  }
+  const size_t nC = (size_t)gx * gy * gridDims.z;
+  dvrRangeZKernel<<<(unsigned)std::min<size_t>((nC + 255) / 256, cap), 256, 0, s>>>(bufY, dims.z, gridDims, ranges);
+  countLaunch();
+  e = cudaGetLastError();
+  if (bufX)
+    cudaFreeAsync(bufX, s);
+  cudaFreeAsync(bufY, s);
+  if (e != cudaSuccess)
+    return cudaFail(e, "macrocell build (linear)");
   return DVR_OK;
 }
 

@@ -400,7 +400,9 @@ void SpatialField::cleanup()
     cudaStreamSynchronize((cudaStream_t)device->stream());
     dvr_field_destroy(m_field);
     m_field = nullptr;
+    m_fieldType = -1;
   }
+  ++m_generation;
 }
 
 void SpatialField::commitParameters()
@@ -436,6 +438,8 @@ static int dvrTypeOf(ANARIDataType t)
 
 void SpatialField::finalize()
 {
+  if (subtype == "structuredRegular" && m_field && m_data && refinalizeInPlace())
+    return;
   cleanup();
   if (subtype == "nanovdb") { // spatial_field/NvdbRegularField.cpp:64-113
     if (!m_data) {
@@ -486,7 +490,28 @@ void SpatialField::finalize()
     m_field = nullptr;
     report(ANARI_SEVERITY_ERROR, rc == DVR_ERR_OUT_OF_MEMORY ? ANARI_STATUS_OUT_OF_MEMORY : ANARI_STATUS_UNKNOWN_ERROR,
         "structuredRegular field upload failed: %s", dvr_last_error());
+    return;
   }
+  m_fieldType = dt;
+  m_fieldFilter = m_filter;
+  for (int i = 0; i < 3; ++i)
+    m_fieldDims[i] = dims[i];
+}
+
+// Time-varying fields (the `data` array rewritten and the field re-committed every step): when shape, element type
+// and filter are unchanged the device array, textures and macrocell storage are reused instead of rebuilt.
+bool SpatialField::refinalizeInPlace()
+{
+  const int dt = dvrTypeOf(m_data->elementType);
+  if (dt < 0 || dt != m_fieldType || m_filter != m_fieldFilter)
+    return false;
+  for (int i = 0; i < 3; ++i)
+    if ((uint32_t)m_data->dims[i] != m_fieldDims[i])
+      return false;
+  CudaDeviceScope scope(device);
+  return dvr_field_update_structured(m_field, m_data->data(), m_data->onDevice() ? 1 : 0, dt, m_origin, m_spacing,
+             device->stream())
+      == DVR_OK;
 }
 
 void SpatialField::bounds(float lo[3], float hi[3]) const
@@ -623,7 +648,7 @@ void Volume::finalize()
   }
   CudaDeviceScope scope(device);
   int rc;
-  if (m_volume && m_volumeField == m_field->handle())
+  if (m_volume && m_volumeField == m_field->handle() && m_volumeFieldGeneration == m_field->generation())
     rc = dvr_volume_update(m_volume, tf.data(), m_valueRange, m_unitDistance, m_id, device->stream());
   else {
     if (m_volume) {
@@ -633,6 +658,7 @@ void Volume::finalize()
     }
     rc = dvr_volume_create(m_field->handle(), tf.data(), m_valueRange, m_unitDistance, m_id, device->stream(), &m_volume);
     m_volumeField = m_field->handle();
+    m_volumeFieldGeneration = m_field->generation();
   }
   if (rc != DVR_OK)
     report(ANARI_SEVERITY_ERROR, ANARI_STATUS_UNKNOWN_ERROR, "volume upload failed: %s", dvr_last_error());

@@ -189,10 +189,17 @@ struct SpatialField : Object
   int commitPriority() const override { return 2; }
   bool getProperty(const std::string &name, ANARIDataType type, void *mem, uint64_t size, uint32_t mask) override;
   DvrField *handle() const { return m_field; }
+  // bumped whenever handle() becomes a NEW device field (not by an in-place refresh): an address alone can be reused
+  uint64_t generation() const { return m_generation; }
   void bounds(float lo[3], float hi[3]) const;
 
  private:
   void cleanup();
+  bool refinalizeInPlace();
+  uint64_t m_generation = 0;
+  int m_fieldType = -1;
+  uint32_t m_fieldDims[3] = {0, 0, 0};
+  std::string m_fieldFilter;
   Ref<Array> m_data;
   float m_origin[3] = {0, 0, 0};
   float m_spacing[3] = {1, 1, 1};
@@ -223,6 +230,7 @@ struct Volume : Object
   uint32_t m_id = ~0u;
   DvrVolume *m_volume = nullptr;
   const DvrField *m_volumeField = nullptr;
+  uint64_t m_volumeFieldGeneration = 0;
   bool m_known = true;
 };
 
