@@ -674,6 +674,11 @@ def run_ours(args, torch, dist, rank, world):
                 out["extra"]["dpt"] = measure_dpt(args, torch, capi, field, cam, fb, stream, vol)
             except Exception as e:
                 out["extra"]["dpt"] = f"unavailable: {e}"
+            if args.field == "ml":
+                try:
+                    out["extra"]["time_varying"] = measure_time_varying(args, torch, capi, field, cam, fb, stream, vol)
+                except Exception as e:
+                    out["extra"]["time_varying"] = f"unavailable: {e}"
     if driver is not None and getattr(driver, "host_frame", None) is not None:
         host_view = None  # drop the numpy view before the shared segment is unmapped
         driver.host_frame.close(dist if world > 1 else None)
@@ -711,6 +716,35 @@ def measure_variants(args, torch, capi, scenes, field, cam, inst, ninst, fb, str
 
 
 DPT_OPACITY = (0.0, 0.02)  # TF alpha ramp of the dpt variant: mean free path >= 25 voxels, multiple scattering
+
+
+def measure_time_varying(args, torch, capi, field, cam, fb, stream, vol_dev):
+    """A field that changes every frame (in-situ): per step the whole f32 volume is re-finalised from
+    device memory (dvr_field_update_structured: upload + macrocell ranges in one pass), the volume re-derives its
+    majorants, and one frame is marched.  Wall clock, result left on the device."""
+    n = args.size
+    tf = capi.tf_discretize(color=scene_colormap(args))
+    v = capi.Volume.create(field, tf, (0.0, 1.0), args.unit_distance, 0, stream)
+    ins, nn = capi.make_instances([v], None, [0])
+    p = capi.frame_params(args.width, args.height, capi.DVR_FORMAT_UFIXED8_RGBA_SRGB, capi.DVR_INTEGRATOR_DEFAULT, 0,
+                          -1, 1, args.rate, (0.1, 0.1, 0.1, 1.0))
+
+    def step():
+        field.update_structured(vol_dev.data_ptr(), True, capi.DVR_FLOAT32, (0, 0, 0), (1, 1, 1), stream)
+        v.update(tf, (0.0, 1.0), args.unit_distance, 0, stream)
+        capi.render(p, cam, ins, nn, fb, stream)
+
+    for _ in range(3):
+        step()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(20):
+        step()
+    torch.cuda.synchronize()
+    ms = (time.perf_counter() - t0) * 1e3 / 20
+    v.destroy()
+    return {"fps": 1000.0 / ms, "ms_per_update_and_frame": ms, "bytes_refreshed_per_step": n ** 3 * 4,
+            "what": "field refresh (4.3 GB f32 from device memory) + volume majorants + one frame, wall clock"}
 
 
 def measure_dpt(args, torch, capi, field, cam, fb, stream, vol_dev):
