@@ -105,6 +105,10 @@ def test_invalid_arguments_are_rejected():
     assert e.value.code == capi.DVR_ERR_INVALID_ARGUMENT
     with pytest.raises(capi.DvrError):
         capi.Field.create_slab(vox.ctypes.data, False, capi.DVR_FLOAT32, (4, 4, 4), 3, 2, (0, 0, 0), (1, 1, 1))
+    # the in-place refresh needs a field and data
+    with pytest.raises(capi.DvrError) as e:
+        capi.Field(None).update_structured(vox.ctypes.data, False, capi.DVR_FLOAT32, (0, 0, 0), (1, 1, 1))
+    assert e.value.code == capi.DVR_ERR_INVALID_ARGUMENT and "dvr_field_update_structured" in str(e.value)
 
 
 def test_product_does_not_reference_the_oracle():

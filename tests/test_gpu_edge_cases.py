@@ -141,3 +141,31 @@ def test_the_test_renderer_paints_ray_directions():
     assert not [m for m in a.d.messages if m[0] <= A.SEVERITY_WARNING], a.d.messages
     assert np.all(np.asarray(color).reshape(-1, 4)[:, 3] == 1.0)
     a.close()
+
+
+def test_in_place_refresh_refuses_what_it_cannot_keep():
+    """dvr_field_update_structured only keeps the device objects of a WHOLE structuredRegular field of unchanged
+    element type: slabs, NanoVDB grids, FLOAT64 and type changes answer DVR_ERR_UNSUPPORTED and leave the field
+    usable (the caller destroys and creates instead, as the ANARI device does)."""
+    from visrtx_b200 import nvdb_writer
+    n = 24
+    vox = scenes.marschner_lobb_np(n)
+    slab = capi.Field.create_slab(vox[7:17].ctypes.data, False, capi.DVR_FLOAT32, (n, n, n), 8, 16, (0, 0, 0), (1, 1, 1))
+    grid = nvdb_writer.fog_sphere(radius=10.0, voxel_size=1.0, half_width=3.0)
+    nv = capi.Field.create_nanovdb(grid.ctypes.data, grid.nbytes)
+    f64 = vox.astype(np.float64)
+    dbl = capi.Field.create_structured(f64.ctypes.data, False, capi.DVR_FLOAT64, (n, n, n), (0, 0, 0), (1, 1, 1))
+    whole = capi.Field.create_structured(vox.ctypes.data, False, capi.DVR_FLOAT32, (n, n, n), (0, 0, 0), (1, 1, 1))
+    try:
+        for fld, dt, data in ((slab, capi.DVR_FLOAT32, vox), (nv, capi.DVR_FLOAT32, vox), (dbl, capi.DVR_FLOAT64, f64),
+                              (whole, capi.DVR_UFIXED8, vox)):
+            with pytest.raises(capi.DvrError) as e:
+                fld.update_structured(data.ctypes.data, False, dt, (0, 0, 0), (1, 1, 1))
+            assert e.value.code == capi.DVR_ERR_UNSUPPORTED
+        before = whole.value_range()
+        whole.update_structured(np.ascontiguousarray(vox * 0.5).ctypes.data, False, capi.DVR_FLOAT32, (0, 0, 0), (1, 1, 1))
+        after = whole.value_range()
+        assert after == (np.float32(before[0]) * np.float32(0.5), np.float32(before[1]) * np.float32(0.5))
+    finally:
+        for fld in (slab, nv, dbl, whole):
+            fld.destroy()
