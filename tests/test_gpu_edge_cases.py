@@ -150,7 +150,8 @@ def test_in_place_refresh_refuses_what_it_cannot_keep():
     from visrtx_b200 import nvdb_writer
     n = 24
     vox = scenes.marschner_lobb_np(n)
-    slab = capi.Field.create_slab(vox[7:17].ctypes.data, False, capi.DVR_FLOAT32, (n, n, n), 8, 16, (0, 0, 0), (1, 1, 1))
+    resident = np.ascontiguousarray(vox[7:17])
+    slab = capi.Field.create_slab(resident.ctypes.data, False, capi.DVR_FLOAT32, (n, n, n), 8, 16, (0, 0, 0), (1, 1, 1))
     grid = nvdb_writer.fog_sphere(radius=10.0, voxel_size=1.0, half_width=3.0)
     nv = capi.Field.create_nanovdb(grid.ctypes.data, grid.nbytes)
     f64 = vox.astype(np.float64)
@@ -163,7 +164,8 @@ def test_in_place_refresh_refuses_what_it_cannot_keep():
                 fld.update_structured(data.ctypes.data, False, dt, (0, 0, 0), (1, 1, 1))
             assert e.value.code == capi.DVR_ERR_UNSUPPORTED
         before = whole.value_range()
-        whole.update_structured(np.ascontiguousarray(vox * 0.5).ctypes.data, False, capi.DVR_FLOAT32, (0, 0, 0), (1, 1, 1))
+        half = np.ascontiguousarray(vox * np.float32(0.5))  # kept alive across the call
+        whole.update_structured(half.ctypes.data, False, capi.DVR_FLOAT32, (0, 0, 0), (1, 1, 1))
         after = whole.value_range()
         assert after == (np.float32(before[0]) * np.float32(0.5), np.float32(before[1]) * np.float32(0.5))
     finally:
