@@ -425,3 +425,35 @@ def test_macrocell_build_from_device_memory_matches_texture_build(dims):
         a.destroy()
         b.destroy()
         c.destroy()
+
+
+@pytest.mark.parametrize("name", ["nvdb_fog_r20", "nvdb_fog_r12_vs025", "nvdb_fp4_r14", "nvdb_fp8_r14", "nvdb_fp16_r14",
+                                  "nvdb_fpn_r14"])
+@pytest.mark.parametrize("skip", [False, True])
+def test_nanovdb_apron_bricks_are_bit_identical_to_the_tree_walk(name, skip, monkeypatch):
+    """NanoVDB fields are gathered into 9^3 apron bricks at creation (dvr_nvdb_bricks.cu) and sampled from those;
+    DVR_B200_NVDB_BRICKS=0 keeps the per-tap tree walk that mirrors the reference's accessor.  Same voxel values,
+    same interpolation arithmetic: every channel of the frame is identical, for float and quantised grids, with
+    negative index coordinates, a non-unit voxel size and an off-origin grid."""
+    scene, frames, cb = ZOO[name]
+    a = H.render_cuda(scene, frames=frames, checkerboard=cb, skip=skip)
+    monkeypatch.setenv("DVR_B200_NVDB_BRICKS", "0")
+    b = H.render_cuda(scene, frames=frames, checkerboard=cb, skip=skip)
+    for k in a:
+        assert np.array_equal(a[k], b[k]), (name, k)
+
+
+def test_nanovdb_apron_bricks_cover_the_grid_and_count_as_device_memory(monkeypatch):
+    from visrtx_b200 import nvdb_writer
+    grid = nvdb_writer.fog_sphere(radius=20.0, voxel_size=1.0, half_width=3.0)
+    f = capi.Field.create_nanovdb(grid.ctypes.data, grid.nbytes)
+    monkeypatch.setenv("DVR_B200_NVDB_BRICKS", "0")
+    g = capi.Field.create_nanovdb(grid.ctypes.data, grid.nbytes)
+    try:
+        extra = f.device_bytes() - g.device_bytes()
+        # table (8 B per 8^3 cell of the bounding box) + at least the bricks of the sphere's shell, at most one per cell
+        cells = 6 ** 3  # index bounding box [-19, 19]^3: cells (-20 >> 3) .. (19 >> 3) per axis
+        assert extra > cells * 8 and extra <= cells * (8 + 729 * 4)
+    finally:
+        f.destroy()
+        g.destroy()

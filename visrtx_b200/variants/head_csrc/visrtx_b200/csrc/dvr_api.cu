@@ -170,9 +170,6 @@ struct DvrField
   size_t voxelBytes = 0;
   size_t texElementSize = 0;
   void *nvdbBlob = nullptr; // NanoVDB fields: device copy of the serialized grid
-  int2 *brickTable = nullptr; // NanoVDB fields: apron bricks (dvr_nvdb_bricks.cu), absent when over budget
-  float *bricks = nullptr;
-  size_t brickBytes = 0;
   int device = 0;
   int dataType = -1; // structured fields: the DvrDataType handed to create
 };
@@ -653,60 +650,6 @@ T rd(const uint8_t *p, size_t off)
 } // namespace
 }
 
-// Gathers the grid into apron bricks (NvdbDev::brickTable) when table and bricks fit the budget: table <= 256 MiB,
-// bricks <= min(4 GiB, a quarter of the free device memory).  Any failure leaves the field on the tree walk.
-static void buildNvdbBricks(DvrField *f, const int bmin[3], const int bmax[3], cudaStream_t s)
-{
-  const char *env = std::getenv("DVR_B200_NVDB_BRICKS");
-  if (env && env[0] == '0')
-    return;
-  if (bmax[0] < bmin[0] || bmax[1] < bmin[1] || bmax[2] < bmin[2])
-    return; // empty grid
-  FieldDev &d = f->dev;
-  // cells of every base voxel whose stencil can touch the bounding box: [bmin - 1, bmax]
-  const int3 org = make_int3((bmin[0] - 1) >> 3, (bmin[1] - 1) >> 3, (bmin[2] - 1) >> 3);
-  const long long dx = (long long)(bmax[0] >> 3) - org.x + 1, dy = (long long)(bmax[1] >> 3) - org.y + 1,
-                  dz = (long long)(bmax[2] >> 3) - org.z + 1;
-  const long long cells = dx * dy * dz;
-  if (dx <= 0 || dy <= 0 || dz <= 0 || cells > (256ll << 20) / (long long)sizeof(int2))
-    return;
-  const int3 dims = make_int3((int)dx, (int)dy, (int)dz);
-  unsigned int *counter = nullptr;
-  int2 *table = nullptr;
-  float *bricks = nullptr;
-  bool ok = cudaMalloc(&table, (size_t)cells * sizeof(int2)) == cudaSuccess
-      && cudaMalloc(&counter, sizeof(unsigned int)) == cudaSuccess
-      && cudaMemsetAsync(counter, 0, sizeof(unsigned int), s) == cudaSuccess
-      && launchNvdbBrickBuild(d.nv, d.kind == FIELD_NANOVDB_QUANT, org, dims, table, nullptr, counter, 0u, s) == DVR_OK;
-  unsigned int need = 0;
-  ok = ok && cudaMemcpyAsync(&need, counter, sizeof(need), cudaMemcpyDeviceToHost, s) == cudaSuccess
-      && cudaStreamSynchronize(s) == cudaSuccess;
-  if (ok) {
-    size_t freeB = 0, totalB = 0;
-    cudaMemGetInfo(&freeB, &totalB);
-    const size_t bytes = (size_t)std::max(need, 1u) * kNvdbBrickVoxels * sizeof(float);
-    ok = bytes <= std::min<size_t>((size_t)4 << 30, freeB / 4) && cudaMalloc(&bricks, bytes) == cudaSuccess
-        && cudaMemsetAsync(counter, 0, sizeof(unsigned int), s) == cudaSuccess
-        && launchNvdbBrickBuild(d.nv, d.kind == FIELD_NANOVDB_QUANT, org, dims, table, bricks, counter, need, s) == DVR_OK
-        && cudaStreamSynchronize(s) == cudaSuccess;
-    if (ok) {
-      f->brickTable = table;
-      f->bricks = bricks;
-      f->brickBytes = (size_t)cells * sizeof(int2) + bytes;
-      d.nv.brickTable = table;
-      d.nv.bricks = bricks;
-      d.nv.brickOrg = org;
-      d.nv.brickDims = dims;
-      table = nullptr;
-      bricks = nullptr;
-    }
-  }
-  cudaGetLastError(); // a failed allocation is not an error of the field
-  cudaFree(counter);
-  cudaFree(table);
-  cudaFree(bricks);
-}
-
 int dvr_field_create_nanovdb(const void *gridData, size_t bytes, int dataIsDevice, void *stream, DvrField **out)
 {
   if (!gridData || !out || bytes < 672 + 64 + 64) {
@@ -826,7 +769,6 @@ int dvr_field_create_nanovdb(const void *gridData, size_t bytes, int dataIsDevic
     dvr_field_destroy(f);
     return rc;
   }
-  buildNvdbBricks(f, bmin, bmax, s);
   *out = f;
   return DVR_OK;
 }
@@ -893,8 +835,6 @@ int dvr_field_destroy(DvrField *f)
   if (f->array) cudaFreeArray(f->array);
   if (f->ranges) cudaFree(f->ranges);
   if (f->nvdbBlob) cudaFree(f->nvdbBlob);
-  if (f->brickTable) cudaFree(f->brickTable);
-  if (f->bricks) cudaFree(f->bricks);
   delete f;
   return DVR_OK;
 }
@@ -926,7 +866,7 @@ int dvr_field_device_bytes(const DvrField *f, size_t *bytes)
     setError("dvr_field_device_bytes: null argument");
     return DVR_ERR_INVALID_ARGUMENT;
   }
-  *bytes = f->voxelBytes + f->nCells * sizeof(float2) + f->brickBytes;
+  *bytes = f->voxelBytes + f->nCells * sizeof(float2);
   return DVR_OK;
 }
 

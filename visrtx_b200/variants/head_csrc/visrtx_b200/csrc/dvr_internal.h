@@ -141,8 +141,6 @@ int launchMacrocellBuild(cudaTextureObject_t pointTex, int3 dims, int zTexBegin,
 bool macrocellLinearIsVectorisable(const void *voxels, int3 dims);
 int launchMacrocellBuildLinear(const float *voxels, int3 dims, int3 gridDims, float2 *ranges,
     cudaSurfaceObject_t uploadTo, cudaStream_t s);
-int launchNvdbBrickBuild(const NvdbDev &g, bool quant, int3 org, int3 dims, int2 *table, float *bricks,
-    unsigned int *counter, unsigned int capacity, cudaStream_t s);
 int launchMacrocellBuildNvdb(const FieldDev &f, float2 *ranges, cudaStream_t s);
 // value ranges on the delta-tracking grid: gridDims cells dividing `spanVoxels` voxel units evenly per axis
 int launchDdaRangeBuild(const FieldDev &f, cudaTextureObject_t pointTex, int3 gridDims, float3 cellWidthVoxels,

@@ -1,0 +1,779 @@
+// dvr_kernels.cu — frame kernel K1 (ray generation + march + background + accumulate/tonemap/encode),
+// the sort-last partial kernel, the resolve kernel K3 and the `over` compositing kernel.
+// Target: sm_100a only.  See DESIGN.md for the layout / scheduling rationale.
+#include "dvr_internal.h"
+#include "dvr_march.cuh"
+#include "dvr_dpt.cuh"
+
+namespace dvr {
+
+// ----------------------------------------------------------------------------------------------
+// warp-granular dynamic tile scheduler.  sched[0] = next tile, sched[1] = warps finished.  The last
+// warp to leave re-arms both counters, so no memset is needed between frames.
+// ----------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t nextTile(unsigned int *sched, int lane)
+{
+  uint32_t t = 0;
+  if (lane == 0)
+    t = atomicAdd(&sched[0], 1u);
+  return __shfl_sync(0xffffffffu, t, 0);
+}
+
+__device__ __forceinline__ void retireWarp(unsigned int *sched, int lane)
+{
+  if (lane == 0) {
+    const unsigned int totalWarps = gridDim.x * (blockDim.x >> 5);
+    __threadfence();
+    const unsigned int done = atomicAdd(&sched[1], 1u);
+    if (done == totalWarps - 1u) {
+      sched[0] = 0u;
+      sched[1] = 0u;
+      sched[2] = 0u;
+      __threadfence();
+    }
+  }
+}
+
+// ---- cross-GPU flags (DvrPeerSync) ----------------------------------------------------------
+__device__ __forceinline__ void signalPeers(const SyncDev &sy)
+{
+  __threadfence_system(); // everything this GPU wrote for the frame is visible system-wide first
+  for (uint32_t i = 0; i < sy.nSignal; ++i)
+    *((volatile unsigned int *)sy.signal[i]) = sy.signalValue;
+  __threadfence_system();
+}
+
+// bounded spin (about 2 s at 1.9 GHz): a missing producer must not hang the GPU
+__device__ __forceinline__ bool waitFlags(const unsigned int *flags, uint32_t n, uint32_t value, unsigned int *err)
+{
+  const long long t0 = clock64();
+  for (uint32_t i = 0; i < n; ++i) {
+    while ((int)(*((volatile const unsigned int *)&flags[i]) - value) < 0) {
+      __nanosleep(200);
+      if (clock64() - t0 > 4000000000ll) {
+        if (err)
+          *err = 1u;
+        return false;
+      }
+    }
+  }
+  __threadfence_system();
+  return true;
+}
+
+// retireWarp + signal from the last warp of the grid
+__device__ __forceinline__ void retireWarpAndSignal(unsigned int *sched, int lane, const SyncDev &sy)
+{
+  if (lane == 0) {
+    const unsigned int totalWarps = gridDim.x * (blockDim.x >> 5);
+    __threadfence();
+    const unsigned int done = atomicAdd(&sched[1], 1u);
+    if (done == totalWarps - 1u) {
+      sched[0] = 0u;
+      sched[1] = 0u;
+      sched[2] = 0u;
+      __threadfence();
+      if (sy.nSignal)
+        signalPeers(sy);
+    }
+  }
+}
+
+__global__ void dvrSignalFlagsKernel(const __grid_constant__ SyncDev sy) { signalPeers(sy); }
+
+int launchSignalFlags(const SyncDev &sy, cudaStream_t s)
+{
+  dvrSignalFlagsKernel<<<1, 1, 0, s>>>(sy);
+  DVR_CUDA(cudaGetLastError());
+  countLaunch();
+  return DVR_OK;
+}
+
+__global__ void dvrWaitFlagsKernel(const unsigned int *flags, uint32_t n, uint32_t value, unsigned int *err)
+{
+  waitFlags(flags, n, value, err);
+}
+
+int launchWaitFlags(const unsigned int *flags, uint32_t n, uint32_t value, unsigned int *errorFlag, cudaStream_t s)
+{
+  dvrWaitFlagsKernel<<<1, 1, 0, s>>>(flags, n, value, errorFlag);
+  DVR_CUDA(cudaGetLastError());
+  countLaunch();
+  return DVR_OK;
+}
+
+__device__ __forceinline__ unsigned long long warpSum(unsigned long long v)
+{
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1)
+    v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// accumResults, gpu/gpu_util.h:393-443, for one pixel-sample.  `init` replaces the cleared
+// buffers of Frame::newFrame (Frame.cu:609-647): 0 + x and min(FLT_MAX, x) are written directly.
+struct AccumCtx
+{
+  uint32_t width, height;
+  int format, frameID, checkerboardID;
+  BuffersDev fb;
+};
+
+__device__ __forceinline__ void accumResults(const AccumCtx &P, uint32_t px, uint32_t py, float4 color,
+    float depth, float3 albedo, float3 normal, uint32_t primID, uint32_t objID, uint32_t instID,
+    int frameIDOffset, bool init)
+{
+  const BuffersDev &fb = P.fb;
+  const uint32_t idx = px + py * P.width;
+  const int frameID = P.frameID + frameIDOffset;
+
+  // tonemap: v / (1 + max(0, compMax(v)))
+  const float m = __fadd_rn(1.0f, fmaxf(0.0f, fmaxf(fmaxf(color.x, color.y), color.z)));
+  const float4 tm = make_float4(__fdiv_rn(color.x, m), __fdiv_rn(color.y, m), __fdiv_rn(color.z, m), color.w);
+
+  float4 acc;
+  if (init) {
+    acc = tm;
+  } else {
+    acc = fb.accum[idx];
+    acc.x = __fadd_rn(acc.x, tm.x);
+    acc.y = __fadd_rn(acc.y, tm.y);
+    acc.z = __fadd_rn(acc.z, tm.z);
+    acc.w = __fadd_rn(acc.w, tm.w);
+  }
+  fb.accum[idx] = acc;
+
+  if (fb.albedo) {
+    float *a = fb.albedo + 3 * (size_t)idx;
+    if (init) {
+      a[0] = albedo.x; a[1] = albedo.y; a[2] = albedo.z;
+    } else {
+      a[0] += albedo.x; a[1] += albedo.y; a[2] += albedo.z;
+    }
+  }
+  if (fb.normal) {
+    float *n = fb.normal + 3 * (size_t)idx;
+    if (init) {
+      n[0] = normal.x; n[1] = normal.y; n[2] = normal.z;
+    } else {
+      n[0] += normal.x; n[1] += normal.y; n[2] += normal.z;
+    }
+  }
+
+  bool closer = true;
+  if (fb.depth) {
+    const float prev = init ? FLT_MAX : fb.depth[idx];
+    closer = depth < prev;
+    if (closer)
+      fb.depth[idx] = depth;
+    else if (init)
+      fb.depth[idx] = prev;
+  }
+  if (closer) {
+    if (fb.primId) fb.primId[idx] = primID;
+    if (fb.objId) fb.objId[idx] = objID;
+    if (fb.instId) fb.instId[idx] = instID;
+  } else if (init) {
+    if (fb.primId) fb.primId[idx] = 0u;
+    if (fb.objId) fb.objId[idx] = 0u;
+    if (fb.instId) fb.instId[idx] = 0u;
+  }
+
+  writeOutputColor(fb, P.format, acc, idx, frameID);
+
+  // first checkerboard pass: replicate the colour into the three not-yet-rendered neighbours
+  // (gpu_util.h:424-442) and initialise their accumulation state for the passes that follow
+  if (P.checkerboardID == 0 && frameID == 0) {
+#pragma unroll
+    for (int n = 1; n < 4; ++n) {
+      const uint32_t ax = px + (n & 1), ay = py + (n >> 1);
+      if (ax >= P.width || ay >= P.height)
+        continue;
+      const uint32_t aidx = ax + ay * P.width;
+      writeOutputColor(fb, P.format, acc, aidx, frameID);
+      if (init) {
+        fb.accum[aidx] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (fb.depth) fb.depth[aidx] = FLT_MAX;
+        if (fb.primId) fb.primId[aidx] = 0u;
+        if (fb.objId) fb.objId[aidx] = 0u;
+        if (fb.instId) fb.instId[aidx] = 0u;
+        if (fb.albedo) { float *a = fb.albedo + 3 * (size_t)aidx; a[0] = a[1] = a[2] = 0.f; }
+        if (fb.normal) { float *a = fb.normal + 3 * (size_t)aidx; a[0] = a[1] = a[2] = 0.f; }
+      }
+    }
+  }
+}
+
+struct TfSelectShared
+{
+  const float4 *smem;
+  const InstanceDev *inst;
+  __device__ __forceinline__ const float4 *operator()(int i) const
+  {
+    return i < kMaxInlineInstances ? smem + i * DVR_TF_SIZE : inst[i].v.tf;
+  }
+};
+struct TfSelectSingle
+{
+  const float4 *smem;
+  __device__ __forceinline__ const float4 *operator()(int) const { return smem; }
+};
+
+// ----------------------------------------------------------------------------------------------
+// K1: one frame.  Persistent CTAs; every warp pulls 8x4-pixel tiles from a global counter.
+// ----------------------------------------------------------------------------------------------
+#ifndef DVR_OCC
+#define DVR_OCC 2 // minimum resident CTAs per SM the frame kernel is compiled for (register budget)
+#endif
+
+// KIND: FIELD_STRUCTURED / FIELD_NANOVDB for the single-volume kernels, -1 for the multi-volume kernel
+#ifndef DVR_OCC_NVDB
+#define DVR_OCC_NVDB 3 // the NanoVDB march chases pointers; A/B on C5 (batch 1): 3/4/5/6 CTAs = 810/732/642/612 fps
+#endif
+// G: depth lanes per ray (see marchSegment); the warp's 8x4 tile is then rendered in G passes of 32/G pixels.
+#ifndef DVR_DEPTH_LANES
+#define DVR_DEPTH_LANES 1
+#endif
+#ifndef DVR_DEPTH_LANES_NVDB
+#define DVR_DEPTH_LANES_NVDB 1
+#endif
+template <bool SKIP, bool STATS, bool SINGLE, int KIND, bool DPT, int G>
+__global__ void __launch_bounds__(kBlockThreads, (KIND >= FIELD_NANOVDB ? DVR_OCC_NVDB : DVR_OCC)) dvrFrameKernel(const __grid_constant__ FrameLaunch P)
+{
+  static_assert(!(DPT && G != 1) && !(!SINGLE && G != 1), "depth lanes: single-volume marching kernels only");
+  __shared__ float4 s_tf[(SINGLE ? 1 : kMaxInlineInstances) * DVR_TF_SIZE];
+
+  const int lane = threadIdx.x & 31;
+  const InstanceDev *inst = (P.nInst <= kMaxInlineInstances) ? P.inl : P.ext;
+  const int nInst = SINGLE ? 1 : P.nInst;
+
+  // stage the transfer-function tables (4 KiB each) once per CTA
+  {
+    const int nTab = SINGLE ? 1 : min(P.nInst, kMaxInlineInstances);
+    for (int i = threadIdx.x; i < nTab * DVR_TF_SIZE; i += blockDim.x)
+      s_tf[i] = __ldg(&inst[i / DVR_TF_SIZE].v.tf[i % DVR_TF_SIZE]);
+    __syncthreads();
+  }
+
+  MarchStats st{0ull, 0ull};
+  unsigned long long raysHit = 0ull;
+  const uint32_t nTiles = P.tilesW * P.tilesH;
+  const bool centered = P.integrator == DVR_INTEGRATOR_RAYCAST;
+  const bool initFrame = P.frameID == 0 && P.checkerboardID <= 0;
+  const AccumCtx actx{P.width, P.height, P.format, P.frameID, P.checkerboardID, P.fb};
+
+  for (uint32_t tile = nextTile(P.sched, lane); tile < nTiles; tile = nextTile(P.sched, lane)) {
+    // only the tile window is scheduled (the whole launch grid unless the launcher knows the screen rectangle of the
+    // volumes; the pixels outside it are then swept by dvrBackgroundSweepKernel on a second stream)
+    const uint32_t tyIdx = P.tileY0 + tile / P.tilesW, txIdx = P.tileX0 + tile % P.tilesW;
+    if (P.tileRanks > 1u && ((tyIdx / P.tileBand) % P.tileRanks) != P.tileRank)
+      continue;
+   for (int pass = 0; pass < G; ++pass) {
+    // G == 1: lane = pixel of the tile.  G > 1: lane / G = pixel within this pass, lane % G = depth slot.
+    const int pix = G == 1 ? lane : pass * (32 / G) + lane / G;
+    const uint32_t lx = txIdx * kTileW + (pix % kTileW), ly = tyIdx * kTileH + (pix / kTileW);
+    if (lx >= P.launchW || ly >= P.launchH)
+      continue;
+    uint32_t px = lx, py = ly;
+    if (P.checkerboardID >= 0) { // createScreenSample.h:38-46
+      px = lx * 2u + (uint32_t)(P.checkerboardID & 1);
+      py = ly * 2u + (uint32_t)((P.checkerboardID >> 1) & 1);
+    }
+    if (px >= P.width || py >= P.height)
+      continue;
+
+    if (!DPT && P.missValid
+        && ((int)px < P.missX0 || (int)px >= P.missX1 || (int)py < P.missY0 || (int)py >= P.missY1)) {
+      // No ray of this pixel can enter a volume: what the march + Raycast_ptx.cu:139-166 produce for a miss, bit for
+      // bit (colour 0*0 + bg*(1-0) = bg, depth min(1e30, tmax), ids ~0u), without Philox or camera work.  Launches
+      // that need the ray direction (normal channel) never set missValid.
+      const float4 bg = P.background;
+      for (int it = 0; it < P.numIterations; ++it)
+        accumResults(actx, px, py, bg, 1e30f, f3(bg.x, bg.y, bg.z), f3(0.f, 0.f, 0.f), 0u, ~0u, ~0u, it,
+            initFrame && it == 0);
+      continue;
+    }
+    Philox rng;
+    rng.init((unsigned long long)(int)(py * P.width + px), (unsigned long long)P.frameID * 512ull);
+    DptPath path{0, f3(1.f, 1.f, 1.f)}; // PathData lives outside the iteration loop in the reference
+
+    for (int it = 0; it < P.numIterations; ++it) {
+      // makePrimaryRay, cameraCreateRay.h:74-81
+      const float4 r = rng.uniform4();
+      const float sx = __fmul_rn(centered ? (float)px : __fadd_rn((float)px, r.x), P.invW);
+      const float sy = __fmul_rn(centered ? (float)py : __fadd_rn((float)py, r.y), P.invH);
+      float3 org, dir;
+      cameraCreateRay(P.cam, sx, sy, r.z, r.w, org, dir);
+
+      if (DPT && P.integrator == DVR_INTEGRATOR_TEST) { // Test_ptx.cu:52-69: one sample, no scene access
+        accumResults(actx, px, py, make_float4(dir.x, dir.y, dir.z, 1.f), 1.f, dir, f3(-dir.x, -dir.y, -dir.z), ~0u,
+            ~0u, ~0u, 0, initFrame);
+        break;
+      }
+      if (DPT) {
+        // DiffusePathTracer_ptx.cu:96-215: colour = Lw * ambient (or the background when nothing scattered),
+        // alpha 1; depth / ids are never set by the reference's loop (its `depth == 0` test runs after the
+        // increment), so depth stays tmax and the ids ~0u; albedo channel = background, normal = primary dir
+        float3 c;
+        if (SINGLE)
+          c = dptTracePath<true, KIND>(P.inl, 1, TfSelectSingle{s_tf}, org, dir, P.maxDepth, P.occlusionDistance,
+              P.ambientIntensity, P.background, rng, path);
+        else
+          c = dptTracePath<false, -1>(inst, nInst, TfSelectShared{s_tf, inst}, org, dir, P.maxDepth,
+              P.occlusionDistance, P.ambientIntensity, P.background, rng, path);
+        accumResults(actx, px, py, make_float4(c.x, c.y, c.z, 1.f), FLT_MAX,
+            f3(P.background.x, P.background.y, P.background.z), dir, ~0u, ~0u, ~0u, it, initFrame && it == 0);
+        continue;
+      }
+
+      float3 color = f3(0.f, 0.f, 0.f);
+      float opacity = 0.f;
+      uint32_t objID = ~0u, instID = ~0u;
+      bool anyHit = false;
+      float volumeDepth;
+      if (SINGLE)
+        volumeDepth = rayMarchAllVolumes<SKIP, false, STATS, true, KIND, G>(P.inl, 1, TfSelectSingle{s_tf}, org, dir,
+            FLT_MAX, P.invSamplingRate, rng, color, opacity, objID, instID, st, P.cellBitmap, anyHit);
+      else
+        volumeDepth = rayMarchAllVolumes<SKIP, false, STATS, false, -1>(inst, nInst, TfSelectShared{s_tf, inst}, org, dir,
+            FLT_MAX, P.invSamplingRate, rng, color, opacity, objID, instID, st, P.cellBitmap, anyHit);
+      const bool writer = G == 1 || (lane & (G - 1)) == 0; // every depth lane holds the same result; one stores it
+      if (STATS && anyHit && writer)
+        raysHit++;
+
+      // Raycast_ptx.cu:139-166 (no-surface branch)
+      const float depth = fminf(1e30f, volumeDepth);
+      color = color * opacity;
+      const float4 bg = P.background;
+      const float oneMinus = __fsub_rn(1.f, opacity);
+      color.x = __fmaf_rn(bg.x, oneMinus, color.x);
+      color.y = __fmaf_rn(bg.y, oneMinus, color.y);
+      color.z = __fmaf_rn(bg.z, oneMinus, color.z);
+      opacity = __fmaf_rn(bg.w, oneMinus, opacity);
+      // outputColor/outputOpacity start at 0: accumulateValue(out, c, 0) == c
+      if (writer)
+        accumResults(actx, px, py, make_float4(color.x, color.y, color.z, opacity), depth, color, dir, 0u, objID,
+            instID, it, initFrame && it == 0);
+    }
+   } // pass
+  }
+
+  if (STATS) {
+    const unsigned long long a = warpSum(st.taken), b = warpSum(st.skipped), c = warpSum(raysHit);
+    if (lane == 0 && P.stats) {
+      atomicAdd(&P.stats->samplesTaken, a);
+      atomicAdd(&P.stats->samplesSkipped, b);
+      atomicAdd(&P.stats->raysHit, c);
+    }
+  }
+  retireWarp(P.sched, lane);
+}
+
+// Background sweep: every pixel outside the tile-aligned screen rectangle of the volumes gets what a missed ray
+// produces (see the in-kernel fast path above), one thread per pixel in row-major order — fully coalesced 512 B
+// accumulation and 128 B colour / mirror stores.  Runs on a second stream next to the frame kernel, which then
+// schedules only the tiles inside the rectangle.
+__global__ void __launch_bounds__(256) dvrBackgroundSweepKernel(const __grid_constant__ FrameLaunch P)
+{
+  const bool initFrame = P.frameID == 0 && P.checkerboardID <= 0;
+  const AccumCtx actx{P.width, P.height, P.format, P.frameID, P.checkerboardID, P.fb};
+  const float4 bg = P.background;
+  const size_t n = (size_t)P.width * P.height;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    const uint32_t y = (uint32_t)(i / P.width), x = (uint32_t)(i - (size_t)y * P.width);
+    if ((int)y >= P.missY0 && (int)y < P.missY1 && (int)x >= P.missX0 && (int)x < P.missX1)
+      continue; // the tiles own the inside
+    for (int it = 0; it < P.numIterations; ++it)
+      accumResults(actx, x, y, bg, 1e30f, f3(bg.x, bg.y, bg.z), f3(0.f, 0.f, 0.f), 0u, ~0u, ~0u, it, initFrame && it == 0);
+  }
+}
+
+int launchBackgroundSweep(const FrameLaunch &p, cudaStream_t s)
+{
+  const size_t n = (size_t)p.width * p.height;
+  if (p.fb.outMirror) {
+    // Colour is mirrored to pinned host memory: the sweep is bound by PCIe, not by the SMs.  A thin grid of small
+    // CTAs (64 threads, ~3 K registers) fits beside the frame kernel's two resident CTAs per SM, so its posted
+    // stores drain over the whole march instead of holding a CTA slot of the march hostage.
+    dvrBackgroundSweepKernel<<<(unsigned)smCount() * 2u, 64, 0, s>>>(p);
+  } else {
+    // device-only: a wide grid that is done in a few tens of microseconds and then frees the SMs
+    const unsigned want = (unsigned)((n + 255) / 256);
+    const unsigned cap = (unsigned)smCount() * 2u;
+    dvrBackgroundSweepKernel<<<want < cap ? want : cap, 256, 0, s>>>(p);
+  }
+  DVR_CUDA(cudaGetLastError());
+  countLaunch();
+  return DVR_OK;
+}
+
+template <bool SKIP, bool STATS, bool SINGLE, int KIND, bool DPT>
+static int launchFrameT(const FrameLaunch &p, cudaStream_t s)
+{
+  constexpr int G = (DPT || !SINGLE) ? 1 : (KIND >= FIELD_NANOVDB ? DVR_DEPTH_LANES_NVDB : DVR_DEPTH_LANES);
+  static int blocksPerSm = 0;
+  if (blocksPerSm == 0) {
+    DVR_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(
+        &blocksPerSm, dvrFrameKernel<SKIP, STATS, SINGLE, KIND, DPT, G>, kBlockThreads, 0));
+    if (blocksPerSm < 1)
+      blocksPerSm = 1;
+  }
+  const uint32_t nTiles = p.tilesW * p.tilesH;
+  const uint32_t warpsPerBlock = kBlockThreads / 32;
+  uint32_t grid = (uint32_t)(smCount() * blocksPerSm);
+  const uint32_t need = (nTiles + warpsPerBlock - 1) / warpsPerBlock;
+  if (grid > need)
+    grid = need;
+  if (grid == 0)
+    grid = 1;
+  dvrFrameKernel<SKIP, STATS, SINGLE, KIND, DPT, G><<<grid, kBlockThreads, 0, s>>>(p);
+  DVR_CUDA(cudaGetLastError());
+  countLaunch();
+  return DVR_OK;
+}
+
+template <bool SKIP, bool STATS>
+static int launchFrameK(const FrameLaunch &p, cudaStream_t s)
+{
+  if (p.nInst != 1)
+    return launchFrameT<SKIP, STATS, false, -1, false>(p, s);
+  if (p.inl[0].v.f.kind == FIELD_NANOVDB)
+    return launchFrameT<SKIP, STATS, true, FIELD_NANOVDB, false>(p, s);
+  if (p.inl[0].v.f.kind == FIELD_NANOVDB_QUANT) {
+    if (STATS) // instrumentation is not worth a dedicated instantiation: the multi-volume kernel dispatches at run time
+      return launchFrameT<SKIP, STATS, false, -1, false>(p, s);
+    return launchFrameT<SKIP, false, true, FIELD_NANOVDB_QUANT, false>(p, s);
+  }
+  return launchFrameT<SKIP, STATS, true, FIELD_STRUCTURED, false>(p, s);
+}
+
+int launchFrame(const FrameLaunch &p, bool skip, bool stats, cudaStream_t s)
+{
+  if (p.integrator == DVR_INTEGRATOR_DPT || p.integrator == DVR_INTEGRATOR_TEST) {
+    // delta tracking has no fixed-step lattice (no SKIP/STATS variants); the test renderer shares the instantiation
+    if (p.nInst != 1)
+      return launchFrameT<false, false, false, -1, true>(p, s);
+    if (p.inl[0].v.f.kind == FIELD_NANOVDB)
+      return launchFrameT<false, false, true, FIELD_NANOVDB, true>(p, s);
+    if (p.inl[0].v.f.kind == FIELD_NANOVDB_QUANT)
+      return launchFrameT<false, false, true, FIELD_NANOVDB_QUANT, true>(p, s);
+    return launchFrameT<false, false, true, FIELD_STRUCTURED, true>(p, s);
+  }
+  if (stats)
+    return skip ? launchFrameK<true, true>(p, s) : launchFrameK<false, true>(p, s);
+  return skip ? launchFrameK<true, false>(p, s) : launchFrameK<false, false>(p, s);
+}
+
+// ----------------------------------------------------------------------------------------------
+// self-test of latticeAdvance(): closed form vs the literal `while (n > 0 && t <= tUpper) t += step` loop on
+// pseudo-random operands (Philox), including power-of-two steps (round-to-even ties) and tiny / huge t
+__global__ void dvrSelftestLatticeKernel(uint32_t count, unsigned long long seed, unsigned int *mismatches)
+{
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= count)
+    return;
+  Philox rng;
+  rng.init(seed + i, 0ull);
+  const float4 r = rng.uniform4();
+  const float4 q = rng.uniform4();
+  float t, step;
+  switch (i % 5u) {
+  case 0: t = r.x * 4000.f; step = r.y * 2.f + 1e-3f; break;
+  case 1: t = r.x * 10.f; step = exp2f(floorf(r.y * 15.f) - 12.f); break;
+  case 2: t = exp2f(floorf(r.x * 17.f) - 3.f) * (1.f + r.z); step = exp2f(floorf(r.y * 24.f) - 20.f) * 1.5f; break;
+  case 3: t = r.x * 1e-3f; step = r.y * 0.1f; break;
+  default: t = r.x * 3000.f + 1000.f; step = 1.f; break;
+  }
+  const int n = 1 + (int)(q.x * 3000.f);
+  const float tUpper = t + q.y * step * (float)n * 1.5f;
+  float a = t;
+  int ka = 0;
+  for (int k = n; k > 0 && a <= tUpper; --k) {
+    a = __fadd_rn(a, step);
+    ++ka;
+  }
+  int kb;
+  const float b = latticeAdvance(t, step, n, tUpper, kb);
+  if (__float_as_int(a) != __float_as_int(b) || ka != kb)
+    atomicAdd(mismatches, 1u);
+}
+
+int launchSelftestLattice(uint32_t count, unsigned long long seed, unsigned int *mismatches, cudaStream_t s)
+{
+  dvrSelftestLatticeKernel<<<(count + 255) / 256, 256, 0, s>>>(count, seed, mismatches);
+  DVR_CUDA(cudaGetLastError());
+  countLaunch();
+  return DVR_OK;
+}
+
+// ----------------------------------------------------------------------------------------------
+// sort-last partial render: premultiplied (C,A) + entry depth of ONE slab on the global lattice
+// ----------------------------------------------------------------------------------------------
+template <bool SKIP, bool STATS>
+__global__ void __launch_bounds__(kBlockThreads, 2) dvrPartialKernel(const __grid_constant__ PartialLaunch P)
+{
+  __shared__ float4 s_tf[DVR_TF_SIZE];
+  const int lane = threadIdx.x & 31;
+  for (int i = threadIdx.x; i < DVR_TF_SIZE; i += blockDim.x)
+    s_tf[i] = __ldg(&P.inst.v.tf[i]);
+  __syncthreads();
+
+  MarchStats st{0ull, 0ull};
+  const uint32_t nTiles = P.tilesW * P.tilesH;
+  const bool centered = P.integrator == DVR_INTEGRATOR_RAYCAST;
+  for (uint32_t tile = nextTile(P.sched, lane); tile < nTiles; tile = nextTile(P.sched, lane)) {
+    const uint32_t tyIdx = P.tileY0 + tile / P.tilesW, txIdx = P.tileX0 + tile % P.tilesW;
+    const uint32_t px = txIdx * kTileW + (lane % kTileW), py = tyIdx * kTileH + (lane / kTileW);
+    if (px >= P.width || py >= P.height)
+      continue;
+    Philox rng;
+    rng.init((unsigned long long)(int)(py * P.width + px), (unsigned long long)P.frameID * 512ull);
+    const float4 r = rng.uniform4();
+    const float sx = __fmul_rn(centered ? (float)px : __fadd_rn((float)px, r.x), P.invW);
+    const float sy = __fmul_rn(centered ? (float)py : __fadd_rn((float)py, r.y), P.invH);
+    float3 org, dir;
+    cameraCreateRay(P.cam, sx, sy, r.z, r.w, org, dir);
+    float3 color = f3(0.f, 0.f, 0.f);
+    float opacity = 0.f;
+    uint32_t objID = ~0u, instID = ~0u;
+    bool anyHit = false;
+    const float depth = rayMarchAllVolumes<SKIP, true, STATS, true, FIELD_STRUCTURED>(&P.inst, 1, TfSelectSingle{s_tf}, org, dir, FLT_MAX,
+        P.invSamplingRate, rng, color, opacity, objID, instID, st, P.cellBitmap, anyHit);
+    const uint32_t idx = px + py * P.width;
+    P.partialRgba[idx] = make_float4(color.x, color.y, color.z, opacity);
+    P.partialDepth[idx] = fminf(1e30f, depth);
+  }
+  if (STATS) {
+    const unsigned long long a = warpSum(st.taken), b = warpSum(st.skipped);
+    if (lane == 0 && P.stats) {
+      atomicAdd(&P.stats->samplesTaken, a);
+      atomicAdd(&P.stats->samplesSkipped, b);
+    }
+  }
+  retireWarpAndSignal(P.sched, lane, P.sync);
+}
+
+template <bool SKIP, bool STATS>
+static int launchPartialT(const PartialLaunch &p, cudaStream_t s)
+{
+  static int bps = 0;
+  if (bps == 0) {
+    DVR_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, dvrPartialKernel<SKIP, STATS>, kBlockThreads, 0));
+    if (bps < 1)
+      bps = 1;
+  }
+  const uint32_t nTiles = p.tilesW * p.tilesH;
+  uint32_t grid = (uint32_t)(smCount() * bps);
+  const uint32_t need = (nTiles + 7) / 8;
+  if (grid > need)
+    grid = need;
+  if (grid == 0)
+    grid = 1;
+  dvrPartialKernel<SKIP, STATS><<<grid, kBlockThreads, 0, s>>>(p);
+  DVR_CUDA(cudaGetLastError());
+  countLaunch();
+  return DVR_OK;
+}
+
+int launchPartial(const PartialLaunch &p, cudaStream_t s)
+{
+  if (p.stats)
+    return p.skip ? launchPartialT<true, true>(p, s) : launchPartialT<false, true>(p, s);
+  return p.skip ? launchPartialT<true, false>(p, s) : launchPartialT<false, false>(p, s);
+}
+
+// ----------------------------------------------------------------------------------------------
+// `over` compositing of two partial images (front-to-back, premultiplied)
+// ----------------------------------------------------------------------------------------------
+__global__ void dvrCompositeOverKernel(float4 *__restrict__ front, float *__restrict__ frontDepth,
+    const float4 *__restrict__ back, const float *__restrict__ backDepth, size_t begin, size_t end,
+    bool backIsInFront)
+{
+  const size_t i = begin + blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  if (i >= end)
+    return;
+  float4 a = front[i];
+  float4 b = back[i];
+  if (backIsInFront) {
+    const float4 t = a;
+    a = b;
+    b = t;
+  }
+  const float k = 1.f - a.w;
+  front[i] = make_float4(a.x + k * b.x, a.y + k * b.y, a.z + k * b.z, a.w + k * b.w);
+  if (frontDepth && backDepth)
+    frontDepth[i] = fminf(frontDepth[i], backDepth[i]);
+}
+
+int launchCompositeOver(float4 *front, float *frontDepth, const float4 *back, const float *backDepth,
+    size_t begin, size_t end, bool backIsInFront, cudaStream_t s)
+{
+  if (end <= begin)
+    return DVR_OK;
+  const size_t n = end - begin;
+  dvrCompositeOverKernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(
+      front, frontDepth, back, backDepth, begin, end, backIsInFront);
+  DVR_CUDA(cudaGetLastError());
+  countLaunch();
+  return DVR_OK;
+}
+
+// ----------------------------------------------------------------------------------------------
+// K3: resolve a composited partial image (quirk Q2 + background + accumulate/tonemap/encode)
+// ----------------------------------------------------------------------------------------------
+__global__ void dvrResolveKernel(const __grid_constant__ ResolveLaunch R)
+{
+  const size_t i = R.pixelBegin + blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  if (i >= R.pixelEnd)
+    return;
+  const float4 pc = R.partialRgba[i];
+  const float pd = R.partialDepth ? R.partialDepth[i] : 1e30f;
+  float3 color = f3(pc.x, pc.y, pc.z);
+  float opacity = pc.w;
+  color = color * opacity;
+  const float oneMinus = 1.f - opacity;
+  color.x += R.background.x * oneMinus;
+  color.y += R.background.y * oneMinus;
+  color.z += R.background.z * oneMinus;
+  opacity += R.background.w * oneMinus;
+
+  const AccumCtx P{R.width, R.height, R.format, R.frameID, -1, R.fb};
+  const bool hit = pd < 1e30f;
+  const uint32_t px = (uint32_t)(i % R.width), py = (uint32_t)(i / R.width);
+  accumResults(P, px, py, make_float4(color.x, color.y, color.z, opacity), pd, color, f3(0.f, 0.f, 0.f), 0u,
+      hit ? R.objId : ~0u, hit ? R.instId : ~0u, 0, R.frameID == 0);
+}
+
+int launchResolve(const ResolveLaunch &r, cudaStream_t s)
+{
+  if (r.pixelEnd <= r.pixelBegin)
+    return DVR_OK;
+  const size_t n = r.pixelEnd - r.pixelBegin;
+  dvrResolveKernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(r);
+  DVR_CUDA(cudaGetLastError());
+  countLaunch();
+  return DVR_OK;
+}
+
+// ----------------------------------------------------------------------------------------------
+// sort-last direct send: composite the slabs' partial images (peer loads over NVLink) in per-pixel
+// view order and resolve, in one kernel
+// ----------------------------------------------------------------------------------------------
+__device__ __forceinline__ void resolvePixel(const ResolveLaunch &R, size_t i, float4 pc, float pd)
+{
+  float3 color = f3(pc.x, pc.y, pc.z);
+  float opacity = pc.w;
+  color = color * opacity; // Raycast_ptx.cu:159
+  const float oneMinus = __fsub_rn(1.f, opacity);
+  color.x = __fmaf_rn(R.background.x, oneMinus, color.x);
+  color.y = __fmaf_rn(R.background.y, oneMinus, color.y);
+  color.z = __fmaf_rn(R.background.z, oneMinus, color.z);
+  opacity = __fmaf_rn(R.background.w, oneMinus, opacity);
+  const AccumCtx P{R.width, R.height, R.format, R.frameID, -1, R.fb};
+  const bool hit = pd < 1e30f;
+  const uint32_t px = (uint32_t)(i % R.width), py = (uint32_t)(i / R.width);
+  accumResults(P, px, py, make_float4(color.x, color.y, color.z, opacity), pd, color, f3(0.f, 0.f, 0.f), 0u,
+      hit ? R.objId : ~0u, hit ? R.instId : ~0u, 0, R.frameID == 0);
+}
+
+__global__ void __launch_bounds__(256) dvrPeerResolveKernel(const __grid_constant__ PeerResolveLaunch L)
+{
+  const size_t i = L.r.pixelBegin + blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  if (i < L.r.pixelEnd) {
+    const uint32_t px = (uint32_t)(i % L.r.width), py = (uint32_t)(i / L.r.width);
+    bool hit = true;
+    bool ascending = true;
+    if (L.cull && L.missValid
+        && ((int)px < L.missX0 || (int)px >= L.missX1 || (int)py < L.missY0 || (int)py >= L.missY1)) {
+      hit = false; // outside the screen rectangle of the bounds: no ray of this pixel can hit
+    } else {
+      // the primary ray exactly as the partial march generated it (same Philox stream, same arithmetic)
+      Philox rng;
+      rng.init((unsigned long long)(int)(py * L.r.width + px), (unsigned long long)L.r.frameID * 512ull);
+      const float4 r = rng.uniform4();
+      const bool centered = L.integrator == DVR_INTEGRATOR_RAYCAST;
+      const float sx = __fmul_rn(centered ? (float)px : __fadd_rn((float)px, r.x), L.invW);
+      const float sy = __fmul_rn(centered ? (float)py : __fadd_rn((float)py, r.y), L.invH);
+      float3 org, dir;
+      cameraCreateRay(L.cam, sx, sy, r.z, r.w, org, dir);
+      float3 lo = org, ld = dir;
+      if (!L.identity) {
+        lo = xfmPoint(L.xfm, org);
+        ld = xfmVector(L.xfm, dir);
+      }
+      if (L.cull) {
+        float t0, t1;
+        hit = intersectVolumeBox(L.boundsLo, L.boundsHi, lo, ld, 0.f, FLT_MAX, t0, t1);
+      }
+      ascending = ld.z >= 0.f; // rays travelling towards +z (object space) meet the low-z slab first
+    }
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    float depth = 1e30f;
+    if (hit) {
+      // (b) issue all peer loads first (independent), then composite front to back
+      float4 part[kMaxSlabs];
+      float pdep[kMaxSlabs];
+#pragma unroll
+      for (int k = 0; k < kMaxSlabs; ++k) {
+        if (k < L.nSlabs) {
+          const int sidx = ascending ? k : L.nSlabs - 1 - k;
+          part[k] = __ldcv(&L.rgba[sidx][i]); // volatile load: another GPU wrote this line
+          pdep[k] = L.depth[sidx] ? __ldcv(&L.depth[sidx][i]) : 1e30f;
+        }
+      }
+#pragma unroll
+      for (int k = 0; k < kMaxSlabs; ++k) {
+        if (k < L.nSlabs) {
+          const float w = __fsub_rn(1.f, acc.w);
+          acc.x = __fmaf_rn(w, part[k].x, acc.x);
+          acc.y = __fmaf_rn(w, part[k].y, acc.y);
+          acc.z = __fmaf_rn(w, part[k].z, acc.z);
+          acc.w = __fmaf_rn(w, part[k].w, acc.w);
+          depth = fminf(depth, pdep[k]);
+        }
+      }
+    }
+    resolvePixel(L.r, i, acc, depth);
+  }
+}
+
+int launchPeerResolve(const PeerResolveLaunch &p, cudaStream_t s)
+{
+  // The cross-GPU ordering of the sync variant brackets the launch with two one-thread kernels: a single
+  // system-scope wait before (instead of one fence per CTA) and a single release after (the kernel
+  // boundary orders every peer store of the composite before the flag).
+  if (p.sync.nWait) {
+    const int rc = launchWaitFlags(p.sync.wait, p.sync.nWait, p.sync.waitValue, p.sync.errorFlag, s);
+    if (rc != DVR_OK)
+      return rc;
+  }
+  if (p.r.pixelEnd > p.r.pixelBegin) {
+    const size_t n = p.r.pixelEnd - p.r.pixelBegin;
+    dvrPeerResolveKernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(p);
+    DVR_CUDA(cudaGetLastError());
+    countLaunch();
+  }
+  if (p.sync.nSignal)
+    return launchSignalFlags(p.sync, s);
+  return DVR_OK;
+}
+
+__global__ void dvrScaleVec3Kernel(const float *__restrict__ in, float *__restrict__ out, size_t n, float scale)
+{
+  const size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  if (i < n)
+    out[i] = in[i] * scale;
+}
+
+int launchScaleVec3(const float *in, float *out, size_t nPixels, float scale, cudaStream_t s)
+{
+  const size_t n = nPixels * 3;
+  if (n == 0)
+    return DVR_OK;
+  dvrScaleVec3Kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(in, out, n, scale);
+  DVR_CUDA(cudaGetLastError());
+  countLaunch();
+  return DVR_OK;
+}
+
+} // namespace dvr

@@ -36,19 +36,7 @@ struct NvdbDev
   float vec[3];    // Map::mVecF
   int3 bboxMin;    // index-space bounding box of the active values (RootData::mBBox)
   int codecLog2Bits; // quantised grids: log2(bits per code) — Fp4 2, Fp8 3, Fp16 4, FpN -1 (per leaf: mFlags >> 5)
-  // Apron bricks (built once at field creation, dvr_nvdb_bricks.cu): a dense table over the 8^3 cells of the index
-  // bounding box; entry.x >= 0 selects a 9^3 float brick holding Tree::getValue of voxels [8c, 8c+8]^3 (decoded for
-  // quantised grids), entry.x < 0 says all of those equal the float whose bits are entry.y.  A trilinear stencil
-  // whose base voxel lies in cell c never leaves brick c, so a sample is one table entry (cached per thread) + 8
-  // loads, with no tree walk.  brickTable == nullptr: not built (memory budget), the tree is walked instead.
-  const int2 *brickTable;
-  const float *bricks;
-  int3 brickOrg;  // cell coordinate (index >> 3) of table entry (0,0,0)
-  int3 brickDims; // table extent in cells, z fastest
 };
-
-constexpr int kNvdbBrickEdge = 9;
-constexpr int kNvdbBrickVoxels = kNvdbBrickEdge * kNvdbBrickEdge * kNvdbBrickEdge;
 
 // per-thread cache of the last visited lower node and leaf (the 8 taps of a trilinear stencil almost
 // always share them) — the role nanovdb::ReadAccessor plays in the reference
@@ -61,14 +49,8 @@ struct NvdbCache
   const uint8_t *lower;
   float qMin, qQuantum;    // quantised grids: LeafFnBase::mMinimum / mQuantum of the cached leaf
   int qLog2Bits;           //                  log2(bits per code) of the cached leaf
-  int bx, by, bz;          // apron-brick key (coords >> 3) of the cached table entry
-  const float *brick;      // nullptr: cell (bx,by,bz) is the constant brickConst
-  float brickConst;
   __device__ __forceinline__ void reset()
   {
-    bx = by = bz = 0x7fffffff;
-    brick = nullptr;
-    brickConst = 0.f;
     lx = ly = lz = nx = ny = nz = 0x7fffffff;
     leaf = lower = nullptr;
     leafTile = 0.f;
@@ -186,61 +168,28 @@ __device__ __forceinline__ float nvdbSampleTrilinear(const NvdbDev &g, NvdbCache
   const int i = (int)fi, j = (int)fj, k = (int)fk;
   const float u = __fsub_rn(idx.x, fi), v = __fsub_rn(idx.y, fj), w = __fsub_rn(idx.z, fk);
   float v000, v001, v011, v010, v100, v101, v111, v110;
-  bool viaBrick = false;
-  if (g.brickTable) {
-    const int kx = i >> 3, ky = j >> 3, kz = k >> 3;
-    viaBrick = (kx == c.bx) & (ky == c.by) & (kz == c.bz);
-    if (!viaBrick) {
-      const unsigned tx = (unsigned)(kx - g.brickOrg.x), ty = (unsigned)(ky - g.brickOrg.y),
-                     tz = (unsigned)(kz - g.brickOrg.z);
-      if ((tx < (unsigned)g.brickDims.x) & (ty < (unsigned)g.brickDims.y) & (tz < (unsigned)g.brickDims.z)) {
-        const int2 e = __ldg(g.brickTable + ((size_t)tx * g.brickDims.y + ty) * g.brickDims.z + tz);
-        c.bx = kx;
-        c.by = ky;
-        c.bz = kz;
-        c.brick = e.x >= 0 ? g.bricks + (size_t)e.x * kNvdbBrickVoxels : nullptr;
-        c.brickConst = __int_as_float(e.y);
-        viaBrick = true;
-      }
-    }
-  }
-  if (viaBrick) {
-    if (c.brick) {
-      const float *b = c.brick + ((i & 7) * (kNvdbBrickEdge * kNvdbBrickEdge) + (j & 7) * kNvdbBrickEdge + (k & 7));
-      v000 = __ldg(b);
-      v001 = __ldg(b + 1);
-      v010 = __ldg(b + kNvdbBrickEdge);
-      v011 = __ldg(b + kNvdbBrickEdge + 1);
-      v100 = __ldg(b + kNvdbBrickEdge * kNvdbBrickEdge);
-      v101 = __ldg(b + kNvdbBrickEdge * kNvdbBrickEdge + 1);
-      v110 = __ldg(b + kNvdbBrickEdge * kNvdbBrickEdge + kNvdbBrickEdge);
-      v111 = __ldg(b + kNvdbBrickEdge * kNvdbBrickEdge + kNvdbBrickEdge + 1);
+  v000 = nvdbGetValue<QUANT>(g, c, i, j, k); // positions the leaf cache on the stencil's base voxel
+  if (((i & 7) < 7) & ((j & 7) < 7) & ((k & 7) < 7)) {
+    // whole stencil inside the cached leaf (or constant region): seven independent loads, no tree walk
+    if (c.leaf) {
+      const uint32_t n = (uint32_t)(((i & 7) << 6) | ((j & 7) << 3) | (k & 7));
+      v001 = nvdbLeafValue<QUANT>(c, n + 1);
+      v010 = nvdbLeafValue<QUANT>(c, n + 8);
+      v011 = nvdbLeafValue<QUANT>(c, n + 9);
+      v100 = nvdbLeafValue<QUANT>(c, n + 64);
+      v101 = nvdbLeafValue<QUANT>(c, n + 65);
+      v110 = nvdbLeafValue<QUANT>(c, n + 72);
+      v111 = nvdbLeafValue<QUANT>(c, n + 73);
     } else
-      v000 = v001 = v010 = v011 = v100 = v101 = v110 = v111 = c.brickConst;
+      v001 = v010 = v011 = v100 = v101 = v110 = v111 = c.leafTile;
   } else {
-    v000 = nvdbGetValue<QUANT>(g, c, i, j, k); // positions the leaf cache on the stencil's base voxel
-    if (((i & 7) < 7) & ((j & 7) < 7) & ((k & 7) < 7)) {
-      // whole stencil inside the cached leaf (or constant region): seven independent loads, no tree walk
-      if (c.leaf) {
-        const uint32_t n = (uint32_t)(((i & 7) << 6) | ((j & 7) << 3) | (k & 7));
-        v001 = nvdbLeafValue<QUANT>(c, n + 1);
-        v010 = nvdbLeafValue<QUANT>(c, n + 8);
-        v011 = nvdbLeafValue<QUANT>(c, n + 9);
-        v100 = nvdbLeafValue<QUANT>(c, n + 64);
-        v101 = nvdbLeafValue<QUANT>(c, n + 65);
-        v110 = nvdbLeafValue<QUANT>(c, n + 72);
-        v111 = nvdbLeafValue<QUANT>(c, n + 73);
-      } else
-        v001 = v010 = v011 = v100 = v101 = v110 = v111 = c.leafTile;
-    } else {
-      v001 = nvdbGetValue<QUANT>(g, c, i, j, k + 1);
-      v011 = nvdbGetValue<QUANT>(g, c, i, j + 1, k + 1);
-      v010 = nvdbGetValue<QUANT>(g, c, i, j + 1, k);
-      v100 = nvdbGetValue<QUANT>(g, c, i + 1, j, k);
-      v101 = nvdbGetValue<QUANT>(g, c, i + 1, j, k + 1);
-      v111 = nvdbGetValue<QUANT>(g, c, i + 1, j + 1, k + 1);
-      v110 = nvdbGetValue<QUANT>(g, c, i + 1, j + 1, k);
-    }
+    v001 = nvdbGetValue<QUANT>(g, c, i, j, k + 1);
+    v011 = nvdbGetValue<QUANT>(g, c, i, j + 1, k + 1);
+    v010 = nvdbGetValue<QUANT>(g, c, i, j + 1, k);
+    v100 = nvdbGetValue<QUANT>(g, c, i + 1, j, k);
+    v101 = nvdbGetValue<QUANT>(g, c, i + 1, j, k + 1);
+    v111 = nvdbGetValue<QUANT>(g, c, i + 1, j + 1, k + 1);
+    v110 = nvdbGetValue<QUANT>(g, c, i + 1, j + 1, k);
   }
 #define DVR_LERP(a, b, t) __fmaf_rn((t), __fsub_rn((b), (a)), (a))
   const float r = DVR_LERP(DVR_LERP(DVR_LERP(v000, v001, w), DVR_LERP(v010, v011, w), v),
