@@ -228,7 +228,7 @@ struct TfSelectSingle
 
 // KIND: FIELD_STRUCTURED / FIELD_NANOVDB for the single-volume kernels, -1 for the multi-volume kernel
 #ifndef DVR_OCC_NVDB
-#define DVR_OCC_NVDB 3 // the NanoVDB march chases pointers; A/B on C5 (batch 1): 3/4/5/6 CTAs = 810/732/642/612 fps
+#define DVR_OCC_NVDB 2 // brick sampling wants registers (no spills at 128), not warps; tree walk alone, batch 1: 3/4/5/6 CTAs = 810/732/642/612 fps
 #endif
 // G: depth lanes per ray (see marchSegment); the warp's 8x4 tile is then rendered in G passes of 32/G pixels.
 #ifndef DVR_DEPTH_LANES

@@ -15,7 +15,8 @@ namespace dvr {
 #define DVR_BATCH 4 // field fetches issued back-to-back before compositing (memory-level parallelism)
 #endif
 #ifndef DVR_BATCH_NVDB
-#define DVR_BATCH_NVDB 1 // NanoVDB fetches are tree walks with their own loads in flight; A/B on C5: 1/2 = 810/635 fps
+#define DVR_BATCH_NVDB 2 // samples come from apron bricks (8 plain loads): A/B on C5 with 2 CTAs/SM: 1 (3 CTAs) / 2 / 4 = 2450/2909/2958 fps;
+                         // the tree-walk fallback alone preferred 1 (810 vs 635 fps at 2)
 #endif
 
 #ifndef DVR_FASTPOW
