@@ -159,3 +159,86 @@ def test_multithreaded_object_creation():
     assert not errs
     assert not [m for m in d.messages if m[0] == A.SEVERITY_FATAL_ERROR]
     d.close()
+
+
+def test_parameter_introspection_as_tsd_walks_it():
+    """tsd/src/tsd/core/Object.cpp:350-424 (parseANARIObjectInfo): for every renderer subtype the application asks for
+    the parameter list and then, per parameter, for description / default / minimum / maximum / value.  Values for the
+    renderers are those of devices/rtx/visrtx_device.json; every listed parameter must be answerable."""
+    d = A.Device()
+    for st in d.subtypes(A.RENDERER):
+        params = d.object_info(A.RENDERER, st, "parameter", A.PARAMETER_LIST)
+        assert params and ("background", A.FLOAT32_VEC4) in params, st
+        for name, t in params:
+            desc = d.parameter_info(A.RENDERER, st, name, t, "description", A.STRING)
+            assert isinstance(desc, str) and desc, (st, name)
+            if t != A.STRING:
+                d.parameter_info(A.RENDERER, st, name, t, "default", t)  # decodable or None
+    info = lambda st, n, t, what: d.parameter_info(A.RENDERER, st, n, t, what, t)
+    # visrtx_device.json:56-64, 88-96, 129-137
+    assert (info("default", "sampleLimit", A.INT32, "default"), info("default", "sampleLimit", A.INT32, "minimum")) == (128, 0)
+    assert info("default", "sampleLimit", A.INT32, "maximum") is None
+    assert (info("default", "pixelSamples", A.INT32, "default"), info("default", "pixelSamples", A.INT32, "minimum")) == (1, 1)
+    rate = [info("default", "volumeSamplingRate", A.FLOAT32, k) for k in ("default", "minimum", "maximum")]
+    assert rate == [0.125, np.float32(0.001), 10.0]
+    assert info("raycast", "volumeSamplingRate", A.FLOAT32, "default") == 0.125
+    assert info("default", "checkerboarding", A.BOOL, "default") == 0
+    # the single-shot renderer has no accumulation parameters, the path tracer no marching rate
+    names = lambda st: [n for n, _ in d.object_info(A.RENDERER, st, "parameter", A.PARAMETER_LIST)]
+    assert "sampleLimit" not in names("raycast") and "pixelSamples" not in names("raycast")
+    assert "volumeSamplingRate" not in names("dpt") and "maxDepth" in names("dpt")
+    assert info("dpt", "ambientRadiance", A.FLOAT32, "default") == 1.0  # DiffusePathTracer.cpp:41
+    assert info("dpt", "maxDepth", A.INT32, "default") == 5
+    # asking in another type than the parameter's, for an unknown parameter or an unknown subtype: no info
+    assert d.parameter_info(A.RENDERER, "default", "sampleLimit", A.INT32, "default", A.FLOAT32) is None
+    assert d.parameter_info(A.RENDERER, "default", "sampleLimit", A.FLOAT32, "default", A.FLOAT32) is None
+    assert d.parameter_info(A.RENDERER, "default", "noSuchParameter", A.INT32, "default", A.INT32) is None
+    assert d.object_info(A.RENDERER, "debug", "parameter", A.PARAMETER_LIST) is None
+    # NULL subtype on a renderer means its default renderer
+    assert d.object_info(A.RENDERER, None, "parameter", A.PARAMETER_LIST) == d.object_info(
+        A.RENDERER, "default", "parameter", A.PARAMETER_LIST)
+    d.close()
+
+
+def test_introspection_of_the_scene_objects_matches_what_the_device_reads():
+    d = A.Device()
+    par = lambda t, st: dict(d.object_info(t, st, "parameter", A.PARAMETER_LIST))
+    cam = par(A.CAMERA, "perspective")
+    assert cam["fovy"] == A.FLOAT32 and cam["imageRegion"] == A.FLOAT32_BOX2 and "height" not in cam
+    assert "height" in par(A.CAMERA, "orthographic") and "fovy" not in par(A.CAMERA, "orthographic")
+    pi = lambda t, st, n, pt, what, it=None: d.parameter_info(t, st, n, pt, what, pt if it is None else it)
+    assert pi(A.CAMERA, "perspective", "fovy", A.FLOAT32, "default") == np.float32(np.pi / 3)
+    assert pi(A.CAMERA, "perspective", "direction", A.FLOAT32_VEC3, "default") == (0.0, 0.0, 1.0)  # Camera.cpp:74
+    assert pi(A.CAMERA, "perspective", "imageRegion", A.FLOAT32_BOX2, "default") == (0.0, 0.0, 1.0, 1.0)
+    # fields: required data array and its element types, filter values
+    assert pi(A.SPATIAL_FIELD, "structuredRegular", "data", A.ARRAY3D, "required", A.BOOL) == 1
+    et = pi(A.SPATIAL_FIELD, "structuredRegular", "data", A.ARRAY3D, "elementType", A.DATA_TYPE_LIST)
+    assert {A.FLOAT32, A.UFIXED8, A.UFIXED16, A.FIXED16, A.FLOAT64} <= set(et)
+    assert pi(A.SPATIAL_FIELD, "structuredRegular", "filter", A.STRING, "value", A.STRING_LIST) == ["linear", "nearest"]
+    assert pi(A.SPATIAL_FIELD, "structuredRegular", "filter", A.STRING, "default") == "linear"
+    assert pi(A.SPATIAL_FIELD, "structuredRegular", "spacing", A.FLOAT32_VEC3, "default") == (1.0, 1.0, 1.0)
+    assert pi(A.SPATIAL_FIELD, "nanovdb", "data", A.ARRAY1D, "elementType", A.DATA_TYPE_LIST) == [A.UINT8]
+    assert pi(A.SPATIAL_FIELD, "structuredRegular", "origin", A.FLOAT32_VEC3, "required", A.BOOL) == 0
+    # volume: both names of the transfer-function volume answer alike
+    for st in ("transferFunction1D", "scivis"):
+        v = par(A.VOLUME, st)
+        assert v["value"] == A.SPATIAL_FIELD and v["valueRange"] == A.FLOAT32_BOX1 and v["unitDistance"] == A.FLOAT32
+        assert pi(A.VOLUME, st, "valueRange", A.FLOAT32_BOX1, "default") == (0.0, 1.0)
+        assert pi(A.VOLUME, st, "color", A.ARRAY1D, "elementType", A.DATA_TYPE_LIST) == [A.FLOAT32_VEC3, A.FLOAT32_VEC4]
+    # objects without subtypes answer for any subtype string
+    assert par(A.FRAME, None)["channel.color"] == A.DATA_TYPE and par(A.FRAME, "")["size"] == A.UINT32_VEC2
+    assert pi(A.FRAME, None, "size", A.UINT32_VEC2, "default") == (10, 10)
+    assert set(par(A.WORLD, None)) == {"name", "volume", "instance"}
+    assert pi(A.INSTANCE, "transform", "transform", A.FLOAT32_MAT4, "default")[::5] == (1.0, 1.0, 1.0, 1.0)
+    # descriptions and source extensions
+    assert "NanoVDB" in d.object_info(A.SPATIAL_FIELD, "nanovdb", "description", A.STRING)
+    assert d.object_info(A.CAMERA, "orthographic", "sourceExtension", A.STRING) == "ANARI_KHR_CAMERA_ORTHOGRAPHIC"
+    assert pi(A.CAMERA, "perspective", "apertureRadius", A.FLOAT32, "sourceExtension",
+              A.STRING) == "ANARI_KHR_CAMERA_DEPTH_OF_FIELD"
+    exts = d.object_info(A.RENDERER, "default", "extension", A.STRING_LIST)
+    assert "ANARI_KHR_SPATIAL_FIELD_STRUCTURED_REGULAR" in exts and "ANARI_NV_ARRAY_CUDA" in exts
+    # every advertised subtype of every object type has a parameter list
+    for t in (A.CAMERA, A.SPATIAL_FIELD, A.VOLUME, A.RENDERER, A.INSTANCE):
+        for st in d.subtypes(t):
+            assert d.object_info(t, st, "parameter", A.PARAMETER_LIST), (t, st)
+    d.close()

@@ -18,7 +18,7 @@ LIB_PATH = os.environ.get("ANARI_B200_LIB") or os.path.join(_HERE, "libanari_lib
 # enums (include/anari/anari.h)
 UNKNOWN = 0
 DATA_TYPE, STRING, VOID_POINTER, BOOL = 100, 101, 102, 103
-STRING_LIST, PARAMETER_LIST = 150, 152
+STRING_LIST, DATA_TYPE_LIST, PARAMETER_LIST = 150, 151, 152
 STATUS_CALLBACK, FRAME_COMPLETION_CALLBACK = 202, 203
 DEVICE, ARRAY1D, ARRAY2D, ARRAY3D, CAMERA, FRAME, GROUP, INSTANCE, RENDERER, SPATIAL_FIELD, VOLUME, WORLD = (
     501, 504, 505, 506, 507, 508, 510, 511, 514, 517, 518, 519)
@@ -96,6 +96,8 @@ def _load() -> C.CDLL:
     lib.anariFrameReady.argtypes = [vp, vp, C.c_uint32]
     lib.anariDiscardFrame.argtypes = [vp, vp]
     lib.anariGetObjectSubtypes.argtypes = [vp, C.c_int]
+    lib.anariGetObjectInfo.argtypes = [vp, C.c_int, C.c_char_p, C.c_char_p, C.c_int]
+    lib.anariGetParameterInfo.argtypes = [vp, C.c_int, C.c_char_p, C.c_char_p, C.c_int, C.c_char_p, C.c_int]
     lib.anariMapParameterArray1D.argtypes = [vp, vp, C.c_char_p, C.c_int, C.c_uint64, C.POINTER(C.c_uint64)]
     lib.anariUnmapParameterArray.argtypes = [vp, vp, C.c_char_p]
     lib.anariUnloadLibrary.argtypes = [vp]
@@ -235,6 +237,59 @@ class Device:
             out.append(p[i].decode())
             i += 1
         return out
+
+    @staticmethod
+    def _decode_info(ptr, info_type: int):
+        """Turns the pointer an info query returned into a Python value (None when the info does not exist)."""
+        if not ptr:
+            return None
+        if info_type == STRING:
+            return C.cast(ptr, C.c_char_p).value.decode()
+        if info_type == STRING_LIST:
+            p, out, i = C.cast(ptr, C.POINTER(C.c_char_p)), [], 0
+            while p[i]:
+                out.append(p[i].decode())
+                i += 1
+            return out
+        if info_type == DATA_TYPE_LIST:
+            p, out, i = C.cast(ptr, C.POINTER(C.c_int32)), [], 0
+            while p[i] != UNKNOWN:
+                out.append(p[i])
+                i += 1
+            return out
+        if info_type == PARAMETER_LIST:
+            class _P(C.Structure):
+                _fields_ = [("name", C.c_char_p), ("type", C.c_int32)]
+            p, out, i = C.cast(ptr, C.POINTER(_P)), [], 0
+            while p[i].name:
+                out.append((p[i].name.decode(), p[i].type))
+                i += 1
+            return out
+        if info_type in (BOOL, INT32, DATA_TYPE):
+            return C.cast(ptr, C.POINTER(C.c_int32))[0]
+        if info_type == UINT32:
+            return C.cast(ptr, C.POINTER(C.c_uint32))[0]
+        if info_type == UINT32_VEC2:
+            return tuple(C.cast(ptr, C.POINTER(C.c_uint32))[i] for i in range(2))
+        n = {FLOAT32: 1, FLOAT32_VEC2: 2, FLOAT32_BOX1: 2, FLOAT32_VEC3: 3, FLOAT32_VEC4: 4, FLOAT32_BOX2: 4,
+             FLOAT32_BOX3: 6, FLOAT32_MAT3x4: 12, FLOAT32_MAT4: 16}.get(info_type)
+        if n is None:
+            raise ValueError(f"no decoder for ANARI type {info_type}")
+        v = tuple(C.cast(ptr, C.POINTER(C.c_float))[i] for i in range(n))
+        return v[0] if n == 1 else v
+
+    def object_info(self, obj_type: int, subtype, info: str, info_type: int):
+        """anariGetObjectInfo: "parameter" (PARAMETER_LIST), "description" / "sourceExtension" (STRING),
+        "extension" (STRING_LIST)."""
+        st = subtype.encode() if subtype is not None else None
+        return self._decode_info(lib.anariGetObjectInfo(self.handle, obj_type, st, info.encode(), info_type), info_type)
+
+    def parameter_info(self, obj_type: int, subtype, name: str, param_type: int, info: str, info_type: int):
+        """anariGetParameterInfo: "description", "required", "default", "minimum", "maximum", "value",
+        "elementType", "sourceExtension"."""
+        st = subtype.encode() if subtype is not None else None
+        return self._decode_info(lib.anariGetParameterInfo(self.handle, obj_type, st, name.encode(), param_type,
+                                                           info.encode(), info_type), info_type)
 
     # ---- frames
     def render(self, frame):

@@ -565,7 +565,8 @@ static const char *kExtensions[] = {"ANARI_KHR_CAMERA_ORTHOGRAPHIC", "ANARI_KHR_
     "ANARI_KHR_FRAME_COMPLETION_CALLBACK", "ANARI_KHR_INSTANCE_TRANSFORM", "ANARI_KHR_SPATIAL_FIELD_STRUCTURED_REGULAR",
     "ANARI_KHR_VOLUME_TRANSFER_FUNCTION1D", "ANARI_VISRTX_SPATIAL_FIELD_NANOVDB", "ANARI_KHR_RENDERER_BACKGROUND_COLOR", "ANARI_KHR_DEVICE_SYNCHRONIZATION",
     "ANARI_NV_ARRAY_CUDA", "ANARI_NV_FRAME_BUFFERS_CUDA", "ANARI_VISRTX_CUDA_OUTPUT_BUFFERS", "ANARI_VISRTX_ARRAY_CUDA",
-    nullptr};
+    "ANARI_KHR_CAMERA_DEPTH_OF_FIELD", "ANARI_KHR_RENDERER_AMBIENT_LIGHT", "ANARI_KHR_ARRAY1D_REGION",
+    "ANARI_VISRTX_B200_DVR", nullptr};
 
 bool Device::getProperty(const std::string &name, ANARIDataType t, void *mem, uint64_t size, uint32_t)
 { // VisRTXDevice.cpp:520-550
@@ -621,41 +622,7 @@ ANARIObject make(ANARIDevice d, A &&...a)
   return (ANARIObject) new T(dev(d), std::forward<A>(a)...);
 }
 
-// introspection tables (subset of the code-generated queries of the reference, visrtx_device.json)
-const char *kCameraTypes[] = {"perspective", "orthographic", nullptr};
-const char *kFieldTypes[] = {"structuredRegular", "nanovdb", nullptr};
-const char *kVolumeTypes[] = {"transferFunction1D", "scivis", nullptr};
-const char *kRendererTypes[] = {"default", "raycast", "ao", "directLight", "dpt", "test", nullptr};
-const char *kInstanceTypes[] = {"transform", nullptr};
-const char *kNone[] = {nullptr};
 const char *kDeviceTypes[] = {"default", nullptr};
-
-struct ParamInfo
-{
-  const char *name;
-  ANARIDataType type;
-};
-const ANARIParameter kRendererParams[] = {{"background", ANARI_FLOAT32_VEC4}, {"pixelSamples", ANARI_INT32},
-    {"sampleLimit", ANARI_INT32}, {"volumeSamplingRate", ANARI_FLOAT32}, {"checkerboarding", ANARI_BOOL},
-    {"macrocellSkipping", ANARI_BOOL}, {"sortFirstRank", ANARI_INT32}, {"sortFirstRanks", ANARI_INT32},
-    {"maxDepth", ANARI_INT32}, {"ambientRadiance", ANARI_FLOAT32}, {"ambientOcclusionDistance", ANARI_FLOAT32},
-    {"dptReferenceGrid", ANARI_BOOL},
-    {nullptr, ANARI_UNKNOWN}};
-const ANARIParameter kFieldParams[] = {{"data", ANARI_ARRAY3D}, {"origin", ANARI_FLOAT32_VEC3},
-    {"spacing", ANARI_FLOAT32_VEC3}, {"filter", ANARI_STRING}, {nullptr, ANARI_UNKNOWN}};
-const ANARIParameter kVolumeParams[] = {{"value", ANARI_SPATIAL_FIELD}, {"color", ANARI_ARRAY1D},
-    {"opacity", ANARI_ARRAY1D}, {"valueRange", ANARI_FLOAT32_BOX1}, {"unitDistance", ANARI_FLOAT32}, {"id", ANARI_UINT32},
-    {nullptr, ANARI_UNKNOWN}};
-const ANARIParameter kCameraParams[] = {{"position", ANARI_FLOAT32_VEC3}, {"direction", ANARI_FLOAT32_VEC3},
-    {"up", ANARI_FLOAT32_VEC3}, {"imageRegion", ANARI_FLOAT32_BOX2}, {"fovy", ANARI_FLOAT32}, {"aspect", ANARI_FLOAT32},
-    {"height", ANARI_FLOAT32}, {"focusDistance", ANARI_FLOAT32}, {"apertureRadius", ANARI_FLOAT32},
-    {nullptr, ANARI_UNKNOWN}};
-const ANARIParameter kFrameParams[] = {{"size", ANARI_UINT32_VEC2}, {"channel.color", ANARI_DATA_TYPE},
-    {"channel.depth", ANARI_DATA_TYPE}, {"channel.primitiveId", ANARI_DATA_TYPE}, {"channel.objectId", ANARI_DATA_TYPE},
-    {"channel.instanceId", ANARI_DATA_TYPE}, {"channel.albedo", ANARI_DATA_TYPE}, {"channel.normal", ANARI_DATA_TYPE},
-    {"renderer", ANARI_RENDERER}, {"camera", ANARI_CAMERA}, {"world", ANARI_WORLD},
-    {"frameCompletionCallback", ANARI_FRAME_COMPLETION_CALLBACK}, {"frameCompletionCallbackUserData", ANARI_VOID_POINTER},
-    {nullptr, ANARI_UNKNOWN}};
 } // namespace
 
 extern "C" {
@@ -867,48 +834,16 @@ void anariRetain(ANARIDevice d, ANARIObject o)
 }
 
 // ---- introspection / properties ----
-const char **anariGetObjectSubtypes(ANARIDevice, ANARIDataType t)
+const char **anariGetObjectSubtypes(ANARIDevice, ANARIDataType t) { return querySubtypes(t); }
+const void *anariGetObjectInfo(ANARIDevice, ANARIDataType t, const char *subtype, const char *infoName,
+    ANARIDataType infoType)
 {
-  switch (t) {
-  case ANARI_CAMERA: return kCameraTypes;
-  case ANARI_SPATIAL_FIELD: return kFieldTypes;
-  case ANARI_VOLUME: return kVolumeTypes;
-  case ANARI_RENDERER: return kRendererTypes;
-  case ANARI_INSTANCE: return kInstanceTypes;
-  default: return kNone;
-  }
+  return queryObjectInfo(t, subtype, infoName, infoType, b200::kExtensions);
 }
-const void *anariGetObjectInfo(ANARIDevice, ANARIDataType t, const char *, const char *infoName, ANARIDataType infoType)
+const void *anariGetParameterInfo(ANARIDevice, ANARIDataType t, const char *subtype, const char *pname,
+    ANARIDataType ptype, const char *infoName, ANARIDataType infoType)
 {
-  const std::string n = infoName ? infoName : "";
-  if (n == "parameter" && infoType == ANARI_PARAMETER_LIST) {
-    switch (t) {
-    case ANARI_RENDERER: return kRendererParams;
-    case ANARI_SPATIAL_FIELD: return kFieldParams;
-    case ANARI_VOLUME: return kVolumeParams;
-    case ANARI_CAMERA: return kCameraParams;
-    case ANARI_FRAME: return kFrameParams;
-    default: return nullptr;
-    }
-  }
-  if (n == "extension" && infoType == ANARI_STRING_LIST)
-    return b200::kExtensions;
-  return nullptr;
-}
-const void *anariGetParameterInfo(ANARIDevice, ANARIDataType t, const char *, const char *pname, ANARIDataType,
-    const char *infoName, ANARIDataType infoType)
-{
-  static const float rateDefault = 0.125f, rateMin = 1e-3f, rateMax = 10.f;
-  static const int32_t sppDefault = 1, limitDefault = 128;
-  const std::string p = pname ? pname : "", n = infoName ? infoName : "";
-  if (t == ANARI_RENDERER && p == "volumeSamplingRate" && infoType == ANARI_FLOAT32) {
-    if (n == "default") return &rateDefault;
-    if (n == "minimum") return &rateMin;
-    if (n == "maximum") return &rateMax;
-  }
-  if (t == ANARI_RENDERER && p == "pixelSamples" && n == "default" && infoType == ANARI_INT32) return &sppDefault;
-  if (t == ANARI_RENDERER && p == "sampleLimit" && n == "default" && infoType == ANARI_INT32) return &limitDefault;
-  return nullptr;
+  return queryParameterInfo(t, subtype, pname, ptype, infoName, infoType);
 }
 int anariGetProperty(ANARIDevice d, ANARIObject o, const char *name, ANARIDataType t, void *mem, uint64_t size,
     ANARIWaitMask mask)

@@ -402,4 +402,11 @@ struct CudaDeviceScope
   bool active = false;
 };
 
+// ---- introspection (queries.cpp) -----------------------------------------------------------------------------------
+const char **querySubtypes(ANARIDataType type);
+const void *queryObjectInfo(ANARIDataType type, const char *subtype, const char *infoName, ANARIDataType infoType,
+    const char **extensions);
+const void *queryParameterInfo(ANARIDataType type, const char *subtype, const char *paramName, ANARIDataType paramType,
+    const char *infoName, ANARIDataType infoType);
+
 } // namespace b200
