@@ -237,6 +237,10 @@ def test_introspection_of_the_scene_objects_matches_what_the_device_reads():
               A.STRING) == "ANARI_KHR_CAMERA_DEPTH_OF_FIELD"
     exts = d.object_info(A.RENDERER, "default", "extension", A.STRING_LIST)
     assert "ANARI_KHR_SPATIAL_FIELD_STRUCTURED_REGULAR" in exts and "ANARI_NV_ARRAY_CUDA" in exts
+    # the device's own parameters (VisRTXDevice.cpp:455-470)
+    dev = par(A.DEVICE, "default")
+    assert dev["cudaDevice"] == A.INT32 and dev["forceInit"] == A.BOOL and dev["statusCallback"] == A.STATUS_CALLBACK
+    assert pi(A.DEVICE, None, "cudaDevice", A.INT32, "default") == 0
     # every advertised subtype of every object type has a parameter list
     for t in (A.CAMERA, A.SPATIAL_FIELD, A.VOLUME, A.RENDERER, A.INSTANCE):
         for st in d.subtypes(t):

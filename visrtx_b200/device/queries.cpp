@@ -231,6 +231,13 @@ std::vector<ObjectInfo> buildTables()
           ext(P("frameCompletionCallbackUserData", ANARI_VOID_POINTER, "passed to the completion callback"),
               "ANARI_KHR_FRAME_COMPLETION_CALLBACK")},
       {}});
+  // ---- the device itself (VisRTXDevice.cpp:455-470)
+  t.push_back({ANARI_DEVICE, nullptr, "B200 direct-volume-rendering device", "ANARI_KHR_CORE",
+      {kName, P("statusCallback", ANARI_STATUS_CALLBACK, "callback used to report information to the application"),
+          P("statusCallbackUserData", ANARI_VOID_POINTER, "passed to the status callback"),
+          P("cudaDevice", ANARI_INT32, "ordinal of the CUDA device to render on", &kI0, &kI0),
+          P("forceInit", ANARI_BOOL, "initialise CUDA when the device is committed instead of at first use", &kFalse)},
+      {}});
   for (ObjectInfo &o : t) {
     for (const ParamDesc &p : o.params)
       o.list.push_back({p.name, p.type});
