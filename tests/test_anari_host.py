@@ -89,6 +89,45 @@ def test_managed_array_is_zero_initialised_and_mappable():
     d.close()
 
 
+def test_mapping_an_object_array_keeps_its_elements_alive():
+    """The normal ANARI pattern: create instances, put them in an array, release the handles — the array is then the
+    only owner.  Mapping that array must not drop those references (the elements would be deleted while World still
+    reads them); unmap reconciles the old handle list with the new contents."""
+    d = A.Device()
+    groups = [d.new("Group") for _ in range(3)]
+    insts = []
+    for g in groups:
+        i = d.new("Instance", "transform")
+        d.set(i, "group", A.GROUP, g)
+        d.commit(i)
+        insts.append(i)
+    arr = d.new_object_array(insts[:2], A.INSTANCE)
+    for i in insts[:2]:
+        d.release(i)  # the array holds the only reference now
+    world = d.new("World")
+    d.set(world, "instance", A.ARRAY1D, arr)
+    d.commit(world)
+    for _ in range(3):  # repeated map/unmap without edits must be neutral
+        p = d.map_array(arr)
+        assert p
+        d.unmap_array(arr)
+    p = d.map_array(arr)
+    handles = C.cast(p, C.POINTER(C.c_void_p))
+    assert handles[0] == insts[0] and handles[1] == insts[1]
+    d.set(insts[0], "id", A.UINT32, 7)  # still a live object: parameter stores on a freed object would corrupt the heap
+    d.commit(insts[0])
+    handles[1] = insts[2]  # replace one element while mapped
+    d.unmap_array(arr)
+    d.release(insts[2])
+    d.commit(world)
+    lo_hi = d.get_property(world, "bounds", A.FLOAT32_BOX3)  # walks the instance array (flatten)
+    assert lo_hi is not None
+    for o in [world, arr] + groups:
+        d.release(o)
+    assert not [m for m in d.messages if m[0] <= A.SEVERITY_ERROR]
+    d.close()
+
+
 def test_captured_array_deleter_runs_on_release():
     d = A.Device()
     calls = []

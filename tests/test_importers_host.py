@@ -274,6 +274,77 @@ def test_import_vti_skips_multi_component_arrays_and_reports_errors(tmp_path):
         I.import_vti(str(tmp_path / "trunc.vti"))
 
 
+def test_import_vti_rejects_block_sizes_that_overflow(tmp_path):
+    """A crafted vtkZLibDataCompressor header whose (nblocks-1)*blockSize + lastSize wraps past 2^64 to a small value
+    must be refused before any buffer is sized from it (it used to make uncompress() write past the heap block)."""
+    vox = np.arange(24, dtype=np.float32).reshape(2, 3, 4)
+    raw = vox.tobytes()
+    comp = zlib.compress(raw)
+    for nblocks, bs, last in ((3, 1 << 63, len(raw)), (2, (1 << 64) - 8, len(raw) + 8), (1, 0, 0), (2, 16, 32)):
+        head = struct.pack("<QQQ", nblocks, bs, last) + b"".join(struct.pack("<Q", len(comp)) for _ in range(nblocks))
+        body = comp * nblocks
+        blob = (base64.b64encode(head) + base64.b64encode(body)).decode()
+        xml = ('<?xml version="1.0"?>\n<VTKFile type="ImageData" version="1.0" byte_order="LittleEndian" '
+               'header_type="UInt64" compressor="vtkZLibDataCompressor">\n  <ImageData WholeExtent="0 3 0 2 0 1" '
+               'Origin="0 0 0" Spacing="1 1 1">\n    <Piece Extent="0 3 0 2 0 1">\n      <PointData Scalars="d">\n'
+               f'        <DataArray type="Float32" Name="d" format="binary">\n{blob}\n        </DataArray>\n'
+               '      </PointData>\n    </Piece>\n  </ImageData>\n</VTKFile>\n')
+        (tmp_path / "evil.vti").write_text(xml)
+        with pytest.raises(I.ImportError_) as e:
+            I.import_vti(str(tmp_path / "evil.vti"))
+        assert e.value.code == I.ERR_FORMAT
+    # compressed sizes larger than the payload that is present
+    head = struct.pack("<QQQ", 1, len(raw), 0) + struct.pack("<Q", (1 << 64) - 1)
+    blob = (base64.b64encode(head) + base64.b64encode(comp)).decode()
+    (tmp_path / "evil2.vti").write_text(xml.replace(xml[xml.index('format="binary">') + 17:xml.index("\n        </DataArray>")], blob))
+    with pytest.raises(I.ImportError_):
+        I.import_vti(str(tmp_path / "evil2.vti"))
+
+
+def test_import_nvdb_rejects_offsets_that_leave_the_grid(tmp_path):
+    """Node offsets come from the file: a tree whose child offsets point outside the buffer is refused by the importer
+    (before its host min/max walk) instead of being dereferenced."""
+    g = nvdb_writer.fog_sphere(6.0)
+    assert I.lib is not None
+    root_off = 672 + int(g[672 + 24:672 + 32].view(np.int64)[0])
+    ok = tmp_path / "ok.nvdb"
+    g.tofile(ok)
+    I.import_nvdb(str(ok))
+    # (a) root tile count far beyond the buffer
+    bad = g.copy()
+    bad[root_off + 24:root_off + 28] = np.array([1 << 30], np.uint32).view(np.uint8)
+    bad[20:24] = (bad[20:24].view(np.uint32) & ~np.uint32(4)).view(np.uint8)  # clear HasMinMax: force the walk
+    (tmp_path / "tiles.nvdb").write_bytes(bad.tobytes())
+    with pytest.raises(I.ImportError_) as e:
+        I.import_nvdb(str(tmp_path / "tiles.nvdb"))
+    assert e.value.code == I.ERR_FORMAT and "corrupt" in str(e.value)
+    # (b) first tile's child offset past the end
+    bad = g.copy()
+    bad[root_off + 64 + 8:root_off + 64 + 16] = np.array([1 << 40], np.int64).view(np.uint8)
+    (tmp_path / "child.nvdb").write_bytes(bad.tobytes())
+    with pytest.raises(I.ImportError_) as e:
+        I.import_nvdb(str(tmp_path / "child.nvdb"))
+    assert e.value.code == I.ERR_FORMAT
+    # (c) negative child offset
+    bad = g.copy()
+    bad[root_off + 64 + 8:root_off + 64 + 16] = np.array([-(1 << 33)], np.int64).view(np.uint8)
+    (tmp_path / "neg.nvdb").write_bytes(bad.tobytes())
+    with pytest.raises(I.ImportError_):
+        I.import_nvdb(str(tmp_path / "neg.nvdb"))
+
+
+def test_path_helpers_keep_the_importers_conventions(tmp_path):
+    """fileOf/extensionOf/splitString drive the RAW name parser: dims come from '_'-separated tokens of the base name."""
+    v = np.arange(2 * 3 * 4, dtype=np.uint8).reshape(2, 3, 4)
+    d = tmp_path / "dir.with.dots"
+    d.mkdir()
+    p = d / "a__b_4x3x2_uint8.raw"  # consecutive delimiters give empty tokens, as std::getline does
+    v.tofile(p)
+    vf = I.import_raw(str(p))
+    assert vf.dims == (4, 3, 2) and vf.name == "a__b_4x3x2_uint8.raw" and np.array_equal(vf.data, v)
+    assert I.import_volume_file(str(p)).dims == (4, 3, 2)  # extension taken after the LAST dot of the path
+
+
 # ------------------------------------------------------------------------------------------------- range
 def test_compute_scalar_range_normalisation():
     assert I.compute_scalar_range(np.array([3, 200, 17], np.uint8), capi.DVR_UFIXED8) == (np.float32(3 / 255), np.float32(200 / 255))

@@ -9,6 +9,7 @@
 #include <vector>
 
 #include "dvr_internal.h"
+#include "../../include/dvr_nvdb_validate.h"
 
 namespace dvr {
 
@@ -193,6 +194,9 @@ struct DvrVolume
   bool ddaReference = false; // content of the current grid: the reference's build (Q7/Q8) or the conservative one
   float vrLo = 0.f, vrHi = 1.f, oneOverUnitDistance = 1.f;
   uint32_t id = ~0u;
+  // the macrocell grid the majorant buffers were allocated for: an update against a field of another shape is refused
+  size_t allocCells = 0;
+  int3 allocGridDims{0, 0, 0};
 };
 
 static inline float3 v3(const float *p) { return make_float3(p[0], p[1], p[2]); }
@@ -765,6 +769,24 @@ int dvr_field_create_nanovdb(const void *gridData, size_t bytes, int dataIsDevic
   else
     std::memcpy(root, (const uint8_t *)gridData + rootOff, sizeof(root));
 
+  // The device tree walk and the brick gather follow offsets stored in the buffer: validate all of them once on the
+  // host (a device-resident grid is staged for the check) before anything is uploaded.
+  {
+    std::vector<uint8_t> staged;
+    const uint8_t *hostGrid = (const uint8_t *)gridData;
+    if (dataIsDevice) {
+      staged.resize(gridSize);
+      DVR_CUDA(cudaMemcpy(staged.data(), gridData, gridSize, cudaMemcpyDeviceToHost));
+      hostGrid = staged.data();
+    }
+    const int bad = dvr_nvdb_validate_tree(hostGrid, gridSize);
+    if (bad != 0) {
+      setError("dvr_field_create_nanovdb: corrupt NanoVDB tree (node offsets leave the grid buffer, code "
+          + std::to_string(bad) + ")");
+      return DVR_ERR_INVALID_ARGUMENT;
+    }
+  }
+
   auto *f = new DvrField();
   cudaGetDevice(&f->device);
   cudaError_t e = cudaMalloc(&f->nvdbBlob, gridSize);
@@ -990,6 +1012,15 @@ int dvr_volume_update(DvrVolume *v, const float *tfRgba, const float valueRange[
     setError("dvr_volume_update: null argument");
     return DVR_ERR_INVALID_ARGUMENT;
   }
+  {
+    const int3 g = v->field->dev.gridDims;
+    if (v->field->nCells != v->allocCells || g.x != v->allocGridDims.x || g.y != v->allocGridDims.y
+        || g.z != v->allocGridDims.z) {
+      setError("dvr_volume_update: the field's macrocell grid differs from the one this volume was created for; "
+               "destroy and create instead");
+      return DVR_ERR_UNSUPPORTED;
+    }
+  }
   cudaStream_t s = (cudaStream_t)stream;
   DVR_CUDA(cudaMemcpyAsync(v->tf, tfRgba, DVR_TF_SIZE * sizeof(float4), cudaMemcpyHostToDevice, s));
   DVR_CUDA(cudaStreamSynchronize(s)); // tfRgba is caller-owned pageable memory
@@ -1032,6 +1063,8 @@ int dvr_volume_create(const DvrField *field, const float *tfRgba, const float va
   if (e == cudaSuccess)
     e = cudaMalloc(&v->maxOpacities, field->nCells * sizeof(float));
   const int3 g = field->dev.gridDims;
+  v->allocCells = field->nCells;
+  v->allocGridDims = g;
   v->coarseDims = make_int3((g.x + 3) / 4, (g.y + 3) / 4, (g.z + 3) / 4);
   if (e == cudaSuccess)
     e = cudaMalloc(&v->maxOpacitiesCoarse, (size_t)v->coarseDims.x * v->coarseDims.y * v->coarseDims.z * sizeof(float));
@@ -1252,6 +1285,10 @@ static int renderImpl(const DvrFrameParams *p, const DvrCamera *camera, const Dv
     setError("dvr_render: no CUDA device (this library has no CPU fallback)");
     return DVR_ERR_NO_DEVICE;
   }
+  if (stats && !statsDev) {
+    setError("dvr_render_instrumented: statsDev is null");
+    return DVR_ERR_INVALID_ARGUMENT;
+  }
   cudaStream_t s = (cudaStream_t)stream;
 
   FrameLaunch L;
@@ -1374,10 +1411,6 @@ static int renderImpl(const DvrFrameParams *p, const DvrCamera *camera, const Dv
   unsigned int *bitmap = nullptr;
   size_t nWords = 0;
   if (stats) {
-    if (!statsDev) {
-      setError("dvr_render_instrumented: statsDev is null");
-      return DVR_ERR_INVALID_ARGUMENT;
-    }
     DVR_CUDA(cudaMemsetAsync(statsDev, 0, sizeof(DvrRenderStats), s));
     if (nInstances >= 1) {
       const size_t nCells = instances[0].volume->field->nCells;
@@ -1476,8 +1509,24 @@ static int renderPartialImpl(const DvrFrameParams *p, const DvrCamera *camera, c
     setError("dvr_render_partial: null argument");
     return DVR_ERR_INVALID_ARGUMENT;
   }
+  if (!instance->volume->field) {
+    setError("dvr_render_partial: instance without a valid volume");
+    return DVR_ERR_INVALID_ARGUMENT;
+  }
+  if (p->width == 0 || p->height == 0) {
+    setError("dvr_render_partial: empty frame");
+    return DVR_ERR_INVALID_ARGUMENT;
+  }
   if (p->numIterations != 1 || p->checkerboardID >= 0) {
     setError("dvr_render_partial: needs numIterations == 1 and no checkerboarding");
+    return DVR_ERR_UNSUPPORTED;
+  }
+  if (p->integrator != DVR_INTEGRATOR_RAYCAST && p->integrator != DVR_INTEGRATOR_DEFAULT) {
+    setError("dvr_render_partial: only the marching integrators (raycast, default) render partial images");
+    return DVR_ERR_UNSUPPORTED;
+  }
+  if (instance->volume->field->dev.kind != FIELD_STRUCTURED) {
+    setError("dvr_render_partial: slab rendering needs a structuredRegular field");
     return DVR_ERR_UNSUPPORTED;
   }
   if (dvr_device_count() <= 0) {

@@ -286,10 +286,12 @@ void *Array::map()
   if (m_mapped)
     report(ANARI_SEVERITY_WARNING, ANARI_STATUS_INVALID_OPERATION, "array mapped again without unmapping");
   m_mapped = true;
-  if (isObjectType(elementType) && m_data) // elements may be replaced while mapped
-    for (size_t i = 0; i < totalSize(); ++i)
-      if (Object *o = ((Object **)m_data)[i])
-        o->refDec(RefType::INTERNAL);
+  // Elements may be replaced while mapped.  The references held on the current elements are KEPT for the duration of
+  // the map (an element whose only owner is this array must stay alive: World / Group still read it); the handle list
+  // is remembered and reconciled with the new contents at unmap, as helium's ObjectArray does.
+  m_mappedHandles.clear();
+  if (isObjectType(elementType) && m_data && !m_onDevice)
+    m_mappedHandles.assign((Object **)m_data, (Object **)m_data + totalSize());
   return m_data;
 }
 
@@ -322,10 +324,15 @@ void Array::unmap()
     return;
   }
   m_mapped = false;
-  if (isObjectType(elementType) && m_data)
-    for (size_t i = 0; i < totalSize(); ++i)
+  if (isObjectType(elementType) && m_data && !m_onDevice) {
+    for (size_t i = 0; i < totalSize(); ++i) // new contents first, so an element present before and after never hits 0
       if (Object *o = ((Object **)m_data)[i])
         o->refInc(RefType::INTERNAL);
+    for (Object *o : m_mappedHandles)
+      if (o)
+        o->refDec(RefType::INTERNAL);
+    m_mappedHandles.clear();
+  }
   notifyObservers(); // Array.cpp:152-162: data modified => observing field/volume re-finalises
 }
 
@@ -393,6 +400,10 @@ SpatialField::~SpatialField()
   cleanup();
 }
 
+// Generations are drawn from ONE counter for all fields: a new DvrField may reuse the heap address of a destroyed
+// one, so (address, per-object counter) pairs can collide across SpatialField objects — a global stamp cannot.
+static std::atomic<uint64_t> g_fieldGeneration{0};
+
 void SpatialField::cleanup()
 {
   if (m_field) {
@@ -402,7 +413,7 @@ void SpatialField::cleanup()
     m_field = nullptr;
     m_fieldType = -1;
   }
-  ++m_generation;
+  m_generation = ++g_fieldGeneration;
 }
 
 void SpatialField::commitParameters()
@@ -562,11 +573,7 @@ Volume::~Volume()
   if (m_color) m_color->removeObserver(this);
   if (m_opacity) m_opacity->removeObserver(this);
   if (m_field) m_field->removeObserver(this);
-  if (m_volume) {
-    CudaDeviceScope scope(device);
-    cudaStreamSynchronize((cudaStream_t)device->stream());
-    dvr_volume_destroy(m_volume);
-  }
+  dropDeviceVolume();
 }
 
 void Volume::commitParameters()
@@ -607,8 +614,24 @@ void Volume::commitParameters()
   }
 }
 
+void Volume::dropDeviceVolume()
+{
+  if (!m_volume)
+    return;
+  CudaDeviceScope scope(device);
+  cudaStreamSynchronize((cudaStream_t)device->stream());
+  dvr_volume_destroy(m_volume);
+  m_volume = nullptr;
+  m_volumeField = nullptr;
+}
+
 void Volume::finalize()
 {
+  // The device volume references its DvrField by pointer: once that field was destroyed or replaced the volume must
+  // not survive an early return below (isValid() would otherwise vouch for a dangling handle).
+  if (m_volume && (!m_field || !m_field->isValid() || m_volumeField != m_field->handle()
+          || m_volumeFieldGeneration != m_field->generation()))
+    dropDeviceVolume();
   if (!m_known) {
     report(ANARI_SEVERITY_WARNING, ANARI_STATUS_INVALID_ARGUMENT, "unknown volume subtype '%s'", subtype.c_str());
     return;
@@ -644,19 +667,18 @@ void Volume::finalize()
           tf.data())
       != DVR_OK) {
     report(ANARI_SEVERITY_WARNING, ANARI_STATUS_INVALID_ARGUMENT, "transfer function rejected: %s", dvr_last_error());
+    dropDeviceVolume(); // a rejected edit must not leave the previous table rendering as if it were current
     return;
   }
   CudaDeviceScope scope(device);
-  int rc;
-  if (m_volume && m_volumeField == m_field->handle() && m_volumeFieldGeneration == m_field->generation())
+  int rc = DVR_ERR_UNSUPPORTED;
+  if (m_volume) // same field object, same generation (checked above): refresh in place
     rc = dvr_volume_update(m_volume, tf.data(), m_valueRange, m_unitDistance, m_id, device->stream());
-  else {
-    if (m_volume) {
-      cudaStreamSynchronize((cudaStream_t)device->stream());
-      dvr_volume_destroy(m_volume);
-      m_volume = nullptr;
-    }
+  if (rc == DVR_ERR_UNSUPPORTED) { // no volume yet, or the field's macrocell grid no longer matches the allocation
+    dropDeviceVolume();
     rc = dvr_volume_create(m_field->handle(), tf.data(), m_valueRange, m_unitDistance, m_id, device->stream(), &m_volume);
+    if (rc != DVR_OK)
+      m_volume = nullptr;
     m_volumeField = m_field->handle();
     m_volumeFieldGeneration = m_field->generation();
   }

@@ -161,6 +161,7 @@ struct Array : Object
   const void *m_deleterPtr = nullptr;
   std::vector<uint8_t> m_managed;
   bool m_mapped = false;
+  std::vector<Object *> m_mappedHandles; // object arrays: the elements referenced when map() was called
   size_t m_begin = 0, m_end = 0;
   ANARIDataType m_arrayType;
 };
@@ -221,6 +222,7 @@ struct Volume : Object
   uint32_t id() const { return m_id; }
 
  private:
+  void dropDeviceVolume();
   Ref<Array> m_color, m_opacity;
   Ref<SpatialField> m_field;
   float m_uniformColor[4] = {1, 1, 1, 1};

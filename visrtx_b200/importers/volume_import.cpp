@@ -4,6 +4,7 @@
 // parameters of the spatial field it would create.  Pure C++17 + zlib; no CUDA, no ANARI.
 #include "dvr_import.h"
 #include "dvr_b200.h"
+#include "dvr_nvdb_validate.h"
 
 #include <zlib.h>
 
@@ -35,28 +36,31 @@ int fail(int code, const char *fmt, ...)
   return code;
 }
 
-// importer_common.cpp:41-64
-std::string fileOf(const std::string &filepath)
+// Path / token helpers with the behaviour of the TSD importers' (importer_common.cpp:41-64): the base name is
+// everything after the last '/', empty when the path has no directory part; the extension includes its dot.
+std::string fileOf(const std::string &path)
 {
-  const size_t pos = filepath.find_last_of('/');
-  if (pos == std::string::npos)
-    return "";
-  return filepath.substr(pos + 1, filepath.size());
+  const char *begin = path.c_str(), *slash = std::strrchr(begin, '/');
+  return slash ? std::string(slash + 1) : std::string();
 }
-std::string extensionOf(const std::string &filepath)
+std::string extensionOf(const std::string &path)
 {
-  const size_t pos = filepath.rfind('.');
-  if (pos == std::string::npos)
-    return "";
-  return filepath.substr(pos);
+  const char *begin = path.c_str(), *dot = std::strrchr(begin, '.');
+  return dot ? std::string(dot) : std::string();
 }
-std::vector<std::string> splitString(const std::string &s, char delim)
+// getline semantics: consecutive delimiters yield empty tokens, a trailing delimiter yields none
+std::vector<std::string> splitString(const std::string &text, char delim)
 {
-  std::vector<std::string> result;
-  std::istringstream stream(s);
-  for (std::string token; std::getline(stream, token, delim);)
-    result.push_back(token);
-  return result;
+  std::vector<std::string> tokens;
+  size_t from = 0;
+  while (from < text.size()) {
+    size_t to = text.find(delim, from);
+    if (to == std::string::npos)
+      to = text.size();
+    tokens.emplace_back(text, from, to - from);
+    from = to + 1;
+  }
+  return tokens;
 }
 
 size_t sizeOfType(int t)
@@ -426,7 +430,7 @@ int decodeBlock(const char *src, size_t avail, bool isBase64, bool zlibCompresse
       dst.resize(n);
       return true;
     }
-    if (pos + n > avail)
+    if (pos > avail || n > avail - pos) // (pos + n could wrap for a header-supplied n)
       return false;
     dst.assign(raw + pos, raw + pos + n);
     pos += n;
@@ -436,7 +440,7 @@ int decodeBlock(const char *src, size_t avail, bool isBase64, bool zlibCompresse
     if (isBase64) { // header and data are one base64 stream
       std::vector<uint8_t> all;
       base64Decode(src, avail, all, hsz + want);
-      if (all.size() < hsz + want)
+      if (want > SIZE_MAX - hsz || all.size() < hsz + want)
         return fail(DVR_IMPORT_ERR_FORMAT, "[import_VTI] truncated base64 data block");
       if (rdHeader(all.data(), hsz) < want)
         return fail(DVR_IMPORT_ERR_FORMAT, "[import_VTI] data block is smaller than the array it should hold");
@@ -465,24 +469,42 @@ int decodeBlock(const char *src, size_t avail, bool isBase64, bool zlibCompresse
     sizes.assign(head.begin() + 3 * hsz, head.end());
   } else if (!take(nblocks * hsz, sizes))
     return fail(DVR_IMPORT_ERR_FORMAT, "[import_VTI] truncated compression header");
-  uint64_t compressedTotal = 0;
-  for (uint64_t b = 0; b < nblocks; ++b)
-    compressedTotal += rdHeader(sizes.data() + b * hsz, hsz);
-  if (!take(compressedTotal, payload))
-    return fail(DVR_IMPORT_ERR_FORMAT, "[import_VTI] truncated compressed payload");
+  // Every quantity below comes from the file: sizes are bounded by what the array can need (`want` plus one block of
+  // slack) and summed with overflow checks, so neither `total` nor the compressed sizes can wrap into a small
+  // allocation that uncompress() would then overrun.
+  if (blockSize == 0 || blockSize > (uint64_t)1 << 40 || lastSize > blockSize)
+    return fail(DVR_IMPORT_ERR_FORMAT, "[import_VTI] implausible compression block size");
+  if ((nblocks - 1) > (UINT64_MAX - blockSize) / blockSize)
+    return fail(DVR_IMPORT_ERR_FORMAT, "[import_VTI] compressed block sizes overflow");
   const uint64_t total = (nblocks - 1) * blockSize + (lastSize ? lastSize : blockSize);
   if (total < want)
     return fail(DVR_IMPORT_ERR_FORMAT, "[import_VTI] data block is smaller than the array it should hold");
-  out.resize(total);
+  if (total - want > blockSize) // total >= want here; a well-formed stream inflates to exactly the array
+    return fail(DVR_IMPORT_ERR_FORMAT, "[import_VTI] data block is larger than the array it should hold");
+  uint64_t compressedTotal = 0;
+  for (uint64_t b = 0; b < nblocks; ++b) {
+    const uint64_t csz = rdHeader(sizes.data() + b * hsz, hsz);
+    if (csz > avail || compressedTotal > (uint64_t)avail - csz) // cannot exceed the bytes that are there
+      return fail(DVR_IMPORT_ERR_FORMAT, "[import_VTI] truncated compressed payload");
+    compressedTotal += csz;
+  }
+  if (!take((size_t)compressedTotal, payload))
+    return fail(DVR_IMPORT_ERR_FORMAT, "[import_VTI] truncated compressed payload");
+  out.resize((size_t)total);
   size_t in = 0, outPos = 0;
   for (uint64_t b = 0; b < nblocks; ++b) {
     const uint64_t csz = rdHeader(sizes.data() + b * hsz, hsz);
-    uLongf dsz = (uLongf)(b + 1 == nblocks && lastSize ? lastSize : blockSize);
+    if (csz > payload.size() - in)
+      return fail(DVR_IMPORT_ERR_FORMAT, "[import_VTI] compressed block %llu exceeds the payload", (unsigned long long)b);
+    const uint64_t blockOut = b + 1 == nblocks && lastSize ? lastSize : blockSize;
+    uLongf dsz = (uLongf)std::min<uint64_t>(blockOut, out.size() - outPos); // never past the buffer
     if (uncompress(out.data() + outPos, &dsz, payload.data() + in, (uLong)csz) != Z_OK)
       return fail(DVR_IMPORT_ERR_FORMAT, "[import_VTI] zlib error in block %llu", (unsigned long long)b);
-    in += csz;
+    in += (size_t)csz;
     outPos += dsz;
   }
+  if (outPos < want)
+    return fail(DVR_IMPORT_ERR_FORMAT, "[import_VTI] compressed blocks inflate to fewer bytes than the array needs");
   out.resize(want);
   return DVR_IMPORT_OK;
 }
@@ -901,6 +923,14 @@ int importNvdb(const char *filepath, DvrVolumeFile *o)
   t.gridType = rd<uint32_t>(grid + 636);
   const int64_t rootOff = 672 + rd<int64_t>(grid + 672 + 24);
   const bool supported = t.gridType == 1u || (t.gridType >= 13u && t.gridType <= 16u);
+  // every offset the min/max pass below (and later the device) follows comes from the file: check them all first
+  if (supported) {
+    const int bad = dvr_nvdb_validate_tree(grid, gridSize);
+    if (bad != 0) {
+      std::free(grid);
+      return fail(DVR_IMPORT_ERR_FORMAT, "[import_NVDB] failed: corrupt NanoVDB tree (node offsets leave the grid buffer, code %d)", bad);
+    }
+  }
   o->hasValueRange = 0;
   if (supported && rootOff >= 736 && (uint64_t)rootOff + 64 <= gridSize) {
     t.root = grid + rootOff;
