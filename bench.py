@@ -62,7 +62,14 @@ def parse_args():
     ap.add_argument("--extra", type=int, default=1, help="also measure the secondary variants (N=1 only)")
     ap.add_argument("--nvdb-codec", default="float", choices=["float", "fp4", "fp8", "fp16", "fpn"],
                     help="c5 only: NanoVDB grid type of the fog sphere (quantised by visrtx_b200.nvdb_writer)")
+    ap.add_argument("--extra-configs", default="c3,c5",
+                    help="N=1 default run only: other BASELINE configs measured after the headline (extra.configs), "
+                         "each with its own roofline and parity block; empty string = none")
     a = ap.parse_args()
+    return apply_preset(a)
+
+
+def apply_preset(a):
     if a.config == "c3":
         a.size, a.width, a.height, a.field = 2048, 3840, 2160, "shells"
         a.skip = 1 if a.skip < 0 else a.skip
@@ -142,8 +149,8 @@ def make_scene(args, torch, device, z_begin=0, z_end=None):
 
 
 def scene_dtype(args):
-    from visrtx_b200 import capi
-    return capi.DVR_UFIXED16 if args.field == "shells" else capi.DVR_FLOAT32
+    from visrtx_b200 import pods
+    return pods.DVR_UFIXED16 if args.field == "shells" else pods.DVR_FLOAT32
 
 
 def voxel_bytes(args):
@@ -187,11 +194,47 @@ def workload_name(args):
             f"{args.rate:g} (step {0.5 / args.rate:g} voxel), orbit camera az30/el20 at 2|diag|, fovy 60")
 
 
-def orbit(args, az_deg=30.0):
-    from visrtx_b200 import capi, scenes
+def orbit(args, az_deg=30.0, oracle_side=False):
+    """Benchmark camera.  oracle_side=True builds the POD with the oracle's camera set-up (bit-identical to
+    dvr_camera_perspective, tests/test_capi_host.py) so that the reference arm never loads libdvr_b200.so."""
+    from visrtx_b200 import scenes
     lo, hi = scene_bounds(args)
     pose = scenes.orbit_camera(lo, hi, args.width, args.height, az_deg=az_deg)
+    if oracle_side:
+        sys.path.insert(0, os.path.join(ROOT, "tests"))
+        import oracle_binding as ob
+        return ob.camera_perspective(pose.position, pose.direction, pose.up, pose.fovy, pose.aspect), pose
+    from visrtx_b200 import capi
     return capi.camera_perspective(pose.position, pose.direction, pose.up, pose.fovy, pose.aspect), pose
+
+
+def oracle_tf(args):
+    """The 256-texel table from the REFERENCE's own discretisation (libref_host.so), else O-cpu's restatement of it —
+    both bit-identical to dvr_tf_discretize (tests/test_capi_host.py)."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import oracle_binding as ob
+    return ob.tf_discretize(color=scene_colormap(args), which="ref" if ob.have_ref_host() else "cpu")
+
+
+def parity_block(torch, fmt_bytes, color_a, color_b, depth_a=None, depth_b=None, what=""):
+    """north_star's tolerance on one frame: per-pixel max |d| in 1/255 units after tonemap/encode, PSNR; depth."""
+    a = color_a.view(torch.uint8).view(-1, 4).to(torch.int32)
+    b = color_b.view(torch.uint8).view(-1, 4).to(torch.int32)
+    d = (a - b).abs()
+    dmax = d.max(dim=1).values
+    mse = float(((d.to(torch.float64) / 255.0) ** 2).mean().item())
+    out = {"max_abs_255": int(dmax.max().item()), "frac_le_2": float((dmax <= 2).double().mean().item()),
+           "frac_identical": float((dmax == 0).double().mean().item()),
+           "psnr_db": 99.0 if mse == 0.0 else 10.0 * math.log10(1.0 / mse),
+           "pixels_gt_2": int((dmax > 2).sum().item()), "tolerance": "north_star: <= 2/255 per pixel, PSNR >= 45 dB",
+           "what": what}
+    if depth_a is not None and depth_b is not None:
+        hit = (depth_a < 1e29) & (depth_b < 1e29)
+        rel = ((depth_a - depth_b).abs() / depth_b.abs().clamp_min(1e-20))[hit]
+        out["depth_max_rel"] = float(rel.max().item()) if rel.numel() else 0.0
+        out["depth_hit_mask_equal"] = bool(((depth_a < 1e29) == (depth_b < 1e29)).all().item())
+    out["pass"] = bool(out["max_abs_255"] <= 2 and out["psnr_db"] >= 45.0)
+    return out
 
 
 def bytes_per_frame(args, cells_touched: int, samples: int = 0, fmt_bytes: int = 4):
@@ -232,17 +275,18 @@ def measured_peak():
 
 
 # ---------------------------------------------------------------------------------------------------------
-def cpu_baseline(args, torch, vol_dev, samples_per_frame: int):
-    """O-cpu on a bounded band of rows around the image centre (all host cores via OpenMP)."""
+def cpu_baseline(args, torch, vol_dev, samples_per_frame, rows=0):
+    """O-cpu on a bounded band of rows around the image centre (all host cores via OpenMP).  samples_per_frame None:
+    frames/s is scaled by rows instead of by samples (no GPU-side sample count available)."""
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     import oracle_binding as ob
-    from visrtx_b200 import capi, scenes
+    from visrtx_b200 import pods as capi
     n = args.size
     host = vol_dev if args.field == "fog" else vol_dev.cpu().numpy()  # (z,y,x) voxels, or the NanoVDB blob
     if args.field == "shells":  # UFIXED16 stored as int16 bits -> what cudaReadModeNormalizedFloat hands the filter
         host = (host.view(np.uint16).astype(np.float32) / np.float32(65535.0))
-    tf = capi.tf_discretize(color=scene_colormap(args))
-    cam, _ = orbit(args)
+    tf = oracle_tf(args)
+    cam, _ = orbit(args, oracle_side=True)
     vols = (ob.OracleVolume * 1)()
     o = vols[0]
     o.voxels = host.ctypes.data_as(C.c_void_p)
@@ -268,7 +312,7 @@ def cpu_baseline(args, torch, vol_dev, samples_per_frame: int):
     p = capi.frame_params(args.width, args.height, capi.DVR_FORMAT_UFIXED8_RGBA_SRGB, capi.DVR_INTEGRATOR_DEFAULT, 0,
                           -1, 1, args.rate, (0.1, 0.1, 0.1, 1.0))
     cores = os.cpu_count() or 1
-    rows = args.cpu_rows
+    rows = rows or args.cpu_rows
     mid = args.height // 2
     lib = ob.cpu()
 
@@ -292,7 +336,8 @@ def cpu_baseline(args, torch, vol_dev, samples_per_frame: int):
         reps += 1
     dt, nsamp = total_dt, total_samp
     sps = nsamp / dt
-    return {"value": sps / max(samples_per_frame, 1), "unit": "frames/s", "cores": cores, "kind": "port",
+    value = (sps / max(samples_per_frame, 1)) if samples_per_frame else (rows * reps / dt) / args.height
+    return {"value": value, "unit": "frames/s", "cores": cores, "kind": "port",
             "gsamples_per_s": sps / 1e9,
             "sample": f"{rows} image rows around the centre of the same {args.width}x{args.height} frame, repeated "
                       f"{reps}x ({nsamp} samples, {dt:.1f} s of CPU work); frames/s = CPU samples/s / samples per frame"}
@@ -623,20 +668,11 @@ def run_ours(args, torch, dist, rank, world):
     # per-GPU achieved bandwidth: every rank reads ~1/N of the touched voxels (its tile rows / its slab)
     achieved = bframe * share / (kernel_ms * 1e-3) / 1e9
     out = {
-        "metric": "DVR frames/s, 1080p, 1024^3 f32 volume (Gsamples/s in extra)" if args.config == "c2" else f"DVR frames/s, config {args.config}",
+        "metric": metric_name(args),
         "value": fps, "unit": "frames/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic (analytic field generated in HBM: " + args.field + ")",
-        "config": {
-            "workload": workload_name(args),
-            "parallelism": mode + (f"x{world}" if world > 1 else ""),
-            **({"slabs": "z-slabs of equal work for the initial camera (sample density ~ 1/r^2 from the eye), "
-                         "not of equal thickness (multigpu.view_balanced_slab_ranges)"}
-               if mode == "sort-last" and world > 1 else {}),
-            "l2": (f"NanoVDB grid {vol.nbytes / 1e6:.0f} MB > 126 MB L2; no flush" if args.field == "fog" else
-                   f"input volume {n ** 3 * voxel_bytes(args) / 2 ** 30:.1f} GiB >> 126 MB L2; no flush needed"),
-            "macrocell_skipping": bool(args.skip),
-        },
+        "config": bench_config(args, mode, world),
         "gpu_launches": int(launches),
         "e2e": {"value": e2e_fps, "unit": "frames/s", "h2d_bytes_per_step": e2e_bytes[0],
                 "d2h_bytes_per_step": e2e_bytes[1],
@@ -649,6 +685,9 @@ def run_ours(args, torch, dist, rank, world):
                   "rays_hit": int(rays_hit), "bytes_per_sample": bframe / max(samples, 1), "setup_s": setup_s,
                   "share_per_rank": share},
     }
+    if mode == "sort-last" and world > 1:
+        out["extra"]["slabs"] = ("z-slabs of equal work for the initial camera (sample density ~ 1/r^2 from the eye), not "
+                                 "of equal thickness (multigpu.view_balanced_slab_ranges)")
     if clocks is not None:
         out["clocks"] = clocks
     if frame_dist is not None:
@@ -664,11 +703,24 @@ def run_ours(args, torch, dist, rank, world):
         except Exception as e:  # the oracle is optional at bench time
             out["cpu_baseline"] = {"value": None, "unit": "frames/s", "cores": os.cpu_count(), "kind": "port",
                                    "sample": f"unavailable: {e}"}
-    if rank == 0 and world == 1 and vol is not None and args.extra:
+    if rank == 0 and world == 1 and vol is not None:
+        # same-config parity: frame 0 of the benchmark camera rendered by both arms on this very scene
         try:
-            out["extra"]["ref_gpu_fps"] = ref_gpu_fps(args, torch, vol, min(args.steps, 30))
+            (ref_color, ref_depth), ref_fps = ref_gpu_frame0(args, torch, vol, min(args.steps, 30) if args.extra else 0)
+            par_color = torch.zeros(npx, dtype=torch.int32, device=device)
+            par_depth = torch.zeros(npx, dtype=torch.float32, device=device)
+            fb_par = capi.frame_buffers(driver.accum.data_ptr(), par_color.data_ptr(), par_depth.data_ptr())
+            capi.render(params(0), cam, inst, ninst, fb_par, stream)
+            torch.cuda.synchronize()
+            out["parity"] = parity_block(torch, 4, par_color, ref_color, par_depth, ref_depth,
+                                         what="frame 0 of the timed scene and camera: this arm (dvr_render) vs O-gpu "
+                                              "(the reference's device code) on the same B200, sRGB8 colour + depth")
+            if ref_fps is not None:
+                out["extra"]["ref_gpu_fps"] = ref_fps
+            del ref_color, ref_depth, par_color, par_depth
         except Exception as e:
-            out["extra"]["ref_gpu_fps"] = f"unavailable: {e}"
+            out["parity"] = {"pass": None, "what": f"unavailable: {e}"}
+    if rank == 0 and world == 1 and vol is not None and args.extra:
         if mode == "single":
             try:
                 out["extra"]["dpt"] = measure_dpt(args, torch, capi, field, cam, fb, stream, vol)
@@ -679,11 +731,153 @@ def run_ours(args, torch, dist, rank, world):
                     out["extra"]["time_varying"] = measure_time_varying(args, torch, capi, field, cam, fb, stream, vol)
                 except Exception as e:
                     out["extra"]["time_varying"] = f"unavailable: {e}"
+    if rank == 0 and world == 1 and mode == "single" and args.extra and args.config == "c2" and args.extra_configs:
+        # the other single-GPU BASELINE configs, driver-observed: free the headline scene first
+        volume.destroy()
+        field.destroy()
+        del vol
+        torch.cuda.empty_cache()
+        out["extra"]["configs"] = {}
+        for name in [c for c in args.extra_configs.split(",") if c in ("c3", "c5")]:
+            try:
+                out["extra"]["configs"][name] = measure_secondary_config(args, name, torch, device, stream)
+            except Exception as e:
+                out["extra"]["configs"][name] = f"unavailable: {type(e).__name__}: {e}"
+    if world > 1:
+        out["parity_vs_single"] = parity_vs_single(args, torch, dist, capi, driver, cam, rank, world, device, stream, mode)
     if driver is not None and getattr(driver, "host_frame", None) is not None:
         host_view = None  # drop the numpy view before the shared segment is unmapped
         driver.host_frame.close(dist if world > 1 else None)
         driver.host_frame = None
     return out
+
+
+def parity_vs_single(args, torch, dist, capi, driver, cam, rank, world, device, stream, mode):
+    """N > 1: the frame the N GPUs assembled against the SAME frame rendered by one GPU holding the whole volume
+    (dvr_render on the display rank's GPU).  Only when the whole volume fits beside the rank's own share."""
+    n, W, H = args.size, args.width, args.height
+    npx = W * H
+    need = n ** 3 * voxel_bytes(args) * 2.2
+    driver.stream_to_host(False)
+    driver.render(0, cam, stream)  # frame 0 (accumulation reset) by all ranks
+    torch.cuda.synchronize()
+    dist.barrier()
+    res = None
+    if rank == 0:
+        free_b, _ = torch.cuda.mem_get_info()
+        if args.field == "fog" or need > free_b:
+            res = {"pass": None, "what": f"not run: the whole {n}^3 volume does not fit one GPU next to this rank's share"}
+        else:
+            multi = driver.color_tensor()
+            vol = make_scene(args, torch, device)
+            field = create_field(args, capi, vol, stream)
+            del vol
+            tf = capi.tf_discretize(color=scene_colormap(args))
+            v = capi.Volume.create(field, tf, (0.0, 1.0), args.unit_distance, 0, stream)
+            inst, ninst = capi.make_instances([v], None, [0])
+            accum = torch.zeros((npx, 4), dtype=torch.float32, device=device)
+            color = torch.zeros(npx, dtype=torch.int32, device=device)
+            depth = torch.zeros(npx, dtype=torch.float32, device=device)
+            fb = capi.frame_buffers(accum.data_ptr(), color.data_ptr(), depth.data_ptr())
+            p = capi.frame_params(W, H, capi.DVR_FORMAT_UFIXED8_RGBA_SRGB, capi.DVR_INTEGRATOR_DEFAULT, 0, -1, 1, args.rate,
+                                  (0.1, 0.1, 0.1, 1.0), skip=bool(args.skip))
+            capi.render(p, cam, inst, ninst, fb, stream)
+            torch.cuda.synchronize()
+            res = parity_block(torch, 4, multi, color, what=f"frame 0 assembled by {world} GPUs ({mode}) vs dvr_render of "
+                               "the whole volume on one GPU, same camera and Philox streams, sRGB8 colour")
+            v.destroy()
+            field.destroy()
+    dist.barrier()
+    return res
+
+
+def measure_secondary_config(base_args, name, torch, device, stream):
+    """Another BASELINE config at N = 1, after the headline: device-timed frames/s, roofline from an instrumented
+    launch, e2e through the ANARI C API, and parity against O-gpu on frame 0 — driver-observed versions of the numbers
+    DESIGN.md quotes for C3 / C5."""
+    import argparse
+    from visrtx_b200 import capi
+    a = argparse.Namespace(**vars(base_args))
+    a.config, a.skip, a.field, a.rate, a.nvdb_codec = name, -1, "ml", 0.5, "float"
+    a = apply_preset(a)
+    W, H, npx = a.width, a.height, a.width * a.height
+    t0 = time.perf_counter()
+    vol = make_scene(a, torch, device)
+    field = create_field(a, capi, vol, stream)
+    torch.cuda.synchronize()
+    tf = capi.tf_discretize(color=scene_colormap(a))
+    v = capi.Volume.create(field, tf, (0.0, 1.0), a.unit_distance, 0, stream)
+    inst, ninst = capi.make_instances([v], None, [0])
+    cam, _ = orbit(a)
+    setup_s = time.perf_counter() - t0
+    accum = torch.zeros((npx, 4), dtype=torch.float32, device=device)
+    color = torch.zeros(npx, dtype=torch.int32, device=device)
+    depth = torch.zeros(npx, dtype=torch.float32, device=device)
+    fb = capi.frame_buffers(accum.data_ptr(), color.data_ptr(), depth.data_ptr())
+    mk = lambda fid: capi.frame_params(W, H, capi.DVR_FORMAT_UFIXED8_RGBA_SRGB, capi.DVR_INTEGRATOR_DEFAULT, fid, -1, 1,
+                                       a.rate, (0.1, 0.1, 0.1, 1.0), skip=bool(a.skip))
+    st = torch.zeros(4, dtype=torch.int64, device=device)
+    capi.render_instrumented(mk(0), cam, inst, ninst, fb, st.data_ptr(), stream)
+    torch.cuda.synchronize()
+    samples, skipped, rays_hit, cells = st.tolist()
+    for i in range(5):
+        capi.render(mk(i), cam, inst, ninst, fb, stream)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    K = 64 if name == "c5" else 30  # C5: the 64-frame progressive accumulation of BASELINE.json
+    e0.record()
+    for i in range(K):
+        capi.render(mk(i), cam, inst, ninst, fb, stream)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / K
+    peak, peak_src = measured_peak()
+    if a.field == "fog":  # apron bricks: 9^3 floats per non-constant 8^3 cell; a sample reads at most 8 sectors
+        bframe, bmodel = samples * 8 * 32 + npx * 44 + 4096, "sector cap: samples * 8 taps * 32 B (brick rows are not sector aligned)"
+    else:
+        bframe, bmodel = bytes_per_frame(a, cells, samples)
+    res = {"workload": workload_name(a), "value": 1000.0 / ms, "unit": "frames/s", "ms_per_step": ms, "steps": K,
+           "samples_per_frame": int(samples), "samples_skipped": int(skipped), "gsamples_per_s": samples / ms / 1e6,
+           "macrocell_skipping": bool(a.skip), "setup_s": setup_s,
+           "roofline": {"bound": "hbm", "achieved": bframe / ms / 1e6, "peak": peak, "unit": "GB/s",
+                        "frac": bframe / ms / 1e6 / peak, "algorithmic_bytes": bframe, "bytes_model": bmodel,
+                        "macrocells_touched": int(cells), "kernel_ms": ms, "peak_source": peak_src,
+                        "note": "sparse / early-terminating workloads are latency- and issue-bound, not HBM-bound: "
+                                "the fraction is reported, not claimed as the bound"}}
+    try:
+        (ref_color, ref_depth), ref_fps = ref_gpu_frame0(a, torch, vol, 10)
+        capi.render(mk(0), cam, inst, ninst, fb, stream)
+        torch.cuda.synchronize()
+        res["parity"] = parity_block(torch, 4, color, ref_color, depth, ref_depth,
+                                     what="frame 0: dvr_render vs O-gpu (reference device code), same scene and camera")
+        res["ref_gpu_fps"] = ref_fps
+        del ref_color, ref_depth
+    except Exception as e:
+        res["parity"] = {"pass": None, "what": f"unavailable: {e}"}
+    v.destroy()
+    field.destroy()
+    del vol, accum, color, depth
+    torch.cuda.empty_cache()
+    try:
+        import types
+        vol2 = make_scene(a, torch, device)
+        e2e = AnariE2E(a, torch, device, vol2, 0, 1, "single")
+        e2e.prepare(K + 3)
+        for i in range(3):
+            e2e.step(i)
+        torch.cuda.synchronize()
+        t1 = time.perf_counter()
+        for i in range(K):
+            e2e.step(i)
+        torch.cuda.synchronize()
+        res["e2e"] = {"value": K / (time.perf_counter() - t1), "unit": "frames/s",
+                      "h2d_bytes_per_step": e2e.bytes_per_step()[0], "d2h_bytes_per_step": e2e.bytes_per_step()[1]}
+        e2e.close()
+        del vol2
+        torch.cuda.empty_cache()
+    except Exception as e:
+        res["e2e"] = {"value": None, "what": f"unavailable: {e}"}
+    return res
 
 
 def measure_variants(args, torch, capi, scenes, field, cam, inst, ninst, fb, stream, stats_t):
@@ -792,7 +986,7 @@ def measure_dpt(args, torch, capi, field, cam, fb, stream, vol_dev):
 def _refgpu_objects(args, torch, vol_dev, tf=None, grid=None):
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     import oracle_binding as ob
-    from visrtx_b200 import capi, scenes
+    from visrtx_b200 import pods
     lib = ob.refgpu()
     n = args.size
     f = C.c_void_p()
@@ -804,7 +998,7 @@ def _refgpu_objects(args, torch, vol_dev, tf=None, grid=None):
                                      C.c_int(0), C.byref(f))
     assert rc == 0, lib.refgpu_last_error()
     if tf is None:
-        tf = capi.tf_discretize(color=scene_colormap(args))
+        tf = oracle_tf(args)
     v = C.c_void_p()
     rc = lib.refgpu_volume_create(f, tf.ctypes.data_as(C.c_void_p), (C.c_float * 2)(0, 1), C.c_float(args.unit_distance),
                                   C.c_uint32(0), C.byref(v))
@@ -814,7 +1008,7 @@ def _refgpu_objects(args, torch, vol_dev, tf=None, grid=None):
         assert rc == 0, lib.refgpu_last_error()
     inst = (ob.RefInstance * 1)()
     inst[0].volume = v
-    inst[0].worldToObject = (C.c_float * 12)(*capi.IDENTITY_3X4)
+    inst[0].worldToObject = (C.c_float * 12)(*pods.IDENTITY_3X4)
     inst[0].instanceId = 0
     sc = C.c_void_p()
     rc = lib.refgpu_scene_create(inst, C.c_int(1), C.byref(sc))
@@ -822,35 +1016,70 @@ def _refgpu_objects(args, torch, vol_dev, tf=None, grid=None):
     return lib, sc, (f, v)
 
 
-def ref_gpu_fps(args, torch, vol_dev, steps):
-    """O-gpu frames/s on the same scene (device-timed), reported next to our own number."""
-    from visrtx_b200 import capi
-    lib, sc, _ = _refgpu_objects(args, torch, vol_dev)
+def ref_gpu_frame0(args, torch, vol_dev, steps=0):
+    """O-gpu (the reference's device code) on the same scene: frame 0 of the benchmark camera (colour + depth, kept on
+    the device for the parity block) and, with steps > 0, its device-timed frames/s."""
+    from visrtx_b200 import pods
+    lib, sc, (rf, rv) = _refgpu_objects(args, torch, vol_dev)
     npx = args.width * args.height
     dev = torch.device("cuda", torch.cuda.current_device())
     accum = torch.zeros((npx, 4), dtype=torch.float32, device=dev)
     color = torch.zeros(npx, dtype=torch.int32, device=dev)
     depth = torch.zeros(npx, dtype=torch.float32, device=dev)
-    fb = capi.frame_buffers(accum.data_ptr(), color.data_ptr(), depth.data_ptr())
-    cam, _ = orbit(args)
+    fb = pods.frame_buffers(accum.data_ptr(), color.data_ptr(), depth.data_ptr())
+    cam, _ = orbit(args, oracle_side=True)
     stream = torch.cuda.current_stream().cuda_stream
-    mk = lambda fid: capi.frame_params(args.width, args.height, capi.DVR_FORMAT_UFIXED8_RGBA_SRGB,
-                                       capi.DVR_INTEGRATOR_DEFAULT, fid, -1, 1, args.rate, (0.1, 0.1, 0.1, 1.0))
-    for i in range(3):
-        lib.refgpu_render(C.byref(mk(i)), C.byref(cam), sc, C.byref(fb), C.c_void_p(stream))
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    mk = lambda fid: pods.frame_params(args.width, args.height, pods.DVR_FORMAT_UFIXED8_RGBA_SRGB,
+                                       pods.DVR_INTEGRATOR_DEFAULT, fid, -1, 1, args.rate, (0.1, 0.1, 0.1, 1.0))
+    rc = lib.refgpu_render(C.byref(mk(0)), C.byref(cam), sc, C.byref(fb), C.c_void_p(stream))
+    assert rc == 0, lib.refgpu_last_error()
     torch.cuda.synchronize()
-    e0.record()
-    for i in range(steps):
-        lib.refgpu_render(C.byref(mk(3 + i)), C.byref(cam), sc, C.byref(fb), C.c_void_p(stream))
-    e1.record()
-    torch.cuda.synchronize()
-    return steps * 1000.0 / e0.elapsed_time(e1)
+    frame0 = (color.clone(), depth.clone())
+    fps = None
+    if steps > 0:
+        for i in range(3):
+            lib.refgpu_render(C.byref(mk(1 + i)), C.byref(cam), sc, C.byref(fb), C.c_void_p(stream))
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        e0.record()
+        for i in range(steps):
+            lib.refgpu_render(C.byref(mk(4 + i)), C.byref(cam), sc, C.byref(fb), C.c_void_p(stream))
+        e1.record()
+        torch.cuda.synchronize()
+        fps = steps * 1000.0 / e0.elapsed_time(e1)
+    lib.refgpu_scene_destroy(sc)
+    lib.refgpu_volume_destroy(rv)
+    lib.refgpu_field_destroy(rf)
+    return frame0, fps
+
+
+REFERENCE_KIND = ("O-gpu: VisRTX device headers (gpu/volumeIntegration.h, sampleSpatialField.h, gpu_util.h ...) compiled "
+                  "for sm_100a from /root/reference, one thread per pixel, OptiX volume-BVH trace replaced by the slab "
+                  "test; VisRTX + OptiX proper cannot be built here (no OptiX headers, no ANARI-SDK)")
+
+
+def bench_config(args, mode, world):
+    """`config` of the JSON line: the SAME keys and values in both arms (the driver compares them)."""
+    n = args.size
+    return {
+        "workload": workload_name(args),
+        "parallelism": mode + (f"x{world}" if world > 1 else ""),
+        "l2": ("NanoVDB grid > 126 MB L2; no flush" if args.field == "fog" else
+               f"input volume {n ** 3 * voxel_bytes(args) / 2 ** 30:.1f} GiB >> 126 MB L2; no flush needed"),
+        "macrocell_skipping": bool(args.skip),
+    }
+
+
+def metric_name(args):
+    return ("DVR frames/s, 1080p, 1024^3 f32 volume (Gsamples/s in extra)" if args.config == "c2"
+            else f"DVR frames/s, config {args.config}")
 
 
 def run_reference(args, torch, dist, rank, world):
-    """Reference arm: O-gpu (reference device headers) on ONE GPU; rank 0 only."""
-    from visrtx_b200 import capi
+    """Reference arm: O-gpu (reference device headers) on ONE GPU; rank 0 only.  Nothing of the product is loaded:
+    parameter blocks come from visrtx_b200.pods (plain ctypes structs), camera and transfer function from the oracle
+    libraries, the kernels from oracle/_ref/libref_gpu_dvr.so."""
+    from visrtx_b200 import pods
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     import oracle_binding as ob
     device = torch.device("cuda", int(os.environ.get("LOCAL_RANK", 0)))
@@ -858,35 +1087,20 @@ def run_reference(args, torch, dist, rank, world):
     n, W, H = args.size, args.width, args.height
     npx = W * H
     vol = make_scene(args, torch, device)
-    base = {"impl": "reference", "metric": "DVR frames/s, 1080p, 1024^3 f32 volume (Gsamples/s in extra)" if args.config == "c2" else f"DVR frames/s, config {args.config}",
+    mode = "single" if world == 1 else ("sort-last" if args.mode == "auto" else args.mode)
+    base = {"impl": "reference", "metric": metric_name(args),
             "unit": "frames/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
-            "data": "synthetic (analytic Marschner-Lobb field generated in HBM)"}
-    workload = workload_name(args)
+            "data": "synthetic (analytic field generated in HBM: " + args.field + ")",
+            "config": bench_config(args, mode, world)}
     if not ob.have_ref_gpu():
-        # fall back to the CPU port
-        cb = cpu_baseline(args, torch, vol, 1)
-        sps = cb["gsamples_per_s"] * 1e9
-        # samples per frame of this workload from the oracle itself is unknown here: report samples/s based fps
-        # with the GPU-measured samples per frame when libdvr is present
-        from visrtx_b200 import scenes
-        stream = torch.cuda.current_stream().cuda_stream
-        field = create_field(args, capi, vol, stream)
-        tf = capi.tf_discretize(color=scene_colormap(args))
-        v = capi.Volume.create(field, tf, (0.0, 1.0), args.unit_distance, 0, stream)
-        inst, ninst = capi.make_instances([v], None, [0])
-        accum = torch.zeros((npx, 4), dtype=torch.float32, device=device)
-        color = torch.zeros(npx, dtype=torch.int32, device=device)
-        fb = capi.frame_buffers(accum.data_ptr(), color.data_ptr())
-        st = torch.zeros(4, dtype=torch.int64, device=device)
-        cam, _ = orbit(args)
-        capi.render_instrumented(capi.frame_params(W, H, 2, 1, 0, -1, 1, args.rate, (0.1, 0.1, 0.1, 1.0)), cam, inst,
-                                 ninst, fb, st.data_ptr(), stream)
-        torch.cuda.synchronize()
-        fps = sps / max(st[0].item(), 1)
-        cb["value"] = fps
-        base.update({"value": fps, "ms_per_step": 1000.0 / fps, "config": {"workload": workload, "parallelism": "cpu"},
-                     "cpu_baseline": cb, "gpu_launches": 0,
+        # O-gpu did not travel: time the CPU port on a band of rows and scale by rows (the centre band is the most
+        # expensive part of the frame, so this under-states the CPU)
+        rows = args.cpu_rows or 8
+        cb = cpu_baseline(args, torch, vol, None, rows=rows)
+        fps = cb["value"]
+        base.update({"value": fps, "ms_per_step": 1000.0 / fps, "cpu_baseline": cb, "gpu_launches": 0,
+                     "reference_kind": "O-cpu port (oracle/liboracle_dvr.so): oracle/_ref/libref_gpu_dvr.so is absent",
                      "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}})
         return base
 
@@ -894,12 +1108,12 @@ def run_reference(args, torch, dist, rank, world):
     accum = torch.zeros((npx, 4), dtype=torch.float32, device=device)
     color = torch.zeros(npx, dtype=torch.int32, device=device)
     depth = torch.zeros(npx, dtype=torch.float32, device=device)
-    fb = capi.frame_buffers(accum.data_ptr(), color.data_ptr(), depth.data_ptr())
+    fb = pods.frame_buffers(accum.data_ptr(), color.data_ptr(), depth.data_ptr())
     host_color = torch.empty(npx, dtype=torch.int32, pin_memory=True)
     stream = torch.cuda.current_stream().cuda_stream
-    mk = lambda fid: capi.frame_params(W, H, capi.DVR_FORMAT_UFIXED8_RGBA_SRGB, capi.DVR_INTEGRATOR_DEFAULT, fid, -1, 1,
+    mk = lambda fid: pods.frame_params(W, H, pods.DVR_FORMAT_UFIXED8_RGBA_SRGB, pods.DVR_INTEGRATOR_DEFAULT, fid, -1, 1,
                                        args.rate, (0.1, 0.1, 0.1, 1.0))
-    cam, _ = orbit(args)
+    cam, _ = orbit(args, oracle_side=True)
     # clocks are sampled from the warm-up to the end of the e2e loop (the timed region alone can be shorter than
     # one 200 ms nvidia-smi period)
     sampler = ClockSampler(device.index)
@@ -915,7 +1129,7 @@ def run_reference(args, torch, dist, rank, world):
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / args.steps
 
-    e2e_cams = [orbit(args, az_deg=30.0 + 0.05 * i)[0] for i in range(args.steps + 3)]
+    e2e_cams = [orbit(args, az_deg=30.0 + 0.05 * i, oracle_side=True)[0] for i in range(args.steps + 3)]
     p0 = mk(0)
 
     def e2e_step(i):
@@ -933,14 +1147,14 @@ def run_reference(args, torch, dist, rank, world):
     clocks = sampler.stop()
     base.update({
         "value": 1000.0 / ms, "ms_per_step": ms,
-        "config": {"workload": workload, "parallelism": "single (the reference has no multi-GPU path)",
-                   "reference_kind": "O-gpu: VisRTX device headers (gpu/volumeIntegration.h, sampleSpatialField.h, "
-                                     "gpu_util.h ...) compiled for sm_100a, one thread per pixel, OptiX volume-BVH "
-                                     "trace replaced by the slab test; VisRTX proper cannot be built here"},
+        "reference_kind": REFERENCE_KIND,
         "gpu_launches": args.steps * 4,
         "cpu_baseline": {"value": 1000.0 / ms, "unit": "frames/s", "cores": 0, "kind": "reference",
-                         "sample": "full frames on the B200 (the reference is GPU code; see config.reference_kind)"},
-        "e2e": {"value": e2e_fps, "unit": "frames/s", "h2d_bytes_per_step": 4 * 1024, "d2h_bytes_per_step": npx * 4},
+                         "sample": "full frames on the B200 (the reference is GPU code; see reference_kind)"},
+        "e2e": {"value": e2e_fps, "unit": "frames/s", "h2d_bytes_per_step": 4 * 1024, "d2h_bytes_per_step": npx * 4,
+                "what": "moved camera (constant upload) + refgpu_render + BLOCKING device->host copy of the colour buffer "
+                        "to pinned memory every step, wall clock (the product arm instead streams the colour into a "
+                        "pinned mirror during the launch)"},
         "clocks": clocks,
     })
     return base

@@ -93,8 +93,14 @@ typedef uint32_t ANARIWaitMask;
 #define ANARI_UFIXED8_VEC4 1039
 #define ANARI_FIXED16 1040
 #define ANARI_UFIXED16 1044
+#define ANARI_UFIXED16_VEC2 1045
+#define ANARI_UFIXED16_VEC3 1046
+#define ANARI_UFIXED16_VEC4 1047
 #define ANARI_FIXED32 1048
 #define ANARI_UFIXED32 1052
+#define ANARI_UFIXED32_VEC2 1053
+#define ANARI_UFIXED32_VEC3 1054
+#define ANARI_UFIXED32_VEC4 1055
 #define ANARI_FLOAT16 1064
 #define ANARI_FLOAT32 1068
 #define ANARI_FLOAT32_VEC2 1069

@@ -92,6 +92,7 @@ typedef enum DvrIntegrator
 /* ---- opaque device objects ------------------------------------------------------ */
 typedef struct DvrField DvrField;   /* replaces StructuredRegularField / NvdbRegularField GPU state */
 typedef struct DvrVolume DvrVolume; /* replaces TransferFunction1D GPU state (TF table + majorants) */
+typedef struct DvrImage DvrImage;   /* replaces the renderer's background texture (Renderer.cpp:172-198) */
 
 /* ---- POD parameter blocks ------------------------------------------------------- */
 
@@ -174,6 +175,10 @@ typedef struct DvrFrameParams
    * — dvr_composite_resolve_peers* regenerates each primary ray and never reads a pixel whose ray misses. */
   int32_t partialCullToBounds;
   int32_t _reserved[1];
+  /* "background" given as an image (Renderer.cpp:154,175-198): non-NULL => every pixel-sample takes its background
+   * from a bilinear fetch of the image at its screen coordinate (gpu/gpu_util.h:289-307) and `background` is
+   * ignored.  NULL = the constant colour. */
+  const DvrImage *backgroundImage;
 } DvrFrameParams;
 
 /* per-launch counters, filled only by dvr_render_instrumented (device memory, 64-bit each) */
@@ -270,6 +275,28 @@ int dvr_field_macrocells(const DvrField *f, uint32_t gridDims[3], const float **
 /* global scalar range of the field (min,max), reduced from the macrocell ranges
  * (tsd/src/tsd/algorithms/computeScalarRange.cpp).  Synchronises the stream. */
 int dvr_field_value_range(const DvrField *f, void *stream, float range[2]);
+
+/* ---- background image ------------------------------------------------------------- */
+
+/* component types of the image array the application hands to the renderer's "background" parameter */
+typedef enum DvrImageComponent
+{
+  DVR_IMAGE_FLOAT32 = 0, /* ANARI_FLOAT32[_VECn] */
+  DVR_IMAGE_UFIXED8 = 1, /* ANARI_UFIXED8[_VECn] */
+  DVR_IMAGE_UFIXED16 = 2,
+  DVR_IMAGE_UFIXED32 = 3,
+  DVR_IMAGE_SRGB8 = 4    /* ANARI_UFIXED8_R[GBA]_SRGB: linearised at upload */
+} DvrImageComponent;
+
+/* Renderer::finalize (renderer/Renderer.cpp:172-179): Array2D::acquireCUDAArrayUint8 -> makeCudaArrayUint8
+ * (utility/CudaImageTexture.cpp:43-58,84-101,139-226) + makeCudaTextureObject(array, normalizedFloat, "linear")
+ * (:316-345).  `pixels` is HOST memory, width*height elements of `channels` (1..4) components, row-major from the
+ * bottom row (row 0 is sampled at screen y = 0).  Every component is converted to 8 bits exactly as the reference's
+ * staging pass does (float: uint8(c*255), truncating; 16/32-bit fixed: uint8(c/max*255); sRGB8: linearised), three
+ * channels are padded with alpha 255, and the result is bound to a clamp / linear / normalised-coordinate texture. */
+int dvr_image_create(const void *pixels, int componentType /*DvrImageComponent*/, int channels, uint32_t width,
+    uint32_t height, void *stream, DvrImage **out);
+int dvr_image_destroy(DvrImage *img);
 
 /* ---- volumes ---------------------------------------------------------------------- */
 

@@ -322,6 +322,38 @@ inline void tfFetch(const float *tf, float coord, float out[4])
     out[c] = (float)(((double)tf[4 * i0 + c] * (256 - k) + (double)tf[4 * i1 + c] * k) / 256.0);
 }
 
+// getBackgroundImage, gpu/gpu_util.h:289-296: the renderer's constant colour, or tex2D<float4> on the RGBA8
+// background texture (clamp, normalised coordinates, linear, cudaReadModeNormalizedFloat; Renderer.cpp:172-179,
+// utility/CudaImageTexture.cpp:139-226,316-345).  The filter is the measured B200 rule of Field::tex for one slice
+// (B = 256).  Channels the texture does not have read as 0, alpha included (measured on B200: a two-channel RG8
+// texture fetched as float4 returns (r, g, 0, 0); golden scene bgimage_u16x2_checkerboard_p5).
+struct BgImage
+{
+  std::vector<uint8_t> texels; // nc bytes per texel, row-major; empty = constant colour
+  int nc = 0, w = 0, h = 0;
+};
+static BgImage g_bgImage;
+
+inline void backgroundAt(const DvrFrameParams &P, float sx, float sy, float out[4])
+{
+  const BgImage &B = g_bgImage;
+  if (B.texels.empty()) {
+    std::memcpy(out, P.background, 4 * sizeof(float));
+    return;
+  }
+  int x0, x1, kx, y0, y1, ky;
+  texAxis(sx, B.w, x0, x1, kx);
+  texAxis(sy, B.h, y0, y1, ky);
+  const int X1 = kx, X0 = 256 - kx;
+  const int w11 = (X1 * ky + 128) >> 8, w10 = X1 - w11;
+  const int w01 = (X0 * ky + 127) >> 8, w00 = X0 - w01;
+  out[0] = out[1] = out[2] = out[3] = 0.f;
+  for (int c = 0; c < B.nc; ++c) {
+    auto at = [&](int x, int y) { return (double)((float)B.texels[((size_t)y * B.w + x) * B.nc + c] / 255.f); };
+    out[c] = (float)((at(x0, y0) * w00 + at(x1, y0) * w10 + at(x0, y1) * w01 + at(x1, y1) * w11) / 256.0);
+  }
+}
+
 inline float position(float v, float lo, float hi)
 { // gpu_math.h:176-180
   v = std::fmax(lo, std::fmin(v, hi));
@@ -690,7 +722,7 @@ struct DptPath // PathData, DiffusePathTracer_ptx.cu:45-50 (declared OUTSIDE the
 };
 
 // the bounce loop of DiffusePathTracer_ptx.cu:111-196 for a world without surfaces
-V3 dptTracePath(const std::vector<Volume> &vols, const std::vector<DdaGrid> &grids, V3 org, V3 dir,
+V3 dptTracePath(const float bg[4], const std::vector<Volume> &vols, const std::vector<DdaGrid> &grids, V3 org, V3 dir,
     const DvrFrameParams &P, Philox &rng, DptPath &path, uint64_t &samples)
 {
   const int maxDepth = P.maxDepth <= 0 ? 5 : std::min(P.maxDepth, 256);
@@ -725,7 +757,7 @@ V3 dptTracePath(const std::vector<Volume> &vols, const std::vector<DdaGrid> &gri
   }
   if (path.depth)
     return path.Lw * P.ambientRadiance;
-  return {P.background[0], P.background[1], P.background[2]};
+  return {bg[0], bg[1], bg[2]};
 }
 
 inline float clamp01(float v) { return std::fmin(std::fmax(v, 0.f), 1.f); }
@@ -962,9 +994,11 @@ int oracle_render(const DvrFrameParams *params, const DvrCamera *camera, const O
         }
         if (dpt) { // DiffusePathTracer_ptx.cu:96-215: depth / ids keep their initial values (tmax, ~0u)
           const float nrm[3] = {dir.x, dir.y, dir.z};
-          const V3 c = dptTracePath(vols, grids, org, dir, P, rng, path, samples);
+          float bgd[4];
+          backgroundAt(P, sx, sy, bgd);
+          const V3 c = dptTracePath(bgd, vols, grids, org, dir, P, rng, path, samples);
           const float c4[4] = {c.x, c.y, c.z, 1.f};
-          const float alb[3] = {P.background[0], P.background[1], P.background[2]};
+          const float alb[3] = {bgd[0], bgd[1], bgd[2]};
           accumResults(F, (uint32_t)x, (uint32_t)y, c4, std::numeric_limits<float>::max(), alb, nrm, ~0u, ~0u, ~0u, it);
           continue;
         }
@@ -976,10 +1010,12 @@ int oracle_render(const DvrFrameParams *params, const DvrCamera *camera, const O
         const float depth = std::fmin(1e30f, vdepth);
         color = color * opacity; // Raycast_ptx.cu:159
         const float om = 1.f - opacity;
-        color.x += P.background[0] * om;
-        color.y += P.background[1] * om;
-        color.z += P.background[2] * om;
-        opacity += P.background[3] * om;
+        float bg[4];
+        backgroundAt(P, sx, sy, bg);
+        color.x += bg[0] * om;
+        color.y += bg[1] * om;
+        color.z += bg[2] * om;
+        opacity += bg[3] * om;
         const float c4[4] = {color.x, color.y, color.z, opacity};
         const float alb[3] = {color.x, color.y, color.z};
         const float nrm[3] = {dir.x, dir.y, dir.z};
@@ -989,6 +1025,22 @@ int oracle_render(const DvrFrameParams *params, const DvrCamera *camera, const O
   }
   if (samplesOut)
     *samplesOut = samples;
+  return 0;
+}
+
+// Background image of the following oracle_render calls (test-infrastructure state, not thread safe): `texels` holds
+// w*h texels of `channels` (1, 2 or 4) bytes as the renderer's RGBA8 staging pass leaves them; NULL clears it.
+int oracle_set_background_image(const uint8_t *texels, int channels, int w, int h)
+{
+  g_bgImage = BgImage();
+  if (!texels)
+    return 0;
+  if ((channels != 1 && channels != 2 && channels != 4) || w <= 0 || h <= 0)
+    return -1;
+  g_bgImage.texels.assign(texels, texels + (size_t)w * h * channels);
+  g_bgImage.nc = channels;
+  g_bgImage.w = w;
+  g_bgImage.h = h;
   return 0;
 }
 

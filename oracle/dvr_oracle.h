@@ -52,6 +52,10 @@ void oracle_philox_uniforms(uint64_t seed, uint64_t offset, int n, float *out);
 int oracle_render(const DvrFrameParams *params, const DvrCamera *camera, const OracleVolume *volumes, int nVolumes,
     const OracleBuffers *buffers, uint64_t *samplesOut, int rowBegin, int rowEnd);
 
+/* background image of the following oracle_render calls (gpu_util.h:289-296); texels = w*h*channels bytes (channels
+ * 1, 2 or 4: the RGBA8 texture the renderer builds, Renderer.cpp:172-179), NULL = back to the constant colour */
+int oracle_set_background_image(const uint8_t *texels, int channels, int w, int h);
+
 /* dpt renderer: the delta-tracking grid (ceil(dims/16) cells over the bounds) with conservative majorants */
 int oracle_dda_majorants(const OracleVolume *volume, int32_t dims[3], float *out, size_t capacity);
 

@@ -13,6 +13,8 @@
 //   - the volume AABB search (RT traversal + IS/CH) scene/Intersectors_ptx.cu:248-274, gpu/populateHit.h:370-390
 //   - host texture set-up                           StructuredRegularField.cpp:98-194, TransferFunction1D.cpp:152-186
 //   - frame reset fills                             frame/Frame.cu:590-660
+//   - the background image's RGBA8 staging pass     utility/CudaImageTexture.cpp:43-58,84-101,139-226,316-345
+//     (that file needs helium's Array class; its per-component conversions are restated with the same glm call)
 #include <cuda_runtime.h>
 #include <cstdio>
 #include <cstring>
@@ -25,6 +27,8 @@
 
 // the reference's own majorant-grid build (host class + kernels), compiled from where it lies
 #include "scene/volume/space_skipping/UniformGrid.cu"
+
+#include <glm/gtc/color_space.hpp>
 
 #include "dvr_b200.h" // POD parameter structs only (DvrFrameParams, DvrCamera, DvrFrameBuffers)
 
@@ -455,7 +459,82 @@ struct RefScene
   CameraGPUData *camera = nullptr;
   int n = 0;
   bool hasGrid = true;
+  cudaTextureObject_t bgTex = 0; // Renderer::m_backgroundTexture (0: BackgroundMode::COLOR)
 };
+
+// Renderer::finalize (Renderer.cpp:172-179): acquireCUDAArrayUint8 + makeCudaTextureObject(array, true, "linear")
+struct RefImage
+{
+  cudaArray_t arr = nullptr;
+  cudaTextureObject_t tex = 0;
+};
+
+int refgpu_image_create(const void *pixels, int componentType, int channels, uint32_t w, uint32_t h, RefImage **out)
+{
+  const size_t n = (size_t)w * h;
+  int nc = channels;
+  std::vector<uint8_t> staging(n * 4);
+  size_t o = 0;
+  for (size_t i = 0; i < n * (size_t)channels; ++i) { // transformToStagingBufferUint8 + convertComponentUint8
+    uint8_t c;
+    if (componentType == DVR_IMAGE_FLOAT32)
+      c = uint8_t(((const float *)pixels)[i] * 255);
+    else if (componentType == DVR_IMAGE_UFIXED16) {
+      constexpr auto maxVal = float(std::numeric_limits<uint16_t>::max());
+      c = uint8_t((((const uint16_t *)pixels)[i] / maxVal) * 255);
+    } else if (componentType == DVR_IMAGE_UFIXED32) {
+      constexpr auto maxVal = float(std::numeric_limits<uint32_t>::max());
+      c = uint8_t((((const uint32_t *)pixels)[i] / maxVal) * 255);
+    } else if (componentType == DVR_IMAGE_SRGB8)
+      c = uint8_t(glm::convertSRGBToLinear(glm::vec1(((const uint8_t *)pixels)[i] / 255.f)).x * 255);
+    else
+      c = ((const uint8_t *)pixels)[i];
+    staging[o++] = c;
+    if (channels == 3 && o % 4 == 3)
+      staging[o++] = 255;
+  }
+  if (nc == 3)
+    nc = 4;
+  auto *img = new RefImage();
+  auto desc = cudaCreateChannelDesc(nc >= 1 ? 8 : 0, nc >= 2 ? 8 : 0, nc >= 3 ? 8 : 0, nc >= 4 ? 8 : 0,
+      cudaChannelFormatKindUnsigned);
+  RCK(cudaMalloc3DArray(&img->arr, &desc, make_cudaExtent(w, h, 0)));
+  cudaMemcpy3DParms p = {};
+  p.dstArray = img->arr;
+  p.srcPtr = make_cudaPitchedPtr(staging.data(), w * nc * sizeof(uint8_t), w, h);
+  p.extent = make_cudaExtent(w, h, 1);
+  p.kind = cudaMemcpyHostToDevice;
+  RCK(cudaMemcpy3D(&p));
+  cudaResourceDesc rd;
+  std::memset(&rd, 0, sizeof(rd));
+  rd.resType = cudaResourceTypeArray;
+  rd.res.array.array = img->arr;
+  cudaTextureDesc td;
+  std::memset(&td, 0, sizeof(td));
+  td.addressMode[0] = td.addressMode[1] = td.addressMode[2] = cudaAddressModeClamp;
+  td.filterMode = cudaFilterModeLinear;
+  td.readMode = cudaReadModeNormalizedFloat;
+  td.normalizedCoords = true;
+  RCK(cudaCreateTextureObject(&img->tex, &rd, &td, nullptr));
+  *out = img;
+  return 0;
+}
+
+int refgpu_image_destroy(RefImage *img)
+{
+  if (!img) return 0;
+  if (img->tex) cudaDestroyTextureObject(img->tex);
+  if (img->arr) cudaFreeArray(img->arr);
+  delete img;
+  return 0;
+}
+
+// Renderer::populateFrameData (Renderer.cpp:191-198): an image switches the frame to BackgroundMode::IMAGE
+int refgpu_scene_set_background_image(RefScene *s, RefImage *img)
+{
+  s->bgTex = img ? img->tex : 0;
+  return 0;
+}
 
 int refgpu_scene_create(const RefInstance *inst, int n, RefScene **out)
 {
@@ -554,8 +633,13 @@ int refgpu_render(const DvrFrameParams *p, const DvrCamera *c, RefScene *scene, 
       : (p->format == DVR_FORMAT_UFIXED8_RGBA_SRGB ? FrameFormat::SRGB : FrameFormat::UINT);
   fd.fb.size = uvec2(p->width, p->height);
   fd.fb.invSize = 1.f / vec2(fd.fb.size);
-  fd.renderer.backgroundMode = BackgroundMode::COLOR;
-  fd.renderer.background.color = vec4(p->background[0], p->background[1], p->background[2], p->background[3]);
+  if (scene->bgTex) {
+    fd.renderer.backgroundMode = BackgroundMode::IMAGE;
+    fd.renderer.background.texobj = scene->bgTex;
+  } else {
+    fd.renderer.backgroundMode = BackgroundMode::COLOR;
+    fd.renderer.background.color = vec4(p->background[0], p->background[1], p->background[2], p->background[3]);
+  }
   fd.renderer.ambientColor = vec3(1.f);
   fd.renderer.ambientIntensity = p->ambientRadiance;
   fd.renderer.occlusionDistance = p->occlusionDistance > 0.f ? p->occlusionDistance : 1e20f;

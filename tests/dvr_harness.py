@@ -83,6 +83,8 @@ class SceneDesc:
     ambient_radiance: float = 1.0
     occlusion_distance: float = 1e20
     dpt_reference_grid: bool = False  # walk the grid content the reference builds (Q7/Q8)
+    # renderer "background" given as an Array2D image: (pixels [h, w, channels], capi.DVR_IMAGE_* component type)
+    background_image: Optional[tuple] = None
 
 
 def default_scene(n=64, width=256, height=256, rate=0.5, field="ml", **kw) -> SceneDesc:
@@ -174,16 +176,49 @@ def render_oracle(scene: SceneDesc, frames=1, checkerboard=False, slab=None, sta
         if key in out:
             setattr(b, name, out[key].ctypes.data_as(C.c_void_p))
     total = 0
-    for frame_id, cb in frame_sequence(scene, frames, checkerboard):
-        p = _params(scene, frame_id, cb)
-        s = C.c_uint64()
-        rc = ob.cpu().oracle_render(C.byref(p), C.byref(scene.camera), vols, len(scene.volumes), C.byref(b),
-                                    C.byref(s), 0, 0)
-        assert rc == 0
-        total += s.value
+    if scene.background_image is not None:
+        st = staged_background(*scene.background_image)
+        assert ob.cpu().oracle_set_background_image(st.ctypes.data_as(C.c_void_p), C.c_int(st.shape[2]),
+                                                    C.c_int(st.shape[1]), C.c_int(st.shape[0])) == 0
+    try:
+        for frame_id, cb in frame_sequence(scene, frames, checkerboard):
+            p = _params(scene, frame_id, cb)
+            s = C.c_uint64()
+            rc = ob.cpu().oracle_render(C.byref(p), C.byref(scene.camera), vols, len(scene.volumes), C.byref(b),
+                                        C.byref(s), 0, 0)
+            assert rc == 0
+            total += s.value
+    finally:
+        if scene.background_image is not None:
+            ob.cpu().oracle_set_background_image(None, C.c_int(0), C.c_int(0), C.c_int(0))
     if return_samples:
         return out, total
     return out
+
+
+def staged_background(pixels: np.ndarray, component_type: int) -> np.ndarray:
+    """The RGBA8 texels the renderer's staging pass makes of a background array (utility/CudaImageTexture.cpp:43-58,
+    84-101): truncating float -> uint8, fixed-point rescale, sRGB linearisation of EVERY component, 3 -> 4 channels
+    with alpha 255.  numpy restatement for O-cpu; [h, w, 1|2|4] uint8."""
+    px = np.ascontiguousarray(pixels)
+    if px.ndim == 2:
+        px = px[:, :, None]
+    if component_type == capi.DVR_IMAGE_FLOAT32:
+        st = (px.astype(np.float32) * np.float32(255)).astype(np.uint8)
+    elif component_type == capi.DVR_IMAGE_UFIXED16:
+        st = ((px.astype(np.float32) / np.float32(65535.0)) * np.float32(255)).astype(np.uint8)
+    elif component_type == capi.DVR_IMAGE_UFIXED32:
+        st = ((px.astype(np.float32) / np.float32(4294967295.0)) * np.float32(255)).astype(np.uint8)
+    elif component_type == capi.DVR_IMAGE_SRGB8:
+        v = px.astype(np.float32) / np.float32(255.0)
+        lin = np.where(v <= np.float32(0.04045), v * np.float32(0.07739938080495356),
+                       np.power((v + np.float32(0.055)) * np.float32(0.9478672985781991), np.float32(2.4)))
+        st = (lin.astype(np.float32) * np.float32(255)).astype(np.uint8)
+    else:
+        st = px.astype(np.uint8)
+    if st.shape[2] == 3:
+        st = np.concatenate([st, np.full(st.shape[:2] + (1,), 255, np.uint8)], axis=2)
+    return np.ascontiguousarray(st)
 
 
 def frame_sequence(scene, frames, checkerboard):
@@ -230,6 +265,7 @@ class CudaScene:
             self.volumes.append(capi.Volume.create(f, v.tf, v.value_range, v.unit_distance, v.vol_id))
         self.instances, self.n = capi.make_instances(
             self.volumes, [v.world_to_object for v in scene.volumes], [v.inst_id for v in scene.volumes])
+        self.bg_image = capi.Image.create(*scene.background_image) if scene.background_image is not None else None
         n = scene.width * scene.height
         t = torch
         self.buf = {"accum": t.zeros((n, 4), dtype=t.float32, device=self.device)}
@@ -248,7 +284,8 @@ class CudaScene:
                                      g("albedo"), g("normal"))
 
     def render(self, frame_id=0, cb=-1, skip=False, tile_rank=0, tile_ranks=1, stats=False):
-        p = _params(self.scene, frame_id, cb, skip=skip, tile_rank=tile_rank, tile_ranks=tile_ranks)
+        p = _params(self.scene, frame_id, cb, skip=skip, tile_rank=tile_rank, tile_ranks=tile_ranks,
+                    background_image=self.bg_image)
         if stats:
             st = self.torch.zeros(4, dtype=self.torch.int64, device=self.device)
             capi.render_instrumented(p, self.scene.camera, self.instances, self.n, self.fb, st.data_ptr())
@@ -284,6 +321,8 @@ class CudaScene:
             v.destroy()
         for f in self.fields:
             f.destroy()
+        if self.bg_image is not None:
+            self.bg_image.destroy()
 
 
 def render_cuda(scene: SceneDesc, frames=1, checkerboard=False, skip=False):
@@ -346,6 +385,17 @@ def render_refgpu(scene: SceneDesc, frames=1, checkerboard=False, grids=None, re
     sc = C.c_void_p()
     rc = lib.refgpu_scene_create(inst, C.c_int(len(scene.volumes)), C.byref(sc))
     assert rc == 0, lib.refgpu_last_error()
+    ref_img = None
+    if scene.background_image is not None:
+        px = np.ascontiguousarray(scene.background_image[0])
+        if px.ndim == 2:
+            px = px[:, :, None]
+        ref_img = C.c_void_p()
+        rc = lib.refgpu_image_create(px.ctypes.data_as(C.c_void_p), C.c_int(scene.background_image[1]),
+                                     C.c_int(px.shape[2]), C.c_uint32(px.shape[1]), C.c_uint32(px.shape[0]),
+                                     C.byref(ref_img))
+        assert rc == 0, lib.refgpu_last_error()
+        lib.refgpu_scene_set_background_image(sc, ref_img)
     n = scene.width * scene.height
     dev = torch.device("cuda:0")
     buf = {"accum": torch.full((n, 4), 777.0, dtype=torch.float32, device=dev)}
@@ -369,6 +419,8 @@ def render_refgpu(scene: SceneDesc, frames=1, checkerboard=False, grids=None, re
         a = v.cpu().numpy()
         out[k] = a.view(np.uint32) if a.dtype == np.int32 else a
     lib.refgpu_scene_destroy(sc)
+    if ref_img is not None:
+        lib.refgpu_image_destroy(ref_img)
     for h in vols:
         lib.refgpu_volume_destroy(h)
     for f in fields:
@@ -493,6 +545,28 @@ def scene_zoo():
         cam = capi.camera_perspective(pose.position, pose.direction, pose.up, pose.fovy, pose.aspect)
         zoo[f"nvdb_{key}_r14"] = (SceneDesc([v], W, H, cam, volume_sampling_rate=0.5,
                                             integrator=capi.DVR_INTEGRATOR_DEFAULT), 2, False)
+    # renderer "background" as an Array2D image (a18): float RGB (padded to RGBA, alpha 255) behind a translucent volume
+    # with the jittered default renderer and 2 spp — every pixel-sample fetches the image at its own jittered screen
+    # coordinate; sRGB RGBA (alpha linearised too, the reference's quirk) with the centred raycast renderer and a
+    # small volume, so most pixels take the missed-ray path; a 2-channel 16-bit image (texture reads (r, g, 0, 1))
+    rng = np.random.default_rng(11)
+    yy, xx = np.mgrid[0:13, 0:17]
+    img_f = np.stack([xx / 16.0, yy / 12.0, 0.5 + 0.5 * np.sin(xx * 0.9) * np.cos(yy * 0.7)], axis=-1).astype(np.float32)
+    s = default_scene(32, W, H, rate=0.5, field="blobs", integrator=capi.DVR_INTEGRATOR_DEFAULT, num_iterations=2,
+                      fmt=capi.DVR_FORMAT_FLOAT32_VEC4, channels=("depth", "objId", "albedo"))
+    s.volumes[0].unit_distance = 0.6
+    s.background_image = (img_f, capi.DVR_IMAGE_FLOAT32)
+    zoo["bgimage_float3_default_spp2_f2"] = (s, 2, False)
+    img_s = rng.integers(0, 256, (9, 21, 4), dtype=np.uint8)
+    s = default_scene(24, 120, 72, rate=0.5)
+    pose = scenes.orbit_camera((-1, -1, -1), (1, 1, 1), 120, 72, dist_scale=2.5)
+    s.camera = capi.camera_perspective(pose.position, pose.direction, pose.up, pose.fovy, pose.aspect)
+    s.background_image = (img_s, capi.DVR_IMAGE_SRGB8)
+    zoo["bgimage_srgb4_raycast_far"] = (s, 1, False)
+    img_u = rng.integers(0, 65536, (6, 5, 2), dtype=np.uint16)
+    s = default_scene(24, 64, 48, rate=0.5, integrator=capi.DVR_INTEGRATOR_DEFAULT)
+    s.background_image = (img_u, capi.DVR_IMAGE_UFIXED16)
+    zoo["bgimage_u16x2_checkerboard_p5"] = (s, 5, True)
     # empty world (no volume instance): background only
     s = default_scene(8, 40, 24, rate=0.5)
     s.volumes = []

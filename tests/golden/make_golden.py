@@ -21,8 +21,18 @@ import dvr_harness as H  # noqa: E402
 
 
 def main():
+    # `--add name1,name2`: render only those scenes and MERGE them into the committed fixture, leaving the existing
+    # pins byte for byte as they are (the round-1 renders stay the reference for the round-1 scenes)
+    only = None
+    if len(sys.argv) > 2 and sys.argv[1] == "--add":
+        only = set(sys.argv[2].split(","))
     out = {}
+    if only is not None:
+        old = np.load(os.path.join(HERE, "refgpu_scenes.npz"))
+        out = {k: old[k] for k in old.files}
     for name, (scene, frames, cb) in H.scene_zoo().items():
+        if only is not None and name not in only:
+            continue
         r = H.render_refgpu(scene, frames=frames, checkerboard=cb)
         for k, v in r.items():
             out[f"{name}/{k}"] = v
@@ -31,6 +41,8 @@ def main():
     os.makedirs(dst, exist_ok=True)
     np.savez_compressed(os.path.join(dst, "refgpu_scenes.npz"), **out)
     print("wrote", os.path.join(dst, "refgpu_scenes.npz"))
+    if only is not None:
+        return
 
     # dpt renderer: the reference's tracker (O-gpu) over O-cpu's majorant grid (the product's grid is tested
     # to be bit-identical to it); frame 0 colour + the accumulation of DPT_GOLDEN_FRAMES frames

@@ -11,7 +11,7 @@ import os
 
 import numpy as np
 
-from visrtx_b200 import capi
+from visrtx_b200 import pods as capi  # POD structs only: the oracle bindings never load libdvr_b200.so
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 ORACLE_DIR = os.path.join(ROOT, "oracle")

@@ -25,13 +25,24 @@ def test_header_and_library_export_the_same_symbols():
         assert hasattr(capi.lib, name), f"libdvr_b200.so does not export {name}"
 
 
-def test_struct_layouts_match_header_sizes():
-    # sizes the C compiler gives the PODs (checked against ctypes mirrors; a mismatch would corrupt launches)
-    assert C.sizeof(capi.DvrCamera) == 4 + 16 + 12 * 6 + 8
-    assert C.sizeof(capi.DvrVolumeInstance) == 8 + 48 + 8
-    assert C.sizeof(capi.DvrFrameBuffers) == 9 * 8
-    assert C.sizeof(capi.DvrFrameParams) == 4 * 8 + 16 + 8 + 4 + 4 + 12 + 12
-    assert C.sizeof(capi.DvrRenderStats) == 32
+def test_struct_layouts_match_header_sizes(tmp_path):
+    """The ctypes mirrors against what the C compiler makes of include/dvr_b200.h itself (sizes and the offsets of the
+    last members): a mismatch would corrupt every launch."""
+    import subprocess
+    src = tmp_path / "sizes.c"
+    src.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "dvr_b200.h"\nint main(void){printf("%zu %zu %zu %zu %zu %zu %zu %zu %zu\\n",'
+                   'sizeof(DvrCamera),sizeof(DvrVolumeInstance),sizeof(DvrFrameBuffers),sizeof(DvrFrameParams),'
+                   'sizeof(DvrRenderStats),sizeof(DvrPeerSync),offsetof(DvrFrameParams,backgroundImage),'
+                   'offsetof(DvrFrameParams,partialCullToBounds),offsetof(DvrFrameBuffers,outColorMirror));return 0;}\n')
+    exe = tmp_path / "sizes"
+    subprocess.run(["gcc", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)], check=True)
+    want = [int(v) for v in subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.split()]
+    got = [C.sizeof(capi.DvrCamera), C.sizeof(capi.DvrVolumeInstance), C.sizeof(capi.DvrFrameBuffers),
+           C.sizeof(capi.DvrFrameParams), C.sizeof(capi.DvrRenderStats), C.sizeof(capi.DvrPeerSync),
+           capi.DvrFrameParams.backgroundImage.offset, capi.DvrFrameParams.partialCullToBounds.offset,
+           capi.DvrFrameBuffers.outColorMirror.offset]
+    assert got == want
+    assert C.sizeof(capi.DvrCamera) == 4 + 16 + 12 * 6 + 8 and C.sizeof(capi.DvrFrameParams) == 96
 
 
 def test_version():

@@ -106,6 +106,45 @@ def test_anari_frame_equals_cabi_frame_and_oracle():
     s.close()
 
 
+def test_background_image_through_anari_equals_cabi_and_reference():
+    """Renderer parameter "background" as an Array2D (Renderer.cpp:154,175-198): sampled per pixel-sample at its screen
+    coordinate.  ANARI frame == C-ABI frame (same texture path) and within north_star's tolerance of O-gpu, which runs
+    the reference's own getBackground; replacing the array's contents (map/unmap) re-finalises the renderer."""
+    import oracle_binding as ob
+    zoo_scene, frames, _ = H.scene_zoo()["bgimage_float3_default_spp2_f2"]
+    img = zoo_scene.background_image[0]
+    s = AnariScene(32, 96, 96, "default", 0.5, color_type=A.FLOAT32_VEC4, channels=("depth", "objectId"),
+                   vox=scenes.blobs_np(32))
+    d = s.d
+    d.set(s.volume, "unitDistance", A.FLOAT32, 0.6)
+    d.commit(s.volume)
+    bg = d.new_array2d(img, A.FLOAT32_VEC3)
+    d.set(s.renderer, "background", A.ARRAY2D, bg)
+    d.set(s.renderer, "pixelSamples", A.INT32, 2)
+    d.commit(s.renderer)
+    for _ in range(frames):
+        s.render()
+    color, w, h, t = d.map_frame(s.frame, "channel.color")
+    assert not _errors(d), d.messages
+    assert not [m for m in d.messages if "background" in m[2]], d.messages  # no "ignored" warning any more
+    zoo_scene.volumes[0].inst_id = 0xFFFFFFFF
+    ref = H.render_cuda(zoo_scene, frames=frames)
+    assert np.array_equal(color.reshape(-1, 4), ref["color"])
+    if ob.have_ref_gpu():
+        want = H.render_refgpu(zoo_scene, frames=frames)
+        dd = np.abs(color.reshape(-1, 4) - want["color"]).max(axis=-1) * 255.0
+        assert dd.max() <= 2.0
+    # the image is really used: a constant-colour render differs in the missed pixels
+    d.unset(s.renderer, "background")
+    d.set(s.renderer, "background", A.FLOAT32_VEC4, (0.1, 0.1, 0.1, 1.0))
+    d.commit(s.renderer)
+    s.render()
+    flat, _, _, _ = d.map_frame(s.frame, "channel.color")
+    assert np.abs(flat.reshape(-1, 4) - color.reshape(-1, 4)).max() > 0.2
+    d.release(bg)
+    s.close()
+
+
 def test_accumulation_reset_semantics_and_frame_properties():
     s = AnariScene(32, 64, 64, "default", 0.5, color_type=A.FLOAT32_VEC4, channels=())
     d = s.d

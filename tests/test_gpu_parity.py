@@ -25,9 +25,18 @@ def _pix_diff(a, b, fmt):
     return np.abs(H.unpack_rgba8(a) - H.unpack_rgba8(b)).max(axis=-1)
 
 
-def _check(got, want, scene, frames=1, strict=False, name=""):
+REPORT = {}  # per-scene figures, written to gpurun_out/parity_report.json at the end of the module
+
+
+def _check(got, want, scene, frames=1, strict=True, name="", against=""):
+    """north_star tolerance: every pixel <= 2/255 after tonemap, PSNR >= 45 dB.  strict=False (comparisons with the
+    CPU restatement only, never with reference renders): up to 0.1 % of the pixels may differ by <= 6/255 — rays whose
+    early termination at opacity 0.99 flips by one sample between the software and the hardware texture filter; the
+    count is recorded per scene in the parity report."""
     max_d, psnr = H.compare_color(got["color"], want["color"], scene.fmt)
     d = _pix_diff(got["color"], want["color"], scene.fmt)
+    REPORT[f"{against}:{name}"] = {"max_abs_255": float(max_d), "psnr_db": float(psnr), "pixels": int(d.size),
+                                   "pixels_gt_2": int((d > 2).sum()), "pixels_identical": int((d == 0).sum())}
     assert psnr >= 45.0, (name, psnr)
     assert (d <= 2).mean() >= 0.999, (name, float((d <= 2).mean()))
     assert max_d <= (2.0 if strict else 6.0), (name, max_d)
@@ -47,7 +56,7 @@ def test_cuda_matches_golden_reference_renders(name):
     g = np.load(os.path.join(GOLD, "refgpu_scenes.npz"))
     want = {k.split("/", 1)[1]: g[k] for k in g.files if k.startswith(name + "/")}
     got = H.render_cuda(scene, frames=frames, checkerboard=cb)
-    _check(got, want, scene, frames, name=name)
+    _check(got, want, scene, frames, name=name, against="golden-O-gpu")
 
 
 @pytest.mark.parametrize("name", sorted(ZOO))
@@ -55,22 +64,33 @@ def test_cuda_matches_oracle_cpu(name):
     scene, frames, cb = ZOO[name]
     got = H.render_cuda(scene, frames=frames, checkerboard=cb)
     want = H.render_oracle(scene, frames=frames, checkerboard=cb)
-    _check(got, want, scene, frames, name=name)
+    _check(got, want, scene, frames, strict=False, name=name, against="O-cpu")
 
 
-@pytest.mark.parametrize("name", ["ml48_raycast_r0.5", "two_volumes_lens", "ml32_checkerboard_p6", "blobs32_u16",
-                                  "nvdb_fog_r20", "nvdb_fp4_r14", "nvdb_fp8_r14", "nvdb_fp16_r14", "nvdb_fpn_r14"])
+def teardown_module(module):
+    import json
+    out = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpurun_out")
+    try:
+        os.makedirs(out, exist_ok=True)
+        with open(os.path.join(out, "parity_report.json"), "w") as f:
+            json.dump(REPORT, f, indent=1, sort_keys=True)
+    except OSError:
+        pass
+
+
+@pytest.mark.parametrize("name", sorted(ZOO))
 def test_cuda_matches_reference_device_code_live(name):
     if not ob.have_ref_gpu():
         pytest.skip("oracle/_ref/libref_gpu_dvr.so not present")
     scene, frames, cb = ZOO[name]
     got = H.render_cuda(scene, frames=frames, checkerboard=cb)
     want = H.render_refgpu(scene, frames=frames, checkerboard=cb)
-    _check(got, want, scene, frames, strict=True, name=name)
+    _check(got, want, scene, frames, strict=True, name=name, against="live-O-gpu")
     # most pixels agree to the last bit of the float accumulation buffer
     # (the thin-lens + instance-transform and the NanoVDB scenes have more places where FMA contraction may differ)
-    assert (got["accum"] == want["accum"]).all(axis=-1).mean() > (
-        0.8 if name == "two_volumes_lens" or name.startswith("nvdb") else 0.9)
+    bit_identical = float((got["accum"] == want["accum"]).all(axis=-1).mean())
+    REPORT[f"live-O-gpu:{name}"]["accum_bit_identical_frac"] = bit_identical
+    assert bit_identical > (0.8 if name == "two_volumes_lens" or name.startswith("nvdb") else 0.9), (name, bit_identical)
 
 
 def test_config_c1_full_size():
@@ -78,9 +98,9 @@ def test_config_c1_full_size():
     scene = H.default_scene(64, 512, 512, rate=0.5)
     got = H.render_cuda(scene)
     want = H.render_oracle(scene)
-    _check(got, want, scene, name="C1")
+    _check(got, want, scene, strict=False, name="C1", against="O-cpu")
     if ob.have_ref_gpu():
-        _check(got, H.render_refgpu(scene), scene, strict=True, name="C1/O-gpu")
+        _check(got, H.render_refgpu(scene), scene, strict=True, name="C1", against="live-O-gpu")
 
 
 @pytest.mark.parametrize("name", ["ml48_raycast_r1.0", "blobs48_translucent", "two_volumes_lens", "blobs32_u8",
@@ -231,7 +251,7 @@ def test_float64_and_float16_fields():
     s16o.volumes[0].unit_distance = 0.5
     s16o.volumes[0].voxels = base.astype(np.float16).astype(np.float32)
     want16 = H.render_oracle(s16o)
-    _check(got16, want16, s16, name="f16")
+    _check(got16, want16, s16, strict=False, name="f16", against="O-cpu")
 
 
 def test_device_pointer_field_upload_equals_host_upload():
@@ -301,6 +321,53 @@ def test_full_size_properties_c2():
     finally:
         v.destroy()
         f.destroy()
+
+
+@pytest.mark.parametrize("config", ["c2", "c3", "c5", "c5_tree_walk"])
+def test_benchmark_configs_match_reference_device_code_at_full_size(config, monkeypatch):
+    """The BASELINE.json configs AT THE SIZES THE BENCH TIMES — C2 1024^3 f32 @1080p, C3 2048^3 UFIXED16 sparse @4K
+    with macrocell skipping, C5 NanoVDB fog r=200 @1080p (apron bricks, and the tree walk with bricks disabled) — frame
+    0 of the benchmark camera against O-gpu (the reference's device code) live on this GPU: north_star's per-pixel
+    <= 2/255 and PSNR >= 45 dB, depth to 2e-5 relative, identical hit masks.  Scene construction is bench.py's own."""
+    if not ob.have_ref_gpu():
+        pytest.skip("oracle/_ref/libref_gpu_dvr.so not present")
+    import argparse
+    import sys
+    import torch
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    import bench
+    a = argparse.Namespace(config=config.split("_")[0], size=1024, width=1920, height=1080, rate=0.5, unit_distance=256.0,
+                           field="ml", skip=-1, mode="auto", nvdb_codec="float", steps=1, warmup=0, cpu_rows=0)
+    a = bench.apply_preset(a)
+    if config == "c5_tree_walk":
+        monkeypatch.setenv("DVR_B200_NVDB_BRICKS", "0")
+    device = torch.device("cuda", 0)
+    stream = torch.cuda.current_stream().cuda_stream
+    vol = bench.make_scene(a, torch, device)
+    field = bench.create_field(a, capi, vol, stream)
+    tf = capi.tf_discretize(color=bench.scene_colormap(a))
+    v = capi.Volume.create(field, tf, (0.0, 1.0), a.unit_distance, 0, stream)
+    inst, ninst = capi.make_instances([v], None, [0])
+    cam, _ = bench.orbit(a)
+    npx = a.width * a.height
+    accum = torch.zeros((npx, 4), dtype=torch.float32, device=device)
+    color = torch.zeros(npx, dtype=torch.int32, device=device)
+    depth = torch.zeros(npx, dtype=torch.float32, device=device)
+    fb = capi.frame_buffers(accum.data_ptr(), color.data_ptr(), depth.data_ptr())
+    try:
+        p = capi.frame_params(a.width, a.height, capi.DVR_FORMAT_UFIXED8_RGBA_SRGB, capi.DVR_INTEGRATOR_DEFAULT, 0, -1, 1,
+                              a.rate, (0.1, 0.1, 0.1, 1.0), skip=bool(a.skip))
+        capi.render(p, cam, inst, ninst, fb, stream)
+        torch.cuda.synchronize()
+        (ref_color, ref_depth), _ = bench.ref_gpu_frame0(a, torch, vol)
+        par = bench.parity_block(torch, 4, color, ref_color, depth, ref_depth, what=config)
+        REPORT[f"live-O-gpu:full-size-{config}"] = par
+        assert par["max_abs_255"] <= 2 and par["psnr_db"] >= 45.0, par
+        assert par["depth_hit_mask_equal"] and par["depth_max_rel"] <= 2e-5, par
+        assert (ref_depth < 1e29).float().mean().item() > 0.02  # the volume is on screen
+    finally:
+        v.destroy()
+        field.destroy()
 
 
 def test_closed_form_lattice_advance_is_bit_identical_to_the_add_loop():

@@ -24,6 +24,7 @@ DEVICE, ARRAY1D, ARRAY2D, ARRAY3D, CAMERA, FRAME, GROUP, INSTANCE, RENDERER, SPA
     501, 504, 505, 506, 507, 508, 510, 511, 514, 517, 518, 519)
 UINT8, INT32, UINT32, UINT32_VEC2, UINT64 = 1004, 1016, 1020, 1021, 1028
 FIXED8, UFIXED8, UFIXED8_VEC4, FIXED16, UFIXED16 = 1032, 1036, 1039, 1040, 1044
+UFIXED8_VEC3, UFIXED16_VEC2 = 1038, 1045
 FLOAT16, FLOAT32, FLOAT32_VEC2, FLOAT32_VEC3, FLOAT32_VEC4, FLOAT64 = 1064, 1068, 1069, 1070, 1071, 1072
 UFIXED8_RGBA_SRGB = 2003
 FLOAT32_BOX1, FLOAT32_BOX2, FLOAT32_BOX3 = 2008, 2009, 2010
@@ -145,6 +146,12 @@ class Device:
         data = np.ascontiguousarray(data)
         self._keep.append(data)
         return lib.anariNewArray1D(self.handle, data.ctypes.data, None, None, elem_type, n or data.shape[0])
+
+    def new_array2d(self, data: np.ndarray, elem_type: int):
+        """data: [h, w] or [h, w, channels] (row 0 first)."""
+        data = np.ascontiguousarray(data)
+        self._keep.append(data)
+        return lib.anariNewArray2D(self.handle, data.ctypes.data, None, None, elem_type, data.shape[1], data.shape[0])
 
     def new_array3d(self, data: np.ndarray, elem_type: int):
         data = np.ascontiguousarray(data)

@@ -12,18 +12,8 @@ from typing import Optional, Sequence
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("DVR_B200_LIB") or os.path.join(_HERE, "libdvr_b200.so")
 
-DVR_TF_SIZE = 256
-DVR_MACROCELL_WIDTH = 16
-
-# enums (include/dvr_b200.h)
-DVR_OK, DVR_ERR_INVALID_ARGUMENT, DVR_ERR_NO_DEVICE, DVR_ERR_CUDA, DVR_ERR_UNSUPPORTED, DVR_ERR_OUT_OF_MEMORY = (
-    0, -1, -2, -3, -4, -5)
-DVR_FLOAT32, DVR_UFIXED8, DVR_FIXED8, DVR_UFIXED16, DVR_FIXED16, DVR_FLOAT64, DVR_FLOAT16 = range(7)
-DVR_FILTER_LINEAR, DVR_FILTER_NEAREST = 0, 1
-DVR_FORMAT_FLOAT32_VEC4, DVR_FORMAT_UFIXED8_VEC4, DVR_FORMAT_UFIXED8_RGBA_SRGB = 0, 1, 2
-DVR_CAMERA_PERSPECTIVE, DVR_CAMERA_ORTHOGRAPHIC = 0, 1
-DVR_INTEGRATOR_RAYCAST, DVR_INTEGRATOR_DEFAULT, DVR_INTEGRATOR_DPT, DVR_INTEGRATOR_TEST = 0, 1, 2, 3
-DVR_SKIP_OFF, DVR_SKIP_ON, DVR_SKIP_AUTO = 0, 1, 2
+from .pods import *  # noqa: F401,F403  (enums, POD structs, frame_params / frame_buffers / peer_sync)
+from .pods import DvrCamera, DvrVolumeInstance, DvrFrameBuffers, DvrFrameParams, DvrRenderStats, DvrPeerSync
 
 # every symbol include/dvr_b200.h declares (tests check the library exports all of them)
 EXPORTED_SYMBOLS = [
@@ -34,7 +24,7 @@ EXPORTED_SYMBOLS = [
     "dvr_field_bounds", "dvr_field_step_size", "dvr_field_device_bytes", "dvr_field_build_macrocells",
     "dvr_field_macrocells", "dvr_field_value_range",
     "dvr_volume_create", "dvr_volume_update", "dvr_volume_destroy", "dvr_volume_majorants",
-    "dvr_volume_dda_majorants",
+    "dvr_volume_dda_majorants", "dvr_image_create", "dvr_image_destroy",
     "dvr_post_convert_float_color", "dvr_post_composite_depth", "dvr_post_outline", "dvr_post_visualize_depth",
     "dvr_post_pick", "dvr_selftest_lattice_advance", "dvr_bounds_screen_rect",
     "dvr_render", "dvr_render_instrumented", "dvr_launch_count",
@@ -48,55 +38,6 @@ class DvrError(RuntimeError):
     def __init__(self, code: int, msg: str):
         super().__init__(f"dvr error {code}: {msg}")
         self.code = code
-
-
-class DvrCamera(C.Structure):
-    _fields_ = [("type", C.c_int32), ("region", C.c_float * 4), ("pos", C.c_float * 3), ("dir", C.c_float * 3),
-                ("up", C.c_float * 3), ("du", C.c_float * 3), ("dv", C.c_float * 3), ("p00", C.c_float * 3),
-                ("scaledAperture", C.c_float), ("aspect", C.c_float)]
-
-
-class DvrVolumeInstance(C.Structure):
-    _fields_ = [("volume", C.c_void_p), ("worldToObject", C.c_float * 12), ("instanceId", C.c_uint32),
-                ("_pad", C.c_uint32)]
-
-
-class DvrFrameBuffers(C.Structure):
-    _fields_ = [("colorAccumulation", C.c_void_p), ("outColor", C.c_void_p), ("depth", C.c_void_p),
-                ("primId", C.c_void_p), ("objId", C.c_void_p), ("instId", C.c_void_p), ("albedo", C.c_void_p),
-                ("normal", C.c_void_p), ("outColorMirror", C.c_void_p)]
-
-
-class DvrFrameParams(C.Structure):
-    _fields_ = [("width", C.c_uint32), ("height", C.c_uint32), ("format", C.c_int32), ("integrator", C.c_int32),
-                ("frameID", C.c_int32), ("checkerboardID", C.c_int32), ("numIterations", C.c_int32),
-                ("inverseVolumeSamplingRate", C.c_float), ("background", C.c_float * 4),
-                ("tileRank", C.c_uint32), ("tileRanks", C.c_uint32), ("useMacrocellSkipping", C.c_int32),
-                ("tileBand", C.c_int32), ("maxDepth", C.c_int32), ("ambientRadiance", C.c_float),
-                ("occlusionDistance", C.c_float), ("dptReferenceGrid", C.c_int32), ("partialCullToBounds", C.c_int32), ("_reserved", C.c_int32 * 1)]
-
-
-class DvrRenderStats(C.Structure):
-    _fields_ = [("samplesTaken", C.c_ulonglong), ("samplesSkipped", C.c_ulonglong), ("raysHit", C.c_ulonglong),
-                ("macrocellsTouched", C.c_ulonglong)]
-
-
-class DvrPeerSync(C.Structure):
-    _fields_ = [("nSignal", C.c_uint32), ("signalValue", C.c_uint32), ("signal", C.c_void_p * 16),
-                ("nWait", C.c_uint32), ("waitValue", C.c_uint32), ("wait", C.c_void_p), ("errorFlag", C.c_void_p)]
-
-
-def peer_sync(signal_ptrs=(), signal_value=0, wait_ptr=0, n_wait=0, wait_value=0, error_flag=0) -> "DvrPeerSync":
-    s = DvrPeerSync()
-    s.nSignal, s.signalValue = len(signal_ptrs), int(signal_value) & 0xFFFFFFFF
-    for i, p in enumerate(signal_ptrs):
-        s.signal[i] = p
-    s.nWait, s.waitValue, s.wait = int(n_wait), int(wait_value) & 0xFFFFFFFF, wait_ptr or None
-    s.errorFlag = error_flag or None
-    return s
-
-
-IDENTITY_3X4 = (1.0, 0.0, 0.0, 0.0, 0.0, 1.0, 0.0, 0.0, 0.0, 0.0, 1.0, 0.0)
 
 
 def _load() -> C.CDLL:
@@ -324,33 +265,30 @@ def make_instances(volumes: Sequence[Volume], xfms=None, inst_ids=None):
     return arr, n
 
 
-def frame_params(width, height, fmt=DVR_FORMAT_UFIXED8_RGBA_SRGB, integrator=DVR_INTEGRATOR_RAYCAST, frame_id=0,
-                 checkerboard_id=-1, num_iterations=1, volume_sampling_rate=0.125, background=(0.0, 0.0, 0.0, 1.0),
-                 tile_rank=0, tile_ranks=1, skip=False, tile_band=1, max_depth=5, ambient_radiance=1.0,
-                 occlusion_distance=1e20, dpt_reference_grid=False, partial_cull_to_bounds=False) -> DvrFrameParams:
-    p = DvrFrameParams()
-    p.width, p.height, p.format, p.integrator = int(width), int(height), int(fmt), int(integrator)
-    p.frameID, p.checkerboardID, p.numIterations = int(frame_id), int(checkerboard_id), int(num_iterations)
-    import numpy as np
-    p.inverseVolumeSamplingRate = float(np.float32(1.0) / np.float32(volume_sampling_rate))
-    p.background = _f4(*background)
-    p.tileRank, p.tileRanks = int(tile_rank), int(tile_ranks)
-    p.useMacrocellSkipping = DVR_SKIP_AUTO if skip == "auto" else (DVR_SKIP_ON if skip else DVR_SKIP_OFF)
-    p.tileBand = int(tile_band)
-    p.maxDepth, p.ambientRadiance, p.occlusionDistance = int(max_depth), float(ambient_radiance), float(occlusion_distance)
-    p.dptReferenceGrid = 1 if dpt_reference_grid else 0
-    p.partialCullToBounds = 1 if partial_cull_to_bounds else 0
-    return p
 
 
-def frame_buffers(accum: int, out_color: int, depth: int = 0, prim: int = 0, obj: int = 0, inst: int = 0,
-                  albedo: int = 0, normal: int = 0, color_mirror: int = 0) -> DvrFrameBuffers:
-    b = DvrFrameBuffers()
-    b.outColorMirror = color_mirror or None
-    b.colorAccumulation, b.outColor = accum or None, out_color or None
-    b.depth, b.primId, b.objId, b.instId = depth or None, prim or None, obj or None, inst or None
-    b.albedo, b.normal = albedo or None, normal or None
-    return b
+class Image:
+    """DvrImage: the renderer's background image (host pixels [h, w, channels] -> RGBA8 texture on the device)."""
+
+    def __init__(self, handle):
+        self.handle = handle
+
+    @staticmethod
+    def create(pixels, component_type: int, stream: int = 0) -> "Image":
+        import numpy as np
+        pixels = np.ascontiguousarray(pixels)
+        if pixels.ndim == 2:
+            pixels = pixels[:, :, None]
+        h, w, c = pixels.shape
+        out = C.c_void_p()
+        _check(lib.dvr_image_create(pixels.ctypes.data_as(C.c_void_p), C.c_int(component_type), C.c_int(c), C.c_uint32(w),
+                                    C.c_uint32(h), C.c_void_p(stream), C.byref(out)))
+        return Image(out)
+
+    def destroy(self):
+        if self.handle:
+            _check(lib.dvr_image_destroy(self.handle))
+            self.handle = None
 
 
 def render(params: DvrFrameParams, camera: DvrCamera, instances, n_instances: int, buffers: DvrFrameBuffers,

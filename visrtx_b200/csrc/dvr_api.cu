@@ -62,6 +62,14 @@ static DeviceScratch *scratch()
       return nullptr;
     cudaMemset(s.sched, 0, kSchedSlots * 4 * sizeof(unsigned int));
     cudaDeviceGetAttribute(&s.sms, cudaDevAttrMultiProcessorCount, dev);
+    // DRAM fetch granularity of L2 misses (32 / 64 / 128 B).  The march reads the whole block-linear volume through
+    // scattered 32-byte sectors; a wider fill turns neighbouring sector misses into L2 hits.  A/B knob, measured in
+    // profiles/r02_l2_fetch_granularity.md.
+    if (const char *g = std::getenv("DVR_B200_L2_FETCH")) {
+      const int bytes = std::atoi(g);
+      if (bytes == 32 || bytes == 64 || bytes == 128)
+        cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)bytes);
+    }
   }
   return &s;
 }
@@ -197,6 +205,14 @@ struct DvrVolume
   // the macrocell grid the majorant buffers were allocated for: an update against a field of another shape is refused
   size_t allocCells = 0;
   int3 allocGridDims{0, 0, 0};
+};
+
+struct DvrImage
+{
+  cudaArray_t array = nullptr;
+  cudaTextureObject_t tex = 0;
+  uint32_t width = 0, height = 0;
+  int channels = 0;
 };
 
 static inline float3 v3(const float *p) { return make_float3(p[0], p[1], p[2]); }
@@ -1003,6 +1019,97 @@ int dvr_field_value_range(const DvrField *f, void *stream, float range[2])
   return rc;
 }
 
+// ---- background image --------------------------------------------------------------------------------
+
+// convertComponentUint8, utility/CudaImageTexture.cpp:43-58 (the float -> uint8 conversions truncate; values outside
+// [0, 255] are undefined behaviour there and saturate here)
+static inline uint8_t toU8(float v)
+{
+  if (!(v > 0.f))
+    return 0;
+  return v >= 255.f ? (uint8_t)255 : (uint8_t)v;
+}
+
+int dvr_image_create(const void *pixels, int componentType, int channels, uint32_t width, uint32_t height,
+    void *stream, DvrImage **out)
+{
+  if (!pixels || !out || width == 0 || height == 0 || channels < 1 || channels > 4
+      || componentType < DVR_IMAGE_FLOAT32 || componentType > DVR_IMAGE_SRGB8) {
+    setError("dvr_image_create: bad argument (host pixels, 1..4 channels, non-empty size)");
+    return DVR_ERR_INVALID_ARGUMENT;
+  }
+  if (dvr_device_count() <= 0) {
+    setError("dvr_image_create: no CUDA device (this library has no CPU fallback)");
+    return DVR_ERR_NO_DEVICE;
+  }
+  const size_t n = (size_t)width * height;
+  const int nc = channels == 3 ? 4 : channels; // three channels are padded with alpha 255
+  std::vector<uint8_t> staging(n * (size_t)nc);
+  size_t o = 0;
+  for (size_t i = 0; i < n * (size_t)channels; ++i) {
+    uint8_t c;
+    switch (componentType) {
+    case DVR_IMAGE_FLOAT32: c = toU8(((const float *)pixels)[i] * 255); break;
+    case DVR_IMAGE_UFIXED16: c = toU8((((const uint16_t *)pixels)[i] / 65535.f) * 255); break;
+    case DVR_IMAGE_UFIXED32: c = toU8((((const uint32_t *)pixels)[i] / float(UINT32_MAX)) * 255); break;
+    case DVR_IMAGE_SRGB8: {
+      // glm::convertSRGBToLinear (gtc/color_space.inl:33-43) on every component, alpha included, like the reference
+      const float v = ((const uint8_t *)pixels)[i] / 255.f;
+      const float lin = v <= 0.04045f ? v * 0.07739938080495356037151702786378f
+                                      : std::pow((v + 0.055f) * 0.94786729857819905213270142180095f, 2.4f);
+      c = toU8(lin * 255);
+      break;
+    }
+    default: c = ((const uint8_t *)pixels)[i]; break;
+    }
+    staging[o++] = c;
+    if (channels == 3 && o % 4 == 3)
+      staging[o++] = 255;
+  }
+  auto *img = new DvrImage();
+  img->width = width;
+  img->height = height;
+  img->channels = nc;
+  const cudaChannelFormatDesc desc =
+      cudaCreateChannelDesc(8, nc >= 2 ? 8 : 0, nc >= 3 ? 8 : 0, nc >= 4 ? 8 : 0, cudaChannelFormatKindUnsigned);
+  cudaError_t e = cudaMallocArray(&img->array, &desc, width, height);
+  cudaStream_t s = (cudaStream_t)stream;
+  if (e == cudaSuccess)
+    e = cudaMemcpy2DToArrayAsync(img->array, 0, 0, staging.data(), (size_t)width * nc, (size_t)width * nc, height,
+        cudaMemcpyHostToDevice, s);
+  if (e == cudaSuccess)
+    e = cudaStreamSynchronize(s); // the staging buffer is pageable and local
+  if (e == cudaSuccess) {
+    cudaResourceDesc rd;
+    std::memset(&rd, 0, sizeof(rd));
+    rd.resType = cudaResourceTypeArray;
+    rd.res.array.array = img->array;
+    cudaTextureDesc td;
+    std::memset(&td, 0, sizeof(td));
+    td.addressMode[0] = td.addressMode[1] = td.addressMode[2] = cudaAddressModeClamp;
+    td.filterMode = cudaFilterModeLinear;
+    td.readMode = cudaReadModeNormalizedFloat;
+    td.normalizedCoords = 1;
+    e = cudaCreateTextureObject(&img->tex, &rd, &td, nullptr);
+  }
+  if (e != cudaSuccess) {
+    dvr_image_destroy(img);
+    return cudaFail(e, "dvr_image_create");
+  }
+  *out = img;
+  return DVR_OK;
+}
+
+int dvr_image_destroy(DvrImage *img)
+{
+  if (!img)
+    return DVR_OK;
+  if (img->tex) cudaDestroyTextureObject(img->tex);
+  if (img->array) cudaFreeArray(img->array);
+  delete img;
+  return DVR_OK;
+}
+
 // ---- volumes -----------------------------------------------------------------------------------------
 
 int dvr_volume_update(DvrVolume *v, const float *tfRgba, const float valueRange[2], float unitDistance, uint32_t id,
@@ -1304,6 +1411,7 @@ static int renderImpl(const DvrFrameParams *p, const DvrCamera *camera, const Dv
   L.numIterations = p->checkerboardID >= 0 ? 1 : p->numIterations; // Renderer.cpp:168-169
   L.invSamplingRate = p->inverseVolumeSamplingRate;
   L.background = make_float4(p->background[0], p->background[1], p->background[2], p->background[3]);
+  L.bgTex = p->backgroundImage ? p->backgroundImage->tex : 0;
   L.maxDepth = p->maxDepth <= 0 ? 5 : (p->maxDepth > 256 ? 256 : p->maxDepth);
   L.ambientIntensity = p->ambientRadiance;
   L.occlusionDistance = p->occlusionDistance > 0.f ? p->occlusionDistance : 1e20f;
@@ -1650,6 +1758,10 @@ int dvr_resolve(const DvrFrameParams *p, const float *partialRgba, const float *
   R.format = p->format;
   R.frameID = p->frameID;
   R.background = make_float4(p->background[0], p->background[1], p->background[2], p->background[3]);
+  R.bgTex = p->backgroundImage ? p->backgroundImage->tex : 0;
+  R.invW = 1.f / (float)p->width;
+  R.invH = 1.f / (float)p->height;
+  R.centered = p->integrator == DVR_INTEGRATOR_RAYCAST ? 1 : 0;
   R.fb.accum = (float4 *)b->colorAccumulation;
   R.fb.outU32 = (uint32_t *)b->outColor;
   R.fb.outF32 = (float4 *)b->outColor;
@@ -1690,6 +1802,10 @@ static int compositeResolveImpl(const DvrFrameParams *p, const DvrCamera *camera
   R.format = p->format;
   R.frameID = p->frameID;
   R.background = make_float4(p->background[0], p->background[1], p->background[2], p->background[3]);
+  R.bgTex = p->backgroundImage ? p->backgroundImage->tex : 0;
+  R.invW = 1.f / (float)p->width;
+  R.invH = 1.f / (float)p->height;
+  R.centered = p->integrator == DVR_INTEGRATOR_RAYCAST ? 1 : 0;
   R.fb.accum = (float4 *)b->colorAccumulation;
   R.fb.outU32 = (uint32_t *)b->outColor;
   R.fb.outF32 = (float4 *)b->outColor;

@@ -255,6 +255,15 @@ __device__ __forceinline__ void cameraCreateRay(
   }
 }
 
+// getBackgroundImage, gpu/gpu_util.h:289-296: the constant colour, or a bilinear fetch of the RGBA8 background
+// texture (clamp, normalised coordinates) at the pixel-sample's screen coordinate
+__device__ __forceinline__ float4 backgroundAt(cudaTextureObject_t bgTex, const float4 constant, float sx, float sy)
+{
+  if (bgTex)
+    return tex2D<float4>(bgTex, sx, sy);
+  return constant;
+}
+
 // ---------------------------------------------------------------------------------------
 // output encoding (gpu/gpu_util.h:323-391; glm gtc/color_space.inl:10-28, func_packing.inl:67-80)
 // ---------------------------------------------------------------------------------------

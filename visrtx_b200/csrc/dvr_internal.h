@@ -38,6 +38,7 @@ struct FrameLaunch
   int format, integrator, frameID, checkerboardID, numIterations;
   float invSamplingRate;
   float4 background;
+  cudaTextureObject_t bgTex; // background image (0 = the constant colour)
   int maxDepth;
   float ambientIntensity, occlusionDistance;
   uint32_t tileRank, tileRanks, tileBand;
@@ -84,6 +85,10 @@ struct ResolveLaunch
   uint32_t width, height;
   int format, frameID;
   float4 background;
+  // background image (0 = constant colour) and what is needed to regenerate the pixel-sample's screen coordinate
+  cudaTextureObject_t bgTex;
+  float invW, invH;
+  int centered;
   BuffersDev fb;
   const float4 *partialRgba;
   const float *partialDepth;

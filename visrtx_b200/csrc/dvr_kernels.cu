@@ -204,6 +204,32 @@ __device__ __forceinline__ void accumResults(const AccumCtx &P, uint32_t px, uin
   }
 }
 
+// A pixel none of whose rays can enter a volume: what the march + Raycast_ptx.cu:139-166 produce for a miss, bit for
+// bit (colour 0*0 + bg*(1-0) = bg, depth min(1e30, tmax), ids ~0u).  With a constant background no Philox or camera
+// work is needed; with a background image the screen coordinate of every pixel-sample is regenerated (each missed
+// iteration consumes exactly the four draws of makePrimaryRay, cameraCreateRay.h:74-81).
+__device__ __forceinline__ void shadeMissedPixel(const AccumCtx &actx, uint32_t px, uint32_t py, const float4 bgConst,
+    cudaTextureObject_t bgTex, bool centered, float invW, float invH, int numIterations, bool initFrame)
+{
+  Philox rng;
+  if (bgTex && !centered)
+    rng.init((unsigned long long)(int)(py * actx.width + px), (unsigned long long)actx.frameID * 512ull);
+  for (int it = 0; it < numIterations; ++it) {
+    float4 bg = bgConst;
+    if (bgTex) {
+      float sx = (float)px, sy = (float)py;
+      if (!centered) {
+        const float4 r = rng.uniform4();
+        sx = __fadd_rn(sx, r.x);
+        sy = __fadd_rn(sy, r.y);
+      }
+      bg = tex2D<float4>(bgTex, __fmul_rn(sx, invW), __fmul_rn(sy, invH));
+    }
+    accumResults(actx, px, py, bg, 1e30f, f3(bg.x, bg.y, bg.z), f3(0.f, 0.f, 0.f), 0u, ~0u, ~0u, it,
+        initFrame && it == 0);
+  }
+}
+
 struct TfSelectShared
 {
   const float4 *smem;
@@ -284,13 +310,9 @@ __global__ void __launch_bounds__(kBlockThreads, (KIND >= FIELD_NANOVDB ? DVR_OC
 
     if (!DPT && P.missValid
         && ((int)px < P.missX0 || (int)px >= P.missX1 || (int)py < P.missY0 || (int)py >= P.missY1)) {
-      // No ray of this pixel can enter a volume: what the march + Raycast_ptx.cu:139-166 produce for a miss, bit for
-      // bit (colour 0*0 + bg*(1-0) = bg, depth min(1e30, tmax), ids ~0u), without Philox or camera work.  Launches
-      // that need the ray direction (normal channel) never set missValid.
-      const float4 bg = P.background;
-      for (int it = 0; it < P.numIterations; ++it)
-        accumResults(actx, px, py, bg, 1e30f, f3(bg.x, bg.y, bg.z), f3(0.f, 0.f, 0.f), 0u, ~0u, ~0u, it,
-            initFrame && it == 0);
+      // No ray of this pixel can enter a volume.  Launches that need the ray direction (normal channel) never set
+      // missValid.
+      shadeMissedPixel(actx, px, py, P.background, P.bgTex, centered, P.invW, P.invH, P.numIterations, initFrame);
       continue;
     }
     Philox rng;
@@ -315,14 +337,15 @@ __global__ void __launch_bounds__(kBlockThreads, (KIND >= FIELD_NANOVDB ? DVR_OC
         // alpha 1; depth / ids are never set by the reference's loop (its `depth == 0` test runs after the
         // increment), so depth stays tmax and the ids ~0u; albedo channel = background, normal = primary dir
         float3 c;
+        const float4 bgd = backgroundAt(P.bgTex, P.background, sx, sy);
         if (SINGLE)
           c = dptTracePath<true, KIND>(P.inl, 1, TfSelectSingle{s_tf}, org, dir, P.maxDepth, P.occlusionDistance,
-              P.ambientIntensity, P.background, rng, path);
+              P.ambientIntensity, bgd, rng, path);
         else
           c = dptTracePath<false, -1>(inst, nInst, TfSelectShared{s_tf, inst}, org, dir, P.maxDepth,
-              P.occlusionDistance, P.ambientIntensity, P.background, rng, path);
-        accumResults(actx, px, py, make_float4(c.x, c.y, c.z, 1.f), FLT_MAX,
-            f3(P.background.x, P.background.y, P.background.z), dir, ~0u, ~0u, ~0u, it, initFrame && it == 0);
+              P.occlusionDistance, P.ambientIntensity, bgd, rng, path);
+        accumResults(actx, px, py, make_float4(c.x, c.y, c.z, 1.f), FLT_MAX, f3(bgd.x, bgd.y, bgd.z), dir, ~0u, ~0u,
+            ~0u, it, initFrame && it == 0);
         continue;
       }
 
@@ -344,7 +367,7 @@ __global__ void __launch_bounds__(kBlockThreads, (KIND >= FIELD_NANOVDB ? DVR_OC
       // Raycast_ptx.cu:139-166 (no-surface branch)
       const float depth = fminf(1e30f, volumeDepth);
       color = color * opacity;
-      const float4 bg = P.background;
+      const float4 bg = backgroundAt(P.bgTex, P.background, sx, sy);
       const float oneMinus = __fsub_rn(1.f, opacity);
       color.x = __fmaf_rn(bg.x, oneMinus, color.x);
       color.y = __fmaf_rn(bg.y, oneMinus, color.y);
@@ -376,15 +399,14 @@ __global__ void __launch_bounds__(kBlockThreads, (KIND >= FIELD_NANOVDB ? DVR_OC
 __global__ void __launch_bounds__(256) dvrBackgroundSweepKernel(const __grid_constant__ FrameLaunch P)
 {
   const bool initFrame = P.frameID == 0 && P.checkerboardID <= 0;
+  const bool centered = P.integrator == DVR_INTEGRATOR_RAYCAST;
   const AccumCtx actx{P.width, P.height, P.format, P.frameID, P.checkerboardID, P.fb};
-  const float4 bg = P.background;
   const size_t n = (size_t)P.width * P.height;
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
     const uint32_t y = (uint32_t)(i / P.width), x = (uint32_t)(i - (size_t)y * P.width);
     if ((int)y >= P.missY0 && (int)y < P.missY1 && (int)x >= P.missX0 && (int)x < P.missX1)
       continue; // the tiles own the inside
-    for (int it = 0; it < P.numIterations; ++it)
-      accumResults(actx, x, y, bg, 1e30f, f3(bg.x, bg.y, bg.z), f3(0.f, 0.f, 0.f), 0u, ~0u, ~0u, it, initFrame && it == 0);
+    shadeMissedPixel(actx, x, y, P.background, P.bgTex, centered, P.invW, P.invH, P.numIterations, initFrame);
   }
 }
 
@@ -621,6 +643,40 @@ int launchCompositeOver(float4 *front, float *frontDepth, const float4 *back, co
 // ----------------------------------------------------------------------------------------------
 // K3: resolve a composited partial image (quirk Q2 + background + accumulate/tonemap/encode)
 // ----------------------------------------------------------------------------------------------
+// background of the (single) pixel-sample of pixel i of a resolve launch: the constant colour, or the image at the
+// screen coordinate makePrimaryRay gave that sample (first four draws of the pixel's Philox stream)
+__device__ __forceinline__ float4 resolveBackground(const ResolveLaunch &R, uint32_t px, uint32_t py)
+{
+  if (!R.bgTex)
+    return R.background;
+  float sx = (float)px, sy = (float)py;
+  if (!R.centered) {
+    Philox rng;
+    rng.init((unsigned long long)(int)(py * R.width + px), (unsigned long long)R.frameID * 512ull);
+    const float4 r = rng.uniform4();
+    sx = __fadd_rn(sx, r.x);
+    sy = __fadd_rn(sy, r.y);
+  }
+  return tex2D<float4>(R.bgTex, __fmul_rn(sx, R.invW), __fmul_rn(sy, R.invH));
+}
+
+__device__ __forceinline__ void resolvePixel(const ResolveLaunch &R, size_t i, float4 pc, float pd, float4 bg)
+{
+  float3 color = f3(pc.x, pc.y, pc.z);
+  float opacity = pc.w;
+  color = color * opacity; // Raycast_ptx.cu:159
+  const float oneMinus = __fsub_rn(1.f, opacity);
+  color.x = __fmaf_rn(bg.x, oneMinus, color.x);
+  color.y = __fmaf_rn(bg.y, oneMinus, color.y);
+  color.z = __fmaf_rn(bg.z, oneMinus, color.z);
+  opacity = __fmaf_rn(bg.w, oneMinus, opacity);
+  const AccumCtx P{R.width, R.height, R.format, R.frameID, -1, R.fb};
+  const bool hit = pd < 1e30f;
+  const uint32_t px = (uint32_t)(i % R.width), py = (uint32_t)(i / R.width);
+  accumResults(P, px, py, make_float4(color.x, color.y, color.z, opacity), pd, color, f3(0.f, 0.f, 0.f), 0u,
+      hit ? R.objId : ~0u, hit ? R.instId : ~0u, 0, R.frameID == 0);
+}
+
 __global__ void dvrResolveKernel(const __grid_constant__ ResolveLaunch R)
 {
   const size_t i = R.pixelBegin + blockIdx.x * (size_t)blockDim.x + threadIdx.x;
@@ -628,20 +684,7 @@ __global__ void dvrResolveKernel(const __grid_constant__ ResolveLaunch R)
     return;
   const float4 pc = R.partialRgba[i];
   const float pd = R.partialDepth ? R.partialDepth[i] : 1e30f;
-  float3 color = f3(pc.x, pc.y, pc.z);
-  float opacity = pc.w;
-  color = color * opacity;
-  const float oneMinus = 1.f - opacity;
-  color.x += R.background.x * oneMinus;
-  color.y += R.background.y * oneMinus;
-  color.z += R.background.z * oneMinus;
-  opacity += R.background.w * oneMinus;
-
-  const AccumCtx P{R.width, R.height, R.format, R.frameID, -1, R.fb};
-  const bool hit = pd < 1e30f;
-  const uint32_t px = (uint32_t)(i % R.width), py = (uint32_t)(i / R.width);
-  accumResults(P, px, py, make_float4(color.x, color.y, color.z, opacity), pd, color, f3(0.f, 0.f, 0.f), 0u,
-      hit ? R.objId : ~0u, hit ? R.instId : ~0u, 0, R.frameID == 0);
+  resolvePixel(R, i, pc, pd, resolveBackground(R, (uint32_t)(i % R.width), (uint32_t)(i / R.width)));
 }
 
 int launchResolve(const ResolveLaunch &r, cudaStream_t s)
@@ -659,23 +702,6 @@ int launchResolve(const ResolveLaunch &r, cudaStream_t s)
 // sort-last direct send: composite the slabs' partial images (peer loads over NVLink) in per-pixel
 // view order and resolve, in one kernel
 // ----------------------------------------------------------------------------------------------
-__device__ __forceinline__ void resolvePixel(const ResolveLaunch &R, size_t i, float4 pc, float pd)
-{
-  float3 color = f3(pc.x, pc.y, pc.z);
-  float opacity = pc.w;
-  color = color * opacity; // Raycast_ptx.cu:159
-  const float oneMinus = __fsub_rn(1.f, opacity);
-  color.x = __fmaf_rn(R.background.x, oneMinus, color.x);
-  color.y = __fmaf_rn(R.background.y, oneMinus, color.y);
-  color.z = __fmaf_rn(R.background.z, oneMinus, color.z);
-  opacity = __fmaf_rn(R.background.w, oneMinus, opacity);
-  const AccumCtx P{R.width, R.height, R.format, R.frameID, -1, R.fb};
-  const bool hit = pd < 1e30f;
-  const uint32_t px = (uint32_t)(i % R.width), py = (uint32_t)(i / R.width);
-  accumResults(P, px, py, make_float4(color.x, color.y, color.z, opacity), pd, color, f3(0.f, 0.f, 0.f), 0u,
-      hit ? R.objId : ~0u, hit ? R.instId : ~0u, 0, R.frameID == 0);
-}
-
 __global__ void __launch_bounds__(256) dvrPeerResolveKernel(const __grid_constant__ PeerResolveLaunch L)
 {
   const size_t i = L.r.pixelBegin + blockIdx.x * (size_t)blockDim.x + threadIdx.x;
@@ -683,9 +709,11 @@ __global__ void __launch_bounds__(256) dvrPeerResolveKernel(const __grid_constan
     const uint32_t px = (uint32_t)(i % L.r.width), py = (uint32_t)(i / L.r.width);
     bool hit = true;
     bool ascending = true;
+    float4 bg = L.r.background;
     if (L.cull && L.missValid
         && ((int)px < L.missX0 || (int)px >= L.missX1 || (int)py < L.missY0 || (int)py >= L.missY1)) {
       hit = false; // outside the screen rectangle of the bounds: no ray of this pixel can hit
+      bg = resolveBackground(L.r, px, py);
     } else {
       // the primary ray exactly as the partial march generated it (same Philox stream, same arithmetic)
       Philox rng;
@@ -696,6 +724,7 @@ __global__ void __launch_bounds__(256) dvrPeerResolveKernel(const __grid_constan
       const float sy = __fmul_rn(centered ? (float)py : __fadd_rn((float)py, r.y), L.invH);
       float3 org, dir;
       cameraCreateRay(L.cam, sx, sy, r.z, r.w, org, dir);
+      bg = backgroundAt(L.r.bgTex, L.r.background, sx, sy);
       float3 lo = org, ld = dir;
       if (!L.identity) {
         lo = xfmPoint(L.xfm, org);
@@ -733,7 +762,7 @@ __global__ void __launch_bounds__(256) dvrPeerResolveKernel(const __grid_constan
         }
       }
     }
-    resolvePixel(L.r, i, acc, depth);
+    resolvePixel(L.r, i, acc, depth, bg);
   }
 }
 

@@ -244,6 +244,7 @@ void Frame::renderFrame()
   p.numIterations = std::max(m_renderer->spp, 1);
   p.inverseVolumeSamplingRate = 1.f / m_renderer->volumeSamplingRate;
   std::memcpy(p.background, m_renderer->background, sizeof(p.background));
+  p.backgroundImage = m_renderer->backgroundImage();
   p.tileRank = m_renderer->tileRank;
   p.tileRanks = m_renderer->tileRanks;
   p.useMacrocellSkipping = m_renderer->macrocellSkipping;

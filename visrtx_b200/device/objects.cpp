@@ -860,9 +860,16 @@ void Renderer::commitParameters()
   background[0] = background[1] = background[2] = 0.f;
   background[3] = 1.f;
   getParamRaw("background", ANARI_FLOAT32_VEC4, background, 16);
-  if (getParamObject("background", ANARI_ARRAY2D))
-    report(ANARI_SEVERITY_WARNING, ANARI_STATUS_INVALID_ARGUMENT,
-        "image backgrounds are outside the DVR path of this device; using the constant colour");
+  { // "background" as an Array2D (Renderer.cpp:154): sampled per pixel-sample; the texture is (re)built in finalize
+    Array *img = static_cast<Array *>(getParamObject("background", ANARI_ARRAY2D));
+    if (m_bgArray.ptr != img) {
+      if (m_bgArray)
+        m_bgArray->removeObserver(this);
+      m_bgArray.reset(img);
+      if (img)
+        img->addObserver(this);
+    }
+  }
   spp = getParam<int>("pixelSamples", ANARI_INT32, 1);
   checkerboard = getParam<int32_t>("checkerboarding", ANARI_BOOL, 0) != 0;
   sampleLimit = getParam<int>("sampleLimit", ANARI_INT32, 128);
@@ -893,6 +900,71 @@ void Renderer::commitParameters()
   occlusionDistance = getParam<float>("ambientOcclusionDistance", ANARI_FLOAT32, 1e20f);
   if (!m_known)
     report(ANARI_SEVERITY_WARNING, ANARI_STATUS_INVALID_ARGUMENT, "unknown renderer subtype '%s'", subtype.c_str());
+}
+
+Renderer::~Renderer()
+{
+  if (m_bgArray)
+    m_bgArray->removeObserver(this);
+  dropBackgroundImage();
+}
+
+void Renderer::dropBackgroundImage()
+{
+  if (!m_bgImage)
+    return;
+  CudaDeviceScope scope(device);
+  cudaStreamSynchronize((cudaStream_t)device->stream());
+  dvr_image_destroy(m_bgImage);
+  m_bgImage = nullptr;
+}
+
+// Renderer::finalize, renderer/Renderer.cpp:172-179: Array2D::acquireCUDAArrayUint8 + a clamp / linear texture.
+// Element types: what numANARIChannels / isFloat / isFixed8|16|32 / isSrgb8 accept (utility/AnariTypeHelpers.h).
+void Renderer::finalize()
+{
+  dropBackgroundImage();
+  if (!m_bgArray)
+    return;
+  const ANARIDataType t = m_bgArray->elementType;
+  int comp = -1, channels = 0;
+  if (t >= ANARI_FLOAT32 && t <= ANARI_FLOAT32_VEC4) {
+    comp = DVR_IMAGE_FLOAT32;
+    channels = t - ANARI_FLOAT32 + 1;
+  } else if (t >= ANARI_UFIXED8 && t <= ANARI_UFIXED8_VEC4) {
+    comp = DVR_IMAGE_UFIXED8;
+    channels = t - ANARI_UFIXED8 + 1;
+  } else if (t >= ANARI_UFIXED16 && t <= ANARI_UFIXED16_VEC4) {
+    comp = DVR_IMAGE_UFIXED16;
+    channels = t - ANARI_UFIXED16 + 1;
+  } else if (t >= ANARI_UFIXED32 && t <= ANARI_UFIXED32_VEC4) {
+    comp = DVR_IMAGE_UFIXED32;
+    channels = t - ANARI_UFIXED32 + 1;
+  } else if (t >= ANARI_UFIXED8_R_SRGB && t <= ANARI_UFIXED8_RGBA_SRGB) {
+    comp = DVR_IMAGE_SRGB8;
+    channels = t - ANARI_UFIXED8_R_SRGB + 1;
+  }
+  if (comp < 0 || m_bgArray->dims[0] == 0 || m_bgArray->dims[1] == 0) {
+    report(ANARI_SEVERITY_WARNING, ANARI_STATUS_INVALID_ARGUMENT,
+        "unusable background image element type (%d); using the constant colour", (int)t);
+    return;
+  }
+  if (!device->initDevice())
+    return;
+  CudaDeviceScope scope(device);
+  const void *pixels = m_bgArray->data();
+  std::vector<uint8_t> staged;
+  if (m_bgArray->onDevice()) { // the staging pass reads host memory (Array::data() of the reference is a host view)
+    staged.resize(m_bgArray->totalBytes());
+    cudaMemcpy(staged.data(), pixels, staged.size(), cudaMemcpyDeviceToHost);
+    pixels = staged.data();
+  }
+  if (dvr_image_create(pixels, comp, channels, (uint32_t)m_bgArray->dims[0], (uint32_t)m_bgArray->dims[1],
+          device->stream(), &m_bgImage)
+      != DVR_OK) {
+    m_bgImage = nullptr;
+    report(ANARI_SEVERITY_ERROR, ANARI_STATUS_UNKNOWN_ERROR, "background image upload failed: %s", dvr_last_error());
+  }
 }
 
 } // namespace b200

@@ -287,10 +287,13 @@ struct World : Object
 struct Renderer : Object
 {
   Renderer(Device *d, const std::string &subtype);
+  ~Renderer() override;
   void commitParameters() override;
+  void finalize() override; // background image -> RGBA8 texture (Renderer.cpp:172-179)
   bool isValid() const override { return m_known; }
   int commitPriority() const override { return 1; }
   float background[4] = {0, 0, 0, 1};
+  const DvrImage *backgroundImage() const { return m_bgImage; }
   int spp = 1;
   int sampleLimit = 128;
   bool checkerboard = false;
@@ -305,7 +308,10 @@ struct Renderer : Object
   uint32_t tileRank = 0, tileRanks = 1;
 
  private:
+  void dropBackgroundImage();
   bool m_known = true;
+  Ref<Array> m_bgArray; // "background" given as an Array2D
+  DvrImage *m_bgImage = nullptr;
 };
 
 // ---- frame ---------------------------------------------------------------------------------------------------------
