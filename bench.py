@@ -57,11 +57,18 @@ def parse_args():
     ap.add_argument("--skip", type=int, default=-1,
                     help="macrocell skipping: 1/0; default -1 = off for the dense C2/C4 fields, on for C3")
     ap.add_argument("--mode", default="auto", choices=["auto", "sort-first", "sort-last"])
+    ap.add_argument("--fused", type=int, default=1,
+                    help="sort-last, N > 1: 1 = one fused launch per GPU and frame (march + exchange + composite), "
+                         "0 = the round-1 sequence (march, wait, peer composite, signal) for A/B")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-rows", type=int, default=0, help="rows of the CPU-baseline band (0 = auto)")
     ap.add_argument("--extra", type=int, default=1, help="also measure the secondary variants (N=1 only)")
     ap.add_argument("--nvdb-codec", default="float", choices=["float", "fp4", "fp8", "fp16", "fpn"],
                     help="c5 only: NanoVDB grid type of the fog sphere (quantised by visrtx_b200.nvdb_writer)")
+    ap.add_argument("--c4-scaling", type=int, default=-1,
+                    help="N = 8 runs: also measure BASELINE config C4 (4096^3 f32, 256 GiB, sort-last) on 2, 4 and 8 of the "
+                         "ranks (extra.c4_scaling); -1 = on for the default C2 run at N = 8, 0 = off")
+    ap.add_argument("--save-frame", default="", help="rank 0: write frame 0 of the timed scene (uint32 sRGB8) to this .npy")
     ap.add_argument("--extra-configs", default="c3,c5",
                     help="N=1 default run only: other BASELINE configs measured after the headline (extra.configs), "
                          "each with its own roofline and parity block; empty string = none")
@@ -497,7 +504,7 @@ def run_ours(args, torch, dist, rank, world):
     FMT, INTEG, BG = capi.DVR_FORMAT_UFIXED8_RGBA_SRGB, capi.DVR_INTEGRATOR_DEFAULT, (0.1, 0.1, 0.1, 1.0)
     if mode == "sort-last":
         driver = multigpu.SortLast(capi, torch, dist, rank, world, device, W, H, inst, 0, 0, FMT, INTEG, args.rate, BG,
-                                   skip=bool(args.skip), host_mirror=world > 1)
+                                   skip=bool(args.skip), host_mirror=world > 1, fused=bool(args.fused))
     else:
         driver = multigpu.SortFirst(capi, torch, dist, rank, world, device, W, H, inst, ninst, FMT, INTEG, args.rate,
                                     BG, skip=bool(args.skip), tile_band=int(os.environ.get("DVR_TILE_BAND", "1")),
@@ -685,7 +692,34 @@ def run_ours(args, torch, dist, rank, world):
                   "rays_hit": int(rays_hit), "bytes_per_sample": bframe / max(samples, 1), "setup_s": setup_s,
                   "share_per_rank": share},
     }
+    if mode == "sort-last" and world > 1 and args.fused:
+        # phases of the fused launch on every rank (%globaltimer stamps of 20 extra, untimed frames)
+        nt = 20
+        tbuf = torch.zeros((nt, 8), dtype=torch.int64, device=device)
+        tbuf[:, 0] = torch.iinfo(torch.int64).max
+        for i in range(nt):
+            driver.timing_ptr = tbuf[i].data_ptr()
+            driver.render(200 + i, cam, stream)
+        driver.timing_ptr = 0
+        torch.cuda.synchronize()
+        dist.barrier()
+        t = tbuf.double()
+        ph = torch.stack([(t[:, 1] - t[:, 0]), (t[:, 2] - t[:, 1]), (t[:, 3] - t[:, 2]), (t[:, 4] - t[:, 3]),
+                          (t[:, 4] - t[:, 0]), (t[:, 6] - t[:, 0]), (t[:, 5] - t[:, 0])], dim=1).median(dim=0).values / 1e3  # us
+        allph = [torch.zeros_like(ph) for _ in range(world)]
+        dist.all_gather(allph, ph)
+        out["extra"]["fused_phases_us_per_rank"] = {
+            "columns": ["march (first CTA -> last tile)", "background strip", "owned regions composited (incl. waiting "
+                        "for the slowest rank's flags)", "retire (display rank: all ranks' flags)", "kernel total", "own last region flag published (since start)",
+                        "last owned region seen complete on all ranks (since start)"],
+            "ranks": [[round(float(v), 1) for v in a.tolist()] for a in allph]}
     if mode == "sort-last" and world > 1:
+        # the slowest rank's march alone (dvr_render_partial, no exchange) against the whole step: what is left is
+        # exchange + compositing + imbalance that the fused launch could not hide
+        out["extra"]["march_us"] = kernel_ms * 1e3
+        out["extra"]["exchange_us"] = (ms_per_step - kernel_ms) * 1e3
+        out["extra"]["sort_last_launch"] = ("fused: dvr_render_slab_frame, one launch per GPU and frame" if args.fused else
+                                            "legacy: partial march + wait + peer composite + signal")
         out["extra"]["slabs"] = ("z-slabs of equal work for the initial camera (sample density ~ 1/r^2 from the eye), not "
                                  "of equal thickness (multigpu.view_balanced_slab_ranges)")
     if clocks is not None:
@@ -743,12 +777,31 @@ def run_ours(args, torch, dist, rank, world):
                 out["extra"]["configs"][name] = measure_secondary_config(args, name, torch, device, stream)
             except Exception as e:
                 out["extra"]["configs"][name] = f"unavailable: {type(e).__name__}: {e}"
+    if rank == 0 and args.save_frame:
+        driver.stream_to_host(False)
+    if args.save_frame:
+        driver.render(0, cam, stream)
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        if rank == 0:
+            np.save(args.save_frame, driver.color_tensor().cpu().numpy().view(np.uint32))
     if world > 1:
         out["parity_vs_single"] = parity_vs_single(args, torch, dist, capi, driver, cam, rank, world, device, stream, mode)
     if driver is not None and getattr(driver, "host_frame", None) is not None:
         host_view = None  # drop the numpy view before the shared segment is unmapped
         driver.host_frame.close(dist if world > 1 else None)
         driver.host_frame = None
+    do_c4 = args.c4_scaling == 1 or (args.c4_scaling < 0 and world == 8 and args.config == "c2" and mode == "sort-last")
+    if do_c4 and world >= 2:
+        # free the headline scene on every rank first: a C4 slab is up to 137 GB per GPU
+        driver.close()
+        volume.destroy()
+        field.destroy()
+        torch.cuda.empty_cache()
+        c4 = measure_c4_scaling(args, torch, dist, capi, rank, world, device, stream)
+        if rank == 0:
+            out["extra"]["c4_scaling"] = c4
     return out
 
 
@@ -788,6 +841,85 @@ def parity_vs_single(args, torch, dist, capi, driver, cam, rank, world, device, 
             v.destroy()
             field.destroy()
     dist.barrier()
+    return res
+
+
+def measure_c4_scaling(base_args, torch, dist, capi, rank, world, device, stream):
+    """BASELINE config C4 — 4096^3 f32 (256 GiB), bricked sort-last — on 2, 4 and 8 of this job's ranks, each time
+    from scratch: slabs of equal work generated in HBM in chunks, one fused launch per GPU and frame.  Frame 0 of
+    every sub-run is kept on rank 0 and compared with the previous one: the volume fits no single GPU, so the images
+    of different partitions are checked against each other (each is the same global sample lattice)."""
+    import argparse
+    from visrtx_b200 import multigpu
+    a = argparse.Namespace(**vars(base_args))
+    a.config, a.skip, a.field, a.rate = "c4", -1, "ml", 0.5
+    a = apply_preset(a)
+    n, W, H = a.size, a.width, a.height
+    npx = W * H
+    res = {"workload": workload_name(a), "unit": "frames/s", "runs": {}}
+    prev_frame, prev_n = None, None
+    groups = {sub: dist.new_group(list(range(sub))) for sub in (2, 4, 8) if sub <= world}
+    for sub, group in groups.items():
+        dist.barrier()
+        entry = None
+        if rank < sub:
+            t0 = time.perf_counter()
+            lo, hi = scene_bounds(a)
+            cam, pose0 = orbit(a)
+            z0, z1 = multigpu.view_balanced_slab_ranges(n, sub, lo, hi, pose0.position)[rank]
+            r0, r1 = multigpu.resident_range(z0, z1, n)
+            field = capi.Field.create_slab(0, True, scene_dtype(a), (n, n, n), z0, z1, (0, 0, 0), (1, 1, 1),
+                                           capi.DVR_FILTER_LINEAR, stream)
+            for zc in range(r0, r1, 32):
+                ze = min(zc + 32, r1)
+                part = make_scene(a, torch, device, z_begin=zc, z_end=ze)
+                field.upload_slices(part.data_ptr(), True, zc - r0, ze - zc, stream)
+                torch.cuda.synchronize()
+                del part
+            field.build_macrocells(stream)
+            tf = capi.tf_discretize(color=scene_colormap(a))
+            volume = capi.Volume.create(field, tf, (0.0, 1.0), a.unit_distance, 0, stream)
+            inst, _ = capi.make_instances([volume], None, [0])
+            torch.cuda.synchronize()
+            setup_s = time.perf_counter() - t0
+            drv = multigpu.SortLast(capi, torch, dist, rank, sub, device, W, H, inst, 0, 0, capi.DVR_FORMAT_UFIXED8_RGBA_SRGB,
+                                    capi.DVR_INTEGRATOR_DEFAULT, a.rate, (0.1, 0.1, 0.1, 1.0), skip=False, group=group)
+            drv.render(0, cam, stream)
+            torch.cuda.synchronize()
+            dist.barrier(group=group)
+            frame0 = drv.color_tensor() if rank == 0 else None
+            K = 30
+            for i in range(5):
+                drv.render(1 + i, cam, stream)
+            torch.cuda.synchronize()
+            dist.barrier(group=group)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for i in range(K):
+                drv.render(6 + i, cam, stream)
+            e1.record()
+            torch.cuda.synchronize()
+            t = torch.tensor([e0.elapsed_time(e1) / K, setup_s], dtype=torch.float64, device=device)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX, group=group)
+            err = drv.check_errors()
+            if rank == 0:
+                entry = {"value": 1000.0 / float(t[0].item()), "ms_per_step": float(t[0].item()), "steps": K,
+                         "setup_s": float(t[1].item()), "slab_gib_per_gpu": (r1 - r0) * n * n * 4 / 2 ** 30,
+                         "spin_timeouts": bool(err)}
+                if prev_frame is not None:
+                    entry[f"parity_vs_n{prev_n}"] = parity_block(
+                        torch, 4, frame0, prev_frame, what=f"frame 0 on {sub} GPUs vs frame 0 on {prev_n} GPUs (the volume "
+                        "fits no single GPU: partitions are checked against each other)")
+                prev_frame, prev_n = frame0, sub
+            drv.close()
+            volume.destroy()
+            field.destroy()
+            torch.cuda.empty_cache()
+        dist.barrier()
+        if rank == 0:
+            res["runs"][f"n{sub}"] = entry
+    if rank == 0 and "n2" in res["runs"] and "n8" in res["runs"]:
+        res["speedup_8_over_2"] = res["runs"]["n8"]["value"] / res["runs"]["n2"]["value"]
     return res
 
 

@@ -137,6 +137,11 @@ typedef struct DvrFrameBuffers
    * reaches the host through posted PCIe writes overlapped with the march instead of a copy after it — what
    * Frame::map("channel.color") needs (frame/Frame.cu:312-330 maps the colour buffer to the host). NULL = off. */
   void *outColorMirror;
+  /* Optional second destination of the depth channel (write-only, same layout as depth): every depth value the launch
+   * stores is also stored here.  Sort-last: each GPU keeps the depth of the pixels it resolves in its own `depth`
+   * (read back by the accumulate step of later frames) and mirrors it into the display GPU's frame through a peer
+   * pointer, so no GPU ever LOADS depth over NVLink.  NULL = off. */
+  float *depthMirror;
 } DvrFrameBuffers;
 
 /* Empty-space skipping never changes a pixel (skipped lattice points classify to alpha == 0 exactly), so the
@@ -407,6 +412,47 @@ int dvr_composite_resolve_peers_sync(const DvrFrameParams *params, const DvrCame
     size_t pixelEnd, const DvrPeerSync *sync, void *stream);
 /* one-thread kernel: returns (in stream order) once flags[i] >= value for all i < n (bounded spin) */
 int dvr_wait_flags(const unsigned int *flags, uint32_t n, uint32_t value, unsigned int *errorFlag, void *stream);
+
+/* The whole sort-last frame of one GPU in ONE launch: march of the own slab, exchange and compositing fused.
+ * Tiles of the volume's screen window are marched in the same order on every GPU and grouped into regions; a GPU that
+ * completes a region publishes a flag to the region's owner (region mod nRanks), and warps that run out of march tiles
+ * composite the regions their GPU owns as soon as all nRanks flags of a region are there — peer loads of the partial
+ * pixels over NVLink, `over` in per-pixel view order, Q2 + background + accumulate + tonemap + encode, stores into
+ * `buffers` (outColor / depth / ids may be peer pointers into the display GPU's frame; colorAccumulation is local:
+ * every pixel is always resolved by the same GPU while the camera stands still).  The pixels outside the window are
+ * shared out in contiguous strips.  The exchange overlaps the march region by region instead of following it
+ * (replaces dvr_render_partial_sync + dvr_composite_resolve_peers_sync + their wait / signal launches).
+ *
+ * All tables live in (CUDA-IPC or peer-mapped) device memory and are zero before the first frame:
+ *   regionFlags[p]   rank p's table uint32[maxRegions][16]: entry [r][q] = last frame in which rank q finished region r
+ *   resolvedFlags[p] rank p's table uint32[16]: entry [q] = last frame rank q finished compositing
+ *   regionDone       LOCAL scratch uint32[maxRegions] (tile counters)
+ * partialRgba[q] / partialDepth[q]: rank q's partial image of THIS frame (float4[W*H] / float[W*H], ascending z order of
+ * the slabs; entry [rank] is the one this launch writes).  Alternate two sets of partial images between frames.
+ * seq: frame number, strictly increasing from 1, identical on all ranks.  waitAllResolved != 0 (display GPU): the
+ * launch completes only when every rank's pixels of this frame have landed. */
+typedef struct DvrSlabExchange
+{
+  uint32_t nRanks, rank;
+  uint32_t seq;
+  uint32_t maxRegions;
+  const float *const *partialRgba;
+  const float *const *partialDepth;
+  unsigned int *const *regionFlags;
+  unsigned int *const *resolvedFlags;
+  unsigned int *regionDone;
+  unsigned int *errorFlag; /* set to 1 when a bounded spin (~2 s) gave up; may be NULL */
+  int32_t waitAllResolved;
+  int32_t _pad;
+  /* optional (bench bookkeeping): device uint64[8], %globaltimer nanoseconds of THIS GPU — [0] first CTA started
+   * (caller presets ~0), [1] last march tile finished, [2] last background chunk finished, [3] last owned region
+   * composited, [4] retire (display GPU: after every rank's flag arrived), [5] last owned region seen complete, [6] last
+   * region flag published; [1..7] preset 0.  NULL = off. */
+  unsigned long long *timing;
+} DvrSlabExchange;
+
+int dvr_render_slab_frame(const DvrFrameParams *params, const DvrCamera *camera, const DvrVolumeInstance *instance,
+    uint32_t objId, uint32_t instId, const DvrFrameBuffers *buffers, const DvrSlabExchange *exchange, void *stream);
 
 /* ---- CUDA IPC plumbing for one-process-per-GPU sharing of frame / partial buffers ------------- */
 #define DVR_IPC_HANDLE_BYTES 64

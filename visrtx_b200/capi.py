@@ -13,7 +13,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("DVR_B200_LIB") or os.path.join(_HERE, "libdvr_b200.so")
 
 from .pods import *  # noqa: F401,F403  (enums, POD structs, frame_params / frame_buffers / peer_sync)
-from .pods import DvrCamera, DvrVolumeInstance, DvrFrameBuffers, DvrFrameParams, DvrRenderStats, DvrPeerSync
+from .pods import DvrCamera, DvrVolumeInstance, DvrFrameBuffers, DvrFrameParams, DvrRenderStats, DvrPeerSync, DvrSlabExchange
 
 # every symbol include/dvr_b200.h declares (tests check the library exports all of them)
 EXPORTED_SYMBOLS = [
@@ -30,6 +30,7 @@ EXPORTED_SYMBOLS = [
     "dvr_render", "dvr_render_instrumented", "dvr_launch_count",
     "dvr_render_partial", "dvr_render_partial_instrumented", "dvr_composite_over", "dvr_resolve", "dvr_scale_vec3",
     "dvr_composite_resolve_peers", "dvr_render_partial_sync", "dvr_composite_resolve_peers_sync", "dvr_wait_flags",
+    "dvr_render_slab_frame",
     "dvr_ipc_alloc", "dvr_ipc_open", "dvr_ipc_close", "dvr_ipc_free",
 ]
 
@@ -380,6 +381,12 @@ def composite_resolve_peers_sync(params, camera, instance, partial_rgba_ptrs, pa
     _check(lib.dvr_composite_resolve_peers_sync(C.byref(params), C.byref(camera), instance, rg, dp, C.c_uint32(n),
                                                 C.c_uint32(obj_id), C.c_uint32(inst_id), C.byref(buffers),
                                                 C.c_size_t(begin), C.c_size_t(end), C.byref(sync), C.c_void_p(stream)))
+
+
+def render_slab_frame(params, camera, instance, obj_id: int, inst_id: int, buffers, exchange: DvrSlabExchange,
+                      stream: int = 0):
+    _check(lib.dvr_render_slab_frame(C.byref(params), C.byref(camera), instance, C.c_uint32(obj_id), C.c_uint32(inst_id),
+                                     C.byref(buffers), C.byref(exchange), C.c_void_p(stream)))
 
 
 def wait_flags(flags_ptr: int, n: int, value: int, error_flag: int = 0, stream: int = 0):

@@ -1434,6 +1434,7 @@ static int renderImpl(const DvrFrameParams *p, const DvrCamera *camera, const Dv
   L.fb.outF32 = (float4 *)b->outColor;
   L.fb.outMirror = b->outColorMirror;
   L.fb.depth = b->depth;
+  L.fb.depthMirror = b->depth ? b->depthMirror : nullptr;
   L.fb.primId = b->primId;
   L.fb.objId = b->objId;
   L.fb.instId = b->instId;
@@ -1610,6 +1611,42 @@ static int fillSync(const DvrPeerSync *in, SyncDev &out)
   return DVR_OK;
 }
 
+// kernel parameters of the slab march (shared by dvr_render_partial* and the fused dvr_render_slab_frame)
+static void fillPartialLaunch(const DvrFrameParams *p, const DvrCamera *camera, const DvrVolumeInstance *instance,
+    float *partialRgba, float *partialDepth, bool cullToBounds, PartialLaunch &L)
+{
+  std::memset(&L, 0, sizeof(L));
+  L.width = p->width;
+  L.height = p->height;
+  L.invW = 1.f / (float)p->width;
+  L.invH = 1.f / (float)p->height;
+  L.integrator = p->integrator;
+  L.frameID = p->frameID;
+  L.invSamplingRate = p->inverseVolumeSamplingRate;
+  L.tilesX = (p->width + kTileW - 1) / kTileW;
+  L.tilesY = (p->height + kTileH - 1) / kTileH;
+  L.tileX0 = L.tileY0 = 0;
+  L.tilesW = L.tilesX;
+  L.tilesH = L.tilesY;
+  int rect[4];
+  if (cullToBounds && screenRectOfBounds(camera, instance, p->width, p->height, rect)) {
+    if (rect[2] <= rect[0] || rect[3] <= rect[1]) { // the volume is off screen: nothing to march
+      L.tilesW = L.tilesH = 0;
+    } else {
+      L.tileX0 = (uint32_t)rect[0] / kTileW;
+      L.tileY0 = (uint32_t)rect[1] / kTileH;
+      L.tilesW = ((uint32_t)rect[2] + kTileW - 1) / kTileW - L.tileX0;
+      L.tilesH = ((uint32_t)rect[3] + kTileH - 1) / kTileH - L.tileY0;
+    }
+  }
+  fillCamera(camera, L.cam);
+  fillInstance(*instance, L.inst);
+  L.partialRgba = (float4 *)partialRgba;
+  L.partialDepth = partialDepth;
+  L.skip = p->useMacrocellSkipping == DVR_SKIP_ON
+      || (p->useMacrocellSkipping == DVR_SKIP_AUTO && instance->volume->emptyFraction >= kSkipAutoThreshold);
+}
+
 static int renderPartialImpl(const DvrFrameParams *p, const DvrCamera *camera, const DvrVolumeInstance *instance,
     float *partialRgba, float *partialDepth, DvrRenderStats *statsDev, void *stream, const DvrPeerSync *sync = nullptr)
 {
@@ -1643,36 +1680,7 @@ static int renderPartialImpl(const DvrFrameParams *p, const DvrCamera *camera, c
   }
   cudaStream_t s = (cudaStream_t)stream;
   PartialLaunch L;
-  std::memset(&L, 0, sizeof(L));
-  L.width = p->width;
-  L.height = p->height;
-  L.invW = 1.f / (float)p->width;
-  L.invH = 1.f / (float)p->height;
-  L.integrator = p->integrator;
-  L.frameID = p->frameID;
-  L.invSamplingRate = p->inverseVolumeSamplingRate;
-  L.tilesX = (p->width + kTileW - 1) / kTileW;
-  L.tilesY = (p->height + kTileH - 1) / kTileH;
-  L.tileX0 = L.tileY0 = 0;
-  L.tilesW = L.tilesX;
-  L.tilesH = L.tilesY;
-  int rect[4];
-  if (p->partialCullToBounds && screenRectOfBounds(camera, instance, p->width, p->height, rect)) {
-    if (rect[2] <= rect[0] || rect[3] <= rect[1]) { // the volume is off screen: nothing to march
-      L.tilesW = L.tilesH = 0;
-    } else {
-      L.tileX0 = (uint32_t)rect[0] / kTileW;
-      L.tileY0 = (uint32_t)rect[1] / kTileH;
-      L.tilesW = ((uint32_t)rect[2] + kTileW - 1) / kTileW - L.tileX0;
-      L.tilesH = ((uint32_t)rect[3] + kTileH - 1) / kTileH - L.tileY0;
-    }
-  }
-  fillCamera(camera, L.cam);
-  fillInstance(*instance, L.inst);
-  L.partialRgba = (float4 *)partialRgba;
-  L.partialDepth = partialDepth;
-  L.skip = p->useMacrocellSkipping == DVR_SKIP_ON
-      || (p->useMacrocellSkipping == DVR_SKIP_AUTO && instance->volume->emptyFraction >= kSkipAutoThreshold);
+  fillPartialLaunch(p, camera, instance, partialRgba, partialDepth, p->partialCullToBounds != 0, L);
   {
     const int rcs = fillSync(sync, L.sync);
     if (rcs != DVR_OK)
@@ -1767,6 +1775,7 @@ int dvr_resolve(const DvrFrameParams *p, const float *partialRgba, const float *
   R.fb.outF32 = (float4 *)b->outColor;
   R.fb.outMirror = b->outColorMirror;
   R.fb.depth = b->depth;
+  R.fb.depthMirror = b->depth ? b->depthMirror : nullptr;
   R.fb.primId = b->primId;
   R.fb.objId = b->objId;
   R.fb.instId = b->instId;
@@ -1781,20 +1790,10 @@ int dvr_resolve(const DvrFrameParams *p, const float *partialRgba, const float *
   return launchResolve(R, (cudaStream_t)stream);
 }
 
-static int compositeResolveImpl(const DvrFrameParams *p, const DvrCamera *camera, const DvrVolumeInstance *instance,
+static int fillPeerResolveLaunch(const DvrFrameParams *p, const DvrCamera *camera, const DvrVolumeInstance *instance,
     const float *const *partialRgba, const float *const *partialDepth, uint32_t nSlabs, uint32_t objId,
-    uint32_t instId, const DvrFrameBuffers *b, size_t pixelBegin, size_t pixelEnd, const DvrPeerSync *sync,
-    void *stream)
+    uint32_t instId, const DvrFrameBuffers *b, size_t pixelBegin, size_t pixelEnd, PeerResolveLaunch &L)
 {
-  if (!p || !camera || !partialRgba || !b || !b->colorAccumulation || !b->outColor || nSlabs == 0) {
-    setError("dvr_composite_resolve_peers: null argument");
-    return DVR_ERR_INVALID_ARGUMENT;
-  }
-  if (nSlabs > (uint32_t)kMaxSlabs) {
-    setError("dvr_composite_resolve_peers: at most 16 slabs");
-    return DVR_ERR_UNSUPPORTED;
-  }
-  PeerResolveLaunch L;
   std::memset(&L, 0, sizeof(L));
   ResolveLaunch &R = L.r;
   R.width = p->width;
@@ -1811,6 +1810,7 @@ static int compositeResolveImpl(const DvrFrameParams *p, const DvrCamera *camera
   R.fb.outF32 = (float4 *)b->outColor;
   R.fb.outMirror = b->outColorMirror;
   R.fb.depth = b->depth;
+  R.fb.depthMirror = b->depth ? b->depthMirror : nullptr;
   R.fb.primId = b->primId;
   R.fb.objId = b->objId;
   R.fb.instId = b->instId;
@@ -1851,6 +1851,29 @@ static int compositeResolveImpl(const DvrFrameParams *p, const DvrCamera *camera
       L.missY1 = rect[3];
     }
   }
+  return DVR_OK;
+}
+
+static int compositeResolveImpl(const DvrFrameParams *p, const DvrCamera *camera, const DvrVolumeInstance *instance,
+    const float *const *partialRgba, const float *const *partialDepth, uint32_t nSlabs, uint32_t objId,
+    uint32_t instId, const DvrFrameBuffers *b, size_t pixelBegin, size_t pixelEnd, const DvrPeerSync *sync,
+    void *stream)
+{
+  if (!p || !camera || !partialRgba || !b || !b->colorAccumulation || !b->outColor || nSlabs == 0) {
+    setError("dvr_composite_resolve_peers: null argument");
+    return DVR_ERR_INVALID_ARGUMENT;
+  }
+  if (nSlabs > (uint32_t)kMaxSlabs) {
+    setError("dvr_composite_resolve_peers: at most 16 slabs");
+    return DVR_ERR_UNSUPPORTED;
+  }
+  PeerResolveLaunch L;
+  {
+    const int rcf = fillPeerResolveLaunch(p, camera, instance, partialRgba, partialDepth, nSlabs, objId, instId, b,
+        pixelBegin, pixelEnd, L);
+    if (rcf != DVR_OK)
+      return rcf;
+  }
   const int rcs = fillSync(sync, L.sync);
   if (rcs != DVR_OK)
     return rcs;
@@ -1872,6 +1895,87 @@ int dvr_composite_resolve_peers_sync(const DvrFrameParams *p, const DvrCamera *c
 {
   return compositeResolveImpl(p, camera, instance, partialRgba, partialDepth, nSlabs, objId, instId, b, pixelBegin,
       pixelEnd, sync, stream);
+}
+
+int dvr_render_slab_frame(const DvrFrameParams *p, const DvrCamera *camera, const DvrVolumeInstance *instance,
+    uint32_t objId, uint32_t instId, const DvrFrameBuffers *b, const DvrSlabExchange *x, void *stream)
+{
+  if (!p || !camera || !instance || !instance->volume || !instance->volume->field || !b || !b->colorAccumulation
+      || !b->outColor || !x || !x->partialRgba || !x->partialDepth || !x->regionFlags || !x->resolvedFlags
+      || !x->regionDone) {
+    setError("dvr_render_slab_frame: null argument");
+    return DVR_ERR_INVALID_ARGUMENT;
+  }
+  if (x->nRanks == 0 || x->nRanks > (uint32_t)kMaxSlabs || x->rank >= x->nRanks || x->seq == 0 || x->maxRegions == 0) {
+    setError("dvr_render_slab_frame: 1..16 ranks, rank < nRanks, seq > 0, maxRegions > 0");
+    return DVR_ERR_INVALID_ARGUMENT;
+  }
+  if (p->width == 0 || p->height == 0) {
+    setError("dvr_render_slab_frame: empty frame");
+    return DVR_ERR_INVALID_ARGUMENT;
+  }
+  if (p->numIterations != 1 || p->checkerboardID >= 0
+      || (p->integrator != DVR_INTEGRATOR_RAYCAST && p->integrator != DVR_INTEGRATOR_DEFAULT)
+      || instance->volume->field->dev.kind != FIELD_STRUCTURED) {
+    setError("dvr_render_slab_frame: marching integrators, 1 sample per pixel, no checkerboarding, structuredRegular slab");
+    return DVR_ERR_UNSUPPORTED;
+  }
+  if (dvr_device_count() <= 0) {
+    setError("dvr_render_slab_frame: no CUDA device (this library has no CPU fallback)");
+    return DVR_ERR_NO_DEVICE;
+  }
+  for (uint32_t i = 0; i < x->nRanks; ++i)
+    if (!x->partialRgba[i] || !x->partialDepth[i] || !x->regionFlags[i] || !x->resolvedFlags[i]) {
+      setError("dvr_render_slab_frame: null per-rank pointer");
+      return DVR_ERR_INVALID_ARGUMENT;
+    }
+  SlabFrameLaunch S;
+  std::memset(&S, 0, sizeof(S));
+  fillPartialLaunch(p, camera, instance, const_cast<float *>(x->partialRgba[x->rank]),
+      const_cast<float *>(x->partialDepth[x->rank]), true, S.m);
+  const size_t npx = (size_t)p->width * p->height;
+  {
+    const int rcf = fillPeerResolveLaunch(p, camera, instance, x->partialRgba, x->partialDepth, x->nRanks, objId, instId,
+        b, 0, npx, S.c);
+    if (rcf != DVR_OK)
+      return rcf;
+  }
+  S.c.sync.errorFlag = x->errorFlag;
+  S.nRanks = x->nRanks;
+  S.rank = x->rank;
+  S.seq = x->seq;
+  const uint32_t nTiles = S.m.tilesW * S.m.tilesH;
+  S.tilesPerRegion = std::max<uint32_t>(32u, (nTiles + x->maxRegions - 1) / x->maxRegions);
+  S.nRegions = (nTiles + S.tilesPerRegion - 1) / S.tilesPerRegion;
+  S.regionDone = x->regionDone;
+  for (uint32_t i = 0; i < x->nRanks; ++i) {
+    S.regionFlags[i] = x->regionFlags[i];
+    S.resolvedFlags[i] = x->resolvedFlags[i];
+  }
+  S.myRegionFlags = x->regionFlags[x->rank];
+  S.myResolved = x->resolvedFlags[x->rank];
+  S.waitAllResolved = x->waitAllResolved;
+  S.timing = x->timing;
+  {
+    static const unsigned spinNs = []() {
+      const char *e = std::getenv("DVR_B200_SPIN_NS");
+      const int v = e ? std::atoi(e) : 0;
+      return v > 0 ? (unsigned)v : 100u;
+    }();
+    S.spinSleepNs = spinNs;
+  }
+  { // this rank's share of the pixels outside the window: contiguous strips, 256-pixel aligned
+    size_t per = (npx + x->nRanks - 1) / x->nRanks;
+    per = (per + 255) / 256 * 256;
+    S.bgPixelBegin = std::min(npx, per * x->rank);
+    S.bgPixelEnd = std::min(npx, S.bgPixelBegin + per);
+  }
+  S.m.sched = acquireSchedSlot();
+  if (!S.m.sched) {
+    setError("dvr_render_slab_frame: could not allocate scheduler scratch");
+    return DVR_ERR_CUDA;
+  }
+  return launchSlabFrame(S, (cudaStream_t)stream);
 }
 
 int dvr_ipc_alloc(size_t bytes, void **devPtr, unsigned char handle[DVR_IPC_HANDLE_BYTES])

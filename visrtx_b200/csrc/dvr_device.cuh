@@ -88,6 +88,7 @@ struct BuffersDev
   float4 *outF32;
   void *outMirror; // optional second destination of the encoded colour (pinned host memory), same layout
   float *depth;
+  float *depthMirror; // optional write-only second destination of the depth channel (peer pointer, sort-last)
   uint32_t *primId, *objId, *instId;
   float *albedo, *normal; // packed vec3
 };

@@ -114,6 +114,26 @@ struct PeerResolveLaunch
   uint32_t identity;
 };
 
+// Sort-last frame in ONE launch per GPU: march of the own slab, per-region completion flags to the regions' owners,
+// compositing + resolve of the owned regions over peer memory, background pixels of the own strip.
+struct SlabFrameLaunch
+{
+  PartialLaunch m;        // march part (own slab -> own partial image)
+  PeerResolveLaunch c;    // composite part: all ranks' partial images of this frame, resolve parameters, camera
+  uint32_t nRanks, rank;
+  uint32_t seq;           // frame number carried by every flag of this launch
+  uint32_t tilesPerRegion, nRegions;
+  unsigned int *regionDone;                 // local per-region tile counters, zero on entry, re-armed by the last warp
+  unsigned int *regionFlags[kMaxSlabs];     // rank p's region table [maxRegions][kMaxSlabs]; we store [region][rank]
+  const unsigned int *myRegionFlags;        // the local table: [region][src] >= seq once src finished the region
+  unsigned int *resolvedFlags[kMaxSlabs];   // rank p's "rank q resolved frame seq" table [kMaxSlabs]; we store [rank]
+  const unsigned int *myResolved;
+  int waitAllResolved;                      // display rank: do not retire before every rank's strip has landed
+  size_t bgPixelBegin, bgPixelEnd;          // this rank's share of the pixels outside the tile window
+  unsigned long long *timing;               // optional %globaltimer stamps (DvrSlabExchange::timing)
+  unsigned spinSleepNs;                     // back-off of the warps that wait for region flags
+};
+
 // error plumbing -----------------------------------------------------------------------------
 void setError(const std::string &msg);
 int cudaFail(cudaError_t e, const char *what);
@@ -138,6 +158,7 @@ int launchResolve(const ResolveLaunch &p, cudaStream_t s);
 int launchCompositeOver(float4 *front, float *frontDepth, const float4 *back, const float *backDepth,
     size_t begin, size_t end, bool backIsInFront, cudaStream_t s);
 int launchPeerResolve(const PeerResolveLaunch &p, cudaStream_t s);
+int launchSlabFrame(const SlabFrameLaunch &p, cudaStream_t s);
 int launchSignalFlags(const SyncDev &sy, cudaStream_t s);
 int launchWaitFlags(const unsigned int *flags, uint32_t n, uint32_t value, unsigned int *errorFlag, cudaStream_t s);
 int launchScaleVec3(const float *in, float *out, size_t n, float scale, cudaStream_t s);

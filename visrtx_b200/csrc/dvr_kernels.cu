@@ -168,6 +168,8 @@ __device__ __forceinline__ void accumResults(const AccumCtx &P, uint32_t px, uin
       fb.depth[idx] = depth;
     else if (init)
       fb.depth[idx] = prev;
+    if (fb.depthMirror && (closer || init))
+      fb.depthMirror[idx] = closer ? depth : prev;
   }
   if (closer) {
     if (fb.primId) fb.primId[idx] = primID;
@@ -194,6 +196,7 @@ __device__ __forceinline__ void accumResults(const AccumCtx &P, uint32_t px, uin
       if (init) {
         fb.accum[aidx] = make_float4(0.f, 0.f, 0.f, 0.f);
         if (fb.depth) fb.depth[aidx] = FLT_MAX;
+        if (fb.depth && fb.depthMirror) fb.depthMirror[aidx] = FLT_MAX;
         if (fb.primId) fb.primId[aidx] = 0u;
         if (fb.objId) fb.objId[aidx] = 0u;
         if (fb.instId) fb.instId[aidx] = 0u;
@@ -752,7 +755,7 @@ __global__ void __launch_bounds__(256) dvrPeerResolveKernel(const __grid_constan
       }
 #pragma unroll
       for (int k = 0; k < kMaxSlabs; ++k) {
-        if (k < L.nSlabs) {
+        if (k < L.nSlabs && acc.w < 0.99f) { // the one-pass march takes no sample once opacity >= 0.99
           const float w = __fsub_rn(1.f, acc.w);
           acc.x = __fmaf_rn(w, part[k].x, acc.x);
           acc.y = __fmaf_rn(w, part[k].y, acc.y);
@@ -784,6 +787,286 @@ int launchPeerResolve(const PeerResolveLaunch &p, cudaStream_t s)
   }
   if (p.sync.nSignal)
     return launchSignalFlags(p.sync, s);
+  return DVR_OK;
+}
+
+// ----------------------------------------------------------------------------------------------
+// Sort-last frame, fused: march + exchange + composite + resolve in one launch per GPU.
+//
+//   phase 1  every warp pulls 8x4 tiles of the screen window in the SAME order on every GPU and marches its slab into
+//            its partial image.  Tiles are grouped into regions of `tilesPerRegion` consecutive tiles; the warp that
+//            completes a region's last tile publishes "region r of frame seq done on rank me" into the table of the
+//            region's owner (r mod N) with a system-scope release.
+//   phase 2  once the tile queue is empty, warps pull (a) chunks of this rank's share of the pixels outside the window
+//            (background only, no peer data) and (b) the tiles of the regions this rank owns, in region order: wait
+//            until all N ranks flagged the region, load the N partial pixels over NVLink (volatile peer loads), `over`
+//            them in per-pixel view order, resolve (Q2, background, accumulate, tonemap, encode) and store into the
+//            display GPU's frame.  Regions complete in order over the frame time, so at the end of the march only
+//            the last regions' composites remain: the exchange hides behind the tail of the long rays.
+//   retire   the last warp re-arms the counters and publishes "rank me resolved frame seq" to every rank (partial
+//            buffers alternate: nobody overwrites a buffer before its readers of two frames ago have finished); the
+//            display rank does not retire before it holds every rank's flag.
+// Replaces dvrPartialKernel + dvrWaitFlagsKernel + dvrPeerResolveKernel + dvrSignalFlagsKernel (3 serialized
+// launches after the march: 42 us of a 180 us step on 8 GPUs).
+// ----------------------------------------------------------------------------------------------
+__device__ __forceinline__ unsigned long long globalTimerNs()
+{
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+
+// Flag protocol of the fused frame.  Everything a consumer reads after a flag is either homed in the producer's own
+// memory (partial pixels: stored, fenced, THEN flagged — a load issued after the flag was seen finds them in the
+// producer's L2) or fetched with strong system-scope loads that bypass L1, so consumers need no fence of their own:
+// acquire-flavoured operations compile to CCTL.IVALL, which would wipe the L1 / texture cache under the warps that are
+// still marching on the same SM, and a fence.sc.sys per composite item costs microseconds once peer stores are in
+// flight (measured: 24 us of composite tail at N = 2 with it, profiles/r02_sort_last_fused.md).
+__device__ __forceinline__ bool spinUntil(const unsigned int *flag, uint32_t value, unsigned int *err,
+    unsigned sleepNs = 100u)
+{
+  const long long t0 = clock64();
+  while ((int)(*((volatile const unsigned int *)flag) - value) < 0) {
+    __nanosleep(sleepNs);
+    if (clock64() - t0 > 4000000000ll) { // ~2 s: a missing producer must not hang the GPU
+      if (err)
+        *err = 1u;
+      return false;
+    }
+  }
+  return true;
+}
+
+// composite + resolve of pixel (px, py) from the N partial images, exactly dvrPeerResolveKernel's arithmetic
+__device__ __forceinline__ void compositePixel(const PeerResolveLaunch &L, uint32_t px, uint32_t py, bool insideWindow)
+{
+  const size_t i = (size_t)py * L.r.width + px;
+  bool hit = insideWindow;
+  bool ascending = true;
+  float4 bg = L.r.background;
+  if (!insideWindow) {
+    bg = resolveBackground(L.r, px, py);
+  } else {
+    Philox rng;
+    rng.init((unsigned long long)(int)(py * L.r.width + px), (unsigned long long)L.r.frameID * 512ull);
+    const float4 r = rng.uniform4();
+    const bool centered = L.integrator == DVR_INTEGRATOR_RAYCAST;
+    const float sx = __fmul_rn(centered ? (float)px : __fadd_rn((float)px, r.x), L.invW);
+    const float sy = __fmul_rn(centered ? (float)py : __fadd_rn((float)py, r.y), L.invH);
+    float3 org, dir;
+    cameraCreateRay(L.cam, sx, sy, r.z, r.w, org, dir);
+    bg = backgroundAt(L.r.bgTex, L.r.background, sx, sy);
+    float3 lo = org, ld = dir;
+    if (!L.identity) {
+      lo = xfmPoint(L.xfm, org);
+      ld = xfmVector(L.xfm, dir);
+    }
+    float t0, t1;
+    hit = intersectVolumeBox(L.boundsLo, L.boundsHi, lo, ld, 0.f, FLT_MAX, t0, t1);
+    ascending = ld.z >= 0.f;
+  }
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  float depth = 1e30f;
+  if (hit) {
+    // two half-batches of peer loads in flight (register budget shared with the march)
+#pragma unroll
+    for (int h = 0; h < kMaxSlabs; h += 8) {
+      if (h < L.nSlabs) {
+        float4 part[8];
+        float pdep[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k)
+          if (h + k < L.nSlabs) {
+            const int sidx = ascending ? h + k : L.nSlabs - 1 - (h + k);
+            part[k] = __ldcv(&L.rgba[sidx][i]);
+            pdep[k] = __ldcv(&L.depth[sidx][i]);
+          }
+#pragma unroll
+        for (int k = 0; k < 8; ++k)
+          if (h + k < L.nSlabs && acc.w < 0.99f) { // the one-pass march takes no sample once opacity >= 0.99
+            const float w = __fsub_rn(1.f, acc.w);
+            acc.x = __fmaf_rn(w, part[k].x, acc.x);
+            acc.y = __fmaf_rn(w, part[k].y, acc.y);
+            acc.z = __fmaf_rn(w, part[k].z, acc.z);
+            acc.w = __fmaf_rn(w, part[k].w, acc.w);
+            depth = fminf(depth, pdep[k]);
+          }
+      }
+    }
+  }
+  resolvePixel(L.r, i, acc, depth, bg);
+}
+
+template <bool SKIP>
+__global__ void __launch_bounds__(kBlockThreads, 2) dvrSlabFrameKernel(const __grid_constant__ SlabFrameLaunch S)
+{
+  const PartialLaunch &P = S.m;
+  __shared__ float4 s_tf[DVR_TF_SIZE];
+  const int lane = threadIdx.x & 31;
+  for (int i = threadIdx.x; i < DVR_TF_SIZE; i += blockDim.x)
+    s_tf[i] = __ldg(&P.inst.v.tf[i]);
+  // The partial buffer of this frame was read by the composites of frame seq-2 on every rank: wait for their
+  // "resolved" flags (normally long satisfied — our own frame seq-1 already waited for their marches of seq-1).
+  if (threadIdx.x == 0 && S.timing)
+    atomicMin(&S.timing[0], globalTimerNs());
+  if (threadIdx.x == 0 && S.seq > 2u)
+    for (uint32_t p = 0; p < S.nRanks; ++p)
+      if (!spinUntil(&S.myResolved[p], S.seq - 2u, S.c.sync.errorFlag))
+        break;
+  __syncthreads();
+
+  // ---- phase 1: march
+  MarchStats st{0ull, 0ull};
+  const uint32_t nTiles = P.tilesW * P.tilesH;
+  const bool centered = P.integrator == DVR_INTEGRATOR_RAYCAST;
+  for (uint32_t tile = nextTile(P.sched, lane); tile < nTiles; tile = nextTile(P.sched, lane)) {
+    const uint32_t tyIdx = P.tileY0 + tile / P.tilesW, txIdx = P.tileX0 + tile % P.tilesW;
+    const uint32_t px = txIdx * kTileW + (lane % kTileW), py = tyIdx * kTileH + (lane / kTileW);
+    if (px < P.width && py < P.height) {
+      Philox rng;
+      rng.init((unsigned long long)(int)(py * P.width + px), (unsigned long long)P.frameID * 512ull);
+      const float4 r = rng.uniform4();
+      const float sx = __fmul_rn(centered ? (float)px : __fadd_rn((float)px, r.x), P.invW);
+      const float sy = __fmul_rn(centered ? (float)py : __fadd_rn((float)py, r.y), P.invH);
+      float3 org, dir;
+      cameraCreateRay(P.cam, sx, sy, r.z, r.w, org, dir);
+      float3 color = f3(0.f, 0.f, 0.f);
+      float opacity = 0.f;
+      uint32_t objID = ~0u, instID = ~0u;
+      bool anyHit = false;
+      const float depth = rayMarchAllVolumes<SKIP, true, false, true, FIELD_STRUCTURED>(&P.inst, 1, TfSelectSingle{s_tf},
+          org, dir, FLT_MAX, P.invSamplingRate, rng, color, opacity, objID, instID, st, nullptr, anyHit);
+      const uint32_t idx = px + py * P.width;
+      P.partialRgba[idx] = make_float4(color.x, color.y, color.z, opacity);
+      P.partialDepth[idx] = fminf(1e30f, depth);
+    }
+    __syncwarp();
+    if (lane == 0) {
+      const uint32_t region = tile / S.tilesPerRegion;
+      const uint32_t inRegion = min(S.tilesPerRegion, nTiles - region * S.tilesPerRegion);
+      // the tile's stores before the count, at device scope.  A RELEASE-only atomic: __threadfence() compiles to
+      // MEMBAR.SC.GPU + CCTL.IVALL, and invalidating the SM's L1 after every tile costs the warps that are still
+      // marching their texture-cache hits (march phase 492 us vs 470 us for the plain partial kernel at N = 2)
+      unsigned int counted;
+      asm volatile("atom.release.gpu.global.add.u32 %0, [%1], %2;"
+                   : "=r"(counted) : "l"(&S.regionDone[region]), "r"(1u) : "memory");
+      if (counted == inRegion - 1u) {
+        __threadfence_system(); // every tile of the region is in L2; release system-wide before the flag
+        *((volatile unsigned int *)&S.regionFlags[region % S.nRanks][(size_t)region * kMaxSlabs + S.rank]) = S.seq;
+        if (S.timing)
+          atomicMax(&S.timing[6], globalTimerNs());
+      }
+    }
+  }
+
+  if (S.timing && lane == 0)
+    atomicMax(&S.timing[1], globalTimerNs());
+
+  // ---- phase 2a: background pixels of this rank's strip outside the window (no peer data, no waiting)
+  {
+    const size_t nBg = S.bgPixelEnd > S.bgPixelBegin ? S.bgPixelEnd - S.bgPixelBegin : 0;
+    const uint32_t nChunks = (uint32_t)((nBg + 255) / 256);
+    const int wx0 = (int)(P.tileX0 * kTileW), wy0 = (int)(P.tileY0 * kTileH);
+    const int wx1 = (int)((P.tileX0 + P.tilesW) * kTileW), wy1 = (int)((P.tileY0 + P.tilesH) * kTileH);
+    for (;;) {
+      uint32_t chunk = 0;
+      if (lane == 0)
+        chunk = atomicAdd(&P.sched[2], 1u);
+      chunk = __shfl_sync(0xffffffffu, chunk, 0);
+      if (chunk >= nChunks)
+        break;
+#pragma unroll 1
+      for (int k = 0; k < 8; ++k) {
+        const size_t i = S.bgPixelBegin + (size_t)chunk * 256 + (size_t)k * 32 + lane;
+        if (i >= S.bgPixelEnd)
+          break;
+        const uint32_t py = (uint32_t)(i / P.width), px = (uint32_t)(i - (size_t)py * P.width);
+        if ((int)px >= wx0 && (int)px < wx1 && (int)py >= wy0 && (int)py < wy1)
+          continue; // the regions own the window
+        compositePixel(S.c, px, py, false);
+      }
+    }
+  }
+
+  if (S.timing && lane == 0)
+    atomicMax(&S.timing[2], globalTimerNs());
+
+  // ---- phase 2b: the regions this rank owns, in order
+  {
+    const uint32_t nOwned = S.nRegions > S.rank ? (S.nRegions - S.rank + S.nRanks - 1u) / S.nRanks : 0u;
+    const uint32_t nItems = nOwned * S.tilesPerRegion;
+    for (;;) {
+      uint32_t item = 0;
+      if (lane == 0)
+        item = atomicAdd(&P.sched[3], 1u);
+      item = __shfl_sync(0xffffffffu, item, 0);
+      if (item >= nItems)
+        break;
+      const uint32_t region = (item / S.tilesPerRegion) * S.nRanks + S.rank;
+      const uint32_t tile = region * S.tilesPerRegion + item % S.tilesPerRegion;
+      if (tile >= nTiles)
+        continue;
+      if ((uint32_t)lane < S.nRanks)
+        spinUntil(&S.myRegionFlags[(size_t)region * kMaxSlabs + lane], S.seq, S.c.sync.errorFlag, S.spinSleepNs);
+      __syncwarp();
+      if (S.timing && lane == 0)
+        atomicMax(&S.timing[5], globalTimerNs());
+      const uint32_t tyIdx = P.tileY0 + tile / P.tilesW, txIdx = P.tileX0 + tile % P.tilesW;
+      const uint32_t px = txIdx * kTileW + (lane % kTileW), py = tyIdx * kTileH + (lane / kTileW);
+      if (px < P.width && py < P.height)
+        compositePixel(S.c, px, py, true);
+    }
+  }
+
+  // ---- retire
+  __syncwarp();
+  if (S.timing && lane == 0)
+    atomicMax(&S.timing[3], globalTimerNs());
+  if (lane == 0) {
+    const unsigned int totalWarps = gridDim.x * (blockDim.x >> 5);
+    __threadfence_system(); // this warp's composite stores (peer memory) are acknowledged before the count
+    const unsigned int done = atomicAdd(&P.sched[1], 1u);
+    if (done == totalWarps - 1u) {
+      for (uint32_t r = 0; r < S.nRegions; ++r)
+        S.regionDone[r] = 0u;
+      P.sched[0] = 0u;
+      P.sched[1] = 0u;
+      P.sched[2] = 0u;
+      P.sched[3] = 0u;
+      __threadfence_system();
+      for (uint32_t p = 0; p < S.nRanks; ++p)
+        *((volatile unsigned int *)&S.resolvedFlags[p][S.rank]) = S.seq;
+      if (S.waitAllResolved)
+        for (uint32_t p = 0; p < S.nRanks; ++p)
+          if (!spinUntil(&S.myResolved[p], S.seq, S.c.sync.errorFlag))
+            break;
+      if (S.timing)
+        S.timing[4] = globalTimerNs();
+    }
+  }
+}
+
+int launchSlabFrame(const SlabFrameLaunch &p, cudaStream_t s)
+{
+  static int bps[2] = {0, 0};
+  const int k = p.m.skip ? 1 : 0;
+  if (bps[k] == 0) {
+    if (k)
+      DVR_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps[k], dvrSlabFrameKernel<true>, kBlockThreads, 0));
+    else
+      DVR_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps[k], dvrSlabFrameKernel<false>, kBlockThreads, 0));
+    if (bps[k] < 1)
+      bps[k] = 1;
+  }
+  // every CTA must be resident: warps of phase 2 spin on flags that other GPUs' resident warps produce, never on
+  // work of this grid that has not been scheduled
+  const uint32_t grid = (uint32_t)(smCount() * bps[k]);
+  if (p.m.skip)
+    dvrSlabFrameKernel<true><<<grid, kBlockThreads, 0, s>>>(p);
+  else
+    dvrSlabFrameKernel<false><<<grid, kBlockThreads, 0, s>>>(p);
+  DVR_CUDA(cudaGetLastError());
+  countLaunch();
   return DVR_OK;
 }
 

@@ -254,6 +254,7 @@ void Frame::renderFrame()
   p.occlusionDistance = m_renderer->occlusionDistance;
 
   DvrFrameBuffers b;
+  std::memset(&b, 0, sizeof(b));
   b.colorAccumulation = (float *)m_accum;
   b.outColor = m_color;
   b.outColorMirror = nullptr;

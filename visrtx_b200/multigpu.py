@@ -97,10 +97,10 @@ def tile_rows_of(rank: int, world: int, height: int, tile_h: int = 4) -> List[in
     return [r for r in range(n_rows) if r % world == rank]
 
 
-def exchange_bytes(dist, payload: bytes, world: int) -> List[bytes]:
+def exchange_bytes(dist, payload: bytes, world: int, group=None) -> List[bytes]:
     """all-gather of one small bytes object per rank (CUDA-IPC handles); works on gloo and nccl."""
     out = [None] * world
-    dist.all_gather_object(out, payload)
+    dist.all_gather_object(out, payload, group=group)
     return out
 
 
@@ -111,15 +111,15 @@ class SharedHostFrame:
     pixels of the final image to the host during the launch — the multi-process version of the single-GPU host
     streaming; no device->host copy after the frame."""
 
-    def __init__(self, dist, rank: int, world: int, nbytes: int):
+    def __init__(self, dist, rank: int, world: int, nbytes: int, group=None):
         import ctypes
         from multiprocessing import shared_memory
-        self.rank, self.nbytes = rank, nbytes
+        self.rank, self.nbytes, self.group = rank, nbytes, group
         name = ""
         if rank == 0:
             self.shm = shared_memory.SharedMemory(create=True, size=nbytes)
             name = self.shm.name
-        names = exchange_bytes(dist, name.encode(), world) if world > 1 else [name.encode()]
+        names = exchange_bytes(dist, name.encode(), world, group) if world > 1 else [name.encode()]
         if rank != 0:
             self.shm = shared_memory.SharedMemory(name=names[0].decode())
             try:  # the creator unlinks the segment; attachments must not be tracked (Python < 3.13 has no track=False)
@@ -147,7 +147,7 @@ class SharedHostFrame:
         import ctypes
         self._cudart.cudaHostUnregister(ctypes.c_void_p(self.host_ptr))
         if dist is not None:
-            dist.barrier()
+            dist.barrier(group=self.group)
         try:
             self.shm.close()
         except BufferError:  # a numpy view is still alive; the segment goes away with the process
@@ -243,22 +243,27 @@ class SortFirst:
 
 
 class SortLast:
-    """Sort-last driver over z-slabs: partial march + fused peer composite/resolve.
+    """Sort-last driver over z-slabs: ONE fused launch per GPU and frame (dvr_render_slab_frame) — march of the own
+    slab, per-region completion flags to the regions' owners, compositing + resolve of the owned regions over peer
+    memory as soon as their inputs are complete, background strips.
 
-    Cross-GPU ordering is done ON THE DEVICE with flags in CUDA-IPC shared memory (DvrPeerSync): the
-    partial kernel's last warp publishes "partial f complete" into every rank's flag table, the composite
-    kernel spins on its local table before touching peer data and publishes "strip f resolved"; a
-    one-thread wait kernel keeps a rank from overwriting a partial buffer that a slower rank may still be
-    reading (two frames back, the buffers alternate) and lets the display rank wait for the full frame.
-    No host synchronisation and no NCCL call on the per-frame path.
+    Cross-GPU ordering is done ON THE DEVICE with flags in CUDA-IPC shared memory: region flags (rank q finished
+    region r of frame seq) and resolved flags (rank q finished compositing frame seq: partial buffers alternate, and
+    the display rank's launch completes only when every rank's pixels have landed).  No host synchronisation, no
+    NCCL call and no second launch on the per-frame path.  `fused=False` keeps the round-1 sequence (partial march,
+    wait, peer composite, signal: three launches after the march) for A/B measurements.
     """
 
-    FLAG_WORDS = 64  # [0:16] partial-complete per source rank, [16:32] strip-resolved per source rank, [32] error
+    MAX_REGIONS = 1024
+    # per-rank flag table (uint32): [MAX_REGIONS][16] region flags, [16] resolved flags, [16] error word + padding,
+    # then the round-1 layout ([0:16] partial-complete, [16:32] strip-resolved, [32] error) for fused=False
+    FLAG_WORDS = MAX_REGIONS * 16 + 32 + 64
 
     def __init__(self, capi, torch, dist, rank: int, world: int, device, width: int, height: int, instance,
                  obj_id: int, inst_id: int, fmt: int, integrator: int, rate: float, background, skip: bool = False,
-                 host_mirror: bool = False):
+                 host_mirror: bool = False, fused: bool = True, group=None):
         self.capi, self.torch, self.dist = capi, torch, dist
+        self.fused, self.group = fused, group
         self.rank, self.world, self.device = rank, world, device
         self.W, self.H, self.fmt = width, height, fmt
         self.integrator, self.rate, self.background, self.skip = integrator, rate, background, skip
@@ -291,10 +296,10 @@ class SortLast:
             ctypes.CDLL("libcudart.so").cudaMemset(ctypes.c_void_p(fp), 0, ctypes.c_size_t(self.FLAG_WORDS * 4))
             torch.cuda.synchronize()
             payload += fh
-            if rank == 0:
-                self._color_owned, hc = capi.ipc_alloc(npx * px_bytes)
+            if rank == 0:  # the display frame: colour, then depth (assembled on the display GPU like the colour)
+                self._color_owned, hc = capi.ipc_alloc(npx * px_bytes + npx * 4)
                 payload += hc
-            all_h = exchange_bytes(dist, payload, world)
+            all_h = exchange_bytes(dist, payload, world, group)
             self.rgba_ptrs, self.depth_ptrs, self.flag_ptrs = [[], []], [[], []], []
             for r in range(world):
                 for b in range(2):
@@ -316,14 +321,22 @@ class SortLast:
             else:
                 self.color_ptr = capi.ipc_open(all_h[0][192:256])
                 self._peer_open.append(self.color_ptr)
-            dist.barrier()  # every table is zeroed and mapped before the first signal can arrive
-        self.host_frame = SharedHostFrame(dist, rank, world, npx * px_bytes) if host_mirror else None
-        self._fb_plain = capi.frame_buffers(self.accum.data_ptr(), self.color_ptr, self.depth.data_ptr())
-        self._fb_mirror = capi.frame_buffers(self.accum.data_ptr(), self.color_ptr, self.depth.data_ptr(),
+            dist.barrier(group=group)  # every table is zeroed and mapped before the first signal can arrive
+            self.region_done = torch.zeros(self.MAX_REGIONS, dtype=torch.int32, device=device)
+        self.host_frame = SharedHostFrame(dist, rank, world, npx * px_bytes, group) if host_mirror else None
+        # world > 1: depth is assembled in the display rank's frame next to the colour.  The display rank resolves
+        # straight into it; the others keep the depth of their own pixels locally (the accumulate step reads it back)
+        # and mirror every store into the display frame through the peer pointer — write-only traffic over NVLink
+        self.display_depth_ptr = self.depth.data_ptr() if world == 1 else self.color_ptr + npx * px_bytes
+        depth_ptr = self.display_depth_ptr if rank == 0 else self.depth.data_ptr()
+        depth_mirror = 0 if rank == 0 else self.display_depth_ptr
+        self._fb_plain = capi.frame_buffers(self.accum.data_ptr(), self.color_ptr, depth_ptr, depth_mirror=depth_mirror)
+        self._fb_mirror = capi.frame_buffers(self.accum.data_ptr(), self.color_ptr, depth_ptr, depth_mirror=depth_mirror,
                                              color_mirror=self.host_frame.dev_ptr) if self.host_frame else None
         self.fb = self._fb_mirror or self._fb_plain
         self.frame_parity = 0
         self._hot = None
+        self.timing_ptr = 0  # fused launches stamp %globaltimer phases into this uint64[8] when set (bench bookkeeping)
 
     def params(self, frame_id: int):
         # the synchronised fused composite (world > 1) regenerates every primary ray and never reads a pixel whose ray
@@ -349,16 +362,19 @@ class SortLast:
                                          self.fb, lo, hi, stream)
             return
         me, W = self.rank, self.world
-        my_flags = self.flag_ptrs[me]
-        err = my_flags + 32 * 4
+        if self.fused:
+            return self._render_fused(frame_id, camera, stream, b, seq, wait_display)
+        leg = (self.MAX_REGIONS * 16 + 32) * 4  # the round-1 flag layout lives behind the fused tables
+        my_flags = self.flag_ptrs[me] + leg
+        err = self.flag_ptrs[me] + (self.MAX_REGIONS * 16 + 16) * 4
         if self._hot is None:  # per-frame host work is pointer/struct reuse only: everything below is built once
             import ctypes as C
             L = capi.lib
             self._hot = {
                 "p": self.params(0),
-                "sync_p": capi.peer_sync(signal_ptrs=[self.flag_ptrs[r] + me * 4 for r in range(W)], signal_value=0),
-                "sync_c": capi.peer_sync(signal_ptrs=[self.flag_ptrs[r] + (16 + me) * 4 for r in range(W)], signal_value=0,
-                                         wait_ptr=my_flags, n_wait=W, wait_value=0, error_flag=err),
+                "sync_p": capi.peer_sync(signal_ptrs=[self.flag_ptrs[r] + leg + me * 4 for r in range(W)], signal_value=0),
+                "sync_c": capi.peer_sync(signal_ptrs=[self.flag_ptrs[r] + leg + (16 + me) * 4 for r in range(W)],
+                                         signal_value=0, wait_ptr=my_flags, n_wait=W, wait_value=0, error_flag=err),
                 "rg": [(C.c_void_p * W)(*self.rgba_ptrs[k]) for k in range(2)],
                 "dp": [(C.c_void_p * W)(*self.depth_ptrs[k]) for k in range(2)],
                 "mine_rg": [C.c_void_p(self.rgba_ptrs[k][me]) for k in range(2)],
@@ -385,13 +401,46 @@ class SortLast:
         if rc != 0:
             raise RuntimeError(f"sort-last frame {seq}: {capi.last_error()}")
 
+    def _render_fused(self, frame_id, camera, stream, b, seq, wait_display):
+        """One dvr_render_slab_frame launch: march + exchange + composite + resolve + background strip."""
+        capi, me, W = self.capi, self.rank, self.world
+        if self._hot is None:
+            import ctypes as C
+            R = self.MAX_REGIONS
+            x = capi.DvrSlabExchange()
+            x.nRanks, x.rank, x.maxRegions = W, me, R
+            keep = {
+                "rg": [(C.c_void_p * W)(*self.rgba_ptrs[k]) for k in range(2)],
+                "dp": [(C.c_void_p * W)(*self.depth_ptrs[k]) for k in range(2)],
+                "rf": (C.c_void_p * W)(*[self.flag_ptrs[r] for r in range(W)]),
+                "sf": (C.c_void_p * W)(*[self.flag_ptrs[r] + R * 16 * 4 for r in range(W)]),
+            }
+            x.regionFlags = C.cast(keep["rf"], C.c_void_p)
+            x.resolvedFlags = C.cast(keep["sf"], C.c_void_p)
+            x.regionDone = self.region_done.data_ptr()
+            x.errorFlag = self.flag_ptrs[me] + (R * 16 + 16) * 4
+            self._hot = {"p": self.params(0), "x": x, "keep": keep, "C": C, "L": capi.lib,
+                         "obj": C.c_uint32(self.obj_id), "inst": C.c_uint32(self.inst_id)}
+        h = self._hot
+        C, L, p, x = h["C"], h["L"], h["p"], h["x"]
+        p.frameID = frame_id
+        x.seq = seq & 0xFFFFFFFF
+        x.partialRgba = C.cast(h["keep"]["rg"][b], C.c_void_p)
+        x.partialDepth = C.cast(h["keep"]["dp"][b], C.c_void_p)
+        x.waitAllResolved = 1 if (me == 0 and wait_display) else 0
+        x.timing = self.timing_ptr or None
+        rc = L.dvr_render_slab_frame(C.byref(p), C.byref(camera), self.instance, h["obj"], h["inst"], C.byref(self.fb),
+                                     C.byref(x), C.c_void_p(stream))
+        if rc != 0:
+            raise RuntimeError(f"sort-last frame {seq}: {capi.last_error()}")
+
     def check_errors(self):
         """True when a bounded spin gave up (a producer never signalled)."""
         if self.world == 1:
             return False
         import ctypes
         v = ctypes.c_uint32()
-        ctypes.CDLL("libcudart.so").cudaMemcpy(ctypes.byref(v), ctypes.c_void_p(self.flag_ptrs[self.rank] + 32 * 4),
+        ctypes.CDLL("libcudart.so").cudaMemcpy(ctypes.byref(v), ctypes.c_void_p(self.flag_ptrs[self.rank] + (self.MAX_REGIONS * 16 + 16) * 4),
                                                ctypes.c_size_t(4), ctypes.c_int(2))
         return v.value != 0
 
@@ -403,15 +452,23 @@ class SortLast:
                                                ctypes.c_size_t(n32 * 4), ctypes.c_int(3))
         return out
 
+    def depth_tensor(self):
+        """Display rank: the assembled depth channel (copy)."""
+        import ctypes
+        out = self.torch.empty(self.npx, dtype=self.torch.float32, device=self.device)
+        ctypes.CDLL("libcudart.so").cudaMemcpy(ctypes.c_void_p(out.data_ptr()), ctypes.c_void_p(self.display_depth_ptr),
+                                               ctypes.c_size_t(self.npx * 4), ctypes.c_int(3))
+        return out
+
     def close(self):
         self.torch.cuda.synchronize()
         if self.host_frame:
             self.host_frame.close(self.dist if self.world > 1 else None)
         if self.world > 1:
-            self.dist.barrier()
+            self.dist.barrier(group=self.group)
             for p in self._peer_open:
                 self.capi.ipc_close(p)
-            self.dist.barrier()
+            self.dist.barrier(group=self.group)
             for p in self._mine:
                 self.capi.ipc_free(p)
             if self._color_owned:

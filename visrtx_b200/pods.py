@@ -38,7 +38,7 @@ class DvrVolumeInstance(C.Structure):
 class DvrFrameBuffers(C.Structure):
     _fields_ = [("colorAccumulation", C.c_void_p), ("outColor", C.c_void_p), ("depth", C.c_void_p),
                 ("primId", C.c_void_p), ("objId", C.c_void_p), ("instId", C.c_void_p), ("albedo", C.c_void_p),
-                ("normal", C.c_void_p), ("outColorMirror", C.c_void_p)]
+                ("normal", C.c_void_p), ("outColorMirror", C.c_void_p), ("depthMirror", C.c_void_p)]
 
 
 class DvrFrameParams(C.Structure):
@@ -59,6 +59,13 @@ class DvrRenderStats(C.Structure):
 class DvrPeerSync(C.Structure):
     _fields_ = [("nSignal", C.c_uint32), ("signalValue", C.c_uint32), ("signal", C.c_void_p * 16),
                 ("nWait", C.c_uint32), ("waitValue", C.c_uint32), ("wait", C.c_void_p), ("errorFlag", C.c_void_p)]
+
+
+class DvrSlabExchange(C.Structure):
+    _fields_ = [("nRanks", C.c_uint32), ("rank", C.c_uint32), ("seq", C.c_uint32), ("maxRegions", C.c_uint32),
+                ("partialRgba", C.c_void_p), ("partialDepth", C.c_void_p), ("regionFlags", C.c_void_p),
+                ("resolvedFlags", C.c_void_p), ("regionDone", C.c_void_p), ("errorFlag", C.c_void_p),
+                ("waitAllResolved", C.c_int32), ("_pad", C.c_int32), ("timing", C.c_void_p)]
 
 
 def peer_sync(signal_ptrs=(), signal_value=0, wait_ptr=0, n_wait=0, wait_value=0, error_flag=0) -> "DvrPeerSync":
@@ -99,9 +106,10 @@ def frame_params(width, height, fmt=DVR_FORMAT_UFIXED8_RGBA_SRGB, integrator=DVR
 
 
 def frame_buffers(accum: int, out_color: int, depth: int = 0, prim: int = 0, obj: int = 0, inst: int = 0,
-                  albedo: int = 0, normal: int = 0, color_mirror: int = 0) -> DvrFrameBuffers:
+                  albedo: int = 0, normal: int = 0, color_mirror: int = 0, depth_mirror: int = 0) -> DvrFrameBuffers:
     b = DvrFrameBuffers()
     b.outColorMirror = color_mirror or None
+    b.depthMirror = depth_mirror or None
     b.colorAccumulation, b.outColor = accum or None, out_color or None
     b.depth, b.primId, b.objId, b.instId = depth or None, prim or None, obj or None, inst or None
     b.albedo, b.normal = albedo or None, normal or None
