@@ -582,10 +582,13 @@ def run_ours(args, torch, dist, rank, world):
     k1.record()
     torch.cuda.synchronize()
     kernel_ms = k0.elapsed_time(k1) / kn
+    kernel_ms_per_rank = [kernel_ms]
     if world > 1:
         t = torch.tensor([kernel_ms], dtype=torch.float64, device=device)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        kernel_ms = float(t.item())
+        allk = [torch.zeros_like(t) for _ in range(world)]
+        dist.all_gather(allk, t)
+        kernel_ms_per_rank = [float(v.item()) for v in allk]
+        kernel_ms = max(kernel_ms_per_rank)
 
     # ---- per-frame distribution (SURVEY 8d timing protocol): progressive accumulation vs single-shot (reset each
     # frame), one CUDA-event pair per frame, median and p95
@@ -717,6 +720,7 @@ def run_ours(args, torch, dist, rank, world):
         # the slowest rank's march alone (dvr_render_partial, no exchange) against the whole step: what is left is
         # exchange + compositing + imbalance that the fused launch could not hide
         out["extra"]["march_us"] = kernel_ms * 1e3
+        out["extra"]["march_alone_us_per_rank"] = [round(v * 1e3, 1) for v in kernel_ms_per_rank]
         out["extra"]["exchange_us"] = (ms_per_step - kernel_ms) * 1e3
         out["extra"]["sort_last_launch"] = ("fused: dvr_render_slab_frame, one launch per GPU and frame" if args.fused else
                                             "legacy: partial march + wait + peer composite + signal")

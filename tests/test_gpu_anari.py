@@ -18,8 +18,14 @@ pytestmark = pytest.mark.gpu
 
 class AnariScene:
     def __init__(self, n=48, w=96, h=96, renderer="raycast", rate=0.5, color_type=A.UFIXED8_RGBA_SRGB,
-                 channels=("depth", "objectId", "instanceId", "primitiveId"), vox=None, elem=A.FLOAT32, device_ptr=None):
+                 channels=("depth", "objectId", "instanceId", "primitiveId"), vox=None, elem=A.FLOAT32, device_ptr=None,
+                 gpus=None, multi_gpu_mode=None):
         self.d = d = A.Device()
+        if gpus is not None:  # multi-GPU device: "cudaDevices" (display GPU first) + "multiGpuMode"
+            d.set(d.handle, "cudaDevices", A.STRING, ",".join(str(g) for g in gpus))
+            if multi_gpu_mode:
+                d.set(d.handle, "multiGpuMode", A.STRING, multi_gpu_mode)
+            d.commit(d.handle)
         self.n, self.w, self.h = n, w, h
         sp = 2.0 / (n - 1)
         self.vox = scenes.marschner_lobb_np(n) if vox is None else vox

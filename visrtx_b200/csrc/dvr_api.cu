@@ -1963,6 +1963,11 @@ int dvr_render_slab_frame(const DvrFrameParams *p, const DvrCamera *camera, cons
       return v > 0 ? (unsigned)v : 100u;
     }();
     S.spinSleepNs = spinNs;
+    static const unsigned dbg = []() {
+      const char *e = std::getenv("DVR_B200_SLAB_DEBUG");
+      return e ? (unsigned)std::atoi(e) : 0u;
+    }();
+    S.debugFlags = dbg;
   }
   { // this rank's share of the pixels outside the window: contiguous strips, 256-pixel aligned
     size_t per = (npx + x->nRanks - 1) / x->nRanks;

@@ -135,13 +135,13 @@ __device__ __forceinline__ void accumResults(const AccumCtx &P, uint32_t px, uin
   if (init) {
     acc = tm;
   } else {
-    acc = fb.accum[idx];
+    acc = __ldcg(&fb.accum[idx]); // streamed once per frame: keep it out of L1, where the field's texels live
     acc.x = __fadd_rn(acc.x, tm.x);
     acc.y = __fadd_rn(acc.y, tm.y);
     acc.z = __fadd_rn(acc.z, tm.z);
     acc.w = __fadd_rn(acc.w, tm.w);
   }
-  fb.accum[idx] = acc;
+  __stcg(&fb.accum[idx], acc);
 
   if (fb.albedo) {
     float *a = fb.albedo + 3 * (size_t)idx;
@@ -162,7 +162,7 @@ __device__ __forceinline__ void accumResults(const AccumCtx &P, uint32_t px, uin
 
   bool closer = true;
   if (fb.depth) {
-    const float prev = init ? FLT_MAX : fb.depth[idx];
+    const float prev = init ? FLT_MAX : __ldcg(&fb.depth[idx]);
     closer = depth < prev;
     if (closer)
       fb.depth[idx] = depth;
@@ -897,6 +897,109 @@ __device__ __forceinline__ void compositePixel(const PeerResolveLaunch &L, uint3
   resolvePixel(L.r, i, acc, depth, bg);
 }
 
+// One chunk (256 pixels) of this rank's share of the pixels outside the window.  Constant background, frames after
+// the first: every such pixel has held the same accumulation value since the reset (same formula, no per-pixel
+// input), so the warp derives the new value ONCE from its first pixel — the same float operations accumResults would
+// do per pixel, bit for bit — and the chunk becomes a pure fill of accumulation + colour (depth / ids do not change:
+// 1e30 < 1e30 is false).  Frame 0 and image backgrounds take the per-pixel path.
+__device__ __forceinline__ void slabBackgroundChunk(const SlabFrameLaunch &S, uint32_t chunk, int lane)
+{
+  const PartialLaunch &P = S.m;
+  const ResolveLaunch &R = S.c.r;
+  const int wx0 = (int)(P.tileX0 * kTileW), wy0 = (int)(P.tileY0 * kTileH);
+  const int wx1 = (int)((P.tileX0 + P.tilesW) * kTileW), wy1 = (int)((P.tileY0 + P.tilesH) * kTileH);
+  const size_t base = S.bgPixelBegin + (size_t)chunk * 256;
+  const bool uniform = R.frameID > 0 && !R.bgTex && !R.fb.albedo && !R.fb.normal;
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f), outF = acc;
+  uint32_t outU = 0u;
+  bool have = false;
+#pragma unroll 1
+  for (int k = 0; k < 8; ++k) {
+    const size_t i = base + (size_t)k * 32 + lane;
+    const bool inRange = i < S.bgPixelEnd;
+    const uint32_t py = inRange ? (uint32_t)(i / P.width) : 0u, px = inRange ? (uint32_t)(i - (size_t)py * P.width) : 0u;
+    const bool mine = inRange && !((int)px >= wx0 && (int)px < wx1 && (int)py >= wy0 && (int)py < wy1);
+    if (!uniform) {
+      if (mine)
+        compositePixel(S.c, px, py, false);
+      continue;
+    }
+    const unsigned m = __ballot_sync(0xffffffffu, mine);
+    if (m == 0u)
+      continue;
+    if (!have) { // first pixel of the chunk that is ours: its accumulation value stands for all of them
+      const int src = __ffs(m) - 1;
+      float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (lane == src)
+        a = __ldcg(&R.fb.accum[i]);
+      a.x = __shfl_sync(0xffffffffu, a.x, src);
+      a.y = __shfl_sync(0xffffffffu, a.y, src);
+      a.z = __shfl_sync(0xffffffffu, a.z, src);
+      a.w = __shfl_sync(0xffffffffu, a.w, src);
+      // accumResults for colour = background (0 * 0 + bg * (1 - 0)): tonemap, add, average, inverse tonemap, encode
+      const float4 bg = R.background;
+      const float tmDen = __fadd_rn(1.0f, fmaxf(0.0f, fmaxf(fmaxf(bg.x, bg.y), bg.z)));
+      acc = make_float4(__fadd_rn(a.x, __fdiv_rn(bg.x, tmDen)), __fadd_rn(a.y, __fdiv_rn(bg.y, tmDen)),
+          __fadd_rn(a.z, __fdiv_rn(bg.z, tmDen)), __fadd_rn(a.w, bg.w));
+      const float div = float(R.frameID + 1);
+      float4 c = make_float4(__fdiv_rn(acc.x, div), __fdiv_rn(acc.y, div), __fdiv_rn(acc.z, div), __fdiv_rn(acc.w, div));
+      const float mm = fmaxf(1e-12f, __fsub_rn(1.0f, fmaxf(fmaxf(c.x, c.y), c.z)));
+      c.x = __fdiv_rn(c.x, mm);
+      c.y = __fdiv_rn(c.y, mm);
+      c.z = __fdiv_rn(c.z, mm);
+      outF = c;
+      outU = R.format == 2 ? packUnorm4x8(linearToSrgb(c.x), linearToSrgb(c.y), linearToSrgb(c.z), c.w)
+                           : packUnorm4x8(c.x, c.y, c.z, c.w);
+      have = true;
+    }
+    if (mine) {
+      __stcg(&R.fb.accum[i], acc);
+      if (R.format == 0) {
+        R.fb.outF32[i] = outF;
+        if (R.fb.outMirror)
+          __stcs(reinterpret_cast<float4 *>(R.fb.outMirror) + i, outF);
+      } else {
+        R.fb.outU32[i] = outU;
+        if (R.fb.outMirror)
+          __stcs(reinterpret_cast<uint32_t *>(R.fb.outMirror) + i, outU);
+      }
+    }
+  }
+}
+
+// Claims the next composite item (a tile of a region this rank owns) if — and only if — every rank has flagged its
+// region, and composites it.  Never blocks: 0 = nothing ready yet, 1 = one tile composited, 2 = all items done.
+template <bool DUMMY = false>
+__device__ __forceinline__ int slabTryComposite(const SlabFrameLaunch &S, uint32_t nItems, uint32_t nTiles, int lane)
+{
+  const PartialLaunch &P = S.m;
+  uint32_t item = 0;
+  if (lane == 0)
+    item = *((volatile unsigned int *)&P.sched[3]);
+  item = __shfl_sync(0xffffffffu, item, 0);
+  if (item >= nItems)
+    return 2;
+  const uint32_t region = (item / S.tilesPerRegion) * S.nRanks + S.rank;
+  bool ready = true;
+  if ((uint32_t)lane < S.nRanks)
+    ready = (int)(*((volatile const unsigned int *)&S.myRegionFlags[(size_t)region * kMaxSlabs + lane]) - S.seq) >= 0;
+  if (!__all_sync(0xffffffffu, ready))
+    return 0;
+  unsigned int got = 0;
+  if (lane == 0)
+    got = atomicCAS(&P.sched[3], item, item + 1u) == item ? 1u : 0u;
+  if (!__shfl_sync(0xffffffffu, got, 0))
+    return 0; // another warp took it; the caller comes back
+  const uint32_t tile = region * S.tilesPerRegion + item % S.tilesPerRegion;
+  if (tile < nTiles) {
+    const uint32_t tyIdx = P.tileY0 + tile / P.tilesW, txIdx = P.tileX0 + tile % P.tilesW;
+    const uint32_t px = txIdx * kTileW + (lane % kTileW), py = tyIdx * kTileH + (lane / kTileW);
+    if (px < P.width && py < P.height)
+      compositePixel(S.c, px, py, true);
+  }
+  return 1;
+}
+
 template <bool SKIP>
 __global__ void __launch_bounds__(kBlockThreads, 2) dvrSlabFrameKernel(const __grid_constant__ SlabFrameLaunch S)
 {
@@ -905,20 +1008,28 @@ __global__ void __launch_bounds__(kBlockThreads, 2) dvrSlabFrameKernel(const __g
   const int lane = threadIdx.x & 31;
   for (int i = threadIdx.x; i < DVR_TF_SIZE; i += blockDim.x)
     s_tf[i] = __ldg(&P.inst.v.tf[i]);
-  // The partial buffer of this frame was read by the composites of frame seq-2 on every rank: wait for their
-  // "resolved" flags (normally long satisfied — our own frame seq-1 already waited for their marches of seq-1).
   if (threadIdx.x == 0 && S.timing)
     atomicMin(&S.timing[0], globalTimerNs());
+  // The partial buffer of this frame was read by the composites of frame seq-2 on every rank: wait for their
+  // "resolved" flags (normally long satisfied — our own frame seq-1 already waited for their marches of seq-1).
   if (threadIdx.x == 0 && S.seq > 2u)
     for (uint32_t p = 0; p < S.nRanks; ++p)
       if (!spinUntil(&S.myResolved[p], S.seq - 2u, S.c.sync.errorFlag))
         break;
   __syncthreads();
 
-  // ---- phase 1: march
   MarchStats st{0ull, 0ull};
   const uint32_t nTiles = P.tilesW * P.tilesH;
   const bool centered = P.integrator == DVR_INTEGRATOR_RAYCAST;
+  const size_t nBg = S.bgPixelEnd > S.bgPixelBegin ? S.bgPixelEnd - S.bgPixelBegin : 0;
+  const uint32_t nChunks = (S.debugFlags & 2u) ? 0u : (uint32_t)((nBg + 255) / 256);
+  const uint32_t nOwned = S.nRegions > S.rank ? (S.nRegions - S.rank + S.nRanks - 1u) / S.nRanks : 0u;
+  const uint32_t nItems = (S.debugFlags & 4u) ? 0u : nOwned * S.tilesPerRegion;
+  bool bgLeft = nChunks > 0u, itemsLeft = nItems > 0u;
+
+  // ---- march; between two tiles every warp also takes one background chunk and, if a region this rank owns has
+  // become complete on all ranks, one composite item: the exchange is spread over the frame instead of landing on the
+  // SMs while only the stragglers of the march are left (that cost 40 us at N = 2, profiles/r02_sort_last_fused.md)
   for (uint32_t tile = nextTile(P.sched, lane); tile < nTiles; tile = nextTile(P.sched, lane)) {
     const uint32_t tyIdx = P.tileY0 + tile / P.tilesW, txIdx = P.tileX0 + tile % P.tilesW;
     const uint32_t px = txIdx * kTileW + (lane % kTileW), py = tyIdx * kTileH + (lane / kTileW);
@@ -941,12 +1052,11 @@ __global__ void __launch_bounds__(kBlockThreads, 2) dvrSlabFrameKernel(const __g
       P.partialDepth[idx] = fminf(1e30f, depth);
     }
     __syncwarp();
-    if (lane == 0) {
+    if (lane == 0 && !(S.debugFlags & 1u)) {
       const uint32_t region = tile / S.tilesPerRegion;
       const uint32_t inRegion = min(S.tilesPerRegion, nTiles - region * S.tilesPerRegion);
       // the tile's stores before the count, at device scope.  A RELEASE-only atomic: __threadfence() compiles to
-      // MEMBAR.SC.GPU + CCTL.IVALL, and invalidating the SM's L1 after every tile costs the warps that are still
-      // marching their texture-cache hits (march phase 492 us vs 470 us for the plain partial kernel at N = 2)
+      // MEMBAR.SC.GPU + CCTL.IVALL (an L1 invalidation under the warps that are still marching)
       unsigned int counted;
       asm volatile("atom.release.gpu.global.add.u32 %0, [%1], %2;"
                    : "=r"(counted) : "l"(&S.regionDone[region]), "r"(1u) : "memory");
@@ -957,64 +1067,53 @@ __global__ void __launch_bounds__(kBlockThreads, 2) dvrSlabFrameKernel(const __g
           atomicMax(&S.timing[6], globalTimerNs());
       }
     }
-  }
-
-  if (S.timing && lane == 0)
-    atomicMax(&S.timing[1], globalTimerNs());
-
-  // ---- phase 2a: background pixels of this rank's strip outside the window (no peer data, no waiting)
-  {
-    const size_t nBg = S.bgPixelEnd > S.bgPixelBegin ? S.bgPixelEnd - S.bgPixelBegin : 0;
-    const uint32_t nChunks = (uint32_t)((nBg + 255) / 256);
-    const int wx0 = (int)(P.tileX0 * kTileW), wy0 = (int)(P.tileY0 * kTileH);
-    const int wx1 = (int)((P.tileX0 + P.tilesW) * kTileW), wy1 = (int)((P.tileY0 + P.tilesH) * kTileH);
-    for (;;) {
+    __syncwarp();
+    if (bgLeft) {
       uint32_t chunk = 0;
       if (lane == 0)
         chunk = atomicAdd(&P.sched[2], 1u);
       chunk = __shfl_sync(0xffffffffu, chunk, 0);
-      if (chunk >= nChunks)
-        break;
-#pragma unroll 1
-      for (int k = 0; k < 8; ++k) {
-        const size_t i = S.bgPixelBegin + (size_t)chunk * 256 + (size_t)k * 32 + lane;
-        if (i >= S.bgPixelEnd)
-          break;
-        const uint32_t py = (uint32_t)(i / P.width), px = (uint32_t)(i - (size_t)py * P.width);
-        if ((int)px >= wx0 && (int)px < wx1 && (int)py >= wy0 && (int)py < wy1)
-          continue; // the regions own the window
-        compositePixel(S.c, px, py, false);
-      }
+      if (chunk < nChunks)
+        slabBackgroundChunk(S, chunk, lane);
+      else
+        bgLeft = false;
     }
+    if (itemsLeft && !(S.debugFlags & 8u))
+      itemsLeft = slabTryComposite(S, nItems, nTiles, lane) != 2;
   }
+  if (S.timing && lane == 0)
+    atomicMax(&S.timing[1], globalTimerNs());
 
+  // ---- the tile queue is empty: what is left of the background strip ...
+  while (bgLeft) {
+    uint32_t chunk = 0;
+    if (lane == 0)
+      chunk = atomicAdd(&P.sched[2], 1u);
+    chunk = __shfl_sync(0xffffffffu, chunk, 0);
+    if (chunk < nChunks)
+      slabBackgroundChunk(S, chunk, lane);
+    else
+      bgLeft = false;
+  }
   if (S.timing && lane == 0)
     atomicMax(&S.timing[2], globalTimerNs());
 
-  // ---- phase 2b: the regions this rank owns, in order
+  // ---- ... and of the owned regions: the last ones complete when the slowest rank finishes its march
   {
-    const uint32_t nOwned = S.nRegions > S.rank ? (S.nRegions - S.rank + S.nRanks - 1u) / S.nRanks : 0u;
-    const uint32_t nItems = nOwned * S.tilesPerRegion;
-    for (;;) {
-      uint32_t item = 0;
-      if (lane == 0)
-        item = atomicAdd(&P.sched[3], 1u);
-      item = __shfl_sync(0xffffffffu, item, 0);
-      if (item >= nItems)
-        break;
-      const uint32_t region = (item / S.tilesPerRegion) * S.nRanks + S.rank;
-      const uint32_t tile = region * S.tilesPerRegion + item % S.tilesPerRegion;
-      if (tile >= nTiles)
-        continue;
-      if ((uint32_t)lane < S.nRanks)
-        spinUntil(&S.myRegionFlags[(size_t)region * kMaxSlabs + lane], S.seq, S.c.sync.errorFlag, S.spinSleepNs);
-      __syncwarp();
-      if (S.timing && lane == 0)
+    const long long t0 = clock64();
+    while (itemsLeft) {
+      const int r = slabTryComposite(S, nItems, nTiles, lane);
+      if (r == 2)
+        itemsLeft = false;
+      else if (r == 0) {
+        __nanosleep(S.spinSleepNs);
+        if (clock64() - t0 > 4000000000ll) { // ~2 s: a missing producer must not hang the GPU
+          if (lane == 0 && S.c.sync.errorFlag)
+            *S.c.sync.errorFlag = 1u;
+          break;
+        }
+      } else if (S.timing && lane == 0)
         atomicMax(&S.timing[5], globalTimerNs());
-      const uint32_t tyIdx = P.tileY0 + tile / P.tilesW, txIdx = P.tileX0 + tile % P.tilesW;
-      const uint32_t px = txIdx * kTileW + (lane % kTileW), py = tyIdx * kTileH + (lane / kTileW);
-      if (px < P.width && py < P.height)
-        compositePixel(S.c, px, py, true);
     }
   }
 

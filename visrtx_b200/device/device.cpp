@@ -38,6 +38,23 @@ CudaDeviceScope::~CudaDeviceScope()
     cudaSetDevice(prev);
 }
 
+GpuScope::GpuScope(int gpu)
+{
+  if (cudaGetDevice(&prev) != cudaSuccess) {
+    cudaGetLastError();
+    prev = -1;
+  }
+  if (prev != gpu)
+    cudaSetDevice(gpu);
+  else
+    prev = -1;
+}
+GpuScope::~GpuScope()
+{
+  if (prev >= 0)
+    cudaSetDevice(prev);
+}
+
 // ---------------------------------------------------------------------------------------------------------
 // Frame
 // ---------------------------------------------------------------------------------------------------------
@@ -47,6 +64,8 @@ Frame::~Frame()
 {
   if (m_eventEnd)
     wait();
+  syncAllGpus();
+  freeMultiGpuBuffers();
   CudaDeviceScope scope(device);
   freeBuffers();
   if (m_eventStart) cudaEventDestroy((cudaEvent_t)m_eventStart);
@@ -63,6 +82,175 @@ void Frame::freeBuffers()
       cudaFree(*b);
     *b = nullptr;
   }
+}
+
+// ---- multi-GPU frames -------------------------------------------------------------------------------------
+// One process drives every GPU of the device (peer access enabled in Device::initDevice).  The display GPU (rank 0)
+// owns the output channels the application maps; every GPU owns the accumulation state of the pixels it resolves.
+namespace {
+constexpr uint32_t kMaxRegions = 1024;                       // rows of a region-flag table (DvrSlabExchange)
+constexpr size_t kFlagWords = (size_t)kMaxRegions * 16 + 32; // region table, resolved table, error word
+} // namespace
+
+void Frame::syncAllGpus() const
+{
+  if (!device || device->gpuCount() <= 1)
+    return;
+  for (int r = 0; r < device->gpuCount(); ++r) {
+    GpuScope scope(device->gpu(r));
+    cudaStreamSynchronize((cudaStream_t)device->stream(r));
+  }
+}
+
+void Frame::freeMultiGpuBuffers()
+{
+  for (size_t r = 0; r < m_perGpu.size(); ++r) {
+    GpuScope scope(device->gpu((int)r));
+    PerGpu &g = m_perGpu[r];
+    if (r > 0) { // rank 0 uses the frame's own accumulation / depth buffers
+      cudaFree(g.accum);
+      cudaFree(g.depth);
+    }
+    cudaFree(g.partial[0]);
+    cudaFree(g.partial[1]);
+    cudaFree(g.flags);
+    cudaFree(g.regionDone);
+    if (g.done)
+      cudaEventDestroy((cudaEvent_t)g.done);
+  }
+  m_perGpu.clear();
+  m_seq = 0;
+}
+
+bool Frame::ensureMultiGpuBuffers()
+{
+  const int world = device->gpuCount();
+  if (world <= 1)
+    return false;
+  if ((int)m_perGpu.size() == world)
+    return true;
+  const size_t n = (size_t)m_size[0] * m_size[1];
+  m_perGpu.assign((size_t)world, PerGpu());
+  bool ok = true;
+  for (int r = 0; r < world && ok; ++r) {
+    GpuScope scope(device->gpu(r));
+    PerGpu &g = m_perGpu[(size_t)r];
+    if (r == 0) {
+      g.accum = m_accum;
+      g.depth = m_depth;
+    } else {
+      ok = ok && cudaMalloc(&g.accum, n * 16) == cudaSuccess;
+      if (m_depth)
+        ok = ok && cudaMalloc(&g.depth, n * 4) == cudaSuccess;
+    }
+    ok = ok && cudaMalloc(&g.partial[0], n * 20) == cudaSuccess && cudaMalloc(&g.partial[1], n * 20) == cudaSuccess;
+    ok = ok && cudaMalloc((void **)&g.flags, kFlagWords * 4) == cudaSuccess
+        && cudaMalloc((void **)&g.regionDone, kMaxRegions * 4) == cudaSuccess;
+    ok = ok && cudaMemset(g.flags, 0, kFlagWords * 4) == cudaSuccess
+        && cudaMemset(g.regionDone, 0, kMaxRegions * 4) == cudaSuccess;
+    ok = ok && cudaEventCreateWithFlags((cudaEvent_t *)&g.done, cudaEventDisableTiming) == cudaSuccess;
+    cudaDeviceSynchronize();
+  }
+  if (!ok) {
+    cudaGetLastError();
+    report(ANARI_SEVERITY_ERROR, ANARI_STATUS_OUT_OF_MEMORY,
+        "multi-GPU frame buffers could not be allocated; rendering on the display GPU only");
+    freeMultiGpuBuffers();
+    return false;
+  }
+  m_seq = 0;
+  return true;
+}
+
+// Sort-last: the volume's z-slabs live on the GPUs; ONE fused launch per GPU marches its slab, exchanges region flags
+// and composites + resolves the regions it owns straight into the display GPU's channels (dvr_render_slab_frame).
+bool Frame::renderSortLast(const DvrFrameParams &p, const DvrFrameBuffers &display, Volume *v, const FlatInstance &fi)
+{
+  const int world = device->gpuCount();
+  const size_t n = (size_t)m_size[0] * m_size[1];
+  const uint32_t seq = ++m_seq;
+  const int parity = (int)(seq & 1u);
+  const float *rgba[16];
+  const float *depth[16];
+  unsigned int *regionFlags[16], *resolvedFlags[16];
+  for (int q = 0; q < world; ++q) {
+    rgba[q] = (const float *)m_perGpu[(size_t)q].partial[parity];
+    depth[q] = (const float *)((const uint8_t *)m_perGpu[(size_t)q].partial[parity] + n * 16);
+    regionFlags[q] = m_perGpu[(size_t)q].flags;
+    resolvedFlags[q] = m_perGpu[(size_t)q].flags + (size_t)kMaxRegions * 16;
+  }
+  bool ok = true;
+  for (int k = 0; k < world; ++k) {
+    const int r = (k + 1) % world; // the display GPU's launch waits for all the others: enqueue it last
+    GpuScope scope(device->gpu(r));
+    DvrFrameBuffers b = display; // colour / ids: peer stores into the display GPU's channels
+    b.colorAccumulation = (float *)m_perGpu[(size_t)r].accum;
+    b.depth = (float *)m_perGpu[(size_t)r].depth;
+    b.depthMirror = (r != 0 && display.depth) ? display.depth : nullptr;
+    DvrVolumeInstance inst;
+    inst.volume = v->part(r);
+    std::memcpy(inst.worldToObject, fi.worldToObject, sizeof(inst.worldToObject));
+    inst.instanceId = fi.instId;
+    inst._pad = 0;
+    DvrSlabExchange x;
+    std::memset(&x, 0, sizeof(x));
+    x.nRanks = (uint32_t)world;
+    x.rank = (uint32_t)r;
+    x.seq = seq;
+    x.maxRegions = kMaxRegions;
+    x.partialRgba = rgba;
+    x.partialDepth = depth;
+    x.regionFlags = regionFlags;
+    x.resolvedFlags = resolvedFlags;
+    x.regionDone = m_perGpu[(size_t)r].regionDone;
+    x.errorFlag = m_perGpu[(size_t)r].flags + (size_t)kMaxRegions * 16 + 16;
+    x.waitAllResolved = r == 0 ? 1 : 0;
+    const int rc = dvr_render_slab_frame(&p, &m_camera->cam, &inst, v->id(), fi.instId, &b, &x, device->stream(r));
+    if (rc != DVR_OK) {
+      report(ANARI_SEVERITY_FATAL_ERROR, ANARI_STATUS_UNKNOWN_ERROR, "dvr_render_slab_frame failed on GPU %d: %s",
+          device->gpu(r), dvr_last_error());
+      ok = false;
+    }
+  }
+  return ok;
+}
+
+// Sort-first: every GPU holds every field; GPU r renders the tile rows (row % N == r) and stores the colour / ids of
+// its pixels into the display GPU's channels; the display stream then waits for the others.
+bool Frame::renderSortFirst(DvrFrameParams p, const DvrFrameBuffers &display, const std::vector<FlatInstance> &flat)
+{
+  const int world = device->gpuCount();
+  bool ok = true;
+  for (int k = 0; k < world; ++k) {
+    const int r = (k + 1) % world;
+    GpuScope scope(device->gpu(r));
+    std::vector<DvrVolumeInstance> inst(flat.size());
+    for (size_t i = 0; i < flat.size(); ++i) {
+      inst[i].volume = flat[i].volume->part(r);
+      std::memcpy(inst[i].worldToObject, flat[i].worldToObject, sizeof(inst[i].worldToObject));
+      inst[i].instanceId = flat[i].instId;
+      inst[i]._pad = 0;
+    }
+    DvrFrameBuffers b = display;
+    b.colorAccumulation = (float *)m_perGpu[(size_t)r].accum;
+    b.depth = (float *)m_perGpu[(size_t)r].depth;
+    b.depthMirror = (r != 0 && display.depth) ? display.depth : nullptr;
+    p.tileRank = (uint32_t)r;
+    p.tileRanks = (uint32_t)world;
+    cudaStream_t s = (cudaStream_t)device->stream(r);
+    const int rc = dvr_render(&p, &m_camera->cam, inst.data(), (uint32_t)inst.size(), &b, s);
+    if (rc != DVR_OK) {
+      report(ANARI_SEVERITY_FATAL_ERROR, ANARI_STATUS_UNKNOWN_ERROR, "dvr_render failed on GPU %d: %s", device->gpu(r),
+          dvr_last_error());
+      ok = false;
+    }
+    if (r != 0) {
+      cudaEventRecord((cudaEvent_t)m_perGpu[(size_t)r].done, s);
+      GpuScope display0(device->gpu(0));
+      cudaStreamWaitEvent((cudaStream_t)device->stream(0), (cudaEvent_t)m_perGpu[(size_t)r].done, 0);
+    }
+  }
+  return ok;
 }
 
 bool Frame::isValid() const
@@ -98,6 +286,8 @@ void Frame::finalize()
     return;
   if (m_eventEnd)
     wait();
+  syncAllGpus();
+  freeMultiGpuBuffers();
   CudaDeviceScope scope(device);
   freeBuffers();
   m_pinnedHoldsFrame = false;
@@ -225,13 +415,6 @@ void Frame::renderFrame()
   m_invFrameID = 1.f / (m_frameID + 1);
 
   const std::vector<FlatInstance> flat = m_world->flatten(true);
-  std::vector<DvrVolumeInstance> inst(flat.size());
-  for (size_t i = 0; i < flat.size(); ++i) {
-    inst[i].volume = flat[i].volume->handle();
-    std::memcpy(inst[i].worldToObject, flat[i].worldToObject, sizeof(inst[i].worldToObject));
-    inst[i].instanceId = flat[i].instId;
-    inst[i]._pad = 0;
-  }
 
   DvrFrameParams p;
   std::memset(&p, 0, sizeof(p));
@@ -271,9 +454,39 @@ void Frame::renderFrame()
   b.albedo = (float *)m_albedoAccum;
   b.normal = (float *)m_normalAccum;
 
-  const int rc = dvr_render(&p, &m_camera->cam, inst.data(), (uint32_t)inst.size(), &b, stream);
-  if (rc != DVR_OK)
-    report(ANARI_SEVERITY_FATAL_ERROR, ANARI_STATUS_UNKNOWN_ERROR, "dvr_render failed: %s", dvr_last_error());
+  // Multi-GPU device: the frame goes to all GPUs when the scene is one the distributed paths cover — marching
+  // renderer, one sample per pixel-pass, no per-GPU auxiliary accumulations (albedo / normal) and no background
+  // texture (texture objects are per GPU); sort-last additionally needs a single slabbed structuredRegular volume.
+  bool done = false;
+  if (device->gpuCount() > 1) {
+    const bool marching = p.integrator == DVR_INTEGRATOR_RAYCAST || p.integrator == DVR_INTEGRATOR_DEFAULT;
+    const bool plain = marching && !m_albedoAccum && !m_normalAccum && !p.backgroundImage && p.tileRanks <= 1;
+    bool allDistributed = !flat.empty();
+    for (const FlatInstance &fi : flat)
+      allDistributed = allDistributed && fi.volume->distributed();
+    if (plain && allDistributed && device->sortLast() && flat.size() == 1 && flat[0].volume->field()->slabbed()
+        && p.numIterations == 1 && p.checkerboardID < 0 && ensureMultiGpuBuffers())
+      done = renderSortLast(p, b, flat[0].volume, flat[0]);
+    else if (plain && allDistributed && device->sortFirst() && ensureMultiGpuBuffers())
+      done = renderSortFirst(p, b, flat);
+  }
+  if (!done) {
+    std::vector<DvrVolumeInstance> inst;
+    inst.reserve(flat.size());
+    for (size_t i = 0; i < flat.size(); ++i) {
+      DvrVolumeInstance in;
+      in.volume = flat[i].volume->whole(); // (multi-GPU device: uploads the whole field to the display GPU on demand)
+      if (!in.volume)
+        continue;
+      std::memcpy(in.worldToObject, flat[i].worldToObject, sizeof(in.worldToObject));
+      in.instanceId = flat[i].instId;
+      in._pad = 0;
+      inst.push_back(in);
+    }
+    const int rc = dvr_render(&p, &m_camera->cam, inst.data(), (uint32_t)inst.size(), &b, stream);
+    if (rc != DVR_OK)
+      report(ANARI_SEVERITY_FATAL_ERROR, ANARI_STATUS_UNKNOWN_ERROR, "dvr_render failed: %s", dvr_last_error());
+  }
   m_everRendered = true;
 
   if (m_callback) { // Frame.cu:295-304
@@ -295,7 +508,8 @@ bool Frame::ensurePinned(size_t bytes)
     cudaFreeHost(m_pinned);
   m_pinned = nullptr;
   m_pinnedBytes = 0;
-  if (cudaMallocHost(&m_pinned, bytes) != cudaSuccess) {
+  // portable + mapped: every GPU of a multi-GPU device streams its pixels into it
+  if (cudaHostAlloc(&m_pinned, bytes, cudaHostAllocPortable | cudaHostAllocMapped) != cudaSuccess) {
     cudaGetLastError();
     m_pinned = nullptr;
     return false;
@@ -440,6 +654,11 @@ Device::~Device()
   for (Object *o : m_commitQueue)
     o->refDec(RefType::INTERNAL);
   m_commitQueue.clear();
+  for (size_t k = 1; k < m_streams.size(); ++k) {
+    GpuScope scope(m_gpus[k]);
+    cudaStreamSynchronize((cudaStream_t)m_streams[k]);
+    cudaStreamDestroy((cudaStream_t)m_streams[k]);
+  }
   if (m_stream) {
     CudaDeviceScope scope(this);
     cudaStreamSynchronize((cudaStream_t)m_stream);
@@ -460,6 +679,36 @@ void Device::commitParameters()
   m_cbUserPtr = getParam<const void *>("statusCallbackUserData", ANARI_VOID_POINTER, m_defaultCbUserPtr);
   const bool eager = getParam<int32_t>("forceInit", ANARI_BOOL, 0) != 0;
   m_desiredGpuID = getParam<int>("cudaDevice", ANARI_INT32, 0);
+  { // "cudaDevices": the GPUs of a multi-GPU device, display GPU first — "0,1,2,3" or an Array1D of INT32
+    std::vector<int> gpus;
+    const std::string list = getParamString("cudaDevices", "");
+    for (size_t i = 0; i < list.size();) {
+      size_t j = list.find(',', i);
+      if (j == std::string::npos)
+        j = list.size();
+      if (j > i)
+        gpus.push_back(std::atoi(list.substr(i, j - i).c_str()));
+      i = j + 1;
+    }
+    if (Object *a = getParamObject("cudaDevices", ANARI_ARRAY1D)) {
+      Array *arr = static_cast<Array *>(a);
+      if (arr->elementType == ANARI_INT32 && !arr->onDevice())
+        for (size_t i = 0; i < arr->regionSize(); ++i)
+          gpus.push_back(((const int32_t *)arr->regionData())[i]);
+    }
+    if (!gpus.empty())
+      m_desiredGpuID = gpus[0];
+    if (m_gpuID >= 0 && !gpus.empty() && gpus != m_gpus)
+      report(ANARI_SEVERITY_WARNING, ANARI_STATUS_INVALID_OPERATION,
+          "visrtx_b200 was already initialized: the new 'cudaDevices' list is ignored.");
+    m_desiredGpus = gpus;
+    const std::string mode = getParamString("multiGpuMode", "sortLast");
+    if (mode != "sortLast" && mode != "sortFirst")
+      report(ANARI_SEVERITY_WARNING, ANARI_STATUS_INVALID_ARGUMENT, "unknown multiGpuMode '%s' (sortLast | sortFirst)",
+          mode.c_str());
+    if (m_gpuID < 0)
+      m_sortLast = mode != "sortFirst";
+  }
   if (m_gpuID >= 0 && m_desiredGpuID != m_gpuID)
     report(ANARI_SEVERITY_WARNING, ANARI_STATUS_INVALID_OPERATION,
         "visrtx_b200 was already initialized to use GPU %i: new device number %i is ignored.", m_gpuID,
@@ -515,6 +764,48 @@ bool Device::initDevice()
   }
   m_stream = s;
   m_gpuID = m_desiredGpuID;
+  m_gpus.assign(1, m_gpuID);
+  m_streams.assign(1, m_stream);
+  // the other GPUs of a multi-GPU device: one private stream each, peer access between every pair (kernels load
+  // partial images from and store final pixels into each other's memory over NVLink)
+  for (size_t i = 1; i < m_desiredGpus.size(); ++i) {
+    const int g = m_desiredGpus[i];
+    bool ok = g >= 0 && g < n && std::find(m_gpus.begin(), m_gpus.end(), g) == m_gpus.end();
+    cudaStream_t sg = nullptr;
+    if (ok) {
+      GpuScope scope(g);
+      ok = cudaStreamCreateWithFlags(&sg, cudaStreamNonBlocking) == cudaSuccess;
+    }
+    if (!ok) {
+      cudaGetLastError();
+      report(ANARI_SEVERITY_ERROR, ANARI_STATUS_INVALID_ARGUMENT, "cudaDevices: GPU %d is unusable or listed twice; ignored", g);
+      continue;
+    }
+    m_gpus.push_back(g);
+    m_streams.push_back(sg);
+  }
+  for (size_t i = 0; i < m_gpus.size(); ++i)
+    for (size_t j = 0; j < m_gpus.size(); ++j) {
+      if (i == j)
+        continue;
+      int can = 0;
+      cudaDeviceCanAccessPeer(&can, m_gpus[i], m_gpus[j]);
+      GpuScope scope(m_gpus[i]);
+      const cudaError_t pe = can ? cudaDeviceEnablePeerAccess(m_gpus[j], 0) : cudaErrorPeerAccessUnsupported;
+      if (pe != cudaSuccess && pe != cudaErrorPeerAccessAlreadyEnabled) {
+        cudaGetLastError();
+        report(ANARI_SEVERITY_ERROR, ANARI_STATUS_UNSUPPORTED_DEVICE,
+            "no peer access from GPU %d to GPU %d: multi-GPU rendering disabled", m_gpus[i], m_gpus[j]);
+        for (size_t k = 1; k < m_streams.size(); ++k) {
+          GpuScope sk(m_gpus[k]);
+          cudaStreamDestroy((cudaStream_t)m_streams[k]);
+        }
+        m_gpus.resize(1);
+        m_streams.resize(1);
+        i = j = 1u << 20; // leave both loops
+      } else
+        cudaGetLastError();
+    }
   m_initStatus = 1;
   report(ANARI_SEVERITY_DEBUG, ANARI_STATUS_NO_ERROR, "initialised on GPU %d (%s, %d SMs)", m_gpuID, prop.name,
       prop.multiProcessorCount);
@@ -588,6 +879,7 @@ bool Device::getProperty(const std::string &name, ANARIDataType t, void *mem, ui
     return true;
   }
   if (t == ANARI_INT32 && name == "cudaDevice") return wi(m_gpuID);
+  if (t == ANARI_INT32 && name == "cudaDeviceCount") return wi((int32_t)m_gpus.size()); // GPUs actually in use
   return false;
 }
 

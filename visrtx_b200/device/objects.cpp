@@ -406,6 +406,15 @@ static std::atomic<uint64_t> g_fieldGeneration{0};
 
 void SpatialField::cleanup()
 {
+  for (size_t r = 0; r < m_parts.size(); ++r) {
+    if (!m_parts[r] || m_parts[r] == m_field)
+      continue;
+    GpuScope scope(device->gpu((int)r));
+    cudaStreamSynchronize((cudaStream_t)device->stream((int)r));
+    dvr_field_destroy(m_parts[r]);
+  }
+  m_parts.clear();
+  m_slabbed = false;
   if (m_field) {
     CudaDeviceScope scope(device);
     cudaStreamSynchronize((cudaStream_t)device->stream());
@@ -414,6 +423,75 @@ void SpatialField::cleanup()
     m_fieldType = -1;
   }
   m_generation = ++g_fieldGeneration;
+}
+
+// Balanced, contiguous z-slice ownership [z0, z1) of `rank` among `world` GPUs (every slice owned exactly once)
+static void slabRange(uint32_t nz, int world, int rank, uint32_t &z0, uint32_t &z1)
+{
+  const uint32_t base = nz / (uint32_t)world, rem = nz % (uint32_t)world;
+  z0 = (uint32_t)rank * base + std::min((uint32_t)rank, rem);
+  z1 = z0 + base + ((uint32_t)rank < rem ? 1u : 0u);
+}
+
+// Multi-GPU: the field on every GPU of the device.  Sort-last: z-slabs (own slices + one ghost slice each side,
+// dvr_field_create_structured_slab) — the volume may be larger than one GPU's memory; sort-first: a replica per GPU.
+bool SpatialField::createDistributed(int dataType, const uint32_t dims[3], int filter)
+{
+  const int world = device->gpuCount();
+  const size_t esz = sizeOfType(m_data->elementType);
+  const bool slabs = device->sortLast() && dims[2] >= (uint32_t)(2 * world);
+  if (device->sortLast() && !slabs)
+    return false; // too thin to slice: the caller keeps it whole on the display GPU
+  m_parts.assign((size_t)world, nullptr);
+  for (int r = 0; r < world; ++r) {
+    GpuScope scope(device->gpu(r));
+    int rc;
+    if (slabs) {
+      uint32_t z0, z1;
+      slabRange(dims[2], world, r, z0, z1);
+      const uint32_t first = z0 > 0 ? z0 - 1 : 0; // data points at the first RESIDENT slice (ghost included)
+      const uint8_t *src = (const uint8_t *)m_data->data() + (size_t)first * dims[0] * dims[1] * esz;
+      rc = dvr_field_create_structured_slab(src, m_data->onDevice() ? 1 : 0, dataType, dims, z0, z1, m_origin, m_spacing,
+          filter, device->stream(r), &m_parts[(size_t)r]);
+    } else
+      rc = dvr_field_create_structured(m_data->data(), m_data->onDevice() ? 1 : 0, dataType, dims, m_origin, m_spacing,
+          filter, device->stream(r), &m_parts[(size_t)r]);
+    if (rc != DVR_OK) {
+      m_parts[(size_t)r] = nullptr;
+      report(ANARI_SEVERITY_ERROR, rc == DVR_ERR_OUT_OF_MEMORY ? ANARI_STATUS_OUT_OF_MEMORY : ANARI_STATUS_UNKNOWN_ERROR,
+          "structuredRegular field upload to GPU %d failed: %s", device->gpu(r), dvr_last_error());
+      cleanup();
+      return false;
+    }
+  }
+  m_slabbed = slabs;
+  if (!slabs)
+    m_field = m_parts[0]; // the display GPU's replica doubles as the whole field
+  return true;
+}
+
+DvrField *SpatialField::createWhole(int dataType, const uint32_t dims[3], int filter)
+{
+  CudaDeviceScope scope(device);
+  DvrField *f = nullptr;
+  const int rc = dvr_field_create_structured(m_data->data(), m_data->onDevice() ? 1 : 0, dataType, dims, m_origin,
+      m_spacing, filter, device->stream(), &f);
+  if (rc != DVR_OK) {
+    report(ANARI_SEVERITY_ERROR, rc == DVR_ERR_OUT_OF_MEMORY ? ANARI_STATUS_OUT_OF_MEMORY : ANARI_STATUS_UNKNOWN_ERROR,
+        "structuredRegular field upload failed: %s", dvr_last_error());
+    return nullptr;
+  }
+  return f;
+}
+
+DvrField *SpatialField::whole()
+{
+  if (m_field || !m_slabbed || !m_data)
+    return m_field;
+  report(ANARI_SEVERITY_PERFORMANCE_WARNING, ANARI_STATUS_NO_ERROR,
+      "this frame is outside what the sort-last path covers: uploading the whole field to the display GPU as well");
+  m_field = createWhole(m_fieldType, m_fieldDims, m_fieldFilter == "nearest" ? DVR_FILTER_NEAREST : DVR_FILTER_LINEAR);
+  return m_field;
 }
 
 void SpatialField::commitParameters()
@@ -495,13 +573,11 @@ void SpatialField::finalize()
     return;
   CudaDeviceScope scope(device);
   const uint32_t dims[3] = {(uint32_t)m_data->dims[0], (uint32_t)m_data->dims[1], (uint32_t)m_data->dims[2]};
-  const int rc = dvr_field_create_structured(m_data->data(), m_data->onDevice() ? 1 : 0, dt, dims, m_origin, m_spacing,
-      m_filter == "nearest" ? DVR_FILTER_NEAREST : DVR_FILTER_LINEAR, device->stream(), &m_field);
-  if (rc != DVR_OK) {
-    m_field = nullptr;
-    report(ANARI_SEVERITY_ERROR, rc == DVR_ERR_OUT_OF_MEMORY ? ANARI_STATUS_OUT_OF_MEMORY : ANARI_STATUS_UNKNOWN_ERROR,
-        "structuredRegular field upload failed: %s", dvr_last_error());
-    return;
+  const int filt = m_filter == "nearest" ? DVR_FILTER_NEAREST : DVR_FILTER_LINEAR;
+  if (!(device->gpuCount() > 1 && dt != DVR_FLOAT64 && createDistributed(dt, dims, filt))) {
+    m_field = createWhole(dt, dims, filt);
+    if (!m_field)
+      return;
   }
   m_fieldType = dt;
   m_fieldFilter = m_filter;
@@ -513,6 +589,8 @@ void SpatialField::finalize()
 // and filter are unchanged the device array, textures and macrocell storage are reused instead of rebuilt.
 bool SpatialField::refinalizeInPlace()
 {
+  if (distributed())
+    return false; // slabs / replicas are rebuilt
   const int dt = dvrTypeOf(m_data->elementType);
   if (dt < 0 || dt != m_fieldType || m_filter != m_fieldFilter)
     return false;
@@ -529,6 +607,8 @@ void SpatialField::bounds(float lo[3], float hi[3]) const
 {
   if (m_field)
     dvr_field_bounds(m_field, lo, hi);
+  else if (!m_parts.empty() && m_parts[0])
+    dvr_field_bounds(m_parts[0], lo, hi); // a slab reports the bounds of the whole field
   else {
     lo[0] = lo[1] = lo[2] = 0.f;
     hi[0] = hi[1] = hi[2] = 1.f;
@@ -548,12 +628,22 @@ bool SpatialField::getProperty(const std::string &name, ANARIDataType t, void *m
   if (name == "valueRange" && t == ANARI_FLOAT32_BOX1 && size >= 8) { // tsd computeScalarRange equivalent
     if (mask & ANARI_WAIT)
       device->flushCommits();
-    if (!m_field)
+    if (!isValid())
       return false;
-    CudaDeviceScope scope(device);
-    float r[2];
-    if (dvr_field_value_range(m_field, device->stream(), r) != DVR_OK)
-      return false;
+    float r[2] = {std::numeric_limits<float>::max(), -std::numeric_limits<float>::max()};
+    if (m_field) {
+      CudaDeviceScope scope(device);
+      if (dvr_field_value_range(m_field, device->stream(), r) != DVR_OK)
+        return false;
+    } else
+      for (size_t k = 0; k < m_parts.size(); ++k) { // slabs: the extrema of all of them
+        GpuScope scope(device->gpu((int)k));
+        float q[2];
+        if (dvr_field_value_range(m_parts[k], device->stream((int)k), q) != DVR_OK)
+          return false;
+        r[0] = std::min(r[0], q[0]);
+        r[1] = std::max(r[1], q[1]);
+      }
     std::memcpy(mem, r, 8);
     return true;
   }
@@ -616,6 +706,14 @@ void Volume::commitParameters()
 
 void Volume::dropDeviceVolume()
 {
+  for (size_t r = 0; r < m_vparts.size(); ++r) {
+    if (!m_vparts[r] || m_vparts[r] == m_volume)
+      continue;
+    GpuScope scope(device->gpu((int)r));
+    cudaStreamSynchronize((cudaStream_t)device->stream((int)r));
+    dvr_volume_destroy(m_vparts[r]);
+  }
+  m_vparts.clear();
   if (!m_volume)
     return;
   CudaDeviceScope scope(device);
@@ -629,9 +727,10 @@ void Volume::finalize()
 {
   // The device volume references its DvrField by pointer: once that field was destroyed or replaced the volume must
   // not survive an early return below (isValid() would otherwise vouch for a dangling handle).
-  if (m_volume && (!m_field || !m_field->isValid() || m_volumeField != m_field->handle()
+  if ((m_volume || !m_vparts.empty())
+      && (!m_field || !m_field->isValid() || m_field->distributed() || m_volumeField != m_field->handle()
           || m_volumeFieldGeneration != m_field->generation()))
-    dropDeviceVolume();
+    dropDeviceVolume(); // (volumes over distributed fields are rebuilt on every finalize)
   if (!m_known) {
     report(ANARI_SEVERITY_WARNING, ANARI_STATUS_INVALID_ARGUMENT, "unknown volume subtype '%s'", subtype.c_str());
     return;
@@ -670,6 +769,28 @@ void Volume::finalize()
     dropDeviceVolume(); // a rejected edit must not leave the previous table rendering as if it were current
     return;
   }
+  m_tf = tf;
+  if (m_field->distributed()) { // one device volume per GPU, over that GPU's slab / replica
+    const int world = device->gpuCount();
+    m_vparts.assign((size_t)world, nullptr);
+    for (int r = 0; r < world; ++r) {
+      GpuScope scope(device->gpu(r));
+      const int rc = dvr_volume_create(m_field->part(r), tf.data(), m_valueRange, m_unitDistance, m_id, device->stream(r),
+          &m_vparts[(size_t)r]);
+      if (rc != DVR_OK) {
+        m_vparts[(size_t)r] = nullptr;
+        report(ANARI_SEVERITY_ERROR, ANARI_STATUS_UNKNOWN_ERROR, "volume upload to GPU %d failed: %s", device->gpu(r),
+            dvr_last_error());
+        dropDeviceVolume();
+        return;
+      }
+    }
+    if (!m_field->slabbed())
+      m_volume = m_vparts[0]; // the display GPU's replica is the whole volume
+    m_volumeField = m_field->handle();
+    m_volumeFieldGeneration = m_field->generation();
+    return;
+  }
   CudaDeviceScope scope(device);
   int rc = DVR_ERR_UNSUPPORTED;
   if (m_volume) // same field object, same generation (checked above): refresh in place
@@ -684,6 +805,21 @@ void Volume::finalize()
   }
   if (rc != DVR_OK)
     report(ANARI_SEVERITY_ERROR, ANARI_STATUS_UNKNOWN_ERROR, "volume upload failed: %s", dvr_last_error());
+}
+
+DvrVolume *Volume::whole()
+{
+  if (m_volume || m_vparts.empty() || !m_field)
+    return m_volume;
+  DvrField *f = m_field->whole();
+  if (!f || m_tf.empty())
+    return nullptr;
+  CudaDeviceScope scope(device);
+  if (dvr_volume_create(f, m_tf.data(), m_valueRange, m_unitDistance, m_id, device->stream(), &m_volume) != DVR_OK) {
+    m_volume = nullptr;
+    report(ANARI_SEVERITY_ERROR, ANARI_STATUS_UNKNOWN_ERROR, "volume upload failed: %s", dvr_last_error());
+  }
+  return m_volume;
 }
 
 // ---------------------------------------------------------------------------------------------------------

@@ -186,10 +186,18 @@ struct SpatialField : Object
   ~SpatialField() override;
   void commitParameters() override;
   void finalize() override;
-  bool isValid() const override { return m_field != nullptr; }
+  bool isValid() const override { return m_field != nullptr || !m_parts.empty(); }
   int commitPriority() const override { return 2; }
   bool getProperty(const std::string &name, ANARIDataType type, void *mem, uint64_t size, uint32_t mask) override;
   DvrField *handle() const { return m_field; }
+  // Multi-GPU: the field as GPU `rank` holds it — its z-slab in sort-last mode, a replica in sort-first mode; null when
+  // the field is not distributed (single GPU, NanoVDB in sort-last mode, too few slices).
+  DvrField *part(int rank) const { return (size_t)rank < m_parts.size() ? m_parts[(size_t)rank] : nullptr; }
+  bool distributed() const { return !m_parts.empty(); }
+  bool slabbed() const { return m_slabbed; }
+  // The whole field on the display GPU, created on demand: what a frame falls back to when the scene is not one the
+  // multi-GPU paths cover (several volumes in sort-last mode, dpt renderer, albedo / normal channels ...)
+  DvrField *whole();
   // bumped whenever handle() becomes a NEW device field (not by an in-place refresh): an address alone can be reused
   uint64_t generation() const { return m_generation; }
   void bounds(float lo[3], float hi[3]) const;
@@ -197,6 +205,10 @@ struct SpatialField : Object
  private:
   void cleanup();
   bool refinalizeInPlace();
+  bool createDistributed(int dataType, const uint32_t dims[3], int filter);
+  DvrField *createWhole(int dataType, const uint32_t dims[3], int filter);
+  std::vector<DvrField *> m_parts;
+  bool m_slabbed = false;
   uint64_t m_generation = 0;
   int m_fieldType = -1;
   uint32_t m_fieldDims[3] = {0, 0, 0};
@@ -215,9 +227,15 @@ struct Volume : Object
   ~Volume() override;
   void commitParameters() override;
   void finalize() override;
-  bool isValid() const override { return m_volume != nullptr && m_field && m_field->isValid(); }
+  bool isValid() const override
+  {
+    return (m_volume != nullptr || !m_vparts.empty()) && m_field && m_field->isValid();
+  }
   int commitPriority() const override { return 3; }
   DvrVolume *handle() const { return m_volume; }
+  DvrVolume *part(int rank) const { return (size_t)rank < m_vparts.size() ? m_vparts[(size_t)rank] : nullptr; }
+  bool distributed() const { return !m_vparts.empty(); }
+  DvrVolume *whole(); // the volume over SpatialField::whole(), created on demand (display GPU)
   SpatialField *field() const { return m_field.ptr; }
   uint32_t id() const { return m_id; }
 
@@ -231,6 +249,8 @@ struct Volume : Object
   float m_valueRange[2] = {0.f, 1.f};
   uint32_t m_id = ~0u;
   DvrVolume *m_volume = nullptr;
+  std::vector<DvrVolume *> m_vparts;
+  std::vector<float> m_tf; // the discretised table of the last finalize (for whole())
   const DvrField *m_volumeField = nullptr;
   uint64_t m_volumeFieldGeneration = 0;
   bool m_known = true;
@@ -333,6 +353,22 @@ struct Frame : Object
  private:
   void checkAccumulationReset();
   void freeBuffers();
+  // multi-GPU frames (device.cpp): per-GPU accumulation / partial images / flag tables, fused slab frames
+  struct PerGpu
+  {
+    void *accum = nullptr, *depth = nullptr;        // this GPU's share of the accumulation state
+    void *partial[2] = {nullptr, nullptr};          // float4[W*H] + float[W*H], alternating between frames
+    unsigned int *flags = nullptr;                  // region table + resolved table + error word
+    unsigned int *regionDone = nullptr;
+    void *done = nullptr;                           // sort-first: "this GPU's tile rows are rendered" event
+  };
+  std::vector<PerGpu> m_perGpu;
+  uint32_t m_seq = 0;
+  bool ensureMultiGpuBuffers();
+  void freeMultiGpuBuffers();
+  void syncAllGpus() const;
+  bool renderSortLast(const DvrFrameParams &p, const DvrFrameBuffers &display, Volume *v, const FlatInstance &fi);
+  bool renderSortFirst(DvrFrameParams p, const DvrFrameBuffers &display, const std::vector<FlatInstance> &flat);
   void *download(void *dev, size_t bytes, std::vector<uint8_t> &host);
 
   Ref<Renderer> m_renderer;
@@ -383,6 +419,15 @@ struct Device : Object
   uint64_t lastFinalization() const { return m_lastFinalization; }
   void *stream() const { return m_stream; }
   int cudaDevice() const { return m_gpuID; }
+  // Multi-GPU (one process, peer access; the reference is single-GPU, VisRTXDevice.cpp:464): the device parameter
+  // "cudaDevices" lists the GPUs, the first one being the display GPU that owns the frame's output channels;
+  // "multiGpuMode" = "sortLast" (z-slabs of every structuredRegular field, fused march + exchange per GPU, default)
+  // or "sortFirst" (fields replicated, interleaved tile rows).
+  int gpuCount() const { return (int)m_gpus.size(); }
+  int gpu(int rank) const { return m_gpus[(size_t)rank]; }
+  void *stream(int rank) const { return m_streams[(size_t)rank]; }
+  bool sortLast() const { return gpuCount() > 1 && m_sortLast; }
+  bool sortFirst() const { return gpuCount() > 1 && !m_sortLast; }
 
   void message(const Object *src, ANARIStatusSeverity sev, ANARIStatusCode code, const char *msg) const;
 
@@ -399,6 +444,18 @@ struct Device : Object
   int m_initStatus = 0; // 0 uninitialised, 1 ok, -1 failed
   int m_desiredGpuID = 0, m_gpuID = -1;
   void *m_stream = nullptr;
+  std::vector<int> m_desiredGpus; // "cudaDevices"; empty = {cudaDevice}
+  std::vector<int> m_gpus;        // after initDevice: [0] == m_gpuID
+  std::vector<void *> m_streams;  // one private stream per GPU, [0] == m_stream
+  bool m_sortLast = true;
+};
+
+// RAII: cudaSetDevice(gpu) for the scope
+struct GpuScope
+{
+  explicit GpuScope(int gpu);
+  ~GpuScope();
+  int prev = -1;
 };
 
 // RAII: every API entry saves / restores the caller's current CUDA device (VisRTXDevice.cpp:790-814)

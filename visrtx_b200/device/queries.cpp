@@ -100,6 +100,8 @@ ParamDesc strings(ParamDesc p, const char *const *values)
 }
 
 const ParamDesc kName = P("name", ANARI_STRING, "optional object name");
+const char *const kSortLast = "sortLast";
+const char *const kMultiGpuModes[] = {"sortLast", "sortFirst", nullptr};
 
 std::vector<ParamDesc> cameraCommon()
 {
@@ -236,7 +238,16 @@ std::vector<ObjectInfo> buildTables()
       {kName, P("statusCallback", ANARI_STATUS_CALLBACK, "callback used to report information to the application"),
           P("statusCallbackUserData", ANARI_VOID_POINTER, "passed to the status callback"),
           P("cudaDevice", ANARI_INT32, "ordinal of the CUDA device to render on", &kI0, &kI0),
-          P("forceInit", ANARI_BOOL, "initialise CUDA when the device is committed instead of at first use", &kFalse)},
+          P("forceInit", ANARI_BOOL, "initialise CUDA when the device is committed instead of at first use", &kFalse),
+          ext(P("cudaDevices", ANARI_STRING,
+                  "multi-GPU: comma separated CUDA device ordinals, display GPU first (also accepted as an Array1D of INT32)"),
+              "ANARI_VISRTX_B200_DVR"),
+          ext(strings(P("multiGpuMode", ANARI_STRING,
+                          "multi-GPU: sortLast = z-slabs of structuredRegular fields, fused march + exchange per GPU; "
+                          "sortFirst = fields replicated, interleaved tile rows",
+                          &kSortLast),
+                  kMultiGpuModes),
+              "ANARI_VISRTX_B200_DVR")},
       {}});
   for (ObjectInfo &o : t) {
     for (const ParamDesc &p : o.params)
