@@ -347,6 +347,92 @@ int dvr_render_instrumented(const DvrFrameParams *params, const DvrCamera *camer
 /* number of kernel launches issued by this library since load (bench.py "gpu_launches") */
 unsigned long long dvr_launch_count(void);
 
+/* ---- surfaces in front of / behind volumes, lights and shadow rays ---------------------------
+ * The mixed-scene branch of the `default` (directLight) and `raycast` renderers: primary rays find the closest
+ * surface, volumes are marched up to surfaceHit.t, the surface is shaded (matte, ambient + direct light with
+ * surface- and volume-attenuated shadow rays, ambient occlusion) and the loop continues behind a translucent
+ * surface (renderer/DirectLight_ptx.cu:64-218,294-418, Raycast_ptx.cu:60-179, gpu/computeAO.h:39-60,
+ * gpu/sampleLight.h:54-80, shaders/MatteShader_ptx.cu:39-80).  OptiX's RT-core traversal is replaced by a BVH over
+ * all primitives of the flattened world, built on the host at dvr_surfaces_create. */
+typedef struct DvrSurfaces DvrSurfaces; /* replaces the surface TLAS/BLAS + SurfaceGPUData / GeometryGPUData / MaterialGPUData */
+
+typedef enum DvrGeometryType
+{
+  DVR_GEOMETRY_TRIANGLE = 0, /* scene/surface/geometry/Triangle.cpp: vertex.position, primitive.index, vertex.normal */
+  DVR_GEOMETRY_SPHERE = 1    /* scene/surface/geometry/Sphere.cu: vertex.position, primitive.index, vertex.radius, radius */
+} DvrGeometryType;
+
+typedef enum DvrAlphaMode /* gpu/evalMaterialParameters.h:392-403 */
+{
+  DVR_ALPHA_OPAQUE = 0,
+  DVR_ALPHA_BLEND = 1,
+  DVR_ALPHA_MASK = 2
+} DvrAlphaMode;
+
+/* One surface instance of the flattened world: geometry + matte material + instance transform.  All arrays are HOST
+ * memory and are copied by dvr_surfaces_create. */
+typedef struct DvrSurfaceDesc
+{
+  int32_t geometryType;        /* DvrGeometryType */
+  uint32_t nVertices;
+  const float *vertexPosition; /* vec3[nVertices]: triangle corners / sphere centres */
+  uint32_t nPrimitives;        /* triangles / spheres; with index == NULL: nVertices / 3 resp. nVertices */
+  const uint32_t *index;       /* triangle: uvec3[nPrimitives]; sphere: uint32[nPrimitives]; NULL = soup */
+  const float *vertexNormal;   /* triangle: vec3[nVertices] or NULL (=> geometric normal) */
+  const float *vertexRadius;   /* sphere: float[nVertices] or NULL (=> radius) */
+  float radius;                /* sphere "radius" (default 0.01) */
+  const uint32_t *primitiveId; /* "primitive.id": uint32[nPrimitives] or NULL (=> primitive index) */
+  int32_t cullBackfaces;       /* triangle "cullBackfaces" (gpu/populateHit.h:331-343) */
+  /* matte material (scene/surface/material/Matte.cpp:38-52): constant colour / opacity only */
+  float color[4];              /* default (0.8, 0.8, 0.8, 1) */
+  float opacity;               /* default 1 */
+  int32_t alphaMode;           /* DvrAlphaMode, default opaque */
+  float alphaCutoff;           /* default 0.5 */
+  uint32_t surfaceId;          /* surface "id", default ~0u */
+  uint32_t instanceId;         /* instance "id", default ~0u */
+  float objectToWorld[12];     /* row-major 3x4 */
+} DvrSurfaceDesc;
+
+int dvr_surfaces_create(const DvrSurfaceDesc *surfaces, uint32_t nSurfaces, void *stream, DvrSurfaces **out);
+int dvr_surfaces_destroy(DvrSurfaces *s);
+/* primitives and BVH nodes held (tests / bookkeeping) */
+int dvr_surfaces_info(const DvrSurfaces *s, uint32_t *nPrimitives, uint32_t *nNodes);
+
+typedef enum DvrLightType
+{
+  DVR_LIGHT_DIRECTIONAL = 0, /* scene/light/Directional.cpp: direction (normalised), irradiance */
+  DVR_LIGHT_POINT = 1        /* scene/light/Point.cpp: position, intensity (or power) */
+} DvrLightType;
+
+/* one light instance, already transformed by its instance (gpu/sampleLight.h:54-78 applies xfmVec / xfmPoint) */
+typedef struct DvrLight
+{
+  int32_t type;
+  float color[3];
+  float vec[3];   /* directional: world-space direction the light travels in; point: world-space position */
+  float strength; /* irradiance / intensity */
+} DvrLight;
+
+/* the RendererGPUData members the surface branch reads (Renderer.cpp:152-207, DirectLight.cpp:49-64) */
+typedef struct DvrSceneParams
+{
+  const DvrSurfaces *surfaces; /* NULL or empty: dvr_render_scene == dvr_render */
+  const DvrLight *lights;      /* HOST array */
+  uint32_t nLights;
+  float ambientColor[3];       /* "ambientColor", default 1,1,1 */
+  float ambientRadiance;       /* "ambientRadiance" (directLight default 0) */
+  float occlusionDistance;     /* "ambientOcclusionDistance"; 0 => 1e20 */
+  int32_t ambientSamples;      /* "ambientSamples" clamped to [0,256], default 1 */
+  int32_t cullTriangleBackfaces; /* "cullTriangleBackfaces" */
+} DvrSceneParams;
+
+/* dvr_render for a world that also holds surfaces and lights.  DVR_INTEGRATOR_DEFAULT runs the directLight raygen
+ * (jittered pixel, numIterations), DVR_INTEGRATOR_RAYCAST the raycast one (|dir . Ns| * ambientColor headlight); any
+ * other integrator -> DVR_ERR_UNSUPPORTED.  Volume segments use the same marcher as dvr_render, so a pixel whose
+ * rays meet no surface is bit-identical to dvr_render. */
+int dvr_render_scene(const DvrFrameParams *params, const DvrCamera *camera, const DvrVolumeInstance *instances,
+    uint32_t nInstances, const DvrSceneParams *scene, const DvrFrameBuffers *buffers, void *stream);
+
 /* ---- sort-last (slab) rendering and compositing, SURVEY 8e ---------------------------- */
 
 /* Partial render of the slab fields on the GLOBAL sample lattice: writes premultiplied

@@ -31,11 +31,13 @@ __device__ inline unsigned optixGetPayload_3() { return 0; }
 __device__ inline unsigned optixGetPayload_4() { return 0; }
 
 __device__ void refgpu_shim_trace(unsigned long long traversable, float3 org, float3 dir, float tmin, float tmax,
-    unsigned ssHi, unsigned ssLo, unsigned dataHi, unsigned dataLo, unsigned bvhSelection);
+    unsigned ssHi, unsigned ssLo, unsigned dataHi, unsigned dataLo, unsigned bvhSelection, unsigned rayFlags);
 
 __device__ inline void optixTrace(OptixTraversableHandle h, float3 org, float3 dir, float tmin, float tmax,
-    float /*time*/, unsigned /*mask*/, unsigned /*flags*/, unsigned /*sbtOffset*/, unsigned /*sbtStride*/,
+    float /*time*/, unsigned /*mask*/, unsigned flags, unsigned /*sbtOffset*/, unsigned /*sbtStride*/,
     unsigned /*miss*/, unsigned &u0, unsigned &u1, unsigned &u2, unsigned &u3, unsigned &u4)
 {
-  refgpu_shim_trace(h, org, dir, tmin, tmax, u0, u1, u2, u3, u4);
+  // the ray flags tell the shim which programs would run: DISABLE_CLOSESTHIT = a shadow ray (any-hit accumulation),
+  // CULL_BACK_FACING_TRIANGLES = the renderer's cullTriangleBackfaces on primary rays
+  refgpu_shim_trace(h, org, dir, tmin, tmax, u0, u1, u2, u3, u4, flags);
 }

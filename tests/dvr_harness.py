@@ -85,6 +85,18 @@ class SceneDesc:
     dpt_reference_grid: bool = False  # walk the grid content the reference builds (Q7/Q8)
     # renderer "background" given as an Array2D image: (pixels [h, w, channels], capi.DVR_IMAGE_* component type)
     background_image: Optional[tuple] = None
+    # mixed scenes: surfaces / lights as dicts with the ANARI parameter names (pods.surface_descs,
+    # pods.scene_params) and the renderer members the surface branch reads
+    surfaces: Optional[list] = None
+    lights: Optional[list] = None
+    ambient_color: tuple = (1.0, 1.0, 1.0)
+    surface_ambient_radiance: float = 0.0
+    ambient_samples: int = 1
+    cull_triangle_backfaces: bool = False
+
+    def scene_params(self, surfaces_handle=None):
+        return capi.scene_params(surfaces_handle, self.lights or [], self.ambient_color, self.surface_ambient_radiance,
+                                 self.occlusion_distance, self.ambient_samples, self.cull_triangle_backfaces)
 
 
 def default_scene(n=64, width=256, height=256, rate=0.5, field="ml", **kw) -> SceneDesc:
@@ -266,6 +278,7 @@ class CudaScene:
         self.instances, self.n = capi.make_instances(
             self.volumes, [v.world_to_object for v in scene.volumes], [v.inst_id for v in scene.volumes])
         self.bg_image = capi.Image.create(*scene.background_image) if scene.background_image is not None else None
+        self.surfaces = capi.Surfaces.create(scene.surfaces) if scene.surfaces else None
         n = scene.width * scene.height
         t = torch
         self.buf = {"accum": t.zeros((n, 4), dtype=t.float32, device=self.device)}
@@ -291,6 +304,11 @@ class CudaScene:
             capi.render_instrumented(p, self.scene.camera, self.instances, self.n, self.fb, st.data_ptr())
             self.torch.cuda.synchronize()
             return dict(zip(("samplesTaken", "samplesSkipped", "raysHit", "macrocellsTouched"), st.tolist()))
+        if self.surfaces is not None:
+            sp, keep = self.scene.scene_params(self.surfaces.handle)
+            capi.render_scene(p, self.scene.camera, self.instances, self.n, sp, self.fb)
+            del keep
+            return None
         capi.render(p, self.scene.camera, self.instances, self.n, self.fb)
         return None
 
@@ -323,6 +341,8 @@ class CudaScene:
             f.destroy()
         if self.bg_image is not None:
             self.bg_image.destroy()
+        if self.surfaces is not None:
+            self.surfaces.destroy()
 
 
 def render_cuda(scene: SceneDesc, frames=1, checkerboard=False, skip=False):
@@ -396,6 +416,14 @@ def render_refgpu(scene: SceneDesc, frames=1, checkerboard=False, grids=None, re
                                      C.byref(ref_img))
         assert rc == 0, lib.refgpu_last_error()
         lib.refgpu_scene_set_background_image(sc, ref_img)
+    if scene.surfaces:
+        sarr, skeep = capi.surface_descs(scene.surfaces)
+        rc = lib.refgpu_scene_set_surfaces(sc, sarr, C.c_uint32(len(scene.surfaces)))
+        assert rc == 0, lib.refgpu_last_error()
+        sp, lkeep = scene.scene_params(None)
+        rc = lib.refgpu_scene_set_lighting(sc, C.byref(sp))
+        assert rc == 0, lib.refgpu_last_error()
+        keep += [skeep, lkeep]
     n = scene.width * scene.height
     dev = torch.device("cuda:0")
     buf = {"accum": torch.full((n, 4), 777.0, dtype=torch.float32, device=dev)}
@@ -579,6 +607,76 @@ def scene_zoo():
 # ------------------------------------------------------------------------------------------------------------
 DPT_KINDS = ("ml40", "ml77", "nvdb", "two")
 DPT_GOLDEN_FRAMES = 8
+
+
+# ------------------------------------------------------------------------------------------------------------
+# mixed scenes: surfaces in front of / behind / inside volumes, lights, shadow rays
+def _quad(p0, p1, p2, p3):
+    """two triangles (soup) over the corners p0..p3 (counter-clockwise seen from the front)"""
+    return np.array([p0, p1, p2, p0, p2, p3], np.float32)
+
+
+def _uv_sphere_mesh(center, radius, nu=12, nv=8):
+    """indexed triangle mesh of a sphere with per-vertex normals"""
+    verts, normals = [], []
+    for j in range(nv + 1):
+        th = np.pi * j / nv
+        for i in range(nu):
+            ph = 2.0 * np.pi * i / nu
+            n = np.array([np.sin(th) * np.cos(ph), np.cos(th), np.sin(th) * np.sin(ph)])
+            normals.append(n)
+            verts.append(np.asarray(center) + radius * n)
+    idx = []
+    for j in range(nv):
+        for i in range(nu):
+            a, b = j * nu + i, j * nu + (i + 1) % nu
+            c, d = a + nu, b + nu
+            idx += [(a, b, d), (a, d, c)]
+    return np.array(verts, np.float32), np.array(normals, np.float32), np.array(idx, np.uint32)
+
+
+def mixed_scene_zoo(wh=96):
+    """name -> SceneDesc: the surface branch of the default / raycast renderers around a 32^3 volume on [-1,1]^3"""
+    zoo = {}
+    sun = {"type": "directional", "direction": (-0.3, -1.0, -0.2), "irradiance": 2.5, "color": (1.0, 0.95, 0.9)}
+    lamp = {"type": "point", "position": (1.6, 1.8, 1.2), "intensity": 6.0}
+    floor = {"geometry": "triangle", "vertex.position": _quad((-3, -1.3, -3), (-3, -1.3, 3), (3, -1.3, 3), (3, -1.3, -3)),
+             "color": (0.7, 0.7, 0.75), "id": 11, "instanceId": 21}
+    balls = {"geometry": "sphere", "vertex.position": [(-0.4, 0.2, 1.3), (0.7, -0.2, 0.2), (0.1, 0.9, -0.6)],
+             "vertex.radius": [0.25, 0.35, 0.2], "color": (0.9, 0.3, 0.2), "id": 12, "instanceId": 22,
+             "primitive.id": [100, 101, 102]}
+
+    def base(**kw):
+        sc = default_scene(32, wh, wh, rate=0.5, field="blobs", integrator=capi.DVR_INTEGRATOR_DEFAULT, **kw)
+        sc.volumes[0].unit_distance = 0.25
+        return sc
+
+    # shadows of the volume and of the spheres on the floor; spheres in front of, inside and behind the volume
+    zoo["floor_balls_sun"] = base(surfaces=[floor, balls], lights=[sun], surface_ambient_radiance=0.2)
+    zoo["floor_balls_lamp_spp2"] = base(surfaces=[floor, balls], lights=[lamp, sun], num_iterations=2,
+                                        ambient_samples=2, ambient_color=(0.6, 0.7, 1.0), surface_ambient_radiance=0.3)
+    # a translucent sheet in front of the volume: the loop continues behind it (blend), a masked one does not exist
+    sheet = {"geometry": "triangle", "vertex.position": _quad((-1.2, -1.2, 1.6), (1.2, -1.2, 1.6), (1.2, 1.2, 1.6), (-1.2, 1.2, 1.6)),
+             "color": (0.2, 0.6, 0.9, 0.8), "opacity": 0.5, "alphaMode": "blend", "id": 13}
+    masked = {"geometry": "triangle", "vertex.position": _quad((-3, -3, 2.2), (3, -3, 2.2), (3, 3, 2.2), (-3, 3, 2.2)),
+              "color": (1, 0, 0, 0.3), "alphaMode": "mask", "alphaCutoff": 0.5, "id": 14}
+    zoo["translucent_sheet"] = base(surfaces=[sheet, masked, floor], lights=[sun], ambient_samples=0,
+                                    surface_ambient_radiance=0.5)
+    # raycast renderer: indexed mesh with vertex normals under an instance transform, back-face culling
+    v, n, idx = _uv_sphere_mesh((0.0, 0.0, 0.0), 0.5)
+    mesh = {"geometry": "triangle", "vertex.position": v, "vertex.normal": n, "primitive.index": idx,
+            "color": (0.3, 0.8, 0.4), "id": 15, "instanceId": 25, "cullBackfaces": True,
+            "transform": (1.2, 0.0, 0.3, 0.5, 0.0, 0.8, 0.0, -0.3, -0.3, 0.0, 1.2, 1.0)}
+    zoo["raycast_mesh_instance"] = base(surfaces=[mesh, floor], ambient_color=(1.0, 0.9, 0.8))
+    zoo["raycast_mesh_instance"].integrator = capi.DVR_INTEGRATOR_RAYCAST
+    zoo["default_mesh_cullbf"] = base(surfaces=[mesh, balls], lights=[lamp], cull_triangle_backfaces=True,
+                                      channels=("depth", "primId", "objId", "instId", "albedo", "normal"))
+    # surfaces only (no volume at all) and a float frame
+    only = base(surfaces=[floor, balls, mesh], lights=[sun, lamp], surface_ambient_radiance=0.1,
+                fmt=capi.DVR_FORMAT_FLOAT32_VEC4)
+    only.volumes = []
+    zoo["surfaces_only_float"] = only
+    return zoo
 
 
 def dpt_scene(kind, wh=96, **kw) -> SceneDesc:

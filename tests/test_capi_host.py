@@ -30,17 +30,20 @@ def test_struct_layouts_match_header_sizes(tmp_path):
     last members): a mismatch would corrupt every launch."""
     import subprocess
     src = tmp_path / "sizes.c"
-    src.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "dvr_b200.h"\nint main(void){printf("%zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu\\n",'
+    src.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "dvr_b200.h"\nint main(void){printf("%zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu ",'
                    'sizeof(DvrCamera),sizeof(DvrVolumeInstance),sizeof(DvrFrameBuffers),sizeof(DvrFrameParams),'
                    'sizeof(DvrRenderStats),sizeof(DvrPeerSync),offsetof(DvrFrameParams,backgroundImage),'
-                   'offsetof(DvrFrameParams,partialCullToBounds),offsetof(DvrFrameBuffers,depthMirror),sizeof(DvrSlabExchange),offsetof(DvrSlabExchange,timing));return 0;}\n')
+                   'offsetof(DvrFrameParams,partialCullToBounds),offsetof(DvrFrameBuffers,depthMirror),sizeof(DvrSlabExchange),offsetof(DvrSlabExchange,timing));'
+                   'printf("%zu %zu %zu %zu %zu\\n",sizeof(DvrSurfaceDesc),offsetof(DvrSurfaceDesc,objectToWorld),sizeof(DvrLight),sizeof(DvrSceneParams),offsetof(DvrSceneParams,cullTriangleBackfaces));return 0;}\n')
     exe = tmp_path / "sizes"
     subprocess.run(["gcc", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)], check=True)
     want = [int(v) for v in subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.split()]
     got = [C.sizeof(capi.DvrCamera), C.sizeof(capi.DvrVolumeInstance), C.sizeof(capi.DvrFrameBuffers),
            C.sizeof(capi.DvrFrameParams), C.sizeof(capi.DvrRenderStats), C.sizeof(capi.DvrPeerSync),
            capi.DvrFrameParams.backgroundImage.offset, capi.DvrFrameParams.partialCullToBounds.offset,
-           capi.DvrFrameBuffers.depthMirror.offset, C.sizeof(capi.DvrSlabExchange), capi.DvrSlabExchange.timing.offset]
+           capi.DvrFrameBuffers.depthMirror.offset, C.sizeof(capi.DvrSlabExchange), capi.DvrSlabExchange.timing.offset,
+           C.sizeof(capi.DvrSurfaceDesc), capi.DvrSurfaceDesc.objectToWorld.offset, C.sizeof(capi.DvrLight),
+           C.sizeof(capi.DvrSceneParams), capi.DvrSceneParams.cullTriangleBackfaces.offset]
     assert got == want
     assert C.sizeof(capi.DvrCamera) == 4 + 16 + 12 * 6 + 8 and C.sizeof(capi.DvrFrameParams) == 96
 
@@ -104,6 +107,9 @@ def test_compute_entries_fail_loudly_without_a_gpu():
     with pytest.raises(capi.DvrError) as e:
         capi.render(p, cam, inst, n, fb)
     assert e.value.code == capi.DVR_ERR_NO_DEVICE
+    with pytest.raises(capi.DvrError) as e:
+        capi.Surfaces.create([{"geometry": "sphere", "vertex.position": [(0.0, 0.0, 0.0)]}])
+    assert e.value.code == capi.DVR_ERR_NO_DEVICE and "no CPU fallback" in str(e.value)
 
 
 def test_invalid_arguments_are_rejected():

@@ -14,6 +14,7 @@ LIB_PATH = os.environ.get("DVR_B200_LIB") or os.path.join(_HERE, "libdvr_b200.so
 
 from .pods import *  # noqa: F401,F403  (enums, POD structs, frame_params / frame_buffers / peer_sync)
 from .pods import DvrCamera, DvrVolumeInstance, DvrFrameBuffers, DvrFrameParams, DvrRenderStats, DvrPeerSync, DvrSlabExchange
+from .pods import DvrSurfaceDesc, DvrLight, DvrSceneParams, surface_descs, scene_params
 
 # every symbol include/dvr_b200.h declares (tests check the library exports all of them)
 EXPORTED_SYMBOLS = [
@@ -28,6 +29,7 @@ EXPORTED_SYMBOLS = [
     "dvr_post_convert_float_color", "dvr_post_composite_depth", "dvr_post_outline", "dvr_post_visualize_depth",
     "dvr_post_pick", "dvr_selftest_lattice_advance", "dvr_bounds_screen_rect",
     "dvr_render", "dvr_render_instrumented", "dvr_launch_count",
+    "dvr_surfaces_create", "dvr_surfaces_destroy", "dvr_surfaces_info", "dvr_render_scene",
     "dvr_render_partial", "dvr_render_partial_instrumented", "dvr_composite_over", "dvr_resolve", "dvr_scale_vec3",
     "dvr_composite_resolve_peers", "dvr_render_partial_sync", "dvr_composite_resolve_peers_sync", "dvr_wait_flags",
     "dvr_render_slab_frame",
@@ -296,6 +298,36 @@ def render(params: DvrFrameParams, camera: DvrCamera, instances, n_instances: in
            stream: int = 0) -> None:
     _check(lib.dvr_render(C.byref(params), C.byref(camera), instances, C.c_uint32(n_instances), C.byref(buffers),
                           C.c_void_p(stream)))
+
+
+class Surfaces:
+    """DvrSurfaces handle: the flattened world's surfaces (geometry + matte material + instance transform) and their BVH."""
+
+    def __init__(self, handle):
+        self.handle = handle
+
+    @staticmethod
+    def create(surfaces, stream: int = 0) -> "Surfaces":
+        arr, keep = surface_descs(surfaces)
+        h = C.c_void_p()
+        _check(lib.dvr_surfaces_create(arr, C.c_uint32(len(surfaces)), C.c_void_p(stream), C.byref(h)))
+        del keep
+        return Surfaces(h)
+
+    def info(self):
+        n, m = C.c_uint32(), C.c_uint32()
+        _check(lib.dvr_surfaces_info(self.handle, C.byref(n), C.byref(m)))
+        return n.value, m.value
+
+    def destroy(self):
+        if self.handle:
+            _check(lib.dvr_surfaces_destroy(self.handle))
+            self.handle = None
+
+
+def render_scene(params, camera, instances, n_instances: int, scene: DvrSceneParams, buffers, stream: int = 0):
+    _check(lib.dvr_render_scene(C.byref(params), C.byref(camera), instances, C.c_uint32(n_instances), C.byref(scene),
+                                C.byref(buffers), C.c_void_p(stream)))
 
 
 def render_instrumented(params, camera, instances, n_instances, buffers, stats_dev_ptr: int, stream: int = 0):

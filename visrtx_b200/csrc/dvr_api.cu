@@ -1368,7 +1368,8 @@ static bool screenRectOfBox(const DvrCamera *c, const float3 lo, const float3 hi
 }
 
 static int renderImpl(const DvrFrameParams *p, const DvrCamera *camera, const DvrVolumeInstance *instances,
-    uint32_t nInstances, const DvrFrameBuffers *b, DvrRenderStats *statsDev, bool stats, void *stream)
+    uint32_t nInstances, const DvrFrameBuffers *b, DvrRenderStats *statsDev, bool stats, void *stream,
+    const DvrSceneParams *scene = nullptr)
 {
   if (!p || !camera || !b || (nInstances && !instances)) {
     setError("dvr_render: null argument");
@@ -1395,6 +1396,12 @@ static int renderImpl(const DvrFrameParams *p, const DvrCamera *camera, const Dv
   if (stats && !statsDev) {
     setError("dvr_render_instrumented: statsDev is null");
     return DVR_ERR_INVALID_ARGUMENT;
+  }
+  // a world with surfaces takes the mixed-scene kernel (dvr_scene.cu); without any it is the plain volume frame
+  const bool hasSurfaces = sceneHasSurfaces(scene);
+  if (hasSurfaces && p->integrator != DVR_INTEGRATOR_RAYCAST && p->integrator != DVR_INTEGRATOR_DEFAULT) {
+    setError("dvr_render_scene: surfaces are rendered by the raycast and default integrators only");
+    return DVR_ERR_UNSUPPORTED;
   }
   cudaStream_t s = (cudaStream_t)stream;
 
@@ -1444,7 +1451,8 @@ static int renderImpl(const DvrFrameParams *p, const DvrCamera *camera, const Dv
 
   // background-only pixels without ray set-up (marching integrators; not when the ray direction is an output)
   L.missValid = 0;
-  if ((p->integrator == DVR_INTEGRATOR_RAYCAST || p->integrator == DVR_INTEGRATOR_DEFAULT) && !b->normal) {
+  if ((p->integrator == DVR_INTEGRATOR_RAYCAST || p->integrator == DVR_INTEGRATOR_DEFAULT) && !b->normal
+      && !hasSurfaces) {
     int u[4] = {(int)p->width, (int)p->height, 0, 0};
     bool ok = true;
     for (uint32_t i = 0; i < nInstances && ok; ++i) {
@@ -1544,7 +1552,9 @@ static int renderImpl(const DvrFrameParams *p, const DvrCamera *camera, const Dv
       if (rc == DVR_OK && sweepFirst)
         rc = enqueueBackgroundSweep(L);
     }
-    if (rc == DVR_OK) {
+    if (rc == DVR_OK && hasSurfaces)
+      rc = launchSceneFrame(L, scene, skip && nInstances > 0, s);
+    else if (rc == DVR_OK) {
       if (nInstances == 0) {
         // a world without volumes still clears to the background (Raycast_ptx.cu:139-166 with no hit)
         L.nInst = 0;
@@ -1582,6 +1592,16 @@ int dvr_render_instrumented(const DvrFrameParams *params, const DvrCamera *camer
     DvrRenderStats *statsDev, void *stream)
 {
   return renderImpl(params, camera, instances, nInstances, buffers, statsDev, true, stream);
+}
+
+int dvr_render_scene(const DvrFrameParams *params, const DvrCamera *camera, const DvrVolumeInstance *instances,
+    uint32_t nInstances, const DvrSceneParams *scene, const DvrFrameBuffers *buffers, void *stream)
+{
+  if (!scene) {
+    setError("dvr_render_scene: null scene parameters");
+    return DVR_ERR_INVALID_ARGUMENT;
+  }
+  return renderImpl(params, camera, instances, nInstances, buffers, nullptr, false, stream, scene);
 }
 
 // ---- sort-last -------------------------------------------------------------------------------------------

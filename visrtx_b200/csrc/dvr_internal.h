@@ -155,6 +155,9 @@ cudaError_t scratchAllocAsync(void **p, size_t bytes, cudaStream_t stream);
 // launchers (defined in the .cu files) --------------------------------------------------------
 int launchFrame(const FrameLaunch &p, bool skip, bool stats, cudaStream_t s);
 int launchBackgroundSweep(const FrameLaunch &p, cudaStream_t s);
+// mixed scenes (dvr_scene.cu): a world that also holds surfaces and lights
+bool sceneHasSurfaces(const DvrSceneParams *scene);
+int launchSceneFrame(const FrameLaunch &p, const DvrSceneParams *scene, bool skip, cudaStream_t s);
 int launchPartial(const PartialLaunch &p, cudaStream_t s);
 int launchResolve(const ResolveLaunch &p, cudaStream_t s);
 int launchCompositeOver(float4 *front, float *frontDepth, const float4 *back, const float *backDepth,

@@ -387,9 +387,9 @@ template <bool SKIP, bool SLAB, bool STATS, bool SINGLE, int KIND, int G = 1, ty
 __device__ __forceinline__ float rayMarchAllVolumes(const InstanceDev *__restrict__ inst, const int nInst,
     TfSelect tfOf, const float3 org, const float3 dir, const float tfar, const float invSamplingRate,
     Philox &rng, float3 &color, float &opacity, uint32_t &objID, uint32_t &instID, MarchStats &stats,
-    unsigned int *cellBitmap, bool &anyHit)
+    unsigned int *cellBitmap, bool &anyHit, const float tnear = 0.f)
 {
-  float rayLower = 0.f;
+  float rayLower = tnear; // ray.t.lower of the caller: 0 for a fresh primary ray, past the last surface otherwise
   const float rayUpper = tfar;
   float depth = tfar;
   bool firstHit = true;

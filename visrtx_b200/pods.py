@@ -22,6 +22,13 @@ DVR_INTEGRATOR_RAYCAST, DVR_INTEGRATOR_DEFAULT, DVR_INTEGRATOR_DPT, DVR_INTEGRAT
 DVR_SKIP_OFF, DVR_SKIP_ON, DVR_SKIP_AUTO = 0, 1, 2
 
 DVR_IMAGE_FLOAT32, DVR_IMAGE_UFIXED8, DVR_IMAGE_UFIXED16, DVR_IMAGE_UFIXED32, DVR_IMAGE_SRGB8 = range(5)
+DVR_GEOMETRY_TRIANGLE, DVR_GEOMETRY_SPHERE = 0, 1
+DVR_ALPHA_OPAQUE, DVR_ALPHA_BLEND, DVR_ALPHA_MASK = 0, 1, 2
+DVR_LIGHT_DIRECTIONAL, DVR_LIGHT_POINT = 0, 1
+
+
+IDENTITY_3X4 = (1.0, 0.0, 0.0, 0.0, 0.0, 1.0, 0.0, 0.0, 0.0, 0.0, 1.0, 0.0)
+_f4 = C.c_float * 4
 
 
 class DvrCamera(C.Structure):
@@ -68,6 +75,96 @@ class DvrSlabExchange(C.Structure):
                 ("waitAllResolved", C.c_int32), ("_pad", C.c_int32), ("timing", C.c_void_p)]
 
 
+class DvrSurfaceDesc(C.Structure):
+    _fields_ = [("geometryType", C.c_int32), ("nVertices", C.c_uint32), ("vertexPosition", C.c_void_p),
+                ("nPrimitives", C.c_uint32), ("index", C.c_void_p), ("vertexNormal", C.c_void_p),
+                ("vertexRadius", C.c_void_p), ("radius", C.c_float), ("primitiveId", C.c_void_p),
+                ("cullBackfaces", C.c_int32), ("color", C.c_float * 4), ("opacity", C.c_float),
+                ("alphaMode", C.c_int32), ("alphaCutoff", C.c_float), ("surfaceId", C.c_uint32),
+                ("instanceId", C.c_uint32), ("objectToWorld", C.c_float * 12)]
+
+
+class DvrLight(C.Structure):
+    _fields_ = [("type", C.c_int32), ("color", C.c_float * 3), ("vec", C.c_float * 3), ("strength", C.c_float)]
+
+
+class DvrSceneParams(C.Structure):
+    _fields_ = [("surfaces", C.c_void_p), ("lights", C.c_void_p), ("nLights", C.c_uint32),
+                ("ambientColor", C.c_float * 3), ("ambientRadiance", C.c_float), ("occlusionDistance", C.c_float),
+                ("ambientSamples", C.c_int32), ("cullTriangleBackfaces", C.c_int32)]
+
+
+def surface_descs(surfaces):
+    """(DvrSurfaceDesc array, keep-alive list) from dicts with the ANARI parameter names: geometry ('triangle' |
+    'sphere'), vertex.position, primitive.index, vertex.normal, vertex.radius, radius, primitive.id, cullBackfaces,
+    color (3 or 4), opacity, alphaMode, alphaCutoff, id, instanceId, transform (row-major 3x4 object->world)."""
+    import numpy as np
+    arr = (DvrSurfaceDesc * max(len(surfaces), 1))()
+    keep = []
+
+    def ptr(a, dtype):
+        if a is None:
+            return None
+        a = np.ascontiguousarray(a, dtype)
+        keep.append(a)
+        return a.ctypes.data
+
+    for i, sdef in enumerate(surfaces):
+        d = arr[i]
+        tri = sdef.get("geometry", "triangle") == "triangle"
+        d.geometryType = DVR_GEOMETRY_TRIANGLE if tri else DVR_GEOMETRY_SPHERE
+        pos = np.ascontiguousarray(sdef["vertex.position"], np.float32).reshape(-1, 3)
+        d.nVertices = pos.shape[0]
+        d.vertexPosition = ptr(pos, np.float32)
+        idx = sdef.get("primitive.index")
+        if idx is not None:
+            idx = np.ascontiguousarray(idx, np.uint32).reshape(-1, 3 if tri else 1)
+            d.nPrimitives = idx.shape[0]
+        else:
+            d.nPrimitives = pos.shape[0] // 3 if tri else pos.shape[0]
+        d.index = ptr(idx, np.uint32)
+        d.vertexNormal = ptr(sdef.get("vertex.normal"), np.float32)
+        d.vertexRadius = ptr(sdef.get("vertex.radius"), np.float32)
+        d.radius = float(sdef.get("radius", 0.01))
+        d.primitiveId = ptr(sdef.get("primitive.id"), np.uint32)
+        d.cullBackfaces = 1 if sdef.get("cullBackfaces", False) else 0
+        col = list(sdef.get("color", (0.8, 0.8, 0.8, 1.0)))
+        if len(col) == 3:
+            col.append(1.0)
+        d.color = _f4(*col)
+        d.opacity = float(sdef.get("opacity", 1.0))
+        d.alphaMode = {"opaque": DVR_ALPHA_OPAQUE, "blend": DVR_ALPHA_BLEND, "mask": DVR_ALPHA_MASK}[
+            sdef.get("alphaMode", "opaque")]
+        d.alphaCutoff = float(sdef.get("alphaCutoff", 0.5))
+        d.surfaceId = int(sdef.get("id", 0xFFFFFFFF))
+        d.instanceId = int(sdef.get("instanceId", 0xFFFFFFFF))
+        d.objectToWorld = (C.c_float * 12)(*sdef.get("transform", IDENTITY_3X4))
+    return arr, keep
+
+
+def scene_params(surfaces_handle=None, lights=(), ambient_color=(1.0, 1.0, 1.0), ambient_radiance=0.0,
+                 occlusion_distance=1e20, ambient_samples=1, cull_triangle_backfaces=False):
+    """(DvrSceneParams, keep-alive) — lights: dicts {type: 'directional'|'point', color, direction|position,
+    irradiance|intensity}."""
+    p = DvrSceneParams()
+    larr = (DvrLight * max(len(lights), 1))()
+    for i, l in enumerate(lights):
+        point = l.get("type", "directional") == "point"
+        larr[i].type = DVR_LIGHT_POINT if point else DVR_LIGHT_DIRECTIONAL
+        larr[i].color = (C.c_float * 3)(*l.get("color", (1.0, 1.0, 1.0)))
+        larr[i].vec = (C.c_float * 3)(*(l["position"] if point else l["direction"]))
+        larr[i].strength = float(l.get("intensity", 1.0) if point else l.get("irradiance", 1.0))
+    p.surfaces = surfaces_handle
+    p.lights = C.cast(larr, C.c_void_p)
+    p.nLights = len(lights)
+    p.ambientColor = (C.c_float * 3)(*ambient_color)
+    p.ambientRadiance = float(ambient_radiance)
+    p.occlusionDistance = float(occlusion_distance)
+    p.ambientSamples = int(ambient_samples)
+    p.cullTriangleBackfaces = 1 if cull_triangle_backfaces else 0
+    return p, larr
+
+
 def peer_sync(signal_ptrs=(), signal_value=0, wait_ptr=0, n_wait=0, wait_value=0, error_flag=0) -> "DvrPeerSync":
     s = DvrPeerSync()
     s.nSignal, s.signalValue = len(signal_ptrs), int(signal_value) & 0xFFFFFFFF
@@ -78,10 +175,6 @@ def peer_sync(signal_ptrs=(), signal_value=0, wait_ptr=0, n_wait=0, wait_value=0
     return s
 
 
-IDENTITY_3X4 = (1.0, 0.0, 0.0, 0.0, 0.0, 1.0, 0.0, 0.0, 0.0, 0.0, 1.0, 0.0)
-
-
-_f4 = C.c_float * 4
 
 
 def frame_params(width, height, fmt=DVR_FORMAT_UFIXED8_RGBA_SRGB, integrator=DVR_INTEGRATOR_RAYCAST, frame_id=0,
