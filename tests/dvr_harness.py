@@ -638,7 +638,10 @@ def _uv_sphere_mesh(center, radius, nu=12, nv=8):
 def mixed_scene_zoo(wh=96):
     """name -> SceneDesc: the surface branch of the default / raycast renderers around a 32^3 volume on [-1,1]^3"""
     zoo = {}
-    sun = {"type": "directional", "direction": (-0.3, -1.0, -0.2), "irradiance": 2.5, "color": (1.0, 0.95, 0.9)}
+    sdir = np.array((-0.3, -1.0, -0.2), np.float32)  # normalised as Directional::commitParameters does (fp32)
+    sdir = sdir * (np.float32(1.0) / np.sqrt(np.float32(sdir[0] * sdir[0] + sdir[1] * sdir[1] + sdir[2] * sdir[2])))
+    sun = {"type": "directional", "direction": tuple(float(c) for c in sdir), "irradiance": 2.5,
+           "color": (1.0, 0.95, 0.9)}
     lamp = {"type": "point", "position": (1.6, 1.8, 1.2), "intensity": 6.0}
     floor = {"geometry": "triangle", "vertex.position": _quad((-3, -1.3, -3), (-3, -1.3, 3), (3, -1.3, 3), (3, -1.3, -3)),
              "color": (0.7, 0.7, 0.75), "id": 11, "instanceId": 21}

@@ -267,7 +267,17 @@ def test_introspection_of_the_scene_objects_matches_what_the_device_reads():
     # objects without subtypes answer for any subtype string
     assert par(A.FRAME, None)["channel.color"] == A.DATA_TYPE and par(A.FRAME, "")["size"] == A.UINT32_VEC2
     assert pi(A.FRAME, None, "size", A.UINT32_VEC2, "default") == (10, 10)
-    assert set(par(A.WORLD, None)) == {"name", "volume", "instance"}
+    assert set(par(A.WORLD, None)) == {"name", "volume", "surface", "light", "instance"}
+    # mixed scenes: the geometry / material / light subtypes the device renders
+    assert d.subtypes(A.GEOMETRY) == ["triangle", "sphere"] and d.subtypes(A.MATERIAL) == ["matte"]
+    assert d.subtypes(A.LIGHT) == ["directional", "point"]
+    assert par(A.GEOMETRY, "triangle")["primitive.index"] == A.ARRAY1D
+    assert pi(A.GEOMETRY, "triangle", "primitive.index", A.ARRAY1D, "elementType", A.DATA_TYPE_LIST) == [A.UINT32_VEC3]
+    assert abs(pi(A.GEOMETRY, "sphere", "radius", A.FLOAT32, "default") - 0.01) < 1e-9
+    assert pi(A.MATERIAL, "matte", "alphaMode", A.STRING, "value", A.STRING_LIST) == ["opaque", "blend", "mask"]
+    assert pi(A.LIGHT, "directional", "direction", A.FLOAT32_VEC3, "default") == (0.0, 0.0, -1.0)
+    assert pi(A.RENDERER, "default", "ambientSamples", A.INT32, "default") == 1
+    assert set(par(A.SURFACE, None)) == {"name", "geometry", "material", "id"}
     assert pi(A.INSTANCE, "transform", "transform", A.FLOAT32_MAT4, "default")[::5] == (1.0, 1.0, 1.0, 1.0)
     # descriptions and source extensions
     assert "NanoVDB" in d.object_info(A.SPATIAL_FIELD, "nanovdb", "description", A.STRING)
@@ -281,7 +291,56 @@ def test_introspection_of_the_scene_objects_matches_what_the_device_reads():
     assert dev["cudaDevice"] == A.INT32 and dev["forceInit"] == A.BOOL and dev["statusCallback"] == A.STATUS_CALLBACK
     assert pi(A.DEVICE, None, "cudaDevice", A.INT32, "default") == 0
     # every advertised subtype of every object type has a parameter list
-    for t in (A.CAMERA, A.SPATIAL_FIELD, A.VOLUME, A.RENDERER, A.INSTANCE):
+    for t in (A.CAMERA, A.SPATIAL_FIELD, A.VOLUME, A.RENDERER, A.INSTANCE, A.GEOMETRY, A.MATERIAL, A.LIGHT):
         for st in d.subtypes(t):
             assert d.object_info(t, st, "parameter", A.PARAMETER_LIST), (t, st)
+    d.close()
+
+
+def test_surface_objects_validate_their_parameters_and_extend_the_world_bounds():
+    """Geometry / Material / Surface / Light objects of mixed scenes: commit-time validation with the
+    reference's messages (Triangle.cpp:59-78, Surface.cpp:49-58) and World 'bounds' over surfaces — no GPU needed."""
+    d = A.Device()
+    g = d.new("Geometry", "triangle")
+    d.set(g, "vertex.position", A.ARRAY1D, d.new_array1d(np.zeros((4, 3), np.float32), A.FLOAT32_VEC3))
+    d.commit(g)
+    s = d.new("Surface")
+    d.set(s, "geometry", A.GEOMETRY, g)
+    d.commit(s)
+    w = d.new("World")
+    d.set(w, "surface", A.ARRAY1D, d.new_object_array([s], A.SURFACE))
+    d.commit(w)
+    b = d.get_property(w, "bounds", A.FLOAT32_BOX3)
+    msgs = " | ".join(m[2] for m in d.messages)
+    assert "non-multiple of 3" in msgs and "missing 'material' on ANARISurface" in msgs
+    assert b[0] > b[3]  # nothing valid in the world: the empty box
+    # a valid sphere surface under an instance transform
+    g2 = d.new("Geometry", "sphere")
+    d.set(g2, "vertex.position", A.ARRAY1D, d.new_array1d(np.array([[1, 2, 3], [-1, 0, 0]], np.float32), A.FLOAT32_VEC3))
+    d.set(g2, "radius", A.FLOAT32, 0.5)
+    d.commit(g2)
+    m = d.new("Material", "matte")
+    d.commit(m)
+    s2 = d.new("Surface")
+    d.set(s2, "geometry", A.GEOMETRY, g2)
+    d.set(s2, "material", A.MATERIAL, m)
+    d.commit(s2)
+    grp = d.new("Group")
+    d.set(grp, "surface", A.ARRAY1D, d.new_object_array([s2], A.SURFACE))
+    d.commit(grp)
+    inst = d.new("Instance", "transform")
+    d.set(inst, "group", A.GROUP, grp)
+    d.set(inst, "transform", A.FLOAT32_MAT3x4, (1, 0, 0, 0, 1, 0, 0, 0, 1, 10, 0, 0))  # translate x by 10
+    d.commit(inst)
+    d.set(w, "instance", A.ARRAY1D, d.new_object_array([inst], A.INSTANCE))
+    d.commit(w)
+    b = d.get_property(w, "bounds", A.FLOAT32_BOX3)
+    assert np.allclose(b, (8.5, -0.5, -0.5, 11.5, 2.5, 3.5))
+    d2 = d.new("Geometry", "cone")
+    d.commit(d2)
+    lt = d.new("Light", "hdri")
+    d.commit(lt)
+    d.get_property(w, "bounds", A.FLOAT32_BOX3)
+    msgs = " | ".join(m[2] for m in d.messages)
+    assert "geometry subtype 'cone' is not rendered" in msgs and "light subtype 'hdri' is not rendered" in msgs
     d.close()

@@ -22,7 +22,8 @@ STRING_LIST, DATA_TYPE_LIST, PARAMETER_LIST = 150, 151, 152
 STATUS_CALLBACK, FRAME_COMPLETION_CALLBACK = 202, 203
 DEVICE, ARRAY1D, ARRAY2D, ARRAY3D, CAMERA, FRAME, GROUP, INSTANCE, RENDERER, SPATIAL_FIELD, VOLUME, WORLD = (
     501, 504, 505, 506, 507, 508, 510, 511, 514, 517, 518, 519)
-UINT8, INT32, UINT32, UINT32_VEC2, UINT64 = 1004, 1016, 1020, 1021, 1028
+GEOMETRY, LIGHT, MATERIAL, SURFACE, SAMPLER = 509, 512, 513, 515, 516
+UINT8, INT32, UINT32, UINT32_VEC2, UINT32_VEC3, UINT64 = 1004, 1016, 1020, 1021, 1022, 1028
 FIXED8, UFIXED8, UFIXED8_VEC4, FIXED16, UFIXED16 = 1032, 1036, 1039, 1040, 1044
 UFIXED8_VEC3, UFIXED16_VEC2 = 1038, 1045
 FLOAT16, FLOAT32, FLOAT32_VEC2, FLOAT32_VEC3, FLOAT32_VEC4, FLOAT64 = 1064, 1068, 1069, 1070, 1071, 1072

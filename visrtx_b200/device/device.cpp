@@ -415,6 +415,13 @@ void Frame::renderFrame()
   m_invFrameID = 1.f / (m_frameID + 1);
 
   const std::vector<FlatInstance> flat = m_world->flatten(true);
+  // surfaces in the world: the frame takes the mixed-scene launch (marching renderers only)
+  DvrSurfaces *surfaceSet = nullptr;
+  if (m_renderer->integrator == DVR_INTEGRATOR_RAYCAST || m_renderer->integrator == DVR_INTEGRATOR_DEFAULT)
+    surfaceSet = m_world->surfaceSet(true);
+  else if (m_world->surfaceSet(false))
+    report(ANARI_SEVERITY_WARNING, ANARI_STATUS_INVALID_OPERATION,
+        "the '%s' renderer of this device draws volumes only: the world's surfaces are ignored", m_renderer->subtype.c_str());
 
   DvrFrameParams p;
   std::memset(&p, 0, sizeof(p));
@@ -458,7 +465,34 @@ void Frame::renderFrame()
   // renderer, one sample per pixel-pass, no per-GPU auxiliary accumulations (albedo / normal) and no background
   // texture (texture objects are per GPU); sort-last additionally needs a single slabbed structuredRegular volume.
   bool done = false;
-  if (device->gpuCount() > 1) {
+  if (surfaceSet) { // mixed scene: one GPU (the display GPU), dvr_render_scene
+    std::vector<DvrVolumeInstance> inst;
+    for (size_t i = 0; i < flat.size(); ++i) {
+      DvrVolumeInstance in;
+      in.volume = flat[i].volume->whole();
+      if (!in.volume)
+        continue;
+      std::memcpy(in.worldToObject, flat[i].worldToObject, sizeof(in.worldToObject));
+      in.instanceId = flat[i].instId;
+      in._pad = 0;
+      inst.push_back(in);
+    }
+    const std::vector<DvrLight> lights = m_world->flattenLights();
+    DvrSceneParams sp;
+    std::memset(&sp, 0, sizeof(sp));
+    sp.surfaces = surfaceSet;
+    sp.lights = lights.data();
+    sp.nLights = (uint32_t)lights.size();
+    std::memcpy(sp.ambientColor, m_renderer->ambientColor, sizeof(sp.ambientColor));
+    sp.ambientRadiance = m_renderer->ambientRadiance;
+    sp.occlusionDistance = m_renderer->occlusionDistance;
+    sp.ambientSamples = m_renderer->ambientSamples;
+    sp.cullTriangleBackfaces = m_renderer->cullTriangleBackfaces ? 1 : 0;
+    const int rc = dvr_render_scene(&p, &m_camera->cam, inst.data(), (uint32_t)inst.size(), &sp, &b, stream);
+    if (rc != DVR_OK)
+      report(ANARI_SEVERITY_FATAL_ERROR, ANARI_STATUS_UNKNOWN_ERROR, "dvr_render_scene failed: %s", dvr_last_error());
+    done = true;
+  } else if (device->gpuCount() > 1) {
     const bool marching = p.integrator == DVR_INTEGRATOR_RAYCAST || p.integrator == DVR_INTEGRATOR_DEFAULT;
     const bool plain = marching && !m_albedoAccum && !m_normalAccum && !p.backgroundImage && p.tileRanks <= 1;
     bool allDistributed = !flat.empty();
@@ -859,6 +893,8 @@ static const char *kExtensions[] = {"ANARI_KHR_CAMERA_ORTHOGRAPHIC", "ANARI_KHR_
     "ANARI_KHR_VOLUME_TRANSFER_FUNCTION1D", "ANARI_VISRTX_SPATIAL_FIELD_NANOVDB", "ANARI_KHR_RENDERER_BACKGROUND_COLOR", "ANARI_KHR_DEVICE_SYNCHRONIZATION",
     "ANARI_NV_ARRAY_CUDA", "ANARI_NV_FRAME_BUFFERS_CUDA", "ANARI_VISRTX_CUDA_OUTPUT_BUFFERS", "ANARI_VISRTX_ARRAY_CUDA",
     "ANARI_KHR_CAMERA_DEPTH_OF_FIELD", "ANARI_KHR_RENDERER_AMBIENT_LIGHT", "ANARI_KHR_ARRAY1D_REGION",
+    "ANARI_KHR_GEOMETRY_TRIANGLE", "ANARI_KHR_GEOMETRY_SPHERE", "ANARI_KHR_MATERIAL_MATTE", "ANARI_KHR_LIGHT_DIRECTIONAL",
+    "ANARI_KHR_LIGHT_POINT",
     "ANARI_VISRTX_B200_DVR", nullptr};
 
 bool Device::getProperty(const std::string &name, ANARIDataType t, void *mem, uint64_t size, uint32_t)
@@ -1009,11 +1045,11 @@ void anariUnmapArray(ANARIDevice d, ANARIArray a)
 }
 
 // ---- objects ----
-ANARILight anariNewLight(ANARIDevice d, const char *t) { return make<Object>(d, ANARI_LIGHT, std::string(t ? t : "")); }
-ANARIGeometry anariNewGeometry(ANARIDevice d, const char *t) { return make<Object>(d, ANARI_GEOMETRY, std::string(t ? t : "")); }
-ANARIMaterial anariNewMaterial(ANARIDevice d, const char *t) { return make<Object>(d, ANARI_MATERIAL, std::string(t ? t : "")); }
+ANARILight anariNewLight(ANARIDevice d, const char *t) { return make<Light>(d, std::string(t ? t : "")); }
+ANARIGeometry anariNewGeometry(ANARIDevice d, const char *t) { return make<Geometry>(d, std::string(t ? t : "")); }
+ANARIMaterial anariNewMaterial(ANARIDevice d, const char *t) { return make<Material>(d, std::string(t ? t : "")); }
 ANARISampler anariNewSampler(ANARIDevice d, const char *t) { return make<Object>(d, ANARI_SAMPLER, std::string(t ? t : "")); }
-ANARISurface anariNewSurface(ANARIDevice d) { return make<Object>(d, ANARI_SURFACE, std::string()); }
+ANARISurface anariNewSurface(ANARIDevice d) { return make<Surface>(d); }
 ANARICamera anariNewCamera(ANARIDevice d, const char *t) { return make<Camera>(d, std::string(t ? t : "")); }
 ANARISpatialField anariNewSpatialField(ANARIDevice d, const char *t) { return make<SpatialField>(d, std::string(t ? t : "")); }
 ANARIVolume anariNewVolume(ANARIDevice d, const char *t) { return make<Volume>(d, std::string(t ? t : "")); }

@@ -825,8 +825,144 @@ DvrVolume *Volume::whole()
 // ---------------------------------------------------------------------------------------------------------
 // Group / Instance / World
 // ---------------------------------------------------------------------------------------------------------
+// ---------------------------------------------------------------------------------------------------------
+// Geometry / Material / Surface / Light
+// ---------------------------------------------------------------------------------------------------------
+Geometry::Geometry(Device *d, const std::string &st) : Object(d, ANARI_GEOMETRY, st)
+{
+  kind = st == "triangle" ? DVR_GEOMETRY_TRIANGLE : (st == "sphere" ? DVR_GEOMETRY_SPHERE : -1);
+}
+
+void Geometry::commitParameters()
+{
+  auto typed = [this](const char *name, ANARIDataType want) -> Array * {
+    Array *a = static_cast<Array *>(getParamObject(name, ANARI_ARRAY1D));
+    if (a && a->elementType != want) {
+      report(ANARI_SEVERITY_WARNING, ANARI_STATUS_INVALID_ARGUMENT, "'%s' on %s geometry has element type %s, expected %s",
+          name, subtype.c_str(), typeName(a->elementType), typeName(want));
+      return nullptr;
+    }
+    if (a && a->onDevice()) {
+      report(ANARI_SEVERITY_WARNING, ANARI_STATUS_INVALID_ARGUMENT,
+          "'%s' on %s geometry lives in device memory: geometry arrays must be host arrays", name, subtype.c_str());
+      return nullptr;
+    }
+    return a;
+  };
+  if (kind < 0) {
+    report(ANARI_SEVERITY_WARNING, ANARI_STATUS_INVALID_ARGUMENT,
+        "geometry subtype '%s' is not rendered by this device (triangle and sphere are)", subtype.c_str());
+    return;
+  }
+  const bool tri = kind == DVR_GEOMETRY_TRIANGLE;
+  m_vertex.reset(typed("vertex.position", ANARI_FLOAT32_VEC3));
+  m_index.reset(typed("primitive.index", tri ? ANARI_UINT32_VEC3 : ANARI_UINT32));
+  m_normal.reset(tri ? typed("vertex.normal", ANARI_FLOAT32_VEC3) : nullptr);
+  m_radius.reset(tri ? nullptr : typed("vertex.radius", ANARI_FLOAT32));
+  m_primId.reset(typed("primitive.id", ANARI_UINT32));
+  radius = getParam<float>("radius", ANARI_FLOAT32, 0.01f);
+  cullBackfaces = getParam<int32_t>("cullBackfaces", ANARI_BOOL, 0) != 0;
+  if (!m_vertex)
+    report(ANARI_SEVERITY_WARNING, ANARI_STATUS_INVALID_ARGUMENT, "missing required parameter 'vertex.position' on %s geometry",
+        subtype.c_str());
+  else if (tri && !m_index && m_vertex->regionSize() % 3 != 0) { // Triangle.cpp:64-70
+    report(ANARI_SEVERITY_ERROR, ANARI_STATUS_INVALID_ARGUMENT,
+        "'vertex.position' on triangle geometry is a non-multiple of 3 without 'primitive.index' present");
+    m_vertex.reset();
+  }
+  if (m_normal && m_vertex && m_normal->regionSize() != m_vertex->regionSize()) {
+    report(ANARI_SEVERITY_WARNING, ANARI_STATUS_INVALID_ARGUMENT,
+        "'vertex.normal' on triangle geometry not the same size as 'vertex.position'");
+    m_normal.reset();
+  }
+  if (m_radius && m_vertex && m_radius->regionSize() != m_vertex->regionSize())
+    m_radius.reset();
+  const size_t nPrims = m_index ? m_index->regionSize() : (m_vertex ? (tri ? m_vertex->regionSize() / 3 : m_vertex->regionSize()) : 0);
+  if (m_primId && m_primId->regionSize() < nPrims)
+    m_primId.reset();
+}
+
+Material::Material(Device *d, const std::string &st) : Object(d, ANARI_MATERIAL, st) {}
+
+void Material::commitParameters()
+{
+  color[0] = color[1] = color[2] = 0.8f;
+  color[3] = 1.f;
+  const bool pbr = subtype == "physicallyBased";
+  getParamRaw(pbr ? "baseColor" : "color", ANARI_FLOAT32_VEC4, color, 16);
+  getParamRaw(pbr ? "baseColor" : "color", ANARI_FLOAT32_VEC3, color, 12);
+  opacity = getParam<float>("opacity", ANARI_FLOAT32, 1.f);
+  alphaCutoff = getParam<float>("alphaCutoff", ANARI_FLOAT32, 0.5f);
+  const std::string mode = getParamString("alphaMode", "opaque");
+  alphaMode = mode == "blend" ? DVR_ALPHA_BLEND : (mode == "mask" ? DVR_ALPHA_MASK : DVR_ALPHA_OPAQUE);
+  if (subtype != "matte")
+    report(ANARI_SEVERITY_WARNING, ANARI_STATUS_INVALID_ARGUMENT,
+        "material subtype '%s' is shaded as matte by this device", subtype.c_str());
+  const Param *c = findParam(pbr ? "baseColor" : "color");
+  if (c && (c->type == ANARI_STRING || c->type == ANARI_SAMPLER))
+    report(ANARI_SEVERITY_WARNING, ANARI_STATUS_INVALID_ARGUMENT,
+        "material colour from an attribute or sampler is not built: the default colour is used");
+}
+
+Surface::Surface(Device *d) : Object(d, ANARI_SURFACE) {}
+
+void Surface::commitParameters()
+{
+  id = getParam<uint32_t>("id", ANARI_UINT32, ~0u);
+  m_geometry.reset(static_cast<Geometry *>(getParamObject("geometry", ANARI_GEOMETRY)));
+  m_material.reset(static_cast<Material *>(getParamObject("material", ANARI_MATERIAL)));
+  if (!m_material)
+    report(ANARI_SEVERITY_WARNING, ANARI_STATUS_INVALID_ARGUMENT, "missing 'material' on ANARISurface");
+  if (!m_geometry)
+    report(ANARI_SEVERITY_WARNING, ANARI_STATUS_INVALID_ARGUMENT, "missing 'geometry' on ANARISurface");
+}
+
+Light::Light(Device *d, const std::string &st) : Object(d, ANARI_LIGHT, st)
+{
+  kind = st == "directional" ? DVR_LIGHT_DIRECTIONAL : (st == "point" ? DVR_LIGHT_POINT : -1);
+}
+
+void Light::commitParameters()
+{
+  color[0] = color[1] = color[2] = 1.f;
+  getParamRaw("color", ANARI_FLOAT32_VEC3, color, 12);
+  if (kind == DVR_LIGHT_DIRECTIONAL) { // Directional.cpp:40-48
+    float d[3] = {0.f, 0.f, -1.f};
+    getParamRaw("direction", ANARI_FLOAT32_VEC3, d, 12);
+    const float inv = 1.f / std::sqrt(d[0] * d[0] + d[1] * d[1] + d[2] * d[2]);
+    for (int i = 0; i < 3; ++i)
+      vec[i] = d[i] * inv;
+    strength = std::max(getParam<float>("irradiance", ANARI_FLOAT32, 1.f), 0.f);
+  } else if (kind == DVR_LIGHT_POINT) { // Point.cpp:40-48
+    vec[0] = vec[1] = vec[2] = 0.f;
+    getParamRaw("position", ANARI_FLOAT32_VEC3, vec, 12);
+    strength = std::max(getParam<float>("intensity", ANARI_FLOAT32, getParam<float>("power", ANARI_FLOAT32, 1.f)), 0.f);
+  } else
+    report(ANARI_SEVERITY_WARNING, ANARI_STATUS_INVALID_ARGUMENT,
+        "light subtype '%s' is not rendered by this device (directional and point are)", subtype.c_str());
+}
+
 Group::Group(Device *d) : Object(d, ANARI_GROUP) {}
-void Group::commitParameters() { m_volumes.reset(static_cast<Array *>(getParamObject("volume", ANARI_ARRAY1D))); }
+void Group::commitParameters()
+{
+  m_volumes.reset(static_cast<Array *>(getParamObject("volume", ANARI_ARRAY1D)));
+  m_surfaces.reset(static_cast<Array *>(getParamObject("surface", ANARI_ARRAY1D)));
+  m_lights.reset(static_cast<Array *>(getParamObject("light", ANARI_ARRAY1D)));
+}
+template <typename T>
+static std::vector<T *> objectsOf(const Ref<Array> &a, ANARIDataType type)
+{
+  std::vector<T *> out;
+  if (a)
+    for (size_t i = 0; i < a->regionSize(); ++i) {
+      Object *o = a->regionObjectAt(i);
+      if (o && o->type == type)
+        out.push_back(static_cast<T *>(o));
+    }
+  return out;
+}
+std::vector<Surface *> Group::surfaces() const { return objectsOf<Surface>(m_surfaces, ANARI_SURFACE); }
+std::vector<Light *> Group::lights() const { return objectsOf<Light>(m_lights, ANARI_LIGHT); }
 std::vector<Volume *> Group::volumes() const
 {
   std::vector<Volume *> out;
@@ -863,10 +999,154 @@ void Instance::commitParameters()
 }
 
 World::World(Device *d) : Object(d, ANARI_WORLD) {}
+World::~World() { dropSurfaceSet(); }
 void World::commitParameters()
 {
   m_zeroVolumes.reset(static_cast<Array *>(getParamObject("volume", ANARI_ARRAY1D)));
   m_instances.reset(static_cast<Array *>(getParamObject("instance", ANARI_ARRAY1D)));
+  m_zeroSurfaces.reset(static_cast<Array *>(getParamObject("surface", ANARI_ARRAY1D)));
+  m_zeroLights.reset(static_cast<Array *>(getParamObject("light", ANARI_ARRAY1D)));
+}
+
+void World::dropSurfaceSet()
+{
+  if (!m_surfaceSet)
+    return;
+  GpuScope scope(m_surfaceSetGpu);
+  cudaDeviceSynchronize();
+  dvr_surfaces_destroy(m_surfaceSet);
+  m_surfaceSet = nullptr;
+  m_surfaceStamp = 0;
+}
+
+std::vector<World::FlatSurface> World::flattenSurfaces(bool warn) const
+{
+  std::vector<FlatSurface> out;
+  static const float ident[12] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0};
+  auto push = [&](Surface *s, const float *o2w, uint32_t instId) {
+    if (!s->isValid()) {
+      if (warn)
+        report(ANARI_SEVERITY_WARNING, ANARI_STATUS_INVALID_ARGUMENT, "skipping invalid surface in world");
+      return;
+    }
+    FlatSurface fs;
+    fs.surface = s;
+    std::memcpy(fs.objectToWorld, o2w, sizeof(fs.objectToWorld));
+    fs.instId = instId;
+    out.push_back(fs);
+  };
+  for (Surface *s : objectsOf<Surface>(m_zeroSurfaces, ANARI_SURFACE))
+    push(s, ident, ~0u);
+  for (Instance *in : objectsOf<Instance>(m_instances, ANARI_INSTANCE)) {
+    if (!in->isValid())
+      continue;
+    float rm[12]; // column-major 4x3 -> row-major 3x4
+    for (int r = 0; r < 3; ++r) {
+      rm[r * 4 + 0] = in->objectToWorld[0 * 3 + r];
+      rm[r * 4 + 1] = in->objectToWorld[1 * 3 + r];
+      rm[r * 4 + 2] = in->objectToWorld[2 * 3 + r];
+      rm[r * 4 + 3] = in->objectToWorld[9 + r];
+    }
+    for (Surface *s : in->group()->surfaces())
+      push(s, rm, in->id);
+  }
+  return out;
+}
+
+std::vector<DvrLight> World::flattenLights() const
+{
+  std::vector<DvrLight> out;
+  auto push = [&](const Light *l, const float *cm /*column-major 4x3 or null*/) {
+    if (!l->isValid())
+      return;
+    DvrLight d;
+    d.type = l->kind;
+    std::memcpy(d.color, l->color, sizeof(d.color));
+    d.strength = l->strength;
+    for (int r = 0; r < 3; ++r) {
+      if (!cm)
+        d.vec[r] = l->vec[r];
+      else // xfmVec for directions, xfmPoint for positions (gpu/gpu_math.h:314-322)
+        d.vec[r] = cm[0 * 3 + r] * l->vec[0] + cm[1 * 3 + r] * l->vec[1] + cm[2 * 3 + r] * l->vec[2]
+            + (l->kind == DVR_LIGHT_POINT ? cm[9 + r] : 0.f);
+    }
+    out.push_back(d);
+  };
+  for (Light *l : objectsOf<Light>(m_zeroLights, ANARI_LIGHT))
+    push(l, nullptr);
+  for (Instance *in : objectsOf<Instance>(m_instances, ANARI_INSTANCE))
+    if (in->isValid())
+      for (Light *l : in->group()->lights())
+        push(l, in->objectToWorld);
+  return out;
+}
+
+DvrSurfaces *World::surfaceSet(bool warn)
+{
+  const std::vector<FlatSurface> flat = flattenSurfaces(warn);
+  if (flat.empty()) {
+    dropSurfaceSet();
+    return nullptr;
+  }
+  // fingerprint: the finalisation stamps of everything the set is built from (+ identities and transforms)
+  uint64_t stamp = 1469598103934665603ull;
+  auto mix = [&stamp](uint64_t v) { stamp = (stamp ^ v) * 1099511628211ull; };
+  auto mixArray = [&](const Array *a) { mix(a ? a->lastFinalized + 1 : 0); mix((uint64_t)(uintptr_t)a); };
+  for (const FlatSurface &fs : flat) {
+    const Geometry *g = fs.surface->geometry();
+    mix((uint64_t)(uintptr_t)fs.surface);
+    mix(fs.surface->lastFinalized);
+    mix(g->lastFinalized);
+    mix(fs.surface->material()->lastFinalized);
+    mixArray(g->vertex());
+    mixArray(g->index());
+    mixArray(g->normal());
+    mixArray(g->vertexRadius());
+    mixArray(g->primitiveId());
+    for (int i = 0; i < 12; ++i) {
+      uint32_t bits;
+      std::memcpy(&bits, &fs.objectToWorld[i], 4);
+      mix(bits);
+    }
+    mix(fs.instId);
+  }
+  if (m_surfaceSet && stamp == m_surfaceStamp && m_surfaceSetGpu == device->cudaDevice())
+    return m_surfaceSet;
+  dropSurfaceSet();
+  std::vector<DvrSurfaceDesc> descs(flat.size());
+  for (size_t i = 0; i < flat.size(); ++i) {
+    const Geometry *g = flat[i].surface->geometry();
+    const Material *m = flat[i].surface->material();
+    DvrSurfaceDesc &d = descs[i];
+    std::memset(&d, 0, sizeof(d));
+    d.geometryType = g->kind;
+    d.nVertices = (uint32_t)g->vertex()->regionSize();
+    d.vertexPosition = (const float *)g->vertex()->regionData();
+    d.index = g->index() ? (const uint32_t *)g->index()->regionData() : nullptr;
+    d.nPrimitives = g->index() ? (uint32_t)g->index()->regionSize()
+                               : (g->kind == DVR_GEOMETRY_TRIANGLE ? d.nVertices / 3u : d.nVertices);
+    d.vertexNormal = g->normal() ? (const float *)g->normal()->regionData() : nullptr;
+    d.vertexRadius = g->vertexRadius() ? (const float *)g->vertexRadius()->regionData() : nullptr;
+    d.radius = g->radius;
+    d.primitiveId = g->primitiveId() ? (const uint32_t *)g->primitiveId()->regionData() : nullptr;
+    d.cullBackfaces = g->cullBackfaces ? 1 : 0;
+    std::memcpy(d.color, m->color, sizeof(d.color));
+    d.opacity = m->opacity;
+    d.alphaMode = m->alphaMode;
+    d.alphaCutoff = m->alphaCutoff;
+    d.surfaceId = flat[i].surface->id;
+    d.instanceId = flat[i].instId;
+    std::memcpy(d.objectToWorld, flat[i].objectToWorld, sizeof(d.objectToWorld));
+  }
+  const int rc = dvr_surfaces_create(descs.data(), (uint32_t)descs.size(), device->stream(), &m_surfaceSet);
+  if (rc != DVR_OK) {
+    report(ANARI_SEVERITY_ERROR, ANARI_STATUS_UNKNOWN_ERROR, "dvr_surfaces_create failed: %s", dvr_last_error());
+    m_surfaceSet = nullptr;
+    return nullptr;
+  }
+  m_surfaceStamp = stamp;
+  m_surfaceSetGpu = device->cudaDevice();
+  return m_surfaceSet;
 }
 
 // inverse of an affine transform given as column-major 4x3 -> row-major 3x4
@@ -964,6 +1244,28 @@ void World::bounds(float lo[3], float hi[3]) const
   }
 }
 
+// object-space box of a geometry's primitives (triangle corners / spheres)
+static bool geometryBounds(const Geometry *g, float lo[3], float hi[3])
+{
+  if (!g || !g->isValid())
+    return false;
+  const float *v = (const float *)g->vertex()->regionData();
+  const size_t n = g->vertex()->regionSize();
+  const float *rad = g->vertexRadius() ? (const float *)g->vertexRadius()->regionData() : nullptr;
+  for (int a = 0; a < 3; ++a) {
+    lo[a] = std::numeric_limits<float>::max();
+    hi[a] = -std::numeric_limits<float>::max();
+  }
+  for (size_t i = 0; i < n; ++i) {
+    const float r = g->kind == DVR_GEOMETRY_SPHERE ? std::fabs(rad ? rad[i] : g->radius) : 0.f;
+    for (int a = 0; a < 3; ++a) {
+      lo[a] = std::min(lo[a], v[3 * i + a] - r);
+      hi[a] = std::max(hi[a], v[3 * i + a] + r);
+    }
+  }
+  return n > 0;
+}
+
 bool World::getProperty(const std::string &name, ANARIDataType t, void *mem, uint64_t size, uint32_t mask)
 {
   if (name == "bounds" && t == ANARI_FLOAT32_BOX3 && size >= 24) { // World.cpp:100-117
@@ -971,6 +1273,20 @@ bool World::getProperty(const std::string &name, ANARIDataType t, void *mem, uin
       device->flushCommits();
     float b[6];
     bounds(b, b + 3);
+    for (const FlatSurface &fs : flattenSurfaces(false)) { // surfaces extend the box
+      float lo[3], hi[3];
+      if (!geometryBounds(fs.surface->geometry(), lo, hi))
+        continue;
+      for (int k = 0; k < 8; ++k) {
+        const float p[3] = {k & 1 ? hi[0] : lo[0], k & 2 ? hi[1] : lo[1], k & 4 ? hi[2] : lo[2]};
+        for (int r = 0; r < 3; ++r) {
+          const float *m = fs.objectToWorld + 4 * r;
+          const float w = m[0] * p[0] + m[1] * p[1] + m[2] * p[2] + m[3];
+          b[r] = std::min(b[r], w);
+          b[3 + r] = std::max(b[3 + r], w);
+        }
+      }
+    }
     std::memcpy(mem, b, 24);
     return true;
   }
@@ -1034,6 +1350,11 @@ void Renderer::commitParameters()
   // Renderer.cpp:159-161; the dpt renderer's default ambient radiance is 1 (DiffusePathTracer.cpp:41)
   ambientRadiance = getParam<float>("ambientRadiance", ANARI_FLOAT32, integrator == DVR_INTEGRATOR_DPT ? 1.f : 0.f);
   occlusionDistance = getParam<float>("ambientOcclusionDistance", ANARI_FLOAT32, 1e20f);
+  // surface shading of mixed scenes (Renderer.cpp:158,165, DirectLight.cpp:49-53)
+  ambientColor[0] = ambientColor[1] = ambientColor[2] = 1.f;
+  getParamRaw("ambientColor", ANARI_FLOAT32_VEC3, ambientColor, 12);
+  ambientSamples = std::min(std::max(getParam<int>("ambientSamples", ANARI_INT32, 1), 0), 256);
+  cullTriangleBackfaces = getParam<int32_t>("cullTriangleBackfaces", ANARI_BOOL, 0) != 0;
   if (!m_known)
     report(ANARI_SEVERITY_WARNING, ANARI_STATUS_INVALID_ARGUMENT, "unknown renderer subtype '%s'", subtype.c_str());
 }

@@ -256,6 +256,69 @@ struct Volume : Object
   bool m_known = true;
 };
 
+// ---- surfaces and lights (what stands in front of, behind and around the volumes) ---------------------
+// scene/surface/geometry/{Triangle.cpp,Sphere.cu}: the arrays stay host-side here; World::surfaceSet() hands them to
+// dvr_surfaces_create, which uploads them and builds the BVH
+struct Geometry : Object
+{
+  Geometry(Device *d, const std::string &subtype);
+  void commitParameters() override;
+  bool isValid() const override { return kind >= 0 && m_vertex; }
+  int commitPriority() const override { return 2; }
+  int kind = -1; // DvrGeometryType, -1 = a subtype this device does not render
+  Array *vertex() const { return m_vertex.ptr; }
+  Array *index() const { return m_index.ptr; }
+  Array *normal() const { return m_normal.ptr; }
+  Array *vertexRadius() const { return m_radius.ptr; }
+  Array *primitiveId() const { return m_primId.ptr; }
+  float radius = 0.01f;
+  bool cullBackfaces = false;
+
+ private:
+  Ref<Array> m_vertex, m_index, m_normal, m_radius, m_primId;
+};
+
+// scene/surface/material/Matte.cpp:38-52 (constant colour / opacity; samplers and attribute names are not built)
+struct Material : Object
+{
+  Material(Device *d, const std::string &subtype);
+  void commitParameters() override;
+  int commitPriority() const override { return 2; }
+  float color[4] = {0.8f, 0.8f, 0.8f, 1.f};
+  float opacity = 1.f;
+  int alphaMode = DVR_ALPHA_OPAQUE;
+  float alphaCutoff = 0.5f;
+};
+
+// scene/surface/Surface.cpp:42-58
+struct Surface : Object
+{
+  Surface(Device *d);
+  void commitParameters() override;
+  bool isValid() const override { return m_geometry && m_geometry->isValid() && m_material; }
+  int commitPriority() const override { return 3; }
+  Geometry *geometry() const { return m_geometry.ptr; }
+  Material *material() const { return m_material.ptr; }
+  uint32_t id = ~0u;
+
+ private:
+  Ref<Geometry> m_geometry;
+  Ref<Material> m_material;
+};
+
+// scene/light/{Light,Directional,Point}.cpp
+struct Light : Object
+{
+  Light(Device *d, const std::string &subtype);
+  void commitParameters() override;
+  bool isValid() const override { return kind >= 0; }
+  int commitPriority() const override { return 2; }
+  int kind = -1; // DvrLightType
+  float color[3] = {1, 1, 1};
+  float vec[3] = {0, 0, -1}; // direction (normalised) or position, object space
+  float strength = 1.f;
+};
+
 // ---- group / instance / world ---------------------------------------------------------------------------------------
 struct Group : Object
 {
@@ -263,9 +326,11 @@ struct Group : Object
   void commitParameters() override;
   int commitPriority() const override { return 4; }
   std::vector<Volume *> volumes() const;
+  std::vector<Surface *> surfaces() const;
+  std::vector<Light *> lights() const;
 
  private:
-  Ref<Array> m_volumes;
+  Ref<Array> m_volumes, m_surfaces, m_lights;
 };
 
 struct Instance : Object
@@ -292,15 +357,32 @@ struct FlatInstance
 struct World : Object
 {
   World(Device *d);
+  ~World() override;
   void commitParameters() override;
   int commitPriority() const override { return 6; }
   bool getProperty(const std::string &name, ANARIDataType type, void *mem, uint64_t size, uint32_t mask) override;
   // World::rebuildWorld + the zero-instance rule (World.cpp:60-135,202-258)
   std::vector<FlatInstance> flatten(bool warn) const;
   void bounds(float lo[3], float hi[3]) const;
+  // The flattened world's surfaces as a device-side set (geometry + matte material + instance transform + BVH),
+  // rebuilt when anything that feeds it was finalised since the last build; null when the world has no surface
+  DvrSurfaces *surfaceSet(bool warn);
+  // every light instance, transformed by its instance (gpu/sampleLight.h:54-78)
+  std::vector<DvrLight> flattenLights() const;
 
  private:
-  Ref<Array> m_zeroVolumes, m_instances;
+  struct FlatSurface
+  {
+    Surface *surface;
+    float objectToWorld[12]; // row-major 3x4
+    uint32_t instId;
+  };
+  std::vector<FlatSurface> flattenSurfaces(bool warn) const;
+  void dropSurfaceSet();
+  Ref<Array> m_zeroVolumes, m_instances, m_zeroSurfaces, m_zeroLights;
+  DvrSurfaces *m_surfaceSet = nullptr;
+  uint64_t m_surfaceStamp = 0; // fingerprint of what m_surfaceSet was built from
+  int m_surfaceSetGpu = -1;
 };
 
 // ---- renderer ----------------------------------------------------------------------------------------------------
@@ -321,8 +403,11 @@ struct Renderer : Object
   int integrator = DVR_INTEGRATOR_DEFAULT;
   int maxDepth = 5;                // dpt only
   bool dptReferenceGrid = false;   // dpt only (extension)
-  float ambientRadiance = 0.f;     // dpt only (the marching renderers have no lighting term for volumes)
-  float occlusionDistance = 1e20f; // dpt only
+  float ambientRadiance = 0.f;     // dpt: light of the walk; default / directLight: ambient term of surface shading
+  float occlusionDistance = 1e20f; // dpt: scatter ray length; default / directLight: ambient-occlusion ray length
+  float ambientColor[3] = {1, 1, 1}; // surface shading only (Renderer.cpp:158)
+  int ambientSamples = 1;            // "ambientSamples" (DirectLight.cpp:52)
+  bool cullTriangleBackfaces = false;
   int macrocellSkipping = DVR_SKIP_AUTO;
   // sort-first extension: this device renders only tile rows (row % tileRanks == tileRank)
   uint32_t tileRank = 0, tileRanks = 1;

@@ -64,6 +64,14 @@ const ANARIDataType kColorTypes[] = {ANARI_FLOAT32_VEC3, ANARI_FLOAT32_VEC4, ANA
 const ANARIDataType kFloatType[] = {ANARI_FLOAT32, ANARI_UNKNOWN};
 const ANARIDataType kVolumeType[] = {ANARI_VOLUME, ANARI_UNKNOWN};
 const ANARIDataType kInstanceType[] = {ANARI_INSTANCE, ANARI_UNKNOWN};
+const ANARIDataType kSurfaceType[] = {ANARI_SURFACE, ANARI_UNKNOWN};
+const ANARIDataType kLightType[] = {ANARI_LIGHT, ANARI_UNKNOWN};
+const ANARIDataType kVec3Type[] = {ANARI_FLOAT32_VEC3, ANARI_UNKNOWN};
+const ANARIDataType kUvec3Type[] = {ANARI_UINT32_VEC3, ANARI_UNKNOWN};
+const ANARIDataType kUintType[] = {ANARI_UINT32, ANARI_UNKNOWN};
+const float kMatteColor[3] = {0.8f, 0.8f, 0.8f}, kDirNegZ[3] = {0.f, 0.f, -1.f}, kRadius = 0.01f, kHalf = 0.5f;
+const char *const kAlphaModes[] = {"opaque", "blend", "mask", nullptr};
+const char *const kOpaque = "opaque";
 const ANARIDataType kColorChannelTypes[] = {ANARI_UFIXED8_VEC4, ANARI_UFIXED8_RGBA_SRGB, ANARI_FLOAT32_VEC4, ANARI_UNKNOWN};
 
 ParamDesc P(const char *name, ANARIDataType type, const char *description, const void *def = nullptr,
@@ -126,6 +134,16 @@ std::vector<ParamDesc> rendererCommon(bool rate, bool progressive)
   if (rate) // visrtx_device.json:129-137
     v.push_back(
         P("volumeSamplingRate", ANARI_FLOAT32, "sampling rate of volumes when ray marching", &kRate, &kRateMin, &kF10));
+  if (rate) { // surface shading of mixed scenes (visrtx_device.json: ambientColor / ambientRadiance / cullTriangleBackfaces)
+    v.push_back(ext(P("ambientColor", ANARI_FLOAT32_VEC3, "ambient light color", kOne3), "ANARI_KHR_RENDERER_AMBIENT_LIGHT"));
+    v.push_back(ext(P("ambientRadiance", ANARI_FLOAT32, "ambient light intensity", &kF0, &kF0),
+        "ANARI_KHR_RENDERER_AMBIENT_LIGHT"));
+    v.push_back(P("cullTriangleBackfaces", ANARI_BOOL, "enable triangle back face culling", &kFalse));
+    if (progressive) {
+      v.push_back(P("ambientSamples", ANARI_INT32, "number of ambient occlusion samples each frame", &kI1, &kI0, &kI256));
+      v.push_back(P("ambientOcclusionDistance", ANARI_FLOAT32, "ambient occlusion distance", &kFar, &kF0));
+    }
+  }
   // extensions of this device; all image-neutral
   v.push_back(ext(P("macrocellSkipping", ANARI_BOOL,
                       "skip macrocells the transfer function makes fully transparent (unset: decided per volume)"),
@@ -204,11 +222,53 @@ std::vector<ObjectInfo> buildTables()
           P("transform", ANARI_FLOAT32_MAT4, "object-to-world transform", kIdentity),
           P("id", ANARI_UINT32, "user id written to the instanceId channel", &kIdNone)},
       {}});
-  t.push_back({ANARI_GROUP, nullptr, "container of volumes", "ANARI_KHR_CORE",
-      {kName, elems(P("volume", ANARI_ARRAY1D, "volumes of the group"), kVolumeType)}, {}});
+  t.push_back({ANARI_GROUP, nullptr, "container of volumes, surfaces and lights", "ANARI_KHR_CORE",
+      {kName, elems(P("volume", ANARI_ARRAY1D, "volumes of the group"), kVolumeType),
+          elems(P("surface", ANARI_ARRAY1D, "surfaces of the group"), kSurfaceType),
+          elems(P("light", ANARI_ARRAY1D, "lights of the group"), kLightType)},
+      {}});
   t.push_back({ANARI_WORLD, nullptr, "container of the scene", "ANARI_KHR_CORE",
       {kName, elems(P("volume", ANARI_ARRAY1D, "volumes placed directly in the world"), kVolumeType),
+          elems(P("surface", ANARI_ARRAY1D, "surfaces placed directly in the world"), kSurfaceType),
+          elems(P("light", ANARI_ARRAY1D, "lights placed directly in the world"), kLightType),
           elems(P("instance", ANARI_ARRAY1D, "instances of the world"), kInstanceType)},
+      {}});
+  // ---- surfaces and lights of mixed scenes (Triangle.cpp:44-57, Sphere.cu:47-55, Matte.cpp:38-52, Surface.cpp:42-47,
+  //      Directional.cpp:38-47, Point.cpp:38-48)
+  t.push_back({ANARI_GEOMETRY, "triangle", "triangle mesh", "ANARI_KHR_GEOMETRY_TRIANGLE",
+      {kName, req(elems(P("vertex.position", ANARI_ARRAY1D, "vertex positions"), kVec3Type)),
+          elems(P("vertex.normal", ANARI_ARRAY1D, "vertex normals"), kVec3Type),
+          elems(P("primitive.index", ANARI_ARRAY1D, "vertex indices of each triangle"), kUvec3Type),
+          elems(P("primitive.id", ANARI_ARRAY1D, "user id of each triangle (primitiveId channel)"), kUintType),
+          P("cullBackfaces", ANARI_BOOL, "cull back-facing triangles on primary rays", &kFalse)},
+      {}});
+  t.push_back({ANARI_GEOMETRY, "sphere", "spheres", "ANARI_KHR_GEOMETRY_SPHERE",
+      {kName, req(elems(P("vertex.position", ANARI_ARRAY1D, "sphere centers"), kVec3Type)),
+          elems(P("vertex.radius", ANARI_ARRAY1D, "per-sphere radius"), kFloatType),
+          elems(P("primitive.index", ANARI_ARRAY1D, "index of each sphere's center"), kUintType),
+          elems(P("primitive.id", ANARI_ARRAY1D, "user id of each sphere (primitiveId channel)"), kUintType),
+          P("radius", ANARI_FLOAT32, "radius of spheres without a vertex.radius", &kRadius, &kF0)},
+      {}});
+  t.push_back({ANARI_MATERIAL, "matte", "diffuse material (constant color and opacity)", "ANARI_KHR_MATERIAL_MATTE",
+      {kName, P("color", ANARI_FLOAT32_VEC3, "diffuse color", kMatteColor),
+          P("opacity", ANARI_FLOAT32, "opacity", &kF1, &kF0, &kF1),
+          strings(P("alphaMode", ANARI_STRING, "how opacity is interpreted", &kOpaque), kAlphaModes),
+          P("alphaCutoff", ANARI_FLOAT32, "threshold of alphaMode mask", &kHalf, &kF0, &kF1)},
+      {}});
+  t.push_back({ANARI_SURFACE, nullptr, "geometry with a material", "ANARI_KHR_CORE",
+      {kName, req(P("geometry", ANARI_GEOMETRY, "geometry of the surface")),
+          req(P("material", ANARI_MATERIAL, "material of the surface")),
+          P("id", ANARI_UINT32, "user id written to the objectId channel", &kIdNone)},
+      {}});
+  t.push_back({ANARI_LIGHT, "directional", "distant light", "ANARI_KHR_LIGHT_DIRECTIONAL",
+      {kName, P("color", ANARI_FLOAT32_VEC3, "color of the light", kOne3),
+          P("direction", ANARI_FLOAT32_VEC3, "direction the light travels in", kDirNegZ),
+          P("irradiance", ANARI_FLOAT32, "irradiance on a surface facing the light", &kF1, &kF0)},
+      {}});
+  t.push_back({ANARI_LIGHT, "point", "point light", "ANARI_KHR_LIGHT_POINT",
+      {kName, P("color", ANARI_FLOAT32_VEC3, "color of the light", kOne3),
+          P("position", ANARI_FLOAT32_VEC3, "position of the light", kZero3),
+          P("intensity", ANARI_FLOAT32, "radiant intensity", &kF1, &kF0)},
       {}});
   // ---- frame (Frame.cu:120-200)
   t.push_back({ANARI_FRAME, nullptr, "render target", "ANARI_KHR_CORE",
