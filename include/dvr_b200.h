@@ -243,6 +243,15 @@ int dvr_field_create_structured(const void *data, int dataIsDevice, int dataType
 int dvr_field_create_structured_slab(const void *data, int dataIsDevice, int dataType,
     const uint32_t globalDims[3], uint32_t zBegin, uint32_t zEnd, const float origin[3],
     const float spacing[3], int filter, void *stream, DvrField **out);
+/* Moves the ownership of a slab field without moving a voxel: afterwards the field takes the lattice samples whose cell
+ * slice lies in [zBegin, zEnd).  The new range must lie inside the range the slab was created with (its resident slices
+ * are those +- one ghost slice), so a slab created with a margin of M slices on each side can hand up to M slices to
+ * either neighbour — and take them back — between two frames.  Sort-last load balancing: the per-GPU march times of the
+ * last frames decide where the cuts go (visrtx_b200/multigpu.py rebalance_slab_ranges); every GPU of the partition must
+ * apply the same cuts before the next frame.  Host-side bookkeeping only (the kernels read the range per launch). */
+int dvr_field_set_owned_slices(DvrField *f, uint32_t zBegin, uint32_t zEnd);
+/* current ownership and the limits it can move in (the range given at creation) */
+int dvr_field_owned_slices(const DvrField *f, uint32_t *zBegin, uint32_t *zEnd, uint32_t *limitBegin, uint32_t *limitEnd);
 /* Chunked fill of a slab field created with data == NULL (volumes too large to stage twice in HBM):
  * copies nSlices z-slices into resident slices [firstResidentSlice, +nSlices); element type = the
  * field's.  Call dvr_field_build_macrocells once all slices are in. */

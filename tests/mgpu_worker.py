@@ -86,6 +86,82 @@ def main():
         sl.close()
         cs.destroy()
 
+    # ---- the very first frame of a fresh driver: every pixel of the display frame (volume window AND background strips
+    # of every rank) must be written by that one launch — nothing may rely on what an earlier frame left behind
+    if world > 1:
+        single0 = H.render_cuda(scene, frames=1) if rank == 0 else None
+        for fused in (True, False):
+            cs = H.CudaScene(scene, slab=(z0, z1), device=f"cuda:{local}")
+            sl = multigpu.SortLast(capi, torch, dist, rank, world, device, scene.width, scene.height, cs.instances, v.vol_id,
+                                   v.inst_id, scene.fmt, scene.integrator, scene.volume_sampling_rate, scene.background,
+                                   fused=fused)
+            if rank == 0:  # poison the display frame
+                import ctypes
+                px_bytes = 4
+                ctypes.CDLL("libcudart.so").cudaMemset(ctypes.c_void_p(sl.color_ptr), 0xAB,
+                                                       ctypes.c_size_t(sl.npx * px_bytes + sl.npx * 4))
+            torch.cuda.synchronize()
+            dist.barrier()
+            sl.render(0, scene.camera, stream)
+            torch.cuda.synchronize()
+            dist.barrier()
+            if rank == 0:
+                got = sl.color_tensor().cpu().numpy().view(np.uint32)
+                d = np.abs(H.unpack_rgba8(got) - H.unpack_rgba8(single0["color"])).max(axis=-1)
+                good = (d <= 1).mean() >= 0.999 and d.max() <= 2
+                print(f"[sort-last x{world} {'fused' if fused else 'legacy'}, first frame of a fresh driver] max diff "
+                      f"{d.max()}/255, pixels off by > 2: {int((d > 2).sum())}: {good}")
+                ok &= bool(good)
+                depth = sl.depth_tensor().cpu().numpy()
+                dgood = np.allclose(depth, single0["depth"], rtol=1e-6, atol=0)
+                print(f"[sort-last x{world} {'fused' if fused else 'legacy'}, first frame] depth == single-GPU depth: {dgood}")
+                ok &= bool(dgood)
+            dist.barrier()
+            sl.close()
+            cs.destroy()
+
+    # ---- ownership shift (sort-last load balancing): slabs created with a margin of resident slices, cuts moved with
+    # dvr_field_set_owned_slices (no voxel moves) — by hand, then by the measured-time feedback of SortLast.calibrate
+    if world > 1:
+        single3 = H.render_cuda(scene, frames=3) if rank == 0 else None
+        ranges0 = multigpu.slab_ranges(nz, world)
+        margin = 5
+        limits = multigpu.creation_ranges(ranges0, nz, margin)
+        cs = H.CudaScene(scene, slab=limits[rank], device=f"cuda:{local}")
+        fld = cs.fields[0]
+        fld.set_owned_slices(*ranges0[rank])
+        sl = multigpu.SortLast(capi, torch, dist, rank, world, device, scene.width, scene.height, cs.instances, v.vol_id,
+                               v.inst_id, scene.fmt, scene.integrator, scene.volume_sampling_rate, scene.background)
+        shifted = [(a + (2 if i > 0 else 0) * (1 if i % 2 else -1), b + (2 if i < world - 1 else 0) * (-1 if i % 2 else 1))
+                   for i, (a, b) in enumerate(ranges0)]  # cut i moves by +-2 slices, alternating
+        for label, rng in (("initial cuts", ranges0), ("cuts moved by 2 slices", shifted), ("calibrated", None)):
+            if rng is None:
+                rng, times, hist = sl.calibrate(fld, shifted, limits, scene.camera, stream, rounds=2, frames=3)
+                if rank == 0:
+                    print(f"[sort-last x{world} balance] calibrated cuts {rng} from march times {[round(t, 3) for t in times]} ms")
+            else:
+                fld.set_owned_slices(*rng[rank])
+            assert fld.owned_slices() == (tuple(rng[rank]), tuple(limits[rank]))
+            for fid in range(3):
+                sl.render(fid, scene.camera, stream)
+            torch.cuda.synchronize()
+            dist.barrier()
+            if rank == 0:
+                got = sl.color_tensor().cpu().numpy().view(np.uint32)
+                d = np.abs(H.unpack_rgba8(got) - H.unpack_rgba8(single3["color"])).max(axis=-1)
+                good = (d <= 1).mean() >= 0.999 and d.max() <= 2
+                print(f"[sort-last x{world} balance, {label}] max diff {d.max()}/255, frac<=1/255 {(d <= 1).mean():.5f}: {good}")
+                ok &= bool(good)
+            dist.barrier()
+        bad = False
+        try:
+            fld.set_owned_slices(limits[rank][0], limits[rank][1] + 1)
+        except capi.DvrError:
+            bad = True
+        ok &= bad
+        sl.close()
+        cs.destroy()
+
     # ---- a moving camera (accumulation reset every frame, the screen window changes) and a camera that does not see
     # the volume at all (empty window: background strips only)
     if world > 1:

@@ -36,13 +36,13 @@ def test_sort_last_through_anari_matches_the_single_gpu_frame(world):
     kw = dict(n=64, w=200, h=152, renderer="default", rate=0.5, vox=vox)
     one = AnariScene(**kw)
     many = AnariScene(gpus=list(range(world)), multi_gpu_mode="sortLast", **kw)
-    assert many.d.get_property(many.d.handle, "cudaDeviceCount", A.INT32) == world
     for s in (one, many):
         s.d.set(s.volume, "unitDistance", A.FLOAT32, 0.5)
         s.d.commit(s.volume)
     c1, d1, o1 = _frames(one, 3)  # 3 accumulated frames
     cn, dn, on = _frames(many, 3)
     assert not _errors(many.d), many.d.messages
+    assert many.d.get_property(many.d.handle, "cudaDeviceCount", A.INT32) == world  # (the device initialises lazily)
     assert many.d.get_property(many.frame, "numSamples", A.INT32) == 2
     d = np.abs(H.unpack_rgba8(cn) - H.unpack_rgba8(c1)).max(axis=-1)
     assert (d <= 1).mean() >= 0.999 and d.max() <= 2, (float((d <= 1).mean()), int(d.max()))

@@ -107,3 +107,36 @@ def test_view_balanced_slabs_partition_and_equalise_the_inverse_square_weight():
     import pytest
     with pytest.raises(ValueError):
         multigpu.view_balanced_slab_ranges(15, 8, lo, hi, eye)
+
+
+def test_rebalance_moves_cuts_to_equal_measured_work_inside_the_margins():
+    """Sort-last feedback balancing (multigpu.rebalance_slab_ranges): cuts go to equal cumulative measured time, never
+    leave what both neighbours hold resident, keep the cover exact; a synthetic cost model converges in a few rounds."""
+    nz, world = 1024, 8
+    ranges = multigpu.slab_ranges(nz, world)
+    margin = multigpu.slab_margin(nz, world)
+    assert margin == 32
+    limits = multigpu.creation_ranges(ranges, nz, margin)
+    assert limits[0] == (0, 128 + 32) and limits[-1] == (896 - 32, 1024) and limits[3] == (384 - 32, 512 + 32)
+
+    def cost(z0, z1):  # per-slice cost falls linearly from 1.15 to 0.9 across the volume + a fixed per-slab cost
+        return sum(1.15 - 0.25 * z / nz for z in range(z0, z1)) + 5.0
+
+    cur = ranges
+    for _ in range(4):
+        times = [cost(*r) for r in cur]
+        cur = multigpu.rebalance_slab_ranges(cur, times, limits)
+        assert cur[0][0] == 0 and cur[-1][1] == nz
+        assert all(cur[i][1] == cur[i + 1][0] for i in range(world - 1))
+        assert all(l0 <= a and b <= l1 and b - a >= 2 for (a, b), (l0, l1) in zip(cur, limits))
+    t0 = [cost(*r) for r in ranges]
+    t1 = [cost(*r) for r in cur]
+    assert max(t1) / (sum(t1) / world) < 1.02 < 1.08 < max(t0) / (sum(t0) / world)
+    # equal times: nothing moves; one rank twice as slow: its slab shrinks, but never past the margins
+    assert multigpu.rebalance_slab_ranges(ranges, [1.0] * world, limits) == ranges
+    slow = multigpu.rebalance_slab_ranges(ranges, [1.0] * 3 + [2.0] + [1.0] * 4, limits)
+    assert slow[3][1] - slow[3][0] < 128 and all(l0 <= a and b <= l1 for (a, b), (l0, l1) in zip(slow, limits))
+    # margins of zero leave no room: the partition is kept
+    assert multigpu.rebalance_slab_ranges(ranges, [1.0] * 3 + [2.0] + [1.0] * 4, ranges) == ranges
+    with pytest.raises(ValueError):
+        multigpu.rebalance_slab_ranges(ranges, [1.0], limits)

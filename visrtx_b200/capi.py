@@ -20,7 +20,7 @@ from .pods import DvrSurfaceDesc, DvrLight, DvrSceneParams, surface_descs, scene
 EXPORTED_SYMBOLS = [
     "dvr_last_error", "dvr_version", "dvr_device_count", "dvr_set_device", "dvr_device_info",
     "dvr_camera_perspective", "dvr_camera_orthographic", "dvr_tf_discretize",
-    "dvr_field_create_structured", "dvr_field_create_structured_slab", "dvr_field_upload_slices", "dvr_field_update_structured", "dvr_field_create_nanovdb",
+    "dvr_field_create_structured", "dvr_field_create_structured_slab", "dvr_field_upload_slices", "dvr_field_set_owned_slices", "dvr_field_owned_slices", "dvr_field_update_structured", "dvr_field_create_nanovdb",
     "dvr_field_destroy",
     "dvr_field_bounds", "dvr_field_step_size", "dvr_field_device_bytes", "dvr_field_build_macrocells",
     "dvr_field_macrocells", "dvr_field_value_range",
@@ -171,6 +171,16 @@ class Field:
                       stream: int = 0) -> None:
         _check(lib.dvr_field_upload_slices(self.handle, C.c_void_p(data_ptr), C.c_int(1 if is_device else 0),
                                            C.c_uint32(first_resident_slice), C.c_uint32(n_slices), C.c_void_p(stream)))
+
+    def set_owned_slices(self, z_begin: int, z_end: int) -> None:
+        """Sort-last load balancing: move the slab's ownership inside the range it was created with (no data moves)."""
+        _check(lib.dvr_field_set_owned_slices(self.handle, C.c_uint32(z_begin), C.c_uint32(z_end)))
+
+    def owned_slices(self):
+        """((z_begin, z_end), (limit_begin, limit_end))"""
+        v = [C.c_uint32() for _ in range(4)]
+        _check(lib.dvr_field_owned_slices(self.handle, *[C.byref(x) for x in v]))
+        return (v[0].value, v[1].value), (v[2].value, v[3].value)
 
     def update_structured(self, data_ptr: int, is_device: bool, data_type: int, origin, spacing,
                           stream: int = 0) -> None:

@@ -184,6 +184,7 @@ struct DvrField
   size_t brickBytes = 0;
   int device = 0;
   int dataType = -1; // structured fields: the DvrDataType handed to create
+  int ownLimitBegin = 0, ownLimitEnd = 0; // slab fields: the ownership range given at creation (dvr_field_set_owned_slices)
 };
 
 struct DvrVolume
@@ -613,6 +614,8 @@ static int createFieldImpl(const void *data, int dataIsDevice, int dataType, con
   d.zOwnEnd = whole ? (int)gdims[2] : (int)zEnd;
   d.zTexBegin = (int)zTexBegin;
   d.texDepth = (int)texDepth;
+  f->ownLimitBegin = d.zOwnBegin;
+  f->ownLimitEnd = d.zOwnEnd;
   d.gridDims = make_int3((int)((gdims[0] + 15) / 16), (int)((gdims[1] + 15) / 16), (int)((gdims[2] + 15) / 16));
   f->nCells = (size_t)d.gridDims.x * d.gridDims.y * d.gridDims.z;
   e = cudaMalloc(&f->ranges, f->nCells * sizeof(float2));
@@ -866,6 +869,40 @@ int dvr_field_create_nanovdb(const void *gridData, size_t bytes, int dataIsDevic
   }
   buildNvdbBricks(f, bmin, bmax, s);
   *out = f;
+  return DVR_OK;
+}
+
+int dvr_field_set_owned_slices(DvrField *f, uint32_t zBegin, uint32_t zEnd)
+{
+  if (!f) {
+    setError("dvr_field_set_owned_slices: null field");
+    return DVR_ERR_INVALID_ARGUMENT;
+  }
+  if (f->dev.kind != FIELD_STRUCTURED) {
+    setError("dvr_field_set_owned_slices: structuredRegular slab fields only");
+    return DVR_ERR_UNSUPPORTED;
+  }
+  if (zBegin >= zEnd || (int)zBegin < f->ownLimitBegin || (int)zEnd > f->ownLimitEnd) {
+    setError("dvr_field_set_owned_slices: [" + std::to_string(zBegin) + ", " + std::to_string(zEnd)
+        + ") is empty or leaves the range the slab was created with [" + std::to_string(f->ownLimitBegin) + ", "
+        + std::to_string(f->ownLimitEnd) + ")");
+    return DVR_ERR_INVALID_ARGUMENT;
+  }
+  f->dev.zOwnBegin = (int)zBegin;
+  f->dev.zOwnEnd = (int)zEnd;
+  return DVR_OK;
+}
+
+int dvr_field_owned_slices(const DvrField *f, uint32_t *zBegin, uint32_t *zEnd, uint32_t *limitBegin, uint32_t *limitEnd)
+{
+  if (!f) {
+    setError("dvr_field_owned_slices: null field");
+    return DVR_ERR_INVALID_ARGUMENT;
+  }
+  if (zBegin) *zBegin = (uint32_t)f->dev.zOwnBegin;
+  if (zEnd) *zEnd = (uint32_t)f->dev.zOwnEnd;
+  if (limitBegin) *limitBegin = (uint32_t)f->ownLimitBegin;
+  if (limitEnd) *limitEnd = (uint32_t)f->ownLimitEnd;
   return DVR_OK;
 }
 

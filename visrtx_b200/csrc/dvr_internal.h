@@ -132,7 +132,7 @@ struct SlabFrameLaunch
   size_t bgPixelBegin, bgPixelEnd;          // this rank's share of the pixels outside the tile window
   unsigned long long *timing;               // optional %globaltimer stamps (DvrSlabExchange::timing)
   unsigned spinSleepNs;                     // back-off of the warps that wait for region flags
-  unsigned debugFlags;                      // timing experiments only (DVR_B200_SLAB_DEBUG): 1 no region flags, 2 no
+  unsigned debugFlags;                      // timing experiments only (DVR_B200_SLAB_DEBUG; 8: also composite between march tiles, 16: no background chunk between march tiles): 1 no region flags, 2 no
                                             // background strip, 4 no compositing — frames are then incomplete
 };
 

@@ -797,30 +797,41 @@ __device__ __forceinline__ void slabBackgroundChunk(const SlabFrameLaunch &S, ui
   }
 }
 
-// Claims the next composite item (a tile of a region this rank owns) if — and only if — every rank has flagged its
-// region, and composites it.  Never blocks: 0 = nothing ready yet, 1 = one tile composited, 2 = all items done.
-template <bool DUMMY = false>
-__device__ __forceinline__ int slabTryComposite(const SlabFrameLaunch &S, uint32_t nItems, uint32_t nTiles, int lane)
+// One step of this warp's share of the compositing.  The tiles of the regions this rank owns form ONE queue in region
+// order; a warp draws a ticket from it (one unconditional atomicAdd — no retry, no contention beyond that) and KEEPS
+// the ticket until the region it belongs to has been flagged by every rank.  The check never blocks, so during the
+// march a warp looks at its pending ticket between two tiles and otherwise keeps marching; regions complete in queue
+// order on every rank, so tickets mature in the order they were drawn.  After the tile queue is empty the warp spins
+// on what it still holds.  Returns 0 = holding a ticket whose region is not complete yet, 1 = one tile composited,
+// 2 = nothing held and the queue is exhausted.
+// (History, profiles/r02_sort_last_fused.md: claiming with a CAS after the readiness check made every warp race for the
+// same item — 2 us per item, 1 ms per frame at N = 8; per-region counters walked by a per-warp cursor cost every warp
+// a dependent load per region — 115 us of tail at N = 2.)
+constexpr uint32_t kNoTicket = 0xffffffffu;
+__device__ __forceinline__ int slabCompositeStep(const SlabFrameLaunch &S, uint32_t &ticket, uint32_t nItems,
+    uint32_t nTiles, int lane)
 {
   const PartialLaunch &P = S.m;
-  uint32_t item = 0;
-  if (lane == 0)
-    item = *((volatile unsigned int *)&P.sched[3]);
-  item = __shfl_sync(0xffffffffu, item, 0);
-  if (item >= nItems)
-    return 2;
-  const uint32_t region = (item / S.tilesPerRegion) * S.nRanks + S.rank;
+  if (ticket == kNoTicket) {
+    uint32_t t = kNoTicket;
+    if (lane == 0) {
+      t = *((volatile unsigned int *)&P.sched[3]);
+      if (t < nItems)
+        t = atomicAdd(&P.sched[3], 1u);
+    }
+    t = __shfl_sync(0xffffffffu, t, 0);
+    if (t >= nItems)
+      return 2;
+    ticket = t;
+  }
+  const uint32_t region = (ticket / S.tilesPerRegion) * S.nRanks + S.rank;
   bool ready = true;
   if ((uint32_t)lane < S.nRanks)
     ready = (int)(*((volatile const unsigned int *)&S.myRegionFlags[(size_t)region * kMaxSlabs + lane]) - S.seq) >= 0;
   if (!__all_sync(0xffffffffu, ready))
     return 0;
-  unsigned int got = 0;
-  if (lane == 0)
-    got = atomicCAS(&P.sched[3], item, item + 1u) == item ? 1u : 0u;
-  if (!__shfl_sync(0xffffffffu, got, 0))
-    return 0; // another warp took it; the caller comes back
-  const uint32_t tile = region * S.tilesPerRegion + item % S.tilesPerRegion;
+  const uint32_t tile = region * S.tilesPerRegion + ticket % S.tilesPerRegion;
+  ticket = kNoTicket;
   if (tile < nTiles) {
     const uint32_t tyIdx = P.tileY0 + tile / P.tilesW, txIdx = P.tileX0 + tile % P.tilesW;
     const uint32_t px = txIdx * kTileW + (lane % kTileW), py = tyIdx * kTileH + (lane / kTileW);
@@ -855,11 +866,14 @@ __global__ void __launch_bounds__(kBlockThreads, 2) dvrSlabFrameKernel(const __g
   const uint32_t nChunks = (S.debugFlags & 2u) ? 0u : (uint32_t)((nBg + 255) / 256);
   const uint32_t nOwned = S.nRegions > S.rank ? (S.nRegions - S.rank + S.nRanks - 1u) / S.nRanks : 0u;
   const uint32_t nItems = (S.debugFlags & 4u) ? 0u : nOwned * S.tilesPerRegion;
+  uint32_t ticket = kNoTicket; // the composite item this warp holds (slabCompositeStep)
   bool bgLeft = nChunks > 0u, itemsLeft = nItems > 0u;
 
-  // ---- march; between two tiles every warp also takes one background chunk and, if a region this rank owns has
-  // become complete on all ranks, one composite item: the exchange is spread over the frame instead of landing on the
-  // SMs while only the stragglers of the march are left (that cost 40 us at N = 2, profiles/r02_sort_last_fused.md)
+  // ---- march; between two tiles every warp also takes one background chunk.  Composite items are drawn once the tile
+  // queue is empty: the warps that finish early then hold the tickets of the regions still being marched and composite
+  // them the moment the last rank's flag arrives.  (DVR_B200_SLAB_DEBUG bit 8 also looks at the held ticket between
+  // two tiles — it stretched the march more than it shortened the tail: 1878 vs 1901 frames/s at N = 2, 5092 vs 5412
+  // at N = 8, profiles/r02_sort_last_fused.md)
   for (uint32_t tile = nextTile(P.sched, lane); tile < nTiles; tile = nextTile(P.sched, lane)) {
     const uint32_t tyIdx = P.tileY0 + tile / P.tilesW, txIdx = P.tileX0 + tile % P.tilesW;
     const uint32_t px = txIdx * kTileW + (lane % kTileW), py = tyIdx * kTileH + (lane / kTileW);
@@ -898,7 +912,7 @@ __global__ void __launch_bounds__(kBlockThreads, 2) dvrSlabFrameKernel(const __g
       }
     }
     __syncwarp();
-    if (bgLeft) {
+    if (bgLeft && !(S.debugFlags & 16u)) {
       uint32_t chunk = 0;
       if (lane == 0)
         chunk = atomicAdd(&P.sched[2], 1u);
@@ -908,8 +922,8 @@ __global__ void __launch_bounds__(kBlockThreads, 2) dvrSlabFrameKernel(const __g
       else
         bgLeft = false;
     }
-    if (itemsLeft && !(S.debugFlags & 8u))
-      itemsLeft = slabTryComposite(S, nItems, nTiles, lane) != 2;
+    if (itemsLeft && (S.debugFlags & 8u)) // off by default: measured slower at N = 2, 4 and 8 (profiles/r02_sort_last_fused.md)
+      itemsLeft = slabCompositeStep(S, ticket, nItems, nTiles, lane) != 2;
   }
   if (S.timing && lane == 0)
     atomicMax(&S.timing[1], globalTimerNs());
@@ -932,7 +946,7 @@ __global__ void __launch_bounds__(kBlockThreads, 2) dvrSlabFrameKernel(const __g
   {
     const long long t0 = clock64();
     while (itemsLeft) {
-      const int r = slabTryComposite(S, nItems, nTiles, lane);
+      const int r = slabCompositeStep(S, ticket, nItems, nTiles, lane);
       if (r == 2)
         itemsLeft = false;
       else if (r == 0) {

@@ -75,6 +75,59 @@ def view_balanced_slab_ranges(nz: int, world: int, bounds_lo, bounds_hi, eye=Non
     return [(cuts[i], cuts[i + 1]) for i in range(world)]
 
 
+def slab_margin(nz: int, world: int, cap: int = 64) -> int:
+    """Extra slices a slab keeps resident on each side of its initial range so that ownership can move later
+    (dvr_field_set_owned_slices): a quarter of the mean slab thickness, between 4 and `cap` slices."""
+    return max(4, min(cap, nz // (4 * max(world, 1))))
+
+
+def creation_ranges(ranges: Sequence[Tuple[int, int]], nz: int, margin: int) -> List[Tuple[int, int]]:
+    """The ownership LIMITS every slab is created with: its initial range widened by `margin` slices on each side."""
+    return [(max(z0 - margin, 0), min(z1 + margin, nz)) for z0, z1 in ranges]
+
+
+def rebalance_slab_ranges(ranges: Sequence[Tuple[int, int]], times: Sequence[float],
+                          limits: Sequence[Tuple[int, int]], min_slices: int = 2) -> List[Tuple[int, int]]:
+    """New z-slice ownership from MEASURED per-GPU march times (any unit) of the current partition.
+
+    The cost of a slice is taken as uniform inside a slab (time / thickness); the cuts go where the cumulative cost
+    reaches k/N of the total, clamped to what both neighbours hold resident (`limits` = the ranges the slabs were
+    created with, see creation_ranges).  No voxel moves: every GPU applies its new range with
+    dvr_field_set_owned_slices before the next frame.  Deterministic, so ranks that all-gather the same times compute
+    the same cuts.  Apply repeatedly (2-3 rounds) — the cost density inside a slab is not really uniform."""
+    world = len(ranges)
+    if world != len(times) or world != len(limits):
+        raise ValueError("ranges, times and limits must have one entry per rank")
+    nz = ranges[-1][1]
+    if world == 1:
+        return [tuple(ranges[0])]
+    total = float(sum(times))
+    if not total > 0.0:
+        return [tuple(r) for r in ranges]
+    cuts = [ranges[0][0]]
+    acc, r = 0.0, 0
+    for k in range(1, world):
+        target = total * k / world
+        while r < world - 1 and acc + times[r] < target:
+            acc += times[r]
+            r += 1
+        z0, z1 = ranges[r]
+        frac = (target - acc) / times[r] if times[r] > 0 else 0.0
+        cuts.append(int(round(z0 + frac * (z1 - z0))))
+    cuts.append(nz)
+    for i in range(1, world):  # what the two neighbours of cut i can own, and a minimum thickness front to back
+        lo = max(limits[i][0], cuts[i - 1] + min_slices)
+        hi = limits[i - 1][1]
+        cuts[i] = min(max(cuts[i], lo), hi)
+    for i in range(world - 1, 0, -1):
+        cuts[i] = min(cuts[i], cuts[i + 1] - min_slices)
+    out = [(cuts[i], cuts[i + 1]) for i in range(world)]
+    for (z0, z1), (l0, l1) in zip(out, limits):
+        if z0 < l0 or z1 > l1 or z1 - z0 < 1:
+            return [tuple(r) for r in ranges]  # the limits leave no valid partition: keep the current one
+    return out
+
+
 def resident_range(z0: int, z1: int, nz: int) -> Tuple[int, int]:
     """Slices a slab must hold: its own plus one ghost slice on each side, clamped to the volume."""
     return max(z0 - 1, 0), min(z1 + 1, nz)
@@ -433,6 +486,41 @@ class SortLast:
                                      C.byref(x), C.c_void_p(stream))
         if rc != 0:
             raise RuntimeError(f"sort-last frame {seq}: {capi.last_error()}")
+
+    def calibrate(self, field, ranges, limits, camera, stream: int, rounds: int = 3, frames: int = 8):
+        """Feedback load balancing: times this rank's march of its slab alone (dvr_render_partial, CUDA events), gathers
+        every rank's time, moves the cuts to equal measured work (rebalance_slab_ranges) and applies this rank's new
+        range with dvr_field_set_owned_slices — no voxel moves, the slabs were created with a margin.  `ranges` is the
+        current partition (all ranks), `limits` the ranges the slabs were created with.  Call it at set-up and whenever
+        the camera has moved far; returns (ranges, times_ms of the last round, history)."""
+        torch, dist, capi = self.torch, self.dist, self.capi
+        ranges = [tuple(r) for r in ranges]
+        history = []
+        times = None
+        for _ in range(max(rounds, 1)):
+            p = self.params(1)
+            for i in range(2):
+                capi.render_partial(p, camera, self.instance, self.rgba_ptrs[0][self.rank], self.depth_ptrs[0][self.rank], stream)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for i in range(frames):
+                capi.render_partial(p, camera, self.instance, self.rgba_ptrs[0][self.rank], self.depth_ptrs[0][self.rank], stream)
+            e1.record()
+            torch.cuda.synchronize()
+            t = torch.tensor([e0.elapsed_time(e1) / frames], dtype=torch.float64, device=self.device)
+            if self.world > 1:
+                allt = [torch.zeros_like(t) for _ in range(self.world)]
+                dist.all_gather(allt, t, group=self.group)
+                times = [float(v.item()) for v in allt]
+            else:
+                times = [float(t.item())]
+            history.append({"ranges": [list(r) for r in ranges], "march_ms": [round(v, 4) for v in times]})
+            new = rebalance_slab_ranges(ranges, times, limits)
+            if new == ranges:
+                break
+            field.set_owned_slices(*new[self.rank])
+            ranges = new
+        return ranges, times, history
 
     def check_errors(self):
         """True when a bounded spin gave up (a producer never signalled)."""
