@@ -7,7 +7,7 @@ mkdir -p ../variants
 for spec in "$@"; do
   name="${spec%%:*}"; flags="${spec#*:}"
   d=../variants/.obj_$name; rm -rf $d; mkdir -p $d
-  for f in dvr_kernels dvr_macrocell dvr_api dvr_post dvr_nvdb_bricks; do
+  for f in dvr_kernels dvr_macrocell dvr_api dvr_post dvr_nvdb_bricks dvr_scene; do
     nvcc -O3 -std=c++17 -lineinfo -gencode arch=compute_100a,code=sm_100a -Xcompiler -fPIC --expt-relaxed-constexpr $flags -c $f.cu -o $d/$f.o &
   done
   wait

@@ -96,8 +96,14 @@ int launchWaitFlags(const unsigned int *flags, uint32_t n, uint32_t value, unsig
 #ifndef DVR_DEPTH_LANES_NVDB
 #define DVR_DEPTH_LANES_NVDB 1
 #endif
+// K2 (delta tracking) on a structured field is latency- and divergence-bound with 4 warps per scheduler
+// (profiles/r02_dpt_ncu.md): 2 / 3 / 4 CTAs per SM = 0.547 / 0.488 / 0.539 ms on C2 (profiles/r02u_brick_staging_probe.md)
+#ifndef DVR_OCC_DPT
+#define DVR_OCC_DPT 3
+#endif
 template <bool SKIP, bool STATS, bool SINGLE, int KIND, bool DPT, int G>
-__global__ void __launch_bounds__(kBlockThreads, (KIND >= FIELD_NANOVDB ? DVR_OCC_NVDB : DVR_OCC)) dvrFrameKernel(const __grid_constant__ FrameLaunch P)
+__global__ void __launch_bounds__(kBlockThreads,
+    (KIND >= FIELD_NANOVDB ? DVR_OCC_NVDB : (DPT && SINGLE && KIND == FIELD_STRUCTURED ? DVR_OCC_DPT : DVR_OCC))) dvrFrameKernel(const __grid_constant__ FrameLaunch P)
 {
   static_assert(!(DPT && G != 1) && !(!SINGLE && G != 1), "depth lanes: single-volume marching kernels only");
   __shared__ float4 s_tf[(SINGLE ? 1 : kMaxInlineInstances) * DVR_TF_SIZE];
