@@ -71,6 +71,9 @@ def parse_args():
     ap.add_argument("--c4-scaling", type=int, default=-1,
                     help="N = 8 runs: also measure BASELINE config C4 (4096^3 f32, 256 GiB, sort-last) on 2, 4 and 8 of the "
                          "ranks (extra.c4_scaling); -1 = on for the default C2 run at N = 8, 0 = off")
+    ap.add_argument("--c3-sort-first", type=int, default=-1,
+                    help="after the headline run on N > 1 GPUs, also render BASELINE config C3 (2048^3 UFIXED16, 4K) "
+                         "sort-first on all ranks (extra.c3_sort_first); -1 = on for the default C2 sort-last run, 0 = off")
     ap.add_argument("--save-frame", default="", help="rank 0: write frame 0 of the timed scene (uint32 sRGB8) to this .npy")
     ap.add_argument("--extra-configs", default="c3,c5",
                     help="N=1 default run only: other BASELINE configs measured after the headline (extra.configs), "
@@ -832,16 +835,122 @@ def run_ours(args, torch, dist, rank, world):
         driver.host_frame.close(dist if world > 1 else None)
         driver.host_frame = None
     do_c4 = args.c4_scaling == 1 or (args.c4_scaling < 0 and world == 8 and args.config == "c2" and mode == "sort-last")
-    if do_c4 and world >= 2:
-        # free the headline scene on every rank first: a C4 slab is up to 137 GB per GPU
+    do_c3 = args.c3_sort_first == 1 or (args.c3_sort_first < 0 and world >= 2 and args.config == "c2" and mode == "sort-last")
+    if (do_c4 or do_c3) and world >= 2:
+        # free the headline scene on every rank first: a C4 slab is up to 137 GB per GPU, a C3 replica 16 GiB (+ 16 GiB
+        # of staging while it is generated)
         driver.close()
         volume.destroy()
         field.destroy()
         torch.cuda.empty_cache()
+    if do_c3 and world >= 2:
+        try:
+            c3 = measure_c3_sort_first(args, torch, dist, capi, rank, world, device, stream)
+        except Exception as e:  # a secondary measurement must never take the headline line down
+            c3 = f"unavailable: {type(e).__name__}: {e}"
+        if rank == 0:
+            out["extra"]["c3_sort_first"] = c3
+    if do_c4 and world >= 2:
         c4 = measure_c4_scaling(args, torch, dist, capi, rank, world, device, stream)
         if rank == 0:
             out["extra"]["c4_scaling"] = c4
     return out
+
+
+def measure_c3_sort_first(base_args, torch, dist, capi, rank, world, device, stream):
+    """BASELINE config C3 — 2048^3 UFIXED16 sparse shells at 3840x2160, macrocell skipping — rendered sort-first on all
+    ranks of this job (field replicated, tile rows interleaved, colour stored straight into the display rank's frame
+    through a peer pointer), next to the same frame rendered by the display rank alone from its own replica: the
+    assembled frame must be bit-identical, and the ratio of the two rates is the sort-first scaling at this N."""
+    import argparse
+    from visrtx_b200 import multigpu
+    a = argparse.Namespace(**vars(base_args))
+    a.config, a.skip, a.field, a.rate, a.mode = "c3", -1, "ml", 0.5, "sort-first"
+    a = apply_preset(a)
+    n, W, H = a.size, a.width, a.height
+    npx = W * H
+    FMT, INTEG, BG = capi.DVR_FORMAT_UFIXED8_RGBA_SRGB, capi.DVR_INTEGRATOR_DEFAULT, (0.1, 0.1, 0.1, 1.0)
+    t0 = time.perf_counter()
+    vol = make_scene(a, torch, device)
+    field = create_field(a, capi, vol, stream)
+    torch.cuda.synchronize()
+    del vol
+    torch.cuda.empty_cache()
+    tf = capi.tf_discretize(color=scene_colormap(a))
+    volume = capi.Volume.create(field, tf, (0.0, 1.0), a.unit_distance, 0, stream)
+    inst, ninst = capi.make_instances([volume], None, [0])
+    cam, _ = orbit(a)
+    torch.cuda.synchronize()
+    setup_s = time.perf_counter() - t0
+    K = 30
+    res = {"workload": workload_name(a), "unit": "frames/s", "n_gpus": world, "steps": K, "macrocell_skipping": bool(a.skip)}
+    bands = {}
+    frame0 = None
+    for band in (1, 8):  # tile rows handed out singly / in bands of 8 rows (32 pixel rows)
+        drv = multigpu.SortFirst(capi, torch, dist, rank, world, device, W, H, inst, ninst, FMT, INTEG, a.rate, BG,
+                                 skip=bool(a.skip), tile_band=band, host_mirror=False)
+        drv.render(0, cam, stream)
+        torch.cuda.synchronize()
+        dist.barrier()
+        f0 = drv.color_tensor() if rank == 0 else None
+        torch.cuda.synchronize()
+        dist.barrier()
+        for i in range(5):
+            drv.render(1 + i, cam, stream)
+        torch.cuda.synchronize()
+        dist.barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(K):
+            drv.render(6 + i, cam, stream)
+        e1.record()
+        torch.cuda.synchronize()
+        t = torch.tensor([e0.elapsed_time(e1) / K], dtype=torch.float64, device=device)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        bands[band] = float(t.item())
+        if band == 1:
+            frame0 = f0
+        drv.close()
+    best = min(bands, key=bands.get)
+    # the display rank alone, whole frame from its own replica
+    single_ms, identical = None, None
+    if rank == 0:
+        accum = torch.zeros((npx, 4), dtype=torch.float32, device=device)
+        color = torch.zeros(npx, dtype=torch.int32, device=device)
+        depth = torch.zeros(npx, dtype=torch.float32, device=device)
+        fb = capi.frame_buffers(accum.data_ptr(), color.data_ptr(), depth.data_ptr())
+        mk = lambda fid: capi.frame_params(W, H, FMT, INTEG, fid, -1, 1, a.rate, BG, skip=bool(a.skip))
+        capi.render(mk(0), cam, inst, ninst, fb, stream)
+        torch.cuda.synchronize()
+        identical = bool(torch.equal(color, frame0))
+        for i in range(5):
+            capi.render(mk(1 + i), cam, inst, ninst, fb, stream)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(K):
+            capi.render(mk(6 + i), cam, inst, ninst, fb, stream)
+        e1.record()
+        torch.cuda.synchronize()
+        single_ms = e0.elapsed_time(e1) / K
+    dist.barrier()
+    volume.destroy()
+    field.destroy()
+    torch.cuda.empty_cache()
+    if rank != 0:
+        return None
+    res.update({"value": 1000.0 / bands[best], "ms_per_step": bands[best], "tile_band": best,
+                "ms_per_step_by_tile_band": {str(k): v for k, v in bands.items()},
+                "single_gpu_value": 1000.0 / single_ms, "single_gpu_ms": single_ms,
+                "speedup_over_one_gpu": single_ms / bands[best], "setup_s": setup_s,
+                "parity_vs_single": {"bit_identical": identical, "pass": identical,
+                                     "what": f"frame 0 assembled by {world} GPUs (sort-first, peer stores into the display "
+                                             "rank's frame) == frame 0 rendered by the display rank alone, every sRGB8 "
+                                             "pixel; the same scene against O-gpu: extra.configs.c3.parity of the N = 1 line"},
+                "what": "field replicated on every GPU, tile rows interleaved across ranks (the best of tileBand 1 and 8 "
+                        "is the value), one frame kernel per GPU storing colour into the display rank's frame over "
+                        "NVLink, a device-side barrier per frame; CUDA events, max over ranks"})
+    return res
 
 
 def parity_vs_single(args, torch, dist, capi, driver, cam, rank, world, device, stream, mode):

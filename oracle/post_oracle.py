@@ -5,9 +5,13 @@ numpy restatement of tsd/src/render_pipeline/passes:
   composite_depth       compositeFrame               AnariSceneRenderPass.cpp:30-46
   outline               computeOutline + shadePixel  OutlineRenderPass.cpp:13-46
   visualize_depth       computeDepthImage            VisualizeDepthPass.cpp:13-21
-helium::cvt_color_to_float4 / cvt_color_to_uint32 live in the ANARI-SDK (helium/helium_math.h, >= 0.15), which is
-not vendored with the reference: c/255.f per byte, uint32(255.f * clamp(f,0,1)) per component, r|g<<8|b<<16|a<<24
-(parity unpinned for these two helpers).  linalg lerp(a,b,t) = a*(1-t) + b*t, every operation rounded to fp32.
+PINNED (tests/test_post_ref_host.py): every function here is checked bit for bit against the reference's own pass
+sources compiled in place into oracle/_ref/libref_post.so (oracle/ref_post/, recipe in oracle/Makefile) — loop bounds,
+the unsigned window arithmetic of computeOutline, comparison / clamp / truncation semantics are reference code.
+Still restated, in the shim that build uses as well as here: helium::cvt_color_to_float4 / cvt_color_to_uint32 and
+linalg's lerp live in the ANARI-SDK (helium/helium_math.h >= 0.15, anari_cpp/ext/linalg.h), which is not vendored with
+the reference: c/255.f per byte, uint32(255.f * clamp(f,0,1)) per component, r|g<<8|b<<16|a<<24; lerp(a,b,t) =
+a*(1-t) + b*t, every operation rounded to fp32 (parity unpinned for these three helpers only).
 """
 import numpy as np
 

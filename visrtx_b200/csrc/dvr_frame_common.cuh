@@ -53,8 +53,10 @@ struct AccumCtx
 
 __device__ __forceinline__ void accumResults(const AccumCtx &P, uint32_t px, uint32_t py, float4 color,
     float depth, float3 albedo, float3 normal, uint32_t primID, uint32_t objID, uint32_t instID,
-    int frameIDOffset, bool init)
+    int frameIDOffset, bool init, const float4 *preAccum = nullptr, const float *preDepth = nullptr)
 {
+  // preAccum / preDepth: the pixel's accumulation / depth values loaded earlier by the caller (K2r issues the loads
+  // when it draws the pixel, so their latency is covered by the walk), instead of two dependent loads here
   const BuffersDev &fb = P.fb;
   const uint32_t idx = px + py * P.width;
   const int frameID = P.frameID + frameIDOffset;
@@ -67,7 +69,7 @@ __device__ __forceinline__ void accumResults(const AccumCtx &P, uint32_t px, uin
   if (init) {
     acc = tm;
   } else {
-    acc = __ldcg(&fb.accum[idx]); // streamed once per frame: keep it out of L1, where the field's texels live
+    acc = preAccum ? *preAccum : __ldcg(&fb.accum[idx]); // streamed once per frame: keep it out of L1, where the field's texels live
     acc.x = __fadd_rn(acc.x, tm.x);
     acc.y = __fadd_rn(acc.y, tm.y);
     acc.z = __fadd_rn(acc.z, tm.z);
@@ -94,7 +96,7 @@ __device__ __forceinline__ void accumResults(const AccumCtx &P, uint32_t px, uin
 
   bool closer = true;
   if (fb.depth) {
-    const float prev = init ? FLT_MAX : __ldcg(&fb.depth[idx]);
+    const float prev = init ? FLT_MAX : (preDepth ? *preDepth : __ldcg(&fb.depth[idx]));
     closer = depth < prev;
     if (closer)
       fb.depth[idx] = depth;

@@ -1,9 +1,11 @@
 // dvr_kernels.cu — frame kernel K1 (ray generation + march + background + accumulate/tonemap/encode),
 // the sort-last partial kernel, the resolve kernel K3 and the `over` compositing kernel.
 // Target: sm_100a only.  See DESIGN.md for the layout / scheduling rationale.
+#include <cstdlib>
 #include "dvr_internal.h"
 #include "dvr_march.cuh"
 #include "dvr_dpt.cuh"
+#include "dvr_dpt_regen.cuh"
 #include "dvr_frame_common.cuh"
 
 namespace dvr {
@@ -308,8 +310,45 @@ static int launchFrameK(const FrameLaunch &p, cudaStream_t s)
   return launchFrameT<SKIP, STATS, true, FIELD_STRUCTURED, false>(p, s);
 }
 
+// K2r: persistent lanes with pixel regeneration (dvr_dpt_regen.cuh)
+template <int KIND>
+static int launchDptRegenT(const FrameLaunch &p, cudaStream_t s)
+{
+  static int blocksPerSm = 0;
+  if (blocksPerSm == 0) {
+    DVR_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocksPerSm, dvrDptRegenKernel<KIND>, kBlockThreads, 0));
+    if (blocksPerSm < 1)
+      blocksPerSm = 1;
+  }
+  const uint32_t nPix = p.tilesW * p.tilesH * 32u;
+  uint32_t grid = (uint32_t)(smCount() * blocksPerSm);
+  const uint32_t need = (nPix + kBlockThreads - 1) / kBlockThreads;
+  if (grid > need)
+    grid = need;
+  if (grid == 0)
+    grid = 1;
+  dvrDptRegenKernel<KIND><<<grid, kBlockThreads, 0, s>>>(p);
+  DVR_CUDA(cudaGetLastError());
+  countLaunch();
+  return DVR_OK;
+}
+
+static bool dptRegenEnabled()
+{
+  // "0": keep the tile kernel.  Read at every launch so that one process can A/B both (bit-identity test)
+  const char *e = std::getenv("DVR_B200_DPT_REGEN");
+  return !(e && e[0] == '0');
+}
+
 int launchFrame(const FrameLaunch &p, bool skip, bool stats, cudaStream_t s)
 {
+  if (p.integrator == DVR_INTEGRATOR_DPT && p.nInst == 1 && p.inl[0].identity && dptRegenEnabled()) {
+    if (p.inl[0].v.f.kind == FIELD_NANOVDB)
+      return launchDptRegenT<FIELD_NANOVDB>(p, s);
+    if (p.inl[0].v.f.kind == FIELD_NANOVDB_QUANT)
+      return launchDptRegenT<FIELD_NANOVDB_QUANT>(p, s);
+    return launchDptRegenT<FIELD_STRUCTURED>(p, s);
+  }
   if (p.integrator == DVR_INTEGRATOR_DPT || p.integrator == DVR_INTEGRATOR_TEST) {
     // delta tracking has no fixed-step lattice (no SKIP/STATS variants); the test renderer shares the instantiation
     if (p.nInst != 1)
