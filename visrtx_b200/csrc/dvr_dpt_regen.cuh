@@ -13,6 +13,12 @@
 // traces it, and when, cannot change its result: frames are bit-identical to the tile kernel
 // (tests/test_gpu_dpt.py::test_regenerated_lanes_equal_the_tile_kernel).
 //
+// STATUS: opt-in experiment (DVR_B200_DPT_REGEN=1), not the default.  It is bit-identical to the tile kernel and keeps
+// ~28 of 32 lanes busy, but it is slower on the C2 dpt scene at every refill threshold (first version, one atomicAdd per
+// service round: refill 1 / 4 / 8 / 16 = 0.773 / 0.694 / 0.637 / 0.555 ms; with the chunk queue and preloaded
+// accumulation values: 4 / 8 / 16 / 24 = 0.903 / 0.787 / 0.699 / 0.693 ms; tile kernel 0.488 ms, profiles/r02_dpt_ncu.md):
+// the closer the schedule gets to "refill when the whole warp is done", the faster it runs.
+//
 // Covers what the benchmarked dpt scenes are: one volume instance with an identity transform (structuredRegular or
 // NanoVDB).  Several instances, transformed instances and the `test` renderer keep the tile kernel.
 #pragma once

@@ -335,9 +335,11 @@ static int launchDptRegenT(const FrameLaunch &p, cudaStream_t s)
 
 static bool dptRegenEnabled()
 {
-  // "0": keep the tile kernel.  Read at every launch so that one process can A/B both (bit-identity test)
+  // Opt-in ("1"): measured SLOWER than the tile kernel on the C2 dpt scene at every refill threshold (0.55-0.90 ms
+  // against 0.488 ms, profiles/r02_dpt_ncu.md), so the tile kernel stays the default.  Read at every launch so that
+  // one process can A/B both (bit-identity test).
   const char *e = std::getenv("DVR_B200_DPT_REGEN");
-  return !(e && e[0] == '0');
+  return e && e[0] == '1';
 }
 
 int launchFrame(const FrameLaunch &p, bool skip, bool stats, cudaStream_t s)
