@@ -2017,9 +2017,15 @@ int dvr_render_slab_frame(const DvrFrameParams *p, const DvrCamera *camera, cons
     static const unsigned spinNs = []() {
       const char *e = std::getenv("DVR_B200_SPIN_NS");
       const int v = e ? std::atoi(e) : 0;
-      return v > 0 ? (unsigned)v : 100u;
+      return v > 0 ? (unsigned)v : 400u; // 100 / 400..3200 / 1000 / 2000 ns at N = 2: 1881 / 1917 / 1917 / 1912 frames/s (call X)
     }();
     S.spinSleepNs = spinNs;
+    static const unsigned capNs = []() {
+      const char *e = std::getenv("DVR_B200_SPIN_CAP_NS");
+      const int v = e ? std::atoi(e) : 0;
+      return v > 0 ? (unsigned)v : 3200u;
+    }();
+    S.spinSleepCapNs = capNs > spinNs ? capNs : spinNs;
     static const unsigned dbg = []() {
       const char *e = std::getenv("DVR_B200_SLAB_DEBUG");
       return e ? (unsigned)std::atoi(e) : 0u;

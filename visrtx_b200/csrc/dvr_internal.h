@@ -131,7 +131,7 @@ struct SlabFrameLaunch
   int waitAllResolved;                      // display rank: do not retire before every rank's strip has landed
   size_t bgPixelBegin, bgPixelEnd;          // this rank's share of the pixels outside the tile window
   unsigned long long *timing;               // optional %globaltimer stamps (DvrSlabExchange::timing)
-  unsigned spinSleepNs;                     // back-off of the warps that wait for region flags
+  unsigned spinSleepNs, spinSleepCapNs;     // back-off of the warps that wait for region flags: first interval, cap of the doubling
   unsigned debugFlags;                      // timing experiments only (DVR_B200_SLAB_DEBUG; 8: also composite between march tiles, 16: no background chunk between march tiles): 1 no region flags, 2 no
                                             // background strip, 4 no compositing — frames are then incomplete
 };

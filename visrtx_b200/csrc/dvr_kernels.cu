@@ -992,18 +992,25 @@ __global__ void __launch_bounds__(kBlockThreads, 2) dvrSlabFrameKernel(const __g
   // ---- ... and of the owned regions: the last ones complete when the slowest rank finishes its march
   {
     const long long t0 = clock64();
+    // Poll interval: starts at spinSleepNs and doubles up to spinSleepCapNs while the held ticket's region is not
+    // complete (every poll of every waiting warp is a strong load of the same few L2 lines, on every SM, next to the
+    // warps that are still marching); back to the start after each composited tile.
+    unsigned sleepNs = S.spinSleepNs;
     while (itemsLeft) {
       const int r = slabCompositeStep(S, ticket, nItems, nTiles, lane);
       if (r == 2)
         itemsLeft = false;
-      else if (r == 0) {
-        __nanosleep(S.spinSleepNs);
+      else if (r == 1)
+        sleepNs = S.spinSleepNs;
+      if (r == 0) {
+        __nanosleep(sleepNs);
+        sleepNs = min(sleepNs * 2u, S.spinSleepCapNs);
         if (clock64() - t0 > 4000000000ll) { // ~2 s: a missing producer must not hang the GPU
           if (lane == 0 && S.c.sync.errorFlag)
             *S.c.sync.errorFlag = 1u;
           break;
         }
-      } else if (S.timing && lane == 0)
+      } else if (r == 1 && S.timing && lane == 0)
         atomicMax(&S.timing[5], globalTimerNs());
     }
   }
@@ -1036,8 +1043,46 @@ __global__ void __launch_bounds__(kBlockThreads, 2) dvrSlabFrameKernel(const __g
   }
 }
 
-int launchSlabFrame(const SlabFrameLaunch &p, cudaStream_t s)
+// This rank's share of the pixels outside the window as a launch of its own, ahead of the fused frame on the same
+// stream — an opt-in (DVR_B200_SLAB_BG_LAUNCH=1).  Inside the fused kernel the chunks sit between march tiles: a
+// dependent accumulation read, 8 rows of stores and the index arithmetic per chunk on the critical path of a warp cost
+// the march phase 18 us at N = 2 (call Y) and 24 us at N = 8 (call Q).  As a launch of its own the strip takes that
+// out of the fused kernel (526 -> 515 us at N = 2) but costs about as much as a serialized launch (525 vs 522 us per
+// frame), and with the colour mirrored to pinned host memory its PCIe stores no longer overlap the march (e2e 1603 vs
+// 1781 frames/s at N = 2, call Z): the in-kernel placement stays the default.
+__global__ void __launch_bounds__(256) dvrSlabBackgroundKernel(const __grid_constant__ SlabFrameLaunch S)
 {
+  const int lane = threadIdx.x & 31;
+  const size_t nBg = S.bgPixelEnd > S.bgPixelBegin ? S.bgPixelEnd - S.bgPixelBegin : 0;
+  const uint32_t nChunks = (uint32_t)((nBg + 255) / 256);
+  const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nWarps = (gridDim.x * blockDim.x) >> 5;
+  for (uint32_t chunk = warp; chunk < nChunks; chunk += nWarps)
+    slabBackgroundChunk(S, chunk, lane);
+}
+
+static bool slabBackgroundInKernel()
+{
+  static const bool ownLaunch = [] {
+    const char *e = std::getenv("DVR_B200_SLAB_BG_LAUNCH");
+    return e && e[0] == '1';
+  }();
+  return !ownLaunch;
+}
+
+int launchSlabFrame(const SlabFrameLaunch &pIn, cudaStream_t s)
+{
+  SlabFrameLaunch p = pIn;
+  if (!(p.debugFlags & 2u) && !slabBackgroundInKernel()) {
+    const size_t nBg = p.bgPixelEnd > p.bgPixelBegin ? p.bgPixelEnd - p.bgPixelBegin : 0;
+    const unsigned nChunks = (unsigned)((nBg + 255) / 256);
+    if (nChunks) {
+      const unsigned want = (nChunks + 7u) / 8u, cap = (unsigned)smCount() * 4u;
+      dvrSlabBackgroundKernel<<<want < cap ? want : cap, 256, 0, s>>>(p);
+      DVR_CUDA(cudaGetLastError());
+      countLaunch();
+    }
+    p.debugFlags |= 2u; // the fused kernel then has no background chunks of its own
+  }
   static int bps[2] = {0, 0};
   const int k = p.m.skip ? 1 : 0;
   if (bps[k] == 0) {
