@@ -733,7 +733,11 @@ def run_ours(args, torch, dist, rank, world):
                   "share_per_rank": share},
     }
     if mode == "sort-last" and world > 1 and args.fused:
-        # phases of the fused launch on every rank (%globaltimer stamps of 20 extra, untimed frames)
+        # phases of the fused launch on every rank (%globaltimer stamps of 20 extra, untimed frames), in the
+        # configuration of the device-timed region: the e2e loop left the host mirror on, and its PCIe stores stretch
+        # the march phase rank by rank (until call AB the phases were stamped with it: the display rank looked 40-80 us
+        # slower than the others, profiles/r02_sort_last_fused.md)
+        driver.stream_to_host(False)
         nt = 20
         tbuf = torch.zeros((nt, 8), dtype=torch.int64, device=device)
         tbuf[:, 0] = torch.iinfo(torch.int64).max

@@ -77,8 +77,10 @@ def view_balanced_slab_ranges(nz: int, world: int, bounds_lo, bounds_hi, eye=Non
 
 def slab_margin(nz: int, world: int, cap: int = 64) -> int:
     """Extra slices a slab keeps resident on each side of its initial range so that ownership can move later
-    (dvr_field_set_owned_slices): a quarter of the mean slab thickness, between 4 and `cap` slices."""
-    return max(4, min(cap, nz // (4 * max(world, 1))))
+    (dvr_field_set_owned_slices): half of the mean slab thickness, between 4 and `cap` slices.  (A quarter was not
+    enough at N = 8: the cuts of the time-balanced partition sit up to 30 slices from the 1/r^2 model's, and the rounds
+    that balance the fused frame's march phases need room beyond that.)"""
+    return max(4, min(cap, nz // (2 * max(world, 1))))
 
 
 def creation_ranges(ranges: Sequence[Tuple[int, int]], nz: int, margin: int) -> List[Tuple[int, int]]:
@@ -87,14 +89,17 @@ def creation_ranges(ranges: Sequence[Tuple[int, int]], nz: int, margin: int) -> 
 
 
 def rebalance_slab_ranges(ranges: Sequence[Tuple[int, int]], times: Sequence[float],
-                          limits: Sequence[Tuple[int, int]], min_slices: int = 2) -> List[Tuple[int, int]]:
+                          limits: Sequence[Tuple[int, int]], min_slices: int = 2,
+                          damping: float = 1.0) -> List[Tuple[int, int]]:
     """New z-slice ownership from MEASURED per-GPU march times (any unit) of the current partition.
 
     The cost of a slice is taken as uniform inside a slab (time / thickness); the cuts go where the cumulative cost
     reaches k/N of the total, clamped to what both neighbours hold resident (`limits` = the ranges the slabs were
     created with, see creation_ranges).  No voxel moves: every GPU applies its new range with
     dvr_field_set_owned_slices before the next frame.  Deterministic, so ranks that all-gather the same times compute
-    the same cuts.  Apply repeatedly (2-3 rounds) — the cost density inside a slab is not really uniform."""
+    the same cuts.  Apply repeatedly (2-3 rounds) — the cost density inside a slab is not really uniform.
+    `damping` < 1 moves every cut only that fraction of the way (for times that contain a part which does not scale
+    with the slab's thickness, e.g. the march phase measured inside the fused frame)."""
     world = len(ranges)
     if world != len(times) or world != len(limits):
         raise ValueError("ranges, times and limits must have one entry per rank")
@@ -115,6 +120,10 @@ def rebalance_slab_ranges(ranges: Sequence[Tuple[int, int]], times: Sequence[flo
         frac = (target - acc) / times[r] if times[r] > 0 else 0.0
         cuts.append(int(round(z0 + frac * (z1 - z0))))
     cuts.append(nz)
+    if damping < 1.0:
+        for i in range(1, world):
+            old = ranges[i][0]
+            cuts[i] = int(round(old + damping * (cuts[i] - old)))
     for i in range(1, world):  # what the two neighbours of cut i can own, and a minimum thickness front to back
         lo = max(limits[i][0], cuts[i - 1] + min_slices)
         hi = limits[i - 1][1]
@@ -487,12 +496,19 @@ class SortLast:
         if rc != 0:
             raise RuntimeError(f"sort-last frame {seq}: {capi.last_error()}")
 
-    def calibrate(self, field, ranges, limits, camera, stream: int, rounds: int = 3, frames: int = 8):
+    def calibrate(self, field, ranges, limits, camera, stream: int, rounds: int = 3, frames: int = 8,
+                  fused_rounds: int = 3):
         """Feedback load balancing: times this rank's march of its slab alone (dvr_render_partial, CUDA events), gathers
         every rank's time, moves the cuts to equal measured work (rebalance_slab_ranges) and applies this rank's new
         range with dvr_field_set_owned_slices — no voxel moves, the slabs were created with a margin.  `ranges` is the
         current partition (all ranks), `limits` the ranges the slabs were created with.  Call it at set-up and whenever
-        the camera has moved far; returns (ranges, times_ms of the last round, history)."""
+        the camera has moved far; returns (ranges, times_ms of the last round, history).
+
+        `fused_rounds` more rounds then balance what the frame time really depends on: the march PHASE of every rank
+        inside the fused frame (first CTA -> last tile, %globaltimer stamps of dvr_render_slab_frame), which is not
+        the march alone — flags, background chunks and composites that run beside it stretch it differently per rank
+        (N = 8, equal marches alone: 170 us on the display rank, 141 us on the last one, profiles/r02_sort_last_fused.md).
+        Part of that time does not scale with the slab's thickness, so these rounds are damped."""
         torch, dist, capi = self.torch, self.dist, self.capi
         ranges = [tuple(r) for r in ranges]
         history = []
@@ -520,6 +536,29 @@ class SortLast:
                 break
             field.set_owned_slices(*new[self.rank])
             ranges = new
+        if self.world > 1 and self.fused:
+            for _ in range(max(fused_rounds, 0)):
+                tbuf = torch.zeros((frames, 8), dtype=torch.int64, device=self.device)
+                tbuf[:, 0] = torch.iinfo(torch.int64).max
+                for i in range(2):
+                    self.render(1 + i, camera, stream)
+                for i in range(frames):
+                    self.timing_ptr = tbuf[i].data_ptr()
+                    self.render(3 + i, camera, stream)
+                self.timing_ptr = 0
+                torch.cuda.synchronize()
+                t = ((tbuf[:, 1] - tbuf[:, 0]).double().median() / 1e6).reshape(1)  # ms
+                allt = [torch.zeros_like(t) for _ in range(self.world)]
+                dist.all_gather(allt, t, group=self.group)
+                ftimes = [float(v.item()) for v in allt]
+                history.append({"ranges": [list(r) for r in ranges], "fused_march_ms": [round(v, 4) for v in ftimes]})
+                if not all(v > 0.0 for v in ftimes):
+                    break
+                new = rebalance_slab_ranges(ranges, ftimes, limits, damping=0.7)
+                if new == ranges:
+                    break
+                field.set_owned_slices(*new[self.rank])
+                ranges = new
         return ranges, times, history
 
     def check_errors(self):
