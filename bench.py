@@ -74,6 +74,10 @@ def parse_args():
     ap.add_argument("--c3-sort-first", type=int, default=-1,
                     help="after the headline run on N > 1 GPUs, also render BASELINE config C3 (2048^3 UFIXED16, 4K) "
                          "sort-first on all ranks (extra.c3_sort_first); -1 = on for the default C2 sort-last run, 0 = off")
+    ap.add_argument("--anari-multi-gpu", type=int, default=-1,
+                    help="N > 1: rank 0 also drives ALL N GPUs through the ANARI C API in one process (device parameter "
+                         "cudaDevices, sort-last) while the other ranks wait (extra.anari_multi_gpu); -1 = on for the "
+                         "default C2 sort-last run, 0 = off")
     ap.add_argument("--save-frame", default="", help="rank 0: write frame 0 of the timed scene (uint32 sRGB8) to this .npy")
     ap.add_argument("--extra-configs", default="c3,c5",
                     help="N=1 default run only: other BASELINE configs measured after the headline (extra.configs), "
@@ -375,13 +379,17 @@ def cpu_baseline(args, torch, vol_dev, samples_per_frame, rows=0):
 class AnariE2E:
     """The C2 scene built through the ANARI C API (what an application does), for the e2e number."""
 
-    def __init__(self, args, torch, device, vol_dev, rank, world, mode):
+    def __init__(self, args, torch, device, vol_dev, rank, world, mode, gpus=None):
         from visrtx_b200 import anari as A
         from visrtx_b200 import scenes
         self.A, self.args, self.torch = A, args, torch
         n, W, H = args.size, args.width, args.height
         d = self.d = A.Device()
-        d.set(d.handle, "cudaDevice", A.INT32, device.index)
+        if gpus:  # one process, several GPUs behind the same anari* calls (display GPU first)
+            d.set(d.handle, "cudaDevices", A.STRING, ",".join(str(g) for g in gpus))
+            d.set(d.handle, "multiGpuMode", A.STRING, "sortLast")
+        else:
+            d.set(d.handle, "cudaDevice", A.INT32, device.index)
         d.commit(d.handle)
         torch.cuda.synchronize()
         if args.field == "fog":
@@ -854,11 +862,79 @@ def run_ours(args, torch, dist, rank, world):
             c3 = f"unavailable: {type(e).__name__}: {e}"
         if rank == 0:
             out["extra"]["c3_sort_first"] = c3
+    do_anari = world >= 2 and (args.anari_multi_gpu == 1 or (args.anari_multi_gpu < 0 and args.config == "c2"
+                                                             and mode == "sort-last"))
+    if do_anari and not (do_c4 or do_c3):
+        driver.close()
+        volume.destroy()
+        field.destroy()
+        torch.cuda.empty_cache()
+    if do_anari:
+        am = measure_anari_multi_gpu(args, torch, dist, rank, world, device)
+        if rank == 0:
+            out["extra"]["anari_multi_gpu"] = am
     if do_c4 and world >= 2:
         c4 = measure_c4_scaling(args, torch, dist, capi, rank, world, device, stream)
         if rank == 0:
             out["extra"]["c4_scaling"] = c4
     return out
+
+
+def measure_anari_multi_gpu(args, torch, dist, rank, world, device):
+    """The drop-in boundary on N GPUs: rank 0 alone builds the C2 scene through the ANARI C API on a device whose
+    `cudaDevices` parameter lists all N GPUs of this job (multiGpuMode sortLast: one process, peer access, z-slabs made
+    by the field's finalize, one fused frame kernel per GPU behind anariRenderFrame, the display GPU's frame behind
+    anariMapFrame) and runs the same per-step sequence as the N = 1 e2e — camera parameters, commit, render, wait, map
+    the colour channel to the host.  The other ranks hold no scene any more and wait at the barrier."""
+    res = None
+    # The waiting ranks must not wait ON their GPU: an NCCL barrier is a kernel that spins on the device, next to which
+    # the fused frame kernel (a persistent grid that needs every CTA resident) crawls — 343 frames/s at N = 2 with it.
+    # A gloo group gives a barrier that blocks on the host.
+    torch.cuda.synchronize()
+    cpu_group = dist.new_group(backend="gloo")
+    if rank == 0:
+        vol = e = None
+        try:
+            vol = make_scene(args, torch, device)
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            e = AnariE2E(args, torch, device, vol, 0, 1, "single", gpus=list(range(world)))
+            K = max(args.steps, 20)
+            e.prepare(K + 3)
+            for i in range(3):
+                e.step(i)
+            setup_s = time.perf_counter() - t0
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            for i in range(K):
+                e.step(i)
+            dt = time.perf_counter() - t0
+            ndev = e.d.get_property(e.d.handle, "cudaDeviceCount", e.A.INT32)
+            hb = e.bytes_per_step()
+            res = {"value": K / dt, "unit": "frames/s", "steps": K, "n_gpus_in_device": int(ndev), "setup_s": setup_s,
+                   "h2d_bytes_per_step": hb[0], "d2h_bytes_per_step": hb[1],
+                   "what": "ONE process, ANARI C API of libanari_library_visrtx_b200.so with device parameters "
+                           f"cudaDevices=0..{world - 1}, multiGpuMode=sortLast: anariSetParameter(camera) + "
+                           "anariCommitParameters + anariRenderFrame + anariFrameReady(WAIT) + anariMapFrame("
+                           "channel.color -> host) per step, wall clock; parity of this path against one GPU: "
+                           "tests/test_gpu_anari_multigpu.py"}
+            e.close()
+            e = None
+        except Exception as ex:  # a secondary measurement must never take the headline line down
+            res = f"unavailable: {type(ex).__name__}: {ex}"
+        finally:
+            del vol, e
+            # the multi-GPU device switches the CUDA current device while it works: hand this process' own GPU back to
+            # everything that follows (torch and the C-ABI both act on the current device)
+            try:
+                C.CDLL("libcudart.so").cudaSetDevice(C.c_int(device.index))
+            except OSError:
+                pass
+            torch.cuda.set_device(device)
+            torch.cuda.empty_cache()
+    dist.barrier(group=cpu_group)
+    dist.destroy_process_group(cpu_group)
+    return res
 
 
 def measure_c3_sort_first(base_args, torch, dist, capi, rank, world, device, stream):
