@@ -1991,6 +1991,10 @@ int dvr_render_slab_frame(const DvrFrameParams *p, const DvrCamera *camera, cons
   fillPartialLaunch(p, camera, instance, const_cast<float *>(x->partialRgba[x->rank]),
       const_cast<float *>(x->partialDepth[x->rank]), true, S.m);
   const size_t npx = (size_t)p->width * p->height;
+  if (npx >= 0xffffffffull) { // the background strip indexes its pixels with 32 bits
+    setError("dvr_render_slab_frame: frames of 2^32 pixels or more are not supported");
+    return DVR_ERR_INVALID_ARGUMENT;
+  }
   {
     const int rcf = fillPeerResolveLaunch(p, camera, instance, x->partialRgba, x->partialDepth, x->nRanks, objId, instId,
         b, 0, npx, S.c);

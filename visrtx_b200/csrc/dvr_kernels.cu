@@ -794,7 +794,9 @@ __device__ __forceinline__ void slabBackgroundChunk(const SlabFrameLaunch &S, ui
   for (int k = 0; k < 8; ++k) {
     const size_t i = base + (size_t)k * 32 + lane;
     const bool inRange = i < S.bgPixelEnd;
-    const uint32_t py = inRange ? (uint32_t)(i / P.width) : 0u, px = inRange ? (uint32_t)(i - (size_t)py * P.width) : 0u;
+    // (frames have fewer than 2^32 pixels: a 32-bit division instead of the emulated 64-bit one, 8 per chunk)
+    const uint32_t i32 = (uint32_t)i;
+    const uint32_t py = inRange ? i32 / P.width : 0u, px = inRange ? i32 - py * P.width : 0u;
     const bool mine = inRange && !((int)px >= wx0 && (int)px < wx1 && (int)py >= wy0 && (int)py < wy1);
     if (!uniform) {
       if (mine)
