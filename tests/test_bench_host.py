@@ -64,3 +64,17 @@ def test_bench_fails_loudly_without_a_gpu():
         assert r.returncode != 0
         line = json.loads(r.stdout.strip().splitlines()[-1])
         assert "no CUDA device" in line["error"]
+
+
+def test_secondary_measurements_of_the_multi_gpu_lines_default_to_auto_and_can_be_switched_off():
+    """N > 1 lines carry C3 sort-first, the ANARI one-process multi-GPU e2e and (at 8) C4 scaling as `extra.*`; each has
+    an auto / on / off switch, and each is wrapped so that it can never take the headline line down."""
+    a = _args()
+    assert (a.c3_sort_first, a.anari_multi_gpu, a.c4_scaling) == (-1, -1, -1)
+    b = _args("--c3-sort-first", "0", "--anari-multi-gpu", "0", "--c4-scaling", "0")
+    assert (b.c3_sort_first, b.anari_multi_gpu, b.c4_scaling) == (0, 0, 0)
+    import inspect
+    src = inspect.getsource(bench.run_ours)
+    assert 'out["extra"]["c3_sort_first"]' in src and 'out["extra"]["anari_multi_gpu"]' in src
+    assert "except Exception" in inspect.getsource(bench.measure_anari_multi_gpu)
+    assert 'backend="gloo"' in inspect.getsource(bench.measure_anari_multi_gpu)  # waiting ranks must not spin on their GPU
