@@ -1,13 +1,13 @@
 #!/bin/bash
-# round 2, GPU call AD (2 GPUs): the N = 2 bench line as the driver runs it, now with extra.anari_multi_gpu (rank 0 drives
+# round 2, GPU call AC (2 GPUs): the N = 2 bench line as the driver runs it, now with extra.anari_multi_gpu (rank 0 drives
 # both GPUs through the ANARI C API in one process) after extra.c3_sort_first
 mkdir -p gpurun_out
 TR="python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1"
-( time timeout 100 $TR --master-port 29881 bench.py --gpus 2 --steps 20 --warmup 5 ) > gpurun_out/r02ad_n2.json 2> gpurun_out/r02ad_n2.err
-tail -5 gpurun_out/r02ad_n2.err
+( time timeout 200 $TR --master-port 29881 bench.py --gpus 2 --steps 20 --warmup 5 ) > gpurun_out/r02ac_n2.json 2> gpurun_out/r02ac_n2.err
+tail -5 gpurun_out/r02ac_n2.err
 python - <<'PY'
 import json
-f = "gpurun_out/r02ad_n2.json"
+f = "gpurun_out/r02ac_n2.json"
 try:
     d = json.loads([l for l in open(f).read().strip().splitlines() if l.startswith("{")][-1])
     x = d["extra"]

@@ -1,5 +1,5 @@
 #!/bin/bash
-# round 2, GPU call AD (2 GPUs): the N = 2 bench line as the driver runs it, now with extra.anari_multi_gpu (rank 0 drives
+# round 2, GPU call AD (2 GPUs): as call AC, with the waiting rank parked in a host-side (gloo) barrier — rank 0 drives
 # both GPUs through the ANARI C API in one process) after extra.c3_sort_first
 mkdir -p gpurun_out
 TR="python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1"
