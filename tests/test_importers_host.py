@@ -333,6 +333,34 @@ def test_import_nvdb_rejects_offsets_that_leave_the_grid(tmp_path):
         I.import_nvdb(str(tmp_path / "neg.nvdb"))
 
 
+def test_import_nvdb_holds_the_declared_grid_size_against_what_the_file_can_deliver(tmp_path):
+    """The size of the grid allocation comes from the segment's FileMetaData.  A file that declares hundreds of
+    gigabytes is refused before anything is allocated: Codec::NONE cannot hold more than the bytes that are left, a
+    zlib stream cannot expand beyond 1032:1 (found by the mutation fuzzer, tools/fuzz_importers.cpp, under ASan)."""
+    import resource
+    fx = np.load(os.path.join(GOLD, "import_fixtures.npz"))
+    for name, codec in (("fog_float_none", 0), ("fog_float_zip", 1)):
+        blob = fx[f"file/{name}.nvdb"].copy()
+        assert int(blob[14:16].view(np.uint16)[0]) == codec
+        good = tmp_path / f"{name}.nvdb"
+        blob.tofile(good)
+        I.import_nvdb(str(good))
+        bad = blob.copy()
+        bad[16:24] = np.array([600 << 30], np.uint64).view(np.uint8)  # FileMetaData::gridSize of grid #0: 600 GiB
+        (tmp_path / f"huge_{name}.nvdb").write_bytes(bad.tobytes())
+        before = resource.getrusage(resource.RUSAGE_SELF).ru_maxrss
+        with pytest.raises(I.ImportError_) as e:
+            I.import_nvdb(str(tmp_path / f"huge_{name}.nvdb"))
+        assert e.value.code in (I.ERR_FORMAT, I.ERR_IO)
+        assert resource.getrusage(resource.RUSAGE_SELF).ru_maxrss - before < 256 * 1024  # KiB: nothing of that size was touched
+        # a size only slightly too large for the stream is still caught by the decoder itself
+        bad = blob.copy()
+        bad[16:24] = (blob[16:24].view(np.uint64) + np.uint64(4096)).view(np.uint8)
+        (tmp_path / f"off_{name}.nvdb").write_bytes(bad.tobytes())
+        with pytest.raises(I.ImportError_):
+            I.import_nvdb(str(tmp_path / f"off_{name}.nvdb"))
+
+
 def test_path_helpers_keep_the_importers_conventions(tmp_path):
     """fileOf/extensionOf/splitString drive the RAW name parser: dims come from '_'-separated tokens of the base name."""
     v = np.arange(2 * 3 * 4, dtype=np.uint8).reshape(2, 3, 4)

@@ -879,12 +879,27 @@ int importNvdb(const char *filepath, DvrVolumeFile *o)
       at += 176 + rd<uint32_t>(meta + 136); // + nameSize
     }
     gridSize = size0;
-    if (gridSize < 672 + 64 || gridSize > (1ull << 40))
+    if (gridSize < 672 + 64 || gridSize > (1ull << 40) || at > fileBytes)
       return fail(DVR_IMPORT_ERR_FORMAT, "[import_NVDB] failed: implausible grid size");
+    // The size of the allocation comes from the file: before trusting it, hold it against what the file can deliver —
+    // the bytes that are left (Codec::NONE) or what a zlib stream of the stored length can expand to (deflate's limit
+    // is 1032:1; Codec::ZIP).
+    uint64_t csz = 0;
+    is.seekg((std::streamoff)at);
+    if (codec == 0) {
+      if (gridSize > fileBytes - at)
+        return fail(DVR_IMPORT_ERR_IO, "[import_NVDB] failed: Failed to read Tree from file");
+    } else if (codec == 1) {
+      is.read((char *)&csz, 8);
+      if (!is || at + 8 > fileBytes || csz > fileBytes - at - 8)
+        return fail(DVR_IMPORT_ERR_FORMAT, "[import_NVDB] failed: truncated ZIP stream");
+      if (gridSize / 1032u > csz + 64u)
+        return fail(DVR_IMPORT_ERR_FORMAT, "[import_NVDB] failed: UNZIP failed on byte size");
+    } else
+      return fail(DVR_IMPORT_ERR_UNSUPPORTED, "[import_NVDB] failed: BLOSC compression codec was disabled during build");
     grid = (uint8_t *)std::malloc(gridSize);
     if (!grid)
       return fail(DVR_IMPORT_ERR_IO, "[import_NVDB] out of memory");
-    is.seekg((std::streamoff)at);
     if (codec == 0) { // Codec::NONE
       is.read((char *)grid, (std::streamsize)gridSize);
       if (!is) {
@@ -892,12 +907,6 @@ int importNvdb(const char *filepath, DvrVolumeFile *o)
         return fail(DVR_IMPORT_ERR_IO, "[import_NVDB] failed: Failed to read Tree from file");
       }
     } else if (codec == 1) { // Codec::ZIP: u64 compressed size + one zlib stream (IO.h:314-327)
-      uint64_t csz = 0;
-      is.read((char *)&csz, 8);
-      if (!is || csz > fileBytes) {
-        std::free(grid);
-        return fail(DVR_IMPORT_ERR_FORMAT, "[import_NVDB] failed: truncated ZIP stream");
-      }
       std::vector<uint8_t> tmp(csz);
       is.read((char *)tmp.data(), (std::streamsize)csz);
       uLongf n = (uLongf)gridSize;
